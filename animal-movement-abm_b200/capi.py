@@ -1,0 +1,237 @@
+"""ctypes binding of the C ABI in include/abm.h.
+
+The same binder is used for three libraries that export the ABI under different prefixes:
+  * ``libabm.so``       prefix ``abm_``    — the product (CUDA, sm_100a); the only one this package loads itself;
+  * ``liboracle.so``    prefix ``oracle_`` — the CPU restatement of the reference (tests / bench baseline only);
+  * ``libabm_emu.so``   prefix ``emu_``    — the engine sources compiled for the host (tests only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+ABM_OK = 0
+ABM_E_BADARG, ABM_E_CUDA, ABM_E_SMALL, ABM_E_STATE, ABM_E_NOWALKABLE = -1, -2, -3, -4, -5
+ABM_E_CAPACITY, ABM_E_NOMEM, ABM_E_INTERNAL = -6, -7, -8
+
+RANDOM_WALK, RANDOM_WALK_ATTRACTOR, RANDOM_WALK_GREGARIOUS, ALTERNATED_WALK, RANDOM_WALKMAP = range(5)
+ASTAR_DIRECT, ASTAR_MAX = 0, 1
+REDUCE_COUNT_AGENTS, REDUCE_COUNT_GROWN, REDUCE_SUM_ENERGY, REDUCE_MAX_ENERGY, REDUCE_MIN_ENERGY = range(5)
+
+
+class AbmConfig(C.Structure):
+    """struct abm_config (include/abm.h)."""
+
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("nx", C.c_int32),
+        ("ny", C.c_int32),
+        ("periodic", C.c_int32),
+        ("walk_type", C.c_int32),
+        ("eat", C.c_int32),
+        ("reproduce", C.c_int32),
+        ("walkmap_regrowth", C.c_int32),
+        ("regrowth_time", C.c_int32),
+        ("visual_distance", C.c_int32),
+        ("counter", C.c_int32),
+        ("randomwalk_ifempty", C.c_int32),
+        ("astar_metric", C.c_int32),
+        ("astar_penalty", C.c_int32),
+        ("device", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("prob_random_walk", C.c_double),
+        ("delta_energy", C.c_double),
+        ("movement_cost", C.c_double),
+        ("reproduction_prob", C.c_double),
+        ("attractor_x", C.c_double),
+        ("attractor_y", C.c_double),
+        ("seed", C.c_uint64),
+    ]
+
+
+class AbmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"abm error {code}: {msg}")
+        self.code = code
+
+
+_P = C.c_void_p
+_I64P = C.POINTER(C.c_int64)
+_U8P = C.POINTER(C.c_uint8)
+_F64P = C.POINTER(C.c_double)
+
+# name -> (restype, argtypes); mirrors include/abm.h one to one
+SIGNATURES = {
+    "config_default": (None, [C.POINTER(AbmConfig)]),
+    "create": (C.c_int, [C.POINTER(AbmConfig), C.POINTER(_P)]),
+    "destroy": (None, [_P]),
+    "set_grid": (C.c_int, [_P, _U8P, _I64P, _U8P, _I64P]),
+    "set_agents": (C.c_int, [_P, C.c_int64, _I64P, _I64P, _I64P, _F64P, C.c_int64]),
+    "set_global_state": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64]),
+    "get_global_state": (C.c_int, [_P, _I64P, _I64P, _I64P, _I64P]),
+    "set_weight_lut": (C.c_int, [_P, _F64P, C.c_int32]),
+    "step": (C.c_int, [_P, C.c_int64]),
+    "count_agents": (C.c_int, [_P, _I64P]),
+    "get_agents": (C.c_int, [_P, _I64P, _I64P, _I64P, _I64P, _F64P]),
+    "get_grid": (C.c_int, [_P, _U8P, _I64P]),
+    "reduce": (C.c_int, [_P, C.c_int32, _F64P]),
+    "plan_routes": (C.c_int, [_P, C.c_int64, _I64P, _I64P, _I64P]),
+    "get_paths": (C.c_int, [_P, C.c_int64, _I64P, _I64P, _I64P, _I64P, _I64P, _I64P]),
+    "get_timing": (C.c_int, [_P, _F64P, C.c_int32]),
+    "last_error": (C.c_char_p, [_P]),
+}
+
+
+def _ptr(a, ty):
+    return None if a is None else a.ctypes.data_as(ty)
+
+
+class CLib:
+    """A loaded shared library exporting the ABI under ``prefix``."""
+
+    def __init__(self, path: str, prefix: str):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.path, self.prefix = path, prefix
+        self.dll = C.CDLL(path)
+        self.fn = {}
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(self.dll, prefix + name)
+            f.restype, f.argtypes = res, args
+            self.fn[name] = f
+
+    def default_config(self, **kw) -> AbmConfig:
+        cfg = AbmConfig()
+        self.fn["config_default"](C.byref(cfg))
+        for k, v in kw.items():
+            if not hasattr(cfg, k):
+                raise AttributeError(f"abm_config has no field {k!r}")
+            setattr(cfg, k, v)
+        return cfg
+
+    def create(self, cfg: AbmConfig) -> "Engine":
+        return Engine(self, cfg)
+
+
+class Engine:
+    """One abm_handle.  Method names follow the ABI; array arguments are numpy arrays."""
+
+    def __init__(self, lib: CLib, cfg: AbmConfig):
+        self.lib, self.cfg = lib, cfg
+        self.h = _P()
+        rc = lib.fn["create"](C.byref(cfg), C.byref(self.h))
+        if rc != ABM_OK:
+            msg = lib.fn["last_error"](None)
+            self.h = None
+            raise AbmError(rc, (msg or b"").decode())
+        self.nx, self.ny = cfg.nx, cfg.ny
+
+    def _ck(self, rc: int):
+        if rc != ABM_OK:
+            raise AbmError(rc, (self.lib.fn["last_error"](self.h) or b"").decode())
+
+    def close(self):
+        if self.h is not None and self.h.value is not None:
+            self.lib.fn["destroy"](self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # grids are (ny, nx) C-ordered numpy arrays == Julia (nx, ny) column-major: a[y, x]
+    def set_grid(self, fully_grown, countdown, walkmap=None, elevation=None):
+        G = self.nx * self.ny
+        fg = np.ascontiguousarray(fully_grown, dtype=np.uint8).reshape(-1)
+        cd = np.ascontiguousarray(countdown, dtype=np.int64).reshape(-1)
+        wm = None if walkmap is None else np.ascontiguousarray(walkmap, dtype=np.uint8).reshape(-1)
+        el = None if elevation is None else np.ascontiguousarray(elevation, dtype=np.int64).reshape(-1)
+        for a in (fg, cd, wm, el):
+            if a is not None and a.size != G:
+                raise ValueError("grid array has the wrong size")
+        self._ck(self.lib.fn["set_grid"](self.h, _ptr(fg, _U8P), _ptr(cd, _I64P), _ptr(wm, _U8P), _ptr(el, _I64P)))
+
+    def set_agents(self, ids, x, y, energy, next_id=None):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        x = np.ascontiguousarray(x, dtype=np.int64)
+        y = np.ascontiguousarray(y, dtype=np.int64)
+        e = np.ascontiguousarray(energy, dtype=np.float64)
+        n = ids.size
+        if not (x.size == y.size == e.size == n):
+            raise ValueError("agent arrays differ in length")
+        if next_id is None:
+            next_id = int(ids.max()) + 1 if n else 1
+        self._ck(self.lib.fn["set_agents"](self.h, n, _ptr(ids, _I64P), _ptr(x, _I64P), _ptr(y, _I64P), _ptr(e, _F64P), int(next_id)))
+
+    def set_global_state(self, tick=0, behav=0, behav_counter=0):
+        self._ck(self.lib.fn["set_global_state"](self.h, int(tick), int(behav), int(behav_counter)))
+
+    def get_global_state(self):
+        v = [C.c_int64() for _ in range(4)]
+        self._ck(self.lib.fn["get_global_state"](self.h, *[C.byref(a) for a in v]))
+        return dict(tick=v[0].value, behav=v[1].value, behav_counter=v[2].value, next_id=v[3].value)
+
+    def set_weight_lut(self, w):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        self._ck(self.lib.fn["set_weight_lut"](self.h, _ptr(w, _F64P), w.size))
+
+    def step(self, n=1):
+        self._ck(self.lib.fn["step"](self.h, int(n)))
+
+    def count_agents(self) -> int:
+        n = C.c_int64()
+        self._ck(self.lib.fn["count_agents"](self.h, C.byref(n)))
+        return n.value
+
+    def get_agents(self):
+        n = self.count_agents()
+        cap = C.c_int64(n)
+        ids = np.empty(n, np.int64); x = np.empty(n, np.int64); y = np.empty(n, np.int64); e = np.empty(n, np.float64)
+        self._ck(self.lib.fn["get_agents"](self.h, C.byref(cap), _ptr(ids, _I64P), _ptr(x, _I64P), _ptr(y, _I64P), _ptr(e, _F64P)))
+        return ids, x, y, e
+
+    def get_grid(self):
+        fg = np.empty((self.ny, self.nx), np.uint8)
+        cd = np.empty((self.ny, self.nx), np.int64)
+        self._ck(self.lib.fn["get_grid"](self.h, _ptr(fg, _U8P), _ptr(cd, _I64P)))
+        return fg, cd
+
+    def reduce(self, what: int) -> float:
+        out = C.c_double()
+        self._ck(self.lib.fn["reduce"](self.h, int(what), C.byref(out)))
+        return out.value
+
+    def plan_routes(self, agent_ids, goal_x, goal_y):
+        a = np.ascontiguousarray(agent_ids, dtype=np.int64)
+        gx = np.ascontiguousarray(goal_x, dtype=np.int64)
+        gy = np.ascontiguousarray(goal_y, dtype=np.int64)
+        self._ck(self.lib.fn["plan_routes"](self.h, a.size, _ptr(a, _I64P), _ptr(gx, _I64P), _ptr(gy, _I64P)))
+
+    def get_paths(self, agent_ids):
+        a = np.ascontiguousarray(agent_ids, dtype=np.int64)
+        b = a.size
+        off = np.zeros(b + 1, np.int64)
+        cost = np.zeros(b, np.int64)
+        cap = C.c_int64(0)
+        px = np.empty(0, np.int64); py = np.empty(0, np.int64)
+        rc = self.lib.fn["get_paths"](self.h, b, _ptr(a, _I64P), _ptr(off, _I64P), C.byref(cap), _ptr(px, _I64P), _ptr(py, _I64P), _ptr(cost, _I64P))
+        if rc == ABM_E_SMALL:
+            px = np.empty(cap.value, np.int64); py = np.empty(cap.value, np.int64)
+            rc = self.lib.fn["get_paths"](self.h, b, _ptr(a, _I64P), _ptr(off, _I64P), C.byref(cap), _ptr(px, _I64P), _ptr(py, _I64P), _ptr(cost, _I64P))
+        self._ck(rc)
+        return off, px[: cap.value], py[: cap.value], cost
+
+    def timing(self):
+        out = np.zeros(8, np.float64)
+        self._ck(self.lib.fn["get_timing"](self.h, _ptr(out, _F64P), out.size))
+        return dict(ms_total=out[0], ms_agents=out[1], ms_grass=out[2], rounds=out[3], launches=out[4], astar_expansions=out[5])
+
+    def snapshot(self):
+        """Full observable state, for parity comparisons."""
+        ids, x, y, e = self.get_agents()
+        fg, cd = self.get_grid()
+        return dict(ids=ids, x=x, y=y, energy=e, fully_grown=fg, countdown=cd, **self.get_global_state())

@@ -1,0 +1,839 @@
+/*
+ * abm_engine.cu — host side of libabm.so: owns device memory, orders the kernels of one tick, implements the
+ * C ABI of include/abm.h.  Compiled by nvcc for sm_100a (the product).  tests/emu compiles the same file with
+ * g++ -DABM_EMU to exercise this orchestration on a box without a GPU (see abm_platform.h); that build is
+ * never shipped nor loaded by the package.
+ */
+#include <math.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "abm_kernels.h"
+
+#ifdef ABM_EMU
+#define ABM_API(name) emu_##name
+namespace abm {
+uint64_t g_emu_launches = 0;
+uint64_t g_emu_shuffle_seed = 12345;
+}
+extern "C" void emu_set_shuffle_seed(uint64_t s) { abm::g_emu_shuffle_seed = s; }
+#else
+#define ABM_API(name) abm_##name
+namespace abm {
+unsigned long long g_launches = 0;
+}
+#endif
+
+using namespace abm;
+
+namespace {
+
+static std::string g_create_error;
+
+/* ------------------------------------------------------------------------------------------ device scan */
+#ifdef ABM_EMU
+static abm_err_t scan_exclusive_u32(abm_stream_t, uint32_t* data, uint64_t n, uint32_t*) {
+  uint32_t run = 0;
+  for (uint64_t i = 0; i < n; ++i) { const uint32_t v = data[i]; data[i] = run; run += v; }
+  ++g_emu_launches;
+  return 0;
+}
+static uint64_t scan_tmp_words(uint64_t) { return 1; }
+#else
+enum { SCAN_THREADS = 256, SCAN_ITEMS = 16, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS };
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total_out) {
+  __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    if (lane < SCAN_THREADS / 32) warp_sums[lane] = w; /* inclusive over warps */
+  }
+  __syncthreads();
+  const uint32_t before = wid ? warp_sums[wid - 1] : 0;
+  *total_out = warp_sums[SCAN_THREADS / 32 - 1];
+  return before + inc - v;
+}
+
+/* pass 1: one partial sum per 4096-element tile */
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, uint64_t n, uint32_t* __restrict__ sums) {
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE;
+  uint32_t s = 0;
+  if (base + SCAN_TILE <= n) {
+    const uint4* p = reinterpret_cast<const uint4*>(in + base);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS / 4; ++i) { const uint4 q = p[i * SCAN_THREADS + threadIdx.x]; s += q.x + q.y + q.z + q.w; }
+  } else {
+    for (uint64_t i = base + threadIdx.x; i < n; i += SCAN_THREADS) s += in[i];
+  }
+  uint32_t total;
+  (void)block_exclusive_scan(s, &total);
+  if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+/* pass 2: exclusive scan inside each tile plus the tile's offset */
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t* __restrict__ data, uint64_t n, const uint32_t* __restrict__ offsets) {
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  if (base + SCAN_ITEMS <= n) {
+    const uint4* p = reinterpret_cast<const uint4*>(data + base);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS / 4; ++i) { const uint4 q = p[i]; v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = base + i < n ? data[base + i] : 0u;
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) s += v[i];
+  uint32_t total;
+  uint32_t run = block_exclusive_scan(s, &total) + (offsets ? offsets[blockIdx.x] : 0u);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) { const uint32_t t = v[i]; v[i] = run; run += t; }
+  if (base + SCAN_ITEMS <= n) {
+    uint4* p = reinterpret_cast<uint4*>(data + base);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS / 4; ++i) p[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) if (base + i < n) data[base + i] = v[i];
+  }
+}
+
+static uint64_t scan_tmp_words(uint64_t n) {
+  uint64_t w = 0;
+  while (n > SCAN_TILE) { n = (n + SCAN_TILE - 1) / SCAN_TILE; w += (n + 3) & ~3ull; }
+  return w + 4;
+}
+
+/* in-place exclusive prefix sum; data must be 16-byte aligned */
+static abm_err_t scan_exclusive_u32(abm_stream_t s, uint32_t* data, uint64_t n, uint32_t* tmp) {
+  if (n == 0) return cudaSuccess;
+  const uint64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (nb == 1) {
+    ++g_launches;
+    k_scan_apply<<<1, SCAN_THREADS, 0, s>>>(data, n, nullptr);
+    return cudaGetLastError();
+  }
+  g_launches += 2;
+  k_scan_reduce<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(data, n, tmp);
+  abm_err_t e = scan_exclusive_u32(s, tmp, nb, tmp + ((nb + 3) & ~3ull));
+  if (e != cudaSuccess) return e;
+  k_scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, s>>>(data, n, tmp);
+  return cudaGetLastError();
+}
+#endif
+
+/* ------------------------------------------------------------------------------------------- buffers */
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { dev_free(p); }
+};
+
+struct Timer {
+#ifndef ABM_EMU
+  cudaEvent_t a = nullptr, b = nullptr;
+  void init() { cudaEventCreate(&a); cudaEventCreate(&b); }
+  void destroy() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  void start(abm_stream_t s) { cudaEventRecord(a, s); }
+  void stop(abm_stream_t s) { cudaEventRecord(b, s); }
+  double ms() { float f = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&f, a, b); return f; }
+#else
+  void init() {}
+  void destroy() {}
+  void start(abm_stream_t) {}
+  void stop(abm_stream_t) {}
+  double ms() { return 0; }
+#endif
+};
+
+enum { CTR_PEND_A = 0, CTR_PEND_B = 1, CTR_BIRTHS = 2, CTR_ERR = 3, CTR_RED_LO = 4, CTR_RED_HI = 5, CTR_WORDS = 8 };
+
+}  // namespace
+
+struct abm_handle {
+  abm_config cfg;
+  Geo g;
+  Params params;
+  abm_stream_t stream = 0;
+  int device = 0;
+
+  DevBuf cell[2], id[2], energy[2]; /* ping-pong cell-sorted SoA */
+  DevBuf cell_start[2];             /* gt + 1 (+ padding) */
+  int cur = 0;
+  DevBuf state, slot, new_cell, pend[2], births;
+  DevBuf grass, walkbits, elev;
+  DevBuf bits, bits_prefix, scan_tmp, stage, lut, greg_order, counters, partials;
+  uint32_t* h_counters = nullptr; /* host mirror (pinned on CUDA) */
+
+  uint64_t n = 0, next_id = 1, tick = 0;
+  int64_t behav = 0, behav_counter = 0;
+  bool grid_set = false, agents_set = false;
+  double t_total = 0, t_agents = 0, t_grass = 0, rounds = 0, launches = 0, expansions = 0;
+  Timer tm_total;
+  std::string err;
+};
+
+namespace {
+
+#define ABM_FAIL(h, code, ...) do { char b_[512]; snprintf(b_, sizeof b_, __VA_ARGS__); (h)->err = b_; return (code); } while (0)
+#define ABM_CK(h, call) do { abm_err_t e_ = (call); if (e_ != 0) { ABM_FAIL(h, ABM_E_CUDA, "%s failed: %s", #call, err_string(e_)); } } while (0)
+
+static int ensure(abm_handle* h, DevBuf& b, size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (b.bytes >= bytes && b.p) return 0;
+  dev_free(b.p);
+  b.p = nullptr; b.bytes = 0;
+  size_t want = bytes + bytes / 4; /* head room so that a growing population does not reallocate every tick */
+  if (dev_malloc(&b.p, want) != 0) {
+    b.p = nullptr;
+    want = bytes;
+    if (dev_malloc(&b.p, want) != 0) { b.p = nullptr; ABM_FAIL(h, ABM_E_NOMEM, "device allocation of %zu bytes failed", bytes); }
+  }
+  b.bytes = want;
+  return 0;
+}
+
+static int set_device(abm_handle* h) {
+#ifndef ABM_EMU
+  ABM_CK(h, cudaSetDevice(h->device));
+#else
+  (void)h;
+#endif
+  return 0;
+}
+
+static uint64_t launches_now() {
+#ifdef ABM_EMU
+  return g_emu_launches;
+#else
+  return g_launches;
+#endif
+}
+
+static int check_launch(abm_handle* h, const char* what) {
+#ifndef ABM_EMU
+  abm_err_t e = cudaGetLastError();
+  if (e != cudaSuccess) ABM_FAIL(h, ABM_E_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+#else
+  (void)h; (void)what;
+#endif
+  return 0;
+}
+
+static View make_view(abm_handle* h) {
+  View v;
+  memset(&v, 0, sizeof v);
+  v.g = h->g;
+  v.p = h->params;
+  v.p.tick = h->tick;
+  v.n = (uint32_t)h->n;
+  v.cell = (uint32_t*)h->cell[h->cur].p;
+  v.id = (uint32_t*)h->id[h->cur].p;
+  v.energy = (double*)h->energy[h->cur].p;
+  v.state = (uint8_t*)h->state.p;
+  v.slot = (uint32_t*)h->slot.p;
+  v.cell_start = (const uint32_t*)h->cell_start[h->cur].p;
+  v.grass = (uint8_t*)h->grass.p;
+  v.walkbits = (const uint32_t*)h->walkbits.p;
+  v.lut = (const double*)h->lut.p;
+  v.greg_order = (const uint8_t*)h->greg_order.p;
+  v.err = (uint32_t*)h->counters.p + CTR_ERR;
+  return v;
+}
+
+static int read_counters(abm_handle* h) {
+  ABM_CK(h, copy_d2h(h->h_counters, h->counters.p, CTR_WORDS * sizeof(uint32_t), h->stream));
+  return 0;
+}
+
+static int device_error_to_code(abm_handle* h) {
+  const uint32_t e = h->h_counters[CTR_ERR];
+  if (e & ERR_NOWALKABLE) ABM_FAIL(h, ABM_E_NOWALKABLE, "random_walkmap: an agent has no walkable neighbour (the reference throws on rand(1:0))");
+  if (e & ERR_INTERNAL) ABM_FAIL(h, ABM_E_BADARG, "device-side validation failed (out-of-range coordinate, id, countdown or elevation, or duplicate id)");
+  return 0;
+}
+
+static uint64_t bitmap_words(uint64_t next_id) { return (next_id >> 5) + 1; }
+
+/* exclusive popcount prefix of h->bits over `words` words into h->bits_prefix */
+static int rank_prefix(abm_handle* h, uint64_t words) {
+  int rc;
+  if ((rc = ensure(h, h->bits_prefix, (words + 4) * 4))) return rc;
+  if ((rc = ensure(h, h->scan_tmp, scan_tmp_words(std::max<uint64_t>(words, (uint64_t)h->g.gt + 1)) * 4))) return rc;
+  PopcountBody pb;
+  pb.bits = (const uint32_t*)h->bits.p;
+  pb.out = (uint32_t*)h->bits_prefix.p;
+  launch_foreach(h->stream, pb, words);
+  ABM_CK(h, scan_exclusive_u32(h->stream, (uint32_t*)h->bits_prefix.p, words, (uint32_t*)h->scan_tmp.p));
+  return 0;
+}
+
+static int ensure_agent_scratch(abm_handle* h, uint64_t n) {
+  int rc;
+  const uint64_t m = std::max<uint64_t>(n, 1);
+  if ((rc = ensure(h, h->state, m))) return rc;
+  if ((rc = ensure(h, h->slot, m * 4))) return rc;
+  if ((rc = ensure(h, h->new_cell, m * 4))) return rc;
+  if ((rc = ensure(h, h->pend[0], m * 4))) return rc;
+  if ((rc = ensure(h, h->pend[1], m * 4))) return rc;
+  if ((rc = ensure(h, h->births, m * sizeof(BirthRec)))) return rc;
+  return 0;
+}
+
+static int ensure_soa(abm_handle* h, int which, uint64_t n) {
+  int rc;
+  const uint64_t m = std::max<uint64_t>(n, 1);
+  if ((rc = ensure(h, h->cell[which], m * 4))) return rc;
+  if ((rc = ensure(h, h->id[which], m * 4))) return rc;
+  if ((rc = ensure(h, h->energy[which], m * 8))) return rc;
+  return 0;
+}
+
+/* one tick: every agent's custom_agent_step! in id order, then custom_model_step! */
+static int tick_once(abm_handle* h) {
+  int rc;
+  const uint64_t n = h->n;
+  const uint64_t gt = h->g.gt;
+  if ((rc = ensure_agent_scratch(h, n))) return rc;
+  uint32_t* ctr = (uint32_t*)h->counters.p;
+  ABM_CK(h, dev_memset(ctr, 0, 3 * sizeof(uint32_t), h->stream)); /* keeps the sticky error word */
+  View v = make_view(h);
+
+  if (n > 0) {
+    ProposeBody pb;
+    pb.v = v;
+    pb.pending = (uint32_t*)h->pend[0].p;
+    pb.pending_count = ctr + CTR_PEND_A;
+    launch_foreach(h->stream, pb, n);
+    if ((rc = check_launch(h, "propose"))) return rc;
+  }
+  /* rank-ordered fixed point over the agents whose outcome depends on lower ids */
+  const bool may_pend = h->cfg.walk_type != ABM_RANDOM_WALKMAP && n > 0;
+  if (may_pend) {
+    if ((rc = read_counters(h))) return rc;
+    uint64_t cnt = h->h_counters[CTR_PEND_A];
+    int in = 0;
+    int stalls = 0;
+    while (cnt > 0) {
+      ABM_CK(h, dev_memset(ctr + (in ? CTR_PEND_A : CTR_PEND_B), 0, sizeof(uint32_t), h->stream));
+      ResolveBody rb;
+      rb.v = v;
+      rb.in = (const uint32_t*)h->pend[in].p;
+      rb.in_count = ctr + (in ? CTR_PEND_B : CTR_PEND_A);
+      rb.out = (uint32_t*)h->pend[in ^ 1].p;
+      rb.out_count = ctr + (in ? CTR_PEND_A : CTR_PEND_B);
+      launch_foreach(h->stream, rb, cnt);
+      if ((rc = check_launch(h, "resolve"))) return rc;
+      if ((rc = read_counters(h))) return rc;
+      const uint64_t left = h->h_counters[in ? CTR_PEND_A : CTR_PEND_B];
+      h->rounds += 1;
+      /* the lowest pending id is always decidable, so a round without progress can only be a stale read */
+      stalls = left == cnt ? stalls + 1 : 0;
+      if (stalls > 8) ABM_FAIL(h, ABM_E_INTERNAL, "conflict resolution made no progress with %llu agents pending", (unsigned long long)left);
+      cnt = left;
+      in ^= 1;
+    }
+  }
+
+  /* commit: eat / energy / reproduce and the counting sort into next tick's order */
+  const int nxt = h->cur ^ 1;
+  uint32_t* new_start = (uint32_t*)h->cell_start[nxt].p;
+  ABM_CK(h, dev_memset(new_start, 0, (gt + 1) * 4, h->stream));
+  const uint64_t words = bitmap_words(h->next_id);
+  const bool repro = h->cfg.reproduce != 0;
+  if (repro) {
+    if ((rc = ensure(h, h->bits, (words + 4) * 4))) return rc;
+    ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, h->stream));
+  }
+  if (n > 0) {
+    CommitBody cb;
+    cb.v = v;
+    cb.new_count = new_start;
+    cb.birth_bits = (uint32_t*)h->bits.p;
+    cb.births = (BirthRec*)h->births.p;
+    cb.birth_count = ctr + CTR_BIRTHS;
+    cb.new_cell = (uint32_t*)h->new_cell.p;
+    launch_foreach(h->stream, cb, n);
+    if ((rc = check_launch(h, "commit"))) return rc;
+  }
+  if ((rc = ensure(h, h->scan_tmp, scan_tmp_words(gt + 1) * 4))) return rc;
+  ABM_CK(h, scan_exclusive_u32(h->stream, new_start, gt + 1, (uint32_t*)h->scan_tmp.p));
+  if ((rc = read_counters(h))) return rc;
+  if ((rc = device_error_to_code(h))) return rc;
+  uint32_t n_new32 = 0;
+  ABM_CK(h, copy_d2h(&n_new32, new_start + gt, 4, h->stream));
+  const uint64_t n_new = n_new32;
+  const uint64_t nb = h->h_counters[CTR_BIRTHS];
+  if (h->next_id + nb > 0xFFFFFFFFull) ABM_FAIL(h, ABM_E_CAPACITY, "agent id space (2^32-1) exhausted");
+  if ((rc = ensure_soa(h, nxt, n_new))) return rc;
+  if (n > 0) {
+    ScatterBody sb;
+    sb.v = v;
+    sb.new_cell = (const uint32_t*)h->new_cell.p;
+    sb.new_start = new_start;
+    sb.out_cell = (uint32_t*)h->cell[nxt].p;
+    sb.out_id = (uint32_t*)h->id[nxt].p;
+    sb.out_energy = (double*)h->energy[nxt].p;
+    launch_foreach(h->stream, sb, n);
+    if ((rc = check_launch(h, "scatter"))) return rc;
+    if (nb > 0) {
+      if ((rc = rank_prefix(h, words))) return rc;
+      BirthScatterBody bb;
+      bb.v = v;
+      bb.births = (const BirthRec*)h->births.p;
+      bb.birth_bits = (const uint32_t*)h->bits.p;
+      bb.birth_prefix = (const uint32_t*)h->bits_prefix.p;
+      bb.new_cell = sb.new_cell;
+      bb.new_start = new_start;
+      bb.next_id = (uint32_t)h->next_id;
+      bb.out_cell = sb.out_cell;
+      bb.out_id = sb.out_id;
+      bb.out_energy = sb.out_energy;
+      launch_foreach(h->stream, bb, nb);
+      if ((rc = check_launch(h, "birth scatter"))) return rc;
+    }
+  }
+  /* custom_model_step!: grass regrowth */
+  {
+    RegrowBody gb;
+    gb.grass4 = (uint32_t*)h->grass.p;
+    gb.walkbits = (const uint32_t*)h->walkbits.p;
+    gb.rt = (uint32_t)h->cfg.regrowth_time;
+    gb.use_walk = h->cfg.walkmap_regrowth;
+    launch_foreach(h->stream, gb, gt / 16);
+    if ((rc = check_launch(h, "regrow"))) return rc;
+  }
+  h->cur = nxt;
+  h->n = n_new;
+  h->next_id += nb;
+  h->tick += 1;
+  return 0;
+}
+
+static int validate_config(const abm_config* c, std::string& why) {
+  char b[256];
+#define BAD(...) do { snprintf(b, sizeof b, __VA_ARGS__); why = b; return ABM_E_BADARG; } while (0)
+  if (c->struct_size != (int32_t)sizeof(abm_config)) BAD("abm_config.struct_size %d != %zu", c->struct_size, sizeof(abm_config));
+  if (c->nx < 1 || c->ny < 1) BAD("grid dims must be positive");
+  const uint64_t tx = ((uint64_t)c->nx + 31) / 32, ty = ((uint64_t)c->ny + 31) / 32;
+  if (tx * ty * 1024 >= 0xFFFFFFF0ull) BAD("grid too large for 32-bit cell indices");
+  if (c->walk_type < 0 || c->walk_type > ABM_RANDOM_WALKMAP) BAD("walk_type %d out of range", c->walk_type);
+  if (c->regrowth_time < 0 || c->regrowth_time > 126) BAD("regrowth_time must be in 0..126");
+  if (c->walk_type == ABM_RANDOM_WALK_GREGARIOUS) {
+    if (!c->periodic) BAD("RANDOM_WALK_GREGARIOUS needs periodic=true (the reference indexes 8 neighbours, src/agent_actions.jl:334)");
+    if (c->visual_distance < 1 || c->visual_distance > GREG_MAX_R) BAD("visual_distance must be in 1..%d", (int)GREG_MAX_R);
+    if (c->nx < 2 * c->visual_distance + 3 || c->ny < 2 * c->visual_distance + 3) BAD("gregarious walk needs dims >= 2*visual_distance+3");
+  }
+  if (c->walk_type == ABM_RANDOM_WALK_ATTRACTOR) {
+    const double ax = 2 * c->attractor_x, ay = 2 * c->attractor_y;
+    if (ax != floor(ax) || ay != floor(ay) || fabs(ax) > 1e9 || fabs(ay) > 1e9) BAD("2*attractor must be integral (griddims ./ 2)");
+  }
+  if (c->walk_type == ABM_ALTERNATED_WALK && c->counter < 1) BAD("counter must be >= 1");
+  if (!(c->prob_random_walk >= 0 && c->prob_random_walk <= 1)) BAD("prob_random_walk must be in [0,1]");
+  if (c->astar_metric != ABM_ASTAR_DIRECT && c->astar_metric != ABM_ASTAR_MAX) BAD("astar_metric out of range");
+#undef BAD
+  return 0;
+}
+
+}  // namespace
+
+/* ================================================================================================ C ABI */
+extern "C" {
+
+void ABM_API(config_default)(abm_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->struct_size = (int32_t)sizeof(abm_config);
+  c->nx = 80; c->ny = 80; c->periodic = 0; c->walk_type = ABM_RANDOM_WALK; c->eat = 1; c->reproduce = 1;
+  c->walkmap_regrowth = 0; c->regrowth_time = 30; c->visual_distance = 5; c->counter = 50;
+  c->randomwalk_ifempty = 1; c->astar_metric = ABM_ASTAR_DIRECT; c->astar_penalty = 0; c->device = 0;
+  c->prob_random_walk = 0.9; c->delta_energy = 4; c->movement_cost = 1; c->reproduction_prob = 0.001;
+  c->attractor_x = 40; c->attractor_y = 40; c->seed = 321;
+}
+
+const char* ABM_API(last_error)(abm_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void ABM_API(destroy)(abm_handle* h) {
+  if (!h) return;
+#ifndef ABM_EMU
+  cudaSetDevice(h->device);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  if (h->h_counters) cudaFreeHost(h->h_counters);
+#else
+  free(h->h_counters);
+#endif
+  h->tm_total.destroy();
+  delete h;
+}
+
+int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return ABM_E_BADARG; }
+  *out = nullptr;
+  int rc = validate_config(cfg, g_create_error);
+  if (rc) return rc;
+  abm_handle* h = new (std::nothrow) abm_handle();
+  if (!h) { g_create_error = "out of host memory"; return ABM_E_NOMEM; }
+  h->cfg = *cfg;
+  h->device = cfg->device;
+#ifndef ABM_EMU
+  {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= cfg->device || cfg->device < 0) {
+      g_create_error = std::string("no usable CUDA device (libabm has no CPU fallback): ") + cudaGetErrorString(e);
+      delete h; return ABM_E_CUDA;
+    }
+    cudaDeviceProp prop;
+    e = cudaSetDevice(cfg->device);
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess || prop.major < 10) {
+      g_create_error = "libabm kernels are built for sm_100a only; device is not a Blackwell-class GPU";
+      delete h; return ABM_E_CUDA;
+    }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_counters, CTR_WORDS * sizeof(uint32_t)) != cudaSuccess) {
+      g_create_error = "stream / pinned memory creation failed";
+      delete h; return ABM_E_CUDA;
+    }
+  }
+#else
+  h->h_counters = (uint32_t*)calloc(CTR_WORDS, sizeof(uint32_t));
+#endif
+  h->tm_total.init();
+  Geo& g = h->g;
+  g.nx = cfg->nx; g.ny = cfg->ny;
+  g.tiles_x = (cfg->nx + 31) / 32; g.tiles_y = (cfg->ny + 31) / 32;
+  g.gt = (uint32_t)((uint64_t)g.tiles_x * g.tiles_y * 1024);
+  g.periodic = cfg->periodic ? 1 : 0;
+  Params& p = h->params;
+  memset(&p, 0, sizeof p);
+  p.walk_type = cfg->walk_type; p.eat = cfg->eat; p.reproduce = cfg->reproduce; p.ifempty = cfg->randomwalk_ifempty;
+  p.walkmap_regrowth = cfg->walkmap_regrowth; p.regrowth_time = cfg->regrowth_time; p.r = cfg->visual_distance; p.counter = cfg->counter;
+  p.prob_random_walk = cfg->prob_random_walk; p.delta_energy = cfg->delta_energy; p.movement_cost = cfg->movement_cost;
+  p.reproduction_prob = cfg->reproduction_prob;
+  p.ax2 = (int64_t)llround(2 * cfg->attractor_x); p.ay2 = (int64_t)llround(2 * cfg->attractor_y);
+  p.seed = cfg->seed;
+
+  rc = 0;
+  do {
+    if ((rc = ensure(h, h->counters, CTR_WORDS * 4))) break;
+    if ((rc = ensure(h, h->grass, g.gt))) break;
+    if ((rc = ensure(h, h->walkbits, (size_t)g.gt / 8 + 16))) break;
+    if ((rc = ensure(h, h->cell_start[0], ((size_t)g.gt + 8) * 4))) break;
+    if ((rc = ensure(h, h->cell_start[1], ((size_t)g.gt + 8) * 4))) break;
+    if ((rc = ensure(h, h->scan_tmp, scan_tmp_words((uint64_t)g.gt + 1) * 4))) break;
+    if ((rc = ensure_soa(h, 0, 1))) break;
+    if ((rc = ensure_soa(h, 1, 1))) break;
+    /* default tables: exp(-sqrt(k)/3) from the C library; closest-neighbour visiting order */
+    const int r = cfg->walk_type == ABM_RANDOM_WALK_GREGARIOUS ? cfg->visual_distance : 1;
+    const int nl = 2 * (r + 1) * (r + 1) + 1;
+    std::vector<double> lut(nl);
+    for (int k = 0; k < nl; ++k) lut[k] = exp(-sqrt((double)k) / 3.0);
+    if ((rc = ensure(h, h->lut, nl * 8))) break;
+    if (copy_h2d(h->lut.p, lut.data(), nl * 8, h->stream) != 0) { rc = ABM_E_CUDA; break; }
+    const int side = 2 * r + 1;
+    std::vector<std::pair<int, int>> order;
+    for (int by = -r; by <= r; ++by) for (int bx = -r; bx <= r; ++bx) order.push_back(std::make_pair(bx * bx + by * by, (by + r) * side + (bx + r)));
+    std::sort(order.begin(), order.end());
+    std::vector<uint8_t> ord(order.size());
+    for (size_t i = 0; i < order.size(); ++i) ord[i] = (uint8_t)order[i].second;
+    if ((rc = ensure(h, h->greg_order, ord.size()))) break;
+    if (copy_h2d(h->greg_order.p, ord.data(), ord.size(), h->stream) != 0) { rc = ABM_E_CUDA; break; }
+  } while (0);
+  if (rc) { g_create_error = h->err.empty() ? "device allocation failed" : h->err; ABM_API(destroy)(h); return rc; }
+  *out = h;
+  return ABM_OK;
+}
+
+int ABM_API(set_weight_lut)(abm_handle* h, const double* w, int32_t n) {
+  if (!h || !w) return ABM_E_BADARG;
+  int rc = set_device(h);
+  if (rc) return rc;
+  const int r = h->cfg.walk_type == ABM_RANDOM_WALK_GREGARIOUS ? h->cfg.visual_distance : 1;
+  const int nl = 2 * (r + 1) * (r + 1) + 1;
+  if (n < nl) ABM_FAIL(h, ABM_E_BADARG, "weight table needs %d entries (k = 0..2(r+1)^2), got %d", nl, n);
+  ABM_CK(h, copy_h2d(h->lut.p, w, (size_t)nl * 8, h->stream));
+  return ABM_OK;
+}
+
+int ABM_API(set_grid)(abm_handle* h, const uint8_t* fg, const int64_t* cd, const uint8_t* wm, const int64_t* el) {
+  if (!h) return ABM_E_BADARG;
+  if (!fg || !cd) ABM_FAIL(h, ABM_E_BADARG, "fully_grown and countdown are required");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const Geo& g = h->g;
+  ABM_CK(h, dev_memset(h->grass.p, GRASS_PAD, g.gt, h->stream));
+  ABM_CK(h, dev_memset(h->walkbits.p, 0, (size_t)g.gt / 8, h->stream));
+  if ((rc = ensure(h, h->elev, (size_t)g.gt * 2))) return rc;
+  ABM_CK(h, dev_memset(h->elev.p, 0, (size_t)g.gt * 2, h->stream));
+  ABM_CK(h, dev_memset((uint32_t*)h->counters.p + CTR_ERR, 0, 4, h->stream));
+  const uint64_t rows_per = std::max<uint64_t>(1, (16ull << 20) / (uint64_t)g.nx);
+  for (uint64_t row0 = 0; row0 < (uint64_t)g.ny; row0 += rows_per) {
+    const uint64_t rows = std::min<uint64_t>(rows_per, (uint64_t)g.ny - row0);
+    const uint64_t cells = rows * (uint64_t)g.nx, off = row0 * (uint64_t)g.nx;
+    const size_t need = cells * 18 + 64;
+    if ((rc = ensure(h, h->stage, need))) return rc;
+    uint8_t* s = (uint8_t*)h->stage.p;
+    int64_t* s_cd = (int64_t*)s;
+    int64_t* s_el = (int64_t*)(s + cells * 8);
+    uint8_t* s_fg = s + cells * 16;
+    uint8_t* s_wm = s + cells * 17;
+    ABM_CK(h, copy_h2d(s_cd, cd + off, cells * 8, h->stream));
+    ABM_CK(h, copy_h2d(s_fg, fg + off, cells, h->stream));
+    if (wm) ABM_CK(h, copy_h2d(s_wm, wm + off, cells, h->stream));
+    if (el) ABM_CK(h, copy_h2d(s_el, el + off, cells * 8, h->stream));
+    GridImportBody ib;
+    ib.g = g; ib.fg = s_fg; ib.cd = s_cd; ib.wm = wm ? s_wm : nullptr; ib.el = el ? s_el : nullptr;
+    ib.row0 = row0; ib.rows = rows;
+    ib.grass = (uint8_t*)h->grass.p; ib.walkbits = (uint32_t*)h->walkbits.p; ib.elev = (int16_t*)h->elev.p;
+    ib.err = (uint32_t*)h->counters.p + CTR_ERR;
+    launch_foreach(h->stream, ib, cells);
+    if ((rc = check_launch(h, "grid import"))) return rc;
+    ABM_CK(h, stream_sync(h->stream));
+  }
+  if ((rc = read_counters(h))) return rc;
+  if (h->h_counters[CTR_ERR]) {
+    ABM_CK(h, dev_memset((uint32_t*)h->counters.p + CTR_ERR, 0, 4, h->stream));
+    ABM_FAIL(h, ABM_E_BADARG, "countdown must be in 0..126 and elevation in -32768..32767");
+  }
+  h->grid_set = true;
+  return ABM_OK;
+}
+
+int ABM_API(get_grid)(abm_handle* h, uint8_t* fg, int64_t* cd) {
+  if (!h) return ABM_E_BADARG;
+  if (!h->grid_set) ABM_FAIL(h, ABM_E_STATE, "abm_set_grid has not been called");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const Geo& g = h->g;
+  const uint64_t rows_per = std::max<uint64_t>(1, (16ull << 20) / (uint64_t)g.nx);
+  for (uint64_t row0 = 0; row0 < (uint64_t)g.ny; row0 += rows_per) {
+    const uint64_t rows = std::min<uint64_t>(rows_per, (uint64_t)g.ny - row0);
+    const uint64_t cells = rows * (uint64_t)g.nx, off = row0 * (uint64_t)g.nx;
+    if ((rc = ensure(h, h->stage, cells * 9 + 64))) return rc;
+    uint8_t* s = (uint8_t*)h->stage.p;
+    GridExportBody eb;
+    eb.g = g; eb.grass = (const uint8_t*)h->grass.p; eb.row0 = row0;
+    eb.cd = cd ? (int64_t*)s : nullptr; eb.fg = fg ? s + cells * 8 : nullptr;
+    launch_foreach(h->stream, eb, cells);
+    if ((rc = check_launch(h, "grid export"))) return rc;
+    if (cd) ABM_CK(h, copy_d2h(cd + off, s, cells * 8, h->stream));
+    if (fg) ABM_CK(h, copy_d2h(fg + off, s + cells * 8, cells, h->stream));
+    ABM_CK(h, stream_sync(h->stream));
+  }
+  return ABM_OK;
+}
+
+int ABM_API(set_agents)(abm_handle* h, int64_t n, const int64_t* id, const int64_t* x, const int64_t* y,
+                        const double* energy, int64_t next_id) {
+  if (!h) return ABM_E_BADARG;
+  if (n < 0 || (n > 0 && (!id || !x || !y || !energy))) ABM_FAIL(h, ABM_E_BADARG, "null agent arrays");
+  if (next_id < 1 || next_id > 0xFFFFFFFFll || n >= 0xFFFFFFF0ll) ABM_FAIL(h, ABM_E_CAPACITY, "next_id must be in 1..2^32-1");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const Geo& g = h->g;
+  const int tmp = h->cur ^ 1, dst = h->cur;
+  if ((rc = ensure_soa(h, tmp, n))) return rc;
+  if ((rc = ensure_soa(h, dst, n))) return rc;
+  if ((rc = ensure_agent_scratch(h, n))) return rc;
+  const uint64_t words = bitmap_words((uint64_t)next_id);
+  if ((rc = ensure(h, h->bits, (words + 4) * 4))) return rc;
+  ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, h->stream));
+  uint32_t* start = (uint32_t*)h->cell_start[dst].p;
+  ABM_CK(h, dev_memset(start, 0, ((size_t)g.gt + 1) * 4, h->stream));
+  ABM_CK(h, dev_memset((uint32_t*)h->counters.p + CTR_ERR, 0, 4, h->stream));
+  if (n > 0) {
+    if ((rc = ensure(h, h->stage, (size_t)n * 32 + 64))) return rc;
+    int64_t* s_id = (int64_t*)h->stage.p;
+    int64_t* s_x = s_id + n;
+    int64_t* s_y = s_x + n;
+    double* s_e = (double*)(s_y + n);
+    ABM_CK(h, copy_h2d(s_id, id, (size_t)n * 8, h->stream));
+    ABM_CK(h, copy_h2d(s_x, x, (size_t)n * 8, h->stream));
+    ABM_CK(h, copy_h2d(s_y, y, (size_t)n * 8, h->stream));
+    ABM_CK(h, copy_h2d(s_e, energy, (size_t)n * 8, h->stream));
+    IngestBody ib;
+    ib.g = g; ib.hid = s_id; ib.hx = s_x; ib.hy = s_y; ib.he = s_e; ib.next_id = next_id;
+    ib.cell = (uint32_t*)h->cell[tmp].p; ib.id = (uint32_t*)h->id[tmp].p; ib.energy = (double*)h->energy[tmp].p;
+    ib.state = (uint8_t*)h->state.p; ib.slot = (uint32_t*)h->slot.p;
+    ib.new_count = start; ib.alive_bits = (uint32_t*)h->bits.p; ib.err = (uint32_t*)h->counters.p + CTR_ERR;
+    launch_foreach(h->stream, ib, (uint64_t)n);
+    if ((rc = check_launch(h, "ingest"))) return rc;
+  }
+  ABM_CK(h, scan_exclusive_u32(h->stream, start, (uint64_t)g.gt + 1, (uint32_t*)h->scan_tmp.p));
+  if (n > 0) {
+    View v = make_view(h);
+    v.cell = (uint32_t*)h->cell[tmp].p; v.id = (uint32_t*)h->id[tmp].p; v.energy = (double*)h->energy[tmp].p;
+    ScatterBody sb;
+    sb.v = v;
+    sb.new_cell = (const uint32_t*)h->cell[tmp].p;
+    sb.new_start = start;
+    sb.out_cell = (uint32_t*)h->cell[dst].p; sb.out_id = (uint32_t*)h->id[dst].p; sb.out_energy = (double*)h->energy[dst].p;
+    launch_foreach(h->stream, sb, (uint64_t)n);
+    if ((rc = check_launch(h, "ingest scatter"))) return rc;
+  }
+  if ((rc = read_counters(h))) return rc;
+  if (h->h_counters[CTR_ERR]) {
+    ABM_CK(h, dev_memset((uint32_t*)h->counters.p + CTR_ERR, 0, 4, h->stream));
+    h->agents_set = false; h->n = 0;
+    ABM_FAIL(h, ABM_E_BADARG, "agent coordinates must lie inside the grid and ids be unique in 1..next_id-1");
+  }
+  h->n = (uint64_t)n;
+  h->next_id = (uint64_t)next_id;
+  h->agents_set = true;
+  return ABM_OK;
+}
+
+int ABM_API(count_agents)(abm_handle* h, int64_t* n) {
+  if (!h || !n) return ABM_E_BADARG;
+  *n = (int64_t)h->n;
+  return ABM_OK;
+}
+
+int ABM_API(get_agents)(abm_handle* h, int64_t* n_inout, int64_t* id, int64_t* x, int64_t* y, double* energy) {
+  if (!h || !n_inout) return ABM_E_BADARG;
+  const int64_t n = (int64_t)h->n;
+  if (*n_inout < n) { *n_inout = n; ABM_FAIL(h, ABM_E_SMALL, "agent buffers hold %lld entries, %lld needed", (long long)*n_inout, (long long)n); }
+  *n_inout = n;
+  if (n == 0) return ABM_OK;
+  int rc = set_device(h);
+  if (rc) return rc;
+  const uint64_t words = bitmap_words(h->next_id);
+  if ((rc = ensure(h, h->bits, (words + 4) * 4))) return rc;
+  ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, h->stream));
+  SetBitsBody sbb;
+  sbb.id = (const uint32_t*)h->id[h->cur].p; sbb.bits = (uint32_t*)h->bits.p;
+  launch_foreach(h->stream, sbb, (uint64_t)n);
+  if ((rc = rank_prefix(h, words))) return rc;
+  if ((rc = ensure(h, h->stage, (size_t)n * 32 + 64))) return rc;
+  int64_t* s_id = (int64_t*)h->stage.p;
+  int64_t* s_x = s_id + n;
+  int64_t* s_y = s_x + n;
+  double* s_e = (double*)(s_y + n);
+  ExportBody eb;
+  eb.g = h->g;
+  eb.cell = (const uint32_t*)h->cell[h->cur].p; eb.id = (const uint32_t*)h->id[h->cur].p; eb.energy = (const double*)h->energy[h->cur].p;
+  eb.alive_bits = (const uint32_t*)h->bits.p; eb.prefix = (const uint32_t*)h->bits_prefix.p;
+  eb.oid = s_id; eb.ox = s_x; eb.oy = s_y; eb.oe = s_e;
+  launch_foreach(h->stream, eb, (uint64_t)n);
+  if ((rc = check_launch(h, "export"))) return rc;
+  if (id) ABM_CK(h, copy_d2h(id, s_id, (size_t)n * 8, h->stream));
+  if (x) ABM_CK(h, copy_d2h(x, s_x, (size_t)n * 8, h->stream));
+  if (y) ABM_CK(h, copy_d2h(y, s_y, (size_t)n * 8, h->stream));
+  if (energy) ABM_CK(h, copy_d2h(energy, s_e, (size_t)n * 8, h->stream));
+  return ABM_OK;
+}
+
+int ABM_API(set_global_state)(abm_handle* h, int64_t tick, int64_t behav, int64_t behav_counter) {
+  if (!h) return ABM_E_BADARG;
+  if (tick < 0 || tick > 0xFFFFFFFFll) ABM_FAIL(h, ABM_E_BADARG, "tick must fit 32 bits");
+  h->tick = (uint64_t)tick; h->behav = behav; h->behav_counter = behav_counter;
+  return ABM_OK;
+}
+
+int ABM_API(get_global_state)(abm_handle* h, int64_t* tick, int64_t* behav, int64_t* behav_counter, int64_t* next_id) {
+  if (!h) return ABM_E_BADARG;
+  if (tick) *tick = (int64_t)h->tick;
+  if (behav) *behav = h->behav;
+  if (behav_counter) *behav_counter = h->behav_counter;
+  if (next_id) *next_id = (int64_t)h->next_id;
+  return ABM_OK;
+}
+
+int ABM_API(step)(abm_handle* h, int64_t n_ticks) {
+  if (!h) return ABM_E_BADARG;
+  if (n_ticks < 0) ABM_FAIL(h, ABM_E_BADARG, "n_ticks must be >= 0");
+  if (!h->grid_set || !h->agents_set) ABM_FAIL(h, ABM_E_STATE, "abm_set_grid and abm_set_agents must precede abm_step");
+  if (h->cfg.walk_type == ABM_ALTERNATED_WALK) ABM_FAIL(h, ABM_E_STATE, "ALTERNATED_WALK is not available in this build yet");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const uint64_t l0 = launches_now();
+  h->rounds = 0;
+  h->tm_total.start(h->stream);
+  for (int64_t t = 0; t < n_ticks; ++t) {
+    if (h->tick >= 0xFFFFFFFFull) ABM_FAIL(h, ABM_E_CAPACITY, "tick counter exhausted");
+    if ((rc = tick_once(h))) return rc;
+  }
+  h->tm_total.stop(h->stream);
+  ABM_CK(h, stream_sync(h->stream));
+  h->t_total = h->tm_total.ms();
+  h->launches = (double)(launches_now() - l0);
+  return ABM_OK;
+}
+
+int ABM_API(reduce)(abm_handle* h, int32_t what, double* out) {
+  if (!h || !out) return ABM_E_BADARG;
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (what == ABM_REDUCE_COUNT_AGENTS) { *out = (double)h->n; return ABM_OK; }
+  if (what == ABM_REDUCE_COUNT_GROWN) {
+    if (!h->grid_set) ABM_FAIL(h, ABM_E_STATE, "abm_set_grid has not been called");
+    unsigned long long* acc = (unsigned long long*)((uint32_t*)h->counters.p + CTR_RED_LO);
+    ABM_CK(h, dev_memset(acc, 0, 8, h->stream));
+    CountGrownBody cb;
+    cb.grass4 = (const uint32_t*)h->grass.p; cb.out = acc;
+    launch_foreach(h->stream, cb, (uint64_t)h->g.gt / 4);
+    if ((rc = check_launch(h, "count grown"))) return rc;
+    unsigned long long v = 0;
+    ABM_CK(h, copy_d2h(&v, acc, 8, h->stream));
+    *out = (double)v;
+    return ABM_OK;
+  }
+  if (what == ABM_REDUCE_SUM_ENERGY || what == ABM_REDUCE_MAX_ENERGY || what == ABM_REDUCE_MIN_ENERGY) {
+    const uint64_t n = h->n;
+    if (n == 0) { *out = 0; return ABM_OK; }
+    const uint64_t chunks = (n + ENERGY_CHUNK - 1) / ENERGY_CHUNK;
+    if ((rc = ensure(h, h->partials, chunks * 8))) return rc;
+    EnergyPartialBody eb;
+    eb.energy = (const double*)h->energy[h->cur].p; eb.n = n; eb.what = what; eb.out = (double*)h->partials.p;
+    launch_foreach(h->stream, eb, chunks);
+    if ((rc = check_launch(h, "energy reduce"))) return rc;
+    std::vector<double> part(chunks);
+    ABM_CK(h, copy_d2h(part.data(), h->partials.p, chunks * 8, h->stream));
+    double v = part[0];
+    for (uint64_t i = 1; i < chunks; ++i) {
+      if (what == ABM_REDUCE_SUM_ENERGY) v += part[i];
+      else if (what == ABM_REDUCE_MAX_ENERGY) v = part[i] > v ? part[i] : v;
+      else v = part[i] < v ? part[i] : v;
+    }
+    *out = v;
+    return ABM_OK;
+  }
+  ABM_FAIL(h, ABM_E_BADARG, "unknown reduction %d", what);
+}
+
+int ABM_API(plan_routes)(abm_handle* h, int64_t, const int64_t*, const int64_t*, const int64_t*) {
+  if (!h) return ABM_E_BADARG;
+  ABM_FAIL(h, ABM_E_STATE, "abm_plan_routes is not available in this build yet");
+}
+int ABM_API(get_paths)(abm_handle* h, int64_t, const int64_t*, int64_t*, int64_t*, int64_t*, int64_t*, int64_t*) {
+  if (!h) return ABM_E_BADARG;
+  ABM_FAIL(h, ABM_E_STATE, "abm_get_paths is not available in this build yet");
+}
+
+int ABM_API(get_timing)(abm_handle* h, double* out, int32_t n) {
+  if (!h || !out) return ABM_E_BADARG;
+  const double v[6] = {h->t_total, h->t_agents, h->t_grass, h->rounds, h->launches, h->expansions};
+  for (int i = 0; i < n; ++i) out[i] = i < 6 ? v[i] : 0.0;
+  return ABM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,668 @@
+/*
+ * abm_kernels.h — device-side bodies of the general ("G") stepping path.
+ *
+ * One tick of the reference (Agents.step!: every agent in id order runs custom_agent_step!,
+ * src/agent_actions.jl:29-69, then custom_model_step!, src/model_actions.jl:18-30) becomes
+ *
+ *   propose   per agent: all state-independent work — RNG draws, walk rule, death and birth flags
+ *   resolve   rounds over the agents whose move depends on what lower-id agents did before them
+ *             (`ifempty` walks, gregarious view): exact rank-ordered fixed point
+ *   commit    eat (lowest id on a grown cell wins), energy, slot of the agent inside its new cell
+ *   scan      new per-cell offsets (cell-sorted SoA, counting sort)
+ *   scatter   agents (minus deaths, plus newborns) into the new cell-sorted SoA
+ *   regrow    grass sweep
+ *
+ * Sequential semantics.  With by-id scheduling, "agent k sees cell c occupied at its turn" is
+ *     exists j > k with old(j) = c                      (j has not moved yet)
+ *  or exists j < k with final(j) = c and present(j)     (j already moved; present = survived or left a newborn)
+ * where final(j) itself may depend on lower ids.  Each agent owns one decision byte; a decision is written
+ * once, and only from definite information, so any interleaving of threads yields the sequential result.
+ *
+ * Layout.  Cells are numbered tile-major: 32x32 tiles, row-major tiles, row-major inside a tile
+ * (tcell = tile<<10 | ly<<5 | lx).  Agents are kept sorted by tcell; cell_start[c] .. cell_start[c+1] is the
+ * run of agents standing on c (this replaces GridSpace.stored_ids).  Agents move at most one cell per tick
+ * (route followers excepted, handled through the `remote` list), so everything that can reach a cell sits in
+ * the 3x3 block of runs around it.
+ */
+#ifndef ABM_KERNELS_H_
+#define ABM_KERNELS_H_
+
+#include "abm_platform.h"
+#include "abm_rng.h"
+#include "../../include/abm.h"
+
+namespace abm {
+
+/* decision byte */
+enum {
+  ST_DIRMASK = 0x0F,
+  ST_DECIDED = 0x10,
+  ST_MOVED = 0x20, /* final cell = old cell + direction; else final = old */
+  ST_DEAD = 0x40,  /* energy - movement_cost < 0 (reduce_energy!, src/agent_actions.jl:85-92) */
+  ST_BIRTH = 0x80  /* rand(model.rng) <= reproduction_prob (src/agent_actions.jl:64) */
+};
+enum { DIR_STAY = 8, DIR_GREG = 9 };
+
+/* grass byte: bit 7 = fully_grown, bits 0..6 = countdown (0..126); 0x7F = padding cell outside the grid */
+enum { GRASS_GROWN = 0x80, GRASS_PAD = 0x7F };
+
+enum { TILE_SHIFT = 5, TILE = 32, TILE_CELLS = 1024 };
+enum { GREG_MAX_R = 7, GREG_WORDS = 4 };
+
+struct Geo {
+  int32_t nx, ny, tiles_x, tiles_y;
+  uint32_t gt; /* number of tile-major cells incl. padding */
+  int32_t periodic;
+};
+
+/* offsets_at_radius(model, 1) order (x fastest), SURVEY.md A-5 */
+ABM_HD void off8(int d, int& dx, int& dy) {
+  /* d: 0..7 -> (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1) */
+  const int q = d < 4 ? d : d + 1; /* skip the centre of the 3x3 */
+  dx = q % 3 - 1;
+  dy = q / 3 - 1;
+}
+ABM_HD int dir_code(int ex, int ey) {
+  const int q = (ey + 1) * 3 + (ex + 1);
+  return q < 4 ? q : (q == 4 ? (int)DIR_STAY : q - 1);
+}
+ABM_HD uint32_t enc(const Geo& g, int x, int y) {
+  return ((uint32_t)((y >> TILE_SHIFT) * g.tiles_x + (x >> TILE_SHIFT)) << 10) | (uint32_t)((y & 31) << 5) | (uint32_t)(x & 31);
+}
+ABM_HD void dec(const Geo& g, uint32_t c, int& x, int& y) {
+  const uint32_t t = c >> 10;
+  const uint32_t ty = t / (uint32_t)g.tiles_x, tx = t - ty * (uint32_t)g.tiles_x;
+  x = (int)(tx << TILE_SHIFT) | (int)(c & 31);
+  y = (int)(ty << TILE_SHIFT) | (int)((c >> 5) & 31);
+}
+/* Julia mod1 on 0-based coordinates for |d| <= n */
+ABM_HD int wrap(int a, int n) { return a < 0 ? a + n : (a >= n ? a - n : a); }
+ABM_HD int wrap_far(int a, int n) { a %= n; return a < 0 ? a + n : a; }
+
+/* pos + (dx,dy): wrapped when periodic; false when it leaves a non-periodic grid */
+ABM_HD bool shift(const Geo& g, int x, int y, int dx, int dy, int& ox, int& oy) {
+  ox = x + dx; oy = y + dy;
+  if (g.periodic) { ox = wrap_far(ox, g.nx); oy = wrap_far(oy, g.ny); return true; }
+  return ox >= 0 && ox < g.nx && oy >= 0 && oy < g.ny;
+}
+
+/* the distinct in-bounds cells of the 3x3 block around (x,y), centre first */
+ABM_HD int block9(const Geo& g, int x, int y, int px[9], int py[9]) {
+  int n = 0;
+  px[n] = x; py[n] = y; ++n;
+  for (int d = 0; d < 8; ++d) {
+    int dx, dy, ox, oy;
+    off8(d, dx, dy);
+    if (!shift(g, x, y, dx, dy, ox, oy)) continue;
+    bool dup = false;
+    if (g.nx < 3 || g.ny < 3) { /* wrap can alias cells only on grids narrower than 3 */
+      for (int i = 0; i < n; ++i) dup = dup || (px[i] == ox && py[i] == oy);
+    }
+    if (!dup) { px[n] = ox; py[n] = oy; ++n; }
+  }
+  return n;
+}
+
+struct Params {
+  int32_t walk_type, eat, reproduce, ifempty, walkmap_regrowth, regrowth_time, r, counter;
+  double prob_random_walk, delta_energy, movement_cost, reproduction_prob;
+  int64_t ax2, ay2; /* 2 * attractor, in 1-based coordinates */
+  uint64_t seed, tick;
+};
+
+/* everything a body needs; plain pointers, passed by value */
+struct View {
+  Geo g;
+  Params p;
+  uint32_t n;                /* agents at tick start */
+  uint32_t* cell;            /* tcell of each agent, ascending */
+  uint32_t* id;
+  double* energy;
+  uint8_t* state;
+  uint32_t* slot;            /* position inside the new cell run */
+  const uint32_t* cell_start; /* gt + 1 */
+  uint8_t* grass;            /* gt */
+  const uint32_t* walkbits;  /* gt / 32 words, bit = walkable */
+  const double* lut;         /* exp(-sqrt(k)/3) */
+  const uint8_t* greg_order; /* box cells by (d^2, β index) */
+  uint32_t* err;             /* sticky device error flags */
+};
+
+enum { ERR_NOWALKABLE = 1, ERR_INTERNAL = 2 };
+
+ABM_HD bool walkable(const View& v, uint32_t c) { return (v.walkbits[c >> 5] >> (c & 31)) & 1u; }
+ABM_HD bool present(uint8_t s) { return !(s & ST_DEAD) || (s & ST_BIRTH); }
+
+/* ------------------------------------------------------------------------------------------------ propose */
+
+/* effective direction code after GridSpace clamping / wrapping (Agents.walk!) */
+ABM_HD int effective_dir(const Geo& g, int x, int y, int dx, int dy) {
+  int tx, ty;
+  if (g.periodic) {
+    tx = wrap_far(x + dx, g.nx); ty = wrap_far(y + dy, g.ny);
+    if (tx == x && ty == y) return DIR_STAY;
+    if (g.nx < 3 && tx != x) dx = 1; /* both x-neighbours alias on a 2-wide ring: canonical direction */
+    if (g.ny < 3 && ty != y) dy = 1;
+    if (tx == x) dx = 0;
+    if (ty == y) dy = 0;
+    return dir_code(dx, dy);
+  }
+  tx = x + dx; ty = y + dy;
+  tx = tx < 0 ? 0 : (tx >= g.nx ? g.nx - 1 : tx);
+  ty = ty < 0 ? 0 : (ty >= g.ny ? g.ny - 1 : ty);
+  return dir_code(tx - x, ty - y);
+}
+
+/* random_walk_to_attractor (src/agent_actions.jl:263-267): round.(Int, normalize(attractor .- pos)) as the
+ * exact integer predicate of SURVEY.md A-6 */
+ABM_HD void attractor_dir(const Params& p, int x, int y, int& dx, int& dy) {
+  const int64_t ex = p.ax2 - 2 * (int64_t)(x + 1), ey = p.ay2 - 2 * (int64_t)(y + 1);
+  dx = 0; dy = 0;
+  if (ex == 0 && ey == 0) return;
+  if (3 * ex * ex > ey * ey) dx = ex > 0 ? 1 : -1;
+  if (3 * ey * ey > ex * ex) dy = ey > 0 ? 1 : -1;
+}
+
+struct ProposeBody {
+  View v;
+  uint32_t* pending;       /* worklist of undecided agents */
+  uint32_t* pending_count;
+
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t k = (uint32_t)i;
+    const Params& p = v.p;
+    const uint32_t c = v.cell[k];
+    const uint32_t id = v.id[k];
+    int x, y;
+    dec(v.g, c, x, y);
+    AgentStream rs;
+    rs.init(p.seed, p.tick, id);
+    uint8_t st = 0;
+    bool cond = false; /* move gated by isempty(target) */
+    int dx = 0, dy = 0;
+    bool randomwalk = false;
+
+    switch (p.walk_type) {
+      case ABM_RANDOM_WALK: randomwalk = true; break; /* :37-39 */
+      case ABM_RANDOM_WALK_ATTRACTOR:                 /* :40-42, execute_walk! :109-117 */
+        if (rs.next_f64() < p.prob_random_walk) randomwalk = true;
+        else { attractor_dir(p, x, y, dx, dy); cond = true; /* walk!(...; ifempty=true), :266 */ }
+        break;
+      case ABM_RANDOM_WALK_GREGARIOUS:                /* :43-45 */
+        if (rs.next_f64() < p.prob_random_walk) randomwalk = true;
+        else { st = DIR_GREG; rs.n += 1; /* draw 1 is consumed in resolve (wsample or rand(1:8)) */ }
+        break;
+      case ABM_RANDOM_WALKMAP: {                      /* :49-51 with prob 0, random_walkmap :182-186 */
+        (void)rs.next_f64(); /* rand(model.rng, Uniform(0,1)) < 0 is never true but is drawn */
+        int cand[8], nc = 0;
+        for (int d = 0; d < 8; ++d) {
+          int ox, oy, ddx, ddy;
+          off8(d, ddx, ddy);
+          if (!shift(v.g, x, y, ddx, ddy, ox, oy)) continue; /* nearby_positions drops out-of-bounds */
+          if (walkable(v, enc(v.g, ox, oy))) cand[nc++] = d;
+        }
+        if (nc == 0) { atomic_or(v.err, ERR_NOWALKABLE); st = DIR_STAY | ST_DECIDED; break; }
+        const int d = cand[rs.next_below((uint64_t)nc)];
+        off8(d, dx, dy);
+        const int e = effective_dir(v.g, x, y, dx, dy);
+        st = (uint8_t)(e | ST_DECIDED | (e != DIR_STAY ? ST_MOVED : 0)); /* move_agent!, unconditional */
+        break;
+      }
+      default: break; /* ABM_ALTERNATED_WALK is proposed by AlternatedProposeBody */
+    }
+    if (randomwalk) { /* randomwalk!: rand(rng, offsets_at_radius(model, 1)) then walk!(...; ifempty) */
+      off8((int)rs.next_below(8), dx, dy);
+      cond = true;
+      if (!p.ifempty) {
+        const int e = effective_dir(v.g, x, y, dx, dy);
+        st = (uint8_t)(e | ST_DECIDED | (e != DIR_STAY ? ST_MOVED : 0));
+        cond = false;
+      }
+    }
+    if (cond) {
+      const int e = effective_dir(v.g, x, y, dx, dy);
+      /* a target equal to the own cell is never empty (the agent stands on it): decided, no move */
+      st = (uint8_t)(e == DIR_STAY ? (DIR_STAY | ST_DECIDED) : e);
+    }
+    if (v.energy[k] - p.movement_cost < 0) st |= ST_DEAD;
+    if (p.reproduce && rs.next_f64() <= p.reproduction_prob) st |= ST_BIRTH;
+    v.state[k] = st;
+    if (!(st & ST_DECIDED)) pending[atomic_add(pending_count, 1u)] = k;
+  }
+};
+
+/* ------------------------------------------------------------------------------------------------ resolve */
+
+enum { RES_PENDING = 0, RES_DONE = 1 };
+
+/* `ifempty` walk of agent k towards T = old + dir.  SURVEY.md Appendix C D1. */
+ABM_HD int resolve_cond(const View& v, uint32_t k, uint8_t st) {
+  const uint32_t myid = v.id[k];
+  int x, y, dx, dy, tx, ty;
+  dec(v.g, v.cell[k], x, y);
+  off8(st & ST_DIRMASK, dx, dy);
+  shift(v.g, x, y, dx, dy, tx, ty);
+  bool blocked = false, unknown = false;
+  int px[9], py[9];
+  const int nb = block9(v.g, tx, ty, px, py);
+  for (int b = 0; b < nb && !blocked; ++b) {
+    const uint32_t cb = enc(v.g, px[b], py[b]);
+    const uint32_t beg = v.cell_start[cb], end = v.cell_start[cb + 1];
+    for (uint32_t j = beg; j < end; ++j) {
+      if (j == k) continue;
+      const uint32_t idj = v.id[j];
+      if (b == 0) { /* agents that start the tick on T */
+        if (idj > myid) { blocked = true; break; } /* still there at k's turn */
+        const uint8_t sj = load_state(&v.state[j]);
+        if (!(sj & ST_DECIDED)) unknown = true;
+        else if (!(sj & ST_MOVED) && present(sj)) { blocked = true; break; }
+      } else { /* agents one step away from T */
+        if (idj > myid) continue; /* has not moved yet */
+        const uint8_t sj = load_state(&v.state[j]);
+        const int dj = sj & ST_DIRMASK;
+        if (dj == DIR_STAY) continue;
+        bool hits = true; /* an undecided gregarious agent may step onto any neighbour */
+        if (dj != DIR_GREG) {
+          int jx, jy, fx, fy;
+          off8(dj, jx, jy);
+          shift(v.g, px[b], py[b], jx, jy, fx, fy);
+          hits = fx == tx && fy == ty;
+        }
+        if (!hits) continue;
+        if (!(sj & ST_DECIDED)) unknown = true;
+        else if ((sj & ST_MOVED) && present(sj)) { blocked = true; break; }
+      }
+    }
+  }
+  if (blocked) { v.state[k] = (uint8_t)(st | ST_DECIDED); return RES_DONE; }
+  if (unknown) return RES_PENDING;
+  v.state[k] = (uint8_t)(st | ST_DECIDED | ST_MOVED);
+  return RES_DONE;
+}
+
+struct BoxMask {
+  uint64_t w[GREG_WORDS];
+  ABM_HD void clear() { for (int i = 0; i < GREG_WORDS; ++i) w[i] = 0; }
+  ABM_HD void set(int bit) { w[bit >> 6] |= 1ull << (bit & 63); }
+  ABM_HD bool get(int bit) const { return (w[bit >> 6] >> (bit & 63)) & 1ull; }
+};
+
+/* random_walk_gregarious (src/agent_actions.jl:297-336) for agent k.  SURVEY.md Appendix C D3, A-5, A-7. */
+ABM_HD int resolve_greg(const View& v, uint32_t k, uint8_t st) {
+  const uint32_t myid = v.id[k];
+  const int r = v.p.r, side = 2 * r + 1;
+  int x, y;
+  dec(v.g, v.cell[k], x, y);
+  BoxMask def, unk;
+  def.clear(); unk.clear();
+#define ABM_MARK(mask, bx, by) do { const int bx_ = (bx), by_ = (by); \
+    if (bx_ >= -r && bx_ <= r && by_ >= -r && by_ <= r) (mask).set((by_ + r) * side + (bx_ + r)); } while (0)
+  for (int sy = -r - 1; sy <= r + 1; ++sy) {
+    const int cy = wrap_far(y + sy, v.g.ny);
+    for (int sx = -r - 1; sx <= r + 1; ++sx) {
+      const int cx = wrap_far(x + sx, v.g.nx);
+      const uint32_t cb = enc(v.g, cx, cy);
+      const uint32_t beg = v.cell_start[cb], end = v.cell_start[cb + 1];
+      for (uint32_t j = beg; j < end; ++j) {
+        if (j == k) continue;
+        if (v.id[j] > myid) { ABM_MARK(def, sx, sy); continue; } /* still on its old cell */
+        const uint8_t sj = load_state(&v.state[j]);
+        const int dj = sj & ST_DIRMASK;
+        int jx = 0, jy = 0;
+        if (dj < 8) off8(dj, jx, jy);
+        if (sj & ST_DECIDED) {
+          if (!present(sj)) continue;
+          if (sj & ST_MOVED) ABM_MARK(def, sx + jx, sy + jy); else ABM_MARK(def, sx, sy);
+        } else if (dj == DIR_GREG) {
+          for (int ay = -1; ay <= 1; ++ay) for (int ax = -1; ax <= 1; ++ax) ABM_MARK(unk, sx + ax, sy + ay);
+        } else {
+          ABM_MARK(unk, sx, sy);
+          ABM_MARK(unk, sx + jx, sy + jy);
+        }
+      }
+    }
+  }
+#undef ABM_MARK
+  /* closest neighbour: strict `<` over nearby_ids order == minimum of (d^2, β index) over occupied cells */
+  int closest = -1;
+  const int cells = side * side;
+  for (int q = 0; q < cells; ++q) {
+    const int bit = v.greg_order[q];
+    if (def.get(bit)) { closest = bit; break; }
+    if (unk.get(bit)) return RES_PENDING;
+  }
+  AgentStream rs;
+  rs.init(v.p.seed, v.p.tick, myid);
+  rs.n = 1; /* draw 0 was the execute_walk! uniform */
+  int dir;
+  if (closest < 0) {
+    dir = (int)rs.next_below(8); /* :334 */
+  } else {
+    const int bx = closest % side - r, by = closest / side - r;
+    double w[8], s1, s2;
+    for (int i = 0; i < 8; ++i) {
+      int ox, oy;
+      off8(i, ox, oy);
+      const int kx = ox - bx, ky = oy - by;
+      w[i] = v.lut[kx * kx + ky * ky];
+    }
+    s1 = w[0];
+    for (int i = 1; i < 8; ++i) s1 += w[i];
+    for (int i = 0; i < 8; ++i) w[i] = w[i] / s1;
+    s2 = w[0];
+    for (int i = 1; i < 8; ++i) s2 += w[i];
+    const double t = rs.next_f64() * s2; /* StatsBase.sample(rng, wv) */
+    int i = 0;
+    double cw = w[0];
+    while (cw < t && i < 7) { ++i; cw += w[i]; }
+    dir = i;
+  }
+  v.state[k] = (uint8_t)((st & (ST_DEAD | ST_BIRTH)) | dir | ST_DECIDED | ST_MOVED); /* move_agent!, :331 */
+  return RES_DONE;
+}
+
+struct ResolveBody {
+  View v;
+  const uint32_t* in;
+  const uint32_t* in_count;
+  uint32_t* out;
+  uint32_t* out_count;
+
+  ABM_HD void operator()(uint64_t i) const {
+    if (i >= *in_count) return;
+    const uint32_t k = in[i];
+    const uint8_t st = v.state[k];
+    const int res = (st & ST_DIRMASK) == DIR_GREG ? resolve_greg(v, k, st) : resolve_cond(v, k, st);
+    if (res == RES_PENDING) out[atomic_add(out_count, 1u)] = k;
+  }
+};
+
+/* ------------------------------------------------------------------------------------------------- commit */
+
+struct BirthRec { uint32_t parent; uint32_t base; };
+
+ABM_HD void final_xy(const View& v, int ox, int oy, uint8_t s, int& fx, int& fy) {
+  fx = ox; fy = oy;
+  if (s & ST_MOVED) {
+    int dx, dy;
+    off8(s & ST_DIRMASK, dx, dy);
+    shift(v.g, ox, oy, dx, dy, fx, fy);
+  }
+}
+
+/* reduce_energy! + eat! + reproduce! (src/agent_actions.jl:54-67) once every final cell is known, plus the
+ * bookkeeping of the counting sort into the next tick's cell-sorted order. */
+struct CommitBody {
+  View v;
+  uint32_t* new_count;  /* gt + 1, zeroed */
+  uint32_t* birth_bits; /* bitmap over ids */
+  BirthRec* births;
+  uint32_t* birth_count;
+  uint32_t* new_cell;   /* final tcell of each agent */
+
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t k = (uint32_t)i;
+    const uint8_t st = v.state[k];
+    const uint32_t myid = v.id[k];
+    int x, y, fx, fy;
+    dec(v.g, v.cell[k], x, y);
+    final_xy(v, x, y, st, fx, fy);
+    const uint32_t fc = enc(v.g, fx, fy);
+    int px[9], py[9];
+    const int nb = block9(v.g, fx, fy, px, py);
+    bool lower = false;
+    uint32_t slot_alive = 0, slot_birth = 0, alive_tot = 0, birth_tot = 0;
+    for (int b = 0; b < nb; ++b) {
+      const uint32_t cb = enc(v.g, px[b], py[b]);
+      const uint32_t beg = v.cell_start[cb], end = v.cell_start[cb + 1];
+      for (uint32_t j = beg; j < end; ++j) {
+        const uint8_t sj = v.state[j];
+        if (b == 0) { if (sj & ST_MOVED) continue; }
+        else {
+          if (!(sj & ST_MOVED)) continue;
+          int jx, jy;
+          final_xy(v, px[b], py[b], sj, jx, jy);
+          if (jx != fx || jy != fy) continue;
+        }
+        const bool alive = !(sj & ST_DEAD), birth = (sj & ST_BIRTH) != 0;
+        alive_tot += alive; birth_tot += birth;
+        if (j != k && v.id[j] < myid) { lower = true; slot_alive += alive; slot_birth += birth; }
+      }
+    }
+    /* eat!: the first agent (lowest id) to stand on a grown cell eats it; killed agents still eat */
+    double e = v.energy[k] - v.p.movement_cost;
+    if (v.p.eat && !lower && (v.grass[fc] & GRASS_GROWN)) {
+      e += v.p.delta_energy;
+      v.grass[fc] = (uint8_t)(v.grass[fc] & ~GRASS_GROWN); /* single writer: the lowest id on fc */
+    }
+    if (st & ST_BIRTH) {
+      e /= 2; /* reproduce!, :172-178 */
+      atomic_or(&birth_bits[myid >> 5], 1u << (myid & 31));
+      BirthRec rec;
+      rec.parent = k;
+      rec.base = alive_tot + slot_birth;
+      births[atomic_add(birth_count, 1u)] = rec;
+    }
+    v.energy[k] = e;
+    v.slot[k] = slot_alive;
+    new_cell[k] = fc;
+    if (!lower) new_count[fc] = alive_tot + birth_tot;
+  }
+};
+
+/* survivors into the next tick's arrays */
+struct ScatterBody {
+  View v;
+  const uint32_t* new_cell;
+  const uint32_t* new_start;
+  uint32_t* out_cell;
+  uint32_t* out_id;
+  double* out_energy;
+
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t k = (uint32_t)i;
+    if (v.state[k] & ST_DEAD) return; /* kill_agent! */
+    const uint32_t fc = new_cell[k];
+    const uint32_t pos = new_start[fc] + v.slot[k];
+    out_cell[pos] = fc;
+    out_id[pos] = v.id[k];
+    out_energy[pos] = v.energy[k];
+  }
+};
+
+/* offspring: id = nextid(model) in order of the parents' ids */
+struct BirthScatterBody {
+  View v;
+  const BirthRec* births;
+  const uint32_t* birth_bits;
+  const uint32_t* birth_prefix; /* exclusive popcount prefix per bitmap word */
+  const uint32_t* new_cell;
+  const uint32_t* new_start;
+  uint32_t next_id;
+  uint32_t* out_cell;
+  uint32_t* out_id;
+  double* out_energy;
+
+  ABM_HD void operator()(uint64_t i) const {
+    const BirthRec rec = births[i];
+    const uint32_t k = rec.parent;
+    const uint32_t pid = v.id[k];
+    const uint32_t w = pid >> 5;
+    const uint32_t rank = birth_prefix[w] + (uint32_t)popc(birth_bits[w] & ((1u << (pid & 31)) - 1u));
+    const uint32_t fc = new_cell[k];
+    const uint32_t pos = new_start[fc] + rec.base;
+    out_cell[pos] = fc;
+    out_id[pos] = next_id + rank;
+    out_energy[pos] = v.energy[k]; /* offspring gets the halved energy */
+  }
+};
+
+struct PopcountBody { /* per-word popcounts as the input of the rank scan */
+  const uint32_t* bits;
+  uint32_t* out;
+  ABM_HD void operator()(uint64_t i) const { out[i] = (uint32_t)popc(bits[i]); }
+};
+
+/* ------------------------------------------------------------------------------------------------- regrow */
+
+ABM_HD uint32_t regrow4(uint32_t w, uint32_t rt, uint32_t walk4, bool use_walk) {
+  uint32_t out = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    uint32_t s = (w >> (8 * b)) & 0xFFu;
+    const bool ok = !use_walk || ((walk4 >> b) & 1u);
+    if (ok && s != GRASS_PAD && !(s & GRASS_GROWN)) {
+      if (s == 0) s = GRASS_GROWN | rt; /* countdown <= 0: fully_grown = true, countdown = regrowth_time */
+      else s -= 1;
+    }
+    out |= s << (8 * b);
+  }
+  return out;
+}
+
+/* custom_model_step! (src/model_actions.jl:18-30): 16 cells per thread */
+struct RegrowBody {
+  uint32_t* grass4; /* gt / 4 words */
+  const uint32_t* walkbits;
+  uint32_t rt;
+  int32_t use_walk;
+
+  ABM_HD void operator()(uint64_t i) const {
+    uint32_t w[4];
+#if defined(__CUDA_ARCH__)
+    const uint4 q = reinterpret_cast<const uint4*>(grass4)[i];
+    w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+#else
+    for (int a = 0; a < 4; ++a) w[a] = grass4[4 * i + a];
+#endif
+    uint32_t wb = 0;
+    if (use_walk) wb = walkbits[i >> 1] >> ((i & 1) * 16);
+    for (int a = 0; a < 4; ++a) w[a] = regrow4(w[a], rt, wb >> (4 * a), use_walk != 0);
+#if defined(__CUDA_ARCH__)
+    reinterpret_cast<uint4*>(grass4)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+#else
+    for (int a = 0; a < 4; ++a) grass4[4 * i + a] = w[a];
+#endif
+  }
+};
+
+/* ---------------------------------------------------------------------------------------- boundary helpers */
+
+/* abm_set_agents: host records -> unsorted SoA + counting-sort bookkeeping */
+struct IngestBody {
+  Geo g;
+  const int64_t* hid; const int64_t* hx; const int64_t* hy; const double* he;
+  int64_t next_id;
+  uint32_t* cell; uint32_t* id; double* energy; uint8_t* state; uint32_t* slot;
+  uint32_t* new_count;
+  uint32_t* alive_bits;
+  uint32_t* err;
+
+  ABM_HD void operator()(uint64_t i) const {
+    const int64_t x = hx[i], y = hy[i], a = hid[i];
+    if (x < 1 || x > g.nx || y < 1 || y > g.ny || a < 1 || a >= next_id) { atomic_or(err, ERR_INTERNAL); cell[i] = 0; id[i] = 0; energy[i] = 0; state[i] = ST_DEAD; return; }
+    const uint32_t c = enc(g, (int)(x - 1), (int)(y - 1));
+    const uint32_t bit = 1u << ((uint32_t)a & 31);
+    if (atomic_or(&alive_bits[(uint32_t)a >> 5], bit) & bit) atomic_or(err, ERR_INTERNAL); /* duplicate id */
+    cell[i] = c; id[i] = (uint32_t)a; energy[i] = he[i]; state[i] = 0;
+    slot[i] = atomic_add(&new_count[c], 1u);
+  }
+};
+
+struct SetBitsBody { /* alive-id bitmap of the current population */
+  const uint32_t* id;
+  uint32_t* bits;
+  ABM_HD void operator()(uint64_t i) const { const uint32_t a = id[i]; atomic_or(&bits[a >> 5], 1u << (a & 31)); }
+};
+
+/* abm_get_agents: cell-sorted SoA -> id-ordered host records */
+struct ExportBody {
+  Geo g;
+  const uint32_t* cell; const uint32_t* id; const double* energy;
+  const uint32_t* alive_bits; const uint32_t* prefix;
+  int64_t* oid; int64_t* ox; int64_t* oy; double* oe;
+
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t a = id[i];
+    const uint32_t w = a >> 5;
+    const uint32_t rank = prefix[w] + (uint32_t)popc(alive_bits[w] & ((1u << (a & 31)) - 1u));
+    int x, y;
+    dec(g, cell[i], x, y);
+    oid[rank] = a; ox[rank] = x + 1; oy[rank] = y + 1; oe[rank] = energy[i];
+  }
+};
+
+/* abm_set_grid: column-major host arrays -> tile-major packed bytes; one thread per tile-major cell */
+struct GridImportBody {
+  Geo g;
+  const uint8_t* fg; const int64_t* cd; const uint8_t* wm; const int64_t* el;
+  uint64_t row0, rows; /* the chunk of grid rows [row0, row0+rows) present in the staging buffers */
+  uint8_t* grass; uint32_t* walkbits; int16_t* elev; uint32_t* err;
+
+  ABM_HD void operator()(uint64_t i) const {
+    /* i indexes (row in chunk, x) */
+    const uint64_t yy = i / (uint64_t)g.nx, x = i - yy * (uint64_t)g.nx;
+    const uint64_t y = row0 + yy;
+    const uint32_t c = enc(g, (int)x, (int)y);
+    const int64_t k = cd[i];
+    if (k < 0 || k > 126) atomic_or(err, ERR_INTERNAL);
+    grass[c] = (uint8_t)((fg[i] ? GRASS_GROWN : 0) | (uint8_t)(k & 0x7F));
+    if (!wm || wm[i]) atomic_or(&walkbits[c >> 5], 1u << (c & 31));
+    if (el) {
+      const int64_t e = el[i];
+      if (e < -32768 || e > 32767) atomic_or(err, ERR_INTERNAL);
+      elev[c] = (int16_t)e;
+    }
+  }
+};
+
+struct GridExportBody {
+  Geo g;
+  const uint8_t* grass;
+  uint64_t row0;
+  uint8_t* fg; int64_t* cd;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint64_t yy = i / (uint64_t)g.nx, x = i - yy * (uint64_t)g.nx;
+    const uint8_t s = grass[enc(g, (int)x, (int)(row0 + yy))];
+    if (fg) fg[i] = (s & GRASS_GROWN) ? 1 : 0;
+    if (cd) cd[i] = s & 0x7F;
+  }
+};
+
+/* reductions for adata/mdata (run!): per-thread partials combined with 64-bit atomics; energy sums are done
+ * in fixed point on the host side of the ABI only when exactness matters — here a tree of doubles per block
+ * would not be order-stable, so sum uses a deterministic two-pass layout (see engine). */
+struct CountGrownBody {
+  const uint32_t* grass4;
+  unsigned long long* out;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t w = grass4[i];
+    /* padding cells are 0x7F: bit 7 clear */
+    const uint32_t c = (uint32_t)popc(w & 0x80808080u);
+    if (c) atomic_add64(out, c);
+  }
+};
+
+/* sum / max / min of agent energy: one partial per 1024-agent chunk, chunks combined in order by the host,
+ * so the result does not depend on thread scheduling */
+enum { ENERGY_CHUNK = 1024 };
+struct EnergyPartialBody {
+  const double* energy;
+  uint64_t n;
+  int32_t what;
+  double* out;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint64_t lo = i * ENERGY_CHUNK, hi = lo + ENERGY_CHUNK < n ? lo + ENERGY_CHUNK : n;
+    double v = energy[lo];
+    for (uint64_t k = lo + 1; k < hi; ++k) {
+      const double e = energy[k];
+      if (what == ABM_REDUCE_SUM_ENERGY) v += e;
+      else if (what == ABM_REDUCE_MAX_ENERGY) v = e > v ? e : v;
+      else v = e < v ? e : v;
+    }
+    out[i] = v;
+  }
+};
+
+}  // namespace abm
+#endif /* ABM_KERNELS_H_ */

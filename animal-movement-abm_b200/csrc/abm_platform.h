@@ -1,0 +1,135 @@
+/*
+ * abm_platform.h — the one place that knows whether the engine sources are being compiled by nvcc for sm_100a
+ * (the product, libabm.so) or by g++ with -DABM_EMU (tests/emu only).
+ *
+ * ABM_EMU is NOT a CPU fallback of the product: libabm.so is never built with it, and nothing in the package
+ * loads the emulation library.  It exists because the build container has no GPU: the kernel bodies are plain
+ * functors over raw pointers, so the `-m "not gpu"` tests run the very same bodies and the very same host
+ * orchestration (allocation, launch order, worklists, re-binning) with a sequential "launcher" that visits the
+ * thread indices in a shuffled order.  That catches logic and ordering bugs before GPU minutes are spent.
+ */
+#ifndef ABM_PLATFORM_H_
+#define ABM_PLATFORM_H_
+
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef ABM_EMU
+/* ------------------------------------------------------------------ emulation (tests only) --------------- */
+#define ABM_HD inline
+#define ABM_D inline
+#include <algorithm>
+#include <vector>
+
+typedef int abm_stream_t;
+typedef int abm_err_t;
+
+namespace abm {
+
+static inline uint32_t atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline uint32_t atomic_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+static inline uint32_t atomic_max(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
+static inline unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+static inline uint8_t load_state(const uint8_t* p) { return *(const volatile uint8_t*)p; }
+static inline int popc(uint32_t v) { return __builtin_popcount(v); }
+
+struct EmuRand {
+  uint64_t s;
+  uint32_t next() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(s >> 33); }
+};
+extern uint64_t g_emu_launches;
+extern uint64_t g_emu_shuffle_seed;
+
+/* visits i in [0,n) in a pseudo-random order (block-shuffled so that big launches stay cheap) */
+template <class F>
+static inline void launch_foreach(abm_stream_t, const F& f, uint64_t n, const char* = 0) {
+  ++g_emu_launches;
+  if (n == 0) return;
+  EmuRand r = {g_emu_shuffle_seed + n * 0x9E3779B97F4A7C15ull + g_emu_launches};
+  const uint64_t B = 61; /* prime block; blocks visited in a strided permutation, lanes reversed at random */
+  const uint64_t nb = (n + B - 1) / B;
+  uint64_t stride = 1;
+  if (nb > 2) { stride = (r.next() % (nb - 1)) + 1; while (std::__gcd(stride, nb) != 1) ++stride; }
+  uint64_t b = r.next() % nb;
+  for (uint64_t k = 0; k < nb; ++k, b = (b + stride) % nb) {
+    const uint64_t lo = b * B, hi = std::min(n, lo + B);
+    if (r.next() & 1) { for (uint64_t i = hi; i-- > lo;) f(i); }
+    else { for (uint64_t i = lo; i < hi; ++i) f(i); }
+  }
+}
+
+static inline abm_err_t dev_malloc(void** p, size_t bytes) { *p = calloc(bytes ? bytes : 1, 1); return *p ? 0 : 2; }
+static inline void dev_free(void* p) { free(p); }
+static inline abm_err_t dev_memset(void* p, int v, size_t bytes, abm_stream_t) { memset(p, v, bytes); return 0; }
+static inline abm_err_t copy_h2d(void* d, const void* h, size_t bytes, abm_stream_t) { memcpy(d, h, bytes); return 0; }
+static inline abm_err_t copy_d2h(void* h, const void* d, size_t bytes, abm_stream_t) { memcpy(h, d, bytes); return 0; }
+static inline abm_err_t copy_d2d(void* d, const void* s, size_t bytes, abm_stream_t) { memmove(d, s, bytes); return 0; }
+static inline abm_err_t stream_sync(abm_stream_t) { return 0; }
+static inline const char* err_string(abm_err_t e) { return e ? "emulated allocation failure" : "ok"; }
+
+}  // namespace abm
+
+#else
+/* ------------------------------------------------------------------ CUDA, sm_100a (the product) ---------- */
+#include <cuda_runtime.h>
+#define ABM_HD __device__ __forceinline__
+#define ABM_D __device__ __forceinline__
+
+typedef cudaStream_t abm_stream_t;
+typedef cudaError_t abm_err_t;
+
+namespace abm {
+
+ABM_D uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+ABM_D uint32_t atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
+ABM_D uint32_t atomic_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
+ABM_D unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+/* per-agent decision bytes are written once by their owner and polled by neighbours in the same launch:
+ * bypass L1 so that a decision published by another SM becomes visible (ld.global.cg = cache at L2 only) */
+ABM_D uint8_t load_state(const uint8_t* p) { return __ldcg(p); }
+ABM_D int popc(uint32_t v) { return __popc(v); }
+
+extern unsigned long long g_launches;
+
+template <class F>
+__global__ void __launch_bounds__(256) k_foreach(const F f, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f(i);
+}
+
+template <class F>
+static inline void launch_foreach(abm_stream_t s, const F& f, uint64_t n, const char* = 0) {
+  if (n == 0) return;
+  ++g_launches;
+  const uint64_t blocks = (n + 255) / 256;
+  k_foreach<F><<<(unsigned)blocks, 256, 0, s>>>(f, n);
+}
+
+static inline abm_err_t dev_malloc(void** p, size_t bytes) {
+  abm_err_t e = cudaMalloc(p, bytes ? bytes : 1);
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes ? bytes : 1);
+  /* the handle's stream is non-blocking: make the legacy-stream memset land before anyone writes the buffer */
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  return e;
+}
+static inline void dev_free(void* p) { if (p) cudaFree(p); }
+static inline abm_err_t dev_memset(void* p, int v, size_t bytes, abm_stream_t s) { return cudaMemsetAsync(p, v, bytes, s); }
+static inline abm_err_t copy_h2d(void* d, const void* h, size_t bytes, abm_stream_t s) {
+  abm_err_t e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(s);
+}
+static inline abm_err_t copy_d2h(void* h, const void* d, size_t bytes, abm_stream_t s) {
+  abm_err_t e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(s);
+}
+static inline abm_err_t copy_d2d(void* d, const void* src, size_t bytes, abm_stream_t s) {
+  return cudaMemcpyAsync(d, src, bytes, cudaMemcpyDeviceToDevice, s);
+}
+static inline abm_err_t stream_sync(abm_stream_t s) { return cudaStreamSynchronize(s); }
+static inline const char* err_string(abm_err_t e) { return cudaGetErrorString(e); }
+
+}  // namespace abm
+#endif
+
+#endif /* ABM_PLATFORM_H_ */

@@ -1,0 +1,174 @@
+/*
+ * abm.h — C ABI of libabm.so, the B200-native stepping engine for the GridSpace sheep model of
+ * tatakof/Animal-Movement-ABM.
+ *
+ * The reference has no FFI of its own; the boundary it defines is functional: two factories return the
+ * callbacks that Agents.jl's step!/run! accept (reference src/agent_actions.jl:24-71 `herbivore_dynamics`,
+ * src/model_actions.jl:15-32 `grass_growth_dynamics`).  A host shim (Julia `ccall`, Python `ctypes`) keeps
+ * those factory names and turns `step!(model, agent_step!, model_step!, n)` into ONE `abm_step(h, n)`.
+ * Each entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *  - every function returns 0 (ABM_OK) or a negative ABM_E_* code; nothing throws or aborts;
+ *  - all arrays are caller-owned; the library copies and never retains a host pointer;
+ *  - grid arrays are nx*ny, column-major with x fastest (Julia `Array`): element (x,y) 1-based is
+ *    a[(y-1)*nx + (x-1)];
+ *  - agent coordinates are 1-based (Julia `agent.pos`);
+ *  - a handle is not thread-safe; distinct handles are independent;
+ *  - there is no CPU fallback: abm_create fails with ABM_E_CUDA when no sm_100 device is usable.
+ *
+ * Randomness contract (north star: counter-based Philox keyed by (seed, tick, agent id, draw index)):
+ *   u64 draw(seed, tick, id, n) = words (2h, 2h+1), h = n & 1, of
+ *       Philox4x32-10(key = (seed_lo, seed_hi), ctr = (n >> 1, tick_lo32, id_lo32, id_hi32))
+ *   as lo | hi << 32.  `n` is POSITIONAL: the n-th `rand` call the reference's agent_step! makes for this
+ *   (tick, agent), with the two global-RNG call sites (src/agent_actions.jl:213 `sample(1:3)`, :328
+ *   `wsample`) routed through the injected RNG.  Float64 = low 52 bits as [1,2) mantissa minus 1
+ *   (Julia Random, generic AbstractRNG); `rand(1:k)` = Lemire nearly-division-less (Julia
+ *   SamplerRangeNDL), redraws advance n.  Scheduler order is by agent id (Schedulers.by_id).
+ */
+#ifndef ABM_H_
+#define ABM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABM_ABI_VERSION 1
+
+/* error codes */
+enum {
+  ABM_OK = 0,
+  ABM_E_BADARG = -1,     /* invalid argument / unsupported parameter combination */
+  ABM_E_CUDA = -2,       /* CUDA runtime error or no usable device */
+  ABM_E_SMALL = -3,      /* caller buffer too small; needed size returned through the count pointer */
+  ABM_E_STATE = -4,      /* call order violated (e.g. abm_step before abm_set_grid) */
+  ABM_E_NOWALKABLE = -5, /* random_walkmap found no walkable neighbour: the reference throws (rand(1:0)) */
+  ABM_E_CAPACITY = -6,   /* id space (2^32-1) or device memory exhausted */
+  ABM_E_NOMEM = -7,
+  ABM_E_INTERNAL = -8
+};
+
+/* reference: `@enum WalkType ...`, src/agent_actions.jl:1 (same order, same values) */
+enum {
+  ABM_RANDOM_WALK = 0,
+  ABM_RANDOM_WALK_ATTRACTOR = 1,
+  ABM_RANDOM_WALK_GREGARIOUS = 2,
+  ABM_ALTERNATED_WALK = 3,
+  ABM_RANDOM_WALKMAP = 4
+};
+
+/* Agents.Pathfinding cost metrics used by the scripts (v0.4/v0.5: DirectDistance default,
+ * v0.6: PenaltyMap(elevation, MaxDistance{2}()), scripts/v0.6.jl:87-93) */
+enum { ABM_ASTAR_DIRECT = 0, ABM_ASTAR_MAX = 1 };
+
+/* what abm_reduce computes (reference: adata/mdata aggregations of run!, scripts/v0.6.jl:204-210) */
+enum {
+  ABM_REDUCE_COUNT_AGENTS = 0, /* adata = [(sheep, count)] */
+  ABM_REDUCE_COUNT_GROWN = 1,  /* mdata = [count_grass] = count(model.fully_grown) */
+  ABM_REDUCE_SUM_ENERGY = 2,
+  ABM_REDUCE_MAX_ENERGY = 3,
+  ABM_REDUCE_MIN_ENERGY = 4
+};
+
+/*
+ * Flat mirror of the kwargs of `initialize_model` (scripts/v0.1.jl:36-46 ... scripts/v0.6.jl:36-47), of the two
+ * factories (src/agent_actions.jl:24-33, src/model_actions.jl:15-17) and of the model `properties`
+ * NamedTuple (scripts/v0.6.jl:78-94).  Sheep parameters are model-uniform: every script gives all sheep the
+ * same values and offspring copy the parent's (src/agent_actions.jl:175).
+ */
+typedef struct abm_config {
+  int32_t struct_size; /* = sizeof(abm_config); ABI versioning */
+  int32_t nx, ny;      /* GridSpace dims (griddims) */
+  int32_t periodic;    /* GridSpace(...; periodic) */
+  int32_t walk_type;   /* herbivore_dynamics(; walk_type) */
+  int32_t eat;         /* herbivore_dynamics(; eat) */
+  int32_t reproduce;   /* herbivore_dynamics(; reproduce) */
+  int32_t walkmap_regrowth; /* grass_growth_dynamics(; walkmap) */
+  int32_t regrowth_time;    /* model.regrowth_time, 1..126 */
+  int32_t visual_distance;  /* floor(agent.visual_distance), 1..7 (gregarious only) */
+  int32_t counter;          /* model.counter (alternated walk) */
+  int32_t randomwalk_ifempty; /* Agents.walk!(...; ifempty) default used by randomwalk!; 1 in Agents 5.14 */
+  int32_t astar_metric;     /* ABM_ASTAR_DIRECT / ABM_ASTAR_MAX */
+  int32_t astar_penalty;    /* 1: PenaltyMap(elevation, base metric) */
+  int32_t device;           /* CUDA device ordinal of this handle */
+  int32_t reserved0;
+  double prob_random_walk;  /* custom_agent_step!(...; prob_random_walk = 0.9), src/agent_actions.jl:32 */
+  double delta_energy;      /* agent.Δenergy */
+  double movement_cost;     /* agent.movement_cost */
+  double reproduction_prob; /* agent.reproduction_prob */
+  double attractor_x, attractor_y; /* model.attractor (griddims ./ 2, scripts/v0.2.jl:57); 2*a must be integral */
+  uint64_t seed;            /* Philox key */
+} abm_config;
+
+typedef struct abm_handle abm_handle;
+
+/* fills cfg with the defaults of scripts/v0.1.jl:36-46 (80x80, regrowth 30, Δenergy 4, repro 0.001, cost 1) */
+void abm_config_default(abm_config* cfg);
+
+/* replaces: AgentBasedModel(Sheep, GridSpace(dims; periodic, metric=:chebyshev); properties, rng, scheduler)
+ * scripts/v0.1.jl:49-64 */
+int abm_create(const abm_config* cfg, abm_handle** out);
+void abm_destroy(abm_handle* h);
+
+/* replaces: model.fully_grown / model.countdown / model.land_walkmap / model.elevation property arrays
+ * (scripts/v0.6.jl:78-94).  fully_grown, walkmap: one byte per cell (0/1); walkmap and elevation may be NULL
+ * (all walkable / flat).  countdown must be in 0..126, elevation in -32768..32767. */
+int abm_set_grid(abm_handle* h, const uint8_t* fully_grown, const int64_t* countdown, const uint8_t* walkmap,
+                 const int64_t* elevation);
+
+/* replaces: add_agent!/add_agent_pos! loops (scripts/v0.1.jl:67-70, scripts/v0.6.jl:104-118).  ids unique,
+ * 1 <= id < next_id <= 2^32-1; next_id = model.maxid[] + 1 (Agents.nextid). */
+int abm_set_agents(abm_handle* h, int64_t n, const int64_t* id, const int64_t* x, const int64_t* y,
+                   const double* energy, int64_t next_id);
+
+/* replaces: model.behav[1], model.behav_counter[1] (scripts/v0.4.jl:69-71,97) and the tick the RNG is keyed by */
+int abm_set_global_state(abm_handle* h, int64_t tick, int64_t behav, int64_t behav_counter);
+int abm_get_global_state(abm_handle* h, int64_t* tick, int64_t* behav, int64_t* behav_counter, int64_t* next_id);
+
+/* w[k] = exp(-sqrt(k)/3), k = 0 .. 2*(visual_distance+1)^2, computed by the HOST's exp so that the device
+ * only does IEEE add/div/compare (reference: f(x) = exp(-x / 3), src/agent_actions.jl:319).  When never
+ * called, the library fills the table with the C library's exp. */
+int abm_set_weight_lut(abm_handle* h, const double* w, int32_t n);
+
+/* replaces: Agents.step!(model, agent_step!, model_step!, n) — n ticks of { agent_step! for every agent in id
+ * order (src/agent_actions.jl:29-69); model_step! (src/model_actions.jl:18-30) }.  Synchronous. */
+int abm_step(abm_handle* h, int64_t n_ticks);
+
+/* replaces: nagents(model) */
+int abm_count_agents(abm_handle* h, int64_t* n);
+
+/* replaces: reading model[id].pos / .energy for all agents, in id order.  *n_inout: capacity in, count out. */
+int abm_get_agents(abm_handle* h, int64_t* n_inout, int64_t* id, int64_t* x, int64_t* y, double* energy);
+
+/* replaces: reading model.fully_grown / model.countdown (e.g. src/plotting.jl:27-57).  Either may be NULL. */
+int abm_get_grid(abm_handle* h, uint8_t* fully_grown, int64_t* countdown);
+
+/* replaces: adata/mdata aggregation inside Agents.run! (scripts/v0.6.jl:204-210) */
+int abm_reduce(abm_handle* h, int32_t what, double* out);
+
+/* replaces: plan_route!(agent, dest, model.pathfinder) for a batch of agents (src/agent_actions.jl:217-221;
+ * Agents.Pathfinding.find_path).  goal coordinates 1-based.  Existing routes of these agents are overwritten;
+ * an unreachable goal leaves the agent without a route. */
+int abm_plan_routes(abm_handle* h, int64_t b, const int64_t* agent_id, const int64_t* goal_x,
+                    const int64_t* goal_y);
+
+/* replaces: model.pathfinder.agent_paths[id] (Agents.Pathfinding).  CSR output: path of agent_id[i] is
+ * (px,py)[offset[i] .. offset[i+1]), 1-based cells, first element = next cell to move to; the start cell is
+ * excluded.  offset has b+1 entries; *cells_inout: capacity of px/py in, total cells out.  cost (nullable)
+ * receives the g-cost of the goal at planning time, or -1 when there is no route. */
+int abm_get_paths(abm_handle* h, int64_t b, const int64_t* agent_id, int64_t* offset, int64_t* cells_inout,
+                  int64_t* px, int64_t* py, int64_t* cost);
+
+/* device timing of the last abm_step in milliseconds: out[0] total, out[1] agent phase, out[2] grass phase,
+ * out[3] resolution rounds (count), out[4] kernels launched, out[5] A* expansions of the last plan call */
+int abm_get_timing(abm_handle* h, double* out, int32_t n);
+
+/* message for the last failing call on h (or on creation when h == NULL); valid until the next call */
+const char* abm_last_error(abm_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABM_H_ */
