@@ -80,6 +80,8 @@ SIGNATURES = {
     "plan_routes": (C.c_int, [_P, C.c_int64, _I64P, _I64P, _I64P]),
     "get_paths": (C.c_int, [_P, C.c_int64, _I64P, _I64P, _I64P, _I64P, _I64P, _I64P]),
     "get_timing": (C.c_int, [_P, _F64P, C.c_int32]),
+    "set_profiling": (C.c_int, [_P, C.c_int32]),
+    "get_kernel_stat": (C.c_int, [_P, C.c_int32, C.c_char_p, C.c_int32, _F64P, _I64P, _I64P]),
     "last_error": (C.c_char_p, [_P]),
 }
 
@@ -228,7 +230,24 @@ class Engine:
     def timing(self):
         out = np.zeros(8, np.float64)
         self._ck(self.lib.fn["get_timing"](self.h, _ptr(out, _F64P), out.size))
-        return dict(ms_total=out[0], ms_agents=out[1], ms_grass=out[2], rounds=out[3], launches=out[4], astar_expansions=out[5])
+        return dict(ms_total=out[0], ms_agents=out[1], ms_grass=out[2], rounds=out[3], launches=out[4], astar_expansions=out[5],
+                    agent_updates=out[6])
+
+    def set_profiling(self, on=True):
+        self._ck(self.lib.fn["set_profiling"](self.h, int(bool(on))))
+
+    def kernel_stats(self):
+        """Per-kernel device time of the last step(): {name: dict(ms, launches, units)}."""
+        out, i = {}, 0
+        while True:
+            name = C.create_string_buffer(64)
+            ms, ln, un = C.c_double(), C.c_int64(), C.c_int64()
+            rc = self.lib.fn["get_kernel_stat"](self.h, i, name, 64, C.byref(ms), C.byref(ln), C.byref(un))
+            if rc == ABM_E_SMALL:
+                return out
+            self._ck(rc)
+            out[name.value.decode()] = dict(ms=ms.value, launches=ln.value, units=un.value)
+            i += 1
 
     def snapshot(self):
         """Full observable state, for parity comparisons."""

@@ -165,6 +165,68 @@ struct Timer {
 #endif
 };
 
+/* per-kernel device timing of the last abm_step (CUDA events on the handle's stream), for bench.py's roofline */
+struct KStat { std::string name; double ms = 0; uint64_t launches = 0, units = 0; };
+struct Prof {
+  bool on = false;
+  std::vector<KStat> stats;
+#ifndef ABM_EMU
+  struct Rec { int idx; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() { if (pool.empty()) { cudaEvent_t e; cudaEventCreate(&e); return e; } cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+#endif
+  int index(const char* name) {
+    for (size_t i = 0; i < stats.size(); ++i) if (stats[i].name == name) return (int)i;
+    KStat k; k.name = name; stats.push_back(k); return (int)stats.size() - 1;
+  }
+  void reset() { for (size_t i = 0; i < stats.size(); ++i) { stats[i].ms = 0; stats[i].launches = 0; stats[i].units = 0; } }
+  void begin(abm_stream_t s, const char* name, uint64_t units, uint64_t launches) {
+    const int i = index(name);
+    stats[i].launches += launches; stats[i].units += units;
+#ifndef ABM_EMU
+    if (!on) return;
+    if (recs.size() >= 8192) collect();
+    Rec r; r.idx = i; r.a = get(); r.b = get();
+    cudaEventRecord(r.a, s);
+    recs.push_back(r);
+#else
+    (void)s;
+#endif
+  }
+  void end(abm_stream_t s) {
+#ifndef ABM_EMU
+    if (on && !recs.empty()) cudaEventRecord(recs.back().b, s);
+#else
+    (void)s;
+#endif
+  }
+  void collect() {
+#ifndef ABM_EMU
+    for (size_t i = 0; i < recs.size(); ++i) {
+      float f = 0;
+      cudaEventSynchronize(recs[i].b);
+      cudaEventElapsedTime(&f, recs[i].a, recs[i].b);
+      stats[recs[i].idx].ms += f;
+      pool.push_back(recs[i].a); pool.push_back(recs[i].b);
+    }
+    recs.clear();
+#endif
+  }
+  void destroy() {
+#ifndef ABM_EMU
+    collect();
+    for (size_t i = 0; i < pool.size(); ++i) cudaEventDestroy(pool[i]);
+    pool.clear();
+#endif
+  }
+};
+struct ProfScope {
+  Prof& p; abm_stream_t s;
+  ProfScope(Prof& p_, abm_stream_t s_, const char* name, uint64_t units, uint64_t launches = 1) : p(p_), s(s_) { p.begin(s, name, units, launches); }
+  ~ProfScope() { p.end(s); }
+};
+
 enum { CTR_PEND_A = 0, CTR_PEND_B = 1, CTR_BIRTHS = 2, CTR_ERR = 3, CTR_RED_LO = 4, CTR_RED_HI = 5, CTR_WORDS = 8 };
 
 }  // namespace
@@ -187,8 +249,9 @@ struct abm_handle {
   uint64_t n = 0, next_id = 1, tick = 0;
   int64_t behav = 0, behav_counter = 0;
   bool grid_set = false, agents_set = false;
-  double t_total = 0, t_agents = 0, t_grass = 0, rounds = 0, launches = 0, expansions = 0;
+  double t_total = 0, t_agents = 0, t_grass = 0, rounds = 0, launches = 0, expansions = 0, updates = 0;
   Timer tm_total;
+  Prof prof;
   std::string err;
 };
 
@@ -323,7 +386,7 @@ static int tick_once(abm_handle* h) {
     pb.v = v;
     pb.pending = (uint32_t*)h->pend[0].p;
     pb.pending_count = ctr + CTR_PEND_A;
-    launch_foreach(h->stream, pb, n);
+    { ProfScope ps(h->prof, h->stream, "propose", n); launch_foreach(h->stream, pb, n); }
     if ((rc = check_launch(h, "propose"))) return rc;
   }
   /* rank-ordered fixed point over the agents whose outcome depends on lower ids */
@@ -341,7 +404,7 @@ static int tick_once(abm_handle* h) {
       rb.in_count = ctr + (in ? CTR_PEND_B : CTR_PEND_A);
       rb.out = (uint32_t*)h->pend[in ^ 1].p;
       rb.out_count = ctr + (in ? CTR_PEND_A : CTR_PEND_B);
-      launch_foreach(h->stream, rb, cnt);
+      { ProfScope ps(h->prof, h->stream, "resolve", cnt); launch_foreach(h->stream, rb, cnt); }
       if ((rc = check_launch(h, "resolve"))) return rc;
       if ((rc = read_counters(h))) return rc;
       const uint64_t left = h->h_counters[in ? CTR_PEND_A : CTR_PEND_B];
@@ -357,7 +420,7 @@ static int tick_once(abm_handle* h) {
   /* commit: eat / energy / reproduce and the counting sort into next tick's order */
   const int nxt = h->cur ^ 1;
   uint32_t* new_start = (uint32_t*)h->cell_start[nxt].p;
-  ABM_CK(h, dev_memset(new_start, 0, (gt + 1) * 4, h->stream));
+  { ProfScope ps(h->prof, h->stream, "memset_cell_counts", gt + 1); ABM_CK(h, dev_memset(new_start, 0, (gt + 1) * 4, h->stream)); }
   const uint64_t words = bitmap_words(h->next_id);
   const bool repro = h->cfg.reproduce != 0;
   if (repro) {
@@ -372,11 +435,11 @@ static int tick_once(abm_handle* h) {
     cb.births = (BirthRec*)h->births.p;
     cb.birth_count = ctr + CTR_BIRTHS;
     cb.new_cell = (uint32_t*)h->new_cell.p;
-    launch_foreach(h->stream, cb, n);
+    { ProfScope ps(h->prof, h->stream, "commit", n); launch_foreach(h->stream, cb, n); }
     if ((rc = check_launch(h, "commit"))) return rc;
   }
   if ((rc = ensure(h, h->scan_tmp, scan_tmp_words(gt + 1) * 4))) return rc;
-  ABM_CK(h, scan_exclusive_u32(h->stream, new_start, gt + 1, (uint32_t*)h->scan_tmp.p));
+  { ProfScope ps(h->prof, h->stream, "cell_scan", gt + 1, 3); ABM_CK(h, scan_exclusive_u32(h->stream, new_start, gt + 1, (uint32_t*)h->scan_tmp.p)); }
   if ((rc = read_counters(h))) return rc;
   if ((rc = device_error_to_code(h))) return rc;
   uint32_t n_new32 = 0;
@@ -393,7 +456,7 @@ static int tick_once(abm_handle* h) {
     sb.out_cell = (uint32_t*)h->cell[nxt].p;
     sb.out_id = (uint32_t*)h->id[nxt].p;
     sb.out_energy = (double*)h->energy[nxt].p;
-    launch_foreach(h->stream, sb, n);
+    { ProfScope ps(h->prof, h->stream, "scatter", n); launch_foreach(h->stream, sb, n); }
     if ((rc = check_launch(h, "scatter"))) return rc;
     if (nb > 0) {
       if ((rc = rank_prefix(h, words))) return rc;
@@ -408,7 +471,7 @@ static int tick_once(abm_handle* h) {
       bb.out_cell = sb.out_cell;
       bb.out_id = sb.out_id;
       bb.out_energy = sb.out_energy;
-      launch_foreach(h->stream, bb, nb);
+      { ProfScope ps(h->prof, h->stream, "birth_scatter", nb); launch_foreach(h->stream, bb, nb); }
       if ((rc = check_launch(h, "birth scatter"))) return rc;
     }
   }
@@ -419,13 +482,14 @@ static int tick_once(abm_handle* h) {
     gb.walkbits = (const uint32_t*)h->walkbits.p;
     gb.rt = (uint32_t)h->cfg.regrowth_time;
     gb.use_walk = h->cfg.walkmap_regrowth;
-    launch_foreach(h->stream, gb, gt / 16);
+    { ProfScope ps(h->prof, h->stream, "regrow", gt); launch_foreach(h->stream, gb, gt / 16); }
     if ((rc = check_launch(h, "regrow"))) return rc;
   }
   h->cur = nxt;
   h->n = n_new;
   h->next_id += nb;
   h->tick += 1;
+  h->updates += (double)n;
   return 0;
 }
 
@@ -481,6 +545,7 @@ void ABM_API(destroy)(abm_handle* h) {
   free(h->h_counters);
 #endif
   h->tm_total.destroy();
+  h->prof.destroy();
   delete h;
 }
 
@@ -767,6 +832,8 @@ int ABM_API(step)(abm_handle* h, int64_t n_ticks) {
   if (rc) return rc;
   const uint64_t l0 = launches_now();
   h->rounds = 0;
+  h->updates = 0;
+  h->prof.reset();
   h->tm_total.start(h->stream);
   for (int64_t t = 0; t < n_ticks; ++t) {
     if (h->tick >= 0xFFFFFFFFull) ABM_FAIL(h, ABM_E_CAPACITY, "tick counter exhausted");
@@ -775,6 +842,7 @@ int ABM_API(step)(abm_handle* h, int64_t n_ticks) {
   h->tm_total.stop(h->stream);
   ABM_CK(h, stream_sync(h->stream));
   h->t_total = h->tm_total.ms();
+  h->prof.collect();
   h->launches = (double)(launches_now() - l0);
   return ABM_OK;
 }
@@ -829,10 +897,27 @@ int ABM_API(get_paths)(abm_handle* h, int64_t, const int64_t*, int64_t*, int64_t
   ABM_FAIL(h, ABM_E_STATE, "abm_get_paths is not available in this build yet");
 }
 
+int ABM_API(set_profiling)(abm_handle* h, int32_t on) {
+  if (!h) return ABM_E_BADARG;
+  h->prof.on = on != 0;
+  return ABM_OK;
+}
+
+int ABM_API(get_kernel_stat)(abm_handle* h, int32_t idx, char* name, int32_t name_cap, double* ms, int64_t* launches, int64_t* units) {
+  if (!h || idx < 0) return ABM_E_BADARG;
+  if ((size_t)idx >= h->prof.stats.size()) return ABM_E_SMALL;
+  const KStat& k = h->prof.stats[idx];
+  if (name && name_cap > 0) { snprintf(name, (size_t)name_cap, "%s", k.name.c_str()); }
+  if (ms) *ms = k.ms;
+  if (launches) *launches = (int64_t)k.launches;
+  if (units) *units = (int64_t)k.units;
+  return ABM_OK;
+}
+
 int ABM_API(get_timing)(abm_handle* h, double* out, int32_t n) {
   if (!h || !out) return ABM_E_BADARG;
-  const double v[6] = {h->t_total, h->t_agents, h->t_grass, h->rounds, h->launches, h->expansions};
-  for (int i = 0; i < n; ++i) out[i] = i < 6 ? v[i] : 0.0;
+  const double v[7] = {h->t_total, h->t_agents, h->t_grass, h->rounds, h->launches, h->expansions, h->updates};
+  for (int i = 0; i < n; ++i) out[i] = i < 7 ? v[i] : 0.0;
   return ABM_OK;
 }
 

@@ -50,8 +50,24 @@ def walkmap_from_elevation(elevation, water_level: int = 1, mountain_level: int 
     return ((elevation > water_level) & (elevation < mountain_level)).astype(np.uint8)
 
 
+def has_walkable_neighbour(walkmap, periodic: bool = True):
+    """Cells with at least one walkable Moore neighbour (random_walkmap throws on the others, rand(1:0))."""
+    w = np.asarray(walkmap).astype(bool)
+    out = np.zeros_like(w)
+    src = w if periodic else np.pad(w, 1)
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            if dx == 0 and dy == 0:
+                continue
+            if periodic:
+                out |= np.roll(np.roll(src, dy, 0), dx, 1)
+            else:
+                out |= src[1 + dy: 1 + dy + w.shape[0], 1 + dx: 1 + dx + w.shape[1]]
+    return out
+
+
 def make_world(nx: int, ny: int, n_sheep: int, seed: int = 321, regrowth_time: int = 30, delta_energy: int = 4,
-               walkmap=None, distinct_cells: bool = False):
+               walkmap=None, distinct_cells: bool = False, periodic: bool = True):
     """Agents (ids 1..n, 1-based positions, energies 0..5Δ-1) and grass arrays."""
     rng = _rng(seed)
     energy = rng.integers(0, delta_energy * 5, n_sheep).astype(np.float64)
@@ -61,7 +77,9 @@ def make_world(nx: int, ny: int, n_sheep: int, seed: int = 321, regrowth_time: i
         else:
             lin = rng.integers(0, nx * ny, n_sheep)
     else:
-        ok = np.flatnonzero(np.asarray(walkmap).reshape(-1))
+        # random_walkable: uniform over walkable cells; cells whose 8 neighbours are all blocked are left out
+        # because the reference's random_walkmap throws there
+        ok = np.flatnonzero((np.asarray(walkmap).astype(bool) & has_walkable_neighbour(walkmap, periodic)).reshape(-1))
         lin = ok[rng.integers(0, ok.size, n_sheep)]  # random_walkable: uniform over walkable cells
     x = (lin % nx).astype(np.int64) + 1
     y = (lin // nx).astype(np.int64) + 1

@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the per-tick stepping path (BASELINE.json metric: agent-updates/s).
+
+Workload (BASELINE.json configs[1], "C2"): v0.3 rules — RANDOM_WALK_GREGARIOUS, visual_distance = 3,
+prob_random_walk = 0.9, eat + reproduce + grass regrowth — on a periodic 4096 x 4096 GridSpace with 2^22 sheep,
+synthetic seeded world (abm_b200.worlds).  A "step" is one tick: every agent's agent_step! in id order, then
+model_step!.  At N > 1 every rank steps its own world of that size (weak scaling, no data-path collective yet).
+
+  value      agent-updates/s with the world resident in HBM; per-tick CUDA-event time on the library's stream,
+             L2 flushed (256 MiB write) between ticks, max over ranks.
+  e2e        the same metric through the C ABI with HOST buffers: per tick abm_set_grid + abm_set_agents (pinned
+             host -> device), abm_step(1), abm_get_agents + abm_get_grid (device -> pinned host).
+  roofline   dominant kernel: algorithmic bytes (A = 36 B per agent-update, C = 2 B per cell-update,
+             +1 B per cell for the gregarious occupancy read) / its CUDA-event time, against MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference: the CPU restatement of the reference (oracle/, sequential like Agents.jl's
+             step!) on a bounded sample of the same workload.  The oracle is only the timed baseline here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+A_BYTES, C_BYTES, C_BYTES_GREG = 36.0, 2.0, 3.0
+WORKLOADS = {
+    # name: (walk_type, terrain, extra config)
+    "C2": dict(walk_type=2, terrain=False, cfg=dict(visual_distance=3, prob_random_walk=0.9, reproduction_prob=0.001),
+               desc="v0.3 RANDOM_WALK_GREGARIOUS r=3, periodic {n}x{n} grid, {a} sheep (BASELINE.json configs[1])"),
+    "C3": dict(walk_type=4, terrain=True, cfg=dict(walkmap_regrowth=1, reproduction_prob=0.004),
+               desc="v0.5 RANDOM_WALKMAP + walkmap regrowth, periodic {n}x{n} terrain, {a} sheep (BASELINE.json configs[2])"),
+    "C1": dict(walk_type=0, terrain=False, cfg=dict(reproduction_prob=0.001),
+               desc="v0.1 RANDOM_WALK, {n}x{n} grid, {a} sheep"),
+}
+
+
+def make_world(workload, size, agents, seed=321):
+    from abm_b200 import worlds
+    wl = WORKLOADS[workload]
+    wm = el = None
+    if wl["terrain"]:
+        el = worlds.make_terrain(size, size, seed=seed + 1)
+        wm = worlds.walkmap_from_elevation(el)
+    w = worlds.make_world(size, size, agents, seed=seed, walkmap=wm, periodic=True)
+    w["walkmap"], w["elevation"] = wm, el
+    cfg = dict(nx=size, ny=size, periodic=1, walk_type=wl["walk_type"], seed=seed)
+    cfg.update(wl["cfg"])
+    return cfg, w
+
+
+def load(lib, cfg, w, device=0):
+    e = lib.create(lib.default_config(device=device, **cfg))
+    e.set_grid(w["fully_grown"], w["countdown"], w.get("walkmap"), w.get("elevation"))
+    e.set_agents(w["ids"], w["x"], w["y"], w["energy"])
+    return e
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([t.strip() for t in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def oracle_lib():
+    from abm_b200 import build, capi
+    return capi.CLib(build.build_oracle(), "oracle_")
+
+
+def time_oracle(workload, size, agents, ticks, warm=1):
+    """agent-updates/s of the CPU restatement (sequential, 1 thread — Agents.jl's step! is serial)."""
+    lib = oracle_lib()
+    cfg, w = make_world(workload, size, agents)
+    e = load(lib, cfg, w)
+    e.step(warm)
+    upd, t0 = 0, time.perf_counter()
+    for _ in range(ticks):
+        upd += e.count_agents()
+        e.step(1)
+    dt = time.perf_counter() - t0
+    e.close()
+    return upd / dt, dt, upd
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    size, agents = args.ref_size, args.ref_size * args.ref_size // 4
+    wl = WORKLOADS[args.workload]
+    # one "step" = one tick of the bounded sample; W warm-up ticks, K timed ticks
+    lib = oracle_lib()
+    cfg, w = make_world(args.workload, size, agents)
+    e = load(lib, cfg, w)
+    e.step(args.warmup)
+    upd, t0 = 0, time.perf_counter()
+    for _ in range(args.steps):
+        upd += e.count_agents()
+        e.step(1)
+    dt = time.perf_counter() - t0
+    v = upd / dt
+    sample = f"{size}x{size} grid, {agents} sheep, same rules/density as the {args.size}x{args.size} workload, {args.steps} ticks"
+    print(json.dumps({
+        "impl": "reference", "metric": "agent_updates_per_s", "value": v, "unit": "agent-updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32 cells / f64 energy", "data": "synthetic",
+        "config": {"workload": wl["desc"].format(n=args.size, a=args.size * args.size // 4), "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "agent-updates/s", "cores": 1, "kind": "port", "sample": sample,
+                         "note": "C++ restatement of the reference rules + Agents.jl semantics (oracle/); Julia is not installed; Agents.jl step! is serial, hence 1 thread"},
+        "e2e": {"value": v, "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--ref-size", type=int, default=1024)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed ticks")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from abm_b200 import build, capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libabm has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    lib = capi.CLib(build.LIBABM if os.path.exists(build.LIBABM) else build.build_libabm(), "abm_")
+    size, agents = args.size, args.size * args.size // 4
+    wl = WORKLOADS[args.workload]
+    cfg, w = make_world(args.workload, size, agents, seed=321 + rank)
+    eng = load(lib, cfg, w, device=local)
+    eng.set_profiling(True)
+    G = size * size
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def tick():
+        if flush is not None:
+            flush.fill_(1)
+            torch.cuda.synchronize()
+        eng.step(1)
+        return eng.timing(), eng.kernel_stats()
+
+    for _ in range(args.warmup):
+        tick()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    ms = upd = launches = rounds = 0.0
+    kstats = {}
+    for _ in range(args.steps):
+        t, ks = tick()
+        ms += t["ms_total"]; upd += t["agent_updates"]; launches += t["launches"]; rounds += t["rounds"]
+        for k, v in ks.items():
+            a = kstats.setdefault(k, dict(ms=0.0, launches=0, units=0))
+            a["ms"] += v["ms"]; a["launches"] += v["launches"]; a["units"] += v["units"]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.finish()
+
+    tt = torch.tensor([ms, upd, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_max, upd_all, launches_all = float(mx[0]), float(sm[1]), float(sm[2])
+    else:
+        ms_max, upd_all, launches_all = ms, upd, launches
+    value = upd_all / (ms_max * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy(), t
+    keep = []
+    ids, x, y, en = eng.get_agents()
+    fg, cd = eng.get_grid()
+    host = {}
+    for k, a in (("ids", ids), ("x", x), ("y", y), ("energy", en), ("fg", fg), ("cd", cd)):
+        host[k], t = pinned(a); keep.append(t)
+    wm = el = None
+    if w.get("walkmap") is not None:
+        wm, t = pinned(w["walkmap"]); keep.append(t)
+        el, t = pinned(w["elevation"]); keep.append(t)
+    st = eng.get_global_state()
+    e2e_upd = h2d = d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        n = host["ids"].size
+        eng.set_grid(host["fg"], host["cd"], wm, el)
+        eng.set_agents(host["ids"], host["x"], host["y"], host["energy"], st["next_id"])
+        h2d += G * 9 + (G * 9 if wm is not None else 0) + n * 32
+        eng.step(1)
+        e2e_upd += n
+        ids, x, y, en = eng.get_agents()
+        fg, cd = eng.get_grid()
+        st = eng.get_global_state()
+        d2h += ids.size * 32 + G * 9
+        for k, a in (("ids", ids), ("x", x), ("y", y), ("energy", en), ("fg", fg), ("cd", cd)):
+            host[k], t = pinned(a) if a.size != host[k].size else (host[k], None)
+            if t is None:
+                np.copyto(host[k], a)
+            else:
+                keep.append(t)
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    e2 = torch.tensor([e2e_dt, e2e_upd], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = e2.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = e2.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        e2e_value = float(sm[1]) / float(mx[0])
+    else:
+        e2e_value = e2e_upd / e2e_dt
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        cell_b = C_BYTES_GREG if wl["walk_type"] == 2 else C_BYTES
+        dom = max(kstats, key=lambda k: kstats[k]["ms"]) if kstats else None
+        roof = None
+        if dom:
+            d = kstats[dom]
+            per_cell = dom in ("regrow", "cell_scan", "memset_cell_counts")
+            # the agent kernels jointly move A bytes per agent-update, the cell sweep C bytes per cell; the dominant kernel
+            # is charged the whole per-unit figure of its kind (the other kernels of the tick are overhead on top)
+            alg = (cell_b * G * args.steps) if per_cell else (A_BYTES * upd)
+            ach = alg / (d["ms"] * 1e-3) / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tp):
+                traffic = json.load(open(tp)).get(dom)
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "peak_source": peak_src, "launches_per_tick": d["launches"] / args.steps, "avg_launch_us": 1e3 * d["ms"] / max(d["launches"], 1),
+                    "algorithmic_bytes_per_tick": alg / args.steps}
+        tick_bytes = A_BYTES * upd / args.steps + cell_b * G
+        tick_ach = tick_bytes / (ms / args.steps * 1e-3) / 1e9
+        out = {
+            "metric": "agent_updates_per_s", "value": value, "unit": "agent-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32 cells / f64 energy", "data": "synthetic",
+            "config": {"workload": wl["desc"].format(n=size, a=agents), "grid": [size, size], "agents": agents, "ticks": args.steps,
+                       "l2": "flushed between ticks (256 MiB device write)" if flush is not None else "not flushed",
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent worlds, one per rank (no exchange)",
+                       "cells_per_s": G * world * args.steps / (ms_max * 1e-3), "resolution_rounds_per_tick": rounds / args.steps},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "agent-updates/s", "h2d_bytes_per_step": h2d // args.e2e_steps, "d2h_bytes_per_step": d2h // args.e2e_steps,
+                    "steps": args.e2e_steps, "ms_per_step": 1e3 * e2e_dt / args.e2e_steps},
+            "gpu_launches": int(launches_all),
+            "roofline": roof,
+            "roofline_tick": {"bound": "hbm", "achieved": tick_ach, "peak": peak, "unit": "GB/s", "frac": tick_ach / peak,
+                              "algorithmic_bytes_per_tick": tick_bytes, "note": "whole tick (all kernels): A*N + C*G over the tick's device time"},
+            "kernels": {k: dict(ms_per_tick=v["ms"] / args.steps, launches_per_tick=v["launches"] / args.steps) for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])},
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rs = args.ref_size
+            v, dt, u = time_oracle(args.workload, rs, rs * rs // 4, ticks=max(2, int(12e6 / (rs * rs // 4))))
+            out["cpu_baseline"] = {"value": v, "unit": "agent-updates/s", "cores": 1, "kind": "port",
+                                   "sample": f"{rs}x{rs} grid, {rs * rs // 4} sheep, same rules and density, {u} agent-updates in {dt:.1f} s",
+                                   "note": "oracle/ C++ restatement, sequential like Agents.jl step!; Julia not installed on the box"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

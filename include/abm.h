@@ -162,8 +162,16 @@ int abm_get_paths(abm_handle* h, int64_t b, const int64_t* agent_id, int64_t* of
                   int64_t* px, int64_t* py, int64_t* cost);
 
 /* device timing of the last abm_step in milliseconds: out[0] total, out[1] agent phase, out[2] grass phase,
- * out[3] resolution rounds (count), out[4] kernels launched, out[5] A* expansions of the last plan call */
+ * out[3] resolution rounds (count), out[4] kernels launched, out[5] A* expansions of the last plan call,
+ * out[6] agent-updates performed (sum over ticks of the population at tick start) */
 int abm_get_timing(abm_handle* h, double* out, int32_t n);
+
+/* no reference counterpart (the reference has no profiler): when on, every kernel of abm_step is bracketed by CUDA
+ * events on the handle's stream; abm_get_kernel_stat(idx = 0, 1, ...) then returns per-kernel totals of the last
+ * abm_step (ABM_E_SMALL past the last kernel).  `units` = agents or cells the launches processed. */
+int abm_set_profiling(abm_handle* h, int32_t on);
+int abm_get_kernel_stat(abm_handle* h, int32_t idx, char* name, int32_t name_cap, double* ms, int64_t* launches,
+                        int64_t* units);
 
 /* message for the last failing call on h (or on creation when h == NULL); valid until the next call */
 const char* abm_last_error(abm_handle* h);

@@ -1,0 +1,69 @@
+"""The C-ABI library loads and exports every symbol include/abm.h declares; argument checking that needs no GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, build, capi
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "abm.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(abm_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_the_boundary():
+    names = _declared()
+    for must in ("abm_create", "abm_destroy", "abm_set_grid", "abm_set_agents", "abm_step", "abm_get_agents", "abm_get_grid",
+                 "abm_reduce", "abm_plan_routes", "abm_get_paths", "abm_last_error", "abm_set_weight_lut"):
+        assert must in names
+
+
+def test_libabm_exports_every_declared_symbol():
+    path = build.build_libabm()
+    dll = C.CDLL(path)
+    for name in _declared():
+        assert hasattr(dll, name), f"{name} declared in include/abm.h but not exported by libabm.so"
+
+
+def test_binding_covers_every_declared_symbol():
+    assert sorted("abm_" + n for n in capi.SIGNATURES) == _declared()
+
+
+def test_config_struct_layout_matches_header():
+    lib = capi.CLib(build.build_libabm(), "abm_")
+    cfg = lib.default_config()
+    assert cfg.struct_size == C.sizeof(capi.AbmConfig) == 120
+    assert (cfg.nx, cfg.ny, cfg.regrowth_time, cfg.seed) == (80, 80, 30, 321)  # scripts/v0.1.jl:36-46
+
+
+def test_bad_config_is_rejected_without_a_gpu():
+    lib = capi.CLib(build.build_libabm(), "abm_")
+    for kw in (dict(nx=0), dict(walk_type=9), dict(regrowth_time=500), dict(walk_type=2, periodic=0)):
+        with pytest.raises(capi.AbmError) as ei:
+            lib.create(lib.default_config(**kw))
+        assert ei.value.code == capi.ABM_E_BADARG
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device abm_create fails loudly with ABM_E_CUDA (the product has no CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = capi.CLib(build.build_libabm(), "abm_")
+    with pytest.raises(capi.AbmError) as ei:
+        lib.create(lib.default_config())
+    assert ei.value.code == capi.ABM_E_CUDA
+
+
+def test_package_never_loads_test_libraries():
+    """Only tests/bench may touch oracle/ or tests/emu: the package sources must not name them as load targets."""
+    pkg = os.path.join(ROOT, "animal-movement-abm_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py") and fn != "build.py":
+            s = open(os.path.join(pkg, fn)).read()
+            for token in ("LIBORACLE", "LIBEMU", "build_oracle", "build_emu", "oracle_", "emu_"):
+                code = "\n".join(l for l in s.split("\n") if "``" not in l)  # docstring bullet lines name the prefixes
+                assert token not in code, (fn, token)

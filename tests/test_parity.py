@@ -1,0 +1,133 @@
+"""Trajectory parity on the named cases of tests/cases.py.
+
+  oracle  vs committed golden fixtures     (not gpu)  — the oracle has not silently changed
+  emu     vs oracle, tick by tick           (not gpu)  — the engine's kernel bodies + host orchestration, on the host
+  libabm  vs golden and vs oracle           (gpu)      — the product, through the C ABI
+
+Bar: bit-exact ids / cells / grass / countdown / global state; energy rtol 1e-6 (observed exact).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from cases import CASES, build_case
+from conftest import ROOT, assert_same_state, load_case
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    snaps = {}
+    for t in meta["ticks"]:
+        s = {k: z[f"t{t}_{k}"] for k in ("ids", "x", "y", "energy", "fully_grown", "countdown")}
+        s["x"], s["y"], s["countdown"] = s["x"].astype(np.int64), s["y"].astype(np.int64), s["countdown"].astype(np.int64)
+        for k in ("tick", "behav", "behav_counter", "next_id"):
+            s[k] = int(z[f"t{t}_{k}"])
+        snaps[t] = s
+    return snaps
+
+
+# walk types the CUDA engine does not implement yet (ALTERNATED_WALK + A*): the engine refuses them loudly
+ENGINE_PENDING = {"v0.4_alternated", "v0.6_alternated_penalty", "dense_alternated"}
+
+
+def _run_against_golden(lib, name):
+    if lib.prefix != "oracle_" and name in ENGINE_PENDING:
+        pytest.xfail("ALTERNATED_WALK not implemented in the engine yet")
+    cfgkw, w, state, ticks = build_case(name)
+    e = load_case(lib, cfgkw, w)
+    if state:
+        e.set_global_state(*state)
+    gold = _golden(name)
+    done = 0
+    for t in ticks:
+        e.step(t - done)
+        done = t
+        assert_same_state(e.snapshot(), gold[t], f"{name} @tick {t}")
+    e.close()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_golden(oracle, name):
+    _run_against_golden(oracle, name)
+
+
+EMU_CASES = [n for n in sorted(CASES) if n != "C1_v0.1_100x100"]  # C1's 1000 ticks are covered on the GPU
+
+
+@pytest.mark.parametrize("name", EMU_CASES)
+def test_emulated_engine_matches_golden(emu, name):
+    _run_against_golden(emu, name)
+
+
+@pytest.mark.parametrize("name", ["dense_rw", "dense_gregarious_r3", "dense_attractor", "dense_walkmap", "dense_alternated"])
+@pytest.mark.parametrize("shuffle", [1, 2, 3])
+def test_emulated_engine_is_schedule_independent(emu, oracle, name, shuffle):
+    """The emulation visits thread indices in a shuffled order; any order must give the sequential result."""
+    if name in ENGINE_PENDING:
+        pytest.xfail("ALTERNATED_WALK not implemented in the engine yet")
+    emu.dll.emu_set_shuffle_seed(1000 * shuffle + 7)
+    cfgkw, w, state, ticks = build_case(name)
+    a, b = load_case(oracle, cfgkw, w), load_case(emu, cfgkw, w)
+    if state:
+        a.set_global_state(*state)
+        b.set_global_state(*state)
+    for t in range(12):
+        a.step(1)
+        b.step(1)
+        assert_same_state(b.snapshot(), a.snapshot(), f"{name} shuffle {shuffle} tick {t}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_gpu_matches_golden(libabm, name):
+    _run_against_golden(libabm, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wt,per,terr,n,nx,ny,extra", [
+    (0, 1, 0, 20000, 256, 192, {}),
+    (0, 0, 0, 20000, 250, 190, {}),
+    (1, 0, 0, 20000, 256, 192, dict(prob_random_walk=0.6)),
+    (2, 1, 0, 16000, 256, 256, dict(visual_distance=3)),
+    (2, 1, 0, 9000, 200, 130, dict(visual_distance=5)),
+    (4, 1, 1, 20000, 256, 256, dict(walkmap_regrowth=1)),
+    (3, 1, 1, 6000, 192, 160, dict(counter=50, astar_metric=1, astar_penalty=1)),
+])
+def test_gpu_matches_oracle_tick_by_tick(libabm, oracle, wt, per, terr, n, nx, ny, extra):
+    """Mid-size seeded worlds (the oracle needs seconds): every tick compared."""
+    from conftest import make_case
+    if wt == 3:
+        pytest.xfail("ALTERNATED_WALK not implemented in the engine yet")
+    kw = dict(reproduction_prob=0.02, regrowth_time=6, delta_energy=3.0)
+    kw.update(extra)
+    cfgkw, w = make_case(nx, ny, n, wt, per, terrain=bool(terr), seed=99, **kw)
+    a, b = load_case(oracle, cfgkw, w), load_case(libabm, cfgkw, w)
+    if wt == 3:
+        a.set_global_state(0, 0, kw["counter"])
+        b.set_global_state(0, 0, kw["counter"])
+    for t in range(20):
+        a.step(1)
+        b.step(1)
+        assert_same_state(b.snapshot(), a.snapshot(), f"wt {wt} tick {t}")
+    a.step(30)
+    b.step(30)
+    assert_same_state(b.snapshot(), a.snapshot(), f"wt {wt} tick 50")
+
+
+@pytest.mark.gpu
+def test_gpu_weight_lut_is_honoured(libabm, oracle):
+    """abm_set_weight_lut: the host's exp table decides the wsample index; a distorted table must change both sides alike."""
+    from conftest import make_case
+    from abm_b200 import worlds
+    cfgkw, w = make_case(96, 96, 4000, 2, 1, seed=4, visual_distance=3, prob_random_walk=0.2)
+    lut = worlds.weight_lut(3)
+    lut[1:] *= 0.5
+    a, b = load_case(oracle, cfgkw, w, lut), load_case(libabm, cfgkw, w, lut)
+    a.step(10)
+    b.step(10)
+    assert_same_state(b.snapshot(), a.snapshot(), "distorted LUT")
