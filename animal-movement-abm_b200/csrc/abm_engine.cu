@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "abm_kernels.h"
+#include "abm_astar.h"
 
 #ifdef ABM_EMU
 #define ABM_API(name) emu_##name
@@ -227,7 +228,8 @@ struct ProfScope {
   ~ProfScope() { p.end(s); }
 };
 
-enum { CTR_PEND_A = 0, CTR_PEND_B = 1, CTR_BIRTHS = 2, CTR_ERR = 3, CTR_RED_LO = 4, CTR_RED_HI = 5, CTR_WORDS = 8 };
+enum { CTR_PEND_A = 0, CTR_PEND_B = 1, CTR_BIRTHS = 2, CTR_ERR = 3, CTR_RED_LO = 4, CTR_RED_HI = 5, CTR_PLANS = 6, CTR_ROUTE_SLOTS = 7,
+       CTR_EXP_LO = 8, CTR_EXP_HI = 9, CTR_WORDS = 12 };
 
 }  // namespace
 
@@ -244,6 +246,12 @@ struct abm_handle {
   DevBuf state, slot, new_cell, pend[2], births;
   DevBuf grass, walkbits, elev;
   DevBuf bits, bits_prefix, scan_tmp, stage, lut, greg_order, counters, partials;
+  /* ALTERNATED_WALK / A*: id-order ranks, behaviour segments, plan requests, route followers, the route store */
+  DevBuf rank, by_rank, seg_behav, plan_agent, plan_goal, remote_head, remote_next, remote_dest, idx_of_id;
+  DevBuf as_g, as_meta, as_heap, as_src, as_dst, as_id, as_status, as_len, as_cost, as_off;
+  DevBuf rt_slot_of_id, rt_off, rt_len, rt_pos, rt_cost, rt_pool;
+  uint64_t as_slots = 0, as_heap_cap = 0, rt_slots_cap = 0, rt_pool_used = 0, rt_ids_cap = 0;
+  uint32_t as_gen = 0;
   uint32_t* h_counters = nullptr; /* host mirror (pinned on CUDA) */
 
   uint64_t n = 0, next_id = 1, tick = 0;
@@ -320,6 +328,11 @@ static View make_view(abm_handle* h) {
   v.lut = (const double*)h->lut.p;
   v.greg_order = (const uint8_t*)h->greg_order.p;
   v.err = (uint32_t*)h->counters.p + CTR_ERR;
+  if (h->cfg.walk_type == ABM_ALTERNATED_WALK) {
+    v.remote_head = (uint32_t*)h->remote_head.p;
+    v.remote_next = (uint32_t*)h->remote_next.p;
+    v.remote_dest = (uint32_t*)h->remote_dest.p;
+  }
   return v;
 }
 
@@ -371,6 +384,211 @@ static int ensure_soa(abm_handle* h, int which, uint64_t n) {
   return 0;
 }
 
+
+/* grows a buffer keeping its contents (new bytes zeroed) */
+static int grow_keep(abm_handle* h, DevBuf& b, size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (b.bytes >= bytes && b.p) return 0;
+  void* np_ = nullptr;
+  const size_t want = bytes + bytes / 2;
+  if (dev_malloc(&np_, want) != 0) ABM_FAIL(h, ABM_E_NOMEM, "device allocation of %zu bytes failed", want);
+  if (b.p && b.bytes) {
+    abm_err_t e = copy_d2d(np_, b.p, b.bytes, h->stream);
+    if (e == 0) e = stream_sync(h->stream);
+    if (e != 0) { dev_free(np_); ABM_FAIL(h, ABM_E_CUDA, "device copy failed: %s", err_string(e)); }
+  }
+  dev_free(b.p);
+  b.p = np_; b.bytes = want;
+  return 0;
+}
+
+static RouteStore route_store(abm_handle* h) {
+  RouteStore rs;
+  rs.slot_of_id = (uint32_t*)h->rt_slot_of_id.p; rs.r_off = (uint64_t*)h->rt_off.p; rs.r_len = (uint32_t*)h->rt_len.p;
+  rs.r_pos = (uint32_t*)h->rt_pos.p; rs.pool = (uint32_t*)h->rt_pool.p;
+  return rs;
+}
+
+static int ensure_route_ids(abm_handle* h, uint64_t ids) {
+  if (ids <= h->rt_ids_cap) return 0;
+  int rc = grow_keep(h, h->rt_slot_of_id, (ids + 1) * 4);
+  if (rc) return rc;
+  h->rt_ids_cap = h->rt_slot_of_id.bytes / 4 - 1;
+  return 0;
+}
+
+static AStarGrid astar_grid(abm_handle* h) {
+  AStarGrid a;
+  a.g = h->g; a.walkbits = (const uint32_t*)h->walkbits.p; a.elev = (const int16_t*)h->elev.p;
+  a.metric = h->cfg.astar_metric; a.penalty = h->cfg.astar_penalty;
+  return a;
+}
+
+static size_t device_free_bytes() {
+#ifndef ABM_EMU
+  size_t f = 0, t = 0;
+  if (cudaMemGetInfo(&f, &t) != cudaSuccess) return (size_t)1 << 30;
+  return f;
+#else
+  return (size_t)1 << 30;
+#endif
+}
+
+/* plan_route! for B requests held in device arrays (agent id, start tcell, goal tcell), in waves of `slots`
+ * concurrent searches.  host_cost (nullable) receives g(goal) or -1. */
+static int plan_batch(abm_handle* h, uint64_t B, const uint32_t* d_id, const uint32_t* d_src, const uint32_t* d_dst) {
+  int rc;
+  if (B == 0) return 0;
+  if (h->g.nx > 65534 || h->g.ny > 65534) ABM_FAIL(h, ABM_E_BADARG, "A* needs grid dims below 65535");
+  const uint64_t gt = h->g.gt;
+  const uint64_t heap_cap = std::min<uint64_t>(8ull * (uint64_t)h->g.nx * h->g.ny + 16, 1ull << 20);
+  const uint64_t per_slot = gt * 6 + heap_cap * 8;
+  if (h->as_slots == 0 || h->as_heap_cap != heap_cap || h->as_slots < std::min<uint64_t>(B, 4096)) {
+    const uint64_t budget = std::min<uint64_t>(device_free_bytes() / 2, 48ull << 30);
+    uint64_t slots = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(B, 1u << 16), budget / per_slot));
+    if (slots > h->as_slots || h->as_heap_cap != heap_cap) {
+      if ((rc = ensure(h, h->as_g, slots * gt * 4))) return rc;
+      if ((rc = ensure(h, h->as_meta, slots * gt * 2))) return rc;
+      if ((rc = ensure(h, h->as_heap, slots * heap_cap * 8))) return rc;
+      ABM_CK(h, dev_memset(h->as_meta.p, 0, slots * gt * 2, h->stream));
+      h->as_slots = slots; h->as_heap_cap = heap_cap; h->as_gen = 0;
+    }
+  }
+  const uint64_t S = h->as_slots;
+  if ((rc = ensure(h, h->as_status, S * 4))) return rc;
+  if ((rc = ensure(h, h->as_len, S * 4))) return rc;
+  if ((rc = ensure(h, h->as_cost, S * 8))) return rc;
+  if ((rc = ensure(h, h->as_off, S * 8))) return rc;
+  std::vector<uint32_t> st(S), ln(S);
+  std::vector<uint64_t> off(S);
+  unsigned long long* d_exp = (unsigned long long*)((uint32_t*)h->counters.p + CTR_EXP_LO);
+  for (uint64_t base = 0; base < B; base += S) {
+    const uint64_t nb = std::min<uint64_t>(S, B - base);
+    if (++h->as_gen > 255) { ABM_CK(h, dev_memset(h->as_meta.p, 0, S * gt * 2, h->stream)); h->as_gen = 1; }
+    AStarSearchBody sb;
+    sb.a = astar_grid(h); sb.src = d_src + base; sb.dst = d_dst + base;
+    sb.gbuf = (uint32_t*)h->as_g.p; sb.meta = (uint16_t*)h->as_meta.p; sb.heap = (uint64_t*)h->as_heap.p;
+    sb.heap_cap = (uint32_t)heap_cap; sb.gen = h->as_gen;
+    sb.out_status = (uint32_t*)h->as_status.p; sb.out_len = (uint32_t*)h->as_len.p; sb.out_cost = (int64_t*)h->as_cost.p;
+    sb.expansions = d_exp;
+    { ProfScope ps(h->prof, h->stream, "astar_search", nb); launch_foreach(h->stream, sb, nb); }
+    if ((rc = check_launch(h, "astar search"))) return rc;
+    ABM_CK(h, copy_d2h(st.data(), h->as_status.p, nb * 4, h->stream));
+    ABM_CK(h, copy_d2h(ln.data(), h->as_len.p, nb * 4, h->stream));
+    uint64_t need = h->rt_pool_used;
+    for (uint64_t i = 0; i < nb; ++i) {
+      if (st[i] == AS_HEAP_FULL) ABM_FAIL(h, ABM_E_CAPACITY, "A* open list exceeded %llu entries", (unsigned long long)heap_cap);
+      off[i] = need;
+      if (st[i] == AS_FOUND) need += ln[i];
+    }
+    if ((rc = grow_keep(h, h->rt_pool, (need + 1) * 4))) return rc;
+    /* slots: at most one new slot per request */
+    const uint64_t slots_needed = h->rt_slots_cap ? 0 : 0;
+    (void)slots_needed;
+    if ((rc = read_counters(h))) return rc;
+    const uint64_t used = h->h_counters[CTR_ROUTE_SLOTS];
+    if (used + nb > h->rt_slots_cap) {
+      const uint64_t cap = (used + nb) * 2 + 64;
+      if ((rc = grow_keep(h, h->rt_off, cap * 8))) return rc;
+      if ((rc = grow_keep(h, h->rt_len, cap * 4))) return rc;
+      if ((rc = grow_keep(h, h->rt_pos, cap * 4))) return rc;
+      if ((rc = grow_keep(h, h->rt_cost, cap * 8))) return rc;
+      h->rt_slots_cap = cap;
+    }
+    ABM_CK(h, copy_h2d(h->as_off.p, off.data(), nb * 8, h->stream));
+    AStarWriteBody wb;
+    wb.a = sb.a; wb.src = sb.src; wb.dst = sb.dst; wb.meta = sb.meta; wb.status = sb.out_status; wb.len = sb.out_len;
+    wb.pool_off = (const uint64_t*)h->as_off.p; wb.pool = (uint32_t*)h->rt_pool.p;
+    { ProfScope ps(h->prof, h->stream, "astar_write", nb); launch_foreach(h->stream, wb, nb); }
+    RouteBindBody bb;
+    bb.rs = route_store(h); bb.r_cost = (int64_t*)h->rt_cost.p; bb.agent_id = d_id + base; bb.status = sb.out_status; bb.len = sb.out_len;
+    bb.cost = sb.out_cost; bb.pool_off = wb.pool_off; bb.slot_counter = (uint32_t*)h->counters.p + CTR_ROUTE_SLOTS;
+    { ProfScope ps(h->prof, h->stream, "route_bind", nb); launch_foreach(h->stream, bb, nb); }
+    if ((rc = check_launch(h, "route bind"))) return rc;
+    h->rt_pool_used = need;
+  }
+  unsigned long long e = 0;
+  ABM_CK(h, copy_d2h(&e, d_exp, 8, h->stream));
+  h->expansions = (double)e;
+  return 0;
+}
+
+/* ALTERNATED_WALK: ranks, behaviour segments, route planning of the switching agents, proposals */
+static int alternated_propose(abm_handle* h, View& v, uint32_t* ctr) {
+  int rc;
+  const uint64_t n = h->n;
+  const uint32_t C = (uint32_t)h->cfg.counter;
+  const uint64_t words = bitmap_words(h->next_id);
+  if ((rc = ensure(h, h->bits, (words + 4) * 4))) return rc;
+  if ((rc = ensure(h, h->rank, n * 4))) return rc;
+  if ((rc = ensure(h, h->by_rank, n * 4))) return rc;
+  if ((rc = ensure(h, h->remote_next, n * 4))) return rc;
+  if ((rc = ensure(h, h->remote_dest, n * 4))) return rc;
+  if ((rc = ensure_route_ids(h, h->next_id))) return rc;
+  v = make_view(h);
+  ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, h->stream));
+  SetBitsBody sbb;
+  sbb.id = v.id; sbb.bits = (uint32_t*)h->bits.p;
+  { ProfScope ps(h->prof, h->stream, "rank_by_id", n, 4); launch_foreach(h->stream, sbb, n);
+    if ((rc = rank_prefix(h, words))) return rc;
+    RankBody rb;
+    rb.id = v.id; rb.alive_bits = (const uint32_t*)h->bits.p; rb.prefix = (const uint32_t*)h->bits_prefix.p;
+    rb.rank = (uint32_t*)h->rank.p; rb.by_rank = (uint32_t*)h->by_rank.p;
+    launch_foreach(h->stream, rb, n); }
+  /* counter value seen by rank r: ((c - 1 - r) mod C) + 1 for c in 1..C; a switch happens where it equals C */
+  const int64_t c = h->behav_counter;
+  const int inert = c == 0 ? 1 : 0;
+  const uint64_t first = inert ? 1 : (uint64_t)(c % C);
+  const uint64_t nsw = first < n ? (n - first + C - 1) / C : 0;
+  if ((rc = ensure(h, h->seg_behav, nsw + 1))) return rc;
+  if ((rc = ensure(h, h->plan_agent, (nsw + 1) * 4))) return rc;
+  if ((rc = ensure(h, h->plan_goal, (nsw + 1) * 4))) return rc;
+  ABM_CK(h, dev_memset(ctr + CTR_PLANS, 0, 4, h->stream));
+  uint64_t plans = 0;
+  if (nsw > 0) {
+    AltSwitchBody sw;
+    sw.v = v; sw.by_rank = (const uint32_t*)h->by_rank.p; sw.first = (uint32_t)first; sw.counter = C;
+    sw.seg_behav = (uint8_t*)h->seg_behav.p; sw.plan_agent = (uint32_t*)h->plan_agent.p; sw.plan_goal = (uint32_t*)h->plan_goal.p;
+    sw.plan_count = ctr + CTR_PLANS;
+    { ProfScope ps(h->prof, h->stream, "alt_switch", nsw); launch_foreach(h->stream, sw, nsw); }
+    if ((rc = check_launch(h, "behaviour switch"))) return rc;
+    if ((rc = read_counters(h))) return rc;
+    plans = h->h_counters[CTR_PLANS];
+  }
+  if (plans > 0) { /* plan_route!(agent, random_walkable(...), pathfinder) from the agents' tick-start cells */
+    if ((rc = ensure(h, h->as_src, plans * 4))) return rc;
+    if ((rc = ensure(h, h->as_id, plans * 4))) return rc;
+    GatherPlanBody gp;
+    gp.cell = v.cell; gp.id = v.id; gp.plan_agent = (const uint32_t*)h->plan_agent.p;
+    gp.src = (uint32_t*)h->as_src.p; gp.aid = (uint32_t*)h->as_id.p;
+    launch_foreach(h->stream, gp, plans);
+    if ((rc = plan_batch(h, plans, (const uint32_t*)h->as_id.p, (const uint32_t*)h->as_src.p, (const uint32_t*)h->plan_goal.p))) return rc;
+  }
+  AltProposeBody ap;
+  ap.v = v;
+  ap.rt.slot_of_id = (uint32_t*)h->rt_slot_of_id.p; ap.rt.r_off = (const uint64_t*)h->rt_off.p; ap.rt.r_len = (const uint32_t*)h->rt_len.p;
+  ap.rt.r_pos = (uint32_t*)h->rt_pos.p; ap.rt.pool = (const uint32_t*)h->rt_pool.p;
+  ap.rank = (const uint32_t*)h->rank.p; ap.seg_behav = (const uint8_t*)h->seg_behav.p;
+  ap.first = (uint32_t)first; ap.counter = C; ap.prev_behav = (int32_t)h->behav; ap.inert_rank0 = inert;
+  ap.pending = (uint32_t*)h->pend[0].p; ap.pending_count = ctr + CTR_PEND_A;
+  { ProfScope ps(h->prof, h->stream, "propose", n); launch_foreach(h->stream, ap, n); }
+  if ((rc = check_launch(h, "alternated propose"))) return rc;
+  /* model.behav[1] / model.behav_counter[1] after this tick's n agent-steps */
+  if (nsw > 0) {
+    uint8_t last = 0;
+    ABM_CK(h, copy_d2h(&last, (uint8_t*)h->seg_behav.p + (nsw - 1), 1, h->stream));
+    h->behav = last;
+  }
+  if (n > 0) {
+    const int64_t c1 = inert ? (int64_t)C : c;
+    const int64_t steps = inert ? (int64_t)n - 1 : (int64_t)n;
+    int64_t m = (c1 - 1 - steps) % (int64_t)C;
+    if (m < 0) m += C;
+    h->behav_counter = m + 1;
+  }
+  return 0;
+}
+
 /* one tick: every agent's custom_agent_step! in id order, then custom_model_step! */
 static int tick_once(abm_handle* h) {
   int rc;
@@ -381,7 +599,9 @@ static int tick_once(abm_handle* h) {
   ABM_CK(h, dev_memset(ctr, 0, 3 * sizeof(uint32_t), h->stream)); /* keeps the sticky error word */
   View v = make_view(h);
 
-  if (n > 0) {
+  if (n > 0 && h->cfg.walk_type == ABM_ALTERNATED_WALK) {
+    if ((rc = alternated_propose(h, v, ctr))) return rc;
+  } else if (n > 0) {
     ProposeBody pb;
     pb.v = v;
     pb.pending = (uint32_t*)h->pend[0].p;
@@ -474,6 +694,11 @@ static int tick_once(abm_handle* h) {
       { ProfScope ps(h->prof, h->stream, "birth_scatter", nb); launch_foreach(h->stream, bb, nb); }
       if ((rc = check_launch(h, "birth scatter"))) return rc;
     }
+  }
+  if (n > 0 && h->cfg.walk_type == ABM_ALTERNATED_WALK) {
+    RemoteResetBody rr;
+    rr.v = v;
+    launch_foreach(h->stream, rr, n);
   }
   /* custom_model_step!: grass regrowth */
   {
@@ -607,6 +832,11 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
     if ((rc = ensure(h, h->scan_tmp, scan_tmp_words((uint64_t)g.gt + 1) * 4))) break;
     if ((rc = ensure_soa(h, 0, 1))) break;
     if ((rc = ensure_soa(h, 1, 1))) break;
+    if (cfg->walk_type == ABM_ALTERNATED_WALK) {
+      if ((rc = ensure(h, h->remote_head, (size_t)g.gt * 4))) break;
+      if (dev_memset(h->remote_head.p, 0xFF, (size_t)g.gt * 4, h->stream) != 0) { rc = ABM_E_CUDA; break; }
+    }
+    if ((rc = ensure(h, h->elev, (size_t)g.gt * 2))) break;
     /* default tables: exp(-sqrt(k)/3) from the C library; closest-neighbour visiting order */
     const int r = cfg->walk_type == ABM_RANDOM_WALK_GREGARIOUS ? cfg->visual_distance : 1;
     const int nl = 2 * (r + 1) * (r + 1) + 1;
@@ -764,6 +994,10 @@ int ABM_API(set_agents)(abm_handle* h, int64_t n, const int64_t* id, const int64
   h->n = (uint64_t)n;
   h->next_id = (uint64_t)next_id;
   h->agents_set = true;
+  /* a fresh population has no routes (pathfinder.agent_paths is empty) */
+  if (h->rt_slot_of_id.p) ABM_CK(h, dev_memset(h->rt_slot_of_id.p, 0, h->rt_slot_of_id.bytes, h->stream));
+  ABM_CK(h, dev_memset((uint32_t*)h->counters.p + CTR_ROUTE_SLOTS, 0, 4, h->stream));
+  h->rt_pool_used = 0;
   return ABM_OK;
 }
 
@@ -810,6 +1044,8 @@ int ABM_API(get_agents)(abm_handle* h, int64_t* n_inout, int64_t* id, int64_t* x
 int ABM_API(set_global_state)(abm_handle* h, int64_t tick, int64_t behav, int64_t behav_counter) {
   if (!h) return ABM_E_BADARG;
   if (tick < 0 || tick > 0xFFFFFFFFll) ABM_FAIL(h, ABM_E_BADARG, "tick must fit 32 bits");
+  if (h->cfg.walk_type == ABM_ALTERNATED_WALK && (behav < 0 || behav > 3 || behav_counter < 0 || behav_counter > h->cfg.counter))
+    ABM_FAIL(h, ABM_E_BADARG, "behav must be in 0..3 and behav_counter in 0..counter");
   h->tick = (uint64_t)tick; h->behav = behav; h->behav_counter = behav_counter;
   return ABM_OK;
 }
@@ -827,7 +1063,6 @@ int ABM_API(step)(abm_handle* h, int64_t n_ticks) {
   if (!h) return ABM_E_BADARG;
   if (n_ticks < 0) ABM_FAIL(h, ABM_E_BADARG, "n_ticks must be >= 0");
   if (!h->grid_set || !h->agents_set) ABM_FAIL(h, ABM_E_STATE, "abm_set_grid and abm_set_agents must precede abm_step");
-  if (h->cfg.walk_type == ABM_ALTERNATED_WALK) ABM_FAIL(h, ABM_E_STATE, "ALTERNATED_WALK is not available in this build yet");
   int rc = set_device(h);
   if (rc) return rc;
   const uint64_t l0 = launches_now();
@@ -888,13 +1123,107 @@ int ABM_API(reduce)(abm_handle* h, int32_t what, double* out) {
   ABM_FAIL(h, ABM_E_BADARG, "unknown reduction %d", what);
 }
 
-int ABM_API(plan_routes)(abm_handle* h, int64_t, const int64_t*, const int64_t*, const int64_t*) {
+int ABM_API(plan_routes)(abm_handle* h, int64_t b, const int64_t* agent_id, const int64_t* goal_x, const int64_t* goal_y) {
   if (!h) return ABM_E_BADARG;
-  ABM_FAIL(h, ABM_E_STATE, "abm_plan_routes is not available in this build yet");
+  if (b < 0 || (b > 0 && (!agent_id || !goal_x || !goal_y))) ABM_FAIL(h, ABM_E_BADARG, "null request arrays");
+  if (!h->grid_set || !h->agents_set) ABM_FAIL(h, ABM_E_STATE, "abm_set_grid and abm_set_agents must precede abm_plan_routes");
+  int rc = set_device(h);
+  if (rc) return rc;
+  h->expansions = 0;
+  h->prof.reset();
+  ABM_CK(h, dev_memset((uint32_t*)h->counters.p + CTR_EXP_LO, 0, 8, h->stream));
+  if (b == 0) return ABM_OK;
+  { /* each agent at most once per batch (the reference plans sequentially; a repeated id would be order-dependent) */
+    std::vector<int64_t> srt(agent_id, agent_id + b);
+    std::sort(srt.begin(), srt.end());
+    for (int64_t i = 1; i < b; ++i) if (srt[i] == srt[i - 1]) ABM_FAIL(h, ABM_E_BADARG, "agent id %lld appears twice in one abm_plan_routes batch", (long long)srt[i]);
+  }
+  const uint64_t n = h->n;
+  if ((rc = ensure(h, h->idx_of_id, (h->next_id + 1) * 4))) return rc;
+  if ((rc = ensure_route_ids(h, h->next_id))) return rc;
+  ABM_CK(h, dev_memset(h->idx_of_id.p, 0xFF, (h->next_id + 1) * 4, h->stream));
+  if (n > 0) {
+    IdIndexBody ii;
+    ii.id = (const uint32_t*)h->id[h->cur].p; ii.idx_of_id = (uint32_t*)h->idx_of_id.p;
+    launch_foreach(h->stream, ii, n);
+  }
+  if ((rc = ensure(h, h->stage, (size_t)b * 24 + 64))) return rc;
+  if ((rc = ensure(h, h->as_id, (size_t)b * 4))) return rc;
+  if ((rc = ensure(h, h->as_src, (size_t)b * 4))) return rc;
+  if ((rc = ensure(h, h->as_dst, (size_t)b * 4))) return rc;
+  int64_t* s_id = (int64_t*)h->stage.p;
+  int64_t* s_x = s_id + b;
+  int64_t* s_y = s_x + b;
+  ABM_CK(h, copy_h2d(s_id, agent_id, (size_t)b * 8, h->stream));
+  ABM_CK(h, copy_h2d(s_x, goal_x, (size_t)b * 8, h->stream));
+  ABM_CK(h, copy_h2d(s_y, goal_y, (size_t)b * 8, h->stream));
+  ABM_CK(h, dev_memset((uint32_t*)h->counters.p + CTR_ERR, 0, 4, h->stream));
+  PlanRequestBody pr;
+  pr.g = h->g; pr.hid = s_id; pr.gx = s_x; pr.gy = s_y; pr.idx_of_id = (const uint32_t*)h->idx_of_id.p;
+  pr.id = (const uint32_t*)h->id[h->cur].p; pr.cell = (const uint32_t*)h->cell[h->cur].p; pr.n = (uint32_t)n; pr.next_id = h->next_id;
+  pr.aid = (uint32_t*)h->as_id.p; pr.src = (uint32_t*)h->as_src.p; pr.dst = (uint32_t*)h->as_dst.p; pr.err = (uint32_t*)h->counters.p + CTR_ERR;
+  launch_foreach(h->stream, pr, (uint64_t)b);
+  if ((rc = check_launch(h, "plan requests"))) return rc;
+  if ((rc = read_counters(h))) return rc;
+  if (h->h_counters[CTR_ERR]) {
+    ABM_CK(h, dev_memset((uint32_t*)h->counters.p + CTR_ERR, 0, 4, h->stream));
+    ABM_FAIL(h, ABM_E_BADARG, "abm_plan_routes: unknown agent id or goal outside the grid");
+  }
+  h->tm_total.start(h->stream);
+  rc = plan_batch(h, (uint64_t)b, (const uint32_t*)h->as_id.p, (const uint32_t*)h->as_src.p, (const uint32_t*)h->as_dst.p);
+  h->tm_total.stop(h->stream);
+  if (rc) return rc;
+  ABM_CK(h, stream_sync(h->stream));
+  h->t_total = h->tm_total.ms();
+  h->prof.collect();
+  return ABM_OK;
 }
-int ABM_API(get_paths)(abm_handle* h, int64_t, const int64_t*, int64_t*, int64_t*, int64_t*, int64_t*, int64_t*) {
+
+int ABM_API(get_paths)(abm_handle* h, int64_t b, const int64_t* agent_id, int64_t* offset, int64_t* cells_inout, int64_t* px, int64_t* py, int64_t* cost) {
   if (!h) return ABM_E_BADARG;
-  ABM_FAIL(h, ABM_E_STATE, "abm_get_paths is not available in this build yet");
+  if (b < 0 || !offset || !cells_inout || (b > 0 && !agent_id)) ABM_FAIL(h, ABM_E_BADARG, "null argument");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (b == 0) { offset[0] = 0; *cells_inout = 0; return ABM_OK; }
+  if ((rc = ensure_route_ids(h, h->next_id))) return rc;
+  if ((rc = ensure(h, h->rt_off, 8))) return rc;
+  if ((rc = ensure(h, h->rt_len, 4))) return rc;
+  if ((rc = ensure(h, h->rt_pos, 4))) return rc;
+  if ((rc = ensure(h, h->rt_cost, 8))) return rc;
+  if ((rc = ensure(h, h->rt_pool, 4))) return rc;
+  if ((rc = ensure(h, h->stage, (size_t)b * 32 + 64))) return rc;
+  int64_t* s_id = (int64_t*)h->stage.p;
+  int64_t* s_len = s_id + b;
+  int64_t* s_cost = s_len + b;
+  int64_t* s_off = s_cost + b;
+  ABM_CK(h, copy_h2d(s_id, agent_id, (size_t)b * 8, h->stream));
+  PathInfoBody pi;
+  pi.rs = route_store(h); pi.r_cost = (const int64_t*)h->rt_cost.p; pi.hid = s_id; pi.ids_cap = h->rt_ids_cap;
+  pi.out_len = s_len; pi.out_cost = s_cost;
+  launch_foreach(h->stream, pi, (uint64_t)b);
+  if ((rc = check_launch(h, "path info"))) return rc;
+  std::vector<int64_t> len(b), off(b + 1);
+  ABM_CK(h, copy_d2h(len.data(), s_len, (size_t)b * 8, h->stream));
+  if (cost) ABM_CK(h, copy_d2h(cost, s_cost, (size_t)b * 8, h->stream));
+  off[0] = 0;
+  for (int64_t i = 0; i < b; ++i) off[i + 1] = off[i] + len[i];
+  const int64_t total = off[b];
+  if (*cells_inout < total) { *cells_inout = total; ABM_FAIL(h, ABM_E_SMALL, "path buffers hold fewer than %lld cells", (long long)total); }
+  *cells_inout = total;
+  memcpy(offset, off.data(), (size_t)(b + 1) * 8);
+  if (total == 0) return ABM_OK;
+  if (!px || !py) ABM_FAIL(h, ABM_E_BADARG, "null path buffers");
+  DevBuf out;
+  if ((rc = ensure(h, out, (size_t)total * 16))) return rc;
+  ABM_CK(h, copy_h2d(s_off, off.data(), (size_t)b * 8, h->stream));
+  PathCopyBody pc;
+  pc.g = h->g; pc.rs = route_store(h); pc.hid = s_id; pc.ids_cap = h->rt_ids_cap; pc.offset = s_off;
+  pc.px = (int64_t*)out.p; pc.py = (int64_t*)out.p + total;
+  launch_foreach(h->stream, pc, (uint64_t)b);
+  if ((rc = check_launch(h, "path copy"))) return rc;
+  ABM_CK(h, copy_d2h(px, pc.px, (size_t)total * 8, h->stream));
+  ABM_CK(h, copy_d2h(py, pc.py, (size_t)total * 8, h->stream));
+  return ABM_OK;
 }
 
 int ABM_API(set_profiling)(abm_handle* h, int32_t on) {

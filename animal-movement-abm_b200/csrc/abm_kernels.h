@@ -41,7 +41,8 @@ enum {
   ST_DEAD = 0x40,  /* energy - movement_cost < 0 (reduce_energy!, src/agent_actions.jl:85-92) */
   ST_BIRTH = 0x80  /* rand(model.rng) <= reproduction_prob (src/agent_actions.jl:64) */
 };
-enum { DIR_STAY = 8, DIR_GREG = 9 };
+enum { DIR_STAY = 8, DIR_GREG = 9, DIR_REMOTE = 10 }; /* REMOTE: move_along_route!, final cell in remote_dest[] */
+enum { REMOTE_NONE = 0xFFFFFFFFu };
 
 /* grass byte: bit 7 = fully_grown, bits 0..6 = countdown (0..126); 0x7F = padding cell outside the grid */
 enum { GRASS_GROWN = 0x80, GRASS_PAD = 0x7F };
@@ -78,6 +79,7 @@ ABM_HD void dec(const Geo& g, uint32_t c, int& x, int& y) {
 /* Julia mod1 on 0-based coordinates for |d| <= n */
 ABM_HD int wrap(int a, int n) { return a < 0 ? a + n : (a >= n ? a - n : a); }
 ABM_HD int wrap_far(int a, int n) { a %= n; return a < 0 ? a + n : a; }
+ABM_HD int g_wrap(int a, int n, int periodic) { return periodic ? wrap_far(a, n) : a; }
 
 /* pos + (dx,dy): wrapped when periodic; false when it leaves a non-periodic grid */
 ABM_HD bool shift(const Geo& g, int x, int y, int dx, int dy, int& ox, int& oy) {
@@ -126,6 +128,11 @@ struct View {
   const double* lut;         /* exp(-sqrt(k)/3) */
   const uint8_t* greg_order; /* box cells by (d^2, β index) */
   uint32_t* err;             /* sticky device error flags */
+  /* ALTERNATED_WALK only (else null): agents that follow a route land on an arbitrary cell; they are chained per
+   * destination cell so that `ifempty` probes and the commit see them */
+  uint32_t* remote_head;     /* gt, REMOTE_NONE = empty */
+  uint32_t* remote_next;     /* per agent */
+  uint32_t* remote_dest;     /* per agent: final tcell */
 };
 
 enum { ERR_NOWALKABLE = 1, ERR_INTERNAL = 2 };
@@ -260,7 +267,7 @@ ABM_HD int resolve_cond(const View& v, uint32_t k, uint8_t st) {
         if (idj > myid) continue; /* has not moved yet */
         const uint8_t sj = load_state(&v.state[j]);
         const int dj = sj & ST_DIRMASK;
-        if (dj == DIR_STAY) continue;
+        if (dj == DIR_STAY || dj == DIR_REMOTE) continue; /* route followers are found through remote_head */
         bool hits = true; /* an undecided gregarious agent may step onto any neighbour */
         if (dj != DIR_GREG) {
           int jx, jy, fx, fy;
@@ -272,6 +279,11 @@ ABM_HD int resolve_cond(const View& v, uint32_t k, uint8_t st) {
         if (!(sj & ST_DECIDED)) unknown = true;
         else if ((sj & ST_MOVED) && present(sj)) { blocked = true; break; }
       }
+    }
+  }
+  if (!blocked && v.remote_head) { /* lower-id route followers that already arrived on T (decided at propose) */
+    for (uint32_t j = v.remote_head[enc(v.g, tx, ty)]; j != REMOTE_NONE; j = v.remote_next[j]) {
+      if (j != k && v.id[j] < myid && present(v.state[j])) { blocked = true; break; }
     }
   }
   if (blocked) { v.state[k] = (uint8_t)(st | ST_DECIDED); return RES_DONE; }
@@ -406,7 +418,8 @@ struct CommitBody {
     const uint32_t myid = v.id[k];
     int x, y, fx, fy;
     dec(v.g, v.cell[k], x, y);
-    final_xy(v, x, y, st, fx, fy);
+    if ((st & ST_DIRMASK) == DIR_REMOTE) dec(v.g, v.remote_dest[k], fx, fy);
+    else final_xy(v, x, y, st, fx, fy);
     const uint32_t fc = enc(v.g, fx, fy);
     int px[9], py[9];
     const int nb = block9(v.g, fx, fy, px, py);
@@ -419,11 +432,19 @@ struct CommitBody {
         const uint8_t sj = v.state[j];
         if (b == 0) { if (sj & ST_MOVED) continue; }
         else {
-          if (!(sj & ST_MOVED)) continue;
+          if (!(sj & ST_MOVED) || (sj & ST_DIRMASK) == DIR_REMOTE) continue;
           int jx, jy;
           final_xy(v, px[b], py[b], sj, jx, jy);
           if (jx != fx || jy != fy) continue;
         }
+        const bool alive = !(sj & ST_DEAD), birth = (sj & ST_BIRTH) != 0;
+        alive_tot += alive; birth_tot += birth;
+        if (j != k && v.id[j] < myid) { lower = true; slot_alive += alive; slot_birth += birth; }
+      }
+    }
+    if (v.remote_head) { /* route followers landing on fc */
+      for (uint32_t j = v.remote_head[fc]; j != REMOTE_NONE; j = v.remote_next[j]) {
+        const uint8_t sj = v.state[j];
         const bool alive = !(sj & ST_DEAD), birth = (sj & ST_BIRTH) != 0;
         alive_tot += alive; birth_tot += birth;
         if (j != k && v.id[j] < myid) { lower = true; slot_alive += alive; slot_birth += birth; }
@@ -544,6 +565,132 @@ struct RegrowBody {
     for (int a = 0; a < 4; ++a) grass4[4 * i + a] = w[a];
 #endif
   }
+};
+
+/* ------------------------------------------------------------------------------------------- alternated walk */
+
+/* Schedulers.by_id rank of every agent (its agent-step index inside the tick) and the inverse map */
+struct RankBody {
+  const uint32_t* id; const uint32_t* alive_bits; const uint32_t* prefix;
+  uint32_t* rank; uint32_t* by_rank;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t a = id[i], w = a >> 5;
+    const uint32_t r = prefix[w] + (uint32_t)popc(alive_bits[w] & ((1u << (a & 31)) - 1u));
+    rank[i] = r; by_rank[r] = (uint32_t)i;
+  }
+};
+
+struct RouteView { /* pathfinder.agent_paths, see abm_astar.h */
+  uint32_t* slot_of_id; const uint64_t* r_off; const uint32_t* r_len; uint32_t* r_pos; const uint32_t* pool;
+};
+
+/* the draws an agent makes when it finds behav_counter == counter (src/agent_actions.jl:212-222): sample(1:3) and,
+ * for 2, the rejection loop of random_walkable.  Leaves the stream positioned after them. */
+ABM_HD int alt_switch_draws(const View& v, AgentStream& rs, uint32_t* goal) {
+  const int b = (int)rs.next_below(3) + 1;
+  if (b == 2) {
+    while (true) {
+      const int gx = (int)rs.next_below((uint64_t)v.g.nx), gy = (int)rs.next_below((uint64_t)v.g.ny);
+      const uint32_t c = enc(v.g, gx, gy);
+      if (walkable(v, c)) { if (goal) *goal = c; break; }
+    }
+  }
+  return b;
+}
+
+/* one thread per behaviour switch of this tick: the agent whose step finds the global counter at `counter` */
+struct AltSwitchBody {
+  View v;
+  const uint32_t* by_rank;
+  uint32_t first, counter;
+  uint8_t* seg_behav;     /* behaviour of segment i */
+  uint32_t* plan_agent;   /* requests: agent index, goal tcell */
+  uint32_t* plan_goal;
+  uint32_t* plan_count;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t k = by_rank[first + (uint32_t)i * counter];
+    AgentStream rs;
+    rs.init(v.p.seed, v.p.tick, v.id[k]);
+    (void)rs.next_f64(); /* execute_walk!'s uniform (prob_random_walk = 0) */
+    uint32_t goal = 0;
+    const int b = alt_switch_draws(v, rs, &goal);
+    seg_behav[i] = (uint8_t)b;
+    if (b == 2) {
+      const uint32_t q = atomic_add(plan_count, 1u);
+      plan_agent[q] = k; plan_goal[q] = goal;
+    }
+  }
+};
+
+/* alternated_walk (src/agent_actions.jl:211-242) with the model-global counter in closed form */
+struct AltProposeBody {
+  View v;
+  RouteView rt;
+  const uint32_t* rank;
+  const uint8_t* seg_behav;
+  uint32_t first, counter;
+  int32_t prev_behav;   /* model.behav[1] at tick start */
+  int32_t inert_rank0;  /* behav_counter was 0 at tick start: the first agent-step only resets the counter */
+  uint32_t* pending; uint32_t* pending_count;
+
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t k = (uint32_t)i;
+    const Params& p = v.p;
+    const uint32_t id = v.id[k], r = rank[k];
+    int x, y;
+    dec(v.g, v.cell[k], x, y);
+    AgentStream rs;
+    rs.init(p.seed, p.tick, id);
+    (void)rs.next_f64();
+    int b = prev_behav;
+    bool acts = true;
+    if (inert_rank0 && r == 0) acts = false;
+    else if (r >= first) {
+      const uint32_t seg = (r - first) / counter;
+      b = seg_behav[seg];
+      if ((r - first) % counter == 0) (void)alt_switch_draws(v, rs, nullptr); /* this agent made the switch draws */
+    }
+    uint8_t st = DIR_STAY | ST_DECIDED; /* behav 3: move_agent!(agent, agent.pos, model); behav 0: nothing */
+    if (acts && b == 1) { /* randomwalk!(agent, model): ignores the walkmap (Appendix D-6) */
+      int dx, dy;
+      off8((int)rs.next_below(8), dx, dy);
+      const int e = effective_dir(v.g, x, y, dx, dy);
+      if (!p.ifempty) st = (uint8_t)(e | ST_DECIDED | (e != DIR_STAY ? ST_MOVED : 0));
+      else st = (uint8_t)(e == DIR_STAY ? (DIR_STAY | ST_DECIDED) : e);
+    } else if (acts && b == 2) { /* move_along_route!: unconditional, one cell of the stored path */
+      const uint32_t s = rt.slot_of_id[id];
+      if (s) {
+        const uint32_t pos = rt.r_pos[s - 1];
+        if (pos < rt.r_len[s - 1]) {
+          const uint32_t dest = rt.pool[rt.r_off[s - 1] + pos];
+          rt.r_pos[s - 1] = pos + 1;
+          if (dest != v.cell[k]) {
+            st = DIR_REMOTE | ST_DECIDED | ST_MOVED;
+            v.remote_dest[k] = dest;
+            /* lock-free push on the destination cell's chain */
+            uint32_t old = atomic_exch(&v.remote_head[dest], k);
+            v.remote_next[k] = old;
+          }
+        }
+      }
+    }
+    if (v.energy[k] - p.movement_cost < 0) st |= ST_DEAD;
+    if (p.reproduce && rs.next_f64() <= p.reproduction_prob) st |= ST_BIRTH;
+    v.state[k] = st;
+    if (!(st & ST_DECIDED)) pending[atomic_add(pending_count, 1u)] = k;
+  }
+};
+
+struct RemoteResetBody { /* empties the chains touched this tick */
+  View v;
+  ABM_HD void operator()(uint64_t i) const {
+    if ((v.state[i] & ST_DIRMASK) == DIR_REMOTE) v.remote_head[v.remote_dest[i]] = REMOTE_NONE;
+  }
+};
+
+struct IdIndexBody { /* id -> position in the cell-sorted arrays */
+  const uint32_t* id; uint32_t* idx_of_id;
+  ABM_HD void operator()(uint64_t i) const { idx_of_id[id[i]] = (uint32_t)i; }
 };
 
 /* ---------------------------------------------------------------------------------------- boundary helpers */

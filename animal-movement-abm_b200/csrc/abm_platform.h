@@ -30,6 +30,7 @@ namespace abm {
 static inline uint32_t atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 static inline uint32_t atomic_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 static inline uint32_t atomic_max(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
+static inline uint32_t atomic_exch(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
 static inline unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 static inline uint8_t load_state(const uint8_t* p) { return *(const volatile uint8_t*)p; }
 static inline int popc(uint32_t v) { return __builtin_popcount(v); }
@@ -84,6 +85,7 @@ namespace abm {
 ABM_D uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 ABM_D uint32_t atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
 ABM_D uint32_t atomic_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
+ABM_D uint32_t atomic_exch(uint32_t* p, uint32_t v) { return atomicExch(p, v); }
 ABM_D unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 /* per-agent decision bytes are written once by their owner and polled by neighbours in the same launch:
  * bypass L1 so that a decision published by another SM becomes visible (ld.global.cg = cache at L2 only) */

@@ -32,7 +32,7 @@ def _golden(name):
 
 
 # walk types the CUDA engine does not implement yet (ALTERNATED_WALK + A*): the engine refuses them loudly
-ENGINE_PENDING = {"v0.4_alternated", "v0.6_alternated_penalty", "dense_alternated"}
+ENGINE_PENDING = set()
 
 
 def _run_against_golden(lib, name):
@@ -101,8 +101,6 @@ def test_gpu_matches_golden(libabm, name):
 def test_gpu_matches_oracle_tick_by_tick(libabm, oracle, wt, per, terr, n, nx, ny, extra):
     """Mid-size seeded worlds (the oracle needs seconds): every tick compared."""
     from conftest import make_case
-    if wt == 3:
-        pytest.xfail("ALTERNATED_WALK not implemented in the engine yet")
     kw = dict(reproduction_prob=0.02, regrowth_time=6, delta_energy=3.0)
     kw.update(extra)
     cfgkw, w = make_case(nx, ny, n, wt, per, terrain=bool(terr), seed=99, **kw)
@@ -131,3 +129,54 @@ def test_gpu_weight_lut_is_honoured(libabm, oracle):
     a.step(10)
     b.step(10)
     assert_same_state(b.snapshot(), a.snapshot(), "distorted LUT")
+
+
+def _plan_case(lib, metric, penalty, periodic, nx=40, ny=31, n=60, seed=12):
+    from conftest import make_case
+    cfgkw, w = make_case(nx, ny, n, 3, periodic, terrain=True, seed=seed, astar_metric=metric, astar_penalty=penalty, counter=9)
+    e = load_case(lib, cfgkw, w)
+    ok = np.argwhere(w["walkmap"] == 1)
+    rng = np.random.default_rng(seed)
+    goals = ok[rng.integers(0, len(ok), n)]
+    goals[0] = (w["y"][0] - 1, w["x"][0] - 1)  # start == goal: an empty route
+    e.plan_routes(w["ids"], goals[:, 1] + 1, goals[:, 0] + 1)
+    return e, w
+
+
+def _same_paths(a, b, ids):
+    oa, xa, ya, ca = a.get_paths(ids)
+    ob, xb, yb, cb = b.get_paths(ids)
+    assert np.array_equal(oa, ob) and np.array_equal(xa, xb) and np.array_equal(ya, yb) and np.array_equal(ca, cb)
+    return oa
+
+
+@pytest.mark.parametrize("metric,penalty,periodic", [(1, 1, 1), (0, 0, 1), (1, 1, 0), (0, 1, 0)])
+def test_emulated_astar_paths_match_oracle(emu, oracle, metric, penalty, periodic):
+    """abm_plan_routes / abm_get_paths: every path cell and the path cost, bit-exact; then the routes are followed."""
+    a, w = _plan_case(oracle, metric, penalty, periodic)
+    b, _ = _plan_case(emu, metric, penalty, periodic)
+    off = _same_paths(a, b, w["ids"])
+    assert off[-1] > 50
+    for lib_e in (a, b):
+        lib_e.set_global_state(0, 2, 5)  # behaviour 2 (follow the route) for the next 5 agent-steps, then a switch
+    for t in range(6):
+        a.step(1)
+        b.step(1)
+        assert_same_state(b.snapshot(), a.snapshot(), f"route following tick {t}")
+        ids = a.get_agents()[0]
+        _same_paths(a, b, ids)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("metric,penalty,periodic", [(1, 1, 1), (0, 0, 1), (1, 1, 0)])
+def test_gpu_astar_paths_match_oracle(libabm, oracle, metric, penalty, periodic):
+    a, w = _plan_case(oracle, metric, penalty, periodic, nx=160, ny=120, n=400)
+    b, _ = _plan_case(libabm, metric, penalty, periodic, nx=160, ny=120, n=400)
+    _same_paths(a, b, w["ids"])
+    for lib_e in (a, b):
+        lib_e.set_global_state(0, 2, 7)
+    for t in range(8):
+        a.step(1)
+        b.step(1)
+        assert_same_state(b.snapshot(), a.snapshot(), f"route following tick {t}")
+    _same_paths(a, b, a.get_agents()[0])
