@@ -14,6 +14,7 @@
 
 #include "abm_kernels.h"
 #include "abm_astar.h"
+#include "abm_tile.h"
 
 #ifdef ABM_EMU
 #define ABM_API(name) emu_##name
@@ -229,7 +230,7 @@ struct ProfScope {
 };
 
 enum { CTR_PEND_A = 0, CTR_PEND_B = 1, CTR_BIRTHS = 2, CTR_ERR = 3, CTR_RED_LO = 4, CTR_RED_HI = 5, CTR_PLANS = 6, CTR_ROUTE_SLOTS = 7,
-       CTR_EXP_LO = 8, CTR_EXP_HI = 9, CTR_WORDS = 12 };
+       CTR_EXP_LO = 8, CTR_EXP_HI = 9, CTR_CURSOR = 10, CTR_BIRTH_FLAGS = 11, CTR_WORDS = 16 };
 
 }  // namespace
 
@@ -252,6 +253,11 @@ struct abm_handle {
   DevBuf rt_slot_of_id, rt_off, rt_len, rt_pos, rt_cost, rt_pool;
   uint64_t as_slots = 0, as_heap_cap = 0, rt_slots_cap = 0, rt_pool_used = 0, rt_ids_cap = 0;
   uint32_t as_gen = 0;
+  /* tile path (abm_tile.h): sub-tile runs of the SoA (ping-pong with the SoA), offspring fix-up lists */
+  bool tile_mode = false;
+  int32_t tile_rounds = 8; /* in-window rounds of the tile resolve kernel (ABM_TILE_ROUNDS overrides; tests use 1) */
+  int32_t nsx = 0, nsy = 0;
+  DevBuf sub_off[2], sub_cnt[2], birth_pos, birth_parent, ingest_sub;
   uint32_t* h_counters = nullptr; /* host mirror (pinned on CUDA) */
 
   uint64_t n = 0, next_id = 1, tick = 0;
@@ -606,6 +612,7 @@ static int tick_once(abm_handle* h) {
     pb.v = v;
     pb.pending = (uint32_t*)h->pend[0].p;
     pb.pending_count = ctr + CTR_PEND_A;
+    pb.birth_flags = nullptr;
     { ProfScope ps(h->prof, h->stream, "propose", n); launch_foreach(h->stream, pb, n); }
     if ((rc = check_launch(h, "propose"))) return rc;
   }
@@ -709,6 +716,106 @@ static int tick_once(abm_handle* h) {
     gb.use_walk = h->cfg.walkmap_regrowth;
     { ProfScope ps(h->prof, h->stream, "regrow", gt); launch_foreach(h->stream, gb, gt / 16); }
     if ((rc = check_launch(h, "regrow"))) return rc;
+  }
+  h->cur = nxt;
+  h->n = n_new;
+  h->next_id += nb;
+  h->tick += 1;
+  h->updates += (double)n;
+  return 0;
+}
+
+static SubIndex sub_index(abm_handle* h, int which) {
+  SubIndex si;
+  si.off = (const uint32_t*)h->sub_off[which].p; si.cnt = (const uint32_t*)h->sub_cnt[which].p; si.nsx = h->nsx; si.nsy = h->nsy;
+  return si;
+}
+
+/* one tick on the tile path (abm_tile.h): propose -> window resolve -> per-agent windows for the rest -> commit */
+static int tick_tile(abm_handle* h) {
+  int rc;
+  const uint64_t n = h->n;
+  const uint64_t cores = (uint64_t)(h->g.nx / CORE) * (uint64_t)(h->g.ny / CORE);
+  const uint64_t m = std::max<uint64_t>(n, 1);
+  if ((rc = ensure(h, h->state, m))) return rc;
+  if ((rc = ensure(h, h->pend[0], m * 4))) return rc;
+  if ((rc = ensure(h, h->pend[1], m * 4))) return rc;
+  uint32_t* ctr = (uint32_t*)h->counters.p;
+  ABM_CK(h, dev_memset(ctr, 0, 3 * sizeof(uint32_t), h->stream));
+  ABM_CK(h, dev_memset(ctr + CTR_CURSOR, 0, 2 * sizeof(uint32_t), h->stream));
+  View v = make_view(h);
+  const SubIndex si = sub_index(h, h->cur);
+  const int wt = h->cfg.walk_type;
+  const bool needs_resolve = wt == ABM_RANDOM_WALK_ATTRACTOR || wt == ABM_RANDOM_WALK_GREGARIOUS || (wt == ABM_RANDOM_WALK && h->cfg.randomwalk_ifempty);
+  uint64_t cnt = 0;
+  if (n > 0) {
+    ProposeBody pb;
+    pb.v = v; pb.pending = nullptr; pb.pending_count = nullptr; pb.birth_flags = ctr + CTR_BIRTH_FLAGS;
+    { ProfScope ps(h->prof, h->stream, "propose", n); launch_foreach(h->stream, pb, n); }
+    if ((rc = check_launch(h, "propose"))) return rc;
+    if (needs_resolve) {
+      ResolveWindow rw;
+      rw.v = v; rw.si = si; rw.mode = 0; rw.cores_x = h->g.nx / CORE; rw.max_rounds = h->tile_rounds; rw.nthreads = TILE_THREADS;
+      rw.in = nullptr; rw.out = (uint32_t*)h->pend[0].p; rw.out_count = ctr + CTR_PEND_A;
+      { ProfScope ps(h->prof, h->stream, "resolve_tiles", n); launch_cta(h->stream, rw, cores, TILE_THREADS, ResolveWindow::smem_bytes(WIN, WIN)); }
+      if ((rc = check_launch(h, "tile resolve"))) return rc;
+    }
+  }
+  if ((rc = read_counters(h))) return rc;
+  cnt = h->h_counters[CTR_PEND_A];
+  const uint64_t birth_flags = h->h_counters[CTR_BIRTH_FLAGS];
+  {
+    int in = 0, stalls = 0;
+    const int q = wt == ABM_RANDOM_WALK_GREGARIOUS ? h->cfg.visual_distance + 1 : 2;
+    while (cnt > 0) { /* chains that left their window: one small window per agent, Jacobi rounds */
+      ABM_CK(h, dev_memset(ctr + (in ? CTR_PEND_A : CTR_PEND_B), 0, sizeof(uint32_t), h->stream));
+      ResolveWindow rw;
+      rw.v = v; rw.si = si; rw.mode = 1; rw.cores_x = 0; rw.max_rounds = 1; rw.nthreads = AGENT_THREADS;
+      rw.in = (const uint32_t*)h->pend[in].p; rw.out = (uint32_t*)h->pend[in ^ 1].p; rw.out_count = ctr + (in ? CTR_PEND_A : CTR_PEND_B);
+      { ProfScope ps(h->prof, h->stream, "resolve_agents", cnt); launch_cta(h->stream, rw, cnt, AGENT_THREADS, ResolveWindow::smem_bytes(2 * q + 1, 2 * q + 1)); }
+      if ((rc = check_launch(h, "agent resolve"))) return rc;
+      if ((rc = read_counters(h))) return rc;
+      const uint64_t left = h->h_counters[in ? CTR_PEND_A : CTR_PEND_B];
+      h->rounds += 1;
+      stalls = left == cnt ? stalls + 1 : 0;
+      if (stalls > 8) ABM_FAIL(h, ABM_E_INTERNAL, "conflict resolution made no progress with %llu agents pending", (unsigned long long)left);
+      cnt = left;
+      in ^= 1;
+    }
+  }
+  /* commit + grass + re-grouping */
+  const int nxt = h->cur ^ 1;
+  if ((rc = ensure_soa(h, nxt, n + birth_flags))) return rc;
+  if ((rc = ensure(h, h->birth_pos, (birth_flags + 1) * 4))) return rc;
+  if ((rc = ensure(h, h->birth_parent, (birth_flags + 1) * 4))) return rc;
+  const uint64_t words = bitmap_words(h->next_id);
+  if (birth_flags > 0) {
+    if ((rc = ensure(h, h->bits, (words + 4) * 4))) return rc;
+    ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, h->stream));
+  }
+  {
+    CommitTile ct;
+    ct.v = v; ct.si = si; ct.cores_x = h->g.nx / CORE;
+    ct.out_cell = (uint32_t*)h->cell[nxt].p; ct.out_id = (uint32_t*)h->id[nxt].p; ct.out_energy = (double*)h->energy[nxt].p;
+    ct.new_off = (uint32_t*)h->sub_off[nxt].p; ct.new_cnt = (uint32_t*)h->sub_cnt[nxt].p;
+    ct.cursor = ctr + CTR_CURSOR;
+    ct.birth_pos = (uint32_t*)h->birth_pos.p; ct.birth_parent = (uint32_t*)h->birth_parent.p; ct.birth_count = ctr + CTR_BIRTHS;
+    ct.birth_bits = (uint32_t*)h->bits.p;
+    { ProfScope ps(h->prof, h->stream, "commit_tiles", n); launch_cta(h->stream, ct, cores, TILE_THREADS, CommitTile::smem_bytes()); }
+    if ((rc = check_launch(h, "tile commit"))) return rc;
+  }
+  if ((rc = read_counters(h))) return rc;
+  if ((rc = device_error_to_code(h))) return rc;
+  const uint64_t n_new = h->h_counters[CTR_CURSOR], nb = h->h_counters[CTR_BIRTHS];
+  if (h->next_id + nb > 0xFFFFFFFFull) ABM_FAIL(h, ABM_E_CAPACITY, "agent id space (2^32-1) exhausted");
+  if (nb > 0) {
+    if ((rc = rank_prefix(h, words))) return rc;
+    BirthIdBody bi;
+    bi.birth_pos = (const uint32_t*)h->birth_pos.p; bi.birth_parent = (const uint32_t*)h->birth_parent.p;
+    bi.birth_bits = (const uint32_t*)h->bits.p; bi.birth_prefix = (const uint32_t*)h->bits_prefix.p;
+    bi.next_id = (uint32_t)h->next_id; bi.out_id = (uint32_t*)h->id[nxt].p;
+    { ProfScope ps(h->prof, h->stream, "birth_ids", nb); launch_foreach(h->stream, bi, nb); }
+    if ((rc = check_launch(h, "birth ids"))) return rc;
   }
   h->cur = nxt;
   h->n = n_new;
@@ -822,13 +929,28 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
   p.ax2 = (int64_t)llround(2 * cfg->attractor_x); p.ay2 = (int64_t)llround(2 * cfg->attractor_y);
   p.seed = cfg->seed;
 
+  /* tile path on grids made of whole 32x32 cores that are wider than one window; everything else (and the model-global
+   * counter of ALTERNATED_WALK) takes the general path.  cfg->reserved0 = 1 forces the general path (tests). */
+  h->tile_mode = cfg->reserved0 != 1 && cfg->walk_type != ABM_ALTERNATED_WALK && cfg->nx % CORE == 0 && cfg->ny % CORE == 0 &&
+                 cfg->nx >= 2 * CORE && cfg->ny >= 2 * CORE;
+  h->nsx = cfg->nx / SUB; h->nsy = cfg->ny / SUB;
+  if (const char* tr = getenv("ABM_TILE_ROUNDS")) { const int q = atoi(tr); if (q >= 1 && q <= 64) h->tile_rounds = q; }
   rc = 0;
   do {
     if ((rc = ensure(h, h->counters, CTR_WORDS * 4))) break;
     if ((rc = ensure(h, h->grass, g.gt))) break;
     if ((rc = ensure(h, h->walkbits, (size_t)g.gt / 8 + 16))) break;
-    if ((rc = ensure(h, h->cell_start[0], ((size_t)g.gt + 8) * 4))) break;
-    if ((rc = ensure(h, h->cell_start[1], ((size_t)g.gt + 8) * 4))) break;
+    if (h->tile_mode) {
+      const size_t nsub = (size_t)h->nsx * h->nsy;
+      for (int q = 0; q < 2; ++q) {
+        if ((rc = ensure(h, h->sub_off[q], (nsub + 8) * 4))) break;
+        if ((rc = ensure(h, h->sub_cnt[q], (nsub + 8) * 4))) break;
+      }
+      if (rc) break;
+    } else {
+      if ((rc = ensure(h, h->cell_start[0], ((size_t)g.gt + 8) * 4))) break;
+      if ((rc = ensure(h, h->cell_start[1], ((size_t)g.gt + 8) * 4))) break;
+    }
     if ((rc = ensure(h, h->scan_tmp, scan_tmp_words((uint64_t)g.gt + 1) * 4))) break;
     if ((rc = ensure_soa(h, 0, 1))) break;
     if ((rc = ensure_soa(h, 1, 1))) break;
@@ -952,10 +1074,45 @@ int ABM_API(set_agents)(abm_handle* h, int64_t n, const int64_t* id, const int64
   const uint64_t words = bitmap_words((uint64_t)next_id);
   if ((rc = ensure(h, h->bits, (words + 4) * 4))) return rc;
   ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, h->stream));
-  uint32_t* start = (uint32_t*)h->cell_start[dst].p;
-  ABM_CK(h, dev_memset(start, 0, ((size_t)g.gt + 1) * 4, h->stream));
   ABM_CK(h, dev_memset((uint32_t*)h->counters.p + CTR_ERR, 0, 4, h->stream));
-  if (n > 0) {
+  if (h->tile_mode) { /* group by 8x8 sub-tile: histogram, scan, scatter */
+    const uint64_t nsub = (uint64_t)h->nsx * h->nsy;
+    uint32_t* scnt = (uint32_t*)h->sub_cnt[dst].p;
+    uint32_t* soff = (uint32_t*)h->sub_off[dst].p;
+    ABM_CK(h, dev_memset(scnt, 0, nsub * 4, h->stream));
+    if (n > 0) {
+      if ((rc = ensure(h, h->stage, (size_t)n * 32 + 64))) return rc;
+      if ((rc = ensure(h, h->ingest_sub, (size_t)n * 4))) return rc;
+      int64_t* s_id = (int64_t*)h->stage.p;
+      int64_t* s_x = s_id + n;
+      int64_t* s_y = s_x + n;
+      double* s_e = (double*)(s_y + n);
+      ABM_CK(h, copy_h2d(s_id, id, (size_t)n * 8, h->stream));
+      ABM_CK(h, copy_h2d(s_x, x, (size_t)n * 8, h->stream));
+      ABM_CK(h, copy_h2d(s_y, y, (size_t)n * 8, h->stream));
+      ABM_CK(h, copy_h2d(s_e, energy, (size_t)n * 8, h->stream));
+      IngestTileBody ib;
+      ib.g = g; ib.nsx = h->nsx; ib.hid = s_id; ib.hx = s_x; ib.hy = s_y; ib.he = s_e; ib.next_id = next_id;
+      ib.cell = (uint32_t*)h->cell[tmp].p; ib.id = (uint32_t*)h->id[tmp].p; ib.energy = (double*)h->energy[tmp].p;
+      ib.slot = (uint32_t*)h->slot.p; ib.sub = (uint32_t*)h->ingest_sub.p; ib.sub_cnt = scnt;
+      ib.alive_bits = (uint32_t*)h->bits.p; ib.err = (uint32_t*)h->counters.p + CTR_ERR;
+      launch_foreach(h->stream, ib, (uint64_t)n);
+      if ((rc = check_launch(h, "tile ingest"))) return rc;
+    }
+    ABM_CK(h, copy_d2d(soff, scnt, nsub * 4, h->stream));
+    ABM_CK(h, scan_exclusive_u32(h->stream, soff, nsub, (uint32_t*)h->scan_tmp.p));
+    if (n > 0) {
+      ScatterTileBody sb;
+      sb.cell = (const uint32_t*)h->cell[tmp].p; sb.id = (const uint32_t*)h->id[tmp].p; sb.energy = (const double*)h->energy[tmp].p;
+      sb.slot = (const uint32_t*)h->slot.p; sb.sub = (const uint32_t*)h->ingest_sub.p; sb.sub_off = soff;
+      sb.out_cell = (uint32_t*)h->cell[dst].p; sb.out_id = (uint32_t*)h->id[dst].p; sb.out_energy = (double*)h->energy[dst].p;
+      launch_foreach(h->stream, sb, (uint64_t)n);
+      if ((rc = check_launch(h, "tile ingest scatter"))) return rc;
+    }
+  }
+  uint32_t* start = h->tile_mode ? nullptr : (uint32_t*)h->cell_start[dst].p;
+  if (!h->tile_mode) ABM_CK(h, dev_memset(start, 0, ((size_t)g.gt + 1) * 4, h->stream));
+  if (n > 0 && !h->tile_mode) {
     if ((rc = ensure(h, h->stage, (size_t)n * 32 + 64))) return rc;
     int64_t* s_id = (int64_t*)h->stage.p;
     int64_t* s_x = s_id + n;
@@ -973,8 +1130,8 @@ int ABM_API(set_agents)(abm_handle* h, int64_t n, const int64_t* id, const int64
     launch_foreach(h->stream, ib, (uint64_t)n);
     if ((rc = check_launch(h, "ingest"))) return rc;
   }
-  ABM_CK(h, scan_exclusive_u32(h->stream, start, (uint64_t)g.gt + 1, (uint32_t*)h->scan_tmp.p));
-  if (n > 0) {
+  if (!h->tile_mode) ABM_CK(h, scan_exclusive_u32(h->stream, start, (uint64_t)g.gt + 1, (uint32_t*)h->scan_tmp.p));
+  if (n > 0 && !h->tile_mode) {
     View v = make_view(h);
     v.cell = (uint32_t*)h->cell[tmp].p; v.id = (uint32_t*)h->id[tmp].p; v.energy = (double*)h->energy[tmp].p;
     ScatterBody sb;
@@ -1072,7 +1229,7 @@ int ABM_API(step)(abm_handle* h, int64_t n_ticks) {
   h->tm_total.start(h->stream);
   for (int64_t t = 0; t < n_ticks; ++t) {
     if (h->tick >= 0xFFFFFFFFull) ABM_FAIL(h, ABM_E_CAPACITY, "tick counter exhausted");
-    if ((rc = tick_once(h))) return rc;
+    if ((rc = h->tile_mode ? tick_tile(h) : tick_once(h))) return rc;
   }
   h->tm_total.stop(h->stream);
   ABM_CK(h, stream_sync(h->stream));

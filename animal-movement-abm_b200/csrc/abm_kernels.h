@@ -172,8 +172,9 @@ ABM_HD void attractor_dir(const Params& p, int x, int y, int& dx, int& dy) {
 
 struct ProposeBody {
   View v;
-  uint32_t* pending;       /* worklist of undecided agents */
+  uint32_t* pending;       /* worklist of undecided agents (general path; null on the tile path) */
   uint32_t* pending_count;
+  uint32_t* birth_flags;   /* tile path: number of agents that will reproduce (sizes the output SoA); else null */
 
   ABM_HD void operator()(uint64_t i) const {
     const uint32_t k = (uint32_t)i;
@@ -234,7 +235,8 @@ struct ProposeBody {
     if (v.energy[k] - p.movement_cost < 0) st |= ST_DEAD;
     if (p.reproduce && rs.next_f64() <= p.reproduction_prob) st |= ST_BIRTH;
     v.state[k] = st;
-    if (!(st & ST_DECIDED)) pending[atomic_add(pending_count, 1u)] = k;
+    if (pending && !(st & ST_DECIDED)) pending[atomic_add(pending_count, 1u)] = k;
+    if (birth_flags && (st & ST_BIRTH)) atomic_add(birth_flags, 1u);
   }
 };
 

@@ -60,6 +60,32 @@ static inline void launch_foreach(abm_stream_t, const F& f, uint64_t n, const ch
   }
 }
 
+/* CTA-structured kernels: the body is a sequence of phases `ABM_CTA_FOR(t, NT) { ... } ABM_CTA_SYNC();` — on the
+ * device every thread runs each phase once (t = threadIdx.x) and phases are separated by __syncthreads(); here a
+ * phase is a loop over the thread indices (visited forwards or backwards), and CTAs run one after another in a
+ * shuffled order.  Code outside the phases must be uniform across the CTA. */
+#define ABM_CTA_FOR(t, NT) for (int t = 0; t < (int)(NT); ++t)
+#define ABM_CTA_SYNC() ((void)0)
+static inline uint32_t smem_min(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
+static inline uint32_t smem_max(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
+static inline uint32_t smem_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline uint32_t smem_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+
+template <class F>
+static inline void launch_cta(abm_stream_t, const F& f, uint64_t n_ctas, int /*threads*/, size_t smem_bytes) {
+  ++g_emu_launches;
+  if (n_ctas == 0) return;
+  std::vector<uint32_t> smem((smem_bytes + 3) / 4 + 1);
+  EmuRand r = {g_emu_shuffle_seed * 31 + n_ctas * 0x9E3779B97F4A7C15ull + g_emu_launches};
+  uint64_t stride = 1;
+  if (n_ctas > 2) { stride = (r.next() % (n_ctas - 1)) + 1; while (std::__gcd(stride, n_ctas) != 1) ++stride; }
+  uint64_t b = r.next() % n_ctas;
+  for (uint64_t k = 0; k < n_ctas; ++k, b = (b + stride) % n_ctas) {
+    std::fill(smem.begin(), smem.end(), 0xA5A5A5A5u); /* shared memory starts uninitialised */
+    f((uint32_t)b, smem.data());
+  }
+}
+
 static inline abm_err_t dev_malloc(void** p, size_t bytes) { *p = calloc(bytes ? bytes : 1, 1); return *p ? 0 : 2; }
 static inline void dev_free(void* p) { free(p); }
 static inline abm_err_t dev_memset(void* p, int v, size_t bytes, abm_stream_t) { memset(p, v, bytes); return 0; }
@@ -106,6 +132,27 @@ static inline void launch_foreach(abm_stream_t s, const F& f, uint64_t n, const 
   ++g_launches;
   const uint64_t blocks = (n + 255) / 256;
   k_foreach<F><<<(unsigned)blocks, 256, 0, s>>>(f, n);
+}
+
+#define ABM_CTA_FOR(t, NT) for (int t = (int)threadIdx.x, abm_once_ = 1; abm_once_ && t < (int)(NT); abm_once_ = 0)
+#define ABM_CTA_SYNC() __syncthreads()
+ABM_D uint32_t smem_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
+ABM_D uint32_t smem_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
+ABM_D uint32_t smem_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+ABM_D uint32_t smem_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
+
+template <class F>
+__global__ void __launch_bounds__(256) k_cta(const F f) {
+  extern __shared__ __align__(16) uint32_t abm_smem[];
+  f(blockIdx.x, abm_smem);
+}
+
+template <class F>
+static inline void launch_cta(abm_stream_t s, const F& f, uint64_t n_ctas, int threads, size_t smem_bytes) {
+  if (n_ctas == 0) return;
+  ++g_launches;
+  if (smem_bytes > 48 * 1024) cudaFuncSetAttribute(k_cta<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  k_cta<F><<<(unsigned)n_ctas, threads, smem_bytes, s>>>(f);
 }
 
 static inline abm_err_t dev_malloc(void** p, size_t bytes) {

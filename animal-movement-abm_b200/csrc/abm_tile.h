@@ -1,0 +1,453 @@
+/*
+ * abm_tile.h — the tile ("T") stepping path: the same tick as abm_kernels.h, organised around 32x32-cell cores.
+ *
+ * Why.  The rank-ordered semantics of the reference only ever ask, about a cell c and an agent
+ * k: "is c occupied when k takes its turn?".  With by-id scheduling that is
+ *        maxOld[c] > k                      some agent with a higher id started the tick on c (it has not moved yet)
+ *     or minNew[c] < k                      some lower-id agent already ended its step on c and is still there
+ * and it is still unknown iff neither holds and
+ *        minMaybe[c] < k                    some lower-id agent whose step is not decided yet could end on c.
+ * Three u32 per cell therefore replace the per-cell agent lists (GridSpace.stored_ids) for `ifempty` walks
+ * (Agents.walk!), for the gregarious closest-neighbour search (src/agent_actions.jl:297-336) and, with a fourth
+ * (min id of all arrivals), for first-come grass eating (src/agent_actions.jl:139-147).
+ *
+ * How.  Agents are grouped by 8x8-cell sub-tile (sub_off/sub_cnt give each group's run in the SoA).  One CTA owns
+ * one core = one 32x32 grass tile; it stages the summaries of the core plus an 8-cell halo (a 48x48 window = 6x6
+ * sub-tile runs) in shared memory with shared-memory atomics, and iterates the fixed point there.  Decision bytes
+ * live in global memory: a decision is unique, so whichever CTA derives it first may publish it, and every CTA
+ * re-reads them each round.  What a window cannot settle (chains that leave it) goes to a worklist that is
+ * resolved by the same code over a small window centred on each agent, one warp-sized CTA per agent.
+ * The commit kernel gathers by DESTINATION: the CTA of a core collects every agent whose final cell lies in it,
+ * settles eating against the core's grass tile held in shared memory, applies energy and births, writes the
+ * survivors grouped by sub-tile into a chunk of the output SoA taken with one atomicAdd, and regrows and writes
+ * back the grass tile — one read and one write of every grass byte per tick.
+ */
+#ifndef ABM_TILE_H_
+#define ABM_TILE_H_
+
+#include "abm_kernels.h"
+
+namespace abm {
+
+enum { SUB = 8, CORE = 32, HALO = 8, WIN = CORE + 2 * HALO, MAX_RUNS = 36, TILE_THREADS = 256, AGENT_THREADS = 32 };
+enum { NONE32 = 0xFFFFFFFFu };
+
+struct SubIndex {
+  const uint32_t* off; /* first agent of the sub-tile's run */
+  const uint32_t* cnt;
+  int32_t nsx, nsy;    /* sub-tile grid */
+};
+
+ABM_HD int floor_div8(int a) { return a >= 0 ? a >> 3 : -((-a + 7) >> 3); }
+
+/* a window of cells [ox, ox+wx) x [oy, oy+wy) in unwrapped coordinates and the sub-tile runs that cover it */
+struct Window {
+  int ox, oy, wx, wy, ssx0, ssy0, nssx, nssy;
+  ABM_HD void set(int ox_, int oy_, int wx_, int wy_) {
+    ox = ox_; oy = oy_; wx = wx_; wy = wy_;
+    ssx0 = floor_div8(ox); ssy0 = floor_div8(oy);
+    nssx = floor_div8(ox + wx - 1) - ssx0 + 1;
+    nssy = floor_div8(oy + wy - 1) - ssy0 + 1;
+  }
+  ABM_HD int runs() const { return nssx * nssy; }
+  /* global sub-tile of run r, or -1 when it lies outside a non-periodic grid */
+  ABM_HD int sub_of_run(int r, const Geo& g, const SubIndex& si) const {
+    int sx = ssx0 + r % nssx, sy = ssy0 + r / nssx;
+    if (g.periodic) { sx = wrap_far(sx, si.nsx); sy = wrap_far(sy, si.nsy); }
+    else if (sx < 0 || sx >= si.nsx || sy < 0 || sy >= si.nsy) return -1;
+    return sy * si.nsx + sx;
+  }
+  /* window coordinates of an agent of run r standing on tcell c; false when outside the window */
+  ABM_HD bool locate(int r, uint32_t c, int& x, int& y) const {
+    x = (ssx0 + r % nssx) * 8 + (int)(c & 7) - ox;
+    y = (ssy0 + r / nssx) * 8 + (int)((c >> 5) & 7) - oy;
+    return x >= 0 && x < wx && y >= 0 && y < wy;
+  }
+};
+
+/* shared-memory run table: which slice of the SoA each of the window's sub-tiles occupies */
+struct RunTable {
+  uint32_t* off;    /* MAX_RUNS */
+  uint32_t* prefix; /* MAX_RUNS + 1 */
+  ABM_HD int find(uint32_t m, int nruns) const { /* run containing flat index m */
+    int lo = 0, hi = nruns;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (prefix[mid] <= m) lo = mid; else hi = mid; }
+    return lo;
+  }
+};
+
+struct Summaries {
+  uint32_t* max_old;
+  uint32_t* min_new;
+  uint32_t* min_maybe;
+  ABM_HD bool occupied(int c, uint32_t id) const { return max_old[c] > id || min_new[c] < id; }
+  ABM_HD bool unknown(int c, uint32_t id) const { return min_maybe[c] < id; }
+};
+
+enum { EV_PENDING = 0, EV_DECIDED = 1, EV_OUTSIDE = 2 };
+
+/* what an agent's current decision byte contributes to the window's summaries */
+ABM_HD void contribute(const Summaries& s, const Window& w, uint32_t id, int x, int y, uint8_t st) {
+  const int dir = st & ST_DIRMASK;
+  if (st & ST_DECIDED) {
+    if (!present(st)) return; /* killed and left no newborn: occupies nothing */
+    int fx = x, fy = y;
+    if (st & ST_MOVED) { int dx, dy; off8(dir, dx, dy); fx += dx; fy += dy; }
+    if (fx >= 0 && fx < w.wx && fy >= 0 && fy < w.wy) smem_min(&s.min_new[fy * w.wx + fx], id);
+    return;
+  }
+  if (dir == DIR_GREG) { /* moves for sure, onto any of its 8 neighbours */
+    for (int d = 0; d < 8; ++d) {
+      int dx, dy;
+      off8(d, dx, dy);
+      const int fx = x + dx, fy = y + dy;
+      if (fx >= 0 && fx < w.wx && fy >= 0 && fy < w.wy) smem_min(&s.min_maybe[fy * w.wx + fx], id);
+    }
+    return;
+  }
+  smem_min(&s.min_maybe[y * w.wx + x], id); /* `ifempty` walk: stays or steps onto its target */
+  int dx, dy;
+  off8(dir, dx, dy);
+  const int fx = x + dx, fy = y + dy;
+  if (fx >= 0 && fx < w.wx && fy >= 0 && fy < w.wy) smem_min(&s.min_maybe[fy * w.wx + fx], id);
+}
+
+/* one attempt to decide agent (id, st) at window cell (x, y); summaries are complete on [1, w-2]^2 */
+ABM_HD int evaluate(const View& v, const Summaries& s, const Window& w, uint32_t id, int x, int y, uint8_t st, uint8_t& out) {
+  const int dir = st & ST_DIRMASK;
+  if (dir != DIR_GREG) { /* walk!(...; ifempty = true) towards old + dir */
+    int dx, dy;
+    off8(dir, dx, dy);
+    const int tx = x + dx, ty = y + dy;
+    if (tx < 1 || tx > w.wx - 2 || ty < 1 || ty > w.wy - 2) return EV_OUTSIDE;
+    const int t = ty * w.wx + tx;
+    if (s.occupied(t, id)) { out = (uint8_t)(st | ST_DECIDED); return EV_DECIDED; }
+    if (s.unknown(t, id)) return EV_PENDING;
+    out = (uint8_t)(st | ST_DECIDED | ST_MOVED);
+    return EV_DECIDED;
+  }
+  /* random_walk_gregarious (src/agent_actions.jl:297-336) */
+  const int r = v.p.r, side = 2 * r + 1;
+  if (x - r < 1 || x + r > w.wx - 2 || y - r < 1 || y + r > w.wy - 2) return EV_OUTSIDE;
+  int closest = -1;
+  const int cells = side * side;
+  for (int q = 0; q < cells; ++q) { /* strict `<` over nearby_ids order == minimum of (d^2, β index) */
+    const int bit = v.greg_order[q];
+    const int c = (y + bit / side - r) * w.wx + (x + bit % side - r);
+    if (s.occupied(c, id)) { closest = bit; break; }
+    if (s.unknown(c, id)) return EV_PENDING;
+  }
+  AgentStream rs;
+  rs.init(v.p.seed, v.p.tick, id);
+  rs.n = 1; /* draw 0 was the execute_walk! uniform */
+  int d;
+  if (closest < 0) {
+    d = (int)rs.next_below(8); /* :334 */
+  } else {
+    const int bx = closest % side - r, by = closest / side - r;
+    double wgt[8], s1, s2;
+    for (int i = 0; i < 8; ++i) {
+      int ox, oy;
+      off8(i, ox, oy);
+      const int kx = ox - bx, ky = oy - by;
+      wgt[i] = v.lut[kx * kx + ky * ky];
+    }
+    s1 = wgt[0];
+    for (int i = 1; i < 8; ++i) s1 += wgt[i];
+    for (int i = 0; i < 8; ++i) wgt[i] = wgt[i] / s1;
+    s2 = wgt[0];
+    for (int i = 1; i < 8; ++i) s2 += wgt[i];
+    const double t = rs.next_f64() * s2; /* StatsBase.sample(rng, wv) */
+    int i = 0;
+    double cw = wgt[0];
+    while (cw < t && i < 7) { ++i; cw += wgt[i]; }
+    d = i;
+  }
+  out = (uint8_t)((st & (ST_DEAD | ST_BIRTH)) | d | ST_DECIDED | ST_MOVED); /* move_agent!, :331 */
+  return EV_DECIDED;
+}
+
+/*
+ * Kernel K_A / K_F.  mode 0: CTA b resolves core b (48x48 window, every agent it can settle, up to max_rounds
+ * rounds) and lists the core's agents that stay undecided.  mode 1: CTA b settles pending agent in[b] alone, over
+ * the smallest window that holds everything its rule looks at, and re-lists it when that is not yet possible.
+ */
+struct ResolveWindow {
+  View v;
+  SubIndex si;
+  int32_t mode, cores_x, max_rounds, nthreads;
+  const uint32_t* in;
+  uint32_t* out;
+  uint32_t* out_count;
+
+  static size_t smem_bytes(int wx, int wy) { return (size_t)(3 * wx * wy + MAX_RUNS + MAX_RUNS + 1 + 8) * 4; }
+
+  ABM_HD void operator()(uint32_t cta, uint32_t* smem) const {
+    Window w;
+    uint32_t target = NONE32;
+    int own_lo = 0, own_hi = 0;
+    if (mode == 0) {
+      const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x);
+      w.set(cx * CORE - HALO, cy * CORE - HALO, WIN, WIN);
+      own_lo = HALO; own_hi = HALO + CORE;
+    } else {
+      target = in[cta];
+      int x, y;
+      dec(v.g, v.cell[target], x, y);
+      const int q = (v.state[target] & ST_DIRMASK) == DIR_GREG ? v.p.r + 1 : 2;
+      w.set(x - q, y - q, 2 * q + 1, 2 * q + 1);
+    }
+    const int cells = w.wx * w.wy, nruns = w.runs(), NT = nthreads;
+    Summaries s;
+    s.max_old = smem; s.min_new = smem + cells; s.min_maybe = smem + 2 * cells;
+    RunTable rt;
+    rt.off = smem + 3 * cells; rt.prefix = rt.off + MAX_RUNS;
+    uint32_t* flags = rt.prefix + MAX_RUNS + 1; /* [0] progress, [1] undecided agents this CTA answers for */
+
+    ABM_CTA_FOR(t, NT) {
+      for (int r = t; r < nruns; r += NT) {
+        const int sub = w.sub_of_run(r, v.g, si);
+        rt.off[r] = sub < 0 ? 0u : si.off[sub];
+        rt.prefix[r + 1] = sub < 0 ? 0u : si.cnt[sub]; /* counts, turned into a prefix below */
+      }
+      for (int c = t; c < cells; c += NT) s.max_old[c] = 0u;
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) {
+      if (t == 0) {
+        uint32_t run = 0;
+        rt.prefix[0] = 0;
+        for (int r = 0; r < nruns; ++r) { run += rt.prefix[r + 1]; rt.prefix[r + 1] = run; }
+      }
+    }
+    ABM_CTA_SYNC();
+    const uint32_t M = rt.prefix[nruns];
+    ABM_CTA_FOR(t, NT) { /* static part: highest id that starts the tick on each cell */
+      for (uint32_t m = (uint32_t)t; m < M; m += (uint32_t)NT) {
+        const int r = rt.find(m, nruns);
+        const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
+        int x, y;
+        if (w.locate(r, v.cell[a], x, y)) smem_max(&s.max_old[y * w.wx + x], v.id[a]);
+      }
+    }
+    ABM_CTA_SYNC();
+
+    for (int round = 0; round < max_rounds; ++round) {
+      ABM_CTA_FOR(t, NT) {
+        for (int c = t; c < cells; c += NT) { s.min_new[c] = NONE32; s.min_maybe[c] = NONE32; }
+        if (t == 0) { flags[0] = 0; flags[1] = 0; }
+      }
+      ABM_CTA_SYNC();
+      ABM_CTA_FOR(t, NT) {
+        for (uint32_t m = (uint32_t)t; m < M; m += (uint32_t)NT) {
+          const int r = rt.find(m, nruns);
+          const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
+          int x, y;
+          if (w.locate(r, v.cell[a], x, y)) contribute(s, w, v.id[a], x, y, load_state(&v.state[a]));
+        }
+      }
+      ABM_CTA_SYNC();
+      ABM_CTA_FOR(t, NT) {
+        for (uint32_t m = (uint32_t)t; m < M; m += (uint32_t)NT) {
+          const int r = rt.find(m, nruns);
+          const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
+          if (mode == 1 && a != target) continue;
+          const uint8_t st = load_state(&v.state[a]);
+          if (st & ST_DECIDED) continue;
+          int x, y;
+          if (!w.locate(r, v.cell[a], x, y)) continue;
+          uint8_t nst = st;
+          const int res = evaluate(v, s, w, v.id[a], x, y, st, nst);
+          if (res == EV_DECIDED) { v.state[a] = nst; flags[0] = 1; }
+          else if (mode == 1 || (x >= own_lo && x < own_hi && y >= own_lo && y < own_hi)) smem_add(&flags[1], 1u);
+        }
+      }
+      ABM_CTA_SYNC();
+      const uint32_t progress = flags[0], left = flags[1];
+      ABM_CTA_SYNC();
+      if (left == 0 || progress == 0) break;
+    }
+    ABM_CTA_FOR(t, NT) { /* hand what is still open to the next pass */
+      for (uint32_t m = (uint32_t)t; m < M; m += (uint32_t)NT) {
+        const int r = rt.find(m, nruns);
+        const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
+        if (mode == 1 && a != target) continue;
+        if (load_state(&v.state[a]) & ST_DECIDED) continue;
+        int x, y;
+        if (!w.locate(r, v.cell[a], x, y)) continue;
+        if (mode == 1 || (x >= own_lo && x < own_hi && y >= own_lo && y < own_hi)) out[atomic_add(out_count, 1u)] = a;
+      }
+    }
+  }
+};
+
+/*
+ * Kernel K_BC: commit by destination + grass + re-grouping.  reduce_energy! / eat! / reproduce!
+ * (src/agent_actions.jl:54-67, :85-92, :139-147, :172-178) and custom_model_step! (src/model_actions.jl:18-30).
+ */
+struct CommitTile {
+  View v;
+  SubIndex si;
+  int32_t cores_x;
+  uint32_t* out_cell; uint32_t* out_id; double* out_energy;
+  uint32_t* new_off; uint32_t* new_cnt; /* next tick's sub-tile runs */
+  uint32_t* cursor;                     /* next free slot of the output SoA */
+  uint32_t* birth_pos; uint32_t* birth_parent; uint32_t* birth_count; uint32_t* birth_bits;
+
+  static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 16 * 3 + MAX_RUNS + MAX_RUNS + 1 + 8) * 4; }
+
+  ABM_HD void operator()(uint32_t cta, uint32_t* smem) const {
+    const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x);
+    Window w;
+    w.set(cx * CORE - HALO, cy * CORE - HALO, WIN, WIN);
+    const int nruns = w.runs(), NT = TILE_THREADS;
+    uint32_t* min_all = smem;                         /* lowest id arriving on each core cell: the one that eats */
+    uint8_t* grass = (uint8_t*)(smem + CORE * CORE);  /* the core's grass tile */
+    uint32_t* counts = smem + CORE * CORE + CORE * CORE / 4; /* per sub-tile of the core: arrivals, base, cursor */
+    uint32_t* base = counts + 16;
+    uint32_t* cur = base + 16;
+    RunTable rt;
+    rt.off = cur + 16; rt.prefix = rt.off + MAX_RUNS;
+    uint32_t* misc = rt.prefix + MAX_RUNS + 1;
+    const uint32_t tile = cta; /* CORE == TILE: core b is grass tile b */
+    uint32_t* gtile = (uint32_t*)(v.grass + (size_t)tile * TILE_CELLS);
+
+    ABM_CTA_FOR(t, NT) {
+      for (int r = t; r < nruns; r += NT) {
+        const int sub = w.sub_of_run(r, v.g, si);
+        rt.off[r] = sub < 0 ? 0u : si.off[sub];
+        rt.prefix[r + 1] = sub < 0 ? 0u : si.cnt[sub];
+      }
+      for (int c = t; c < CORE * CORE; c += NT) min_all[c] = NONE32;
+      for (int c = t; c < CORE * CORE / 4; c += NT) ((uint32_t*)grass)[c] = gtile[c];
+      if (t < 16) counts[t] = 0;
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) {
+      if (t == 0) {
+        uint32_t run = 0;
+        rt.prefix[0] = 0;
+        for (int r = 0; r < nruns; ++r) { run += rt.prefix[r + 1]; rt.prefix[r + 1] = run; }
+      }
+    }
+    ABM_CTA_SYNC();
+    const uint32_t M = rt.prefix[nruns];
+    ABM_CTA_FOR(t, NT) { /* pass 1: who lands in the core */
+      for (uint32_t m = (uint32_t)t; m < M; m += (uint32_t)NT) {
+        const int r = rt.find(m, nruns);
+        const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
+        int x, y;
+        if (!w.locate(r, v.cell[a], x, y)) continue;
+        const uint8_t st = v.state[a];
+        if (!(st & ST_DECIDED)) { atomic_or(v.err, ERR_INTERNAL); continue; }
+        if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); x += dx; y += dy; }
+        x -= HALO; y -= HALO;
+        if (x < 0 || x >= CORE || y < 0 || y >= CORE) continue;
+        smem_min(&min_all[y * CORE + x], v.id[a]);
+        const uint32_t add = ((st & ST_DEAD) ? 0u : 1u) + ((st & ST_BIRTH) ? 1u : 0u);
+        if (add) smem_add(&counts[(y >> 3) * 4 + (x >> 3)], add);
+      }
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) {
+      if (t == 0) {
+        uint32_t total = 0;
+        for (int q = 0; q < 16; ++q) { base[q] = total; total += counts[q]; }
+        const uint32_t chunk = total ? atomic_add(cursor, total) : 0u;
+        misc[0] = chunk;
+        for (int q = 0; q < 16; ++q) {
+          cur[q] = chunk + base[q];
+          const int sub = (cy * 4 + (q >> 2)) * si.nsx + cx * 4 + (q & 3);
+          new_off[sub] = chunk + base[q];
+          new_cnt[sub] = counts[q];
+        }
+      }
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) { /* pass 2: energy, eating, births, output */
+      for (uint32_t m = (uint32_t)t; m < M; m += (uint32_t)NT) {
+        const int r = rt.find(m, nruns);
+        const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
+        int x, y;
+        if (!w.locate(r, v.cell[a], x, y)) continue;
+        const uint8_t st = v.state[a];
+        if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); x += dx; y += dy; }
+        x -= HALO; y -= HALO;
+        if (x < 0 || x >= CORE || y < 0 || y >= CORE) continue;
+        const int lc = y * CORE + x;
+        const uint32_t id = v.id[a];
+        double e = v.energy[a] - v.p.movement_cost; /* walk_ocurred is always true */
+        if (v.p.eat && min_all[lc] == id && (grass[lc] & GRASS_GROWN)) { /* killed agents still eat (Appendix D-1) */
+          e += v.p.delta_energy;
+          grass[lc] = (uint8_t)(grass[lc] & ~GRASS_GROWN);
+        }
+        if (st & ST_BIRTH) e /= 2;
+        const uint32_t fc = (tile << 10) | (uint32_t)lc;
+        const int q = (y >> 3) * 4 + (x >> 3);
+        if (!(st & ST_DEAD)) {
+          const uint32_t pos = smem_add(&cur[q], 1u);
+          out_cell[pos] = fc; out_id[pos] = id; out_energy[pos] = e;
+        }
+        if (st & ST_BIRTH) { /* offspring on the parent's cell with the halved energy; its id is patched in afterwards */
+          const uint32_t pos = smem_add(&cur[q], 1u);
+          out_cell[pos] = fc; out_id[pos] = 0u; out_energy[pos] = e;
+          const uint32_t b = atomic_add(birth_count, 1u);
+          birth_pos[b] = pos; birth_parent[b] = id;
+          atomic_or(&birth_bits[id >> 5], 1u << (id & 31));
+        }
+      }
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) { /* custom_model_step! on the tile, then one coalesced write-back */
+      if (t < CORE * CORE / 16) {
+        uint32_t* w4 = (uint32_t*)grass + 4 * t;
+        uint32_t wb = 0;
+        if (v.p.walkmap_regrowth) wb = v.walkbits[tile * 32 + (uint32_t)(t >> 1)] >> ((t & 1) * 16);
+        for (int q = 0; q < 4; ++q) gtile[4 * t + q] = regrow4(w4[q], (uint32_t)v.p.regrowth_time, wb >> (4 * q), v.p.walkmap_regrowth != 0);
+      }
+    }
+  }
+};
+
+/* offspring ids: nextid(model) in the order of the parents' ids */
+struct BirthIdBody {
+  const uint32_t* birth_pos; const uint32_t* birth_parent; const uint32_t* birth_bits; const uint32_t* birth_prefix;
+  uint32_t next_id;
+  uint32_t* out_id;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t pid = birth_parent[i], wd = pid >> 5;
+    const uint32_t rank = birth_prefix[wd] + (uint32_t)popc(birth_bits[wd] & ((1u << (pid & 31)) - 1u));
+    out_id[birth_pos[i]] = next_id + rank;
+  }
+};
+
+/* abm_set_agents on the tile path: host records -> SoA grouped by sub-tile */
+struct IngestTileBody {
+  Geo g; int32_t nsx;
+  const int64_t* hid; const int64_t* hx; const int64_t* hy; const double* he;
+  int64_t next_id;
+  uint32_t* cell; uint32_t* id; double* energy; uint32_t* slot; uint32_t* sub;
+  uint32_t* sub_cnt; uint32_t* alive_bits; uint32_t* err;
+  ABM_HD void operator()(uint64_t i) const {
+    const int64_t x = hx[i], y = hy[i], a = hid[i];
+    if (x < 1 || x > g.nx || y < 1 || y > g.ny || a < 1 || a >= next_id) { atomic_or(err, ERR_INTERNAL); cell[i] = 0; id[i] = 0; energy[i] = 0; sub[i] = NONE32; return; }
+    const uint32_t bit = 1u << ((uint32_t)a & 31);
+    if (atomic_or(&alive_bits[(uint32_t)a >> 5], bit) & bit) atomic_or(err, ERR_INTERNAL);
+    const uint32_t st = (uint32_t)(((y - 1) >> 3) * nsx + ((x - 1) >> 3));
+    cell[i] = enc(g, (int)(x - 1), (int)(y - 1)); id[i] = (uint32_t)a; energy[i] = he[i];
+    sub[i] = st; slot[i] = atomic_add(&sub_cnt[st], 1u);
+  }
+};
+struct ScatterTileBody {
+  const uint32_t* cell; const uint32_t* id; const double* energy; const uint32_t* slot; const uint32_t* sub;
+  const uint32_t* sub_off;
+  uint32_t* out_cell; uint32_t* out_id; double* out_energy;
+  ABM_HD void operator()(uint64_t i) const {
+    if (sub[i] == NONE32) return;
+    const uint32_t pos = sub_off[sub[i]] + slot[i];
+    out_cell[pos] = cell[i]; out_id[pos] = id[i]; out_energy[pos] = energy[i];
+  }
+};
+
+}  // namespace abm
+#endif /* ABM_TILE_H_ */

@@ -180,3 +180,55 @@ def test_gpu_astar_paths_match_oracle(libabm, oracle, metric, penalty, periodic)
         b.step(1)
         assert_same_state(b.snapshot(), a.snapshot(), f"route following tick {t}")
     _same_paths(a, b, a.get_agents()[0])
+
+
+@pytest.mark.parametrize("name", ["tile_rw_96x64", "tile_gregarious_r3_96x96", "tile_gregarious_r7_p0_64x64", "tile_attractor_128x64", "tile_crowded_64x64"])
+def test_emulated_tile_path_with_per_agent_windows(emu, oracle, name, monkeypatch):
+    """One in-window round only: most conflicts are then left to the per-agent windows (resolve_agents)."""
+    monkeypatch.setenv("ABM_TILE_ROUNDS", "1")
+    cfgkw, w, state, ticks = build_case(name)
+    a, b = load_case(oracle, cfgkw, w), load_case(emu, cfgkw, w)
+    used = 0
+    for t in range(8):
+        a.step(1)
+        b.step(1)
+        used += b.kernel_stats().get("resolve_agents", dict(launches=0))["launches"]
+        assert_same_state(b.snapshot(), a.snapshot(), f"{name} tick {t}")
+    assert used > 0
+
+
+@pytest.mark.parametrize("name", ["tile_rw_96x64", "tile_gregarious_r3_96x96", "tile_walkmap_128x96"])
+def test_emulated_general_path_on_tile_sized_grids(emu, oracle, name):
+    """abm_config.reserved0 = 1 forces the general path: both engine paths must agree with the oracle."""
+    cfgkw, w, state, ticks = build_case(name)
+    a, b = load_case(oracle, cfgkw, w), load_case(emu, dict(cfgkw, reserved0=1), w)
+    for t in range(6):
+        a.step(1)
+        b.step(1)
+        assert "resolve_tiles" not in {k for k, v in b.kernel_stats().items() if v["launches"]}
+        assert_same_state(b.snapshot(), a.snapshot(), f"{name} tick {t}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wt,per,terr,n,nx,ny,extra", [
+    (0, 1, 0, 60000, 512, 256, {}),
+    (0, 0, 0, 60000, 256, 512, {}),
+    (1, 0, 0, 60000, 512, 256, dict(prob_random_walk=0.6)),
+    (2, 1, 0, 40000, 384, 384, dict(visual_distance=3)),
+    (2, 1, 0, 20000, 256, 256, dict(visual_distance=7, prob_random_walk=0.5)),
+    (4, 1, 1, 60000, 512, 512, dict(walkmap_regrowth=1)),
+])
+def test_gpu_tile_path_matches_oracle(libabm, oracle, wt, per, terr, n, nx, ny, extra):
+    from conftest import make_case
+    kw = dict(reproduction_prob=0.02, regrowth_time=6, delta_energy=3.0)
+    kw.update(extra)
+    cfgkw, w = make_case(nx, ny, n, wt, per, terrain=bool(terr), seed=77, **kw)
+    a, b = load_case(oracle, cfgkw, w), load_case(libabm, cfgkw, w)
+    for t in range(12):
+        a.step(1)
+        b.step(1)
+        assert "commit_tiles" in {k for k, v in b.kernel_stats().items() if v["launches"]}
+        assert_same_state(b.snapshot(), a.snapshot(), f"wt {wt} tick {t}")
+    a.step(20)
+    b.step(20)
+    assert_same_state(b.snapshot(), a.snapshot(), f"wt {wt} tick 32")
