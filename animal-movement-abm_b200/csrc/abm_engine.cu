@@ -757,7 +757,7 @@ static int tick_tile(abm_handle* h) {
       ResolveWindow rw;
       rw.v = v; rw.si = si; rw.mode = 0; rw.cores_x = h->g.nx / CORE; rw.max_rounds = h->tile_rounds; rw.nthreads = TILE_THREADS;
       rw.in = nullptr; rw.out = (uint32_t*)h->pend[0].p; rw.out_count = ctr + CTR_PEND_A;
-      { ProfScope ps(h->prof, h->stream, "resolve_tiles", n); launch_cta(h->stream, rw, cores, TILE_THREADS, ResolveWindow::smem_bytes(WIN, WIN)); }
+      { ProfScope ps(h->prof, h->stream, "resolve_tiles", n); launch_cta(h->stream, rw, cores, TILE_THREADS, ResolveWindow::smem_bytes_core()); }
       if ((rc = check_launch(h, "tile resolve"))) return rc;
     }
   }

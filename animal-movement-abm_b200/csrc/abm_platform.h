@@ -151,7 +151,12 @@ template <class F>
 static inline void launch_cta(abm_stream_t s, const F& f, uint64_t n_ctas, int threads, size_t smem_bytes) {
   if (n_ctas == 0) return;
   ++g_launches;
-  if (smem_bytes > 48 * 1024) cudaFuncSetAttribute(k_cta<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  static bool configured = false; /* per kernel instantiation */
+  if (!configured) {
+    cudaFuncSetAttribute(k_cta<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_cta<F>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
   k_cta<F><<<(unsigned)n_ctas, threads, smem_bytes, s>>>(f);
 }
 

@@ -31,6 +31,7 @@ namespace abm {
 
 enum { SUB = 8, CORE = 32, HALO = 8, WIN = CORE + 2 * HALO, MAX_RUNS = 36, TILE_THREADS = 256, AGENT_THREADS = 32 };
 enum { NONE32 = 0xFFFFFFFFu };
+enum { ULIST_CAP = 768, ARRIVE_CAP = 768 }; /* shared-memory work lists of a core; larger populations take the streaming code */
 
 struct SubIndex {
   const uint32_t* off; /* first agent of the sub-tile's run */
@@ -112,6 +113,31 @@ ABM_HD void contribute(const Summaries& s, const Window& w, uint32_t id, int x, 
   if (fx >= 0 && fx < w.wx && fy >= 0 && fy < w.wy) smem_min(&s.min_maybe[fy * w.wx + fx], id);
 }
 
+/* the cells an undecided agent may still end on, into one min_maybe buffer */
+ABM_HD void contribute_maybe(uint32_t* min_maybe, const Window& w, uint32_t id, int x, int y, uint8_t st) {
+  const int dir = st & ST_DIRMASK;
+  if (dir == DIR_GREG) {
+    for (int d = 0; d < 8; ++d) {
+      int dx, dy;
+      off8(d, dx, dy);
+      const int fx = x + dx, fy = y + dy;
+      if (fx >= 0 && fx < w.wx && fy >= 0 && fy < w.wy) smem_min(&min_maybe[fy * w.wx + fx], id);
+    }
+    return;
+  }
+  smem_min(&min_maybe[y * w.wx + x], id);
+  int dx, dy;
+  off8(dir, dx, dy);
+  const int fx = x + dx, fy = y + dy;
+  if (fx >= 0 && fx < w.wx && fy >= 0 && fy < w.wy) smem_min(&min_maybe[fy * w.wx + fx], id);
+}
+/* a decided, still present agent: its final cell */
+ABM_HD void contribute_final(uint32_t* min_new, const Window& w, uint32_t id, int x, int y, uint8_t st) {
+  if (!present(st)) return;
+  if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); x += dx; y += dy; }
+  if (x >= 0 && x < w.wx && y >= 0 && y < w.wy) smem_min(&min_new[y * w.wx + x], id);
+}
+
 /* one attempt to decide agent (id, st) at window cell (x, y); summaries are complete on [1, w-2]^2 */
 ABM_HD int evaluate(const View& v, const Summaries& s, const Window& w, uint32_t id, int x, int y, uint8_t st, uint8_t& out) {
   const int dir = st & ST_DIRMASK;
@@ -181,8 +207,115 @@ struct ResolveWindow {
   uint32_t* out_count;
 
   static size_t smem_bytes(int wx, int wy) { return (size_t)(3 * wx * wy + MAX_RUNS + MAX_RUNS + 1 + 8) * 4; }
+  static size_t smem_bytes_core() { return (size_t)(4 * WIN * WIN + 6 * ULIST_CAP + MAX_RUNS + MAX_RUNS + 1 + 16) * 4; }
+
+  /* Core window with the undecided agents held in a shared-memory work list: each round touches only what is still
+   * open.  min_new only ever gains entries (decisions are final), min_maybe is rebuilt per round from the list (double
+   * buffered).  Agents are read from global memory exactly once.  Returns false (uniformly) when the list overflows. */
+  ABM_HD bool core_fast(uint32_t cta, uint32_t* smem) const {
+    Window w;
+    const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x);
+    w.set(cx * CORE - HALO, cy * CORE - HALO, WIN, WIN);
+    const int cells = WIN * WIN, nruns = w.runs(), NT = TILE_THREADS;
+    uint32_t* max_old = smem;
+    uint32_t* min_new = smem + cells;
+    uint32_t* maybe[2] = {smem + 2 * cells, smem + 3 * cells};
+    uint32_t* lst = smem + 4 * cells; /* two lists x {agent index, id, x | y << 8 | state << 16} */
+    uint32_t* l_a[2] = {lst, lst + 3 * ULIST_CAP};
+    uint32_t* l_id[2] = {lst + ULIST_CAP, lst + 4 * ULIST_CAP};
+    uint32_t* l_xs[2] = {lst + 2 * ULIST_CAP, lst + 5 * ULIST_CAP};
+    RunTable rt;
+    rt.off = lst + 6 * ULIST_CAP; rt.prefix = rt.off + MAX_RUNS;
+    uint32_t* cnt = rt.prefix + MAX_RUNS + 1; /* [0],[1] list lengths, [2] progress, [3] open agents of the core, [4] overflow */
+
+    ABM_CTA_FOR(t, NT) {
+      for (int r = t; r < nruns; r += NT) {
+        const int sub = w.sub_of_run(r, v.g, si);
+        rt.off[r] = sub < 0 ? 0u : si.off[sub];
+        rt.prefix[r + 1] = sub < 0 ? 0u : si.cnt[sub];
+      }
+      for (int c = t; c < cells; c += NT) { max_old[c] = 0u; min_new[c] = NONE32; maybe[0][c] = NONE32; }
+      if (t < 8) cnt[t] = 0;
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) {
+      if (t == 0) {
+        uint32_t run = 0;
+        rt.prefix[0] = 0;
+        for (int r = 0; r < nruns; ++r) { run += rt.prefix[r + 1]; rt.prefix[r + 1] = run; }
+      }
+    }
+    ABM_CTA_SYNC();
+    const uint32_t M = rt.prefix[nruns];
+    ABM_CTA_FOR(t, NT) {
+      for (uint32_t m = (uint32_t)t; m < M; m += (uint32_t)NT) {
+        const int r = rt.find(m, nruns);
+        const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
+        int x, y;
+        if (!w.locate(r, v.cell[a], x, y)) continue;
+        const uint32_t id = v.id[a];
+        const uint8_t st = load_state(&v.state[a]);
+        smem_max(&max_old[y * WIN + x], id);
+        if (st & ST_DECIDED) { contribute_final(min_new, w, id, x, y, st); continue; }
+        const uint32_t slot = smem_add(&cnt[0], 1u);
+        if (slot >= ULIST_CAP) { cnt[4] = 1; continue; }
+        l_a[0][slot] = a; l_id[0][slot] = id; l_xs[0][slot] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)st << 16);
+        contribute_maybe(maybe[0], w, id, x, y, st);
+      }
+    }
+    ABM_CTA_SYNC();
+    if (cnt[4]) return false;
+    int cur = 0;
+    for (int round = 0; round < max_rounds; ++round) {
+      const uint32_t nu = cnt[cur];
+      if (nu == 0) break;
+      ABM_CTA_SYNC();
+      ABM_CTA_FOR(t, NT) {
+        for (int c = t; c < cells; c += NT) maybe[cur ^ 1][c] = NONE32;
+        if (t == 0) { cnt[cur ^ 1] = 0; cnt[2] = 0; cnt[3] = 0; }
+      }
+      ABM_CTA_SYNC();
+      Summaries s;
+      s.max_old = max_old; s.min_new = min_new; s.min_maybe = maybe[cur];
+      ABM_CTA_FOR(t, NT) {
+        for (uint32_t u = (uint32_t)t; u < nu; u += (uint32_t)NT) {
+          const uint32_t a = l_a[cur][u], id = l_id[cur][u], xs = l_xs[cur][u];
+          const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
+          const uint8_t st = (uint8_t)(xs >> 16);
+          uint8_t nst = st;
+          if (evaluate(v, s, w, id, x, y, st, nst) == EV_DECIDED) {
+            v.state[a] = nst;
+            contribute_final(min_new, w, id, x, y, nst);
+            cnt[2] = 1;
+          } else {
+            const uint32_t slot = smem_add(&cnt[cur ^ 1], 1u);
+            l_a[cur ^ 1][slot] = a; l_id[cur ^ 1][slot] = id; l_xs[cur ^ 1][slot] = xs;
+            contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
+            if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&cnt[3], 1u);
+          }
+        }
+      }
+      ABM_CTA_SYNC();
+      cur ^= 1;
+      if (cnt[3] == 0 || cnt[2] == 0) break;
+    }
+    ABM_CTA_SYNC();
+    const uint32_t nu = cnt[cur];
+    ABM_CTA_FOR(t, NT) { /* the core's agents that stay open go to the per-agent windows */
+      for (uint32_t u = (uint32_t)t; u < nu; u += (uint32_t)NT) {
+        const uint32_t xs = l_xs[cur][u];
+        const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
+        if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) out[atomic_add(out_count, 1u)] = l_a[cur][u];
+      }
+    }
+    return true;
+  }
 
   ABM_HD void operator()(uint32_t cta, uint32_t* smem) const {
+    if (mode == 0) {
+      if (core_fast(cta, smem)) return;
+      ABM_CTA_SYNC();
+    }
     Window w;
     uint32_t target = NONE32;
     int own_lo = 0, own_hi = 0;
@@ -294,7 +427,7 @@ struct CommitTile {
   uint32_t* cursor;                     /* next free slot of the output SoA */
   uint32_t* birth_pos; uint32_t* birth_parent; uint32_t* birth_count; uint32_t* birth_bits;
 
-  static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 16 * 3 + MAX_RUNS + MAX_RUNS + 1 + 8) * 4; }
+  static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 16 * 3 + MAX_RUNS + MAX_RUNS + 1 + 8 + 3 * ARRIVE_CAP) * 4; }
 
   ABM_HD void operator()(uint32_t cta, uint32_t* smem) const {
     const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x);
@@ -308,7 +441,10 @@ struct CommitTile {
     uint32_t* cur = base + 16;
     RunTable rt;
     rt.off = cur + 16; rt.prefix = rt.off + MAX_RUNS;
-    uint32_t* misc = rt.prefix + MAX_RUNS + 1;
+    uint32_t* misc = rt.prefix + MAX_RUNS + 1; /* [0] chunk, [1] arrivals listed, [2] list overflow */
+    uint32_t* ar_a = misc + 8;                 /* arrivals: agent index, id, core cell | state << 16 */
+    uint32_t* ar_id = ar_a + ARRIVE_CAP;
+    uint32_t* ar_cs = ar_id + ARRIVE_CAP;
     const uint32_t tile = cta; /* CORE == TILE: core b is grass tile b */
     uint32_t* gtile = (uint32_t*)(v.grass + (size_t)tile * TILE_CELLS);
 
@@ -321,6 +457,7 @@ struct CommitTile {
       for (int c = t; c < CORE * CORE; c += NT) min_all[c] = NONE32;
       for (int c = t; c < CORE * CORE / 4; c += NT) ((uint32_t*)grass)[c] = gtile[c];
       if (t < 16) counts[t] = 0;
+      if (t < 8) misc[t] = 0;
     }
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, NT) {
@@ -343,9 +480,13 @@ struct CommitTile {
         if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); x += dx; y += dy; }
         x -= HALO; y -= HALO;
         if (x < 0 || x >= CORE || y < 0 || y >= CORE) continue;
-        smem_min(&min_all[y * CORE + x], v.id[a]);
+        const uint32_t id = v.id[a];
+        smem_min(&min_all[y * CORE + x], id);
         const uint32_t add = ((st & ST_DEAD) ? 0u : 1u) + ((st & ST_BIRTH) ? 1u : 0u);
         if (add) smem_add(&counts[(y >> 3) * 4 + (x >> 3)], add);
+        const uint32_t slot = smem_add(&misc[1], 1u);
+        if (slot < ARRIVE_CAP) { ar_a[slot] = a; ar_id[slot] = id; ar_cs[slot] = (uint32_t)(y * CORE + x) | ((uint32_t)st << 16); }
+        else misc[2] = 1;
       }
     }
     ABM_CTA_SYNC();
@@ -364,18 +505,28 @@ struct CommitTile {
       }
     }
     ABM_CTA_SYNC();
-    ABM_CTA_FOR(t, NT) { /* pass 2: energy, eating, births, output */
-      for (uint32_t m = (uint32_t)t; m < M; m += (uint32_t)NT) {
-        const int r = rt.find(m, nruns);
-        const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
+    const bool listed = misc[2] == 0;
+    const uint32_t n_pass2 = listed ? misc[1] : M;
+    ABM_CTA_FOR(t, NT) { /* pass 2: energy, eating, births, output (over the arrival list when it fits) */
+      for (uint32_t m = (uint32_t)t; m < n_pass2; m += (uint32_t)NT) {
+        uint32_t a, id;
         int x, y;
-        if (!w.locate(r, v.cell[a], x, y)) continue;
-        const uint8_t st = v.state[a];
-        if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); x += dx; y += dy; }
-        x -= HALO; y -= HALO;
-        if (x < 0 || x >= CORE || y < 0 || y >= CORE) continue;
+        uint8_t st;
+        if (listed) {
+          a = ar_a[m]; id = ar_id[m];
+          const uint32_t cs = ar_cs[m];
+          x = (int)(cs & 31); y = (int)((cs >> 5) & 31); st = (uint8_t)(cs >> 16);
+        } else {
+          const int r = rt.find(m, nruns);
+          a = rt.off[r] + (m - rt.prefix[r]);
+          if (!w.locate(r, v.cell[a], x, y)) continue;
+          st = v.state[a];
+          if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); x += dx; y += dy; }
+          x -= HALO; y -= HALO;
+          if (x < 0 || x >= CORE || y < 0 || y >= CORE) continue;
+          id = v.id[a];
+        }
         const int lc = y * CORE + x;
-        const uint32_t id = v.id[a];
         double e = v.energy[a] - v.p.movement_cost; /* walk_ocurred is always true */
         if (v.p.eat && min_all[lc] == id && (grass[lc] & GRASS_GROWN)) { /* killed agents still eat (Appendix D-1) */
           e += v.p.delta_energy;

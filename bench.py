@@ -75,25 +75,32 @@ class ClockSampler(threading.Thread):
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([t.strip() for t in line.split(",")])
+                self.rows.append([t.strip() for t in line.split(",")] + [time.perf_counter()])
                 if self.stop_flag:
                     break
         except Exception:
             pass
 
-    def finish(self):
+    def finish(self, t0=None, t1=None):
         self.stop_flag = True
         if self.proc is not None:
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r for r in self.rows if len(r) >= 10]
+        inside = [r for r in rows if t0 is not None and t0 - 0.15 <= r[-1] <= t1 + 0.15]
+        window = "timed region"
+        if not inside:  # the timed region is shorter than nvidia-smi's sampling period: use the whole loaded span
+            inside, window = rows, "warm-up + timed region + e2e (timed region shorter than the sampling period)"
+        self.rows = inside
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
         reasons = set()
+        self.window = window
         for r in self.rows:
             if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm), window=window)
 
 
 def measured_peak():
@@ -209,11 +216,11 @@ def main():
         eng.step(1)
         return eng.timing(), eng.kernel_stats()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         tick()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     t_wall0 = time.perf_counter()
     ms = upd = launches = rounds = 0.0
     kstats = {}
@@ -224,8 +231,8 @@ def main():
             a = kstats.setdefault(k, dict(ms=0.0, launches=0, units=0))
             a["ms"] += v["ms"]; a["launches"] += v["launches"]; a["units"] += v["units"]
     barrier()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.finish()
+    t_wall1 = time.perf_counter()
+    t_wall = t_wall1 - t_wall0
 
     tt = torch.tensor([ms, upd, launches], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -273,6 +280,7 @@ def main():
                 keep.append(t)
     barrier()
     e2e_dt = time.perf_counter() - t0
+    clocks = sampler.finish(t_wall0, t_wall1)
     e2 = torch.tensor([e2e_dt, e2e_upd], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = e2.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
