@@ -84,7 +84,7 @@ ABM_HD int g_wrap(int a, int n, int periodic) { return periodic ? wrap_far(a, n)
 /* pos + (dx,dy): wrapped when periodic; false when it leaves a non-periodic grid */
 ABM_HD bool shift(const Geo& g, int x, int y, int dx, int dy, int& ox, int& oy) {
   ox = x + dx; oy = y + dy;
-  if (g.periodic) { ox = wrap_far(ox, g.nx); oy = wrap_far(oy, g.ny); return true; }
+  if (g.periodic) { ox = wrap(ox, g.nx); oy = wrap(oy, g.ny); return true; } /* |dx|, |dy| <= 1 at every call site */
   return ox >= 0 && ox < g.nx && oy >= 0 && oy < g.ny;
 }
 
@@ -146,7 +146,7 @@ ABM_HD bool present(uint8_t s) { return !(s & ST_DEAD) || (s & ST_BIRTH); }
 ABM_HD int effective_dir(const Geo& g, int x, int y, int dx, int dy) {
   int tx, ty;
   if (g.periodic) {
-    tx = wrap_far(x + dx, g.nx); ty = wrap_far(y + dy, g.ny);
+    tx = wrap(x + dx, g.nx); ty = wrap(y + dy, g.ny);
     if (tx == x && ty == y) return DIR_STAY;
     if (g.nx < 3 && tx != x) dx = 1; /* both x-neighbours alias on a 2-wide ring: canonical direction */
     if (g.ny < 3 && ty != y) dy = 1;

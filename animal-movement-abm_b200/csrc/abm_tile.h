@@ -31,7 +31,7 @@ namespace abm {
 
 enum { SUB = 8, CORE = 32, HALO = 8, WIN = CORE + 2 * HALO, MAX_RUNS = 36, TILE_THREADS = 256, AGENT_THREADS = 32 };
 enum { NONE32 = 0xFFFFFFFFu };
-enum { ULIST_CAP = 768, ARRIVE_CAP = 768 }; /* shared-memory work lists of a core; larger populations take the streaming code */
+enum { ULIST_CAP = 768, ARRIVE_CAP = 768, RUNOF_CAP = 2048, RUNTABLE_WORDS = 3 * MAX_RUNS + 1 + RUNOF_CAP / 4 }; /* shared-memory work lists of a core; larger populations take the streaming code */
 
 struct SubIndex {
   const uint32_t* off; /* first agent of the sub-tile's run */
@@ -70,10 +70,37 @@ struct Window {
 struct RunTable {
   uint32_t* off;    /* MAX_RUNS */
   uint32_t* prefix; /* MAX_RUNS + 1 */
+  uint32_t* cnt;    /* MAX_RUNS */
+  uint8_t* runof;   /* RUNOF_CAP: run of flat index m (valid when the window holds at most RUNOF_CAP agents) */
+  ABM_HD void bind(uint32_t* p) { off = p; prefix = p + MAX_RUNS; cnt = prefix + MAX_RUNS + 1; runof = (uint8_t*)(cnt + MAX_RUNS); }
   ABM_HD int find(uint32_t m, int nruns) const { /* run containing flat index m */
+    if (prefix[nruns] <= RUNOF_CAP) return runof[m];
     int lo = 0, hi = nruns;
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (prefix[mid] <= m) lo = mid; else hi = mid; }
     return lo;
+  }
+  /* phase 1 of 2 (then sync): slices of the window's sub-tiles */
+  ABM_HD void load(int t, int NT, int nruns, const Window& w, const Geo& g, const SubIndex& si) const {
+    for (int r = t; r < nruns; r += NT) {
+      const int sub = w.sub_of_run(r, g, si);
+      off[r] = sub < 0 ? 0u : si.off[sub];
+      cnt[r] = sub < 0 ? 0u : si.cnt[sub];
+    }
+  }
+  /* phase 2 of 2 (then sync): every run sums the counts before it */
+  ABM_HD void scan(int t, int NT, int nruns) const {
+    for (int r = t; r < nruns; r += NT) {
+      uint32_t run = 0;
+      for (int q = 0; q <= r; ++q) run += cnt[q];
+      prefix[r + 1] = run;
+      if (r == 0) prefix[0] = 0;
+    }
+  }
+  /* phase 3 (then sync): flat index -> run */
+  ABM_HD void expand(int t, int NT, int nruns) const {
+    if (prefix[nruns] > RUNOF_CAP) return;
+    for (int r = t; r < nruns; r += NT)
+      for (uint32_t m = prefix[r]; m < prefix[r + 1]; ++m) runof[m] = (uint8_t)r;
   }
 };
 
@@ -206,8 +233,8 @@ struct ResolveWindow {
   uint32_t* out;
   uint32_t* out_count;
 
-  static size_t smem_bytes(int wx, int wy) { return (size_t)(3 * wx * wy + MAX_RUNS + MAX_RUNS + 1 + 8) * 4; }
-  static size_t smem_bytes_core() { return (size_t)(4 * WIN * WIN + 6 * ULIST_CAP + MAX_RUNS + MAX_RUNS + 1 + 16) * 4; }
+  static size_t smem_bytes(int wx, int wy) { return (size_t)(3 * wx * wy + RUNTABLE_WORDS + 8) * 4; }
+  static size_t smem_bytes_core() { return (size_t)(4 * WIN * WIN + 6 * ULIST_CAP + RUNTABLE_WORDS + 16) * 4; }
 
   /* Core window with the undecided agents held in a shared-memory work list: each round touches only what is still
    * open.  min_new only ever gains entries (decisions are final), min_maybe is rebuilt per round from the list (double
@@ -225,28 +252,23 @@ struct ResolveWindow {
     uint32_t* l_id[2] = {lst + ULIST_CAP, lst + 4 * ULIST_CAP};
     uint32_t* l_xs[2] = {lst + 2 * ULIST_CAP, lst + 5 * ULIST_CAP};
     RunTable rt;
-    rt.off = lst + 6 * ULIST_CAP; rt.prefix = rt.off + MAX_RUNS;
-    uint32_t* cnt = rt.prefix + MAX_RUNS + 1; /* [0],[1] list lengths, [2] progress, [3] open agents of the core, [4] overflow */
+    rt.bind(lst + 6 * ULIST_CAP);
+    uint32_t* cnt = lst + 6 * ULIST_CAP + RUNTABLE_WORDS; /* [0],[1] walker list lengths, [5],[6] gregarious list lengths, [2] progress,
+                                               * [3] open agents of the core, [4] overflow, [7] entries listed at load */
 
     ABM_CTA_FOR(t, NT) {
-      for (int r = t; r < nruns; r += NT) {
-        const int sub = w.sub_of_run(r, v.g, si);
-        rt.off[r] = sub < 0 ? 0u : si.off[sub];
-        rt.prefix[r + 1] = sub < 0 ? 0u : si.cnt[sub];
-      }
+      rt.load(t, NT, nruns, w, v.g, si);
       for (int c = t; c < cells; c += NT) { max_old[c] = 0u; min_new[c] = NONE32; maybe[0][c] = NONE32; }
       if (t < 8) cnt[t] = 0;
     }
     ABM_CTA_SYNC();
-    ABM_CTA_FOR(t, NT) {
-      if (t == 0) {
-        uint32_t run = 0;
-        rt.prefix[0] = 0;
-        for (int r = 0; r < nruns; ++r) { run += rt.prefix[r + 1]; rt.prefix[r + 1] = run; }
-      }
-    }
+    ABM_CTA_FOR(t, NT) { rt.scan(t, NT, nruns); }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) { rt.expand(t, NT, nruns); }
     ABM_CTA_SYNC();
     const uint32_t M = rt.prefix[nruns];
+    /* work-list layout: `ifempty` walkers fill a list from the front, gregarious agents from the back, so that each
+     * kind is evaluated by full warps (their code paths differ by two orders of magnitude in length) */
     ABM_CTA_FOR(t, NT) {
       for (uint32_t m = (uint32_t)t; m < M; m += (uint32_t)NT) {
         const int r = rt.find(m, nruns);
@@ -257,8 +279,10 @@ struct ResolveWindow {
         const uint8_t st = load_state(&v.state[a]);
         smem_max(&max_old[y * WIN + x], id);
         if (st & ST_DECIDED) { contribute_final(min_new, w, id, x, y, st); continue; }
-        const uint32_t slot = smem_add(&cnt[0], 1u);
-        if (slot >= ULIST_CAP) { cnt[4] = 1; continue; }
+        const bool greg = (st & ST_DIRMASK) == DIR_GREG;
+        const uint32_t k = smem_add(&cnt[greg ? 5 : 0], 1u);
+        if (smem_add(&cnt[7], 1u) >= ULIST_CAP) { cnt[4] = 1; continue; }
+        const uint32_t slot = greg ? ULIST_CAP - 1 - k : k;
         l_a[0][slot] = a; l_id[0][slot] = id; l_xs[0][slot] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)st << 16);
         contribute_maybe(maybe[0], w, id, x, y, st);
       }
@@ -267,19 +291,21 @@ struct ResolveWindow {
     if (cnt[4]) return false;
     int cur = 0;
     for (int round = 0; round < max_rounds; ++round) {
-      const uint32_t nu = cnt[cur];
-      if (nu == 0) break;
+      const uint32_t nc = cnt[cur], ng = cnt[5 + cur];
+      if (nc + ng == 0) break;
       ABM_CTA_SYNC();
       ABM_CTA_FOR(t, NT) {
         for (int c = t; c < cells; c += NT) maybe[cur ^ 1][c] = NONE32;
-        if (t == 0) { cnt[cur ^ 1] = 0; cnt[2] = 0; cnt[3] = 0; }
+        if (t == 0) { cnt[cur ^ 1] = 0; cnt[5 + (cur ^ 1)] = 0; cnt[2] = 0; cnt[3] = 0; }
       }
       ABM_CTA_SYNC();
       Summaries s;
       s.max_old = max_old; s.min_new = min_new; s.min_maybe = maybe[cur];
       ABM_CTA_FOR(t, NT) {
-        for (uint32_t u = (uint32_t)t; u < nu; u += (uint32_t)NT) {
-          const uint32_t a = l_a[cur][u], id = l_id[cur][u], xs = l_xs[cur][u];
+        for (uint32_t u = (uint32_t)t; u < nc + ng; u += (uint32_t)NT) {
+          const bool greg = u >= nc;
+          const uint32_t e = greg ? ULIST_CAP - 1 - (u - nc) : u;
+          const uint32_t a = l_a[cur][e], id = l_id[cur][e], xs = l_xs[cur][e];
           const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
           const uint8_t st = (uint8_t)(xs >> 16);
           uint8_t nst = st;
@@ -288,7 +314,8 @@ struct ResolveWindow {
             contribute_final(min_new, w, id, x, y, nst);
             cnt[2] = 1;
           } else {
-            const uint32_t slot = smem_add(&cnt[cur ^ 1], 1u);
+            const uint32_t k = smem_add(&cnt[greg ? 5 + (cur ^ 1) : (cur ^ 1)], 1u);
+            const uint32_t slot = greg ? ULIST_CAP - 1 - k : k;
             l_a[cur ^ 1][slot] = a; l_id[cur ^ 1][slot] = id; l_xs[cur ^ 1][slot] = xs;
             contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
             if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&cnt[3], 1u);
@@ -300,12 +327,13 @@ struct ResolveWindow {
       if (cnt[3] == 0 || cnt[2] == 0) break;
     }
     ABM_CTA_SYNC();
-    const uint32_t nu = cnt[cur];
+    const uint32_t nc = cnt[cur], ng = cnt[5 + cur];
     ABM_CTA_FOR(t, NT) { /* the core's agents that stay open go to the per-agent windows */
-      for (uint32_t u = (uint32_t)t; u < nu; u += (uint32_t)NT) {
-        const uint32_t xs = l_xs[cur][u];
+      for (uint32_t u = (uint32_t)t; u < nc + ng; u += (uint32_t)NT) {
+        const uint32_t e = u >= nc ? ULIST_CAP - 1 - (u - nc) : u;
+        const uint32_t xs = l_xs[cur][e];
         const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
-        if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) out[atomic_add(out_count, 1u)] = l_a[cur][u];
+        if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) out[atomic_add(out_count, 1u)] = l_a[cur][e];
       }
     }
     return true;
@@ -334,25 +362,17 @@ struct ResolveWindow {
     Summaries s;
     s.max_old = smem; s.min_new = smem + cells; s.min_maybe = smem + 2 * cells;
     RunTable rt;
-    rt.off = smem + 3 * cells; rt.prefix = rt.off + MAX_RUNS;
-    uint32_t* flags = rt.prefix + MAX_RUNS + 1; /* [0] progress, [1] undecided agents this CTA answers for */
+    rt.bind(smem + 3 * cells);
+    uint32_t* flags = smem + 3 * cells + RUNTABLE_WORDS; /* [0] progress, [1] undecided agents this CTA answers for */
 
     ABM_CTA_FOR(t, NT) {
-      for (int r = t; r < nruns; r += NT) {
-        const int sub = w.sub_of_run(r, v.g, si);
-        rt.off[r] = sub < 0 ? 0u : si.off[sub];
-        rt.prefix[r + 1] = sub < 0 ? 0u : si.cnt[sub]; /* counts, turned into a prefix below */
-      }
+      rt.load(t, NT, nruns, w, v.g, si);
       for (int c = t; c < cells; c += NT) s.max_old[c] = 0u;
     }
     ABM_CTA_SYNC();
-    ABM_CTA_FOR(t, NT) {
-      if (t == 0) {
-        uint32_t run = 0;
-        rt.prefix[0] = 0;
-        for (int r = 0; r < nruns; ++r) { run += rt.prefix[r + 1]; rt.prefix[r + 1] = run; }
-      }
-    }
+    ABM_CTA_FOR(t, NT) { rt.scan(t, NT, nruns); }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) { rt.expand(t, NT, nruns); }
     ABM_CTA_SYNC();
     const uint32_t M = rt.prefix[nruns];
     ABM_CTA_FOR(t, NT) { /* static part: highest id that starts the tick on each cell */
@@ -427,7 +447,7 @@ struct CommitTile {
   uint32_t* cursor;                     /* next free slot of the output SoA */
   uint32_t* birth_pos; uint32_t* birth_parent; uint32_t* birth_count; uint32_t* birth_bits;
 
-  static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 16 * 3 + MAX_RUNS + MAX_RUNS + 1 + 8 + 3 * ARRIVE_CAP) * 4; }
+  static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 16 * 3 + RUNTABLE_WORDS + 8 + 3 * ARRIVE_CAP) * 4; }
 
   ABM_HD void operator()(uint32_t cta, uint32_t* smem) const {
     const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x);
@@ -440,8 +460,8 @@ struct CommitTile {
     uint32_t* base = counts + 16;
     uint32_t* cur = base + 16;
     RunTable rt;
-    rt.off = cur + 16; rt.prefix = rt.off + MAX_RUNS;
-    uint32_t* misc = rt.prefix + MAX_RUNS + 1; /* [0] chunk, [1] arrivals listed, [2] list overflow */
+    rt.bind(cur + 16);
+    uint32_t* misc = cur + 16 + RUNTABLE_WORDS; /* [0] chunk, [1] arrivals listed, [2] list overflow */
     uint32_t* ar_a = misc + 8;                 /* arrivals: agent index, id, core cell | state << 16 */
     uint32_t* ar_id = ar_a + ARRIVE_CAP;
     uint32_t* ar_cs = ar_id + ARRIVE_CAP;
@@ -449,24 +469,16 @@ struct CommitTile {
     uint32_t* gtile = (uint32_t*)(v.grass + (size_t)tile * TILE_CELLS);
 
     ABM_CTA_FOR(t, NT) {
-      for (int r = t; r < nruns; r += NT) {
-        const int sub = w.sub_of_run(r, v.g, si);
-        rt.off[r] = sub < 0 ? 0u : si.off[sub];
-        rt.prefix[r + 1] = sub < 0 ? 0u : si.cnt[sub];
-      }
+      rt.load(t, NT, nruns, w, v.g, si);
       for (int c = t; c < CORE * CORE; c += NT) min_all[c] = NONE32;
       for (int c = t; c < CORE * CORE / 4; c += NT) ((uint32_t*)grass)[c] = gtile[c];
       if (t < 16) counts[t] = 0;
       if (t < 8) misc[t] = 0;
     }
     ABM_CTA_SYNC();
-    ABM_CTA_FOR(t, NT) {
-      if (t == 0) {
-        uint32_t run = 0;
-        rt.prefix[0] = 0;
-        for (int r = 0; r < nruns; ++r) { run += rt.prefix[r + 1]; rt.prefix[r + 1] = run; }
-      }
-    }
+    ABM_CTA_FOR(t, NT) { rt.scan(t, NT, nruns); }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) { rt.expand(t, NT, nruns); }
     ABM_CTA_SYNC();
     const uint32_t M = rt.prefix[nruns];
     ABM_CTA_FOR(t, NT) { /* pass 1: who lands in the core */
@@ -491,17 +503,17 @@ struct CommitTile {
     }
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, NT) {
-      if (t == 0) {
-        uint32_t total = 0;
-        for (int q = 0; q < 16; ++q) { base[q] = total; total += counts[q]; }
-        const uint32_t chunk = total ? atomic_add(cursor, total) : 0u;
-        misc[0] = chunk;
-        for (int q = 0; q < 16; ++q) {
-          cur[q] = chunk + base[q];
-          const int sub = (cy * 4 + (q >> 2)) * si.nsx + cx * 4 + (q & 3);
-          new_off[sub] = chunk + base[q];
-          new_cnt[sub] = counts[q];
-        }
+      if (t < 16) { uint32_t b = 0; for (int q = 0; q < t; ++q) b += counts[q]; base[t] = b; }
+      if (t == 16) { uint32_t total = 0; for (int q = 0; q < 16; ++q) total += counts[q]; misc[0] = total ? atomic_add(cursor, total) : 0u; }
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) {
+      if (t < 16) {
+        const uint32_t at = misc[0] + base[t];
+        cur[t] = at;
+        const int sub = (cy * 4 + (t >> 2)) * si.nsx + cx * 4 + (t & 3);
+        new_off[sub] = at;
+        new_cnt[sub] = counts[t];
       }
     }
     ABM_CTA_SYNC();
