@@ -246,7 +246,7 @@ struct abm_handle {
   int cur = 0;
   DevBuf state, slot, new_cell, pend[2], births;
   DevBuf grass, walkbits, elev;
-  DevBuf bits, bits_prefix, scan_tmp, stage, lut, greg_order, counters, partials;
+  DevBuf bits, bits_prefix, scan_tmp, stage, lut, greg_order, greg_table, counters, partials;
   /* ALTERNATED_WALK / A*: id-order ranks, behaviour segments, plan requests, route followers, the route store */
   DevBuf rank, by_rank, seg_behav, plan_agent, plan_goal, remote_head, remote_next, remote_dest, idx_of_id;
   DevBuf as_g, as_meta, as_heap, as_src, as_dst, as_id, as_status, as_len, as_cost, as_off;
@@ -316,6 +316,18 @@ static int check_launch(abm_handle* h, const char* what) {
   return 0;
 }
 
+static int build_greg_table(abm_handle* h) {
+  const int r = h->cfg.walk_type == ABM_RANDOM_WALK_GREGARIOUS ? h->cfg.visual_distance : 1;
+  const int side = 2 * r + 1;
+  int rc = ensure(h, h->greg_table, (size_t)side * side * 8 * sizeof(double));
+  if (rc) return rc;
+  GregTableBody gb;
+  gb.lut = (const double*)h->lut.p; gb.r = r; gb.table = (double*)h->greg_table.p;
+  launch_foreach(h->stream, gb, (uint64_t)side * side);
+  ABM_CK(h, stream_sync(h->stream));
+  return 0;
+}
+
 static View make_view(abm_handle* h) {
   View v;
   memset(&v, 0, sizeof v);
@@ -333,6 +345,7 @@ static View make_view(abm_handle* h) {
   v.walkbits = (const uint32_t*)h->walkbits.p;
   v.lut = (const double*)h->lut.p;
   v.greg_order = (const uint8_t*)h->greg_order.p;
+  v.greg_table = (const double*)h->greg_table.p;
   v.err = (uint32_t*)h->counters.p + CTR_ERR;
   if (h->cfg.walk_type == ABM_ALTERNATED_WALK) {
     v.remote_head = (uint32_t*)h->remote_head.p;
@@ -974,6 +987,7 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
     for (size_t i = 0; i < order.size(); ++i) ord[i] = (uint8_t)order[i].second;
     if ((rc = ensure(h, h->greg_order, ord.size()))) break;
     if (copy_h2d(h->greg_order.p, ord.data(), ord.size(), h->stream) != 0) { rc = ABM_E_CUDA; break; }
+    if ((rc = build_greg_table(h))) break;
   } while (0);
   if (rc) { g_create_error = h->err.empty() ? "device allocation failed" : h->err; ABM_API(destroy)(h); return rc; }
   *out = h;
@@ -988,7 +1002,7 @@ int ABM_API(set_weight_lut)(abm_handle* h, const double* w, int32_t n) {
   const int nl = 2 * (r + 1) * (r + 1) + 1;
   if (n < nl) ABM_FAIL(h, ABM_E_BADARG, "weight table needs %d entries (k = 0..2(r+1)^2), got %d", nl, n);
   ABM_CK(h, copy_h2d(h->lut.p, w, (size_t)nl * 8, h->stream));
-  return ABM_OK;
+  return build_greg_table(h);
 }
 
 int ABM_API(set_grid)(abm_handle* h, const uint8_t* fg, const int64_t* cd, const uint8_t* wm, const int64_t* el) {

@@ -127,6 +127,7 @@ struct View {
   const uint32_t* walkbits;  /* gt / 32 words, bit = walkable */
   const double* lut;         /* exp(-sqrt(k)/3) */
   const uint8_t* greg_order; /* box cells by (d^2, β index) */
+  const double* greg_table;  /* per closest-neighbour offset: the 8 cumulative wsample weights (GregTableBody) */
   uint32_t* err;             /* sticky device error flags */
   /* ALTERNATED_WALK only (else null): agents that follow a route land on an arbitrary cell; they are chained per
    * destination cell so that `ifempty` probes and the commit see them */
@@ -374,6 +375,32 @@ ABM_HD int resolve_greg(const View& v, uint32_t k, uint8_t st) {
   v.state[k] = (uint8_t)((st & (ST_DEAD | ST_BIRTH)) | dir | ST_DECIDED | ST_MOVED); /* move_agent!, :331 */
   return RES_DONE;
 }
+
+/* wsample weights of random_walk_gregarious (src/agent_actions.jl:319-328) for every possible offset of
+ * the closest neighbour: w_i = lut[d_i^2], p = w ./ sum(w) (left to right), cumulative sums of p as StatsBase's
+ * sample(rng, wv) forms them.  Entry 7 equals sum(p), the factor of the uniform draw.  One thread per offset. */
+struct GregTableBody {
+  const double* lut;
+  int32_t r;
+  double* table; /* (2r+1)^2 x 8 */
+  ABM_HD void operator()(uint64_t code) const {
+    const int side = 2 * r + 1;
+    const int bx = (int)(code % (uint64_t)side) - r, by = (int)(code / (uint64_t)side) - r;
+    double w[8], s1;
+    for (int i = 0; i < 8; ++i) {
+      int ox, oy;
+      off8(i, ox, oy);
+      const int kx = ox - bx, ky = oy - by;
+      w[i] = lut[kx * kx + ky * ky];
+    }
+    s1 = w[0];
+    for (int i = 1; i < 8; ++i) s1 += w[i];
+    for (int i = 0; i < 8; ++i) w[i] = w[i] / s1;
+    double cw = w[0];
+    table[code * 8] = cw;
+    for (int i = 1; i < 8; ++i) { cw += w[i]; table[code * 8 + i] = cw; }
+  }
+};
 
 struct ResolveBody {
   View v;

@@ -165,6 +165,40 @@ ABM_HD void contribute_final(uint32_t* min_new, const Window& w, uint32_t id, in
   if (x >= 0 && x < w.wx && y >= 0 && y < w.wy) smem_min(&min_new[y * w.wx + x], id);
 }
 
+enum { GREG_NOBODY = 252, GREG_PENDING = 253, GREG_OUTSIDE = 254 };
+
+/* closest neighbour of a gregarious agent: strict `<` over nearby_ids order == the first occupied cell in (d^2, β index)
+ * order.  Returns its box index, GREG_NOBODY, or why that cannot be known yet. */
+ABM_HD int greg_scan(const View& v, const Summaries& s, const Window& w, uint32_t id, int x, int y) {
+  const int r = v.p.r, side = 2 * r + 1;
+  if (x - r < 1 || x + r > w.wx - 2 || y - r < 1 || y + r > w.wy - 2) return GREG_OUTSIDE;
+  const int cells = side * side;
+  for (int q = 0; q < cells; ++q) {
+    const int bit = v.greg_order[q];
+    const int c = (y + bit / side - r) * w.wx + (x + bit % side - r);
+    if (s.occupied(c, id)) return bit;
+    if (s.unknown(c, id)) return GREG_PENDING;
+  }
+  return GREG_NOBODY;
+}
+/* the draw that follows: wsample over the 8 neighbours (global RNG routed to the agent's stream, draw 1), or
+ * rand(model.rng, 1:8) when nobody is in view (:334); move_agent! is unconditional (:331) */
+ABM_HD uint8_t greg_finish(const View& v, uint32_t id, uint8_t st, int code) {
+  AgentStream rs;
+  rs.init(v.p.seed, v.p.tick, id);
+  rs.n = 1; /* draw 0 was the execute_walk! uniform */
+  int d;
+  if (code == GREG_NOBODY) {
+    d = (int)rs.next_below(8);
+  } else {
+    const double* cw = v.greg_table + code * 8;
+    const double t = rs.next_f64() * cw[7]; /* StatsBase.sample(rng, wv): t = rand(rng) * sum(wv) */
+    d = 0;
+    while (cw[d] < t && d < 7) ++d;
+  }
+  return (uint8_t)((st & (ST_DEAD | ST_BIRTH)) | d | ST_DECIDED | ST_MOVED);
+}
+
 /* one attempt to decide agent (id, st) at window cell (x, y); summaries are complete on [1, w-2]^2 */
 ABM_HD int evaluate(const View& v, const Summaries& s, const Window& w, uint32_t id, int x, int y, uint8_t st, uint8_t& out) {
   const int dir = st & ST_DIRMASK;
@@ -180,43 +214,10 @@ ABM_HD int evaluate(const View& v, const Summaries& s, const Window& w, uint32_t
     return EV_DECIDED;
   }
   /* random_walk_gregarious (src/agent_actions.jl:297-336) */
-  const int r = v.p.r, side = 2 * r + 1;
-  if (x - r < 1 || x + r > w.wx - 2 || y - r < 1 || y + r > w.wy - 2) return EV_OUTSIDE;
-  int closest = -1;
-  const int cells = side * side;
-  for (int q = 0; q < cells; ++q) { /* strict `<` over nearby_ids order == minimum of (d^2, β index) */
-    const int bit = v.greg_order[q];
-    const int c = (y + bit / side - r) * w.wx + (x + bit % side - r);
-    if (s.occupied(c, id)) { closest = bit; break; }
-    if (s.unknown(c, id)) return EV_PENDING;
-  }
-  AgentStream rs;
-  rs.init(v.p.seed, v.p.tick, id);
-  rs.n = 1; /* draw 0 was the execute_walk! uniform */
-  int d;
-  if (closest < 0) {
-    d = (int)rs.next_below(8); /* :334 */
-  } else {
-    const int bx = closest % side - r, by = closest / side - r;
-    double wgt[8], s1, s2;
-    for (int i = 0; i < 8; ++i) {
-      int ox, oy;
-      off8(i, ox, oy);
-      const int kx = ox - bx, ky = oy - by;
-      wgt[i] = v.lut[kx * kx + ky * ky];
-    }
-    s1 = wgt[0];
-    for (int i = 1; i < 8; ++i) s1 += wgt[i];
-    for (int i = 0; i < 8; ++i) wgt[i] = wgt[i] / s1;
-    s2 = wgt[0];
-    for (int i = 1; i < 8; ++i) s2 += wgt[i];
-    const double t = rs.next_f64() * s2; /* StatsBase.sample(rng, wv) */
-    int i = 0;
-    double cw = wgt[0];
-    while (cw < t && i < 7) { ++i; cw += wgt[i]; }
-    d = i;
-  }
-  out = (uint8_t)((st & (ST_DEAD | ST_BIRTH)) | d | ST_DECIDED | ST_MOVED); /* move_agent!, :331 */
+  const int code = greg_scan(v, s, w, id, x, y);
+  if (code == GREG_OUTSIDE) return EV_OUTSIDE;
+  if (code == GREG_PENDING) return EV_PENDING;
+  out = greg_finish(v, id, st, code);
   return EV_DECIDED;
 }
 
@@ -284,11 +285,19 @@ struct ResolveWindow {
         if (smem_add(&cnt[7], 1u) >= ULIST_CAP) { cnt[4] = 1; continue; }
         const uint32_t slot = greg ? ULIST_CAP - 1 - k : k;
         l_a[0][slot] = a; l_id[0][slot] = id; l_xs[0][slot] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)st << 16);
-        contribute_maybe(maybe[0], w, id, x, y, st);
+        if (!greg) contribute_maybe(maybe[0], w, id, x, y, st);
       }
     }
     ABM_CTA_SYNC();
     if (cnt[4]) return false;
+    ABM_CTA_FOR(t, NT) { /* the gregarious agents' eight candidate cells, by full warps */
+      const uint32_t ng0 = cnt[5];
+      for (uint32_t u = (uint32_t)t; u < ng0; u += (uint32_t)NT) {
+        const uint32_t e = ULIST_CAP - 1 - u, xs = l_xs[0][e];
+        contribute_maybe(maybe[0], w, l_id[0][e], (int)(xs & 0xFF), (int)((xs >> 8) & 0xFF), (uint8_t)(xs >> 16));
+      }
+    }
+    ABM_CTA_SYNC();
     int cur = 0;
     for (int round = 0; round < max_rounds; ++round) {
       const uint32_t nc = cnt[cur], ng = cnt[5 + cur];
@@ -309,17 +318,40 @@ struct ResolveWindow {
           const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
           const uint8_t st = (uint8_t)(xs >> 16);
           uint8_t nst = st;
-          if (evaluate(v, s, w, id, x, y, st, nst) == EV_DECIDED) {
+          int res;
+          if (greg) { /* scan now, draw in the next phase: the warp must reconverge before the long tail */
+            const int code = greg_scan(v, s, w, id, x, y);
+            l_xs[cur][e] = (xs & 0x00FFFFFFu) | ((uint32_t)code << 24);
+            if (code < GREG_PENDING) continue;
+            res = EV_PENDING;
+          } else {
+            res = evaluate(v, s, w, id, x, y, st, nst);
+          }
+          if (res == EV_DECIDED) {
             v.state[a] = nst;
             contribute_final(min_new, w, id, x, y, nst);
             cnt[2] = 1;
           } else {
             const uint32_t k = smem_add(&cnt[greg ? 5 + (cur ^ 1) : (cur ^ 1)], 1u);
             const uint32_t slot = greg ? ULIST_CAP - 1 - k : k;
-            l_a[cur ^ 1][slot] = a; l_id[cur ^ 1][slot] = id; l_xs[cur ^ 1][slot] = xs;
+            l_a[cur ^ 1][slot] = a; l_id[cur ^ 1][slot] = id; l_xs[cur ^ 1][slot] = xs & 0x00FFFFFFu;
             contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
             if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&cnt[3], 1u);
           }
+        }
+      }
+      ABM_CTA_SYNC();
+      ABM_CTA_FOR(t, NT) { /* gregarious agents whose closest neighbour is known: draw and publish */
+        for (uint32_t u = (uint32_t)t; u < ng; u += (uint32_t)NT) {
+          const uint32_t e = ULIST_CAP - 1 - u, xs = l_xs[cur][e];
+          const int code = (int)(xs >> 24);
+          if (code >= GREG_PENDING) continue;
+          const uint32_t id = l_id[cur][e];
+          const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
+          const uint8_t nst = greg_finish(v, id, (uint8_t)(xs >> 16), code);
+          v.state[l_a[cur][e]] = nst;
+          contribute_final(min_new, w, id, x, y, nst);
+          cnt[2] = 1;
         }
       }
       ABM_CTA_SYNC();
