@@ -246,7 +246,7 @@ struct abm_handle {
   int cur = 0;
   DevBuf state, slot, new_cell, pend[2], births;
   DevBuf grass, walkbits, elev;
-  DevBuf bits, bits_prefix, scan_tmp, stage, lut, greg_order, greg_table, counters, partials;
+  DevBuf bits, bits_prefix, scan_tmp, stage, lut, greg_order, greg_dxy, greg_table, counters, partials;
   /* ALTERNATED_WALK / A*: id-order ranks, behaviour segments, plan requests, route followers, the route store */
   DevBuf rank, by_rank, seg_behav, plan_agent, plan_goal, remote_head, remote_next, remote_dest, idx_of_id;
   DevBuf as_g, as_meta, as_heap, as_src, as_dst, as_id, as_status, as_len, as_cost, as_off;
@@ -346,6 +346,7 @@ static View make_view(abm_handle* h) {
   v.lut = (const double*)h->lut.p;
   v.greg_order = (const uint8_t*)h->greg_order.p;
   v.greg_table = (const double*)h->greg_table.p;
+  v.greg_dxy = (const int8_t*)h->greg_dxy.p;
   v.err = (uint32_t*)h->counters.p + CTR_ERR;
   if (h->cfg.walk_type == ABM_ALTERNATED_WALK) {
     v.remote_head = (uint32_t*)h->remote_head.p;
@@ -987,6 +988,10 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
     for (size_t i = 0; i < order.size(); ++i) ord[i] = (uint8_t)order[i].second;
     if ((rc = ensure(h, h->greg_order, ord.size()))) break;
     if (copy_h2d(h->greg_order.p, ord.data(), ord.size(), h->stream) != 0) { rc = ABM_E_CUDA; break; }
+    std::vector<int8_t> dxy(2 * ord.size());
+    for (size_t i = 0; i < ord.size(); ++i) { dxy[2 * i] = (int8_t)(ord[i] % side - r); dxy[2 * i + 1] = (int8_t)(ord[i] / side - r); }
+    if ((rc = ensure(h, h->greg_dxy, dxy.size()))) break;
+    if (copy_h2d(h->greg_dxy.p, dxy.data(), dxy.size(), h->stream) != 0) { rc = ABM_E_CUDA; break; }
     if ((rc = build_greg_table(h))) break;
   } while (0);
   if (rc) { g_create_error = h->err.empty() ? "device allocation failed" : h->err; ABM_API(destroy)(h); return rc; }

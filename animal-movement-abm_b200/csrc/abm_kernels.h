@@ -127,6 +127,7 @@ struct View {
   const uint32_t* walkbits;  /* gt / 32 words, bit = walkable */
   const double* lut;         /* exp(-sqrt(k)/3) */
   const uint8_t* greg_order; /* box cells by (d^2, β index) */
+  const int8_t* greg_dxy;    /* the same order as (dx, dy) pairs */
   const double* greg_table;  /* per closest-neighbour offset: the 8 cumulative wsample weights (GregTableBody) */
   uint32_t* err;             /* sticky device error flags */
   /* ALTERNATED_WALK only (else null): agents that follow a route land on an arbitrary cell; they are chained per

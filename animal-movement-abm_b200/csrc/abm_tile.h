@@ -174,9 +174,8 @@ ABM_HD int greg_scan(const View& v, const Summaries& s, const Window& w, uint32_
   if (x - r < 1 || x + r > w.wx - 2 || y - r < 1 || y + r > w.wy - 2) return GREG_OUTSIDE;
   const int cells = side * side;
   for (int q = 0; q < cells; ++q) {
-    const int bit = v.greg_order[q];
-    const int c = (y + bit / side - r) * w.wx + (x + bit % side - r);
-    if (s.occupied(c, id)) return bit;
+    const int c = (y + v.greg_dxy[2 * q + 1]) * w.wx + (x + v.greg_dxy[2 * q]);
+    if (s.occupied(c, id)) return v.greg_order[q];
     if (s.unknown(c, id)) return GREG_PENDING;
   }
   return GREG_NOBODY;
@@ -235,7 +234,7 @@ struct ResolveWindow {
   uint32_t* out_count;
 
   static size_t smem_bytes(int wx, int wy) { return (size_t)(3 * wx * wy + RUNTABLE_WORDS + 8) * 4; }
-  static size_t smem_bytes_core() { return (size_t)(4 * WIN * WIN + 6 * ULIST_CAP + RUNTABLE_WORDS + 16) * 4; }
+  static size_t smem_bytes_core() { return (size_t)(4 * WIN * WIN + 7 * ULIST_CAP + RUNTABLE_WORDS + 16) * 4; }
 
   /* Core window with the undecided agents held in a shared-memory work list: each round touches only what is still
    * open.  min_new only ever gains entries (decisions are final), min_maybe is rebuilt per round from the list (double
@@ -252,9 +251,10 @@ struct ResolveWindow {
     uint32_t* l_a[2] = {lst, lst + 3 * ULIST_CAP};
     uint32_t* l_id[2] = {lst + ULIST_CAP, lst + 4 * ULIST_CAP};
     uint32_t* l_xs[2] = {lst + 2 * ULIST_CAP, lst + 5 * ULIST_CAP};
+    uint32_t* best = lst + 6 * ULIST_CAP; /* per gregarious task: min over box cells of (visiting rank << 1 | only-maybe) */
     RunTable rt;
-    rt.bind(lst + 6 * ULIST_CAP);
-    uint32_t* cnt = lst + 6 * ULIST_CAP + RUNTABLE_WORDS; /* [0],[1] walker list lengths, [5],[6] gregarious list lengths, [2] progress,
+    rt.bind(lst + 7 * ULIST_CAP);
+    uint32_t* cnt = lst + 7 * ULIST_CAP + RUNTABLE_WORDS; /* [0],[1] walker list lengths, [5],[6] gregarious list lengths, [2] progress,
                                                * [3] open agents of the core, [4] overflow, [7] entries listed at load */
 
     ABM_CTA_FOR(t, NT) {
@@ -305,53 +305,63 @@ struct ResolveWindow {
       ABM_CTA_SYNC();
       ABM_CTA_FOR(t, NT) {
         for (int c = t; c < cells; c += NT) maybe[cur ^ 1][c] = NONE32;
+        for (uint32_t u = (uint32_t)t; u < ng; u += (uint32_t)NT) best[u] = NONE32;
         if (t == 0) { cnt[cur ^ 1] = 0; cnt[5 + (cur ^ 1)] = 0; cnt[2] = 0; cnt[3] = 0; }
       }
       ABM_CTA_SYNC();
       Summaries s;
       s.max_old = max_old; s.min_new = min_new; s.min_maybe = maybe[cur];
       ABM_CTA_FOR(t, NT) {
-        for (uint32_t u = (uint32_t)t; u < nc + ng; u += (uint32_t)NT) {
-          const bool greg = u >= nc;
-          const uint32_t e = greg ? ULIST_CAP - 1 - (u - nc) : u;
-          const uint32_t a = l_a[cur][e], id = l_id[cur][e], xs = l_xs[cur][e];
+        for (uint32_t u = (uint32_t)t; u < nc; u += (uint32_t)NT) { /* `ifempty` walkers: three loads and a compare */
+          const uint32_t a = l_a[cur][u], id = l_id[cur][u], xs = l_xs[cur][u];
           const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
           const uint8_t st = (uint8_t)(xs >> 16);
           uint8_t nst = st;
-          int res;
-          if (greg) { /* scan now, draw in the next phase: the warp must reconverge before the long tail */
-            const int code = greg_scan(v, s, w, id, x, y);
-            l_xs[cur][e] = (xs & 0x00FFFFFFu) | ((uint32_t)code << 24);
-            if (code < GREG_PENDING) continue;
-            res = EV_PENDING;
-          } else {
-            res = evaluate(v, s, w, id, x, y, st, nst);
-          }
-          if (res == EV_DECIDED) {
+          if (evaluate(v, s, w, id, x, y, st, nst) == EV_DECIDED) {
             v.state[a] = nst;
             contribute_final(min_new, w, id, x, y, nst);
             cnt[2] = 1;
           } else {
-            const uint32_t k = smem_add(&cnt[greg ? 5 + (cur ^ 1) : (cur ^ 1)], 1u);
-            const uint32_t slot = greg ? ULIST_CAP - 1 - k : k;
-            l_a[cur ^ 1][slot] = a; l_id[cur ^ 1][slot] = id; l_xs[cur ^ 1][slot] = xs & 0x00FFFFFFu;
+            const uint32_t slot = smem_add(&cnt[cur ^ 1], 1u);
+            l_a[cur ^ 1][slot] = a; l_id[cur ^ 1][slot] = id; l_xs[cur ^ 1][slot] = xs;
             contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
             if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&cnt[3], 1u);
           }
         }
+        /* gregarious closest-neighbour search: one warp per agent, one lane per box cell; the first cell in visiting
+         * order that is occupied or unknown wins through a shared-memory min */
+        const int side = 2 * v.p.r + 1, box = side * side;
+        for (uint32_t task = (uint32_t)t >> 5; task < ng; task += (uint32_t)NT >> 5) {
+          const uint32_t e = ULIST_CAP - 1 - task, xs = l_xs[cur][e], id = l_id[cur][e];
+          const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
+          if (x - v.p.r < 1 || x + v.p.r > WIN - 2 || y - v.p.r < 1 || y + v.p.r > WIN - 2) continue; /* box not fully trusted */
+          for (int q = t & 31; q < box; q += 32) {
+            const int c = (y + v.greg_dxy[2 * q + 1]) * WIN + (x + v.greg_dxy[2 * q]);
+            if (s.occupied(c, id)) smem_min(&best[task], (uint32_t)q << 1);
+            else if (s.unknown(c, id)) smem_min(&best[task], ((uint32_t)q << 1) | 1u);
+          }
+        }
       }
       ABM_CTA_SYNC();
-      ABM_CTA_FOR(t, NT) { /* gregarious agents whose closest neighbour is known: draw and publish */
+      ABM_CTA_FOR(t, NT) { /* one thread per gregarious agent: draw and publish, or carry over */
         for (uint32_t u = (uint32_t)t; u < ng; u += (uint32_t)NT) {
-          const uint32_t e = ULIST_CAP - 1 - u, xs = l_xs[cur][e];
-          const int code = (int)(xs >> 24);
-          if (code >= GREG_PENDING) continue;
-          const uint32_t id = l_id[cur][e];
+          const uint32_t e = ULIST_CAP - 1 - u, xs = l_xs[cur][e], id = l_id[cur][e], a = l_a[cur][e];
           const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
-          const uint8_t nst = greg_finish(v, id, (uint8_t)(xs >> 16), code);
-          v.state[l_a[cur][e]] = nst;
-          contribute_final(min_new, w, id, x, y, nst);
-          cnt[2] = 1;
+          const uint8_t st = (uint8_t)(xs >> 16);
+          const bool inside = !(x - v.p.r < 1 || x + v.p.r > WIN - 2 || y - v.p.r < 1 || y + v.p.r > WIN - 2);
+          const uint32_t b = best[u];
+          if (inside && (b == NONE32 || !(b & 1u))) {
+            const uint8_t nst = greg_finish(v, id, st, b == NONE32 ? (int)GREG_NOBODY : (int)v.greg_order[b >> 1]);
+            v.state[a] = nst;
+            contribute_final(min_new, w, id, x, y, nst);
+            cnt[2] = 1;
+          } else {
+            const uint32_t k = smem_add(&cnt[5 + (cur ^ 1)], 1u);
+            const uint32_t slot = ULIST_CAP - 1 - k;
+            l_a[cur ^ 1][slot] = a; l_id[cur ^ 1][slot] = id; l_xs[cur ^ 1][slot] = xs;
+            contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
+            if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&cnt[3], 1u);
+          }
         }
       }
       ABM_CTA_SYNC();
