@@ -31,7 +31,7 @@ namespace abm {
 
 enum { SUB = 8, CORE = 32, HALO = 8, WIN = CORE + 2 * HALO, MAX_RUNS = 36, TILE_THREADS = 256, AGENT_THREADS = 32 };
 enum { NONE32 = 0xFFFFFFFFu };
-enum { ULIST_CAP = 768, ARRIVE_CAP = 768, RUNOF_CAP = 2048, RUNTABLE_WORDS = 3 * MAX_RUNS + 1 + RUNOF_CAP / 4 }; /* shared-memory work lists of a core; larger populations take the streaming code */
+enum { ULIST_CAP = 512, ARRIVE_CAP = 768, RUNOF_CAP = 2048, RUNTABLE_WORDS = 3 * MAX_RUNS + 1 + RUNOF_CAP / 4 }; /* shared-memory work lists of a core; larger populations take the streaming code */
 
 struct SubIndex {
   const uint32_t* off; /* first agent of the sub-tile's run */
@@ -191,9 +191,13 @@ ABM_HD uint8_t greg_finish(const View& v, uint32_t id, uint8_t st, int code) {
     d = (int)rs.next_below(8);
   } else {
     const double* cw = v.greg_table + code * 8;
-    const double t = rs.next_f64() * cw[7]; /* StatsBase.sample(rng, wv): t = rand(rng) * sum(wv) */
+    double c8[8];
+    for (int i = 0; i < 8; ++i) c8[i] = cw[i]; /* independent loads: one memory latency instead of a chain */
+    const double t = rs.next_f64() * c8[7]; /* StatsBase.sample(rng, wv): t = rand(rng) * sum(wv) */
+    /* i = 1; cw = w[1]; while cw < t && i < n: i += 1; cw += w[i] — the cumulative sums never decrease, so the stopping
+     * index is the number of the first seven sums below t */
     d = 0;
-    while (cw[d] < t && d < 7) ++d;
+    for (int i = 0; i < 7; ++i) d += c8[i] < t ? 1 : 0;
   }
   return (uint8_t)((st & (ST_DEAD | ST_BIRTH)) | d | ST_DECIDED | ST_MOVED);
 }
@@ -271,13 +275,22 @@ struct ResolveWindow {
     /* work-list layout: `ifempty` walkers fill a list from the front, gregarious agents from the back, so that each
      * kind is evaluated by full warps (their code paths differ by two orders of magnitude in length) */
     ABM_CTA_FOR(t, NT) {
-      for (uint32_t m = (uint32_t)t; m < M; m += (uint32_t)NT) {
-        const int r = rt.find(m, nruns);
-        const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
+      for (uint32_t m0 = (uint32_t)t; m0 < M; m0 += 3u * (uint32_t)NT) {
+       int rr[3]; uint32_t aa[3], cc[3], ii[3]; uint8_t ss[3];
+       for (int j = 0; j < 3; ++j) { /* all global loads of up to three agents in flight before any is used */
+        const uint32_t m = m0 + (uint32_t)(j * NT);
+        if (m >= M) { rr[j] = -1; continue; }
+        rr[j] = rt.find(m, nruns);
+        aa[j] = rt.off[rr[j]] + (m - rt.prefix[rr[j]]);
+        cc[j] = v.cell[aa[j]]; ii[j] = v.id[aa[j]]; ss[j] = load_state(&v.state[aa[j]]);
+       }
+       for (int j = 0; j < 3; ++j) {
+        if (rr[j] < 0) continue;
+        const uint32_t a = aa[j];
         int x, y;
-        if (!w.locate(r, v.cell[a], x, y)) continue;
-        const uint32_t id = v.id[a];
-        const uint8_t st = load_state(&v.state[a]);
+        if (!w.locate(rr[j], cc[j], x, y)) continue;
+        const uint32_t id = ii[j];
+        const uint8_t st = ss[j];
         smem_max(&max_old[y * WIN + x], id);
         if (st & ST_DECIDED) { contribute_final(min_new, w, id, x, y, st); continue; }
         const bool greg = (st & ST_DIRMASK) == DIR_GREG;
@@ -286,6 +299,7 @@ struct ResolveWindow {
         const uint32_t slot = greg ? ULIST_CAP - 1 - k : k;
         l_a[0][slot] = a; l_id[0][slot] = id; l_xs[0][slot] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)st << 16);
         if (!greg) contribute_maybe(maybe[0], w, id, x, y, st);
+       }
       }
     }
     ABM_CTA_SYNC();
@@ -331,14 +345,23 @@ struct ResolveWindow {
         /* gregarious closest-neighbour search: one warp per agent, one lane per box cell; the first cell in visiting
          * order that is occupied or unknown wins through a shared-memory min */
         const int side = 2 * v.p.r + 1, box = side * side;
-        for (uint32_t task = (uint32_t)t >> 5; task < ng; task += (uint32_t)NT >> 5) {
-          const uint32_t e = ULIST_CAP - 1 - task, xs = l_xs[cur][e], id = l_id[cur][e];
-          const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
-          if (x - v.p.r < 1 || x + v.p.r > WIN - 2 || y - v.p.r < 1 || y + v.p.r > WIN - 2) continue; /* box not fully trusted */
-          for (int q = t & 31; q < box; q += 32) {
-            const int c = (y + v.greg_dxy[2 * q + 1]) * WIN + (x + v.greg_dxy[2 * q]);
-            if (s.occupied(c, id)) smem_min(&best[task], (uint32_t)q << 1);
-            else if (s.unknown(c, id)) smem_min(&best[task], ((uint32_t)q << 1) | 1u);
+        if (ng > 0) {
+          int rel[8]; /* this lane's box cells (visiting ranks lane, lane + 32, ...) as offsets inside the window */
+          for (int j = 0; j < 8; ++j) {
+            const int q = (t & 31) + 32 * j;
+            rel[j] = q < box ? (int)v.greg_dxy[2 * q + 1] * WIN + (int)v.greg_dxy[2 * q] : 0;
+          }
+          for (uint32_t task = (uint32_t)t >> 5; task < ng; task += (uint32_t)NT >> 5) {
+            const uint32_t e = ULIST_CAP - 1 - task, xs = l_xs[cur][e], id = l_id[cur][e];
+            const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
+            if (x - v.p.r < 1 || x + v.p.r > WIN - 2 || y - v.p.r < 1 || y + v.p.r > WIN - 2) continue; /* box not fully trusted */
+            const int base = y * WIN + x;
+            for (int j = 0; j < 8 && (t & 31) + 32 * j < box; ++j) {
+              const int c = base + rel[j];
+              const uint32_t q = (uint32_t)((t & 31) + 32 * j);
+              if (s.occupied(c, id)) smem_min(&best[task], q << 1);
+              else if (s.unknown(c, id)) smem_min(&best[task], (q << 1) | 1u);
+            }
           }
         }
       }
