@@ -1,0 +1,83 @@
+"""Host-side mirror of the reference's operator interface (abm_b200.model): factories, step, run with adata/mdata.
+The library object is injected (`lib=`): the emulated engine here, the product library under -m gpu."""
+import numpy as np
+import pytest
+
+import abm_b200 as A
+from conftest import assert_same_state
+
+
+def _script_model(lib, version, **kw):
+    """initialize_model with the defaults of scripts/v0.N.jl"""
+    if version == "v0.1":
+        return A.initialize_model(periodic=False, lib=lib, **kw), A.herbivore_dynamics(), A.grass_growth_dynamics()
+    if version == "v0.3":
+        return (A.initialize_model(periodic=True, visual_distance=5, lib=lib, **kw),
+                A.herbivore_dynamics(walk_type=A.WalkType.RANDOM_WALK_GREGARIOUS, eat=True, reproduce=True), A.grass_growth_dynamics())
+    if version == "v0.5":
+        return (A.initialize_model(periodic=True, use_walkmap=True, sheep_reproduce=0.004, lib=lib, **kw),
+                A.herbivore_dynamics(walk_type=A.WalkType.RANDOM_WALKMAP), A.grass_growth_dynamics(walkmap=True))
+    if version == "v0.6":
+        return (A.initialize_model(periodic=True, use_walkmap=True, sheep_reproduce=0.004, counter=50, astar_metric=A.capi.ASTAR_MAX, astar_penalty=True, lib=lib, **kw),
+                A.herbivore_dynamics(walk_type=A.WalkType.ALTERNATED_WALK), A.grass_growth_dynamics(walkmap=True))
+    raise KeyError(version)
+
+
+def test_factories_keep_the_reference_signature():
+    a = A.herbivore_dynamics()
+    assert (a.walk_type, a.eat, a.reproduce, a.prob_random_walk) == (A.WalkType.RANDOM_WALK, True, True, 0.9)
+    assert A.grass_growth_dynamics().walkmap is False and A.grass_growth_dynamics(walkmap=True).walkmap is True
+    assert [w.name for w in A.WalkType] == ["RANDOM_WALK", "RANDOM_WALK_ATTRACTOR", "RANDOM_WALK_GREGARIOUS", "ALTERNATED_WALK", "RANDOM_WALKMAP"]
+    with pytest.raises(TypeError):
+        A.herbivore_dynamics(walk_type=2)
+    with pytest.raises(TypeError):
+        A.herbivore_dynamics(True)  # keyword-only, like the Julia factory
+
+
+def _check_step_and_run(lib, oracle):
+    for version in ("v0.1", "v0.3", "v0.5", "v0.6"):
+        m, astep, mstep = _script_model(lib, version)
+        ref, _, _ = _script_model(oracle, version)
+        n0 = m.nagents()
+        A.step(m, astep, mstep, 7)
+        A.step(ref, astep, mstep, 7)
+        assert m.tick == 7
+        ids, x, y, e = m.agents()
+        rids, rx, ry, re = ref.agents()
+        assert np.array_equal(ids, rids) and np.array_equal(x, rx) and np.array_equal(y, ry) and np.array_equal(e, re)
+        assert np.array_equal(m.fully_grown, ref.fully_grown) and np.array_equal(m.countdown, ref.countdown)
+        assert n0 == 40
+        # run!(model, agent_step!, model_step!, n; adata = [(sheep, count)], mdata = [count_grass]), scripts/v0.6.jl:204-221
+        adf, mdf = A.run(m, astep, mstep, 5, adata=[(A.sheep, A.count), ("energy", sum), ("energy", max)], mdata=[A.count_grass])
+        assert list(adf.columns) == ["step", "count_sheep", "sum_energy", "max_energy"] and list(mdf.columns) == ["step", "count_grass"]
+        assert list(adf["step"]) == [0, 1, 2, 3, 4, 5]
+        ids, x, y, e = m.agents()
+        assert adf["count_sheep"].iloc[-1] == ids.size and adf["sum_energy"].iloc[-1] == e.sum() and adf["max_energy"].iloc[-1] == e.max()
+        assert mdf["count_grass"].iloc[-1] == int(m.fully_grown.sum())
+
+
+def test_step_and_run_on_the_emulated_engine(emu, oracle):
+    _check_step_and_run(emu, oracle)
+
+
+@pytest.mark.gpu
+def test_step_and_run_on_the_gpu(libabm, oracle):
+    _check_step_and_run(libabm, oracle)
+
+
+def test_changing_the_rules_keeps_the_state(emu):
+    m, astep, mstep = _script_model(emu, "v0.3")
+    A.step(m, astep, mstep, 3)
+    ids = m.agents()[0].copy()
+    A.step(m, A.herbivore_dynamics(walk_type=A.WalkType.RANDOM_WALK, reproduce=False), mstep, 1)  # new engine, same world
+    assert m.tick == 4 and set(m.agents()[0]) <= set(ids)
+
+
+def test_product_library_is_the_default_and_has_no_cpu_path():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    m = A.initialize_model()
+    with pytest.raises(A.AbmError) as ei:
+        A.step(m, A.herbivore_dynamics(), A.grass_growth_dynamics(), 1)
+    assert ei.value.code == A.capi.ABM_E_CUDA
