@@ -749,7 +749,7 @@ static SubIndex sub_index(abm_handle* h, int which) {
 static int tick_tile(abm_handle* h) {
   int rc;
   const uint64_t n = h->n;
-  const uint64_t cores = (uint64_t)(h->g.nx / CORE) * (uint64_t)(h->g.ny / CORE);
+  const uint64_t cores = (uint64_t)(h->g.nx / CORE) * (uint64_t)((h->g.own_hi - h->g.own_lo) / CORE);
   const uint64_t m = std::max<uint64_t>(n, 1);
   if ((rc = ensure(h, h->state, m))) return rc;
   if ((rc = ensure(h, h->pend[0], m * 4))) return rc;
@@ -769,7 +769,7 @@ static int tick_tile(abm_handle* h) {
     if ((rc = check_launch(h, "propose"))) return rc;
     if (needs_resolve) {
       ResolveWindow rw;
-      rw.v = v; rw.si = si; rw.mode = 0; rw.cores_x = h->g.nx / CORE; rw.max_rounds = h->tile_rounds; rw.nthreads = TILE_THREADS;
+      rw.v = v; rw.si = si; rw.mode = 0; rw.cores_x = h->g.nx / CORE; rw.core_y0 = h->g.own_lo / CORE; rw.max_rounds = h->tile_rounds; rw.nthreads = TILE_THREADS;
       rw.in = nullptr; rw.out = (uint32_t*)h->pend[0].p; rw.out_count = ctr + CTR_PEND_A;
       { ProfScope ps(h->prof, h->stream, "resolve_tiles", n); launch_cta(h->stream, rw, cores, TILE_THREADS, ResolveWindow::smem_bytes_core()); }
       if ((rc = check_launch(h, "tile resolve"))) return rc;
@@ -784,7 +784,7 @@ static int tick_tile(abm_handle* h) {
     while (cnt > 0) { /* chains that left their window: one small window per agent, Jacobi rounds */
       ABM_CK(h, dev_memset(ctr + (in ? CTR_PEND_A : CTR_PEND_B), 0, sizeof(uint32_t), h->stream));
       ResolveWindow rw;
-      rw.v = v; rw.si = si; rw.mode = 1; rw.cores_x = 0; rw.max_rounds = 1; rw.nthreads = AGENT_THREADS;
+      rw.v = v; rw.si = si; rw.mode = 1; rw.cores_x = 0; rw.core_y0 = 0; rw.max_rounds = 1; rw.nthreads = AGENT_THREADS;
       rw.in = (const uint32_t*)h->pend[in].p; rw.out = (uint32_t*)h->pend[in ^ 1].p; rw.out_count = ctr + (in ? CTR_PEND_A : CTR_PEND_B);
       { ProfScope ps(h->prof, h->stream, "resolve_agents", cnt); launch_cta(h->stream, rw, cnt, AGENT_THREADS, ResolveWindow::smem_bytes(2 * q + 1, 2 * q + 1)); }
       if ((rc = check_launch(h, "agent resolve"))) return rc;
@@ -809,7 +809,7 @@ static int tick_tile(abm_handle* h) {
   }
   {
     CommitTile ct;
-    ct.v = v; ct.si = si; ct.cores_x = h->g.nx / CORE;
+    ct.v = v; ct.si = si; ct.cores_x = h->g.nx / CORE; ct.core_y0 = h->g.own_lo / CORE;
     ct.out_cell = (uint32_t*)h->cell[nxt].p; ct.out_id = (uint32_t*)h->id[nxt].p; ct.out_energy = (double*)h->energy[nxt].p;
     ct.new_off = (uint32_t*)h->sub_off[nxt].p; ct.new_cnt = (uint32_t*)h->sub_cnt[nxt].p;
     ct.cursor = ctr + CTR_CURSOR;
@@ -934,6 +934,7 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
   g.tiles_x = (cfg->nx + 31) / 32; g.tiles_y = (cfg->ny + 31) / 32;
   g.gt = (uint32_t)((uint64_t)g.tiles_x * g.tiles_y * 1024);
   g.periodic = cfg->periodic ? 1 : 0;
+  g.py = g.periodic; g.y_lo = 0; g.y_hi = g.ny; g.y_off = 0; g.own_lo = 0; g.own_hi = g.ny;
   Params& p = h->params;
   memset(&p, 0, sizeof p);
   p.walk_type = cfg->walk_type; p.eat = cfg->eat; p.reproduce = cfg->reproduce; p.ifempty = cfg->randomwalk_ifempty;

@@ -51,9 +51,14 @@ enum { TILE_SHIFT = 5, TILE = 32, TILE_CELLS = 1024 };
 enum { GREG_MAX_R = 7, GREG_WORDS = 4 };
 
 struct Geo {
-  int32_t nx, ny, tiles_x, tiles_y;
-  uint32_t gt; /* number of tile-major cells incl. padding */
-  int32_t periodic;
+  int32_t nx, ny, tiles_x, tiles_y; /* the grid this handle stores: the whole GridSpace, or (strip mode) the rows of one
+                                     * strip plus one 32-row ghost tile row above and below */
+  uint32_t gt;      /* number of tile-major cells incl. padding */
+  int32_t periodic; /* x axis wraps (and y too, unless a strip) */
+  int32_t py;       /* y axis wraps inside this handle's grid (0 in strip mode: the ghost rows carry the wrap) */
+  int32_t y_lo, y_hi; /* rows a non-wrapping move may land on (clamping bounds of Agents.walk! on a non-periodic space) */
+  int32_t y_off;    /* global y = stored y + y_off */
+  int32_t own_lo, own_hi; /* rows owned by this handle */
 };
 
 /* offsets_at_radius(model, 1) order (x fastest), SURVEY.md A-5 */
@@ -83,9 +88,11 @@ ABM_HD int g_wrap(int a, int n, int periodic) { return periodic ? wrap_far(a, n)
 
 /* pos + (dx,dy): wrapped when periodic; false when it leaves a non-periodic grid */
 ABM_HD bool shift(const Geo& g, int x, int y, int dx, int dy, int& ox, int& oy) {
-  ox = x + dx; oy = y + dy;
-  if (g.periodic) { ox = wrap(ox, g.nx); oy = wrap(oy, g.ny); return true; } /* |dx|, |dy| <= 1 at every call site */
-  return ox >= 0 && ox < g.nx && oy >= 0 && oy < g.ny;
+  ox = x + dx; oy = y + dy; /* |dx|, |dy| <= 1 at every call site */
+  bool ok = true;
+  if (g.periodic) ox = wrap(ox, g.nx); else ok = ox >= 0 && ox < g.nx;
+  if (g.py) oy = wrap(oy, g.ny); else ok = ok && oy >= g.y_lo && oy < g.y_hi;
+  return ok;
 }
 
 /* the distinct in-bounds cells of the 3x3 block around (x,y), centre first */
@@ -146,26 +153,30 @@ ABM_HD bool present(uint8_t s) { return !(s & ST_DEAD) || (s & ST_BIRTH); }
 
 /* effective direction code after GridSpace clamping / wrapping (Agents.walk!) */
 ABM_HD int effective_dir(const Geo& g, int x, int y, int dx, int dy) {
-  int tx, ty;
+  int tx = x + dx, ty = y + dy;
   if (g.periodic) {
-    tx = wrap(x + dx, g.nx); ty = wrap(y + dy, g.ny);
-    if (tx == x && ty == y) return DIR_STAY;
+    tx = wrap(tx, g.nx);
     if (g.nx < 3 && tx != x) dx = 1; /* both x-neighbours alias on a 2-wide ring: canonical direction */
-    if (g.ny < 3 && ty != y) dy = 1;
     if (tx == x) dx = 0;
-    if (ty == y) dy = 0;
-    return dir_code(dx, dy);
+  } else {
+    tx = tx < 0 ? 0 : (tx >= g.nx ? g.nx - 1 : tx);
+    dx = tx - x;
   }
-  tx = x + dx; ty = y + dy;
-  tx = tx < 0 ? 0 : (tx >= g.nx ? g.nx - 1 : tx);
-  ty = ty < 0 ? 0 : (ty >= g.ny ? g.ny - 1 : ty);
-  return dir_code(tx - x, ty - y);
+  if (g.py) {
+    ty = wrap(ty, g.ny);
+    if (g.ny < 3 && ty != y) dy = 1;
+    if (ty == y) dy = 0;
+  } else {
+    ty = ty < g.y_lo ? g.y_lo : (ty >= g.y_hi ? g.y_hi - 1 : ty);
+    dy = ty - y;
+  }
+  return dir_code(dx, dy); /* (0, 0) -> DIR_STAY */
 }
 
 /* random_walk_to_attractor (src/agent_actions.jl:263-267): round.(Int, normalize(attractor .- pos)) as the
  * exact integer predicate of SURVEY.md A-6 */
-ABM_HD void attractor_dir(const Params& p, int x, int y, int& dx, int& dy) {
-  const int64_t ex = p.ax2 - 2 * (int64_t)(x + 1), ey = p.ay2 - 2 * (int64_t)(y + 1);
+ABM_HD void attractor_dir(const Params& p, const Geo& g, int x, int y, int& dx, int& dy) {
+  const int64_t ex = p.ax2 - 2 * (int64_t)(x + 1), ey = p.ay2 - 2 * (int64_t)(y + g.y_off + 1);
   dx = 0; dy = 0;
   if (ex == 0 && ey == 0) return;
   if (3 * ex * ex > ey * ey) dx = ex > 0 ? 1 : -1;
@@ -196,7 +207,7 @@ struct ProposeBody {
       case ABM_RANDOM_WALK: randomwalk = true; break; /* :37-39 */
       case ABM_RANDOM_WALK_ATTRACTOR:                 /* :40-42, execute_walk! :109-117 */
         if (rs.next_f64() < p.prob_random_walk) randomwalk = true;
-        else { attractor_dir(p, x, y, dx, dy); cond = true; /* walk!(...; ifempty=true), :266 */ }
+        else { attractor_dir(p, v.g, x, y, dx, dy); cond = true; /* walk!(...; ifempty=true), :266 */ }
         break;
       case ABM_RANDOM_WALK_GREGARIOUS:                /* :43-45 */
         if (rs.next_f64() < p.prob_random_walk) randomwalk = true;
@@ -736,8 +747,8 @@ struct IngestBody {
   uint32_t* err;
 
   ABM_HD void operator()(uint64_t i) const {
-    const int64_t x = hx[i], y = hy[i], a = hid[i];
-    if (x < 1 || x > g.nx || y < 1 || y > g.ny || a < 1 || a >= next_id) { atomic_or(err, ERR_INTERNAL); cell[i] = 0; id[i] = 0; energy[i] = 0; state[i] = ST_DEAD; return; }
+    const int64_t x = hx[i], y = hy[i] - g.y_off, a = hid[i];
+    if (x < 1 || x > g.nx || y < 1 + g.own_lo || y > g.own_hi || a < 1 || a >= next_id) { atomic_or(err, ERR_INTERNAL); cell[i] = 0; id[i] = 0; energy[i] = 0; state[i] = ST_DEAD; return; }
     const uint32_t c = enc(g, (int)(x - 1), (int)(y - 1));
     const uint32_t bit = 1u << ((uint32_t)a & 31);
     if (atomic_or(&alive_bits[(uint32_t)a >> 5], bit) & bit) atomic_or(err, ERR_INTERNAL); /* duplicate id */
@@ -765,7 +776,7 @@ struct ExportBody {
     const uint32_t rank = prefix[w] + (uint32_t)popc(alive_bits[w] & ((1u << (a & 31)) - 1u));
     int x, y;
     dec(g, cell[i], x, y);
-    oid[rank] = a; ox[rank] = x + 1; oy[rank] = y + 1; oe[rank] = energy[i];
+    oid[rank] = a; ox[rank] = x + 1; oy[rank] = y + g.y_off + 1; oe[rank] = energy[i];
   }
 };
 

@@ -54,8 +54,8 @@ struct Window {
   /* global sub-tile of run r, or -1 when it lies outside a non-periodic grid */
   ABM_HD int sub_of_run(int r, const Geo& g, const SubIndex& si) const {
     int sx = ssx0 + r % nssx, sy = ssy0 + r / nssx;
-    if (g.periodic) { sx = wrap_far(sx, si.nsx); sy = wrap_far(sy, si.nsy); }
-    else if (sx < 0 || sx >= si.nsx || sy < 0 || sy >= si.nsy) return -1;
+    if (g.periodic) sx = wrap_far(sx, si.nsx); else if (sx < 0 || sx >= si.nsx) return -1;
+    if (g.py) sy = wrap_far(sy, si.nsy); else if (sy < 0 || sy >= si.nsy) return -1;
     return sy * si.nsx + sx;
   }
   /* window coordinates of an agent of run r standing on tcell c; false when outside the window */
@@ -232,7 +232,7 @@ ABM_HD int evaluate(const View& v, const Summaries& s, const Window& w, uint32_t
 struct ResolveWindow {
   View v;
   SubIndex si;
-  int32_t mode, cores_x, max_rounds, nthreads;
+  int32_t mode, cores_x, core_y0, max_rounds, nthreads;
   const uint32_t* in;
   uint32_t* out;
   uint32_t* out_count;
@@ -245,7 +245,7 @@ struct ResolveWindow {
    * buffered).  Agents are read from global memory exactly once.  Returns false (uniformly) when the list overflows. */
   ABM_HD bool core_fast(uint32_t cta, uint32_t* smem) const {
     Window w;
-    const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x);
+    const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) + core_y0;
     w.set(cx * CORE - HALO, cy * CORE - HALO, WIN, WIN);
     const int cells = WIN * WIN, nruns = w.runs(), NT = TILE_THREADS;
     uint32_t* max_old = smem;
@@ -413,7 +413,7 @@ struct ResolveWindow {
     uint32_t target = NONE32;
     int own_lo = 0, own_hi = 0;
     if (mode == 0) {
-      const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x);
+      const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) + core_y0;
       w.set(cx * CORE - HALO, cy * CORE - HALO, WIN, WIN);
       own_lo = HALO; own_hi = HALO + CORE;
     } else {
@@ -506,7 +506,7 @@ struct ResolveWindow {
 struct CommitTile {
   View v;
   SubIndex si;
-  int32_t cores_x;
+  int32_t cores_x, core_y0;
   uint32_t* out_cell; uint32_t* out_id; double* out_energy;
   uint32_t* new_off; uint32_t* new_cnt; /* next tick's sub-tile runs */
   uint32_t* cursor;                     /* next free slot of the output SoA */
@@ -515,7 +515,7 @@ struct CommitTile {
   static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 16 * 3 + RUNTABLE_WORDS + 8 + 3 * ARRIVE_CAP) * 4; }
 
   ABM_HD void operator()(uint32_t cta, uint32_t* smem) const {
-    const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x);
+    const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) + core_y0;
     Window w;
     w.set(cx * CORE - HALO, cy * CORE - HALO, WIN, WIN);
     const int nruns = w.runs(), NT = TILE_THREADS;
@@ -530,7 +530,7 @@ struct CommitTile {
     uint32_t* ar_a = misc + 8;                 /* arrivals: agent index, id, core cell | state << 16 */
     uint32_t* ar_id = ar_a + ARRIVE_CAP;
     uint32_t* ar_cs = ar_id + ARRIVE_CAP;
-    const uint32_t tile = cta; /* CORE == TILE: core b is grass tile b */
+    const uint32_t tile = (uint32_t)(cy * cores_x + cx); /* CORE == TILE: a core is one grass tile */
     uint32_t* gtile = (uint32_t*)(v.grass + (size_t)tile * TILE_CELLS);
 
     ABM_CTA_FOR(t, NT) {
@@ -657,8 +657,8 @@ struct IngestTileBody {
   uint32_t* cell; uint32_t* id; double* energy; uint32_t* slot; uint32_t* sub;
   uint32_t* sub_cnt; uint32_t* alive_bits; uint32_t* err;
   ABM_HD void operator()(uint64_t i) const {
-    const int64_t x = hx[i], y = hy[i], a = hid[i];
-    if (x < 1 || x > g.nx || y < 1 || y > g.ny || a < 1 || a >= next_id) { atomic_or(err, ERR_INTERNAL); cell[i] = 0; id[i] = 0; energy[i] = 0; sub[i] = NONE32; return; }
+    const int64_t x = hx[i], y = hy[i] - g.y_off, a = hid[i];
+    if (x < 1 || x > g.nx || y < 1 + g.own_lo || y > g.own_hi || a < 1 || a >= next_id) { atomic_or(err, ERR_INTERNAL); cell[i] = 0; id[i] = 0; energy[i] = 0; sub[i] = NONE32; return; }
     const uint32_t bit = 1u << ((uint32_t)a & 31);
     if (atomic_or(&alive_bits[(uint32_t)a >> 5], bit) & bit) atomic_or(err, ERR_INTERNAL);
     const uint32_t st = (uint32_t)(((y - 1) >> 3) * nsx + ((x - 1) >> 3));
