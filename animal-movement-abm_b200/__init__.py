@@ -5,7 +5,7 @@ The package directory is named ``animal-movement-abm_b200`` (not importable as w
 kernels and the C ABI of ``include/abm.h``), the ctypes binding, and the host-side mirror of the reference's
 operator interface (``herbivore_dynamics`` / ``grass_growth_dynamics`` / ``step`` / ``run``).
 """
-from . import capi, model, worlds  # noqa: F401
+from . import capi, model, strips, worlds  # noqa: F401
 from .capi import (ALTERNATED_WALK, RANDOM_WALK, RANDOM_WALK_ATTRACTOR, RANDOM_WALK_GREGARIOUS,  # noqa: F401
                    RANDOM_WALKMAP, AbmConfig, AbmError, CLib, Engine)
 from .model import (EngineAgentStep, EngineModelStep, SheepModel, WalkType, count, count_grass,  # noqa: F401

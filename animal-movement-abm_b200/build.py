@@ -19,7 +19,7 @@ LIBEMU = os.path.join(ROOT, "tests", "emu", "libabm_emu.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",  # the gregarious weights and energies must round exactly like the reference's IEEE ops
-    "-Xcompiler", "-fPIC,-Wall", "-shared",
+    "-Xcompiler", "-fPIC,-Wall", "-shared", "-ldl",
 ]
 
 

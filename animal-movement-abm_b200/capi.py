@@ -48,7 +48,22 @@ class AbmConfig(C.Structure):
         ("attractor_x", C.c_double),
         ("attractor_y", C.c_double),
         ("seed", C.c_uint64),
+        ("strip_y0", C.c_int32),
+        ("strip_ny", C.c_int32),
+        ("n_ranks", C.c_int32),
+        ("rank", C.c_int32),
     ]
+
+
+SENDRECV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_int32)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32)
+
+
+class AbmTransport(C.Structure):
+    """struct abm_transport (include/abm.h)."""
+
+    _fields_ = [("user", C.c_void_p), ("sendrecv", SENDRECV_FN), ("allreduce_sum_u64", ALLREDUCE_FN), ("allgather_u32", ALLGATHER_FN)]
 
 
 class AbmError(RuntimeError):
@@ -82,6 +97,9 @@ SIGNATURES = {
     "get_timing": (C.c_int, [_P, _F64P, C.c_int32]),
     "set_profiling": (C.c_int, [_P, C.c_int32]),
     "get_kernel_stat": (C.c_int, [_P, C.c_int32, C.c_char_p, C.c_int32, _F64P, _I64P, _I64P]),
+    "set_transport": (C.c_int, [_P, C.POINTER(AbmTransport)]),
+    "nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "comm_init_nccl": (C.c_int, [_P, C.c_void_p]),
     "last_error": (C.c_char_p, [_P]),
 }
 
@@ -232,6 +250,14 @@ class Engine:
         self._ck(self.lib.fn["get_timing"](self.h, _ptr(out, _F64P), out.size))
         return dict(ms_total=out[0], ms_agents=out[1], ms_grass=out[2], rounds=out[3], launches=out[4], astar_expansions=out[5],
                     agent_updates=out[6])
+
+    def set_transport(self, transport: "AbmTransport"):
+        self._transport = transport  # keep the callbacks alive
+        self._ck(self.lib.fn["set_transport"](self.h, C.byref(transport)))
+
+    def comm_init_nccl(self, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._ck(self.lib.fn["comm_init_nccl"](self.h, buf))
 
     def set_profiling(self, on=True):
         self._ck(self.lib.fn["set_profiling"](self.h, int(bool(on))))

@@ -6,6 +6,10 @@
  */
 #include <math.h>
 #include <stdio.h>
+#ifndef ABM_EMU
+#include <dlfcn.h>
+#include <nccl.h>
+#endif
 
 #include <algorithm>
 #include <new>
@@ -258,6 +262,16 @@ struct abm_handle {
   int32_t tile_rounds = 8; /* in-window rounds of the tile resolve kernel (ABM_TILE_ROUNDS overrides; tests use 1) */
   int32_t nsx = 0, nsy = 0;
   DevBuf sub_off[2], sub_cnt[2], birth_pos, birth_parent, ingest_sub;
+  /* row strips: ring neighbours, transport, boundary-row staging ([0] = towards / from the previous strip, [1] = next) */
+  bool strip = false;
+  int32_t n_ranks = 1, my_rank = 0;
+  bool has_prev = false, has_next = false;
+  abm_transport tr;
+  bool has_tr = false;
+  void* nccl_comm = nullptr;
+  DevBuf sx_cnt[2], sx_pre[2], rx_cnt[2], rx_pre[2], sx_buf[2], rx_buf[2], sx_st[2], rx_st[2], red_buf, birth_ids;
+  uint64_t n_send[2] = {0, 0}, n_recv[2] = {0, 0}, n_ghost = 0;
+  std::vector<uint8_t> hstage[4];
   uint32_t* h_counters = nullptr; /* host mirror (pinned on CUDA) */
 
   uint64_t n = 0, next_id = 1, tick = 0;
@@ -745,6 +759,246 @@ static SubIndex sub_index(abm_handle* h, int which) {
   return si;
 }
 
+/* ------------------------------------------------------------------------------------------ ring transport */
+#ifndef ABM_EMU
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (lib) return true;
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL); /* the copy the host process already loaded (torch's), if any */
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return false;
+#define ABM_NCCL_SYM(name) *(void**)(&name) = dlsym(lib, "nccl" #name); if (!name) return false;
+    ABM_NCCL_SYM(GetUniqueId) ABM_NCCL_SYM(CommInitRank) ABM_NCCL_SYM(CommDestroy) ABM_NCCL_SYM(Send) ABM_NCCL_SYM(Recv)
+    ABM_NCCL_SYM(GroupStart) ABM_NCCL_SYM(GroupEnd) ABM_NCCL_SYM(AllReduce) ABM_NCCL_SYM(AllGather) ABM_NCCL_SYM(GetErrorString)
+#undef ABM_NCCL_SYM
+    return true;
+  }
+};
+static NcclApi g_nccl;
+#define ABM_NCCL(h, call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) ABM_FAIL(h, ABM_E_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); } while (0)
+#endif
+
+/* boundary exchange with the ring neighbours; all pointers are device memory of this handle */
+static int comm_sendrecv(abm_handle* h, const void* to_prev, uint64_t b_tp, const void* to_next, uint64_t b_tn, void* from_prev, uint64_t b_fp, void* from_next, uint64_t b_fn) {
+  if (!h->has_prev) { b_tp = 0; b_fp = 0; }
+  if (!h->has_next) { b_tn = 0; b_fn = 0; }
+  if (h->n_ranks == 1) { /* a ring of one: my first rows are the ghost rows below my last rows and vice versa */
+    if (b_tp != b_fn || b_tn != b_fp) ABM_FAIL(h, ABM_E_INTERNAL, "self exchange size mismatch");
+    if (b_tp) ABM_CK(h, copy_d2d(from_next, to_prev, b_tp, h->stream));
+    if (b_tn) ABM_CK(h, copy_d2d(from_prev, to_next, b_tn, h->stream));
+    return 0;
+  }
+  const int prev = (h->my_rank + h->n_ranks - 1) % h->n_ranks, next = (h->my_rank + 1) % h->n_ranks;
+#ifndef ABM_EMU
+  if (h->nccl_comm) {
+    ncclComm_t c = (ncclComm_t)h->nccl_comm;
+    ABM_NCCL(h, g_nccl.GroupStart());
+    if (b_tp) ABM_NCCL(h, g_nccl.Send(to_prev, b_tp, ncclUint8, prev, c, h->stream));
+    if (b_tn) ABM_NCCL(h, g_nccl.Send(to_next, b_tn, ncclUint8, next, c, h->stream));
+    if (b_fn) ABM_NCCL(h, g_nccl.Recv(from_next, b_fn, ncclUint8, next, c, h->stream));
+    if (b_fp) ABM_NCCL(h, g_nccl.Recv(from_prev, b_fp, ncclUint8, prev, c, h->stream));
+    ABM_NCCL(h, g_nccl.GroupEnd());
+    return 0;
+  }
+#endif
+  (void)prev; (void)next;
+  if (!h->has_tr) ABM_FAIL(h, ABM_E_STATE, "n_ranks > 1 needs abm_comm_init_nccl or abm_set_transport before abm_step");
+  const void* src[2] = {to_prev, to_next};
+  const uint64_t sb[2] = {b_tp, b_tn}, rb[2] = {b_fp, b_fn};
+  for (int q = 0; q < 2; ++q) {
+    h->hstage[q].resize(sb[q] + 8);
+    h->hstage[2 + q].resize(rb[q] + 8);
+    if (sb[q]) ABM_CK(h, copy_d2h(h->hstage[q].data(), src[q], sb[q], h->stream));
+  }
+  ABM_CK(h, stream_sync(h->stream));
+  if (h->tr.sendrecv(h->tr.user, h->hstage[0].data(), b_tp, h->hstage[1].data(), b_tn, h->hstage[2].data(), b_fp, h->hstage[3].data(), b_fn) != 0)
+    ABM_FAIL(h, ABM_E_INTERNAL, "transport sendrecv failed");
+  if (b_fp) ABM_CK(h, copy_h2d(from_prev, h->hstage[2].data(), b_fp, h->stream));
+  if (b_fn) ABM_CK(h, copy_h2d(from_next, h->hstage[3].data(), b_fn, h->stream));
+  return 0;
+}
+
+static int comm_allreduce_u64(abm_handle* h, uint64_t* vals, int n) {
+  if (h->n_ranks == 1) return 0;
+#ifndef ABM_EMU
+  if (h->nccl_comm) {
+    int rc = ensure(h, h->red_buf, (size_t)n * 8);
+    if (rc) return rc;
+    ABM_CK(h, copy_h2d(h->red_buf.p, vals, (size_t)n * 8, h->stream));
+    ABM_NCCL(h, g_nccl.AllReduce(h->red_buf.p, h->red_buf.p, (size_t)n, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+    ABM_CK(h, copy_d2h(vals, h->red_buf.p, (size_t)n * 8, h->stream));
+    return 0;
+  }
+#endif
+  if (!h->has_tr) ABM_FAIL(h, ABM_E_STATE, "n_ranks > 1 needs abm_comm_init_nccl or abm_set_transport before abm_step");
+  if (h->tr.allreduce_sum_u64(h->tr.user, vals, n) != 0) ABM_FAIL(h, ABM_E_INTERNAL, "transport allreduce failed");
+  return 0;
+}
+
+/* every rank contributes n u32; recv holds n_ranks * n */
+static int comm_allgather_u32(abm_handle* h, const uint32_t* send, uint32_t* recv, uint32_t n) {
+  if (h->n_ranks == 1) { memcpy(recv, send, (size_t)n * 4); return 0; }
+#ifndef ABM_EMU
+  if (h->nccl_comm) {
+    int rc = ensure(h, h->red_buf, (size_t)n * 4 * (size_t)(h->n_ranks + 1));
+    if (rc) return rc;
+    uint32_t* d_send = (uint32_t*)h->red_buf.p;
+    uint32_t* d_recv = d_send + n;
+    ABM_CK(h, copy_h2d(d_send, send, (size_t)n * 4, h->stream));
+    ABM_NCCL(h, g_nccl.AllGather(d_send, d_recv, (size_t)n, ncclUint32, (ncclComm_t)h->nccl_comm, h->stream));
+    ABM_CK(h, copy_d2h(recv, d_recv, (size_t)n * 4 * (size_t)h->n_ranks, h->stream));
+    return 0;
+  }
+#endif
+  if (!h->has_tr) ABM_FAIL(h, ABM_E_STATE, "n_ranks > 1 needs abm_comm_init_nccl or abm_set_transport before abm_step");
+  if (h->tr.allgather_u32(h->tr.user, send, recv, n) != 0) ABM_FAIL(h, ABM_E_INTERNAL, "transport allgather failed");
+  return 0;
+}
+
+/* E1: this strip's first and last sub-tile rows (cell, id, energy, proposal) become the neighbours' ghost rows */
+static int strip_exchange_agents(abm_handle* h) {
+  int rc;
+  const int nsx = h->nsx, cur = h->cur;
+  const int row_s[2] = {h->g.own_lo / SUB, h->g.own_hi / SUB - 1};       /* my rows sent to prev / next */
+  const int row_g[2] = {h->g.own_lo / SUB - 1, h->g.own_hi / SUB};       /* ghost rows filled from prev / next */
+  const uint32_t tile_row_g[2] = {(uint32_t)(h->g.own_lo / CORE - 1), (uint32_t)(h->g.own_hi / CORE)};
+  std::vector<uint32_t> cnt((size_t)nsx), pre((size_t)nsx + 1);
+  for (int d = 0; d < 2; ++d) {
+    if ((rc = ensure(h, h->sx_cnt[d], (size_t)nsx * 4))) return rc;
+    if ((rc = ensure(h, h->sx_pre[d], (size_t)nsx * 4 + 4))) return rc;
+    if ((rc = ensure(h, h->rx_cnt[d], (size_t)nsx * 4))) return rc;
+    if ((rc = ensure(h, h->rx_pre[d], (size_t)nsx * 4 + 4))) return rc;
+    GatherCountsBody gc;
+    gc.sub_cnt = (const uint32_t*)h->sub_cnt[cur].p; gc.row = row_s[d]; gc.nsx = nsx; gc.out = (uint32_t*)h->sx_cnt[d].p;
+    launch_foreach(h->stream, gc, (uint64_t)nsx);
+    ABM_CK(h, copy_d2h(cnt.data(), h->sx_cnt[d].p, (size_t)nsx * 4, h->stream));
+    uint32_t run = 0;
+    for (int i = 0; i < nsx; ++i) { pre[i] = run; run += cnt[i]; }
+    h->n_send[d] = run;
+    ABM_CK(h, copy_h2d(h->sx_pre[d].p, pre.data(), (size_t)nsx * 4, h->stream));
+    ABM_CK(h, dev_memset(h->rx_cnt[d].p, 0, (size_t)nsx * 4, h->stream));
+  }
+  if ((rc = comm_sendrecv(h, h->sx_cnt[0].p, (uint64_t)nsx * 4, h->sx_cnt[1].p, (uint64_t)nsx * 4, h->rx_cnt[0].p, (uint64_t)nsx * 4, h->rx_cnt[1].p, (uint64_t)nsx * 4))) return rc;
+  for (int d = 0; d < 2; ++d) {
+    ABM_CK(h, copy_d2h(cnt.data(), h->rx_cnt[d].p, (size_t)nsx * 4, h->stream));
+    uint32_t run = 0;
+    for (int i = 0; i < nsx; ++i) { pre[i] = run; run += cnt[i]; }
+    h->n_recv[d] = run;
+    ABM_CK(h, copy_h2d(h->rx_pre[d].p, pre.data(), (size_t)nsx * 4, h->stream));
+  }
+  h->n_ghost = h->n_recv[0] + h->n_recv[1];
+  /* payload: [energy n x 8][cell n x 4][id n x 4][state n] per direction */
+  for (int d = 0; d < 2; ++d) {
+    const uint64_t n = h->n_send[d];
+    if ((rc = ensure(h, h->sx_buf[d], n * 17 + 64))) return rc;
+    if ((rc = ensure(h, h->rx_buf[d], h->n_recv[d] * 17 + 64))) return rc;
+    uint8_t* b = (uint8_t*)h->sx_buf[d].p;
+    PackRowBody pk;
+    pk.si = sub_index(h, cur); pk.row = row_s[d]; pk.tiles_x = h->g.tiles_x;
+    pk.cell = (const uint32_t*)h->cell[cur].p; pk.id = (const uint32_t*)h->id[cur].p; pk.energy = (const double*)h->energy[cur].p; pk.state = (const uint8_t*)h->state.p;
+    pk.prefix = (const uint32_t*)h->sx_pre[d].p;
+    pk.p_energy = (double*)b; pk.p_cell = (uint32_t*)(b + n * 8); pk.p_id = (uint32_t*)(b + n * 12); pk.p_state = b + n * 16;
+    launch_foreach(h->stream, pk, (uint64_t)nsx);
+  }
+  if ((rc = check_launch(h, "strip pack"))) return rc;
+  if ((rc = comm_sendrecv(h, h->sx_buf[0].p, h->n_send[0] * 17, h->sx_buf[1].p, h->n_send[1] * 17, h->rx_buf[0].p, h->n_recv[0] * 17, h->rx_buf[1].p, h->n_recv[1] * 17))) return rc;
+  /* ghost agents go behind the own agents of the current SoA */
+  const uint64_t tot = h->n + h->n_ghost + 1;
+  if ((rc = grow_keep(h, h->cell[cur], tot * 4))) return rc;
+  if ((rc = grow_keep(h, h->id[cur], tot * 4))) return rc;
+  if ((rc = grow_keep(h, h->energy[cur], tot * 8))) return rc;
+  if ((rc = grow_keep(h, h->state, tot))) return rc;
+  if ((rc = ensure(h, h->pend[0], tot * 4))) return rc;
+  if ((rc = ensure(h, h->pend[1], tot * 4))) return rc;
+  uint64_t base = h->n;
+  for (int d = 0; d < 2; ++d) {
+    const uint64_t n = h->n_recv[d];
+    const uint8_t* b = (const uint8_t*)h->rx_buf[d].p;
+    UnpackRowBody up;
+    up.row = row_g[d]; up.nsx = nsx; up.tile_row_base = (tile_row_g[d] * (uint32_t)h->g.tiles_x) << 10; up.base = (uint32_t)base;
+    up.counts = (const uint32_t*)h->rx_cnt[d].p; up.prefix = (const uint32_t*)h->rx_pre[d].p;
+    up.p_energy = (const double*)b; up.p_cell = (const uint32_t*)(b + n * 8); up.p_id = (const uint32_t*)(b + n * 12); up.p_state = b + n * 16;
+    up.sub_off = (uint32_t*)h->sub_off[cur].p; up.sub_cnt = (uint32_t*)h->sub_cnt[cur].p;
+    up.cell = (uint32_t*)h->cell[cur].p; up.id = (uint32_t*)h->id[cur].p; up.energy = (double*)h->energy[cur].p; up.state = (uint8_t*)h->state.p;
+    launch_foreach(h->stream, up, (uint64_t)nsx);
+    base += n;
+  }
+  return check_launch(h, "strip unpack");
+}
+
+/* E2: the decision bytes of the same boundary rows, merged into the ghost copies */
+static int strip_exchange_states(abm_handle* h) {
+  int rc;
+  const int cur = h->cur;
+  const int row_s[2] = {h->g.own_lo / SUB, h->g.own_hi / SUB - 1};
+  for (int d = 0; d < 2; ++d) {
+    if ((rc = ensure(h, h->sx_st[d], h->n_send[d] + 64))) return rc;
+    if ((rc = ensure(h, h->rx_st[d], h->n_recv[d] + 64))) return rc;
+    PackRowBody pk;
+    pk.si = sub_index(h, cur); pk.row = row_s[d]; pk.tiles_x = h->g.tiles_x;
+    pk.cell = (const uint32_t*)h->cell[cur].p; pk.id = nullptr; pk.energy = nullptr; pk.state = (const uint8_t*)h->state.p;
+    pk.prefix = (const uint32_t*)h->sx_pre[d].p;
+    pk.p_energy = nullptr; pk.p_cell = nullptr; pk.p_id = nullptr; pk.p_state = (uint8_t*)h->sx_st[d].p;
+    launch_foreach(h->stream, pk, (uint64_t)h->nsx);
+  }
+  if ((rc = comm_sendrecv(h, h->sx_st[0].p, h->n_send[0], h->sx_st[1].p, h->n_send[1], h->rx_st[0].p, h->n_recv[0], h->rx_st[1].p, h->n_recv[1]))) return rc;
+  uint64_t base = h->n;
+  for (int d = 0; d < 2; ++d) {
+    MergeStateBody mg;
+    mg.incoming = (const uint8_t*)h->rx_st[d].p; mg.state = (uint8_t*)h->state.p; mg.base = (uint32_t)base;
+    launch_foreach(h->stream, mg, h->n_recv[d]);
+    base += h->n_recv[d];
+  }
+  return check_launch(h, "strip state merge");
+}
+
+/* offspring ids across strips: global order of all parents' ids */
+static int strip_birth_ids(abm_handle* h, uint64_t nb, int nxt, uint64_t* total_out) {
+  int rc;
+  std::vector<uint64_t> counts((size_t)h->n_ranks, 0);
+  counts[h->my_rank] = nb;
+  if ((rc = comm_allreduce_u64(h, counts.data(), h->n_ranks))) return rc;
+  uint64_t total = 0, nmax = 0;
+  for (int r = 0; r < h->n_ranks; ++r) { total += counts[r]; nmax = std::max(nmax, counts[r]); }
+  *total_out = total;
+  if (total == 0) return 0;
+  std::vector<uint32_t> mine((size_t)nmax, 0xFFFFFFFFu), pos((size_t)nb), all((size_t)nmax * h->n_ranks);
+  if (nb) {
+    ABM_CK(h, copy_d2h(mine.data(), h->birth_parent.p, nb * 4, h->stream));
+    ABM_CK(h, copy_d2h(pos.data(), h->birth_pos.p, nb * 4, h->stream));
+  }
+  if ((rc = comm_allgather_u32(h, mine.data(), all.data(), (uint32_t)nmax))) return rc;
+  std::vector<uint32_t> sorted;
+  sorted.reserve((size_t)total);
+  for (int r = 0; r < h->n_ranks; ++r) for (uint64_t i = 0; i < counts[r]; ++i) sorted.push_back(all[(size_t)r * nmax + i]);
+  std::sort(sorted.begin(), sorted.end());
+  if (nb) {
+    std::vector<uint32_t> ids((size_t)nb);
+    for (uint64_t i = 0; i < nb; ++i) ids[i] = (uint32_t)(h->next_id + (uint64_t)(std::lower_bound(sorted.begin(), sorted.end(), mine[i]) - sorted.begin()));
+    if ((rc = ensure(h, h->birth_ids, nb * 8))) return rc;
+    uint32_t* d_ids = (uint32_t*)h->birth_ids.p;
+    uint32_t* d_pos = d_ids + nb;
+    ABM_CK(h, copy_h2d(d_ids, ids.data(), nb * 4, h->stream));
+    ABM_CK(h, copy_h2d(d_pos, pos.data(), nb * 4, h->stream));
+    ScatterIdsBody sc;
+    sc.pos = d_pos; sc.ids = d_ids; sc.out_id = (uint32_t*)h->id[nxt].p;
+    launch_foreach(h->stream, sc, nb);
+    if ((rc = check_launch(h, "birth ids"))) return rc;
+  }
+  return 0;
+}
+
 /* one tick on the tile path (abm_tile.h): propose -> window resolve -> per-agent windows for the rest -> commit */
 static int tick_tile(abm_handle* h) {
   int rc;
@@ -767,6 +1021,12 @@ static int tick_tile(abm_handle* h) {
     pb.v = v; pb.pending = nullptr; pb.pending_count = nullptr; pb.birth_flags = ctr + CTR_BIRTH_FLAGS;
     { ProfScope ps(h->prof, h->stream, "propose", n); launch_foreach(h->stream, pb, n); }
     if ((rc = check_launch(h, "propose"))) return rc;
+  }
+  if (h->strip) { /* neighbours' boundary rows become ghost rows behind the own agents */
+    if ((rc = strip_exchange_agents(h))) return rc;
+    v = make_view(h);
+  }
+  if (n + h->n_ghost > 0) {
     if (needs_resolve) {
       ResolveWindow rw;
       rw.v = v; rw.si = si; rw.mode = 0; rw.cores_x = h->g.nx / CORE; rw.core_y0 = h->g.own_lo / CORE; rw.max_rounds = h->tile_rounds; rw.nthreads = TILE_THREADS;
@@ -781,7 +1041,17 @@ static int tick_tile(abm_handle* h) {
   {
     int in = 0, stalls = 0;
     const int q = wt == ABM_RANDOM_WALK_GREGARIOUS ? h->cfg.visual_distance + 1 : 2;
-    while (cnt > 0) { /* chains that left their window: one small window per agent, Jacobi rounds */
+    uint64_t global_cnt = cnt;
+    while (true) { /* chains that left their window: one small window per agent, Jacobi rounds */
+      if (h->strip) { /* the owners' decisions reach the ghost copies; every rank stays in the loop until all are done */
+        global_cnt = cnt;
+        if ((rc = comm_allreduce_u64(h, &global_cnt, 1))) return rc;
+        if (needs_resolve && (rc = strip_exchange_states(h))) return rc;
+      } else {
+        global_cnt = cnt;
+      }
+      if (global_cnt == 0) break;
+      if (cnt == 0) { h->rounds += 1; continue; }
       ABM_CK(h, dev_memset(ctr + (in ? CTR_PEND_A : CTR_PEND_B), 0, sizeof(uint32_t), h->stream));
       ResolveWindow rw;
       rw.v = v; rw.si = si; rw.mode = 1; rw.cores_x = 0; rw.core_y0 = 0; rw.max_rounds = 1; rw.nthreads = AGENT_THREADS;
@@ -792,7 +1062,7 @@ static int tick_tile(abm_handle* h) {
       const uint64_t left = h->h_counters[in ? CTR_PEND_A : CTR_PEND_B];
       h->rounds += 1;
       stalls = left == cnt ? stalls + 1 : 0;
-      if (stalls > 8) ABM_FAIL(h, ABM_E_INTERNAL, "conflict resolution made no progress with %llu agents pending", (unsigned long long)left);
+      if (stalls > 64) ABM_FAIL(h, ABM_E_INTERNAL, "conflict resolution made no progress with %llu agents pending", (unsigned long long)left);
       cnt = left;
       in ^= 1;
     }
@@ -822,7 +1092,11 @@ static int tick_tile(abm_handle* h) {
   if ((rc = device_error_to_code(h))) return rc;
   const uint64_t n_new = h->h_counters[CTR_CURSOR], nb = h->h_counters[CTR_BIRTHS];
   if (h->next_id + nb > 0xFFFFFFFFull) ABM_FAIL(h, ABM_E_CAPACITY, "agent id space (2^32-1) exhausted");
-  if (nb > 0) {
+  uint64_t nb_total = nb;
+  if (h->strip) {
+    if ((rc = strip_birth_ids(h, nb, nxt, &nb_total))) return rc;
+    if (h->next_id + nb_total > 0xFFFFFFFFull) ABM_FAIL(h, ABM_E_CAPACITY, "agent id space (2^32-1) exhausted");
+  } else if (nb > 0) {
     if ((rc = rank_prefix(h, words))) return rc;
     BirthIdBody bi;
     bi.birth_pos = (const uint32_t*)h->birth_pos.p; bi.birth_parent = (const uint32_t*)h->birth_parent.p;
@@ -833,7 +1107,8 @@ static int tick_tile(abm_handle* h) {
   }
   h->cur = nxt;
   h->n = n_new;
-  h->next_id += nb;
+  h->next_id += nb_total;
+  h->n_ghost = 0;
   h->tick += 1;
   h->updates += (double)n;
   return 0;
@@ -860,6 +1135,14 @@ static int validate_config(const abm_config* c, std::string& why) {
   if (c->walk_type == ABM_ALTERNATED_WALK && c->counter < 1) BAD("counter must be >= 1");
   if (!(c->prob_random_walk >= 0 && c->prob_random_walk <= 1)) BAD("prob_random_walk must be in [0,1]");
   if (c->astar_metric != ABM_ASTAR_DIRECT && c->astar_metric != ABM_ASTAR_MAX) BAD("astar_metric out of range");
+  if (c->n_ranks > 1 || c->strip_ny > 0) { /* row strip */
+    const int P = c->n_ranks > 1 ? c->n_ranks : 1;
+    if (c->rank < 0 || c->rank >= P) BAD("rank out of range");
+    if (c->strip_ny < 32 || c->strip_ny % 32 || c->strip_y0 % 32 || c->strip_y0 < 0 || c->strip_y0 + c->strip_ny > c->ny) BAD("strip rows must be multiples of 32 inside the grid");
+    if (c->nx % 32 || c->nx < 64) BAD("strip mode needs nx to be a multiple of 32, at least 64");
+    if (c->walk_type == ABM_ALTERNATED_WALK) BAD("ALTERNATED_WALK (model-global counter, route teleports) is not available in strip mode");
+    if (P == 1 && c->periodic && c->strip_ny != c->ny) BAD("a single periodic strip must cover the whole grid");
+  }
 #undef BAD
   return 0;
 }
@@ -885,7 +1168,9 @@ void ABM_API(destroy)(abm_handle* h) {
   if (!h) return;
 #ifndef ABM_EMU
   cudaSetDevice(h->device);
-  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  if (h->stream) { cudaStreamSynchronize(h->stream); }
+  if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
+  if (h->stream) { cudaStreamDestroy(h->stream); }
   if (h->h_counters) cudaFreeHost(h->h_counters);
 #else
   free(h->h_counters);
@@ -929,12 +1214,23 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
   h->h_counters = (uint32_t*)calloc(CTR_WORDS, sizeof(uint32_t));
 #endif
   h->tm_total.init();
+  h->strip = cfg->n_ranks > 1 || cfg->strip_ny > 0;
+  h->n_ranks = cfg->n_ranks > 1 ? cfg->n_ranks : 1;
+  h->my_rank = h->strip ? cfg->rank : 0;
   Geo& g = h->g;
-  g.nx = cfg->nx; g.ny = cfg->ny;
-  g.tiles_x = (cfg->nx + 31) / 32; g.tiles_y = (cfg->ny + 31) / 32;
+  g.nx = cfg->nx; g.ny = h->strip ? cfg->strip_ny + 2 * CORE : cfg->ny;
+  g.tiles_x = (g.nx + 31) / 32; g.tiles_y = (g.ny + 31) / 32;
   g.gt = (uint32_t)((uint64_t)g.tiles_x * g.tiles_y * 1024);
   g.periodic = cfg->periodic ? 1 : 0;
   g.py = g.periodic; g.y_lo = 0; g.y_hi = g.ny; g.y_off = 0; g.own_lo = 0; g.own_hi = g.ny;
+  if (h->strip) { /* stored rows: [ghost tile row][own rows][ghost tile row]; the ring exchange carries the y wrap */
+    g.py = 0; g.own_lo = CORE; g.own_hi = CORE + cfg->strip_ny; g.y_off = cfg->strip_y0 - CORE;
+    const bool first = cfg->strip_y0 == 0, last = cfg->strip_y0 + cfg->strip_ny == cfg->ny;
+    g.y_lo = (!g.periodic && first) ? g.own_lo : 0;
+    g.y_hi = (!g.periodic && last) ? g.own_hi : g.ny;
+    h->has_prev = g.periodic || !first;
+    h->has_next = g.periodic || !last;
+  }
   Params& p = h->params;
   memset(&p, 0, sizeof p);
   p.walk_type = cfg->walk_type; p.eat = cfg->eat; p.reproduce = cfg->reproduce; p.ifempty = cfg->randomwalk_ifempty;
@@ -946,9 +1242,9 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
 
   /* tile path on grids made of whole 32x32 cores that are wider than one window; everything else (and the model-global
    * counter of ALTERNATED_WALK) takes the general path.  cfg->reserved0 = 1 forces the general path (tests). */
-  h->tile_mode = cfg->reserved0 != 1 && cfg->walk_type != ABM_ALTERNATED_WALK && cfg->nx % CORE == 0 && cfg->ny % CORE == 0 &&
-                 cfg->nx >= 2 * CORE && cfg->ny >= 2 * CORE;
-  h->nsx = cfg->nx / SUB; h->nsy = cfg->ny / SUB;
+  h->tile_mode = h->strip || (cfg->reserved0 != 1 && cfg->walk_type != ABM_ALTERNATED_WALK && cfg->nx % CORE == 0 && cfg->ny % CORE == 0 &&
+                             cfg->nx >= 2 * CORE && cfg->ny >= 2 * CORE);
+  h->nsx = g.nx / SUB; h->nsy = g.ny / SUB;
   if (const char* tr = getenv("ABM_TILE_ROUNDS")) { const int q = atoi(tr); if (q >= 1 && q <= 64) h->tile_rounds = q; }
   rc = 0;
   do {
@@ -958,7 +1254,7 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
     if (h->tile_mode) {
       const size_t nsub = (size_t)h->nsx * h->nsy;
       for (int q = 0; q < 2; ++q) {
-        if ((rc = ensure(h, h->sub_off[q], (nsub + 8) * 4))) break;
+        if ((rc = ensure(h, h->sub_off[q], (nsub + 8) * 4))) break; /* dev_malloc zero-fills: empty ghost rows stay empty */
         if ((rc = ensure(h, h->sub_cnt[q], (nsub + 8) * 4))) break;
       }
       if (rc) break;
@@ -1401,6 +1697,46 @@ int ABM_API(get_paths)(abm_handle* h, int64_t b, const int64_t* agent_id, int64_
   ABM_CK(h, copy_d2h(px, pc.px, (size_t)total * 8, h->stream));
   ABM_CK(h, copy_d2h(py, pc.py, (size_t)total * 8, h->stream));
   return ABM_OK;
+}
+
+int ABM_API(set_transport)(abm_handle* h, const abm_transport* t) {
+  if (!h || !t || !t->sendrecv || !t->allreduce_sum_u64 || !t->allgather_u32) return ABM_E_BADARG;
+  h->tr = *t;
+  h->has_tr = true;
+  return ABM_OK;
+}
+
+int ABM_API(nccl_unique_id)(void* out128) {
+#ifndef ABM_EMU
+  if (!out128) return ABM_E_BADARG;
+  if (!g_nccl.load()) { g_create_error = "libnccl.so.2 could not be loaded"; return ABM_E_CUDA; }
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return ABM_E_CUDA; }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(out128, &id, 128);
+  return ABM_OK;
+#else
+  (void)out128;
+  return ABM_E_STATE;
+#endif
+}
+
+int ABM_API(comm_init_nccl)(abm_handle* h, const void* unique_id128) {
+  if (!h || !unique_id128) return ABM_E_BADARG;
+#ifndef ABM_EMU
+  if (!h->strip || h->n_ranks < 2) ABM_FAIL(h, ABM_E_STATE, "abm_comm_init_nccl needs a strip handle with n_ranks > 1");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (!g_nccl.load()) ABM_FAIL(h, ABM_E_CUDA, "libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  memcpy(&id, unique_id128, 128);
+  ncclComm_t c;
+  ABM_NCCL(h, g_nccl.CommInitRank(&c, h->n_ranks, id, h->my_rank));
+  h->nccl_comm = (void*)c;
+  return ABM_OK;
+#else
+  ABM_FAIL(h, ABM_E_STATE, "NCCL is not part of the emulation build");
+#endif
 }
 
 int ABM_API(set_profiling)(abm_handle* h, int32_t on) {

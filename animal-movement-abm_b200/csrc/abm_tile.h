@@ -677,5 +677,60 @@ struct ScatterTileBody {
   }
 };
 
+/* ----------------------------------------------------------------------------------- row strips (multi-GPU) */
+
+/* One boundary sub-tile row of this strip, packed for a neighbour: cells normalised to tile row 0 (the receiver adds
+ * its ghost tile row), ids, energies, decision bytes; sub-tile i's agents start at prefix[i].  One thread per sub-tile. */
+struct PackRowBody {
+  SubIndex si; int32_t row; int32_t tiles_x;
+  const uint32_t* cell; const uint32_t* id; const double* energy; const uint8_t* state;
+  const uint32_t* prefix; /* exclusive scan of the row's counts */
+  uint32_t* p_cell; uint32_t* p_id; double* p_energy; uint8_t* p_state;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t sub = (uint32_t)row * (uint32_t)si.nsx + (uint32_t)i;
+    const uint32_t off = si.off[sub], cnt = si.cnt[sub];
+    uint32_t o = prefix[i];
+    for (uint32_t k = 0; k < cnt; ++k, ++o) {
+      const uint32_t c = cell[off + k];
+      const uint32_t tx = (c >> 10) % (uint32_t)tiles_x;
+      if (p_cell) { p_cell[o] = (tx << 10) | (c & 1023u); p_id[o] = id[off + k]; p_energy[o] = energy[off + k]; }
+      p_state[o] = state[off + k];
+    }
+  }
+};
+/* the received row becomes a ghost sub-tile row at the tail of the SoA */
+struct UnpackRowBody {
+  int32_t row, nsx; uint32_t tile_row_base; /* (ghost tile row * tiles_x) << 10 */
+  uint32_t base;                            /* first SoA slot of this ghost row */
+  const uint32_t* counts; const uint32_t* prefix;
+  const uint32_t* p_cell; const uint32_t* p_id; const double* p_energy; const uint8_t* p_state;
+  uint32_t* sub_off; uint32_t* sub_cnt;
+  uint32_t* cell; uint32_t* id; double* energy; uint8_t* state;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t sub = (uint32_t)row * (uint32_t)nsx + (uint32_t)i, cnt = counts[i], o = prefix[i];
+    sub_off[sub] = base + o; sub_cnt[sub] = cnt;
+    for (uint32_t k = 0; k < cnt; ++k) {
+      cell[base + o + k] = p_cell[o + k] + tile_row_base; id[base + o + k] = p_id[o + k];
+      energy[base + o + k] = p_energy[o + k]; state[base + o + k] = p_state[o + k];
+    }
+  }
+};
+/* decisions are unique and final: a ghost copy keeps what it already settled locally, the owner's decision wins otherwise */
+struct MergeStateBody {
+  const uint8_t* incoming; uint8_t* state; uint32_t base;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint8_t in = incoming[i];
+    if ((in & ST_DECIDED) || !(state[base + i] & ST_DECIDED)) state[base + i] = in;
+  }
+};
+struct ScatterIdsBody { /* offspring ids computed on the host from the global order of the parents' ids */
+  const uint32_t* pos; const uint32_t* ids; uint32_t* out_id;
+  ABM_HD void operator()(uint64_t i) const { out_id[pos[i]] = ids[i]; }
+};
+struct GatherCountsBody { /* the counts of one sub-tile row */
+  const uint32_t* sub_cnt; int32_t row, nsx; uint32_t* out;
+  ABM_HD void operator()(uint64_t i) const { out[i] = sub_cnt[(uint32_t)row * (uint32_t)nsx + (uint32_t)i]; }
+};
+
 }  // namespace abm
 #endif /* ABM_TILE_H_ */

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ABM_ABI_VERSION 1
+#define ABM_ABI_VERSION 2
 
 /* error codes */
 enum {
@@ -93,13 +93,20 @@ typedef struct abm_config {
   int32_t astar_metric;     /* ABM_ASTAR_DIRECT / ABM_ASTAR_MAX */
   int32_t astar_penalty;    /* 1: PenaltyMap(elevation, base metric) */
   int32_t device;           /* CUDA device ordinal of this handle */
-  int32_t reserved0;
+  int32_t reserved0;        /* 1: force the general stepping path (tests); 0: automatic */
   double prob_random_walk;  /* custom_agent_step!(...; prob_random_walk = 0.9), src/agent_actions.jl:32 */
   double delta_energy;      /* agent.Δenergy */
   double movement_cost;     /* agent.movement_cost */
   double reproduction_prob; /* agent.reproduction_prob */
   double attractor_x, attractor_y; /* model.attractor (griddims ./ 2, scripts/v0.2.jl:57); 2*a must be integral */
   uint64_t seed;            /* Philox key */
+  /* Row-strip decomposition (no reference counterpart: the reference is one process).  n_ranks <= 1: this handle holds the
+   * whole GridSpace.  n_ranks > 1 (or strip_ny > 0): `ny` is the GLOBAL height and this handle owns the rows
+   * strip_y0 .. strip_y0 + strip_ny - 1 (0-based, multiples of 32); rank r's ring neighbours are r-1 (previous rows) and
+   * r+1.  In strip mode every grid array passed to / returned by abm_set_grid / abm_get_grid has strip_ny + 64 rows: 32
+   * ghost rows of the neighbouring strips above and below (wrapped when periodic; only walkmap and elevation are read
+   * there), and agents are exchanged with global 1-based y. */
+  int32_t strip_y0, strip_ny, n_ranks, rank;
 } abm_config;
 
 typedef struct abm_handle abm_handle;
@@ -172,6 +179,26 @@ int abm_get_timing(abm_handle* h, double* out, int32_t n);
 int abm_set_profiling(abm_handle* h, int32_t on);
 int abm_get_kernel_stat(abm_handle* h, int32_t idx, char* name, int32_t name_cap, double* ms, int64_t* launches,
                         int64_t* units);
+
+/* ---- multi-GPU: one process per GPU, one handle per process; abm_step performs the per-tick halo exchange itself ---- */
+
+/* Transport supplied by the host (MPI, gloo, ...): all pointers are HOST memory, calls are collective over the ring of
+ * n_ranks handles and return 0 on success.  sendrecv: `to_prev` goes to rank-1 (who receives it as `from_next`), `to_next`
+ * to rank+1 (who receives it as `from_prev`); with n_ranks == 2 both neighbours are the same rank and the `to_prev`
+ * message must be matched first. */
+typedef struct abm_transport {
+  void* user;
+  int (*sendrecv)(void* user, const void* to_prev, uint64_t to_prev_bytes, const void* to_next, uint64_t to_next_bytes,
+                  void* from_prev, uint64_t from_prev_bytes, void* from_next, uint64_t from_next_bytes);
+  int (*allreduce_sum_u64)(void* user, uint64_t* values, int32_t n);
+  int (*allgather_u32)(void* user, const uint32_t* send, uint32_t* recv /* n_ranks * n */, uint32_t n);
+} abm_transport;
+int abm_set_transport(abm_handle* h, const abm_transport* t);
+
+/* NCCL transport over NVLink (device buffers, no host staging): rank 0 calls abm_nccl_unique_id, the host ships the 128
+ * bytes to every rank (e.g. torch.distributed.broadcast), every rank calls abm_comm_init_nccl. */
+int abm_nccl_unique_id(void* out128);
+int abm_comm_init_nccl(abm_handle* h, const void* unique_id128);
 
 /* message for the last failing call on h (or on creation when h == NULL); valid until the next call */
 const char* abm_last_error(abm_handle* h);

@@ -35,7 +35,7 @@ def test_binding_covers_every_declared_symbol():
 def test_config_struct_layout_matches_header():
     lib = capi.CLib(build.build_libabm(), "abm_")
     cfg = lib.default_config()
-    assert cfg.struct_size == C.sizeof(capi.AbmConfig) == 120
+    assert cfg.struct_size == C.sizeof(capi.AbmConfig) == 136
     assert (cfg.nx, cfg.ny, cfg.regrowth_time, cfg.seed) == (80, 80, 30, 321)  # scripts/v0.1.jl:36-46
 
 

@@ -1,0 +1,117 @@
+"""Row strips: the strip decomposition must reproduce the single-handle / oracle trajectory bit for bit.
+
+  * one strip that is its own ring neighbour (exercises pack / unpack / ghost rows / merge without processes);
+  * world_size-2 and -3 rings of processes over gloo (CPU, emulated engine, host-memory transport callbacks);
+  * on the GPU box: 2 strips with the NCCL transport (needs 2 GPUs; skipped otherwise).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_same_state, build, capi, load_case, make_case
+from abm_b200 import strips
+
+CASES = {
+    "rw": dict(nx=64, ny=128, n=3000, wt=0, per=1, kw=dict(reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0)),
+    "rw_clamped": dict(nx=96, ny=96, n=3000, wt=0, per=0, kw=dict(reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0)),
+    "attractor": dict(nx=64, ny=192, n=3000, wt=1, per=0, kw=dict(reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0, prob_random_walk=0.5)),
+    "gregarious": dict(nx=64, ny=128, n=2500, wt=2, per=1, kw=dict(visual_distance=3, reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0)),
+    "gregarious_r7": dict(nx=64, ny=96, n=900, wt=2, per=1, kw=dict(visual_distance=7, prob_random_walk=0.2, reproduction_prob=0.05, regrowth_time=2, delta_energy=3.0)),
+    "walkmap": dict(nx=96, ny=128, n=3000, wt=4, per=1, terrain=True, kw=dict(walkmap_regrowth=1, reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0)),
+}
+
+
+def _case(name):
+    c = CASES[name]
+    return make_case(c["nx"], c["ny"], c["n"], c["wt"], c["per"], terrain=c.get("terrain", False), seed=31, **c["kw"])
+
+
+@pytest.mark.parametrize("name", ["rw", "gregarious", "walkmap"])
+def test_single_strip_ring_of_one(emu, oracle, name):
+    cfgkw, w = _case(name)
+    a = load_case(oracle, cfgkw, w)
+    b = strips.load_strip(emu, cfgkw, w, 1, 0)
+    for t in range(10):
+        a.step(1)
+        b.step(1)
+        assert_same_state(strips.merge_snapshots([strips.strip_snapshot(b)]), a.snapshot(), f"{name} tick {t}")
+
+
+def _ring_worker(rank, world, name, ticks, port, out_dir, use_gpu):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from conftest import build as b2, capi as c2
+    if use_gpu:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        lib = c2.CLib(b2.LIBABM, "abm_")
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        lib = c2.CLib(b2.LIBEMU, "emu_")
+    cfgkw, w = _case(name)
+    if use_gpu:
+        cfgkw = dict(cfgkw, device=rank)
+    e = strips.load_strip(lib, cfgkw, w, world, rank)
+    if use_gpu:
+        strips.init_nccl(e)
+    else:
+        tr = strips.DistTransport()
+        e.set_transport(tr.struct)
+    snaps = []
+    for t in range(ticks):
+        e.step(1)
+        snaps.append(strips.strip_snapshot(e))
+    np.save(os.path.join(out_dir, f"snap_{rank}.npy"), np.array(snaps, dtype=object), allow_pickle=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_ring(world, name, ticks, tmp_path, use_gpu=False):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() + world * 7 + len(name)) % 400
+    mp.spawn(_ring_worker, args=(world, name, ticks, port, str(tmp_path), use_gpu), nprocs=world, join=True)
+    return [np.load(os.path.join(str(tmp_path), f"snap_{r}.npy"), allow_pickle=True) for r in range(world)]
+
+
+@pytest.mark.parametrize("world,name", [(2, "rw"), (2, "gregarious"), (2, "rw_clamped"), (3, "attractor"), (2, "walkmap"), (3, "gregarious_r7")])
+def test_ring_of_processes_over_gloo(oracle, tmp_path, world, name):
+    build.build_emu()
+    ticks = 8
+    per_rank = _run_ring(world, name, ticks, tmp_path)
+    cfgkw, w = _case(name)
+    a = load_case(oracle, cfgkw, w)
+    for t in range(ticks):
+        a.step(1)
+        assert_same_state(strips.merge_snapshots([per_rank[r][t] for r in range(world)]), a.snapshot(), f"{name} world {world} tick {t}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["rw", "gregarious"])
+def test_single_strip_on_the_gpu(libabm, oracle, name):
+    cfgkw, w = _case(name)
+    a = load_case(oracle, cfgkw, w)
+    b = strips.load_strip(libabm, cfgkw, w, 1, 0)
+    for t in range(10):
+        a.step(1)
+        b.step(1)
+        assert_same_state(strips.merge_snapshots([strips.strip_snapshot(b)]), a.snapshot(), f"{name} tick {t}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["rw", "gregarious", "walkmap"])
+def test_two_strips_over_nccl(libabm, oracle, tmp_path, name):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ticks = 8
+    per_rank = _run_ring(2, name, ticks, tmp_path, use_gpu=True)
+    cfgkw, w = _case(name)
+    a = load_case(oracle, cfgkw, w)
+    for t in range(ticks):
+        a.step(1)
+        assert_same_state(strips.merge_snapshots([per_rank[r][t] for r in range(2)]), a.snapshot(), f"{name} tick {t}")
