@@ -4,7 +4,8 @@
 Workload (BASELINE.json configs[1], "C2"): v0.3 rules — RANDOM_WALK_GREGARIOUS, visual_distance = 3,
 prob_random_walk = 0.9, eat + reproduce + grass regrowth — on a periodic 4096 x 4096 GridSpace with 2^22 sheep,
 synthetic seeded world (abm_b200.worlds).  A "step" is one tick: every agent's agent_step! in id order, then
-model_step!.  At N > 1 every rank steps its own world of that size (weak scaling, no data-path collective yet).
+model_step!.  At N > 1 the GridSpace is 4096 x (4096 N) with 2^22 N sheep, cut into N row strips (one per GPU, weak
+scaling); abm_step exchanges the boundary sub-tile rows with the ring neighbours over NCCL every tick.
 
   value      agent-updates/s with the world resident in HBM; per-tick CUDA-event time on the library's stream,
              L2 flushed (256 MiB write) between ticks, max over ranks.
@@ -198,7 +199,20 @@ def main():
     size, agents = args.size, args.size * args.size // 4
     wl = WORKLOADS[args.workload]
     cfg, w = make_world(args.workload, size, agents, seed=321 + rank)
-    eng = load(lib, cfg, w, device=local)
+    if world > 1:
+        # strip `rank` of a size x (size * world) GridSpace: this rank's rows and sheep (global ids and y), ghost rows for the grids
+        from abm_b200 import strips
+        if wl["terrain"]:
+            raise SystemExit("the multi-GPU bench runs the C2 workload (terrain would have to be generated globally)")
+        cfg.update(ny=size * world, strip_y0=size * rank, strip_ny=size, n_ranks=world, rank=rank, seed=321, device=local)
+        eng = lib.create(lib.default_config(**cfg))
+        pad = lambda a: np.concatenate([np.zeros((strips.GHOST, size), a.dtype), a, np.zeros((strips.GHOST, size), a.dtype)], 0)
+        eng.ny = size + 2 * strips.GHOST
+        eng.set_grid(pad(w["fully_grown"]), pad(w["countdown"]))
+        eng.set_agents(w["ids"] + rank * agents, w["x"], w["y"] + size * rank, w["energy"], agents * world + 1)
+        strips.init_nccl(eng)
+    else:
+        eng = load(lib, cfg, w, device=local)
     eng.set_profiling(True)
     G = size * size
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -248,6 +262,7 @@ def main():
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t.numpy(), t
     keep = []
+    Gl = G if world == 1 else eng.ny * size  # grid arrays of a strip carry 2 x 32 ghost rows
     ids, x, y, en = eng.get_agents()
     fg, cd = eng.get_grid()
     host = {}
@@ -265,13 +280,13 @@ def main():
         n = host["ids"].size
         eng.set_grid(host["fg"], host["cd"], wm, el)
         eng.set_agents(host["ids"], host["x"], host["y"], host["energy"], st["next_id"])
-        h2d += G * 9 + (G * 9 if wm is not None else 0) + n * 32
+        h2d += Gl * 9 + (Gl * 9 if wm is not None else 0) + n * 32
         eng.step(1)
         e2e_upd += n
         ids, x, y, en = eng.get_agents()
         fg, cd = eng.get_grid()
         st = eng.get_global_state()
-        d2h += ids.size * 32 + G * 9
+        d2h += ids.size * 32 + Gl * 9
         for k, a in (("ids", ids), ("x", x), ("y", y), ("energy", en), ("fg", fg), ("cd", cd)):
             host[k], t = pinned(a) if a.size != host[k].size else (host[k], None)
             if t is None:
@@ -316,7 +331,7 @@ def main():
             "dtype": "int32 cells / f64 energy", "data": "synthetic",
             "config": {"workload": wl["desc"].format(n=size, a=agents), "grid": [size, size], "agents": agents, "ticks": args.steps,
                        "l2": "flushed between ticks (256 MiB device write)" if flush is not None else "not flushed",
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent worlds, one per rank (no exchange)",
+                       "parallelism": "single GPU" if world == 1 else f"{world} row strips of a {size}x{size * world} grid, one per GPU, NCCL halo exchange inside abm_step",
                        "cells_per_s": G * world * args.steps / (ms_max * 1e-3), "resolution_rounds_per_tick": rounds / args.steps},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "agent-updates/s", "h2d_bytes_per_step": h2d // args.e2e_steps, "d2h_bytes_per_step": d2h // args.e2e_steps,
