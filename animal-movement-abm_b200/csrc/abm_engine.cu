@@ -233,7 +233,7 @@ struct ProfScope {
   ~ProfScope() { p.end(s); }
 };
 
-enum { CTR_PEND_A = 0, CTR_PEND_B = 1, CTR_BIRTHS = 2, CTR_ERR = 3, CTR_RED_LO = 4, CTR_RED_HI = 5, CTR_PLANS = 6, CTR_ROUTE_SLOTS = 7,
+enum { CTR_BIRTH_TOTAL = 12, CTR_PEND_A = 0, CTR_PEND_B = 1, CTR_BIRTHS = 2, CTR_ERR = 3, CTR_RED_LO = 4, CTR_RED_HI = 5, CTR_PLANS = 6, CTR_ROUTE_SLOTS = 7,
        CTR_EXP_LO = 8, CTR_EXP_HI = 9, CTR_CURSOR = 10, CTR_BIRTH_FLAGS = 11, CTR_WORDS = 16 };
 
 }  // namespace
@@ -269,8 +269,9 @@ struct abm_handle {
   abm_transport tr;
   bool has_tr = false;
   void* nccl_comm = nullptr;
-  DevBuf sx_cnt[2], sx_pre[2], rx_cnt[2], rx_pre[2], sx_buf[2], rx_buf[2], sx_st[2], rx_st[2], red_buf, birth_ids;
-  uint64_t n_send[2] = {0, 0}, n_recv[2] = {0, 0}, n_ghost = 0;
+  DevBuf sx_pre[2], rx_pre[2], sx_buf[2], rx_buf[2], sx_st[2], rx_st[2], red_buf, birth_ids;
+  uint64_t n_ghost = 0, bcap = 4096, next_bcap = 4096;
+  bool bcap_agreed = false; /* capacity (agents) of a boundary message, the same on every rank */
   std::vector<uint8_t> hstage[4];
   uint32_t* h_counters = nullptr; /* host mirror (pinned on CUDA) */
 
@@ -378,6 +379,7 @@ static int read_counters(abm_handle* h) {
 static int device_error_to_code(abm_handle* h) {
   const uint32_t e = h->h_counters[CTR_ERR];
   if (e & ERR_NOWALKABLE) ABM_FAIL(h, ABM_E_NOWALKABLE, "random_walkmap: an agent has no walkable neighbour (the reference throws on rand(1:0))");
+  if (e & ERR_STRIP_CAP) ABM_FAIL(h, ABM_E_CAPACITY, "a boundary row outgrew the agreed halo message capacity (%llu agents) within one tick", (unsigned long long)h->bcap);
   if (e & ERR_INTERNAL) ABM_FAIL(h, ABM_E_BADARG, "device-side validation failed (out-of-range coordinate, id, countdown or elevation, or duplicate id)");
   return 0;
 }
@@ -866,137 +868,166 @@ static int comm_allgather_u32(abm_handle* h, const uint32_t* send, uint32_t* rec
   return 0;
 }
 
-/* E1: this strip's first and last sub-tile rows (cell, id, energy, proposal) become the neighbours' ghost rows */
+/* capacity of a boundary message, agreed by all ranks from the same all-reduced figures */
+static uint64_t strip_cap_for(uint64_t max_row) { return 2 * max_row + 4096; }
+
+static int strip_alloc(abm_handle* h) {
+  int rc;
+  const uint64_t bytes = strip_msg_bytes(h->nsx, h->bcap);
+  for (int d = 0; d < 2; ++d) {
+    if ((rc = ensure(h, h->sx_buf[d], bytes))) return rc;
+    if ((rc = ensure(h, h->rx_buf[d], bytes))) return rc;
+    if ((rc = ensure(h, h->sx_pre[d], ((size_t)h->nsx + 8) * 4))) return rc;
+    if ((rc = ensure(h, h->rx_pre[d], ((size_t)h->nsx + 8) * 4))) return rc;
+    if ((rc = ensure(h, h->sx_st[d], h->bcap + 64))) return rc;
+    if ((rc = ensure(h, h->rx_st[d], h->bcap + 64))) return rc;
+  }
+  return ensure(h, h->red_buf, 4096);
+}
+
+/* E1: this strip's first and last sub-tile rows (cell, id, energy, proposal) become the neighbours' ghost rows.
+ * One fixed-size message per neighbour, prefixes on the device: no host round trip. */
 static int strip_exchange_agents(abm_handle* h) {
   int rc;
   const int nsx = h->nsx, cur = h->cur;
   const int row_s[2] = {h->g.own_lo / SUB, h->g.own_hi / SUB - 1};       /* my rows sent to prev / next */
   const int row_g[2] = {h->g.own_lo / SUB - 1, h->g.own_hi / SUB};       /* ghost rows filled from prev / next */
   const uint32_t tile_row_g[2] = {(uint32_t)(h->g.own_lo / CORE - 1), (uint32_t)(h->g.own_hi / CORE)};
-  std::vector<uint32_t> cnt((size_t)nsx), pre((size_t)nsx + 1);
-  for (int d = 0; d < 2; ++d) {
-    if ((rc = ensure(h, h->sx_cnt[d], (size_t)nsx * 4))) return rc;
-    if ((rc = ensure(h, h->sx_pre[d], (size_t)nsx * 4 + 4))) return rc;
-    if ((rc = ensure(h, h->rx_cnt[d], (size_t)nsx * 4))) return rc;
-    if ((rc = ensure(h, h->rx_pre[d], (size_t)nsx * 4 + 4))) return rc;
-    GatherCountsBody gc;
-    gc.sub_cnt = (const uint32_t*)h->sub_cnt[cur].p; gc.row = row_s[d]; gc.nsx = nsx; gc.out = (uint32_t*)h->sx_cnt[d].p;
-    launch_foreach(h->stream, gc, (uint64_t)nsx);
-    ABM_CK(h, copy_d2h(cnt.data(), h->sx_cnt[d].p, (size_t)nsx * 4, h->stream));
-    uint32_t run = 0;
-    for (int i = 0; i < nsx; ++i) { pre[i] = run; run += cnt[i]; }
-    h->n_send[d] = run;
-    ABM_CK(h, copy_h2d(h->sx_pre[d].p, pre.data(), (size_t)nsx * 4, h->stream));
-    ABM_CK(h, dev_memset(h->rx_cnt[d].p, 0, (size_t)nsx * 4, h->stream));
-  }
-  if ((rc = comm_sendrecv(h, h->sx_cnt[0].p, (uint64_t)nsx * 4, h->sx_cnt[1].p, (uint64_t)nsx * 4, h->rx_cnt[0].p, (uint64_t)nsx * 4, h->rx_cnt[1].p, (uint64_t)nsx * 4))) return rc;
-  for (int d = 0; d < 2; ++d) {
-    ABM_CK(h, copy_d2h(cnt.data(), h->rx_cnt[d].p, (size_t)nsx * 4, h->stream));
-    uint32_t run = 0;
-    for (int i = 0; i < nsx; ++i) { pre[i] = run; run += cnt[i]; }
-    h->n_recv[d] = run;
-    ABM_CK(h, copy_h2d(h->rx_pre[d].p, pre.data(), (size_t)nsx * 4, h->stream));
-  }
-  h->n_ghost = h->n_recv[0] + h->n_recv[1];
-  /* payload: [energy n x 8][cell n x 4][id n x 4][state n] per direction */
-  for (int d = 0; d < 2; ++d) {
-    const uint64_t n = h->n_send[d];
-    if ((rc = ensure(h, h->sx_buf[d], n * 17 + 64))) return rc;
-    if ((rc = ensure(h, h->rx_buf[d], h->n_recv[d] * 17 + 64))) return rc;
-    uint8_t* b = (uint8_t*)h->sx_buf[d].p;
-    PackRowBody pk;
-    pk.si = sub_index(h, cur); pk.row = row_s[d]; pk.tiles_x = h->g.tiles_x;
-    pk.cell = (const uint32_t*)h->cell[cur].p; pk.id = (const uint32_t*)h->id[cur].p; pk.energy = (const double*)h->energy[cur].p; pk.state = (const uint8_t*)h->state.p;
-    pk.prefix = (const uint32_t*)h->sx_pre[d].p;
-    pk.p_energy = (double*)b; pk.p_cell = (uint32_t*)(b + n * 8); pk.p_id = (uint32_t*)(b + n * 12); pk.p_state = b + n * 16;
-    launch_foreach(h->stream, pk, (uint64_t)nsx);
-  }
-  if ((rc = check_launch(h, "strip pack"))) return rc;
-  if ((rc = comm_sendrecv(h, h->sx_buf[0].p, h->n_send[0] * 17, h->sx_buf[1].p, h->n_send[1] * 17, h->rx_buf[0].p, h->n_recv[0] * 17, h->rx_buf[1].p, h->n_recv[1] * 17))) return rc;
-  /* ghost agents go behind the own agents of the current SoA */
-  const uint64_t tot = h->n + h->n_ghost + 1;
+  const uint64_t cap = h->bcap, hdr = strip_hdr_bytes(nsx), bytes = strip_msg_bytes(nsx, cap);
+  if ((rc = strip_alloc(h))) return rc;
+  /* ghost agents live at fixed places behind the own agents: [n, n + cap) from prev, [n + cap, n + 2 cap) from next */
+  const uint64_t tot = h->n + 2 * cap + 1;
   if ((rc = grow_keep(h, h->cell[cur], tot * 4))) return rc;
   if ((rc = grow_keep(h, h->id[cur], tot * 4))) return rc;
   if ((rc = grow_keep(h, h->energy[cur], tot * 8))) return rc;
   if ((rc = grow_keep(h, h->state, tot))) return rc;
   if ((rc = ensure(h, h->pend[0], tot * 4))) return rc;
   if ((rc = ensure(h, h->pend[1], tot * 4))) return rc;
-  uint64_t base = h->n;
+  uint32_t* err = (uint32_t*)h->counters.p + CTR_ERR;
   for (int d = 0; d < 2; ++d) {
-    const uint64_t n = h->n_recv[d];
+    uint8_t* b = (uint8_t*)h->sx_buf[d].p;
+    GatherCountsBody gc;
+    gc.sub_cnt = (const uint32_t*)h->sub_cnt[cur].p; gc.row = row_s[d]; gc.nsx = nsx; gc.out = (uint32_t*)b;
+    launch_foreach(h->stream, gc, (uint64_t)nsx + 1);
+    ABM_CK(h, copy_d2d(h->sx_pre[d].p, b, ((size_t)nsx + 1) * 4, h->stream));
+    ABM_CK(h, scan_exclusive_u32(h->stream, (uint32_t*)h->sx_pre[d].p, (uint64_t)nsx + 1, (uint32_t*)h->scan_tmp.p));
+    PackRowBody pk;
+    pk.si = sub_index(h, cur); pk.row = row_s[d]; pk.tiles_x = h->g.tiles_x; pk.with_agents = 1; pk.cap = (uint32_t)cap;
+    pk.cell = (const uint32_t*)h->cell[cur].p; pk.id = (const uint32_t*)h->id[cur].p; pk.energy = (const double*)h->energy[cur].p; pk.state = (const uint8_t*)h->state.p;
+    pk.prefix = (const uint32_t*)h->sx_pre[d].p;
+    pk.p_energy = (double*)(b + hdr); pk.p_cell = (uint32_t*)(b + hdr + cap * 8); pk.p_id = (uint32_t*)(b + hdr + cap * 12); pk.p_state = b + hdr + cap * 16;
+    pk.err = err;
+    launch_foreach(h->stream, pk, (uint64_t)nsx);
+    ABM_CK(h, dev_memset(h->rx_buf[d].p, 0, hdr, h->stream)); /* a missing neighbour sends nothing: empty ghost row */
+  }
+  if ((rc = check_launch(h, "strip pack"))) return rc;
+  { ProfScope ps(h->prof, h->stream, "halo_exchange", 2 * cap);
+    if ((rc = comm_sendrecv(h, h->sx_buf[0].p, bytes, h->sx_buf[1].p, bytes, h->rx_buf[0].p, bytes, h->rx_buf[1].p, bytes))) return rc; }
+  for (int d = 0; d < 2; ++d) {
     const uint8_t* b = (const uint8_t*)h->rx_buf[d].p;
+    ABM_CK(h, copy_d2d(h->rx_pre[d].p, b, ((size_t)nsx + 1) * 4, h->stream));
+    ABM_CK(h, scan_exclusive_u32(h->stream, (uint32_t*)h->rx_pre[d].p, (uint64_t)nsx + 1, (uint32_t*)h->scan_tmp.p));
     UnpackRowBody up;
-    up.row = row_g[d]; up.nsx = nsx; up.tile_row_base = (tile_row_g[d] * (uint32_t)h->g.tiles_x) << 10; up.base = (uint32_t)base;
-    up.counts = (const uint32_t*)h->rx_cnt[d].p; up.prefix = (const uint32_t*)h->rx_pre[d].p;
-    up.p_energy = (const double*)b; up.p_cell = (const uint32_t*)(b + n * 8); up.p_id = (const uint32_t*)(b + n * 12); up.p_state = b + n * 16;
+    up.row = row_g[d]; up.nsx = nsx; up.tile_row_base = (tile_row_g[d] * (uint32_t)h->g.tiles_x) << 10;
+    up.base = (uint32_t)(h->n + (uint64_t)d * cap); up.cap = (uint32_t)cap;
+    up.counts = (const uint32_t*)b; up.prefix = (const uint32_t*)h->rx_pre[d].p;
+    up.p_energy = (const double*)(b + hdr); up.p_cell = (const uint32_t*)(b + hdr + cap * 8); up.p_id = (const uint32_t*)(b + hdr + cap * 12); up.p_state = b + hdr + cap * 16;
     up.sub_off = (uint32_t*)h->sub_off[cur].p; up.sub_cnt = (uint32_t*)h->sub_cnt[cur].p;
     up.cell = (uint32_t*)h->cell[cur].p; up.id = (uint32_t*)h->id[cur].p; up.energy = (double*)h->energy[cur].p; up.state = (uint8_t*)h->state.p;
+    up.err = err;
     launch_foreach(h->stream, up, (uint64_t)nsx);
-    base += n;
   }
+  h->n_ghost = 2 * cap; /* upper bound; the sub-tile index knows the real counts */
   return check_launch(h, "strip unpack");
 }
 
-/* E2: the decision bytes of the same boundary rows, merged into the ghost copies */
+/* E2: the decision bytes of the same boundary rows (same order), merged into the ghost copies */
 static int strip_exchange_states(abm_handle* h) {
   int rc;
-  const int cur = h->cur;
+  const int cur = h->cur, nsx = h->nsx;
   const int row_s[2] = {h->g.own_lo / SUB, h->g.own_hi / SUB - 1};
+  const uint64_t cap = h->bcap;
   for (int d = 0; d < 2; ++d) {
-    if ((rc = ensure(h, h->sx_st[d], h->n_send[d] + 64))) return rc;
-    if ((rc = ensure(h, h->rx_st[d], h->n_recv[d] + 64))) return rc;
     PackRowBody pk;
-    pk.si = sub_index(h, cur); pk.row = row_s[d]; pk.tiles_x = h->g.tiles_x;
-    pk.cell = (const uint32_t*)h->cell[cur].p; pk.id = nullptr; pk.energy = nullptr; pk.state = (const uint8_t*)h->state.p;
+    pk.si = sub_index(h, cur); pk.row = row_s[d]; pk.tiles_x = h->g.tiles_x; pk.with_agents = 0; pk.cap = (uint32_t)cap;
+    pk.cell = nullptr; pk.id = nullptr; pk.energy = nullptr; pk.state = (const uint8_t*)h->state.p;
     pk.prefix = (const uint32_t*)h->sx_pre[d].p;
     pk.p_energy = nullptr; pk.p_cell = nullptr; pk.p_id = nullptr; pk.p_state = (uint8_t*)h->sx_st[d].p;
-    launch_foreach(h->stream, pk, (uint64_t)h->nsx);
+    pk.err = (uint32_t*)h->counters.p + CTR_ERR;
+    launch_foreach(h->stream, pk, (uint64_t)nsx);
   }
-  if ((rc = comm_sendrecv(h, h->sx_st[0].p, h->n_send[0], h->sx_st[1].p, h->n_send[1], h->rx_st[0].p, h->n_recv[0], h->rx_st[1].p, h->n_recv[1]))) return rc;
-  uint64_t base = h->n;
+  { ProfScope ps(h->prof, h->stream, "decision_exchange", 2 * cap);
+    if ((rc = comm_sendrecv(h, h->sx_st[0].p, cap, h->sx_st[1].p, cap, h->rx_st[0].p, cap, h->rx_st[1].p, cap))) return rc; }
   for (int d = 0; d < 2; ++d) {
+    if ((d == 0 && !h->has_prev) || (d == 1 && !h->has_next)) continue;
     MergeStateBody mg;
-    mg.incoming = (const uint8_t*)h->rx_st[d].p; mg.state = (uint8_t*)h->state.p; mg.base = (uint32_t)base;
-    launch_foreach(h->stream, mg, h->n_recv[d]);
-    base += h->n_recv[d];
+    mg.incoming = (const uint8_t*)h->rx_st[d].p; mg.state = (uint8_t*)h->state.p; mg.base = (uint32_t)(h->n + (uint64_t)d * cap);
+    mg.total = (const uint32_t*)h->rx_pre[d].p + nsx;
+    launch_foreach(h->stream, mg, cap);
   }
   return check_launch(h, "strip state merge");
 }
 
-/* offspring ids across strips: global order of all parents' ids */
-static int strip_birth_ids(abm_handle* h, uint64_t nb, int nxt, uint64_t* total_out) {
+/* the figures of StripStatsBody from every rank: one all-reduce on device data, one read-back */
+static int strip_stats(abm_handle* h, const uint32_t* d_pending, std::vector<uint64_t>& out) {
   int rc;
-  std::vector<uint64_t> counts((size_t)h->n_ranks, 0);
-  counts[h->my_rank] = nb;
-  if ((rc = comm_allreduce_u64(h, counts.data(), h->n_ranks))) return rc;
-  uint64_t total = 0, nmax = 0;
-  for (int r = 0; r < h->n_ranks; ++r) { total += counts[r]; nmax = std::max(nmax, counts[r]); }
-  *total_out = total;
-  if (total == 0) return 0;
-  std::vector<uint32_t> mine((size_t)nmax, 0xFFFFFFFFu), pos((size_t)nb), all((size_t)nmax * h->n_ranks);
-  if (nb) {
-    ABM_CK(h, copy_d2h(mine.data(), h->birth_parent.p, nb * 4, h->stream));
-    ABM_CK(h, copy_d2h(pos.data(), h->birth_pos.p, nb * 4, h->stream));
+  const int P = h->n_ranks, nv = 1 + 3 * P;
+  uint32_t* ctr = (uint32_t*)h->counters.p;
+  unsigned long long* d = (unsigned long long*)h->red_buf.p;
+  StripStatsBody sb;
+  sb.pending = d_pending; sb.birth_flags = ctr + CTR_BIRTH_FLAGS;
+  sb.tot_up = (const uint32_t*)h->sx_pre[0].p + h->nsx; sb.tot_down = (const uint32_t*)h->sx_pre[1].p + h->nsx;
+  sb.n_ranks = P; sb.rank = h->my_rank; sb.out = d;
+  launch_foreach(h->stream, sb, 1);
+  out.assign((size_t)nv, 0);
+#ifndef ABM_EMU
+  if (h->nccl_comm) {
+    ABM_NCCL(h, g_nccl.AllReduce(d, d, (size_t)nv, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+    ABM_CK(h, copy_d2h(out.data(), d, (size_t)nv * 8, h->stream));
+    return 0;
   }
-  if ((rc = comm_allgather_u32(h, mine.data(), all.data(), (uint32_t)nmax))) return rc;
-  std::vector<uint32_t> sorted;
-  sorted.reserve((size_t)total);
-  for (int r = 0; r < h->n_ranks; ++r) for (uint64_t i = 0; i < counts[r]; ++i) sorted.push_back(all[(size_t)r * nmax + i]);
-  std::sort(sorted.begin(), sorted.end());
-  if (nb) {
-    std::vector<uint32_t> ids((size_t)nb);
-    for (uint64_t i = 0; i < nb; ++i) ids[i] = (uint32_t)(h->next_id + (uint64_t)(std::lower_bound(sorted.begin(), sorted.end(), mine[i]) - sorted.begin()));
-    if ((rc = ensure(h, h->birth_ids, nb * 8))) return rc;
-    uint32_t* d_ids = (uint32_t*)h->birth_ids.p;
-    uint32_t* d_pos = d_ids + nb;
-    ABM_CK(h, copy_h2d(d_ids, ids.data(), nb * 4, h->stream));
-    ABM_CK(h, copy_h2d(d_pos, pos.data(), nb * 4, h->stream));
-    ScatterIdsBody sc;
-    sc.pos = d_pos; sc.ids = d_ids; sc.out_id = (uint32_t*)h->id[nxt].p;
-    launch_foreach(h->stream, sc, nb);
-    if ((rc = check_launch(h, "birth ids"))) return rc;
-  }
+#endif
+  ABM_CK(h, copy_d2h(out.data(), d, (size_t)nv * 8, h->stream));
+  if ((rc = comm_allreduce_u64(h, out.data(), nv))) return rc;
   return 0;
+}
+
+/* offspring ids across strips: all-gather of [count, parent ids ...] and a rank kernel; returns the total through a
+ * device counter read with the commit counters */
+static int strip_birth_ids(abm_handle* h, uint64_t bbcap, int nxt, uint32_t* d_total) {
+  int rc;
+  const int P = h->n_ranks;
+  const uint64_t words = 1 + bbcap;
+  if ((rc = ensure(h, h->birth_ids, words * 4 * (size_t)(P + 1)))) return rc;
+  uint32_t* msg = (uint32_t*)h->birth_ids.p;
+  uint32_t* all = msg + words;
+  uint32_t* ctr = (uint32_t*)h->counters.p;
+  BirthPackBody bp;
+  bp.birth_parent = (const uint32_t*)h->birth_parent.p; bp.birth_count = ctr + CTR_BIRTHS; bp.cap = (uint32_t)bbcap; bp.msg = msg;
+  launch_foreach(h->stream, bp, bbcap ? bbcap : 1);
+  if (P == 1) {
+    ABM_CK(h, copy_d2d(all, msg, words * 4, h->stream));
+  } else {
+    bool done = false;
+#ifndef ABM_EMU
+    if (h->nccl_comm) {
+      ABM_NCCL(h, g_nccl.AllGather(msg, all, (size_t)words, ncclUint32, (ncclComm_t)h->nccl_comm, h->stream));
+      done = true;
+    }
+#endif
+    if (!done) {
+      std::vector<uint32_t> hs((size_t)words), hr((size_t)words * P);
+      ABM_CK(h, copy_d2h(hs.data(), msg, words * 4, h->stream));
+      if ((rc = comm_allgather_u32(h, hs.data(), hr.data(), (uint32_t)words))) return rc;
+      ABM_CK(h, copy_h2d(all, hr.data(), words * 4 * (size_t)P, h->stream));
+    }
+  }
+  BirthRankBody br;
+  br.all = all; br.n_ranks = P; br.cap = (uint32_t)bbcap; br.next_id = (uint32_t)h->next_id;
+  br.birth_pos = (const uint32_t*)h->birth_pos.p; br.birth_parent = (const uint32_t*)h->birth_parent.p; br.birth_count = ctr + CTR_BIRTHS;
+  br.out_id = (uint32_t*)h->id[nxt].p; br.total_out = d_total;
+  { ProfScope ps(h->prof, h->stream, "birth_ids", bbcap); launch_foreach(h->stream, br, bbcap ? bbcap : 1); }
+  return check_launch(h, "birth ids");
 }
 
 /* one tick on the tile path (abm_tile.h): propose -> window resolve -> per-agent windows for the rest -> commit */
@@ -1023,6 +1054,22 @@ static int tick_tile(abm_handle* h) {
     if ((rc = check_launch(h, "propose"))) return rc;
   }
   if (h->strip) { /* neighbours' boundary rows become ghost rows behind the own agents */
+    if (!h->bcap_agreed) { /* first tick after abm_set_agents: agree on the message capacity from the real row sizes */
+      if ((rc = strip_alloc(h))) return rc;
+      const int row_s[2] = {h->g.own_lo / SUB, h->g.own_hi / SUB - 1};
+      for (int d = 0; d < 2; ++d) {
+        GatherCountsBody gc;
+        gc.sub_cnt = (const uint32_t*)h->sub_cnt[h->cur].p; gc.row = row_s[d]; gc.nsx = h->nsx; gc.out = (uint32_t*)h->sx_pre[d].p;
+        launch_foreach(h->stream, gc, (uint64_t)h->nsx + 1);
+        ABM_CK(h, scan_exclusive_u32(h->stream, (uint32_t*)h->sx_pre[d].p, (uint64_t)h->nsx + 1, (uint32_t*)h->scan_tmp.p));
+      }
+      std::vector<uint64_t> st0;
+      if ((rc = strip_stats(h, ctr + CTR_PEND_A, st0))) return rc;
+      uint64_t rmax = 0;
+      for (int q = 0; q < h->n_ranks; ++q) rmax = std::max(rmax, st0[1 + 2 * h->n_ranks + q]);
+      h->bcap = h->next_bcap = strip_cap_for(rmax);
+      h->bcap_agreed = true;
+    }
     if ((rc = strip_exchange_agents(h))) return rc;
     v = make_view(h);
   }
@@ -1035,47 +1082,66 @@ static int tick_tile(abm_handle* h) {
       if ((rc = check_launch(h, "tile resolve"))) return rc;
     }
   }
-  if ((rc = read_counters(h))) return rc;
-  cnt = h->h_counters[CTR_PEND_A];
-  const uint64_t birth_flags = h->h_counters[CTR_BIRTH_FLAGS];
+  /* figures the host needs before it can go on: open agents, reproducing agents (sizes of the output SoA); in strip
+   * mode from every rank, through one all-reduce of device-resident counters */
+  uint64_t birth_flags = 0, birth_cap = 0, global_cnt = 0;
+  std::vector<uint64_t> stats;
+  const int P = h->n_ranks;
+  auto take_stats = [&](const uint32_t* d_pending) -> int {
+    if (!h->strip) {
+      int r = read_counters(h);
+      if (r) return r;
+      cnt = h->h_counters[d_pending - ctr];
+      global_cnt = cnt;
+      birth_flags = h->h_counters[CTR_BIRTH_FLAGS];
+      return 0;
+    }
+    int r = strip_stats(h, d_pending, stats);
+    if (r) return r;
+    global_cnt = stats[0];
+    cnt = stats[1 + h->my_rank];
+    birth_flags = stats[1 + P + h->my_rank];
+    uint64_t fmax = 0, rmax = 0;
+    for (int q = 0; q < P; ++q) { fmax = std::max(fmax, stats[1 + P + q]); rmax = std::max(rmax, stats[1 + 2 * P + q]); }
+    birth_cap = 3 * fmax + 64; /* a rank commits its own and its neighbours' arriving parents */
+    h->next_bcap = rmax * 2 > h->bcap ? strip_cap_for(rmax) : h->bcap; /* every rank sees the same figures */
+    return 0;
+  };
+  if ((rc = take_stats(ctr + CTR_PEND_A))) return rc;
   {
     int in = 0, stalls = 0;
     const int q = wt == ABM_RANDOM_WALK_GREGARIOUS ? h->cfg.visual_distance + 1 : 2;
-    uint64_t global_cnt = cnt;
     while (true) { /* chains that left their window: one small window per agent, Jacobi rounds */
-      if (h->strip) { /* the owners' decisions reach the ghost copies; every rank stays in the loop until all are done */
-        global_cnt = cnt;
-        if ((rc = comm_allreduce_u64(h, &global_cnt, 1))) return rc;
-        if (needs_resolve && (rc = strip_exchange_states(h))) return rc;
-      } else {
-        global_cnt = cnt;
-      }
+      /* strips: the owners' decisions reach the ghost copies; every rank stays in the loop until all ranks are done */
+      if (h->strip && needs_resolve && (rc = strip_exchange_states(h))) return rc;
       if (global_cnt == 0) break;
-      if (cnt == 0) { h->rounds += 1; continue; }
-      ABM_CK(h, dev_memset(ctr + (in ? CTR_PEND_A : CTR_PEND_B), 0, sizeof(uint32_t), h->stream));
-      ResolveWindow rw;
-      rw.v = v; rw.si = si; rw.mode = 1; rw.cores_x = 0; rw.core_y0 = 0; rw.max_rounds = 1; rw.nthreads = AGENT_THREADS;
-      rw.in = (const uint32_t*)h->pend[in].p; rw.out = (uint32_t*)h->pend[in ^ 1].p; rw.out_count = ctr + (in ? CTR_PEND_A : CTR_PEND_B);
-      { ProfScope ps(h->prof, h->stream, "resolve_agents", cnt); launch_cta(h->stream, rw, cnt, AGENT_THREADS, ResolveWindow::smem_bytes(2 * q + 1, 2 * q + 1)); }
-      if ((rc = check_launch(h, "agent resolve"))) return rc;
-      if ((rc = read_counters(h))) return rc;
-      const uint64_t left = h->h_counters[in ? CTR_PEND_A : CTR_PEND_B];
+      uint32_t* d_out = ctr + (in ? CTR_PEND_A : CTR_PEND_B);
+      ABM_CK(h, dev_memset(d_out, 0, sizeof(uint32_t), h->stream));
+      if (cnt > 0) {
+        ResolveWindow rw;
+        rw.v = v; rw.si = si; rw.mode = 1; rw.cores_x = 0; rw.core_y0 = 0; rw.max_rounds = 1; rw.nthreads = AGENT_THREADS;
+        rw.in = (const uint32_t*)h->pend[in].p; rw.out = (uint32_t*)h->pend[in ^ 1].p; rw.out_count = d_out;
+        { ProfScope ps(h->prof, h->stream, "resolve_agents", cnt); launch_cta(h->stream, rw, cnt, AGENT_THREADS, ResolveWindow::smem_bytes(2 * q + 1, 2 * q + 1)); }
+        if ((rc = check_launch(h, "agent resolve"))) return rc;
+      }
+      const uint64_t before = global_cnt;
+      if ((rc = take_stats(d_out))) return rc;
       h->rounds += 1;
-      stalls = left == cnt ? stalls + 1 : 0;
-      if (stalls > 64) ABM_FAIL(h, ABM_E_INTERNAL, "conflict resolution made no progress with %llu agents pending", (unsigned long long)left);
-      cnt = left;
+      stalls = global_cnt == before ? stalls + 1 : 0;
+      if (stalls > 64) ABM_FAIL(h, ABM_E_INTERNAL, "conflict resolution made no progress with %llu agents pending", (unsigned long long)global_cnt);
       in ^= 1;
     }
   }
   /* commit + grass + re-grouping */
   const int nxt = h->cur ^ 1;
-  if ((rc = ensure_soa(h, nxt, n + birth_flags))) return rc;
-  if ((rc = ensure(h, h->birth_pos, (birth_flags + 1) * 4))) return rc;
-  if ((rc = ensure(h, h->birth_parent, (birth_flags + 1) * 4))) return rc;
+  const uint64_t arrivals_cap = h->strip ? 2 * h->bcap : 0; /* ghost agents (and their offspring) may land here */
+  if ((rc = ensure_soa(h, nxt, n + birth_flags + 2 * arrivals_cap))) return rc;
+  if ((rc = ensure(h, h->birth_pos, (birth_flags + arrivals_cap + 1) * 4))) return rc;
+  if ((rc = ensure(h, h->birth_parent, (birth_flags + arrivals_cap + 1) * 4))) return rc;
   const uint64_t words = bitmap_words(h->next_id);
-  if (birth_flags > 0) {
+  if (birth_flags > 0 || h->strip) {
     if ((rc = ensure(h, h->bits, (words + 4) * 4))) return rc;
-    ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, h->stream));
+    if (!h->strip) ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, h->stream));
   }
   {
     CommitTile ct;
@@ -1084,18 +1150,19 @@ static int tick_tile(abm_handle* h) {
     ct.new_off = (uint32_t*)h->sub_off[nxt].p; ct.new_cnt = (uint32_t*)h->sub_cnt[nxt].p;
     ct.cursor = ctr + CTR_CURSOR;
     ct.birth_pos = (uint32_t*)h->birth_pos.p; ct.birth_parent = (uint32_t*)h->birth_parent.p; ct.birth_count = ctr + CTR_BIRTHS;
-    ct.birth_bits = (uint32_t*)h->bits.p;
+    ct.birth_bits = h->strip ? nullptr : (uint32_t*)h->bits.p; /* strips rank the parents globally instead */
     { ProfScope ps(h->prof, h->stream, "commit_tiles", n); launch_cta(h->stream, ct, cores, TILE_THREADS, CommitTile::smem_bytes()); }
     if ((rc = check_launch(h, "tile commit"))) return rc;
   }
+  if (h->strip && (rc = strip_birth_ids(h, birth_cap, nxt, ctr + CTR_BIRTH_TOTAL))) return rc;
   if ((rc = read_counters(h))) return rc;
   if ((rc = device_error_to_code(h))) return rc;
   const uint64_t n_new = h->h_counters[CTR_CURSOR], nb = h->h_counters[CTR_BIRTHS];
-  if (h->next_id + nb > 0xFFFFFFFFull) ABM_FAIL(h, ABM_E_CAPACITY, "agent id space (2^32-1) exhausted");
   uint64_t nb_total = nb;
   if (h->strip) {
-    if ((rc = strip_birth_ids(h, nb, nxt, &nb_total))) return rc;
-    if (h->next_id + nb_total > 0xFFFFFFFFull) ABM_FAIL(h, ABM_E_CAPACITY, "agent id space (2^32-1) exhausted");
+    nb_total = h->h_counters[CTR_BIRTH_TOTAL];
+    if (nb > birth_cap) ABM_FAIL(h, ABM_E_INTERNAL, "more offspring (%llu) than the agreed message capacity", (unsigned long long)nb);
+    h->bcap = h->next_bcap;
   } else if (nb > 0) {
     if ((rc = rank_prefix(h, words))) return rc;
     BirthIdBody bi;
@@ -1105,6 +1172,7 @@ static int tick_tile(abm_handle* h) {
     { ProfScope ps(h->prof, h->stream, "birth_ids", nb); launch_foreach(h->stream, bi, nb); }
     if ((rc = check_launch(h, "birth ids"))) return rc;
   }
+  if (h->next_id + nb_total > 0xFFFFFFFFull) ABM_FAIL(h, ABM_E_CAPACITY, "agent id space (2^32-1) exhausted");
   h->cur = nxt;
   h->n = n_new;
   h->next_id += nb_total;
@@ -1467,6 +1535,7 @@ int ABM_API(set_agents)(abm_handle* h, int64_t n, const int64_t* id, const int64
   h->n = (uint64_t)n;
   h->next_id = (uint64_t)next_id;
   h->agents_set = true;
+  h->bcap_agreed = false;
   /* a fresh population has no routes (pathfinder.agent_paths is empty) */
   if (h->rt_slot_of_id.p) ABM_CK(h, dev_memset(h->rt_slot_of_id.p, 0, h->rt_slot_of_id.bytes, h->stream));
   ABM_CK(h, dev_memset((uint32_t*)h->counters.p + CTR_ROUTE_SLOTS, 0, 4, h->stream));

@@ -621,7 +621,7 @@ struct CommitTile {
           out_cell[pos] = fc; out_id[pos] = 0u; out_energy[pos] = e;
           const uint32_t b = atomic_add(birth_count, 1u);
           birth_pos[b] = pos; birth_parent[b] = id;
-          atomic_or(&birth_bits[id >> 5], 1u << (id & 31));
+          if (birth_bits) atomic_or(&birth_bits[id >> 5], 1u << (id & 31));
         }
       }
     }
@@ -679,35 +679,52 @@ struct ScatterTileBody {
 
 /* ----------------------------------------------------------------------------------- row strips (multi-GPU) */
 
-/* One boundary sub-tile row of this strip, packed for a neighbour: cells normalised to tile row 0 (the receiver adds
- * its ghost tile row), ids, energies, decision bytes; sub-tile i's agents start at prefix[i].  One thread per sub-tile. */
+/* Boundary messages have a fixed capacity `cap` (agents), agreed by all ranks, so that one exchange per tick suffices:
+ * [header: nsx + 1 counts (the last is unused) padded to 16 bytes][energy cap x 8][cell cap x 4][id cap x 4][state cap].
+ * prefix = exclusive scan of the header counts (nsx + 1 entries, the last = total), computed on the device. */
+static inline uint64_t strip_hdr_bytes(int nsx) { return (((uint64_t)nsx + 1) * 4 + 15) & ~(uint64_t)15; }
+static inline uint64_t strip_msg_bytes(int nsx, uint64_t cap) { return strip_hdr_bytes(nsx) + cap * 17; }
+
+struct GatherCountsBody { /* the counts of one sub-tile row -> message header */
+  const uint32_t* sub_cnt; int32_t row, nsx; uint32_t* out;
+  ABM_HD void operator()(uint64_t i) const { out[i] = i < (uint64_t)nsx ? sub_cnt[(uint32_t)row * (uint32_t)nsx + (uint32_t)i] : 0u; }
+};
+
+/* one boundary sub-tile row packed for a neighbour: cells normalised to tile row 0 (the receiver adds its ghost tile
+ * row).  with_agents = 0 packs the decision bytes only (same order).  One thread per sub-tile. */
 struct PackRowBody {
-  SubIndex si; int32_t row; int32_t tiles_x;
+  SubIndex si; int32_t row, tiles_x, with_agents; uint32_t cap;
   const uint32_t* cell; const uint32_t* id; const double* energy; const uint8_t* state;
-  const uint32_t* prefix; /* exclusive scan of the row's counts */
+  const uint32_t* prefix;
   uint32_t* p_cell; uint32_t* p_id; double* p_energy; uint8_t* p_state;
+  uint32_t* err;
   ABM_HD void operator()(uint64_t i) const {
     const uint32_t sub = (uint32_t)row * (uint32_t)si.nsx + (uint32_t)i;
     const uint32_t off = si.off[sub], cnt = si.cnt[sub];
     uint32_t o = prefix[i];
+    if (o + cnt > cap) { atomic_or(err, ERR_STRIP_CAP); return; }
     for (uint32_t k = 0; k < cnt; ++k, ++o) {
-      const uint32_t c = cell[off + k];
-      const uint32_t tx = (c >> 10) % (uint32_t)tiles_x;
-      if (p_cell) { p_cell[o] = (tx << 10) | (c & 1023u); p_id[o] = id[off + k]; p_energy[o] = energy[off + k]; }
+      if (with_agents) {
+        const uint32_t c = cell[off + k];
+        const uint32_t tx = (c >> 10) % (uint32_t)tiles_x;
+        p_cell[o] = (tx << 10) | (c & 1023u); p_id[o] = id[off + k]; p_energy[o] = energy[off + k];
+      }
       p_state[o] = state[off + k];
     }
   }
 };
-/* the received row becomes a ghost sub-tile row at the tail of the SoA */
+/* the received row becomes a ghost sub-tile row at a fixed place behind the own agents */
 struct UnpackRowBody {
   int32_t row, nsx; uint32_t tile_row_base; /* (ghost tile row * tiles_x) << 10 */
-  uint32_t base;                            /* first SoA slot of this ghost row */
+  uint32_t base, cap;
   const uint32_t* counts; const uint32_t* prefix;
   const uint32_t* p_cell; const uint32_t* p_id; const double* p_energy; const uint8_t* p_state;
   uint32_t* sub_off; uint32_t* sub_cnt;
   uint32_t* cell; uint32_t* id; double* energy; uint8_t* state;
+  uint32_t* err;
   ABM_HD void operator()(uint64_t i) const {
     const uint32_t sub = (uint32_t)row * (uint32_t)nsx + (uint32_t)i, cnt = counts[i], o = prefix[i];
+    if (o + cnt > cap) { atomic_or(err, ERR_STRIP_CAP); sub_off[sub] = base; sub_cnt[sub] = 0; return; }
     sub_off[sub] = base + o; sub_cnt[sub] = cnt;
     for (uint32_t k = 0; k < cnt; ++k) {
       cell[base + o + k] = p_cell[o + k] + tile_row_base; id[base + o + k] = p_id[o + k];
@@ -717,19 +734,53 @@ struct UnpackRowBody {
 };
 /* decisions are unique and final: a ghost copy keeps what it already settled locally, the owner's decision wins otherwise */
 struct MergeStateBody {
-  const uint8_t* incoming; uint8_t* state; uint32_t base;
+  const uint8_t* incoming; uint8_t* state; uint32_t base; const uint32_t* total; /* device-side number of ghost agents */
   ABM_HD void operator()(uint64_t i) const {
+    if (i >= *total) return;
     const uint8_t in = incoming[i];
     if ((in & ST_DECIDED) || !(state[base + i] & ST_DECIDED)) state[base + i] = in;
   }
 };
-struct ScatterIdsBody { /* offspring ids computed on the host from the global order of the parents' ids */
-  const uint32_t* pos; const uint32_t* ids; uint32_t* out_id;
-  ABM_HD void operator()(uint64_t i) const { out_id[pos[i]] = ids[i]; }
+/* per-tick figures every rank needs from every rank, summed by one all-reduce (one-hot slots):
+ * [0] open agents (all ranks), [1 + r] open agents of rank r, [1 + P + r] reproducing agents, [1 + 2P + r] largest boundary row */
+struct StripStatsBody {
+  const uint32_t* pending; const uint32_t* birth_flags; const uint32_t* tot_up; const uint32_t* tot_down;
+  int32_t n_ranks, rank; unsigned long long* out;
+  ABM_HD void operator()(uint64_t) const {
+    const int P = n_ranks;
+    for (int q = 0; q < 1 + 3 * P; ++q) out[q] = 0;
+    out[0] = *pending; out[1 + rank] = *pending; out[1 + P + rank] = *birth_flags;
+    const uint32_t a = *tot_up, b = *tot_down;
+    out[1 + 2 * P + rank] = a > b ? a : b;
+  }
 };
-struct GatherCountsBody { /* the counts of one sub-tile row */
-  const uint32_t* sub_cnt; int32_t row, nsx; uint32_t* out;
-  ABM_HD void operator()(uint64_t i) const { out[i] = sub_cnt[(uint32_t)row * (uint32_t)nsx + (uint32_t)i]; }
+/* offspring ids across strips: every rank contributes [count, parent ids ...]; an offspring's id
+ * is next_id + the number of reproducing parents (anywhere) with a lower id.  One thread per local birth. */
+struct BirthPackBody {
+  const uint32_t* birth_parent; const uint32_t* birth_count; uint32_t cap; uint32_t* msg;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t n = *birth_count;
+    if (i == 0) msg[0] = n;
+    if (i < n && i < cap) msg[1 + i] = birth_parent[i];
+  }
+};
+struct BirthRankBody {
+  const uint32_t* all; /* n_ranks x (1 + cap) */
+  int32_t n_ranks; uint32_t cap; uint32_t next_id;
+  const uint32_t* birth_pos; const uint32_t* birth_parent; const uint32_t* birth_count;
+  uint32_t* out_id; uint32_t* total_out;
+  ABM_HD void operator()(uint64_t i) const {
+    if (i == 0) { uint32_t t = 0; for (int r = 0; r < n_ranks; ++r) t += all[(size_t)r * (1 + cap)]; *total_out = t; }
+    if (i >= *birth_count) return;
+    const uint32_t mine = birth_parent[i];
+    uint32_t rank = 0;
+    for (int r = 0; r < n_ranks; ++r) {
+      const uint32_t* p = all + (size_t)r * (1 + cap);
+      const uint32_t n = p[0] < cap ? p[0] : cap;
+      for (uint32_t k = 0; k < n; ++k) rank += p[1 + k] < mine ? 1u : 0u;
+    }
+    out_id[birth_pos[i]] = next_id + rank;
+  }
 };
 
 }  // namespace abm
