@@ -998,7 +998,7 @@ static int strip_birth_ids(abm_handle* h, uint64_t bbcap, int nxt, uint32_t* d_t
   int rc;
   const int P = h->n_ranks;
   const uint64_t words = 1 + bbcap;
-  if ((rc = ensure(h, h->birth_ids, words * 4 * (size_t)(P + 1)))) return rc;
+  if ((rc = ensure(h, h->birth_ids, words * 4 * (size_t)(P + 2) + 64))) return rc;
   uint32_t* msg = (uint32_t*)h->birth_ids.p;
   uint32_t* all = msg + words;
   uint32_t* ctr = (uint32_t*)h->counters.p;
@@ -1022,11 +1022,18 @@ static int strip_birth_ids(abm_handle* h, uint64_t bbcap, int nxt, uint32_t* d_t
       ABM_CK(h, copy_h2d(all, hr.data(), words * 4 * (size_t)P, h->stream));
     }
   }
+  uint32_t* ranks = all + words * (size_t)P; /* zeroed scratch, one counter per local birth */
+  ABM_CK(h, dev_memset(ranks, 0, (bbcap + 1) * 4, h->stream));
   BirthRankBody br;
-  br.all = all; br.n_ranks = P; br.cap = (uint32_t)bbcap; br.next_id = (uint32_t)h->next_id;
-  br.birth_pos = (const uint32_t*)h->birth_pos.p; br.birth_parent = (const uint32_t*)h->birth_parent.p; br.birth_count = ctr + CTR_BIRTHS;
-  br.out_id = (uint32_t*)h->id[nxt].p; br.total_out = d_total;
-  { ProfScope ps(h->prof, h->stream, "birth_ids", bbcap); launch_foreach(h->stream, br, bbcap ? bbcap : 1); }
+  br.all = all; br.n_ranks = P; br.cap = (uint32_t)bbcap;
+  br.birth_parent = (const uint32_t*)h->birth_parent.p; br.birth_count = ctr + CTR_BIRTHS; br.rank_out = ranks;
+  BirthAssignBody ba;
+  ba.all = all; ba.n_ranks = P; ba.cap = (uint32_t)bbcap; ba.next_id = (uint32_t)h->next_id;
+  ba.birth_pos = (const uint32_t*)h->birth_pos.p; ba.birth_count = ctr + CTR_BIRTHS; ba.rank_in = ranks;
+  ba.out_id = (uint32_t*)h->id[nxt].p; ba.total_out = d_total;
+  { ProfScope ps(h->prof, h->stream, "birth_ids", bbcap, 2);
+    launch_foreach(h->stream, br, (bbcap ? bbcap : 1) * 32);
+    launch_foreach(h->stream, ba, bbcap ? bbcap : 1); }
   return check_launch(h, "birth ids");
 }
 

@@ -764,22 +764,33 @@ struct BirthPackBody {
     if (i < n && i < cap) msg[1 + i] = birth_parent[i];
   }
 };
+/* 32 work items per local birth: item (i, lane) counts the lower parent ids among every 32nd gathered id */
 struct BirthRankBody {
   const uint32_t* all; /* n_ranks x (1 + cap) */
-  int32_t n_ranks; uint32_t cap; uint32_t next_id;
-  const uint32_t* birth_pos; const uint32_t* birth_parent; const uint32_t* birth_count;
+  int32_t n_ranks; uint32_t cap;
+  const uint32_t* birth_parent; const uint32_t* birth_count;
+  uint32_t* rank_out; /* zeroed, one per local birth */
+  ABM_HD void operator()(uint64_t w) const {
+    const uint32_t i = (uint32_t)(w >> 5), lane = (uint32_t)(w & 31);
+    if (i >= *birth_count) return;
+    const uint32_t mine = birth_parent[i];
+    uint32_t below = 0;
+    for (int r = 0; r < n_ranks; ++r) {
+      const uint32_t* p = all + (size_t)r * (1 + cap);
+      const uint32_t n = p[0] < cap ? p[0] : cap;
+      for (uint32_t k = lane; k < n; k += 32) below += p[1 + k] < mine ? 1u : 0u;
+    }
+    if (below) atomic_add(&rank_out[i], below);
+  }
+};
+struct BirthAssignBody {
+  const uint32_t* all; int32_t n_ranks; uint32_t cap; uint32_t next_id;
+  const uint32_t* birth_pos; const uint32_t* birth_count; const uint32_t* rank_in;
   uint32_t* out_id; uint32_t* total_out;
   ABM_HD void operator()(uint64_t i) const {
     if (i == 0) { uint32_t t = 0; for (int r = 0; r < n_ranks; ++r) t += all[(size_t)r * (1 + cap)]; *total_out = t; }
     if (i >= *birth_count) return;
-    const uint32_t mine = birth_parent[i];
-    uint32_t rank = 0;
-    for (int r = 0; r < n_ranks; ++r) {
-      const uint32_t* p = all + (size_t)r * (1 + cap);
-      const uint32_t n = p[0] < cap ? p[0] : cap;
-      for (uint32_t k = 0; k < n; ++k) rank += p[1 + k] < mine ? 1u : 0u;
-    }
-    out_id[birth_pos[i]] = next_id + rank;
+    out_id[birth_pos[i]] = next_id + rank_in[i];
   }
 };
 
