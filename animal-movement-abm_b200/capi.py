@@ -207,16 +207,25 @@ class Engine:
         self._ck(self.lib.fn["count_agents"](self.h, C.byref(n)))
         return n.value
 
-    def get_agents(self):
+    def get_agents(self, out=None):
+        """ids, x, y, energy in id order.  `out`: optional (ids, x, y, energy) buffers (e.g. pinned) of sufficient length."""
         n = self.count_agents()
-        cap = C.c_int64(n)
-        ids = np.empty(n, np.int64); x = np.empty(n, np.int64); y = np.empty(n, np.int64); e = np.empty(n, np.float64)
+        if out is None:
+            ids = np.empty(n, np.int64); x = np.empty(n, np.int64); y = np.empty(n, np.int64); e = np.empty(n, np.float64)
+        else:
+            ids, x, y, e = out
+            if min(ids.size, x.size, y.size, e.size) < n:
+                raise AbmError(ABM_E_SMALL, f"agent buffers hold fewer than {n} entries")
+        cap = C.c_int64(ids.size)
         self._ck(self.lib.fn["get_agents"](self.h, C.byref(cap), _ptr(ids, _I64P), _ptr(x, _I64P), _ptr(y, _I64P), _ptr(e, _F64P)))
-        return ids, x, y, e
+        return ids[:n], x[:n], y[:n], e[:n]
 
-    def get_grid(self):
-        fg = np.empty((self.ny, self.nx), np.uint8)
-        cd = np.empty((self.ny, self.nx), np.int64)
+    def get_grid(self, out=None):
+        if out is None:
+            fg = np.empty((self.ny, self.nx), np.uint8)
+            cd = np.empty((self.ny, self.nx), np.int64)
+        else:
+            fg, cd = out
         self._ck(self.lib.fn["get_grid"](self.h, _ptr(fg, _U8P), _ptr(cd, _I64P)))
         return fg, cd
 

@@ -263,8 +263,9 @@ struct ResolveWindow {
 
     ABM_CTA_FOR(t, NT) {
       rt.load(t, NT, nruns, w, v.g, si);
-      for (int c = t; c < cells; c += NT) { max_old[c] = 0u; min_new[c] = NONE32; maybe[0][c] = NONE32; }
-      if (t < 8) cnt[t] = 0;
+      for (int c = t; c < cells; c += NT) { max_old[c] = 0u; min_new[c] = NONE32; maybe[0][c] = NONE32; maybe[1][c] = NONE32; }
+      for (int u = t; u < ULIST_CAP; u += NT) best[u] = NONE32;
+      if (t < 16) cnt[t] = 0;
     }
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, NT) { rt.scan(t, NT, nruns); }
@@ -312,17 +313,17 @@ struct ResolveWindow {
       }
     }
     ABM_CTA_SYNC();
+    /* Rounds, two barriers each.  P1: walkers are evaluated, gregarious agents scanned.  P2: gregarious agents draw and
+     * publish; the buffers of the round after next are cleared.  Counters live in slots that alternate with the round's
+     * parity so that nobody resets what others still read.  cnt: [0],[1] walker list lengths, [5],[6] gregarious list
+     * lengths, [8 + 2p], [9 + 2p] progress / open agents of the core for round parity p. */
+    const int side = 2 * v.p.r + 1, box = side * side;
     int cur = 0;
     for (int round = 0; round < max_rounds; ++round) {
       const uint32_t nc = cnt[cur], ng = cnt[5 + cur];
       if (nc + ng == 0) break;
-      ABM_CTA_SYNC();
-      ABM_CTA_FOR(t, NT) {
-        for (int c = t; c < cells; c += NT) maybe[cur ^ 1][c] = NONE32;
-        for (uint32_t u = (uint32_t)t; u < ng; u += (uint32_t)NT) best[u] = NONE32;
-        if (t == 0) { cnt[cur ^ 1] = 0; cnt[5 + (cur ^ 1)] = 0; cnt[2] = 0; cnt[3] = 0; }
-      }
-      ABM_CTA_SYNC();
+      uint32_t* flag = cnt + 8 + 2 * (round & 1);
+      uint32_t* flag_next = cnt + 8 + 2 * ((round + 1) & 1);
       Summaries s;
       s.max_old = max_old; s.min_new = min_new; s.min_maybe = maybe[cur];
       ABM_CTA_FOR(t, NT) {
@@ -334,34 +335,33 @@ struct ResolveWindow {
           if (evaluate(v, s, w, id, x, y, st, nst) == EV_DECIDED) {
             v.state[a] = nst;
             contribute_final(min_new, w, id, x, y, nst);
-            cnt[2] = 1;
+            flag[0] = 1;
           } else {
             const uint32_t slot = smem_add(&cnt[cur ^ 1], 1u);
             l_a[cur ^ 1][slot] = a; l_id[cur ^ 1][slot] = id; l_xs[cur ^ 1][slot] = xs;
             contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
-            if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&cnt[3], 1u);
+            if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&flag[1], 1u);
           }
         }
         /* gregarious closest-neighbour search: one warp per agent, one lane per box cell; the first cell in visiting
          * order that is occupied or unknown wins through a shared-memory min */
-        const int side = 2 * v.p.r + 1, box = side * side;
+        int rel[8]; /* this lane's box cells (visiting ranks lane, lane + 32, ...) as offsets inside the window */
         if (ng > 0) {
-          int rel[8]; /* this lane's box cells (visiting ranks lane, lane + 32, ...) as offsets inside the window */
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 8 && (t & 31) + 32 * j < box; ++j) {
             const int q = (t & 31) + 32 * j;
-            rel[j] = q < box ? (int)v.greg_dxy[2 * q + 1] * WIN + (int)v.greg_dxy[2 * q] : 0;
+            rel[j] = (int)v.greg_dxy[2 * q + 1] * WIN + (int)v.greg_dxy[2 * q];
           }
-          for (uint32_t task = (uint32_t)t >> 5; task < ng; task += (uint32_t)NT >> 5) {
-            const uint32_t e = ULIST_CAP - 1 - task, xs = l_xs[cur][e], id = l_id[cur][e];
-            const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
-            if (x - v.p.r < 1 || x + v.p.r > WIN - 2 || y - v.p.r < 1 || y + v.p.r > WIN - 2) continue; /* box not fully trusted */
-            const int base = y * WIN + x;
-            for (int j = 0; j < 8 && (t & 31) + 32 * j < box; ++j) {
-              const int c = base + rel[j];
-              const uint32_t q = (uint32_t)((t & 31) + 32 * j);
-              if (s.occupied(c, id)) smem_min(&best[task], q << 1);
-              else if (s.unknown(c, id)) smem_min(&best[task], (q << 1) | 1u);
-            }
+        }
+        for (uint32_t task = (uint32_t)t >> 5; task < ng; task += (uint32_t)NT >> 5) {
+          const uint32_t e = ULIST_CAP - 1 - task, xs = l_xs[cur][e], id = l_id[cur][e];
+          const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
+          if (x - v.p.r < 1 || x + v.p.r > WIN - 2 || y - v.p.r < 1 || y + v.p.r > WIN - 2) continue; /* box not fully trusted */
+          const int base = y * WIN + x;
+          for (int j = 0; j < 8 && (t & 31) + 32 * j < box; ++j) {
+            const int c = base + rel[j];
+            const uint32_t q = (uint32_t)((t & 31) + 32 * j);
+            if (s.occupied(c, id)) smem_min(&best[task], q << 1);
+            else if (s.unknown(c, id)) smem_min(&best[task], (q << 1) | 1u);
           }
         }
       }
@@ -373,23 +373,27 @@ struct ResolveWindow {
           const uint8_t st = (uint8_t)(xs >> 16);
           const bool inside = !(x - v.p.r < 1 || x + v.p.r > WIN - 2 || y - v.p.r < 1 || y + v.p.r > WIN - 2);
           const uint32_t b = best[u];
+          best[u] = NONE32; /* ready for the next round */
           if (inside && (b == NONE32 || !(b & 1u))) {
             const uint8_t nst = greg_finish(v, id, st, b == NONE32 ? (int)GREG_NOBODY : (int)v.greg_order[b >> 1]);
             v.state[a] = nst;
             contribute_final(min_new, w, id, x, y, nst);
-            cnt[2] = 1;
+            flag[0] = 1;
           } else {
             const uint32_t k = smem_add(&cnt[5 + (cur ^ 1)], 1u);
             const uint32_t slot = ULIST_CAP - 1 - k;
             l_a[cur ^ 1][slot] = a; l_id[cur ^ 1][slot] = id; l_xs[cur ^ 1][slot] = xs;
             contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
-            if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&cnt[3], 1u);
+            if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&flag[1], 1u);
           }
         }
+        /* what this round read is dead now: make it the clean target of the next round */
+        for (int c = t; c < cells; c += NT) maybe[cur][c] = NONE32;
+        if (t == 0) { cnt[cur] = 0; cnt[5 + cur] = 0; flag_next[0] = 0; flag_next[1] = 0; }
       }
       ABM_CTA_SYNC();
       cur ^= 1;
-      if (cnt[3] == 0 || cnt[2] == 0) break;
+      if (flag[1] == 0 || flag[0] == 0) break;
     }
     ABM_CTA_SYNC();
     const uint32_t nc = cnt[cur], ng = cnt[5 + cur];

@@ -258,41 +258,43 @@ def main():
     value = upd_all / (ms_max * 1e-3)
 
     # ---- end to end through the C ABI with pinned host buffers
-    def pinned(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    def pinned_empty(n, dtype):
+        t = torch.empty(int(n), dtype=dtype).pin_memory()
         return t.numpy(), t
     keep = []
     Gl = G if world == 1 else eng.ny * size  # grid arrays of a strip carry 2 x 32 ghost rows
-    ids, x, y, en = eng.get_agents()
-    fg, cd = eng.get_grid()
+    n_now = eng.count_agents()
+    cap = int(n_now * 1.25) + 4096  # room for the offspring of the timed ticks
     host = {}
-    for k, a in (("ids", ids), ("x", x), ("y", y), ("energy", en), ("fg", fg), ("cd", cd)):
-        host[k], t = pinned(a); keep.append(t)
+    for k, dt in (("ids", torch.int64), ("x", torch.int64), ("y", torch.int64), ("energy", torch.float64)):
+        host[k], t = pinned_empty(cap, dt); keep.append(t)
+    host["fg"], t = pinned_empty(Gl, torch.uint8); keep.append(t)
+    host["cd"], t = pinned_empty(Gl, torch.int64); keep.append(t)
+    host["fg"] = host["fg"].reshape(-1, size); host["cd"] = host["cd"].reshape(-1, size)
     wm = el = None
     if w.get("walkmap") is not None:
-        wm, t = pinned(w["walkmap"]); keep.append(t)
-        el, t = pinned(w["elevation"]); keep.append(t)
+        wm, t = pinned_empty(Gl, torch.uint8); keep.append(t)
+        el, t = pinned_empty(Gl, torch.int64); keep.append(t)
+        wm[:] = np.asarray(w["walkmap"]).reshape(-1); el[:] = np.asarray(w["elevation"]).reshape(-1)
+    # the model as the host sees it after the timed ticks (pinned buffers, as a Julia host would hold its arrays)
+    out_agents = (host["ids"], host["x"], host["y"], host["energy"])
+    ids, x, y, en = eng.get_agents(out_agents)
+    eng.get_grid((host["fg"], host["cd"]))
     st = eng.get_global_state()
     e2e_upd = h2d = d2h = 0
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        n = host["ids"].size
+        n = ids.size
         eng.set_grid(host["fg"], host["cd"], wm, el)
-        eng.set_agents(host["ids"], host["x"], host["y"], host["energy"], st["next_id"])
+        eng.set_agents(host["ids"][:n], host["x"][:n], host["y"][:n], host["energy"][:n], st["next_id"])
         h2d += Gl * 9 + (Gl * 9 if wm is not None else 0) + n * 32
         eng.step(1)
         e2e_upd += n
-        ids, x, y, en = eng.get_agents()
-        fg, cd = eng.get_grid()
+        ids, x, y, en = eng.get_agents(out_agents)
+        eng.get_grid((host["fg"], host["cd"]))
         st = eng.get_global_state()
         d2h += ids.size * 32 + Gl * 9
-        for k, a in (("ids", ids), ("x", x), ("y", y), ("energy", en), ("fg", fg), ("cd", cd)):
-            host[k], t = pinned(a) if a.size != host[k].size else (host[k], None)
-            if t is None:
-                np.copyto(host[k], a)
-            else:
-                keep.append(t)
     barrier()
     e2e_dt = time.perf_counter() - t0
     clocks = sampler.finish(t_wall0, t_wall1)
