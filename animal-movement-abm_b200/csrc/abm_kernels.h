@@ -215,15 +215,26 @@ struct ProposeBody {
         break;
       case ABM_RANDOM_WALKMAP: {                      /* :49-51 with prob 0, random_walkmap :182-186 */
         (void)rs.next_f64(); /* rand(model.rng, Uniform(0,1)) < 0 is never true but is drawn */
-        int cand[8], nc = 0;
-        for (int d = 0; d < 8; ++d) {
-          int ox, oy, ddx, ddy;
-          off8(d, ddx, ddy);
-          if (!shift(v.g, x, y, ddx, ddy, ox, oy)) continue; /* nearby_positions drops out-of-bounds */
-          if (walkable(v, enc(v.g, ox, oy))) cand[nc++] = d;
+        /* nearby_walkable(pos, model, pathfinder, 1): bit d of `ok` = neighbour d (offsets_at_radius order) is walkable */
+        uint32_t ok = 0;
+        const uint32_t lx = c & 31u, ly = (c >> 5) & 31u;
+        if (lx >= 1 && lx <= 30 && ly >= 1 && ly <= 30 && x + 1 < v.g.nx && y + 1 < v.g.y_hi && y - 1 >= v.g.y_lo) { /* 3x3 block inside one tile and inside the grid */
+          const uint32_t* wr = v.walkbits + (size_t)(c >> 10) * 32 + (ly - 1);
+          const uint32_t b0 = (wr[0] >> (lx - 1)) & 7u, b1 = (wr[1] >> (lx - 1)) & 7u, b2 = (wr[2] >> (lx - 1)) & 7u;
+          ok = b0 | ((b1 & 1u) << 3) | ((b1 & 4u) << 2) | (b2 << 5);
+        } else {
+          for (int d = 0; d < 8; ++d) {
+            int ox, oy, ddx, ddy;
+            off8(d, ddx, ddy);
+            if (!shift(v.g, x, y, ddx, ddy, ox, oy)) continue; /* nearby_positions drops out-of-bounds */
+            if (walkable(v, enc(v.g, ox, oy))) ok |= 1u << d;
+          }
         }
+        const int nc = popc(ok);
         if (nc == 0) { atomic_or(v.err, ERR_NOWALKABLE); st = DIR_STAY | ST_DECIDED; break; }
-        const int d = cand[rs.next_below((uint64_t)nc)];
+        int pick = (int)rs.next_below((uint64_t)nc); /* rand(model.rng, 1:length(nearby_pos)) */
+        int d = 0;
+        for (uint32_t m = ok; ; m >>= 1, ++d) { if (m & 1u) { if (pick == 0) break; --pick; } }
         off8(d, dx, dy);
         const int e = effective_dir(v.g, x, y, dx, dy);
         st = (uint8_t)(e | ST_DECIDED | (e != DIR_STAY ? ST_MOVED : 0)); /* move_agent!, unconditional */

@@ -31,7 +31,7 @@ namespace abm {
 
 enum { SUB = 8, CORE = 32, HALO = 8, WIN = CORE + 2 * HALO, MAX_RUNS = 36, TILE_THREADS = 256, AGENT_THREADS = 32 };
 enum { NONE32 = 0xFFFFFFFFu };
-enum { ULIST_CAP = 512, ARRIVE_CAP = 768, RUNOF_CAP = 2048, RUNTABLE_WORDS = 3 * MAX_RUNS + 1 + RUNOF_CAP / 4 }; /* shared-memory work lists of a core; larger populations take the streaming code */
+enum { ULIST_CAP = 512, ARRIVE_CAP = 768, RUNOF_CAP = 2048, RUNTABLE_WORDS = 4 * MAX_RUNS + 1 + RUNOF_CAP / 4 }; /* shared-memory work lists of a core; larger populations take the streaming code */
 
 struct SubIndex {
   const uint32_t* off; /* first agent of the sub-tile's run */
@@ -71,8 +71,16 @@ struct RunTable {
   uint32_t* off;    /* MAX_RUNS */
   uint32_t* prefix; /* MAX_RUNS + 1 */
   uint32_t* cnt;    /* MAX_RUNS */
+  uint32_t* xy0;    /* MAX_RUNS: window coordinates of the run's sub-tile origin, (x0 + 64) | (y0 + 64) << 16 */
   uint8_t* runof;   /* RUNOF_CAP: run of flat index m (valid when the window holds at most RUNOF_CAP agents) */
-  ABM_HD void bind(uint32_t* p) { off = p; prefix = p + MAX_RUNS; cnt = prefix + MAX_RUNS + 1; runof = (uint8_t*)(cnt + MAX_RUNS); }
+  ABM_HD void bind(uint32_t* p) { off = p; prefix = p + MAX_RUNS; cnt = prefix + MAX_RUNS + 1; xy0 = cnt + MAX_RUNS; runof = (uint8_t*)(xy0 + MAX_RUNS); }
+  /* window coordinates of an agent of run r standing on tcell c; false when outside the window */
+  ABM_HD bool locate(const Window& w, int r, uint32_t c, int& x, int& y) const {
+    const uint32_t o = xy0[r];
+    x = (int)(o & 0xFFFF) - 64 + (int)(c & 7);
+    y = (int)(o >> 16) - 64 + (int)((c >> 5) & 7);
+    return x >= 0 && x < w.wx && y >= 0 && y < w.wy;
+  }
   ABM_HD int find(uint32_t m, int nruns) const { /* run containing flat index m */
     if (prefix[nruns] <= RUNOF_CAP) return runof[m];
     int lo = 0, hi = nruns;
@@ -85,6 +93,7 @@ struct RunTable {
       const int sub = w.sub_of_run(r, g, si);
       off[r] = sub < 0 ? 0u : si.off[sub];
       cnt[r] = sub < 0 ? 0u : si.cnt[sub];
+      xy0[r] = (uint32_t)((w.ssx0 + r % w.nssx) * 8 - w.ox + 64) | ((uint32_t)((w.ssy0 + r / w.nssx) * 8 - w.oy + 64) << 16);
     }
   }
   /* phase 2 of 2 (then sync): every run sums the counts before it */
@@ -289,7 +298,7 @@ struct ResolveWindow {
         if (rr[j] < 0) continue;
         const uint32_t a = aa[j];
         int x, y;
-        if (!w.locate(rr[j], cc[j], x, y)) continue;
+        if (!rt.locate(w, rr[j], cc[j], x, y)) continue;
         const uint32_t id = ii[j];
         const uint8_t st = ss[j];
         smem_max(&max_old[y * WIN + x], id);
@@ -449,7 +458,7 @@ struct ResolveWindow {
         const int r = rt.find(m, nruns);
         const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
         int x, y;
-        if (w.locate(r, v.cell[a], x, y)) smem_max(&s.max_old[y * w.wx + x], v.id[a]);
+        if (rt.locate(w, r, v.cell[a], x, y)) smem_max(&s.max_old[y * w.wx + x], v.id[a]);
       }
     }
     ABM_CTA_SYNC();
@@ -465,7 +474,7 @@ struct ResolveWindow {
           const int r = rt.find(m, nruns);
           const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
           int x, y;
-          if (w.locate(r, v.cell[a], x, y)) contribute(s, w, v.id[a], x, y, load_state(&v.state[a]));
+          if (rt.locate(w, r, v.cell[a], x, y)) contribute(s, w, v.id[a], x, y, load_state(&v.state[a]));
         }
       }
       ABM_CTA_SYNC();
@@ -477,7 +486,7 @@ struct ResolveWindow {
           const uint8_t st = load_state(&v.state[a]);
           if (st & ST_DECIDED) continue;
           int x, y;
-          if (!w.locate(r, v.cell[a], x, y)) continue;
+          if (!rt.locate(w, r, v.cell[a], x, y)) continue;
           uint8_t nst = st;
           const int res = evaluate(v, s, w, v.id[a], x, y, st, nst);
           if (res == EV_DECIDED) { v.state[a] = nst; flags[0] = 1; }
@@ -496,7 +505,7 @@ struct ResolveWindow {
         if (mode == 1 && a != target) continue;
         if (load_state(&v.state[a]) & ST_DECIDED) continue;
         int x, y;
-        if (!w.locate(r, v.cell[a], x, y)) continue;
+        if (!rt.locate(w, r, v.cell[a], x, y)) continue;
         if (mode == 1 || (x >= own_lo && x < own_hi && y >= own_lo && y < own_hi)) out[atomic_add(out_count, 1u)] = a;
       }
     }
@@ -516,7 +525,7 @@ struct CommitTile {
   uint32_t* cursor;                     /* next free slot of the output SoA */
   uint32_t* birth_pos; uint32_t* birth_parent; uint32_t* birth_count; uint32_t* birth_bits;
 
-  static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 16 * 3 + RUNTABLE_WORDS + 8 + 3 * ARRIVE_CAP) * 4; }
+  static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 16 * 3 + RUNTABLE_WORDS + 8 + 3 * ARRIVE_CAP + 16 * (TILE_THREADS / 32)) * 4; }
 
   ABM_HD void operator()(uint32_t cta, uint32_t* smem) const {
     const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) + core_y0;
@@ -534,6 +543,7 @@ struct CommitTile {
     uint32_t* ar_a = misc + 8;                 /* arrivals: agent index, id, core cell | state << 16 */
     uint32_t* ar_id = ar_a + ARRIVE_CAP;
     uint32_t* ar_cs = ar_id + ARRIVE_CAP;
+    uint32_t* wcounts = ar_cs + ARRIVE_CAP;    /* per warp x per sub-tile arrival counts (one hot address would serialise) */
     const uint32_t tile = (uint32_t)(cy * cores_x + cx); /* CORE == TILE: a core is one grass tile */
     uint32_t* gtile = (uint32_t*)(v.grass + (size_t)tile * TILE_CELLS);
 
@@ -541,7 +551,7 @@ struct CommitTile {
       rt.load(t, NT, nruns, w, v.g, si);
       for (int c = t; c < CORE * CORE; c += NT) min_all[c] = NONE32;
       for (int c = t; c < CORE * CORE / 4; c += NT) ((uint32_t*)grass)[c] = gtile[c];
-      if (t < 16) counts[t] = 0;
+      if (t < 16 * (TILE_THREADS / 32)) wcounts[t] = 0;
       if (t < 8) misc[t] = 0;
     }
     ABM_CTA_SYNC();
@@ -555,7 +565,7 @@ struct CommitTile {
         const int r = rt.find(m, nruns);
         const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
         int x, y;
-        if (!w.locate(r, v.cell[a], x, y)) continue;
+        if (!rt.locate(w, r, v.cell[a], x, y)) continue;
         const uint8_t st = v.state[a];
         if (!(st & ST_DECIDED)) { atomic_or(v.err, ERR_INTERNAL); continue; }
         if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); x += dx; y += dy; }
@@ -564,11 +574,15 @@ struct CommitTile {
         const uint32_t id = v.id[a];
         smem_min(&min_all[y * CORE + x], id);
         const uint32_t add = ((st & ST_DEAD) ? 0u : 1u) + ((st & ST_BIRTH) ? 1u : 0u);
-        if (add) smem_add(&counts[(y >> 3) * 4 + (x >> 3)], add);
+        if (add) smem_add(&wcounts[(t >> 5) * 16 + (y >> 3) * 4 + (x >> 3)], add);
         const uint32_t slot = smem_add(&misc[1], 1u);
         if (slot < ARRIVE_CAP) { ar_a[slot] = a; ar_id[slot] = id; ar_cs[slot] = (uint32_t)(y * CORE + x) | ((uint32_t)st << 16); }
         else misc[2] = 1;
       }
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) {
+      if (t < 16) { uint32_t c = 0; for (int q = 0; q < TILE_THREADS / 32; ++q) c += wcounts[q * 16 + t]; counts[t] = c; }
     }
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, NT) {
@@ -600,7 +614,7 @@ struct CommitTile {
         } else {
           const int r = rt.find(m, nruns);
           a = rt.off[r] + (m - rt.prefix[r]);
-          if (!w.locate(r, v.cell[a], x, y)) continue;
+          if (!rt.locate(w, r, v.cell[a], x, y)) continue;
           st = v.state[a];
           if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); x += dx; y += dy; }
           x -= HALO; y -= HALO;
@@ -631,11 +645,10 @@ struct CommitTile {
     }
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, NT) { /* custom_model_step! on the tile, then one coalesced write-back */
-      if (t < CORE * CORE / 16) {
-        uint32_t* w4 = (uint32_t*)grass + 4 * t;
+      for (int q = t; q < CORE * CORE / 4; q += NT) { /* one word = four cells per thread */
         uint32_t wb = 0;
-        if (v.p.walkmap_regrowth) wb = v.walkbits[tile * 32 + (uint32_t)(t >> 1)] >> ((t & 1) * 16);
-        for (int q = 0; q < 4; ++q) gtile[4 * t + q] = regrow4(w4[q], (uint32_t)v.p.regrowth_time, wb >> (4 * q), v.p.walkmap_regrowth != 0);
+        if (v.p.walkmap_regrowth) wb = v.walkbits[tile * 32 + (uint32_t)(q >> 3)] >> ((q & 7) * 4);
+        gtile[q] = regrow4(((const uint32_t*)grass)[q], (uint32_t)v.p.regrowth_time, wb, v.p.walkmap_regrowth != 0);
       }
     }
   }
