@@ -64,9 +64,10 @@ struct Geo {
 /* offsets_at_radius(model, 1) order (x fastest), SURVEY.md A-5 */
 ABM_HD void off8(int d, int& dx, int& dy) {
   /* d: 0..7 -> (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1) */
-  const int q = d < 4 ? d : d + 1; /* skip the centre of the 3x3 */
-  dx = q % 3 - 1;
-  dy = q / 3 - 1;
+  const int q = d + (d >= 4); /* skip the centre of the 3x3 */
+  const int row = (q >= 3) + (q >= 6);
+  dx = q - 3 * row - 1;
+  dy = row - 1;
 }
 ABM_HD int dir_code(int ex, int ey) {
   const int q = (ey + 1) * 3 + (ex + 1);
@@ -217,17 +218,22 @@ struct ProposeBody {
         (void)rs.next_f64(); /* rand(model.rng, Uniform(0,1)) < 0 is never true but is drawn */
         /* nearby_walkable(pos, model, pathfinder, 1): bit d of `ok` = neighbour d (offsets_at_radius order) is walkable */
         uint32_t ok = 0;
-        const uint32_t lx = c & 31u, ly = (c >> 5) & 31u;
-        if (lx >= 1 && lx <= 30 && ly >= 1 && ly <= 30 && x + 1 < v.g.nx && y + 1 < v.g.y_hi && y - 1 >= v.g.y_lo) { /* 3x3 block inside one tile and inside the grid */
-          const uint32_t* wr = v.walkbits + (size_t)(c >> 10) * 32 + (ly - 1);
-          const uint32_t b0 = (wr[0] >> (lx - 1)) & 7u, b1 = (wr[1] >> (lx - 1)) & 7u, b2 = (wr[2] >> (lx - 1)) & 7u;
-          ok = b0 | ((b1 & 1u) << 3) | ((b1 & 4u) << 2) | (b2 << 5);
-        } else {
-          for (int d = 0; d < 8; ++d) {
-            int ox, oy, ddx, ddy;
-            off8(d, ddx, ddy);
-            if (!shift(v.g, x, y, ddx, ddy, ox, oy)) continue; /* nearby_positions drops out-of-bounds */
-            if (walkable(v, enc(v.g, ox, oy))) ok |= 1u << d;
+        int xs[3] = {x - 1, x, x + 1};
+        if (v.g.periodic) { xs[0] = wrap(xs[0], v.g.nx); xs[2] = wrap(xs[2], v.g.nx); }
+        else { if (xs[0] < 0) xs[0] = -1; if (xs[2] >= v.g.nx) xs[2] = -1; } /* nearby_positions drops out-of-bounds */
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          int yy = y + r - 1;
+          if (v.g.py) yy = wrap(yy, v.g.ny); else if (yy < v.g.y_lo || yy >= v.g.y_hi) continue;
+          const uint32_t* row = v.walkbits + ((size_t)(yy >> 5) * v.g.tiles_x) * 32 + (yy & 31); /* word of tile column 0 */
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            if (r == 1 && q == 1) continue;
+            const int xx = xs[q];
+            if (xx < 0) continue;
+            const uint32_t bit = (row[(size_t)(xx >> 5) * 32] >> (xx & 31)) & 1u;
+            const int idx = r * 3 + q;
+            ok |= bit << (idx < 4 ? idx : idx - 1);
           }
         }
         const int nc = popc(ok);
