@@ -232,3 +232,53 @@ def test_gpu_tile_path_matches_oracle(libabm, oracle, wt, per, terr, n, nx, ny, 
     a.step(20)
     b.step(20)
     assert_same_state(b.snapshot(), a.snapshot(), f"wt {wt} tick 32")
+
+
+def _full_size_world(size, wt, seed=5):
+    from abm_b200 import worlds
+    wm = el = None
+    if wt == 4:
+        el = worlds.make_terrain(size, size, seed=seed + 1)
+        wm = worlds.walkmap_from_elevation(el)
+    w = worlds.make_world(size, size, size * size // 4, seed=seed, walkmap=wm, periodic=True)
+    w["walkmap"], w["elevation"] = wm, el
+    return w
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wt,size,extra", [
+    (2, 4096, dict(visual_distance=3, reproduction_prob=0.001)),          # BASELINE.json configs[1] (C2) at full size
+    (4, 4096, dict(walkmap_regrowth=1, reproduction_prob=0.004)),         # C3 rules at a quarter of its area
+    (0, 2048, dict(reproduction_prob=0.01)),
+])
+def test_gpu_full_size_two_engine_paths_and_invariants(libabm, wt, size, extra):
+    """At sizes the CPU oracle cannot reach in seconds: the two independently written GPU paths (tile path, general
+    path forced with reserved0 = 1) must agree bit for bit, and the trajectory must satisfy the size-independent
+    properties of the rules: ids strictly increasing and unique, every survivor moved at most one cell (Chebyshev,
+    periodic), population = survivors + offspring, offspring ids = the next free ids, at most one meal per grown cell,
+    energy bookkeeping (every meal adds exactly delta_energy), grass countdown within range."""
+    w = _full_size_world(size, wt)
+    cfg = dict(nx=size, ny=size, periodic=1, walk_type=wt, seed=77, **extra)
+    a, b = load_case(libabm, cfg, w), load_case(libabm, dict(cfg, reserved0=1), w)
+    prev = a.snapshot()
+    for t in range(3):
+        a.step(1)
+        b.step(1)
+        assert "commit_tiles" in {k for k, v in a.kernel_stats().items() if v["launches"]}
+        assert "commit_tiles" not in {k for k, v in b.kernel_stats().items() if v["launches"]}
+        sa, sb = a.snapshot(), b.snapshot()
+        assert_same_state(sa, sb, f"tile vs general path, walk type {wt}, tick {t}")
+        ids, pid = sa["ids"], prev["ids"]
+        assert np.all(np.diff(ids) > 0)
+        old = np.isin(ids, pid, assume_unique=True)
+        born = ids[~old]
+        assert born.size == sa["next_id"] - prev["next_id"] and (born.size == 0 or (born.min() == prev["next_id"] and born.max() == sa["next_id"] - 1))
+        was = np.searchsorted(pid, ids[old])
+        dx = np.abs(sa["x"][old] - prev["x"][was]); dy = np.abs(sa["y"][old] - prev["y"][was])
+        dx = np.minimum(dx, size - dx); dy = np.minimum(dy, size - dy)
+        assert max(dx.max(), dy.max()) <= 1
+        eaten = int(((prev["fully_grown"] == 1) & (sa["fully_grown"] == 0)).sum())
+        assert 0 < eaten <= pid.size
+        assert sa["countdown"].min() >= 0 and sa["countdown"].max() <= 30
+        assert np.all(sa["energy"] >= 0)  # agents below zero were removed (reduce_energy!, strict <)
+        prev = sa
