@@ -134,6 +134,46 @@ def time_oracle(workload, size, agents, ticks, warm=1):
     return upd / dt, dt, upd
 
 
+def run_astar(args):
+    """BASELINE.json configs[3] (C4): batched A* replans (PenaltyMap(elevation, MaxDistance), scripts/v0.6.jl:87-93) on
+    synthetic terrain.  Not the headline metric: prints its own line (replans/s, expansions/s) for profiles/."""
+    import torch
+    from abm_b200 import build, capi, worlds
+    size, n = args.size, args.replans
+    el = worlds.make_terrain(size, size, seed=322)
+    wm = worlds.walkmap_from_elevation(el)
+    w = worlds.make_world(size, size, n, seed=321, walkmap=wm, periodic=True)
+    ok = np.flatnonzero(wm.reshape(-1))
+    rng = np.random.Generator(np.random.Philox(key=99))
+    goal = ok[rng.integers(0, ok.size, n)]  # random_walkable: uniform over walkable cells
+    if args.max_dist:  # bounded replans (local goals): |goal - start| <= max_dist per axis, still walkable
+        gx = np.clip(w["x"] - 1 + rng.integers(-args.max_dist, args.max_dist + 1, n), 0, size - 1)
+        gy = np.clip(w["y"] - 1 + rng.integers(-args.max_dist, args.max_dist + 1, n), 0, size - 1)
+        lin = gy * size + gx
+        keep = wm.reshape(-1)[lin] == 1
+        goal = np.where(keep, lin, (w["y"] - 1) * size + (w["x"] - 1))
+    gx, gy = goal % size + 1, goal // size + 1
+    cfg = dict(nx=size, ny=size, periodic=1, walk_type=3, astar_metric=1, astar_penalty=1, counter=50, seed=321)
+    res = {}
+    for name, lib, m in (("b200", capi.CLib(build.LIBABM, "abm_"), n), ("oracle", oracle_lib(), min(n, args.ref_replans))):
+        e = lib.create(lib.default_config(**cfg))
+        e.set_grid(w["fully_grown"], w["countdown"], wm, el)
+        e.set_agents(w["ids"], w["x"], w["y"], w["energy"])
+        e.set_profiling(True) if name == "b200" else None
+        t0 = time.perf_counter()
+        e.plan_routes(w["ids"][:m], gx[:m], gy[:m])
+        dt = time.perf_counter() - t0
+        tm = e.timing()
+        off, px, py, cost = e.get_paths(w["ids"][: min(m, 2000)])
+        res[name] = dict(replans=m, seconds=dt, device_ms=tm["ms_total"], expansions=tm["astar_expansions"], replans_per_s=m / dt,
+                         expansions_per_s=tm["astar_expansions"] / dt, mean_path_cells=float(off[-1]) / max(1, min(m, 2000)), found=int((cost >= 0).sum()))
+        e.close()
+    print(json.dumps({"metric": "astar_replans_per_s", "value": res["b200"]["replans_per_s"], "unit": "replans/s", "n_gpus": 1,
+                      "config": {"workload": f"v0.6 batched A* replans, PenaltyMap(elevation, MaxDistance), {size}x{size} synthetic terrain, {n} replans"
+                                 + (f", goals within {args.max_dist} cells" if args.max_dist else ", goals = random_walkable")},
+                      "b200": res["b200"], "cpu_baseline": dict(kind="port", cores=1, **res["oracle"]), "data": "synthetic", "dtype": "int32 costs"}))
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -168,7 +208,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS) + ["C4"])
+    ap.add_argument("--replans", type=int, default=1 << 14)
+    ap.add_argument("--ref-replans", type=int, default=64)
+    ap.add_argument("--max-dist", type=int, default=0)
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--ref-size", type=int, default=1024)
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -180,6 +223,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.workload == "C4":
+        if rank == 0:
+            run_astar(args)
+        return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
