@@ -234,7 +234,7 @@ struct ProfScope {
 };
 
 enum { CTR_BIRTH_TOTAL = 12, CTR_PEND_A = 0, CTR_PEND_B = 1, CTR_BIRTHS = 2, CTR_ERR = 3, CTR_RED_LO = 4, CTR_RED_HI = 5, CTR_PLANS = 6, CTR_ROUTE_SLOTS = 7,
-       CTR_EXP_LO = 8, CTR_EXP_HI = 9, CTR_CURSOR = 10, CTR_BIRTH_FLAGS = 11, CTR_WORDS = 16 };
+       CTR_EXP_LO = 8, CTR_EXP_HI = 9, CTR_CURSOR = 10, CTR_BIRTH_FLAGS = 11, CTR_PEND_FIRST = 13, CTR_WORDS = 16 };
 
 }  // namespace
 
@@ -259,6 +259,8 @@ struct abm_handle {
   uint32_t as_gen = 0;
   /* tile path (abm_tile.h): sub-tile runs of the SoA (ping-pong with the SoA), offspring fix-up lists */
   bool tile_mode = false;
+  int32_t fixed_agent_rounds = 2; /* per-agent rounds enqueued without asking the host (ABM_AGENT_ROUNDS overrides) */
+  uint64_t kf_grid = 1024;        /* CTAs of those launches: an upper bound learnt from the previous tick */
   int32_t tile_rounds = 8; /* in-window rounds of the tile resolve kernel (ABM_TILE_ROUNDS overrides; tests use 1) */
   int32_t nsx = 0, nsy = 0;
   DevBuf sub_off[2], sub_cnt[2], birth_pos, birth_parent, ingest_sub;
@@ -886,13 +888,10 @@ static int strip_alloc(abm_handle* h) {
 }
 
 /* E1: this strip's first and last sub-tile rows (cell, id, energy, proposal) become the neighbours' ghost rows.
- * One fixed-size message per neighbour, prefixes on the device: no host round trip. */
+ * One fixed-size message per neighbour; header, prefix and packing by one CTA per direction: no host round trip. */
 static int strip_exchange_agents(abm_handle* h) {
   int rc;
   const int nsx = h->nsx, cur = h->cur;
-  const int row_s[2] = {h->g.own_lo / SUB, h->g.own_hi / SUB - 1};       /* my rows sent to prev / next */
-  const int row_g[2] = {h->g.own_lo / SUB - 1, h->g.own_hi / SUB};       /* ghost rows filled from prev / next */
-  const uint32_t tile_row_g[2] = {(uint32_t)(h->g.own_lo / CORE - 1), (uint32_t)(h->g.own_hi / CORE)};
   const uint64_t cap = h->bcap, hdr = strip_hdr_bytes(nsx), bytes = strip_msg_bytes(nsx, cap);
   if ((rc = strip_alloc(h))) return rc;
   /* ghost agents live at fixed places behind the own agents: [n, n + cap) from prev, [n + cap, n + 2 cap) from next */
@@ -904,39 +903,27 @@ static int strip_exchange_agents(abm_handle* h) {
   if ((rc = ensure(h, h->pend[0], tot * 4))) return rc;
   if ((rc = ensure(h, h->pend[1], tot * 4))) return rc;
   uint32_t* err = (uint32_t*)h->counters.p + CTR_ERR;
-  for (int d = 0; d < 2; ++d) {
-    uint8_t* b = (uint8_t*)h->sx_buf[d].p;
-    GatherCountsBody gc;
-    gc.sub_cnt = (const uint32_t*)h->sub_cnt[cur].p; gc.row = row_s[d]; gc.nsx = nsx; gc.out = (uint32_t*)b;
-    launch_foreach(h->stream, gc, (uint64_t)nsx + 1);
-    ABM_CK(h, copy_d2d(h->sx_pre[d].p, b, ((size_t)nsx + 1) * 4, h->stream));
-    ABM_CK(h, scan_exclusive_u32(h->stream, (uint32_t*)h->sx_pre[d].p, (uint64_t)nsx + 1, (uint32_t*)h->scan_tmp.p));
-    PackRowBody pk;
-    pk.si = sub_index(h, cur); pk.row = row_s[d]; pk.tiles_x = h->g.tiles_x; pk.with_agents = 1; pk.cap = (uint32_t)cap;
-    pk.cell = (const uint32_t*)h->cell[cur].p; pk.id = (const uint32_t*)h->id[cur].p; pk.energy = (const double*)h->energy[cur].p; pk.state = (const uint8_t*)h->state.p;
-    pk.prefix = (const uint32_t*)h->sx_pre[d].p;
-    pk.p_energy = (double*)(b + hdr); pk.p_cell = (uint32_t*)(b + hdr + cap * 8); pk.p_id = (uint32_t*)(b + hdr + cap * 12); pk.p_state = b + hdr + cap * 16;
-    pk.err = err;
-    launch_foreach(h->stream, pk, (uint64_t)nsx);
-    ABM_CK(h, dev_memset(h->rx_buf[d].p, 0, hdr, h->stream)); /* a missing neighbour sends nothing: empty ghost row */
-  }
+  StripPackCta pk;
+  pk.si = sub_index(h, cur); pk.row[0] = h->g.own_lo / SUB; pk.row[1] = h->g.own_hi / SUB - 1; pk.tiles_x = h->g.tiles_x; pk.cap = (uint32_t)cap;
+  pk.cell = (const uint32_t*)h->cell[cur].p; pk.id = (const uint32_t*)h->id[cur].p; pk.energy = (const double*)h->energy[cur].p; pk.state = (const uint8_t*)h->state.p;
+  for (int d = 0; d < 2; ++d) { pk.msg[d] = (uint8_t*)h->sx_buf[d].p; pk.pre[d] = (uint32_t*)h->sx_pre[d].p; }
+  pk.hdr = hdr; pk.err = err;
+  launch_cta(h->stream, pk, 2, TILE_THREADS, StripPackCta::smem_bytes());
+  for (int d = 0; d < 2; ++d) ABM_CK(h, dev_memset(h->rx_buf[d].p, 0, hdr, h->stream)); /* a missing neighbour sends nothing */
   if ((rc = check_launch(h, "strip pack"))) return rc;
   { ProfScope ps(h->prof, h->stream, "halo_exchange", 2 * cap);
     if ((rc = comm_sendrecv(h, h->sx_buf[0].p, bytes, h->sx_buf[1].p, bytes, h->rx_buf[0].p, bytes, h->rx_buf[1].p, bytes))) return rc; }
-  for (int d = 0; d < 2; ++d) {
-    const uint8_t* b = (const uint8_t*)h->rx_buf[d].p;
-    ABM_CK(h, copy_d2d(h->rx_pre[d].p, b, ((size_t)nsx + 1) * 4, h->stream));
-    ABM_CK(h, scan_exclusive_u32(h->stream, (uint32_t*)h->rx_pre[d].p, (uint64_t)nsx + 1, (uint32_t*)h->scan_tmp.p));
-    UnpackRowBody up;
-    up.row = row_g[d]; up.nsx = nsx; up.tile_row_base = (tile_row_g[d] * (uint32_t)h->g.tiles_x) << 10;
-    up.base = (uint32_t)(h->n + (uint64_t)d * cap); up.cap = (uint32_t)cap;
-    up.counts = (const uint32_t*)b; up.prefix = (const uint32_t*)h->rx_pre[d].p;
-    up.p_energy = (const double*)(b + hdr); up.p_cell = (const uint32_t*)(b + hdr + cap * 8); up.p_id = (const uint32_t*)(b + hdr + cap * 12); up.p_state = b + hdr + cap * 16;
-    up.sub_off = (uint32_t*)h->sub_off[cur].p; up.sub_cnt = (uint32_t*)h->sub_cnt[cur].p;
-    up.cell = (uint32_t*)h->cell[cur].p; up.id = (uint32_t*)h->id[cur].p; up.energy = (double*)h->energy[cur].p; up.state = (uint8_t*)h->state.p;
-    up.err = err;
-    launch_foreach(h->stream, up, (uint64_t)nsx);
-  }
+  StripUnpackCta up;
+  up.row[0] = h->g.own_lo / SUB - 1; up.row[1] = h->g.own_hi / SUB; up.nsx = nsx;
+  up.tile_row_base[0] = ((uint32_t)(h->g.own_lo / CORE - 1) * (uint32_t)h->g.tiles_x) << 10;
+  up.tile_row_base[1] = ((uint32_t)(h->g.own_hi / CORE) * (uint32_t)h->g.tiles_x) << 10;
+  up.base[0] = (uint32_t)h->n; up.base[1] = (uint32_t)(h->n + cap); up.cap = (uint32_t)cap;
+  for (int d = 0; d < 2; ++d) { up.msg[d] = (const uint8_t*)h->rx_buf[d].p; up.pre[d] = (uint32_t*)h->rx_pre[d].p; }
+  up.hdr = hdr;
+  up.sub_off = (uint32_t*)h->sub_off[cur].p; up.sub_cnt = (uint32_t*)h->sub_cnt[cur].p;
+  up.cell = (uint32_t*)h->cell[cur].p; up.id = (uint32_t*)h->id[cur].p; up.energy = (double*)h->energy[cur].p; up.state = (uint8_t*)h->state.p;
+  up.err = err;
+  launch_cta(h->stream, up, 2, TILE_THREADS, StripUnpackCta::smem_bytes());
   h->n_ghost = 2 * cap; /* upper bound; the sub-tile index knows the real counts */
   return check_launch(h, "strip unpack");
 }
@@ -945,26 +932,22 @@ static int strip_exchange_agents(abm_handle* h) {
 static int strip_exchange_states(abm_handle* h) {
   int rc;
   const int cur = h->cur, nsx = h->nsx;
-  const int row_s[2] = {h->g.own_lo / SUB, h->g.own_hi / SUB - 1};
   const uint64_t cap = h->bcap;
-  for (int d = 0; d < 2; ++d) {
-    PackRowBody pk;
-    pk.si = sub_index(h, cur); pk.row = row_s[d]; pk.tiles_x = h->g.tiles_x; pk.with_agents = 0; pk.cap = (uint32_t)cap;
-    pk.cell = nullptr; pk.id = nullptr; pk.energy = nullptr; pk.state = (const uint8_t*)h->state.p;
-    pk.prefix = (const uint32_t*)h->sx_pre[d].p;
-    pk.p_energy = nullptr; pk.p_cell = nullptr; pk.p_id = nullptr; pk.p_state = (uint8_t*)h->sx_st[d].p;
-    pk.err = (uint32_t*)h->counters.p + CTR_ERR;
-    launch_foreach(h->stream, pk, (uint64_t)nsx);
-  }
+  PackStatesBody pk;
+  pk.si = sub_index(h, cur); pk.row[0] = h->g.own_lo / SUB; pk.row[1] = h->g.own_hi / SUB - 1; pk.cap = (uint32_t)cap;
+  pk.state = (const uint8_t*)h->state.p;
+  for (int d = 0; d < 2; ++d) { pk.pre[d] = (const uint32_t*)h->sx_pre[d].p; pk.out[d] = (uint8_t*)h->sx_st[d].p; }
+  launch_foreach(h->stream, pk, 2 * (uint64_t)nsx);
   { ProfScope ps(h->prof, h->stream, "decision_exchange", 2 * cap);
     if ((rc = comm_sendrecv(h, h->sx_st[0].p, cap, h->sx_st[1].p, cap, h->rx_st[0].p, cap, h->rx_st[1].p, cap))) return rc; }
+  MergeStatesBody mg;
   for (int d = 0; d < 2; ++d) {
-    if ((d == 0 && !h->has_prev) || (d == 1 && !h->has_next)) continue;
-    MergeStateBody mg;
-    mg.incoming = (const uint8_t*)h->rx_st[d].p; mg.state = (uint8_t*)h->state.p; mg.base = (uint32_t)(h->n + (uint64_t)d * cap);
-    mg.total = (const uint32_t*)h->rx_pre[d].p + nsx;
-    launch_foreach(h->stream, mg, cap);
+    mg.incoming[d] = (const uint8_t*)h->rx_st[d].p; mg.base[d] = (uint32_t)(h->n + (uint64_t)d * cap);
+    mg.total[d] = (const uint32_t*)h->rx_pre[d].p + nsx;
   }
+  mg.present[0] = h->has_prev ? 1 : 0; mg.present[1] = h->has_next ? 1 : 0;
+  mg.state = (uint8_t*)h->state.p; mg.cap = (uint32_t)cap;
+  launch_foreach(h->stream, mg, 2 * cap);
   return check_launch(h, "strip state merge");
 }
 
@@ -1114,23 +1097,40 @@ static int tick_tile(abm_handle* h) {
     h->next_bcap = rmax * 2 > h->bcap ? strip_cap_for(rmax) : h->bcap; /* every rank sees the same figures */
     return 0;
   };
-  if ((rc = take_stats(ctr + CTR_PEND_A))) return rc;
+  int in = 0;
+  const int q = wt == ABM_RANDOM_WALK_GREGARIOUS ? h->cfg.visual_distance + 1 : 2;
+  auto launch_agents = [&](uint64_t grid, uint32_t* d_out) -> int { /* one Jacobi round of per-agent windows over pend[in] */
+    ABM_CK(h, dev_memset(d_out, 0, sizeof(uint32_t), h->stream));
+    ResolveWindow rw;
+    rw.v = v; rw.si = si; rw.mode = 1; rw.cores_x = 0; rw.core_y0 = 0; rw.max_rounds = 1; rw.nthreads = AGENT_THREADS;
+    rw.grid = (uint32_t)grid; rw.in = (const uint32_t*)h->pend[in].p; rw.in_count = ctr + (in ? CTR_PEND_B : CTR_PEND_A);
+    rw.out = (uint32_t*)h->pend[in ^ 1].p; rw.out_count = d_out;
+    { ProfScope ps(h->prof, h->stream, "resolve_agents", grid); launch_cta(h->stream, rw, grid, AGENT_THREADS, ResolveWindow::smem_bytes(2 * q + 1, 2 * q + 1)); }
+    return check_launch(h, "agent resolve");
+  };
+  if (needs_resolve && n + h->n_ghost > 0) {
+    /* the first rounds of per-agent windows are enqueued blind: their list lengths stay on the device, the launch is an
+     * upper bound learnt from the previous tick (grid-stride inside), and the host reads everything back once */
+    ABM_CK(h, copy_d2d(ctr + CTR_PEND_FIRST, ctr + CTR_PEND_A, sizeof(uint32_t), h->stream));
+    for (int r = 0; r < h->fixed_agent_rounds; ++r) {
+      if (h->strip && (rc = strip_exchange_states(h))) return rc;
+      if ((rc = launch_agents(std::max<uint64_t>(h->kf_grid, 1), ctr + (in ? CTR_PEND_A : CTR_PEND_B)))) return rc;
+      in ^= 1;
+      h->rounds += 1;
+    }
+  }
+  if ((rc = take_stats(ctr + (in ? CTR_PEND_B : CTR_PEND_A)))) return rc;
+  if (h->strip && (rc = read_counters(h))) return rc;
+  h->kf_grid = std::min<uint64_t>(std::max<uint64_t>(2ull * h->h_counters[CTR_PEND_FIRST] + 256, 512), std::max<uint64_t>(n + h->n_ghost, 1));
   {
-    int in = 0, stalls = 0;
-    const int q = wt == ABM_RANDOM_WALK_GREGARIOUS ? h->cfg.visual_distance + 1 : 2;
+    int stalls = 0;
     while (true) { /* chains that left their window: one small window per agent, Jacobi rounds */
       /* strips: the owners' decisions reach the ghost copies; every rank stays in the loop until all ranks are done */
       if (h->strip && needs_resolve && (rc = strip_exchange_states(h))) return rc;
       if (global_cnt == 0) break;
       uint32_t* d_out = ctr + (in ? CTR_PEND_A : CTR_PEND_B);
-      ABM_CK(h, dev_memset(d_out, 0, sizeof(uint32_t), h->stream));
-      if (cnt > 0) {
-        ResolveWindow rw;
-        rw.v = v; rw.si = si; rw.mode = 1; rw.cores_x = 0; rw.core_y0 = 0; rw.max_rounds = 1; rw.nthreads = AGENT_THREADS;
-        rw.in = (const uint32_t*)h->pend[in].p; rw.out = (uint32_t*)h->pend[in ^ 1].p; rw.out_count = d_out;
-        { ProfScope ps(h->prof, h->stream, "resolve_agents", cnt); launch_cta(h->stream, rw, cnt, AGENT_THREADS, ResolveWindow::smem_bytes(2 * q + 1, 2 * q + 1)); }
-        if ((rc = check_launch(h, "agent resolve"))) return rc;
-      }
+      if (cnt > 0) { if ((rc = launch_agents(cnt, d_out))) return rc; }
+      else ABM_CK(h, dev_memset(d_out, 0, sizeof(uint32_t), h->stream));
       const uint64_t before = global_cnt;
       if ((rc = take_stats(d_out))) return rc;
       h->rounds += 1;
@@ -1320,6 +1320,7 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
   h->tile_mode = h->strip || (cfg->reserved0 != 1 && cfg->walk_type != ABM_ALTERNATED_WALK && cfg->nx % CORE == 0 && cfg->ny % CORE == 0 &&
                              cfg->nx >= 2 * CORE && cfg->ny >= 2 * CORE);
   h->nsx = g.nx / SUB; h->nsy = g.ny / SUB;
+  if (const char* ar = getenv("ABM_AGENT_ROUNDS")) { const int q = atoi(ar); if (q >= 0 && q <= 16) h->fixed_agent_rounds = q; }
   if (const char* tr = getenv("ABM_TILE_ROUNDS")) { const int q = atoi(tr); if (q >= 1 && q <= 64) h->tile_rounds = q; }
   rc = 0;
   do {

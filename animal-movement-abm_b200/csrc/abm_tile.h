@@ -242,7 +242,9 @@ struct ResolveWindow {
   View v;
   SubIndex si;
   int32_t mode, cores_x, core_y0, max_rounds, nthreads;
+  uint32_t grid;            /* mode 1: number of CTAs launched */
   const uint32_t* in;
+  const uint32_t* in_count; /* mode 1: device-side length of `in` */
   uint32_t* out;
   uint32_t* out_count;
 
@@ -421,16 +423,25 @@ struct ResolveWindow {
     if (mode == 0) {
       if (core_fast(cta, smem)) return;
       ABM_CTA_SYNC();
+      window_body(cta, NONE32, smem);
+      return;
     }
+    /* per-agent windows: the list length lives on the device (the host launches an upper bound), grid-stride over it */
+    const uint32_t n_in = *in_count;
+    for (uint32_t b = cta; b < n_in; b += grid) {
+      window_body(0, in[b], smem);
+      ABM_CTA_SYNC();
+    }
+  }
+
+  ABM_HD void window_body(uint32_t cta, uint32_t target, uint32_t* smem) const {
     Window w;
-    uint32_t target = NONE32;
     int own_lo = 0, own_hi = 0;
     if (mode == 0) {
       const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) + core_y0;
       w.set(cx * CORE - HALO, cy * CORE - HALO, WIN, WIN);
       own_lo = HALO; own_hi = HALO + CORE;
     } else {
-      target = in[cta];
       int x, y;
       dec(v.g, v.cell[target], x, y);
       const int q = (v.state[target] & ST_DIRMASK) == DIR_GREG ? v.p.r + 1 : 2;
@@ -707,57 +718,125 @@ struct GatherCountsBody { /* the counts of one sub-tile row -> message header */
   ABM_HD void operator()(uint64_t i) const { out[i] = i < (uint64_t)nsx ? sub_cnt[(uint32_t)row * (uint32_t)nsx + (uint32_t)i] : 0u; }
 };
 
-/* one boundary sub-tile row packed for a neighbour: cells normalised to tile row 0 (the receiver adds its ghost tile
- * row).  with_agents = 0 packs the decision bytes only (same order).  One thread per sub-tile. */
-struct PackRowBody {
-  SubIndex si; int32_t row, tiles_x, with_agents; uint32_t cap;
+/* exclusive prefix of `nsx` counts by one CTA of NT threads, thread t owning the chunk [t * per, (t + 1) * per):
+ * phase 1 (chunk sums -> part[t]), phase 2 (sums of 32 parts -> part2), then every thread adds what precedes it */
+ABM_HD uint32_t chunk_prefix(const uint32_t* part, const uint32_t* part2, int t) {
+  uint32_t p = 0;
+  for (int q = 0; q < (t >> 5); ++q) p += part2[q];
+  for (int q = t & ~31; q < t; ++q) p += part[q];
+  return p;
+}
+
+/* E1, sender side, CTA d = direction (0: my first own sub-tile row, to the previous strip; 1: my last, to the next):
+ * header counts, their prefix (kept in pre[d] for the decision exchanges of this tick) and the agents, packed in order.
+ * Cells are normalised to tile row 0 (the receiver adds its ghost tile row). */
+struct StripPackCta {
+  SubIndex si; int32_t row[2]; int32_t tiles_x; uint32_t cap;
   const uint32_t* cell; const uint32_t* id; const double* energy; const uint8_t* state;
-  const uint32_t* prefix;
-  uint32_t* p_cell; uint32_t* p_id; double* p_energy; uint8_t* p_state;
+  uint8_t* msg[2]; uint32_t* pre[2]; /* nsx + 1 entries, the last = total */
+  uint64_t hdr;
   uint32_t* err;
-  ABM_HD void operator()(uint64_t i) const {
-    const uint32_t sub = (uint32_t)row * (uint32_t)si.nsx + (uint32_t)i;
-    const uint32_t off = si.off[sub], cnt = si.cnt[sub];
-    uint32_t o = prefix[i];
-    if (o + cnt > cap) { atomic_or(err, ERR_STRIP_CAP); return; }
-    for (uint32_t k = 0; k < cnt; ++k, ++o) {
-      if (with_agents) {
-        const uint32_t c = cell[off + k];
-        const uint32_t tx = (c >> 10) % (uint32_t)tiles_x;
-        p_cell[o] = (tx << 10) | (c & 1023u); p_id[o] = id[off + k]; p_energy[o] = energy[off + k];
+  static size_t smem_bytes() { return (size_t)(TILE_THREADS + 32 + 4) * 4; }
+  ABM_HD void operator()(uint32_t d, uint32_t* smem) const {
+    const int NT = TILE_THREADS, nsx = si.nsx, per = (nsx + NT - 1) / NT;
+    uint32_t* part = smem; uint32_t* part2 = smem + NT;
+    uint32_t* hdr_counts = (uint32_t*)msg[d];
+    double* p_energy = (double*)(msg[d] + hdr);
+    uint32_t* p_cell = (uint32_t*)(msg[d] + hdr + (uint64_t)cap * 8);
+    uint32_t* p_id = (uint32_t*)(msg[d] + hdr + (uint64_t)cap * 12);
+    uint8_t* p_state = msg[d] + hdr + (uint64_t)cap * 16;
+    ABM_CTA_FOR(t, NT) {
+      uint32_t sum = 0;
+      for (int i = t * per; i < (t + 1) * per && i < nsx; ++i) { const uint32_t c = si.cnt[(uint32_t)row[d] * (uint32_t)nsx + (uint32_t)i]; hdr_counts[i] = c; sum += c; }
+      part[t] = sum;
+      if (t == 0) hdr_counts[nsx] = 0;
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) { if (t < NT / 32) { uint32_t q = 0; for (int k = 0; k < 32; ++k) q += part[32 * t + k]; part2[t] = q; } }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) {
+      uint32_t o = chunk_prefix(part, part2, t);
+      for (int i = t * per; i < (t + 1) * per && i < nsx; ++i) {
+        const uint32_t sub = (uint32_t)row[d] * (uint32_t)nsx + (uint32_t)i, off = si.off[sub], cnt = si.cnt[sub];
+        pre[d][i] = o;
+        if (o + cnt > cap) { atomic_or(err, ERR_STRIP_CAP); o += cnt; continue; }
+        for (uint32_t k = 0; k < cnt; ++k, ++o) {
+          const uint32_t c = cell[off + k];
+          const uint32_t tx = (c >> 10) % (uint32_t)tiles_x;
+          p_cell[o] = (tx << 10) | (c & 1023u); p_id[o] = id[off + k]; p_energy[o] = energy[off + k]; p_state[o] = state[off + k];
+        }
       }
-      p_state[o] = state[off + k];
+      if (t == NT - 1) pre[d][nsx] = o; /* total: the last chunk ends the row */
     }
   }
 };
-/* the received row becomes a ghost sub-tile row at a fixed place behind the own agents */
-struct UnpackRowBody {
-  int32_t row, nsx; uint32_t tile_row_base; /* (ghost tile row * tiles_x) << 10 */
-  uint32_t base, cap;
-  const uint32_t* counts; const uint32_t* prefix;
-  const uint32_t* p_cell; const uint32_t* p_id; const double* p_energy; const uint8_t* p_state;
+
+/* E1, receiver side, CTA d (0: from the previous strip -> ghost row above, 1: from the next -> ghost row below) */
+struct StripUnpackCta {
+  int32_t row[2], nsx; uint32_t tile_row_base[2]; uint32_t base[2], cap;
+  const uint8_t* msg[2]; uint32_t* pre[2]; uint64_t hdr;
   uint32_t* sub_off; uint32_t* sub_cnt;
   uint32_t* cell; uint32_t* id; double* energy; uint8_t* state;
   uint32_t* err;
-  ABM_HD void operator()(uint64_t i) const {
-    const uint32_t sub = (uint32_t)row * (uint32_t)nsx + (uint32_t)i, cnt = counts[i], o = prefix[i];
-    if (o + cnt > cap) { atomic_or(err, ERR_STRIP_CAP); sub_off[sub] = base; sub_cnt[sub] = 0; return; }
-    sub_off[sub] = base + o; sub_cnt[sub] = cnt;
-    for (uint32_t k = 0; k < cnt; ++k) {
-      cell[base + o + k] = p_cell[o + k] + tile_row_base; id[base + o + k] = p_id[o + k];
-      energy[base + o + k] = p_energy[o + k]; state[base + o + k] = p_state[o + k];
+  static size_t smem_bytes() { return (size_t)(TILE_THREADS + 32 + 4) * 4; }
+  ABM_HD void operator()(uint32_t d, uint32_t* smem) const {
+    const int NT = TILE_THREADS, per = (nsx + NT - 1) / NT;
+    uint32_t* part = smem; uint32_t* part2 = smem + NT;
+    const uint32_t* counts = (const uint32_t*)msg[d];
+    const double* p_energy = (const double*)(msg[d] + hdr);
+    const uint32_t* p_cell = (const uint32_t*)(msg[d] + hdr + (uint64_t)cap * 8);
+    const uint32_t* p_id = (const uint32_t*)(msg[d] + hdr + (uint64_t)cap * 12);
+    const uint8_t* p_state = msg[d] + hdr + (uint64_t)cap * 16;
+    ABM_CTA_FOR(t, NT) {
+      uint32_t sum = 0;
+      for (int i = t * per; i < (t + 1) * per && i < nsx; ++i) sum += counts[i];
+      part[t] = sum;
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) { if (t < NT / 32) { uint32_t q = 0; for (int k = 0; k < 32; ++k) q += part[32 * t + k]; part2[t] = q; } }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) {
+      uint32_t o = chunk_prefix(part, part2, t);
+      for (int i = t * per; i < (t + 1) * per && i < nsx; ++i) {
+        const uint32_t sub = (uint32_t)row[d] * (uint32_t)nsx + (uint32_t)i, cnt = counts[i];
+        pre[d][i] = o;
+        if (o + cnt > cap) { atomic_or(err, ERR_STRIP_CAP); sub_off[sub] = base[d]; sub_cnt[sub] = 0; o += cnt; continue; }
+        sub_off[sub] = base[d] + o; sub_cnt[sub] = cnt;
+        for (uint32_t k = 0; k < cnt; ++k, ++o) {
+          cell[base[d] + o] = p_cell[o] + tile_row_base[d]; id[base[d] + o] = p_id[o];
+          energy[base[d] + o] = p_energy[o]; state[base[d] + o] = p_state[o];
+        }
+      }
+      if (t == NT - 1) pre[d][nsx] = o;
     }
   }
 };
-/* decisions are unique and final: a ghost copy keeps what it already settled locally, the owner's decision wins otherwise */
-struct MergeStateBody {
-  const uint8_t* incoming; uint8_t* state; uint32_t base; const uint32_t* total; /* device-side number of ghost agents */
-  ABM_HD void operator()(uint64_t i) const {
-    if (i >= *total) return;
-    const uint8_t in = incoming[i];
-    if ((in & ST_DECIDED) || !(state[base + i] & ST_DECIDED)) state[base + i] = in;
+
+/* E2: the decision bytes of both boundary rows, in the order of E1 (one thread per sub-tile, 2 nsx threads) */
+struct PackStatesBody {
+  SubIndex si; int32_t row[2]; uint32_t cap;
+  const uint8_t* state; const uint32_t* pre[2]; uint8_t* out[2];
+  ABM_HD void operator()(uint64_t w) const {
+    const int d = w >= (uint64_t)si.nsx ? 1 : 0;
+    const uint32_t i = (uint32_t)(w - (uint64_t)d * si.nsx);
+    const uint32_t sub = (uint32_t)row[d] * (uint32_t)si.nsx + i, off = si.off[sub], cnt = si.cnt[sub];
+    uint32_t o = pre[d][i];
+    if (o + cnt > cap) return; /* flagged by the agent exchange */
+    for (uint32_t k = 0; k < cnt; ++k, ++o) out[d][o] = state[off + k];
   }
 };
+/* decisions are unique and final: a ghost copy keeps what it already settled locally, the owner's decision wins otherwise */
+struct MergeStatesBody {
+  const uint8_t* incoming[2]; uint8_t* state; uint32_t base[2], cap; const uint32_t* total[2]; int32_t present[2];
+  ABM_HD void operator()(uint64_t w) const {
+    const int d = w >= cap ? 1 : 0;
+    const uint32_t i = (uint32_t)(w - (uint64_t)d * cap);
+    if (!present[d] || i >= *total[d]) return;
+    const uint8_t in = incoming[d][i];
+    if ((in & ST_DECIDED) || !(state[base[d] + i] & ST_DECIDED)) state[base[d] + i] = in;
+  }
+};
+
 /* per-tick figures every rank needs from every rank, summed by one all-reduce (one-hot slots):
  * [0] open agents (all ranks), [1 + r] open agents of rank r, [1 + P + r] reproducing agents, [1 + 2P + r] largest boundary row */
 struct StripStatsBody {
