@@ -31,7 +31,7 @@ namespace abm {
 
 enum { SUB = 8, CORE = 32, HALO = 8, WIN = CORE + 2 * HALO, MAX_RUNS = 36, TILE_THREADS = 256, AGENT_THREADS = 32 };
 enum { NONE32 = 0xFFFFFFFFu };
-enum { ULIST_CAP = 512, ARRIVE_CAP = 768, RUNOF_CAP = 2048, RUNTABLE_WORDS = 4 * MAX_RUNS + 1 + RUNOF_CAP / 4 }; /* shared-memory work lists of a core; larger populations take the streaming code */
+enum { ULIST_CAP = 1024, ARRIVE_CAP = 768, RUNOF_CAP = 2048, RUNTABLE_WORDS = 4 * MAX_RUNS + 1 + RUNOF_CAP / 4 }; /* shared-memory work lists of a core; larger populations take the streaming code */
 
 struct SubIndex {
   const uint32_t* off; /* first agent of the sub-tile's run */
@@ -249,7 +249,7 @@ struct ResolveWindow {
   uint32_t* out_count;
 
   static size_t smem_bytes(int wx, int wy) { return (size_t)(3 * wx * wy + RUNTABLE_WORDS + 8) * 4; }
-  static size_t smem_bytes_core() { return (size_t)(4 * WIN * WIN + 7 * ULIST_CAP + RUNTABLE_WORDS + 16) * 4; }
+  static size_t smem_bytes_core() { return (size_t)(4 * WIN * WIN + 3 * ULIST_CAP + RUNTABLE_WORDS + 16) * 4; }
 
   /* Core window with the undecided agents held in a shared-memory work list: each round touches only what is still
    * open.  min_new only ever gains entries (decisions are final), min_maybe is rebuilt per round from the list (double
@@ -262,20 +262,22 @@ struct ResolveWindow {
     uint32_t* max_old = smem;
     uint32_t* min_new = smem + cells;
     uint32_t* maybe[2] = {smem + 2 * cells, smem + 3 * cells};
-    uint32_t* lst = smem + 4 * cells; /* two lists x {agent index, id, x | y << 8 | state << 16} */
-    uint32_t* l_a[2] = {lst, lst + 3 * ULIST_CAP};
-    uint32_t* l_id[2] = {lst + ULIST_CAP, lst + 4 * ULIST_CAP};
-    uint32_t* l_xs[2] = {lst + 2 * ULIST_CAP, lst + 5 * ULIST_CAP};
-    uint32_t* best = lst + 6 * ULIST_CAP; /* per gregarious task: min over box cells of (visiting rank << 1 | only-maybe) */
+    /* one work list, never compacted: `ifempty` walkers from the front, gregarious agents from the back (each kind is
+     * then evaluated by full warps; their code paths differ by an order of magnitude in length).  Entry = agent index,
+     * id, and a word  best:9 | done:1 | state:8 | y:6 | x:6  — `best` is the running minimum of the gregarious search
+     * (visiting rank << 1 | only-maybe), in the top bits so that atomicMin on the word orders by it. */
+    uint32_t* l_a = smem + 4 * cells;
+    uint32_t* l_id = l_a + ULIST_CAP;
+    uint32_t* l_xs = l_id + ULIST_CAP;
     RunTable rt;
-    rt.bind(lst + 7 * ULIST_CAP);
-    uint32_t* cnt = lst + 7 * ULIST_CAP + RUNTABLE_WORDS; /* [0],[1] walker list lengths, [5],[6] gregarious list lengths, [2] progress,
-                                               * [3] open agents of the core, [4] overflow, [7] entries listed at load */
+    rt.bind(l_xs + ULIST_CAP);
+    uint32_t* cnt = l_xs + ULIST_CAP + RUNTABLE_WORDS; /* [0] walkers, [5] gregarious, [4] overflow, [7] listed,
+                                                        * [8 + 2p], [9 + 2p] progress / open agents of the core, round parity p */
+    const uint32_t XS_DONE = 1u << 20, XS_BEST_NONE = 0x1FFu << 21, XS_LOW = (1u << 21) - 1;
 
     ABM_CTA_FOR(t, NT) {
       rt.load(t, NT, nruns, w, v.g, si);
       for (int c = t; c < cells; c += NT) { max_old[c] = 0u; min_new[c] = NONE32; maybe[0][c] = NONE32; maybe[1][c] = NONE32; }
-      for (int u = t; u < ULIST_CAP; u += NT) best[u] = NONE32;
       if (t < 16) cnt[t] = 0;
     }
     ABM_CTA_SYNC();
@@ -284,8 +286,6 @@ struct ResolveWindow {
     ABM_CTA_FOR(t, NT) { rt.expand(t, NT, nruns); }
     ABM_CTA_SYNC();
     const uint32_t M = rt.prefix[nruns];
-    /* work-list layout: `ifempty` walkers fill a list from the front, gregarious agents from the back, so that each
-     * kind is evaluated by full warps (their code paths differ by two orders of magnitude in length) */
     ABM_CTA_FOR(t, NT) {
       for (uint32_t m0 = (uint32_t)t; m0 < M; m0 += 3u * (uint32_t)NT) {
        int rr[3]; uint32_t aa[3], cc[3], ii[3]; uint8_t ss[3];
@@ -298,7 +298,6 @@ struct ResolveWindow {
        }
        for (int j = 0; j < 3; ++j) {
         if (rr[j] < 0) continue;
-        const uint32_t a = aa[j];
         int x, y;
         if (!rt.locate(w, rr[j], cc[j], x, y)) continue;
         const uint32_t id = ii[j];
@@ -309,53 +308,51 @@ struct ResolveWindow {
         const uint32_t k = smem_add(&cnt[greg ? 5 : 0], 1u);
         if (smem_add(&cnt[7], 1u) >= ULIST_CAP) { cnt[4] = 1; continue; }
         const uint32_t slot = greg ? ULIST_CAP - 1 - k : k;
-        l_a[0][slot] = a; l_id[0][slot] = id; l_xs[0][slot] = (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)st << 16);
+        l_a[slot] = aa[j]; l_id[slot] = id; l_xs[slot] = (uint32_t)x | ((uint32_t)y << 6) | ((uint32_t)st << 12) | XS_BEST_NONE;
         if (!greg) contribute_maybe(maybe[0], w, id, x, y, st);
        }
       }
     }
     ABM_CTA_SYNC();
     if (cnt[4]) return false;
+    const uint32_t nc = cnt[0], ng = cnt[5];
     ABM_CTA_FOR(t, NT) { /* the gregarious agents' eight candidate cells, by full warps */
-      const uint32_t ng0 = cnt[5];
-      for (uint32_t u = (uint32_t)t; u < ng0; u += (uint32_t)NT) {
-        const uint32_t e = ULIST_CAP - 1 - u, xs = l_xs[0][e];
-        contribute_maybe(maybe[0], w, l_id[0][e], (int)(xs & 0xFF), (int)((xs >> 8) & 0xFF), (uint8_t)(xs >> 16));
+      for (uint32_t u = (uint32_t)t; u < ng; u += (uint32_t)NT) {
+        const uint32_t e = ULIST_CAP - 1 - u, xs = l_xs[e];
+        contribute_maybe(maybe[0], w, l_id[e], (int)(xs & 63), (int)((xs >> 6) & 63), (uint8_t)(xs >> 12));
       }
     }
     ABM_CTA_SYNC();
-    /* Rounds, two barriers each.  P1: walkers are evaluated, gregarious agents scanned.  P2: gregarious agents draw and
-     * publish; the buffers of the round after next are cleared.  Counters live in slots that alternate with the round's
-     * parity so that nobody resets what others still read.  cnt: [0],[1] walker list lengths, [5],[6] gregarious list
-     * lengths, [8 + 2p], [9 + 2p] progress / open agents of the core for round parity p. */
+    /* Rounds, two barriers each.  P1: open walkers are evaluated, open gregarious agents searched.  P2: gregarious agents
+     * draw and publish; the buffer this round read is cleared for the round after next.  min_new only gains entries
+     * (decisions are final); min_maybe is rebuilt every round from the entries still open (double buffered). */
     const int side = 2 * v.p.r + 1, box = side * side;
     int cur = 0;
     for (int round = 0; round < max_rounds; ++round) {
-      const uint32_t nc = cnt[cur], ng = cnt[5 + cur];
-      if (nc + ng == 0) break;
       uint32_t* flag = cnt + 8 + 2 * (round & 1);
       uint32_t* flag_next = cnt + 8 + 2 * ((round + 1) & 1);
       Summaries s;
       s.max_old = max_old; s.min_new = min_new; s.min_maybe = maybe[cur];
       ABM_CTA_FOR(t, NT) {
         for (uint32_t u = (uint32_t)t; u < nc; u += (uint32_t)NT) { /* `ifempty` walkers: three loads and a compare */
-          const uint32_t a = l_a[cur][u], id = l_id[cur][u], xs = l_xs[cur][u];
-          const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
-          const uint8_t st = (uint8_t)(xs >> 16);
+          const uint32_t xs = l_xs[u];
+          if (xs & XS_DONE) continue;
+          const uint32_t id = l_id[u];
+          const int x = (int)(xs & 63), y = (int)((xs >> 6) & 63);
+          const uint8_t st = (uint8_t)(xs >> 12);
           uint8_t nst = st;
           if (evaluate(v, s, w, id, x, y, st, nst) == EV_DECIDED) {
-            v.state[a] = nst;
+            v.state[l_a[u]] = nst;
             contribute_final(min_new, w, id, x, y, nst);
+            l_xs[u] = xs | XS_DONE;
             flag[0] = 1;
           } else {
-            const uint32_t slot = smem_add(&cnt[cur ^ 1], 1u);
-            l_a[cur ^ 1][slot] = a; l_id[cur ^ 1][slot] = id; l_xs[cur ^ 1][slot] = xs;
             contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
             if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&flag[1], 1u);
           }
         }
         /* gregarious closest-neighbour search: one warp per agent, one lane per box cell; the first cell in visiting
-         * order that is occupied or unknown wins through a shared-memory min */
+         * order that is occupied or unknown wins through a shared-memory min on the entry's top bits */
         int rel[8]; /* this lane's box cells (visiting ranks lane, lane + 32, ...) as offsets inside the window */
         if (ng > 0) {
           for (int j = 0; j < 8 && (t & 31) + 32 * j < box; ++j) {
@@ -364,56 +361,57 @@ struct ResolveWindow {
           }
         }
         for (uint32_t task = (uint32_t)t >> 5; task < ng; task += (uint32_t)NT >> 5) {
-          const uint32_t e = ULIST_CAP - 1 - task, xs = l_xs[cur][e], id = l_id[cur][e];
-          const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
+          const uint32_t e = ULIST_CAP - 1 - task, xs = l_xs[e];
+          if (xs & XS_DONE) continue;
+          const uint32_t id = l_id[e], low = xs & XS_LOW;
+          const int x = (int)(xs & 63), y = (int)((xs >> 6) & 63);
           if (x - v.p.r < 1 || x + v.p.r > WIN - 2 || y - v.p.r < 1 || y + v.p.r > WIN - 2) continue; /* box not fully trusted */
           const int base = y * WIN + x;
           for (int j = 0; j < 8 && (t & 31) + 32 * j < box; ++j) {
             const int c = base + rel[j];
             const uint32_t q = (uint32_t)((t & 31) + 32 * j);
-            if (s.occupied(c, id)) smem_min(&best[task], q << 1);
-            else if (s.unknown(c, id)) smem_min(&best[task], (q << 1) | 1u);
+            if (s.occupied(c, id)) smem_min(&l_xs[e], ((q << 1) << 21) | low);
+            else if (s.unknown(c, id)) smem_min(&l_xs[e], (((q << 1) | 1u) << 21) | low);
           }
         }
       }
       ABM_CTA_SYNC();
-      ABM_CTA_FOR(t, NT) { /* one thread per gregarious agent: draw and publish, or carry over */
+      ABM_CTA_FOR(t, NT) { /* one thread per open gregarious agent: draw and publish, or stay open */
         for (uint32_t u = (uint32_t)t; u < ng; u += (uint32_t)NT) {
-          const uint32_t e = ULIST_CAP - 1 - u, xs = l_xs[cur][e], id = l_id[cur][e], a = l_a[cur][e];
-          const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
-          const uint8_t st = (uint8_t)(xs >> 16);
+          const uint32_t e = ULIST_CAP - 1 - u, xs = l_xs[e];
+          if (xs & XS_DONE) continue;
+          const uint32_t id = l_id[e], b = xs >> 21;
+          const int x = (int)(xs & 63), y = (int)((xs >> 6) & 63);
+          const uint8_t st = (uint8_t)(xs >> 12);
           const bool inside = !(x - v.p.r < 1 || x + v.p.r > WIN - 2 || y - v.p.r < 1 || y + v.p.r > WIN - 2);
-          const uint32_t b = best[u];
-          best[u] = NONE32; /* ready for the next round */
-          if (inside && (b == NONE32 || !(b & 1u))) {
-            const uint8_t nst = greg_finish(v, id, st, b == NONE32 ? (int)GREG_NOBODY : (int)v.greg_order[b >> 1]);
-            v.state[a] = nst;
+          if (inside && (b == 0x1FFu || !(b & 1u))) {
+            const uint8_t nst = greg_finish(v, id, st, b == 0x1FFu ? (int)GREG_NOBODY : (int)v.greg_order[b >> 1]);
+            v.state[l_a[e]] = nst;
             contribute_final(min_new, w, id, x, y, nst);
+            l_xs[e] = xs | XS_DONE;
             flag[0] = 1;
           } else {
-            const uint32_t k = smem_add(&cnt[5 + (cur ^ 1)], 1u);
-            const uint32_t slot = ULIST_CAP - 1 - k;
-            l_a[cur ^ 1][slot] = a; l_id[cur ^ 1][slot] = id; l_xs[cur ^ 1][slot] = xs;
+            l_xs[e] = (xs & XS_LOW) | XS_BEST_NONE; /* search again next round */
             contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
             if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&flag[1], 1u);
           }
         }
         /* what this round read is dead now: make it the clean target of the next round */
         for (int c = t; c < cells; c += NT) maybe[cur][c] = NONE32;
-        if (t == 0) { cnt[cur] = 0; cnt[5 + cur] = 0; flag_next[0] = 0; flag_next[1] = 0; }
+        if (t == 0) { flag_next[0] = 0; flag_next[1] = 0; }
       }
       ABM_CTA_SYNC();
       cur ^= 1;
       if (flag[1] == 0 || flag[0] == 0) break;
     }
     ABM_CTA_SYNC();
-    const uint32_t nc = cnt[cur], ng = cnt[5 + cur];
     ABM_CTA_FOR(t, NT) { /* the core's agents that stay open go to the per-agent windows */
       for (uint32_t u = (uint32_t)t; u < nc + ng; u += (uint32_t)NT) {
         const uint32_t e = u >= nc ? ULIST_CAP - 1 - (u - nc) : u;
-        const uint32_t xs = l_xs[cur][e];
-        const int x = (int)(xs & 0xFF), y = (int)((xs >> 8) & 0xFF);
-        if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) out[atomic_add(out_count, 1u)] = l_a[cur][e];
+        const uint32_t xs = l_xs[e];
+        if (xs & XS_DONE) continue;
+        const int x = (int)(xs & 63), y = (int)((xs >> 6) & 63);
+        if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) out[atomic_add(out_count, 1u)] = l_a[e];
       }
     }
     return true;
