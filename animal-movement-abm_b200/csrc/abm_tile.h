@@ -271,7 +271,7 @@ struct ResolveWindow {
     uint32_t* l_xs = l_id + ULIST_CAP;
     RunTable rt;
     rt.bind(l_xs + ULIST_CAP);
-    uint32_t* cnt = l_xs + ULIST_CAP + RUNTABLE_WORDS; /* [0] walkers, [5] gregarious, [4] overflow, [7] listed,
+    uint32_t* cnt = l_xs + ULIST_CAP + RUNTABLE_WORDS; /* [0] walkers, [5] gregarious,
                                                         * [8 + 2p], [9 + 2p] progress / open agents of the core, round parity p */
     const uint32_t XS_DONE = 1u << 20, XS_BEST_NONE = 0x1FFu << 21, XS_LOW = (1u << 21) - 1;
 
@@ -306,7 +306,7 @@ struct ResolveWindow {
         if (st & ST_DECIDED) { contribute_final(min_new, w, id, x, y, st); continue; }
         const bool greg = (st & ST_DIRMASK) == DIR_GREG;
         const uint32_t k = smem_add(&cnt[greg ? 5 : 0], 1u);
-        if (smem_add(&cnt[7], 1u) >= ULIST_CAP) { cnt[4] = 1; continue; }
+        if (k >= ULIST_CAP) continue; /* overflow: detected below from the two counters, the list is abandoned */
         const uint32_t slot = greg ? ULIST_CAP - 1 - k : k;
         l_a[slot] = aa[j]; l_id[slot] = id; l_xs[slot] = (uint32_t)x | ((uint32_t)y << 6) | ((uint32_t)st << 12) | XS_BEST_NONE;
         if (!greg) contribute_maybe(maybe[0], w, id, x, y, st);
@@ -314,7 +314,7 @@ struct ResolveWindow {
       }
     }
     ABM_CTA_SYNC();
-    if (cnt[4]) return false;
+    if (cnt[0] + cnt[5] > ULIST_CAP) return false; /* the two ends of the list met: take the streaming code */
     const uint32_t nc = cnt[0], ng = cnt[5];
     ABM_CTA_FOR(t, NT) { /* the gregarious agents' eight candidate cells, by full warps */
       for (uint32_t u = (uint32_t)t; u < ng; u += (uint32_t)NT) {
