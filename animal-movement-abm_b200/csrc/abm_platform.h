@@ -70,6 +70,9 @@ static inline uint32_t smem_min(uint32_t* p, uint32_t v) { uint32_t o = *p; if (
 static inline uint32_t smem_max(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
 static inline uint32_t smem_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 static inline uint32_t smem_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+/* minimum over the 32 lanes of a warp that all execute this call, folded into *dst; returns the minimum known to the
+ * caller (lanes run one after another here, so that is the running value) */
+static inline uint32_t warp_min_into(uint32_t* dst, uint32_t v, int /*lane*/) { if (v < *dst) *dst = v; return *dst; }
 
 template <class F>
 static inline void launch_cta(abm_stream_t, const F& f, uint64_t n_ctas, int /*threads*/, size_t smem_bytes) {
@@ -140,6 +143,12 @@ ABM_D uint32_t smem_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 ABM_D uint32_t smem_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
 ABM_D uint32_t smem_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 ABM_D uint32_t smem_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
+/* minimum over the 32 lanes of a warp that all execute this call (converged), folded into *dst by lane 0 */
+ABM_D uint32_t warp_min_into(uint32_t* dst, uint32_t v, int lane) {
+  const uint32_t m = __reduce_min_sync(0xffffffffu, v);
+  if (lane == 0 && m < *dst) *dst = m;
+  return m; /* the same value in every lane */
+}
 
 template <class F>
 __global__ void __launch_bounds__(256) k_cta(const F f) {

@@ -117,7 +117,7 @@ struct Summaries {
   uint32_t* max_old;
   uint32_t* min_new;
   uint32_t* min_maybe;
-  ABM_HD bool occupied(int c, uint32_t id) const { return max_old[c] > id || min_new[c] < id; }
+  ABM_HD bool occupied(int c, uint32_t id) const { const uint32_t a = max_old[c], b = min_new[c]; return (a > id) | (b < id); }
   ABM_HD bool unknown(int c, uint32_t id) const { return min_maybe[c] < id; }
 };
 
@@ -367,11 +367,16 @@ struct ResolveWindow {
           const int x = (int)(xs & 63), y = (int)((xs >> 6) & 63);
           if (x - v.p.r < 1 || x + v.p.r > WIN - 2 || y - v.p.r < 1 || y + v.p.r > WIN - 2) continue; /* box not fully trusted */
           const int base = y * WIN + x;
-          for (int j = 0; j < 8 && (t & 31) + 32 * j < box; ++j) {
-            const int c = base + rel[j];
+          uint32_t mine = NONE32; /* this lane's best candidate word; the box is visited 32 cells at a time, nearest first */
+          for (int j = 0; j < 8 && 32 * j < box; ++j) {
             const uint32_t q = (uint32_t)((t & 31) + 32 * j);
-            if (s.occupied(c, id)) smem_min(&l_xs[e], ((q << 1) << 21) | low);
-            else if (s.unknown(c, id)) smem_min(&l_xs[e], (((q << 1) | 1u) << 21) | low);
+            if ((int)q < box && mine == NONE32) {
+              const int c = base + rel[j];
+              if (s.occupied(c, id)) mine = ((q << 1) << 21) | low;
+              else if (s.unknown(c, id)) mine = (((q << 1) | 1u) << 21) | low;
+            }
+            const uint32_t m = warp_min_into(&l_xs[e], mine, t & 31);
+            if ((m >> 22) < 32u * (uint32_t)(j + 1)) break; /* nearer than every cell still to visit: done (warp-uniform) */
           }
         }
       }
