@@ -261,7 +261,8 @@ struct abm_handle {
   bool tile_mode = false;
   int32_t fixed_agent_rounds = 2; /* per-agent rounds enqueued without asking the host (ABM_AGENT_ROUNDS overrides) */
   uint64_t kf_grid = 1024;        /* CTAs of those launches: an upper bound learnt from the previous tick */
-  int32_t tile_rounds = 8; /* in-window rounds of the tile resolve kernel (ABM_TILE_ROUNDS overrides; tests use 1) */
+  int32_t tile_rounds = 8;
+  int32_t tile_margin = HALO;     /* halo cells actually taken into a core's window (ABM_TILE_MARGIN overrides) */ /* in-window rounds of the tile resolve kernel (ABM_TILE_ROUNDS overrides; tests use 1) */
   int32_t nsx = 0, nsy = 0;
   DevBuf sub_off[2], sub_cnt[2], birth_pos, birth_parent, ingest_sub;
   /* row strips: ring neighbours, transport, boundary-row staging ([0] = towards / from the previous strip, [1] = next) */
@@ -1066,7 +1067,7 @@ static int tick_tile(abm_handle* h) {
   if (n + h->n_ghost > 0) {
     if (needs_resolve) {
       ResolveWindow rw;
-      rw.v = v; rw.si = si; rw.mode = 0; rw.cores_x = h->g.nx / CORE; rw.core_y0 = h->g.own_lo / CORE; rw.max_rounds = h->tile_rounds; rw.nthreads = TILE_THREADS;
+      rw.v = v; rw.si = si; rw.mode = 0; rw.cores_x = h->g.nx / CORE; rw.core_y0 = h->g.own_lo / CORE; rw.max_rounds = h->tile_rounds; rw.nthreads = TILE_THREADS; rw.margin = std::max<int>(h->tile_margin, wt == ABM_RANDOM_WALK_GREGARIOUS ? std::min<int>(h->cfg.visual_distance + 1, HALO) : 2);
       rw.in = nullptr; rw.out = (uint32_t*)h->pend[0].p; rw.out_count = ctr + CTR_PEND_A;
       { ProfScope ps(h->prof, h->stream, "resolve_tiles", n); launch_cta(h->stream, rw, cores, TILE_THREADS, ResolveWindow::smem_bytes_core()); }
       if ((rc = check_launch(h, "tile resolve"))) return rc;
@@ -1102,7 +1103,7 @@ static int tick_tile(abm_handle* h) {
   auto launch_agents = [&](uint64_t grid, uint32_t* d_out) -> int { /* one Jacobi round of per-agent windows over pend[in] */
     ABM_CK(h, dev_memset(d_out, 0, sizeof(uint32_t), h->stream));
     ResolveWindow rw;
-    rw.v = v; rw.si = si; rw.mode = 1; rw.cores_x = 0; rw.core_y0 = 0; rw.max_rounds = 1; rw.nthreads = AGENT_THREADS;
+    rw.v = v; rw.si = si; rw.mode = 1; rw.cores_x = 0; rw.core_y0 = 0; rw.max_rounds = 1; rw.nthreads = AGENT_THREADS; rw.margin = HALO;
     rw.grid = (uint32_t)grid; rw.in = (const uint32_t*)h->pend[in].p; rw.in_count = ctr + (in ? CTR_PEND_B : CTR_PEND_A);
     rw.out = (uint32_t*)h->pend[in ^ 1].p; rw.out_count = d_out;
     { ProfScope ps(h->prof, h->stream, "resolve_agents", grid); launch_cta(h->stream, rw, grid, AGENT_THREADS, ResolveWindow::smem_bytes(2 * q + 1, 2 * q + 1)); }
@@ -1158,7 +1159,7 @@ static int tick_tile(abm_handle* h) {
     ct.cursor = ctr + CTR_CURSOR;
     ct.birth_pos = (uint32_t*)h->birth_pos.p; ct.birth_parent = (uint32_t*)h->birth_parent.p; ct.birth_count = ctr + CTR_BIRTHS;
     ct.birth_bits = h->strip ? nullptr : (uint32_t*)h->bits.p; /* strips rank the parents globally instead */
-    { ProfScope ps(h->prof, h->stream, "commit_tiles", n); launch_cta(h->stream, ct, cores, TILE_THREADS, CommitTile::smem_bytes()); }
+    { ProfScope ps(h->prof, h->stream, "commit_tiles", n); launch_cta(h->stream, ct, cores, COMMIT_THREADS, CommitTile::smem_bytes()); }
     if ((rc = check_launch(h, "tile commit"))) return rc;
   }
   if (h->strip && (rc = strip_birth_ids(h, birth_cap, nxt, ctr + CTR_BIRTH_TOTAL))) return rc;
@@ -1321,6 +1322,7 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
                              cfg->nx >= 2 * CORE && cfg->ny >= 2 * CORE);
   h->nsx = g.nx / SUB; h->nsy = g.ny / SUB;
   if (const char* ar = getenv("ABM_AGENT_ROUNDS")) { const int q = atoi(ar); if (q >= 0 && q <= 16) h->fixed_agent_rounds = q; }
+  if (const char* tm = getenv("ABM_TILE_MARGIN")) { const int q = atoi(tm); if (q >= 2 && q <= HALO) h->tile_margin = q; }
   if (const char* tr = getenv("ABM_TILE_ROUNDS")) { const int q = atoi(tr); if (q >= 1 && q <= 64) h->tile_rounds = q; }
   rc = 0;
   do {

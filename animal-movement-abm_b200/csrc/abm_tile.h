@@ -29,7 +29,7 @@
 
 namespace abm {
 
-enum { SUB = 8, CORE = 32, HALO = 8, WIN = CORE + 2 * HALO, MAX_RUNS = 36, TILE_THREADS = 256, AGENT_THREADS = 32 };
+enum { SUB = 8, CORE = 32, HALO = 8, WIN = CORE + 2 * HALO, MAX_RUNS = 36, TILE_THREADS = 256, COMMIT_THREADS = 128, AGENT_THREADS = 32 };
 enum { NONE32 = 0xFFFFFFFFu };
 enum { ULIST_CAP = 1024, ARRIVE_CAP = 768, RUNOF_CAP = 2048, RUNTABLE_WORDS = 4 * MAX_RUNS + 1 + RUNOF_CAP / 4 }; /* shared-memory work lists of a core; larger populations take the streaming code */
 
@@ -44,8 +44,9 @@ ABM_HD int floor_div8(int a) { return a >= 0 ? a >> 3 : -((-a + 7) >> 3); }
 /* a window of cells [ox, ox+wx) x [oy, oy+wy) in unwrapped coordinates and the sub-tile runs that cover it */
 struct Window {
   int ox, oy, wx, wy, ssx0, ssy0, nssx, nssy;
+  int tlo, thi; /* summaries are complete on cells [tlo, thi]^2 (window coordinates): every agent that can reach them was taken in */
   ABM_HD void set(int ox_, int oy_, int wx_, int wy_) {
-    ox = ox_; oy = oy_; wx = wx_; wy = wy_;
+    ox = ox_; oy = oy_; wx = wx_; wy = wy_; tlo = 1; thi = wx_ - 2;
     ssx0 = floor_div8(ox); ssy0 = floor_div8(oy);
     nssx = floor_div8(ox + wx - 1) - ssx0 + 1;
     nssy = floor_div8(oy + wy - 1) - ssy0 + 1;
@@ -180,7 +181,7 @@ enum { GREG_NOBODY = 252, GREG_PENDING = 253, GREG_OUTSIDE = 254 };
  * order.  Returns its box index, GREG_NOBODY, or why that cannot be known yet. */
 ABM_HD int greg_scan(const View& v, const Summaries& s, const Window& w, uint32_t id, int x, int y) {
   const int r = v.p.r, side = 2 * r + 1;
-  if (x - r < 1 || x + r > w.wx - 2 || y - r < 1 || y + r > w.wy - 2) return GREG_OUTSIDE;
+  if (x - r < w.tlo || x + r > w.thi || y - r < w.tlo || y + r > w.thi) return GREG_OUTSIDE;
   const int cells = side * side;
   for (int q = 0; q < cells; ++q) {
     const int c = (y + v.greg_dxy[2 * q + 1]) * w.wx + (x + v.greg_dxy[2 * q]);
@@ -218,7 +219,7 @@ ABM_HD int evaluate(const View& v, const Summaries& s, const Window& w, uint32_t
     int dx, dy;
     off8(dir, dx, dy);
     const int tx = x + dx, ty = y + dy;
-    if (tx < 1 || tx > w.wx - 2 || ty < 1 || ty > w.wy - 2) return EV_OUTSIDE;
+    if (tx < w.tlo || tx > w.thi || ty < w.tlo || ty > w.thi) return EV_OUTSIDE;
     const int t = ty * w.wx + tx;
     if (s.occupied(t, id)) { out = (uint8_t)(st | ST_DECIDED); return EV_DECIDED; }
     if (s.unknown(t, id)) return EV_PENDING;
@@ -242,6 +243,7 @@ struct ResolveWindow {
   View v;
   SubIndex si;
   int32_t mode, cores_x, core_y0, max_rounds, nthreads;
+  int32_t margin;           /* mode 0: agents farther than this from the core are left out of the window (<= HALO) */
   uint32_t grid;            /* mode 1: number of CTAs launched */
   const uint32_t* in;
   const uint32_t* in_count; /* mode 1: device-side length of `in` */
@@ -258,6 +260,8 @@ struct ResolveWindow {
     Window w;
     const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) + core_y0;
     w.set(cx * CORE - HALO, cy * CORE - HALO, WIN, WIN);
+    const int in_lo = HALO - margin, in_hi = HALO + CORE + margin; /* agents taken in: [in_lo, in_hi)^2 */
+    w.tlo = in_lo + 1; w.thi = in_hi - 2;
     const int cells = WIN * WIN, nruns = w.runs(), NT = TILE_THREADS;
     uint32_t* max_old = smem;
     uint32_t* min_new = smem + cells;
@@ -300,6 +304,7 @@ struct ResolveWindow {
         if (rr[j] < 0) continue;
         int x, y;
         if (!rt.locate(w, rr[j], cc[j], x, y)) continue;
+        if (x < in_lo || x >= in_hi || y < in_lo || y >= in_hi) continue;
         const uint32_t id = ii[j];
         const uint8_t st = ss[j];
         smem_max(&max_old[y * WIN + x], id);
@@ -365,7 +370,7 @@ struct ResolveWindow {
           if (xs & XS_DONE) continue;
           const uint32_t id = l_id[e], low = xs & XS_LOW;
           const int x = (int)(xs & 63), y = (int)((xs >> 6) & 63);
-          if (x - v.p.r < 1 || x + v.p.r > WIN - 2 || y - v.p.r < 1 || y + v.p.r > WIN - 2) continue; /* box not fully trusted */
+          if (x - v.p.r < w.tlo || x + v.p.r > w.thi || y - v.p.r < w.tlo || y + v.p.r > w.thi) continue; /* box not fully trusted */
           const int base = y * WIN + x;
           uint32_t mine = NONE32; /* this lane's best candidate word; the box is visited 32 cells at a time, nearest first */
           for (int j = 0; j < 8 && 32 * j < box; ++j) {
@@ -388,7 +393,7 @@ struct ResolveWindow {
           const uint32_t id = l_id[e], b = xs >> 21;
           const int x = (int)(xs & 63), y = (int)((xs >> 6) & 63);
           const uint8_t st = (uint8_t)(xs >> 12);
-          const bool inside = !(x - v.p.r < 1 || x + v.p.r > WIN - 2 || y - v.p.r < 1 || y + v.p.r > WIN - 2);
+          const bool inside = !(x - v.p.r < w.tlo || x + v.p.r > w.thi || y - v.p.r < w.tlo || y + v.p.r > w.thi);
           if (inside && (b == 0x1FFu || !(b & 1u))) {
             const uint8_t nst = greg_finish(v, id, st, b == 0x1FFu ? (int)GREG_NOBODY : (int)v.greg_order[b >> 1]);
             v.state[l_a[e]] = nst;
@@ -539,13 +544,13 @@ struct CommitTile {
   uint32_t* cursor;                     /* next free slot of the output SoA */
   uint32_t* birth_pos; uint32_t* birth_parent; uint32_t* birth_count; uint32_t* birth_bits;
 
-  static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 16 * 3 + RUNTABLE_WORDS + 8 + 3 * ARRIVE_CAP + 16 * (TILE_THREADS / 32)) * 4; }
+  static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 16 * 3 + RUNTABLE_WORDS + 8 + 3 * ARRIVE_CAP + 16 * (COMMIT_THREADS / 32)) * 4; }
 
   ABM_HD void operator()(uint32_t cta, uint32_t* smem) const {
     const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) + core_y0;
     Window w;
     w.set(cx * CORE - HALO, cy * CORE - HALO, WIN, WIN);
-    const int nruns = w.runs(), NT = TILE_THREADS;
+    const int nruns = w.runs(), NT = COMMIT_THREADS;
     uint32_t* min_all = smem;                         /* lowest id arriving on each core cell: the one that eats */
     uint8_t* grass = (uint8_t*)(smem + CORE * CORE);  /* the core's grass tile */
     uint32_t* counts = smem + CORE * CORE + CORE * CORE / 4; /* per sub-tile of the core: arrivals, base, cursor */
@@ -565,7 +570,7 @@ struct CommitTile {
       rt.load(t, NT, nruns, w, v.g, si);
       for (int c = t; c < CORE * CORE; c += NT) min_all[c] = NONE32;
       for (int c = t; c < CORE * CORE / 4; c += NT) ((uint32_t*)grass)[c] = gtile[c];
-      if (t < 16 * (TILE_THREADS / 32)) wcounts[t] = 0;
+      if (t < 16 * (COMMIT_THREADS / 32)) wcounts[t] = 0;
       if (t < 8) misc[t] = 0;
     }
     ABM_CTA_SYNC();
@@ -596,7 +601,7 @@ struct CommitTile {
     }
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, NT) {
-      if (t < 16) { uint32_t c = 0; for (int q = 0; q < TILE_THREADS / 32; ++q) c += wcounts[q * 16 + t]; counts[t] = c; }
+      if (t < 16) { uint32_t c = 0; for (int q = 0; q < COMMIT_THREADS / 32; ++q) c += wcounts[q * 16 + t]; counts[t] = c; }
     }
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, NT) {
