@@ -795,7 +795,8 @@ static NcclApi g_nccl;
 #endif
 
 /* boundary exchange with the ring neighbours; all pointers are device memory of this handle */
-static int comm_sendrecv(abm_handle* h, const void* to_prev, uint64_t b_tp, const void* to_next, uint64_t b_tn, void* from_prev, uint64_t b_fp, void* from_next, uint64_t b_fn) {
+static int comm_sendrecv(abm_handle* h, const void* to_prev, uint64_t b_tp, const void* to_next, uint64_t b_tn, void* from_prev, uint64_t b_fp, void* from_next, uint64_t b_fn,
+                         unsigned long long* d_allreduce = nullptr, int n_allreduce = 0) {
   if (!h->has_prev) { b_tp = 0; b_fp = 0; }
   if (!h->has_next) { b_tn = 0; b_fn = 0; }
   if (h->n_ranks == 1) { /* a ring of one: my first rows are the ghost rows below my last rows and vice versa */
@@ -808,7 +809,8 @@ static int comm_sendrecv(abm_handle* h, const void* to_prev, uint64_t b_tp, cons
 #ifndef ABM_EMU
   if (h->nccl_comm) {
     ncclComm_t c = (ncclComm_t)h->nccl_comm;
-    ABM_NCCL(h, g_nccl.GroupStart());
+    ABM_NCCL(h, g_nccl.GroupStart()); /* one launch: the ring exchange and, when asked, the all-reduce of the device counters */
+    if (d_allreduce) ABM_NCCL(h, g_nccl.AllReduce(d_allreduce, d_allreduce, (size_t)n_allreduce, ncclUint64, ncclSum, c, h->stream));
     if (b_tp) ABM_NCCL(h, g_nccl.Send(to_prev, b_tp, ncclUint8, prev, c, h->stream));
     if (b_tn) ABM_NCCL(h, g_nccl.Send(to_next, b_tn, ncclUint8, next, c, h->stream));
     if (b_fn) ABM_NCCL(h, g_nccl.Recv(from_next, b_fn, ncclUint8, next, c, h->stream));
@@ -930,7 +932,7 @@ static int strip_exchange_agents(abm_handle* h) {
 }
 
 /* E2: the decision bytes of the same boundary rows (same order), merged into the ghost copies */
-static int strip_exchange_states(abm_handle* h) {
+static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce = nullptr, int n_allreduce = 0) {
   int rc;
   const int cur = h->cur, nsx = h->nsx;
   const uint64_t cap = h->bcap;
@@ -940,7 +942,7 @@ static int strip_exchange_states(abm_handle* h) {
   for (int d = 0; d < 2; ++d) { pk.pre[d] = (const uint32_t*)h->sx_pre[d].p; pk.out[d] = (uint8_t*)h->sx_st[d].p; }
   launch_foreach(h->stream, pk, 2 * (uint64_t)nsx);
   { ProfScope ps(h->prof, h->stream, "decision_exchange", 2 * cap);
-    if ((rc = comm_sendrecv(h, h->sx_st[0].p, cap, h->sx_st[1].p, cap, h->rx_st[0].p, cap, h->rx_st[1].p, cap))) return rc; }
+    if ((rc = comm_sendrecv(h, h->sx_st[0].p, cap, h->sx_st[1].p, cap, h->rx_st[0].p, cap, h->rx_st[1].p, cap, d_allreduce, n_allreduce))) return rc; }
   MergeStatesBody mg;
   for (int d = 0; d < 2; ++d) {
     mg.incoming[d] = (const uint8_t*)h->rx_st[d].p; mg.base[d] = (uint32_t)(h->n + (uint64_t)d * cap);
@@ -953,7 +955,7 @@ static int strip_exchange_states(abm_handle* h) {
 }
 
 /* the figures of StripStatsBody from every rank: one all-reduce on device data, one read-back */
-static int strip_stats(abm_handle* h, const uint32_t* d_pending, std::vector<uint64_t>& out) {
+static int strip_stats(abm_handle* h, const uint32_t* d_pending, std::vector<uint64_t>& out, bool with_state_exchange = false) {
   int rc;
   const int P = h->n_ranks, nv = 1 + 3 * P;
   uint32_t* ctr = (uint32_t*)h->counters.p;
@@ -966,11 +968,13 @@ static int strip_stats(abm_handle* h, const uint32_t* d_pending, std::vector<uin
   out.assign((size_t)nv, 0);
 #ifndef ABM_EMU
   if (h->nccl_comm) {
-    ABM_NCCL(h, g_nccl.AllReduce(d, d, (size_t)nv, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+    if (with_state_exchange) { if ((rc = strip_exchange_states(h, d, nv))) return rc; } /* same NCCL group as the decision bytes */
+    else ABM_NCCL(h, g_nccl.AllReduce(d, d, (size_t)nv, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
     ABM_CK(h, copy_d2h(out.data(), d, (size_t)nv * 8, h->stream));
     return 0;
   }
 #endif
+  if (with_state_exchange && (rc = strip_exchange_states(h))) return rc;
   ABM_CK(h, copy_d2h(out.data(), d, (size_t)nv * 8, h->stream));
   if ((rc = comm_allreduce_u64(h, out.data(), nv))) return rc;
   return 0;
@@ -1087,7 +1091,7 @@ static int tick_tile(abm_handle* h) {
       birth_flags = h->h_counters[CTR_BIRTH_FLAGS];
       return 0;
     }
-    int r = strip_stats(h, d_pending, stats);
+    int r = strip_stats(h, d_pending, stats, needs_resolve);
     if (r) return r;
     global_cnt = stats[0];
     cnt = stats[1 + h->my_rank];
@@ -1126,8 +1130,8 @@ static int tick_tile(abm_handle* h) {
   {
     int stalls = 0;
     while (true) { /* chains that left their window: one small window per agent, Jacobi rounds */
-      /* strips: the owners' decisions reach the ghost copies; every rank stays in the loop until all ranks are done */
-      if (h->strip && needs_resolve && (rc = strip_exchange_states(h))) return rc;
+      /* strips: take_stats also carried the owners' decisions to the ghost copies; every rank stays in the loop until all
+       * ranks are done */
       if (global_cnt == 0) break;
       uint32_t* d_out = ctr + (in ? CTR_PEND_A : CTR_PEND_B);
       if (cnt > 0) { if ((rc = launch_agents(cnt, d_out))) return rc; }
