@@ -234,7 +234,7 @@ struct ProfScope {
 };
 
 enum { CTR_BIRTH_TOTAL = 12, CTR_PEND_A = 0, CTR_PEND_B = 1, CTR_BIRTHS = 2, CTR_ERR = 3, CTR_RED_LO = 4, CTR_RED_HI = 5, CTR_PLANS = 6, CTR_ROUTE_SLOTS = 7,
-       CTR_EXP_LO = 8, CTR_EXP_HI = 9, CTR_CURSOR = 10, CTR_BIRTH_FLAGS = 11, CTR_PEND_FIRST = 13, CTR_WORDS = 16 };
+       CTR_EXP_LO = 8, CTR_EXP_HI = 9, CTR_CURSOR = 10, CTR_BIRTH_FLAGS = 11, CTR_PEND_FIRST = 13, CTR_GO = 14, CTR_WORDS = 16 };
 
 }  // namespace
 
@@ -259,6 +259,8 @@ struct abm_handle {
   uint32_t as_gen = 0;
   /* tile path (abm_tile.h): sub-tile runs of the SoA (ping-pong with the SoA), offspring fix-up lists */
   bool tile_mode = false;
+  bool optimistic = true;         /* enqueue the commit behind a device-side guard instead of reading counters first (ABM_OPTIMISTIC=0 disables) */
+  uint64_t bf_est = 0;            /* expected upper bound of reproducing agents, learnt from the previous tick */
   int32_t fixed_agent_rounds = 2; /* per-agent rounds enqueued without asking the host (ABM_AGENT_ROUNDS overrides) */
   uint64_t kf_grid = 1024;        /* CTAs of those launches: an upper bound learnt from the previous tick */
   int32_t tile_rounds = 8;
@@ -1124,6 +1126,60 @@ static int tick_tile(abm_handle* h) {
       h->rounds += 1;
     }
   }
+  const int nxt = h->cur ^ 1;
+  const uint64_t words = bitmap_words(h->next_id);
+  /* commit + grass + re-grouping (+ offspring ids on one GPU); `go` = device flag checked by the kernels, or null */
+  auto commit_phase = [&](uint64_t bflags, const uint32_t* go) -> int {
+    const uint64_t arrivals_cap = h->strip ? 2 * h->bcap : 0; /* ghost agents (and their offspring) may land here */
+    int r;
+    if ((r = ensure_soa(h, nxt, n + bflags + 2 * arrivals_cap))) return r;
+    if ((r = ensure(h, h->birth_pos, (bflags + arrivals_cap + 1) * 4))) return r;
+    if ((r = ensure(h, h->birth_parent, (bflags + arrivals_cap + 1) * 4))) return r;
+    if (bflags > 0 || h->strip) {
+      if ((r = ensure(h, h->bits, (words + 4) * 4))) return r;
+      if (!h->strip) ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, h->stream));
+    }
+    CommitTile ct;
+    ct.v = v; ct.si = si; ct.cores_x = h->g.nx / CORE; ct.core_y0 = h->g.own_lo / CORE;
+    ct.out_cell = (uint32_t*)h->cell[nxt].p; ct.out_id = (uint32_t*)h->id[nxt].p; ct.out_energy = (double*)h->energy[nxt].p;
+    ct.new_off = (uint32_t*)h->sub_off[nxt].p; ct.new_cnt = (uint32_t*)h->sub_cnt[nxt].p;
+    ct.cursor = ctr + CTR_CURSOR;
+    ct.birth_pos = (uint32_t*)h->birth_pos.p; ct.birth_parent = (uint32_t*)h->birth_parent.p; ct.birth_count = ctr + CTR_BIRTHS;
+    ct.birth_bits = h->strip ? nullptr : (uint32_t*)h->bits.p; /* strips rank the parents globally instead */
+    ct.go = go;
+    { ProfScope ps(h->prof, h->stream, "commit_tiles", n); launch_cta(h->stream, ct, cores, COMMIT_THREADS, CommitTile::smem_bytes()); }
+    return check_launch(h, "tile commit");
+  };
+  auto finish_tick = [&](uint64_t n_new, uint64_t nb_total) -> int {
+    if (h->next_id + nb_total > 0xFFFFFFFFull) ABM_FAIL(h, ABM_E_CAPACITY, "agent id space (2^32-1) exhausted");
+    h->kf_grid = std::min<uint64_t>(std::max<uint64_t>(2ull * h->h_counters[CTR_PEND_FIRST] + 256, 512), std::max<uint64_t>(n + h->n_ghost, 1));
+    h->bf_est = 2ull * h->h_counters[CTR_BIRTH_FLAGS] + 1024;
+    h->cur = nxt; h->n = n_new; h->next_id += nb_total; h->n_ghost = 0; h->tick += 1; h->updates += (double)n;
+    return 0;
+  };
+  if (h->optimistic && !h->strip && h->bf_est > 0) {
+    /* one GPU, steady state: no read-back before the commit.  A one-thread guard tells the commit and the offspring
+     * kernels whether everybody is decided and the output arrays (sized from last tick's births) are large enough; when
+     * not, they do nothing and the careful path below redoes this part with exact figures. */
+    const uint64_t bcapn = h->bf_est;
+    TickGuardBody tg;
+    tg.pending = ctr + (in ? CTR_PEND_B : CTR_PEND_A); tg.birth_flags = ctr + CTR_BIRTH_FLAGS; tg.birth_cap = (uint32_t)std::min<uint64_t>(bcapn, 0xFFFFFFFFull); tg.go = ctr + CTR_GO;
+    launch_foreach(h->stream, tg, 1);
+    if ((rc = commit_phase(bcapn, ctr + CTR_GO))) return rc;
+    if (h->cfg.reproduce) {
+      if ((rc = rank_prefix(h, words))) return rc;
+      BirthIdBody bi;
+      bi.birth_pos = (const uint32_t*)h->birth_pos.p; bi.birth_parent = (const uint32_t*)h->birth_parent.p;
+      bi.birth_bits = (const uint32_t*)h->bits.p; bi.birth_prefix = (const uint32_t*)h->bits_prefix.p;
+      bi.next_id = (uint32_t)h->next_id; bi.out_id = (uint32_t*)h->id[nxt].p; bi.birth_count = ctr + CTR_BIRTHS;
+      { ProfScope ps(h->prof, h->stream, "birth_ids", bcapn); launch_foreach(h->stream, bi, bcapn); }
+      if ((rc = check_launch(h, "birth ids"))) return rc;
+    }
+    if ((rc = read_counters(h))) return rc;
+    if ((rc = device_error_to_code(h))) return rc;
+    if (h->h_counters[CTR_GO]) return finish_tick(h->h_counters[CTR_CURSOR], h->h_counters[CTR_BIRTHS]);
+    /* not ready (agents still open, or more births than expected): nothing was touched; go on carefully */
+  }
   if ((rc = take_stats(ctr + (in ? CTR_PEND_B : CTR_PEND_A)))) return rc;
   if (h->strip && (rc = read_counters(h))) return rc;
   h->kf_grid = std::min<uint64_t>(std::max<uint64_t>(2ull * h->h_counters[CTR_PEND_FIRST] + 256, 512), std::max<uint64_t>(n + h->n_ghost, 1));
@@ -1144,28 +1200,7 @@ static int tick_tile(abm_handle* h) {
       in ^= 1;
     }
   }
-  /* commit + grass + re-grouping */
-  const int nxt = h->cur ^ 1;
-  const uint64_t arrivals_cap = h->strip ? 2 * h->bcap : 0; /* ghost agents (and their offspring) may land here */
-  if ((rc = ensure_soa(h, nxt, n + birth_flags + 2 * arrivals_cap))) return rc;
-  if ((rc = ensure(h, h->birth_pos, (birth_flags + arrivals_cap + 1) * 4))) return rc;
-  if ((rc = ensure(h, h->birth_parent, (birth_flags + arrivals_cap + 1) * 4))) return rc;
-  const uint64_t words = bitmap_words(h->next_id);
-  if (birth_flags > 0 || h->strip) {
-    if ((rc = ensure(h, h->bits, (words + 4) * 4))) return rc;
-    if (!h->strip) ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, h->stream));
-  }
-  {
-    CommitTile ct;
-    ct.v = v; ct.si = si; ct.cores_x = h->g.nx / CORE; ct.core_y0 = h->g.own_lo / CORE;
-    ct.out_cell = (uint32_t*)h->cell[nxt].p; ct.out_id = (uint32_t*)h->id[nxt].p; ct.out_energy = (double*)h->energy[nxt].p;
-    ct.new_off = (uint32_t*)h->sub_off[nxt].p; ct.new_cnt = (uint32_t*)h->sub_cnt[nxt].p;
-    ct.cursor = ctr + CTR_CURSOR;
-    ct.birth_pos = (uint32_t*)h->birth_pos.p; ct.birth_parent = (uint32_t*)h->birth_parent.p; ct.birth_count = ctr + CTR_BIRTHS;
-    ct.birth_bits = h->strip ? nullptr : (uint32_t*)h->bits.p; /* strips rank the parents globally instead */
-    { ProfScope ps(h->prof, h->stream, "commit_tiles", n); launch_cta(h->stream, ct, cores, COMMIT_THREADS, CommitTile::smem_bytes()); }
-    if ((rc = check_launch(h, "tile commit"))) return rc;
-  }
+  if ((rc = commit_phase(birth_flags, nullptr))) return rc;
   if (h->strip && (rc = strip_birth_ids(h, birth_cap, nxt, ctr + CTR_BIRTH_TOTAL))) return rc;
   if ((rc = read_counters(h))) return rc;
   if ((rc = device_error_to_code(h))) return rc;
@@ -1180,18 +1215,11 @@ static int tick_tile(abm_handle* h) {
     BirthIdBody bi;
     bi.birth_pos = (const uint32_t*)h->birth_pos.p; bi.birth_parent = (const uint32_t*)h->birth_parent.p;
     bi.birth_bits = (const uint32_t*)h->bits.p; bi.birth_prefix = (const uint32_t*)h->bits_prefix.p;
-    bi.next_id = (uint32_t)h->next_id; bi.out_id = (uint32_t*)h->id[nxt].p;
+    bi.next_id = (uint32_t)h->next_id; bi.out_id = (uint32_t*)h->id[nxt].p; bi.birth_count = nullptr;
     { ProfScope ps(h->prof, h->stream, "birth_ids", nb); launch_foreach(h->stream, bi, nb); }
     if ((rc = check_launch(h, "birth ids"))) return rc;
   }
-  if (h->next_id + nb_total > 0xFFFFFFFFull) ABM_FAIL(h, ABM_E_CAPACITY, "agent id space (2^32-1) exhausted");
-  h->cur = nxt;
-  h->n = n_new;
-  h->next_id += nb_total;
-  h->n_ghost = 0;
-  h->tick += 1;
-  h->updates += (double)n;
-  return 0;
+  return finish_tick(n_new, nb_total);
 }
 
 static int validate_config(const abm_config* c, std::string& why) {
@@ -1325,6 +1353,7 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
   h->tile_mode = h->strip || (cfg->reserved0 != 1 && cfg->walk_type != ABM_ALTERNATED_WALK && cfg->nx % CORE == 0 && cfg->ny % CORE == 0 &&
                              cfg->nx >= 2 * CORE && cfg->ny >= 2 * CORE);
   h->nsx = g.nx / SUB; h->nsy = g.ny / SUB;
+  if (const char* op = getenv("ABM_OPTIMISTIC")) h->optimistic = atoi(op) != 0;
   if (const char* ar = getenv("ABM_AGENT_ROUNDS")) { const int q = atoi(ar); if (q >= 0 && q <= 16) h->fixed_agent_rounds = q; }
   if (const char* tm = getenv("ABM_TILE_MARGIN")) { const int q = atoi(tm); if (q >= 2 && q <= HALO) h->tile_margin = q; }
   if (const char* tr = getenv("ABM_TILE_ROUNDS")) { const int q = atoi(tr); if (q >= 1 && q <= 64) h->tile_rounds = q; }

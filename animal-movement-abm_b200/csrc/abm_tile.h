@@ -543,10 +543,12 @@ struct CommitTile {
   uint32_t* new_off; uint32_t* new_cnt; /* next tick's sub-tile runs */
   uint32_t* cursor;                     /* next free slot of the output SoA */
   uint32_t* birth_pos; uint32_t* birth_parent; uint32_t* birth_count; uint32_t* birth_bits;
+  const uint32_t* go; /* optional device flag: 0 = the host enqueued this commit optimistically and the tick is not ready for it */
 
   static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 16 * 3 + RUNTABLE_WORDS + 8 + 3 * ARRIVE_CAP + 16 * (COMMIT_THREADS / 32)) * 4; }
 
   ABM_HD void operator()(uint32_t cta, uint32_t* smem) const {
+    if (go && !*go) return; /* uniform: nothing has been touched, the host takes the careful path */
     const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) + core_y0;
     Window w;
     w.set(cx * CORE - HALO, cy * CORE - HALO, WIN, WIN);
@@ -673,12 +675,20 @@ struct CommitTile {
   }
 };
 
+/* 1 when the tick is ready for an optimistic commit: nobody left undecided and the output arrays are large enough */
+struct TickGuardBody {
+  const uint32_t* pending; const uint32_t* birth_flags; uint32_t birth_cap; uint32_t* go;
+  ABM_HD void operator()(uint64_t) const { *go = (*pending == 0 && *birth_flags <= birth_cap) ? 1u : 0u; }
+};
+
 /* offspring ids: nextid(model) in the order of the parents' ids */
 struct BirthIdBody {
   const uint32_t* birth_pos; const uint32_t* birth_parent; const uint32_t* birth_bits; const uint32_t* birth_prefix;
   uint32_t next_id;
   uint32_t* out_id;
+  const uint32_t* birth_count; /* optional: device-side number of births (the launch is then an upper bound) */
   ABM_HD void operator()(uint64_t i) const {
+    if (birth_count && i >= *birth_count) return;
     const uint32_t pid = birth_parent[i], wd = pid >> 5;
     const uint32_t rank = birth_prefix[wd] + (uint32_t)popc(birth_bits[wd] & ((1u << (pid & 31)) - 1u));
     out_id[birth_pos[i]] = next_id + rank;
