@@ -266,7 +266,8 @@ struct abm_handle {
   int32_t tile_rounds = 8;
   int32_t tile_margin = HALO;     /* halo cells actually taken into a core's window (ABM_TILE_MARGIN overrides) */ /* in-window rounds of the tile resolve kernel (ABM_TILE_ROUNDS overrides; tests use 1) */
   int32_t nsx = 0, nsy = 0;
-  DevBuf sub_off[2], sub_cnt[2], birth_pos, birth_parent, ingest_sub;
+  DevBuf sub_off[2], sub_cnt[2], birth_pos, birth_parent, ingest_sub, mig_cnt, mig_a, mig_lc;
+  bool use_migrants = true; /* ABM_MIGRANTS=0: the commit scans the halo sub-tiles instead */
   /* row strips: ring neighbours, transport, boundary-row staging ([0] = towards / from the previous strip, [1] = next) */
   bool strip = false;
   int32_t n_ranks = 1, my_rank = 0;
@@ -1140,6 +1141,22 @@ static int tick_tile(abm_handle* h) {
       if (!h->strip) ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, h->stream));
     }
     CommitTile ct;
+    ct.mig_cnt = nullptr; ct.mig_a = nullptr; ct.mig_lc = nullptr;
+    if (h->use_migrants) { /* decisions are final here (or `go` is 0): list the agents that cross a core border at their destination */
+      if ((r = ensure(h, h->mig_cnt, cores * 4))) return r;
+      if ((r = ensure(h, h->mig_a, cores * MIG_CAP * 4))) return r;
+      if ((r = ensure(h, h->mig_lc, cores * MIG_CAP * 2))) return r;
+      ABM_CK(h, dev_memset(h->mig_cnt.p, 0, cores * 4, h->stream));
+      MigrantScanBody ms;
+      ms.g = h->g; ms.cores_x = h->g.nx / CORE; ms.core_y0 = h->g.own_lo / CORE; ms.core_rows = (h->g.own_hi - h->g.own_lo) / CORE;
+      ms.cell = (const uint32_t*)h->cell[h->cur].p; ms.state = (const uint8_t*)h->state.p;
+      ms.mig_cnt = (uint32_t*)h->mig_cnt.p; ms.mig_a = (uint32_t*)h->mig_a.p; ms.mig_lc = (uint16_t*)h->mig_lc.p;
+      ms.go = go; ms.n_own = (uint32_t)n; ms.ghost_cap = (uint32_t)h->bcap;
+      ms.ghost_total[0] = h->strip ? (const uint32_t*)h->rx_pre[0].p + h->nsx : nullptr;
+      ms.ghost_total[1] = h->strip ? (const uint32_t*)h->rx_pre[1].p + h->nsx : nullptr;
+      { ProfScope ps(h->prof, h->stream, "migrant_scan", n + h->n_ghost); launch_foreach(h->stream, ms, n + h->n_ghost); }
+      ct.mig_cnt = ms.mig_cnt; ct.mig_a = ms.mig_a; ct.mig_lc = ms.mig_lc;
+    }
     ct.v = v; ct.si = si; ct.cores_x = h->g.nx / CORE; ct.core_y0 = h->g.own_lo / CORE;
     ct.out_cell = (uint32_t*)h->cell[nxt].p; ct.out_id = (uint32_t*)h->id[nxt].p; ct.out_energy = (double*)h->energy[nxt].p;
     ct.new_off = (uint32_t*)h->sub_off[nxt].p; ct.new_cnt = (uint32_t*)h->sub_cnt[nxt].p;
@@ -1353,6 +1370,7 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
   h->tile_mode = h->strip || (cfg->reserved0 != 1 && cfg->walk_type != ABM_ALTERNATED_WALK && cfg->nx % CORE == 0 && cfg->ny % CORE == 0 &&
                              cfg->nx >= 2 * CORE && cfg->ny >= 2 * CORE);
   h->nsx = g.nx / SUB; h->nsy = g.ny / SUB;
+  if (const char* mg = getenv("ABM_MIGRANTS")) h->use_migrants = atoi(mg) != 0;
   if (const char* op = getenv("ABM_OPTIMISTIC")) h->optimistic = atoi(op) != 0;
   if (const char* ar = getenv("ABM_AGENT_ROUNDS")) { const int q = atoi(ar); if (q >= 0 && q <= 16) h->fixed_agent_rounds = q; }
   if (const char* tm = getenv("ABM_TILE_MARGIN")) { const int q = atoi(tm); if (q >= 2 && q <= HALO) h->tile_margin = q; }

@@ -535,6 +535,45 @@ struct ResolveWindow {
  * Kernel K_BC: commit by destination + grass + re-grouping.  reduce_energy! / eat! / reproduce!
  * (src/agent_actions.jl:54-67, :85-92, :139-147, :172-178) and custom_model_step! (src/model_actions.jl:18-30).
  */
+enum { MIG_CAP = 96 }; /* migrants listed per core and tick; a core that receives more falls back to scanning its halo */
+
+/* After every decision is final: agents whose step crosses a core border are listed at their destination core, so that
+ * the commit of a core reads its own agents plus this list instead of scanning the 20 halo sub-tiles around it.
+ * One thread per agent (own and ghost). */
+struct MigrantScanBody {
+  Geo g; int32_t cores_x, core_y0, core_rows;
+  const uint32_t* cell; const uint8_t* state;
+  uint32_t* mig_cnt; uint32_t* mig_a; uint16_t* mig_lc;
+  const uint32_t* go;              /* optional: 0 = decisions are not final, do nothing */
+  uint32_t n_own, ghost_cap;       /* strips: ghost agents sit at [n_own, n_own + cap) and [n_own + cap, n_own + 2 cap) ... */
+  const uint32_t* ghost_total[2];  /* ... of which only the first *ghost_total[d] are real */
+  ABM_HD void operator()(uint64_t i) const {
+    if (go && !*go) return;
+    if (i >= n_own) {
+      const uint32_t k = (uint32_t)i - n_own, d = k >= ghost_cap ? 1u : 0u;
+      if (k - d * ghost_cap >= *ghost_total[d]) return;
+    }
+    const uint8_t st = state[i];
+    if (!(st & ST_MOVED)) return;
+    const uint32_t c = cell[i];
+    int dx, dy;
+    off8(st & ST_DIRMASK, dx, dy);
+    const int lx = (int)(c & 31) + dx, ly = (int)((c >> 5) & 31) + dy;
+    if (lx >= 0 && lx < CORE && ly >= 0 && ly < CORE) return; /* stays inside its core */
+    const uint32_t t = c >> 10;
+    int ty = (int)(t / (uint32_t)g.tiles_x), tx = (int)(t - (uint32_t)ty * (uint32_t)g.tiles_x);
+    tx += lx < 0 ? -1 : (lx >= CORE ? 1 : 0);
+    ty += ly < 0 ? -1 : (ly >= CORE ? 1 : 0);
+    if (g.periodic) tx = wrap(tx, g.tiles_x); /* the move itself was valid: off-grid targets never get ST_MOVED */
+    if (g.py) ty = wrap(ty, g.tiles_y);
+    const int cy = ty - core_y0;
+    if (cy < 0 || cy >= core_rows || tx < 0 || tx >= cores_x) return; /* lands in a neighbouring strip's rows */
+    const uint32_t core = (uint32_t)cy * (uint32_t)cores_x + (uint32_t)tx;
+    const uint32_t k = atomic_add(&mig_cnt[core], 1u);
+    if (k < MIG_CAP) { mig_a[(size_t)core * MIG_CAP + k] = (uint32_t)i; mig_lc[(size_t)core * MIG_CAP + k] = (uint16_t)(((ly & 31) << 5) | (lx & 31)); }
+  }
+};
+
 struct CommitTile {
   View v;
   SubIndex si;
@@ -544,14 +583,19 @@ struct CommitTile {
   uint32_t* cursor;                     /* next free slot of the output SoA */
   uint32_t* birth_pos; uint32_t* birth_parent; uint32_t* birth_count; uint32_t* birth_bits;
   const uint32_t* go; /* optional device flag: 0 = the host enqueued this commit optimistically and the tick is not ready for it */
+  const uint32_t* mig_cnt; const uint32_t* mig_a; const uint16_t* mig_lc; /* optional migrant lists (MigrantScanBody) */
 
   static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 16 * 3 + RUNTABLE_WORDS + 8 + 3 * ARRIVE_CAP + 16 * (COMMIT_THREADS / 32)) * 4; }
 
   ABM_HD void operator()(uint32_t cta, uint32_t* smem) const {
     if (go && !*go) return; /* uniform: nothing has been touched, the host takes the careful path */
     const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) + core_y0;
+    /* with a complete migrant list the window is the core itself (16 sub-tile runs); otherwise core + halo (36 runs) */
+    const uint32_t n_mig = mig_cnt ? mig_cnt[cta] : NONE32;
+    const bool use_mig = n_mig <= MIG_CAP;
+    const int halo = use_mig ? 0 : HALO;
     Window w;
-    w.set(cx * CORE - HALO, cy * CORE - HALO, WIN, WIN);
+    w.set(cx * CORE - halo, cy * CORE - halo, CORE + 2 * halo, CORE + 2 * halo);
     const int nruns = w.runs(), NT = COMMIT_THREADS;
     uint32_t* min_all = smem;                         /* lowest id arriving on each core cell: the one that eats */
     uint8_t* grass = (uint8_t*)(smem + CORE * CORE);  /* the core's grass tile */
@@ -567,6 +611,8 @@ struct CommitTile {
     uint32_t* wcounts = ar_cs + ARRIVE_CAP;    /* per warp x per sub-tile arrival counts (one hot address would serialise) */
     const uint32_t tile = (uint32_t)(cy * cores_x + cx); /* CORE == TILE: a core is one grass tile */
     uint32_t* gtile = (uint32_t*)(v.grass + (size_t)tile * TILE_CELLS);
+    const uint32_t* my_mig_a = mig_a ? mig_a + (size_t)cta * MIG_CAP : nullptr;
+    const uint16_t* my_mig_lc = mig_lc ? mig_lc + (size_t)cta * MIG_CAP : nullptr;
 
     ABM_CTA_FOR(t, NT) {
       rt.load(t, NT, nruns, w, v.g, si);
@@ -582,16 +628,25 @@ struct CommitTile {
     ABM_CTA_SYNC();
     const uint32_t M = rt.prefix[nruns];
     ABM_CTA_FOR(t, NT) { /* pass 1: who lands in the core */
-      for (uint32_t m = (uint32_t)t; m < M; m += (uint32_t)NT) {
-        const int r = rt.find(m, nruns);
-        const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
+      for (uint32_t m = (uint32_t)t; m < M + (use_mig ? n_mig : 0u); m += (uint32_t)NT) {
+        uint32_t a;
         int x, y;
-        if (!rt.locate(w, r, v.cell[a], x, y)) continue;
-        const uint8_t st = v.state[a];
-        if (!(st & ST_DECIDED)) { atomic_or(v.err, ERR_INTERNAL); continue; }
-        if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); x += dx; y += dy; }
-        x -= HALO; y -= HALO;
-        if (x < 0 || x >= CORE || y < 0 || y >= CORE) continue;
+        uint8_t st;
+        if (m < M) {
+          const int r = rt.find(m, nruns);
+          a = rt.off[r] + (m - rt.prefix[r]);
+          if (!rt.locate(w, r, v.cell[a], x, y)) continue;
+          st = v.state[a];
+          if (!(st & ST_DECIDED)) { atomic_or(v.err, ERR_INTERNAL); continue; }
+          if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); x += dx; y += dy; }
+          x -= halo; y -= halo;
+          if (x < 0 || x >= CORE || y < 0 || y >= CORE) continue;
+        } else { /* a migrant: its final cell inside this core was computed by the scan */
+          a = my_mig_a[m - M];
+          const uint32_t lc = my_mig_lc[m - M];
+          x = (int)(lc & 31); y = (int)(lc >> 5);
+          st = v.state[a];
+        }
         const uint32_t id = v.id[a];
         smem_min(&min_all[y * CORE + x], id);
         const uint32_t add = ((st & ST_DEAD) ? 0u : 1u) + ((st & ST_BIRTH) ? 1u : 0u);
@@ -622,7 +677,7 @@ struct CommitTile {
     }
     ABM_CTA_SYNC();
     const bool listed = misc[2] == 0;
-    const uint32_t n_pass2 = listed ? misc[1] : M;
+    const uint32_t n_pass2 = listed ? misc[1] : M + (use_mig ? n_mig : 0u);
     ABM_CTA_FOR(t, NT) { /* pass 2: energy, eating, births, output (over the arrival list when it fits) */
       for (uint32_t m = (uint32_t)t; m < n_pass2; m += (uint32_t)NT) {
         uint32_t a, id;
@@ -632,15 +687,20 @@ struct CommitTile {
           a = ar_a[m]; id = ar_id[m];
           const uint32_t cs = ar_cs[m];
           x = (int)(cs & 31); y = (int)((cs >> 5) & 31); st = (uint8_t)(cs >> 16);
-        } else {
+        } else if (m < M) {
           const int r = rt.find(m, nruns);
           a = rt.off[r] + (m - rt.prefix[r]);
           if (!rt.locate(w, r, v.cell[a], x, y)) continue;
           st = v.state[a];
           if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); x += dx; y += dy; }
-          x -= HALO; y -= HALO;
+          x -= halo; y -= halo;
           if (x < 0 || x >= CORE || y < 0 || y >= CORE) continue;
           id = v.id[a];
+        } else {
+          a = my_mig_a[m - M];
+          const uint32_t lc = my_mig_lc[m - M];
+          x = (int)(lc & 31); y = (int)(lc >> 5);
+          st = v.state[a]; id = v.id[a];
         }
         const int lc = y * CORE + x;
         double e = v.energy[a] - v.p.movement_cost; /* walk_ocurred is always true */
