@@ -267,7 +267,8 @@ struct abm_handle {
   int32_t tile_margin = HALO;     /* halo cells actually taken into a core's window (ABM_TILE_MARGIN overrides) */ /* in-window rounds of the tile resolve kernel (ABM_TILE_ROUNDS overrides; tests use 1) */
   int32_t nsx = 0, nsy = 0;
   DevBuf sub_off[2], sub_cnt[2], birth_pos, birth_parent, ingest_sub, mig_cnt, mig_a, mig_lc;
-  bool use_migrants = true; /* ABM_MIGRANTS=0: the commit scans the halo sub-tiles instead */
+  bool use_migrants = false; /* ABM_MIGRANTS=1: border crossers are listed per destination core and the commit reads only its
+                              * own core + that list; measured slower than scanning the halo (profiles/README.md), so off */
   /* row strips: ring neighbours, transport, boundary-row staging ([0] = towards / from the previous strip, [1] = next) */
   bool strip = false;
   int32_t n_ranks = 1, my_rank = 0;

@@ -282,3 +282,16 @@ def test_gpu_full_size_two_engine_paths_and_invariants(libabm, wt, size, extra):
         assert sa["countdown"].min() >= 0 and sa["countdown"].max() <= 30
         assert np.all(sa["energy"][old] >= 0)  # agents below zero were removed (reduce_energy!, strict <); offspring of a killed parent may be below
         prev = sa
+
+
+@pytest.mark.parametrize("name", ["tile_rw_96x64", "tile_gregarious_r3_96x96", "tile_walkmap_128x96", "tile_crowded_64x64"])
+def test_emulated_tile_path_with_migrant_lists(emu, oracle, name, monkeypatch):
+    """ABM_MIGRANTS=1: the commit reads its own core plus the per-core list of border crossers (off by default)."""
+    monkeypatch.setenv("ABM_MIGRANTS", "1")
+    cfgkw, w, state, ticks = build_case(name)
+    a, b = load_case(oracle, cfgkw, w), load_case(emu, cfgkw, w)
+    for t in range(6):
+        a.step(1)
+        b.step(1)
+        assert "migrant_scan" in {k for k, v in b.kernel_stats().items() if v["launches"]}
+        assert_same_state(b.snapshot(), a.snapshot(), f"{name} tick {t}")
