@@ -585,7 +585,7 @@ struct CommitTile {
   const uint32_t* go; /* optional device flag: 0 = the host enqueued this commit optimistically and the tick is not ready for it */
   const uint32_t* mig_cnt; const uint32_t* mig_a; const uint16_t* mig_lc; /* optional migrant lists (MigrantScanBody) */
 
-  static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 16 * 3 + RUNTABLE_WORDS + 8 + 3 * ARRIVE_CAP + 16 * (COMMIT_THREADS / 32) + 2 * ARRIVE_CAP + 2) * 4; }
+  static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 16 * 3 + RUNTABLE_WORDS + 8 + 3 * ARRIVE_CAP + 16 * (COMMIT_THREADS / 32)) * 4; }
 
   ABM_HD void operator()(uint32_t cta, uint32_t* smem) const {
     if (go && !*go) return; /* uniform: nothing has been touched, the host takes the careful path */
@@ -609,7 +609,6 @@ struct CommitTile {
     uint32_t* ar_id = ar_a + ARRIVE_CAP;
     uint32_t* ar_cs = ar_id + ARRIVE_CAP;
     uint32_t* wcounts = ar_cs + ARRIVE_CAP;    /* per warp x per sub-tile arrival counts (one hot address would serialise) */
-    double* ar_e = (double*)(((uintptr_t)(wcounts + 16 * (COMMIT_THREADS / 32)) + 7) & ~(uintptr_t)7); /* arrivals' energies, 8-byte aligned */
     const uint32_t tile = (uint32_t)(cy * cores_x + cx); /* CORE == TILE: a core is one grass tile */
     uint32_t* gtile = (uint32_t*)(v.grass + (size_t)tile * TILE_CELLS);
     const uint32_t* my_mig_a = mig_a ? mig_a + (size_t)cta * MIG_CAP : nullptr;
@@ -628,39 +627,33 @@ struct CommitTile {
     ABM_CTA_FOR(t, NT) { rt.expand(t, NT, nruns); }
     ABM_CTA_SYNC();
     const uint32_t M = rt.prefix[nruns];
-    ABM_CTA_FOR(t, NT) { /* pass 1: who lands in the core.  All global loads of a batch of agents are issued before any is
-                          * used (cell, state, id and — speculatively — energy): one memory latency per batch, none in pass 2 */
-      const uint32_t n1 = M + (use_mig ? n_mig : 0u);
-      for (uint32_t m0 = (uint32_t)t; m0 < n1; m0 += 4u * (uint32_t)NT) {
-        int rr[4]; uint32_t aa[4], cc[4], ii[4]; uint8_t ss[4]; double ee[4];
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t m = m0 + (uint32_t)(j * NT);
-          if (m >= n1) { rr[j] = -2; continue; }
-          if (m < M) { rr[j] = rt.find(m, nruns); aa[j] = rt.off[rr[j]] + (m - rt.prefix[rr[j]]); cc[j] = v.cell[aa[j]]; }
-          else { rr[j] = -1; aa[j] = my_mig_a[m - M]; cc[j] = my_mig_lc[m - M]; }
-          ss[j] = v.state[aa[j]]; ii[j] = v.id[aa[j]]; ee[j] = v.energy[aa[j]];
+    ABM_CTA_FOR(t, NT) { /* pass 1: who lands in the core */
+      for (uint32_t m = (uint32_t)t; m < M + (use_mig ? n_mig : 0u); m += (uint32_t)NT) {
+        uint32_t a;
+        int x, y;
+        uint8_t st;
+        if (m < M) {
+          const int r = rt.find(m, nruns);
+          a = rt.off[r] + (m - rt.prefix[r]);
+          if (!rt.locate(w, r, v.cell[a], x, y)) continue;
+          st = v.state[a];
+          if (!(st & ST_DECIDED)) { atomic_or(v.err, ERR_INTERNAL); continue; }
+          if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); x += dx; y += dy; }
+          x -= halo; y -= halo;
+          if (x < 0 || x >= CORE || y < 0 || y >= CORE) continue;
+        } else { /* a migrant: its final cell inside this core was computed by the scan */
+          a = my_mig_a[m - M];
+          const uint32_t lc = my_mig_lc[m - M];
+          x = (int)(lc & 31); y = (int)(lc >> 5);
+          st = v.state[a];
         }
-        for (int j = 0; j < 4; ++j) {
-          if (rr[j] == -2) continue;
-          int x, y;
-          const uint8_t st = ss[j];
-          if (rr[j] >= 0) {
-            if (!rt.locate(w, rr[j], cc[j], x, y)) continue;
-            if (!(st & ST_DECIDED)) { atomic_or(v.err, ERR_INTERNAL); continue; }
-            if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); x += dx; y += dy; }
-            x -= halo; y -= halo;
-            if (x < 0 || x >= CORE || y < 0 || y >= CORE) continue;
-          } else { /* a migrant: its final cell inside this core was computed by the scan */
-            x = (int)(cc[j] & 31); y = (int)(cc[j] >> 5);
-          }
-          const uint32_t id = ii[j];
-          smem_min(&min_all[y * CORE + x], id);
-          const uint32_t add = ((st & ST_DEAD) ? 0u : 1u) + ((st & ST_BIRTH) ? 1u : 0u);
-          if (add) smem_add(&wcounts[(t >> 5) * 16 + (y >> 3) * 4 + (x >> 3)], add);
-          const uint32_t slot = smem_add(&misc[1], 1u);
-          if (slot < ARRIVE_CAP) { ar_a[slot] = aa[j]; ar_id[slot] = id; ar_cs[slot] = (uint32_t)(y * CORE + x) | ((uint32_t)st << 16); ar_e[slot] = ee[j]; }
-          else misc[2] = 1;
-        }
+        const uint32_t id = v.id[a];
+        smem_min(&min_all[y * CORE + x], id);
+        const uint32_t add = ((st & ST_DEAD) ? 0u : 1u) + ((st & ST_BIRTH) ? 1u : 0u);
+        if (add) smem_add(&wcounts[(t >> 5) * 16 + (y >> 3) * 4 + (x >> 3)], add);
+        const uint32_t slot = smem_add(&misc[1], 1u);
+        if (slot < ARRIVE_CAP) { ar_a[slot] = a; ar_id[slot] = id; ar_cs[slot] = (uint32_t)(y * CORE + x) | ((uint32_t)st << 16); }
+        else misc[2] = 1;
       }
     }
     ABM_CTA_SYNC();
@@ -710,7 +703,7 @@ struct CommitTile {
           st = v.state[a]; id = v.id[a];
         }
         const int lc = y * CORE + x;
-        double e = (listed ? ar_e[m] : v.energy[a]) - v.p.movement_cost; /* walk_ocurred is always true */
+        double e = v.energy[a] - v.p.movement_cost; /* walk_ocurred is always true */
         if (v.p.eat && min_all[lc] == id && (grass[lc] & GRASS_GROWN)) { /* killed agents still eat (Appendix D-1) */
           e += v.p.delta_energy;
           grass[lc] = (uint8_t)(grass[lc] & ~GRASS_GROWN);
