@@ -243,6 +243,10 @@ struct abm_handle {
   Geo g;
   Params params;
   abm_stream_t stream = 0;
+#ifndef ABM_EMU
+  cudaStream_t stream2 = nullptr; /* strips: the halo exchange runs here while the interior cores resolve on `stream` */
+  cudaEvent_t ev_proposed = nullptr, ev_halo = nullptr;
+#endif
   int device = 0;
 
   DevBuf cell[2], id[2], energy[2]; /* ping-pong cell-sorted SoA */
@@ -896,19 +900,26 @@ static int strip_alloc(abm_handle* h) {
 
 /* E1: this strip's first and last sub-tile rows (cell, id, energy, proposal) become the neighbours' ghost rows.
  * One fixed-size message per neighbour; header, prefix and packing by one CTA per direction: no host round trip. */
-static int strip_exchange_agents(abm_handle* h) {
+/* room for this tick's ghost agents: they live at fixed places behind the own agents, [n, n + cap) from the previous
+ * strip and [n + cap, n + 2 cap) from the next.  Called before any kernel of the tick takes pointers. */
+static int strip_prepare(abm_handle* h) {
   int rc;
-  const int nsx = h->nsx, cur = h->cur;
-  const uint64_t cap = h->bcap, hdr = strip_hdr_bytes(nsx), bytes = strip_msg_bytes(nsx, cap);
+  const int cur = h->cur;
   if ((rc = strip_alloc(h))) return rc;
-  /* ghost agents live at fixed places behind the own agents: [n, n + cap) from prev, [n + cap, n + 2 cap) from next */
-  const uint64_t tot = h->n + 2 * cap + 1;
+  const uint64_t tot = h->n + 2 * h->bcap + 1;
   if ((rc = grow_keep(h, h->cell[cur], tot * 4))) return rc;
   if ((rc = grow_keep(h, h->id[cur], tot * 4))) return rc;
   if ((rc = grow_keep(h, h->energy[cur], tot * 8))) return rc;
   if ((rc = grow_keep(h, h->state, tot))) return rc;
   if ((rc = ensure(h, h->pend[0], tot * 4))) return rc;
   if ((rc = ensure(h, h->pend[1], tot * 4))) return rc;
+  return 0;
+}
+
+static int strip_exchange_agents(abm_handle* h) {
+  int rc;
+  const int nsx = h->nsx, cur = h->cur;
+  const uint64_t cap = h->bcap, hdr = strip_hdr_bytes(nsx), bytes = strip_msg_bytes(nsx, cap);
   uint32_t* err = (uint32_t*)h->counters.p + CTR_ERR;
   StripPackCta pk;
   pk.si = sub_index(h, cur); pk.row[0] = h->g.own_lo / SUB; pk.row[1] = h->g.own_hi / SUB - 1; pk.tiles_x = h->g.tiles_x; pk.cap = (uint32_t)cap;
@@ -959,16 +970,41 @@ static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce 
 }
 
 /* the figures of StripStatsBody from every rank: one all-reduce on device data, one read-back */
-static int strip_stats(abm_handle* h, const uint32_t* d_pending, std::vector<uint64_t>& out, bool with_state_exchange = false) {
-  int rc;
-  const int P = h->n_ranks, nv = 1 + 3 * P;
+/* true when the all-reduce of the counters can stay on the device (NCCL, or a ring of one) */
+static bool strip_stats_on_device(abm_handle* h) { return h->nccl_comm != nullptr || h->n_ranks == 1; }
+
+static void strip_stats_kernel(abm_handle* h, const uint32_t* d_pending) {
   uint32_t* ctr = (uint32_t*)h->counters.p;
-  unsigned long long* d = (unsigned long long*)h->red_buf.p;
   StripStatsBody sb;
   sb.pending = d_pending; sb.birth_flags = ctr + CTR_BIRTH_FLAGS;
   sb.tot_up = (const uint32_t*)h->sx_pre[0].p + h->nsx; sb.tot_down = (const uint32_t*)h->sx_pre[1].p + h->nsx;
-  sb.n_ranks = P; sb.rank = h->my_rank; sb.out = d;
+  sb.n_ranks = h->n_ranks; sb.rank = h->my_rank; sb.out = (unsigned long long*)h->red_buf.p;
   launch_foreach(h->stream, sb, 1);
+}
+
+/* counters all-reduced into red_buf and (optionally) the decision exchange, without any read-back */
+static int strip_stats_enqueue(abm_handle* h, const uint32_t* d_pending, bool with_state_exchange) {
+  int rc;
+  const int nv = 1 + 3 * h->n_ranks;
+  unsigned long long* d = (unsigned long long*)h->red_buf.p;
+  strip_stats_kernel(h, d_pending);
+#ifndef ABM_EMU
+  if (h->nccl_comm) {
+    if (with_state_exchange) return strip_exchange_states(h, d, nv);
+    ABM_NCCL(h, g_nccl.AllReduce(d, d, (size_t)nv, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
+    return 0;
+  }
+#endif
+  (void)nv; (void)d;
+  if (with_state_exchange && (rc = strip_exchange_states(h))) return rc; /* ring of one: the local figures are the global ones */
+  return 0;
+}
+
+static int strip_stats(abm_handle* h, const uint32_t* d_pending, std::vector<uint64_t>& out, bool with_state_exchange = false) {
+  int rc;
+  const int P = h->n_ranks, nv = 1 + 3 * P;
+  unsigned long long* d = (unsigned long long*)h->red_buf.p;
+  strip_stats_kernel(h, d_pending);
   out.assign((size_t)nv, 0);
 #ifndef ABM_EMU
   if (h->nccl_comm) {
@@ -1041,18 +1077,7 @@ static int tick_tile(abm_handle* h) {
   uint32_t* ctr = (uint32_t*)h->counters.p;
   ABM_CK(h, dev_memset(ctr, 0, 3 * sizeof(uint32_t), h->stream));
   ABM_CK(h, dev_memset(ctr + CTR_CURSOR, 0, 2 * sizeof(uint32_t), h->stream));
-  View v = make_view(h);
-  const SubIndex si = sub_index(h, h->cur);
-  const int wt = h->cfg.walk_type;
-  const bool needs_resolve = wt == ABM_RANDOM_WALK_ATTRACTOR || wt == ABM_RANDOM_WALK_GREGARIOUS || (wt == ABM_RANDOM_WALK && h->cfg.randomwalk_ifempty);
-  uint64_t cnt = 0;
-  if (n > 0) {
-    ProposeBody pb;
-    pb.v = v; pb.pending = nullptr; pb.pending_count = nullptr; pb.birth_flags = ctr + CTR_BIRTH_FLAGS;
-    { ProfScope ps(h->prof, h->stream, "propose", n); launch_foreach(h->stream, pb, n); }
-    if ((rc = check_launch(h, "propose"))) return rc;
-  }
-  if (h->strip) { /* neighbours' boundary rows become ghost rows behind the own agents */
+  if (h->strip) {
     if (!h->bcap_agreed) { /* first tick after abm_set_agents: agree on the message capacity from the real row sizes */
       if ((rc = strip_alloc(h))) return rc;
       const int row_s[2] = {h->g.own_lo / SUB, h->g.own_hi / SUB - 1};
@@ -1069,21 +1094,56 @@ static int tick_tile(abm_handle* h) {
       h->bcap = h->next_bcap = strip_cap_for(rmax);
       h->bcap_agreed = true;
     }
-    if ((rc = strip_exchange_agents(h))) return rc;
-    v = make_view(h);
+    if ((rc = strip_prepare(h))) return rc; /* before anybody takes pointers */
   }
-  if (n + h->n_ghost > 0) {
-    if (needs_resolve) {
-      ResolveWindow rw;
-      rw.v = v; rw.si = si; rw.mode = 0; rw.cores_x = h->g.nx / CORE; rw.core_y0 = h->g.own_lo / CORE; rw.max_rounds = h->tile_rounds; rw.nthreads = TILE_THREADS; rw.margin = std::max<int>(h->tile_margin, wt == ABM_RANDOM_WALK_GREGARIOUS ? std::min<int>(h->cfg.visual_distance + 1, HALO) : 2);
-      rw.in = nullptr; rw.out = (uint32_t*)h->pend[0].p; rw.out_count = ctr + CTR_PEND_A;
-      { ProfScope ps(h->prof, h->stream, "resolve_tiles", n); launch_cta(h->stream, rw, cores, TILE_THREADS, ResolveWindow::smem_bytes_core()); }
-      if ((rc = check_launch(h, "tile resolve"))) return rc;
-    }
+  View v = make_view(h);
+  const SubIndex si = sub_index(h, h->cur);
+  const int wt = h->cfg.walk_type;
+  const bool needs_resolve = wt == ABM_RANDOM_WALK_ATTRACTOR || wt == ABM_RANDOM_WALK_GREGARIOUS || (wt == ABM_RANDOM_WALK && h->cfg.randomwalk_ifempty);
+  uint64_t cnt = 0;
+  if (n > 0) {
+    ProposeBody pb;
+    pb.v = v; pb.pending = nullptr; pb.pending_count = nullptr; pb.birth_flags = ctr + CTR_BIRTH_FLAGS;
+    { ProfScope ps(h->prof, h->stream, "propose", n); launch_foreach(h->stream, pb, n); }
+    if ((rc = check_launch(h, "propose"))) return rc;
+  }
+  const int cores_x = h->g.nx / CORE, core_rows = (h->g.own_hi - h->g.own_lo) / CORE;
+  auto launch_tiles = [&](int row0, int nrows) -> int { /* window resolve of the core rows [row0, row0 + nrows) */
+    if (nrows <= 0) return 0;
+    ResolveWindow rw;
+    rw.v = v; rw.si = si; rw.mode = 0; rw.cores_x = cores_x; rw.core_y0 = h->g.own_lo / CORE + row0; rw.max_rounds = h->tile_rounds; rw.nthreads = TILE_THREADS;
+    rw.margin = std::max<int>(h->tile_margin, wt == ABM_RANDOM_WALK_GREGARIOUS ? std::min<int>(h->cfg.visual_distance + 1, HALO) : 2);
+    rw.in = nullptr; rw.out = (uint32_t*)h->pend[0].p; rw.out_count = ctr + CTR_PEND_A;
+    const uint64_t grid = (uint64_t)nrows * (uint64_t)cores_x;
+    { ProfScope ps(h->prof, h->stream, "resolve_tiles", grid * 256, 1); launch_cta(h->stream, rw, grid, TILE_THREADS, ResolveWindow::smem_bytes_core()); }
+    return check_launch(h, "tile resolve");
+  };
+  bool overlapped = false;
+#ifndef ABM_EMU
+  if (h->strip && h->nccl_comm && h->stream2 && needs_resolve && core_rows >= 3 && n > 0) {
+    /* the halo exchange travels on a second stream while the core rows that cannot see a ghost row are resolved */
+    ABM_CK(h, cudaEventRecord(h->ev_proposed, h->stream));
+    ABM_CK(h, cudaStreamWaitEvent(h->stream2, h->ev_proposed, 0));
+    cudaStream_t main_stream = h->stream;
+    h->stream = h->stream2;
+    rc = strip_exchange_agents(h);
+    h->stream = main_stream;
+    if (rc) return rc;
+    ABM_CK(h, cudaEventRecord(h->ev_halo, h->stream2));
+    if ((rc = launch_tiles(1, core_rows - 2))) return rc;
+    ABM_CK(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
+    if ((rc = launch_tiles(0, 1))) return rc;
+    if ((rc = launch_tiles(core_rows - 1, 1))) return rc;
+    overlapped = true;
+  }
+#endif
+  if (!overlapped) {
+    if (h->strip && (rc = strip_exchange_agents(h))) return rc; /* neighbours' boundary rows become ghost rows behind the own agents */
+    if (n + h->n_ghost > 0 && needs_resolve && (rc = launch_tiles(0, core_rows))) return rc;
   }
   /* figures the host needs before it can go on: open agents, reproducing agents (sizes of the output SoA); in strip
    * mode from every rank, through one all-reduce of device-resident counters */
-  uint64_t birth_flags = 0, birth_cap = 0, global_cnt = 0;
+  uint64_t birth_flags = 0, birth_cap = 0, global_cnt = 0, strip_fmax = 0;
   std::vector<uint64_t> stats;
   const int P = h->n_ranks;
   auto take_stats = [&](const uint32_t* d_pending) -> int {
@@ -1175,16 +1235,30 @@ static int tick_tile(abm_handle* h) {
     h->cur = nxt; h->n = n_new; h->next_id += nb_total; h->n_ghost = 0; h->tick += 1; h->updates += (double)n;
     return 0;
   };
-  if (h->optimistic && !h->strip && h->bf_est > 0) {
-    /* one GPU, steady state: no read-back before the commit.  A one-thread guard tells the commit and the offspring
-     * kernels whether everybody is decided and the output arrays (sized from last tick's births) are large enough; when
-     * not, they do nothing and the careful path below redoes this part with exact figures. */
+  if (h->optimistic && h->bf_est > 0 && (!h->strip || strip_stats_on_device(h))) {
+    /* steady state: no read-back before the commit.  A one-thread guard tells the commit and the offspring kernels
+     * whether everybody is decided and the output arrays (sized from last tick's births) are large enough; when not,
+     * they do nothing and the careful path below redoes this part with exact figures.  Strips: the guard reads the
+     * all-reduced counters, so every rank decides alike and the collectives stay matched. */
     const uint64_t bcapn = h->bf_est;
-    TickGuardBody tg;
-    tg.pending = ctr + (in ? CTR_PEND_B : CTR_PEND_A); tg.birth_flags = ctr + CTR_BIRTH_FLAGS; tg.birth_cap = (uint32_t)std::min<uint64_t>(bcapn, 0xFFFFFFFFull); tg.go = ctr + CTR_GO;
-    launch_foreach(h->stream, tg, 1);
+    uint32_t* d_pend = ctr + (in ? CTR_PEND_B : CTR_PEND_A);
+    if (h->strip) {
+      if ((rc = strip_stats_enqueue(h, d_pend, needs_resolve))) return rc;
+      StripGuardBody sg;
+      sg.stats = (const unsigned long long*)h->red_buf.p; sg.n_ranks = P; sg.birth_cap = (uint32_t)std::min<uint64_t>(bcapn, 0xFFFFFFFFull); sg.go = ctr + CTR_GO;
+      launch_foreach(h->stream, sg, 1);
+    } else {
+      TickGuardBody tg;
+      tg.pending = d_pend; tg.birth_flags = ctr + CTR_BIRTH_FLAGS; tg.birth_cap = (uint32_t)std::min<uint64_t>(bcapn, 0xFFFFFFFFull); tg.go = ctr + CTR_GO;
+      launch_foreach(h->stream, tg, 1);
+    }
     if ((rc = commit_phase(bcapn, ctr + CTR_GO))) return rc;
-    if (h->cfg.reproduce) {
+    if (h->strip) {
+      birth_cap = 3 * bcapn + 64;
+      if ((rc = strip_birth_ids(h, birth_cap, nxt, ctr + CTR_BIRTH_TOTAL))) return rc;
+      stats.assign((size_t)(1 + 3 * P), 0);
+      ABM_CK(h, copy_d2h(stats.data(), h->red_buf.p, stats.size() * 8, h->stream));
+    } else if (h->cfg.reproduce) {
       if ((rc = rank_prefix(h, words))) return rc;
       BirthIdBody bi;
       bi.birth_pos = (const uint32_t*)h->birth_pos.p; bi.birth_parent = (const uint32_t*)h->birth_parent.p;
@@ -1195,7 +1269,16 @@ static int tick_tile(abm_handle* h) {
     }
     if ((rc = read_counters(h))) return rc;
     if ((rc = device_error_to_code(h))) return rc;
-    if (h->h_counters[CTR_GO]) return finish_tick(h->h_counters[CTR_CURSOR], h->h_counters[CTR_BIRTHS]);
+    if (h->h_counters[CTR_GO]) {
+      if (!h->strip) return finish_tick(h->h_counters[CTR_CURSOR], h->h_counters[CTR_BIRTHS]);
+      uint64_t fmax = 0, rmax = 0;
+      for (int r = 0; r < P; ++r) { fmax = std::max(fmax, stats[1 + P + r]); rmax = std::max(rmax, stats[1 + 2 * P + r]); }
+      if (h->h_counters[CTR_BIRTHS] > birth_cap) ABM_FAIL(h, ABM_E_INTERNAL, "more offspring than the agreed message capacity");
+      h->bcap = rmax * 2 > h->bcap ? strip_cap_for(rmax) : h->bcap; /* every rank sees the same figures */
+      if ((rc = finish_tick(h->h_counters[CTR_CURSOR], h->h_counters[CTR_BIRTH_TOTAL]))) return rc;
+      h->bf_est = 2 * fmax + 1024; /* strips: the estimate must be the same on every rank */
+      return 0;
+    }
     /* not ready (agents still open, or more births than expected): nothing was touched; go on carefully */
   }
   if ((rc = take_stats(ctr + (in ? CTR_PEND_B : CTR_PEND_A)))) return rc;
@@ -1228,6 +1311,7 @@ static int tick_tile(abm_handle* h) {
     nb_total = h->h_counters[CTR_BIRTH_TOTAL];
     if (nb > birth_cap) ABM_FAIL(h, ABM_E_INTERNAL, "more offspring (%llu) than the agreed message capacity", (unsigned long long)nb);
     h->bcap = h->next_bcap;
+    strip_fmax = (birth_cap - 64) / 3;
   } else if (nb > 0) {
     if ((rc = rank_prefix(h, words))) return rc;
     BirthIdBody bi;
@@ -1237,7 +1321,9 @@ static int tick_tile(abm_handle* h) {
     { ProfScope ps(h->prof, h->stream, "birth_ids", nb); launch_foreach(h->stream, bi, nb); }
     if ((rc = check_launch(h, "birth ids"))) return rc;
   }
-  return finish_tick(n_new, nb_total);
+  if ((rc = finish_tick(n_new, nb_total))) return rc;
+  if (h->strip) h->bf_est = 2 * strip_fmax + 1024; /* the same on every rank */
+  return 0;
 }
 
 static int validate_config(const abm_config* c, std::string& why) {
@@ -1295,6 +1381,9 @@ void ABM_API(destroy)(abm_handle* h) {
 #ifndef ABM_EMU
   cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); }
+  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+  if (h->ev_proposed) cudaEventDestroy(h->ev_proposed);
+  if (h->ev_halo) cudaEventDestroy(h->ev_halo);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
   if (h->stream) { cudaStreamDestroy(h->stream); }
   if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -1375,7 +1464,7 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
   if (const char* op = getenv("ABM_OPTIMISTIC")) h->optimistic = atoi(op) != 0;
   if (const char* ar = getenv("ABM_AGENT_ROUNDS")) { const int q = atoi(ar); if (q >= 0 && q <= 16) h->fixed_agent_rounds = q; }
   if (const char* tm = getenv("ABM_TILE_MARGIN")) { const int q = atoi(tm); if (q >= 2 && q <= HALO) h->tile_margin = q; }
-  if (const char* tr = getenv("ABM_TILE_ROUNDS")) { const int q = atoi(tr); if (q >= 1 && q <= 64) h->tile_rounds = q; }
+  if (const char* tr = getenv("ABM_TILE_ROUNDS")) { const int q = atoi(tr); if (q >= 0 && q <= 64) h->tile_rounds = q; }
   rc = 0;
   do {
     if ((rc = ensure(h, h->counters, CTR_WORDS * 4))) break;
@@ -1864,6 +1953,11 @@ int ABM_API(comm_init_nccl)(abm_handle* h, const void* unique_id128) {
   ncclComm_t c;
   ABM_NCCL(h, g_nccl.CommInitRank(&c, h->n_ranks, id, h->my_rank));
   h->nccl_comm = (void*)c;
+  if (!h->stream2) {
+    ABM_CK(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    ABM_CK(h, cudaEventCreateWithFlags(&h->ev_proposed, cudaEventDisableTiming));
+    ABM_CK(h, cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+  }
   return ABM_OK;
 #else
   ABM_FAIL(h, ABM_E_STATE, "NCCL is not part of the emulation build");

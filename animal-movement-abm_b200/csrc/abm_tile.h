@@ -741,6 +741,16 @@ struct TickGuardBody {
   ABM_HD void operator()(uint64_t) const { *go = (*pending == 0 && *birth_flags <= birth_cap) ? 1u : 0u; }
 };
 
+/* the same for strips, from the all-reduced figures of StripStatsBody (identical on every rank, so every rank decides alike) */
+struct StripGuardBody {
+  const unsigned long long* stats; int32_t n_ranks; uint32_t birth_cap; uint32_t* go;
+  ABM_HD void operator()(uint64_t) const {
+    bool ok = stats[0] == 0;
+    for (int r = 0; r < n_ranks; ++r) ok = ok && stats[1 + n_ranks + r] <= birth_cap;
+    *go = ok ? 1u : 0u;
+  }
+};
+
 /* offspring ids: nextid(model) in the order of the parents' ids */
 struct BirthIdBody {
   const uint32_t* birth_pos; const uint32_t* birth_parent; const uint32_t* birth_bits; const uint32_t* birth_prefix;
