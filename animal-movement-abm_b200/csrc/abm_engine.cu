@@ -1108,10 +1108,10 @@ static int tick_tile(abm_handle* h) {
     if ((rc = check_launch(h, "propose"))) return rc;
   }
   const int cores_x = h->g.nx / CORE, core_rows = (h->g.own_hi - h->g.own_lo) / CORE;
-  auto launch_tiles = [&](int row0, int nrows) -> int { /* window resolve of the core rows [row0, row0 + nrows) */
+  auto launch_tiles = [&](int row0, int nrows, int row_step = 1) -> int { /* window resolve of the core rows row0, row0 + step, ... */
     if (nrows <= 0) return 0;
     ResolveWindow rw;
-    rw.v = v; rw.si = si; rw.mode = 0; rw.cores_x = cores_x; rw.core_y0 = h->g.own_lo / CORE + row0; rw.max_rounds = h->tile_rounds; rw.nthreads = TILE_THREADS;
+    rw.v = v; rw.si = si; rw.mode = 0; rw.cores_x = cores_x; rw.core_y0 = h->g.own_lo / CORE + row0; rw.row_step = row_step; rw.max_rounds = h->tile_rounds; rw.nthreads = TILE_THREADS;
     rw.margin = std::max<int>(h->tile_margin, wt == ABM_RANDOM_WALK_GREGARIOUS ? std::min<int>(h->cfg.visual_distance + 1, HALO) : 2);
     rw.in = nullptr; rw.out = (uint32_t*)h->pend[0].p; rw.out_count = ctr + CTR_PEND_A;
     const uint64_t grid = (uint64_t)nrows * (uint64_t)cores_x;
@@ -1127,13 +1127,12 @@ static int tick_tile(abm_handle* h) {
     cudaStream_t main_stream = h->stream;
     h->stream = h->stream2;
     rc = strip_exchange_agents(h);
+    if (!rc) rc = launch_tiles(0, 2, core_rows - 1); /* the first and the last core row, behind the exchange on its stream */
     h->stream = main_stream;
     if (rc) return rc;
     ABM_CK(h, cudaEventRecord(h->ev_halo, h->stream2));
-    if ((rc = launch_tiles(1, core_rows - 2))) return rc;
+    if ((rc = launch_tiles(1, core_rows - 2))) return rc; /* meanwhile: the rows that cannot see a ghost row */
     ABM_CK(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
-    if ((rc = launch_tiles(0, 1))) return rc;
-    if ((rc = launch_tiles(core_rows - 1, 1))) return rc;
     overlapped = true;
   }
 #endif
@@ -1171,7 +1170,7 @@ static int tick_tile(abm_handle* h) {
   auto launch_agents = [&](uint64_t grid, uint32_t* d_out) -> int { /* one Jacobi round of per-agent windows over pend[in] */
     ABM_CK(h, dev_memset(d_out, 0, sizeof(uint32_t), h->stream));
     ResolveWindow rw;
-    rw.v = v; rw.si = si; rw.mode = 1; rw.cores_x = 0; rw.core_y0 = 0; rw.max_rounds = 1; rw.nthreads = AGENT_THREADS; rw.margin = HALO;
+    rw.v = v; rw.si = si; rw.mode = 1; rw.cores_x = 0; rw.core_y0 = 0; rw.row_step = 1; rw.max_rounds = 1; rw.nthreads = AGENT_THREADS; rw.margin = HALO;
     rw.grid = (uint32_t)grid; rw.in = (const uint32_t*)h->pend[in].p; rw.in_count = ctr + (in ? CTR_PEND_B : CTR_PEND_A);
     rw.out = (uint32_t*)h->pend[in ^ 1].p; rw.out_count = d_out;
     { ProfScope ps(h->prof, h->stream, "resolve_agents", grid); launch_cta(h->stream, rw, grid, AGENT_THREADS, ResolveWindow::smem_bytes(2 * q + 1, 2 * q + 1)); }

@@ -243,6 +243,7 @@ struct ResolveWindow {
   View v;
   SubIndex si;
   int32_t mode, cores_x, core_y0, max_rounds, nthreads;
+  int32_t row_step;         /* mode 0: CTA row q handles core row core_y0 + q * row_step (1 = consecutive rows) */
   int32_t margin;           /* mode 0: agents farther than this from the core are left out of the window (<= HALO) */
   uint32_t grid;            /* mode 1: number of CTAs launched */
   const uint32_t* in;
@@ -258,7 +259,7 @@ struct ResolveWindow {
    * buffered).  Agents are read from global memory exactly once.  Returns false (uniformly) when the list overflows. */
   ABM_HD bool core_fast(uint32_t cta, uint32_t* smem) const {
     Window w;
-    const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) + core_y0;
+    const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) * row_step + core_y0;
     w.set(cx * CORE - HALO, cy * CORE - HALO, WIN, WIN);
     const int in_lo = HALO - margin, in_hi = HALO + CORE + margin; /* agents taken in: [in_lo, in_hi)^2 */
     w.tlo = in_lo + 1; w.thi = in_hi - 2;
@@ -446,7 +447,7 @@ struct ResolveWindow {
     Window w;
     int own_lo = 0, own_hi = 0;
     if (mode == 0) {
-      const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) + core_y0;
+      const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) * row_step + core_y0;
       w.set(cx * CORE - HALO, cy * CORE - HALO, WIN, WIN);
       own_lo = HALO; own_hi = HALO + CORE;
     } else {
