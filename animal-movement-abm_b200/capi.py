@@ -100,6 +100,8 @@ SIGNATURES = {
     "set_transport": (C.c_int, [_P, C.POINTER(AbmTransport)]),
     "nccl_unique_id": (C.c_int, [C.c_void_p]),
     "comm_init_nccl": (C.c_int, [_P, C.c_void_p]),
+    "p2p_export": (C.c_int, [_P, C.c_void_p]),
+    "p2p_connect": (C.c_int, [_P, C.c_void_p, C.c_int32]),
     "last_error": (C.c_char_p, [_P]),
 }
 
@@ -267,6 +269,15 @@ class Engine:
     def comm_init_nccl(self, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
         self._ck(self.lib.fn["comm_init_nccl"](self.h, buf))
+
+    def p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.fn["p2p_export"](self.h, buf))
+        return buf.raw
+
+    def p2p_connect(self, handles: bytes, n_ranks: int):
+        buf = C.create_string_buffer(handles, 64 * n_ranks)
+        self._ck(self.lib.fn["p2p_connect"](self.h, buf, n_ranks))
 
     def set_profiling(self, on=True):
         self._ck(self.lib.fn["set_profiling"](self.h, int(bool(on))))

@@ -19,6 +19,7 @@
 #include "abm_kernels.h"
 #include "abm_astar.h"
 #include "abm_tile.h"
+#include "abm_p2p.h"
 
 #ifdef ABM_EMU
 #define ABM_API(name) emu_##name
@@ -246,6 +247,13 @@ struct abm_handle {
 #ifndef ABM_EMU
   cudaStream_t stream2 = nullptr; /* strips: the halo exchange runs here while the interior cores resolve on `stream` */
   cudaEvent_t ev_proposed = nullptr, ev_halo = nullptr;
+  /* peer-memory transport (abm_p2p.h): this rank's mailbox, the peers' mailboxes mapped through CUDA IPC */
+  uint8_t* p2p_mine = nullptr;
+  uint8_t* p2p_peer[P2P_MAXP] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  P2PLayout p2p_lay;
+  bool p2p_on = false;
+  uint32_t p2p_seq[4] = {0, 0, 0, 0};
+  uint64_t p2p_capmax = 0, p2p_birthmax = 0;
 #endif
   int device = 0;
 
@@ -263,6 +271,7 @@ struct abm_handle {
   uint32_t as_gen = 0;
   /* tile path (abm_tile.h): sub-tile runs of the SoA (ping-pong with the SoA), offspring fix-up lists */
   bool tile_mode = false;
+  bool overlap_halo = false;      /* ABM_OVERLAP=1: halo exchange on a second stream behind the interior rows (measured: no gain) */
   bool optimistic = true;         /* enqueue the commit behind a device-side guard instead of reading counters first (ABM_OPTIMISTIC=0 disables) */
   uint64_t bf_est = 0;            /* expected upper bound of reproducing agents, learnt from the previous tick */
   int32_t fixed_agent_rounds = 2; /* per-agent rounds enqueued without asking the host (ABM_AGENT_ROUNDS overrides) */
@@ -390,6 +399,7 @@ static int read_counters(abm_handle* h) {
 static int device_error_to_code(abm_handle* h) {
   const uint32_t e = h->h_counters[CTR_ERR];
   if (e & ERR_NOWALKABLE) ABM_FAIL(h, ABM_E_NOWALKABLE, "random_walkmap: an agent has no walkable neighbour (the reference throws on rand(1:0))");
+  if (e & ERR_P2P_TIMEOUT) ABM_FAIL(h, ABM_E_CUDA, "peer exchange timed out: a neighbouring strip did not deliver its message");
   if (e & ERR_STRIP_CAP) ABM_FAIL(h, ABM_E_CAPACITY, "a boundary row outgrew the agreed halo message capacity (%llu agents) within one tick", (unsigned long long)h->bcap);
   if (e & ERR_INTERNAL) ABM_FAIL(h, ABM_E_BADARG, "device-side validation failed (out-of-range coordinate, id, countdown or elevation, or duplicate id)");
   return 0;
@@ -881,6 +891,93 @@ static int comm_allgather_u32(abm_handle* h, const uint32_t* send, uint32_t* rec
   return 0;
 }
 
+
+#ifndef ABM_EMU
+/* ------------------------------------------------------------------------------- peer-memory transport */
+static const long long P2P_TIMEOUT_CYCLES = 8000000000ll; /* ~4 s at 2 GHz: a lost neighbour becomes an error, not a hang */
+
+static int p2p_publish_wait(abm_handle* h, int ch, uint32_t seq, const int* targets, const int* target_slot, int nt, const int* sources, int ns) {
+  const int parity = (int)(seq & 1u);
+  uint32_t* err = (uint32_t*)h->counters.p + CTR_ERR;
+  if (nt > 0) {
+    P2PPublishBody pb;
+    pb.n = nt; pb.seq = seq;
+    for (int i = 0; i < nt; ++i) pb.flag[i] = (uint32_t*)(h->p2p_peer[targets[i]] + h->p2p_lay.flag_off(ch, target_slot[i], parity));
+    launch_foreach(h->stream, pb, (uint64_t)nt);
+  }
+  if (ns > 0) {
+    P2PWaitBody wb;
+    wb.n = ns; wb.seq = seq; wb.err = err; wb.limit = P2P_TIMEOUT_CYCLES;
+    for (int i = 0; i < ns; ++i) wb.flag[i] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.flag_off(ch, sources[i], parity));
+    launch_foreach(h->stream, wb, (uint64_t)ns);
+  }
+  return check_launch(h, "peer publish / wait");
+}
+
+/* ring exchange of one channel (agents or decision bytes): my `to_prev` lands in the previous strip's "from next" slot and
+ * vice versa; returns where the neighbours' messages land in my mailbox */
+static int p2p_exchange(abm_handle* h, int ch, const void* to_prev, uint64_t b_tp, const void* to_next, uint64_t b_tn, const uint8_t** from_prev, const uint8_t** from_next) {
+  const uint32_t seq = ++h->p2p_seq[ch];
+  const int parity = (int)(seq & 1u);
+  const int prev = (h->my_rank + h->n_ranks - 1) % h->n_ranks, next = (h->my_rank + 1) % h->n_ranks;
+  const P2PLayout& L = h->p2p_lay;
+  const uint64_t cap = ch == P2P_CH_AGENTS ? L.agents_bytes : L.state_bytes;
+  if (b_tp > cap || b_tn > cap) ABM_FAIL(h, ABM_E_CAPACITY, "halo message (%llu bytes) exceeds the mailbox allocated at abm_p2p_export", (unsigned long long)std::max(b_tp, b_tn));
+  auto off = [&](int dir) { return ch == P2P_CH_AGENTS ? L.agents_off(dir, parity) : L.state_off(dir, parity); };
+  P2PCopyBody cp;
+  cp.src[0] = (const uint4*)to_prev; cp.dst[0] = (uint4*)(h->p2p_peer[prev] + off(1)); cp.words[0] = h->has_prev ? (b_tp + 15) / 16 : 0;
+  cp.src[1] = (const uint4*)to_next; cp.dst[1] = (uint4*)(h->p2p_peer[next] + off(0)); cp.words[1] = h->has_next ? (b_tn + 15) / 16 : 0;
+  if (cp.words[0] + cp.words[1] > 0) launch_foreach(h->stream, cp, cp.words[0] + cp.words[1]);
+  int targets[2], tslot[2], sources[2], nt = 0, ns = 0;
+  if (h->has_prev) { targets[nt] = prev; tslot[nt] = 1; ++nt; sources[ns++] = 0; }
+  if (h->has_next) { targets[nt] = next; tslot[nt] = 0; ++nt; sources[ns++] = 1; }
+  int rc = p2p_publish_wait(h, ch, seq, targets, tslot, nt, sources, ns);
+  if (rc) return rc;
+  *from_prev = h->p2p_mine + off(0);
+  *from_next = h->p2p_mine + off(1);
+  return 0;
+}
+
+/* sum of every rank's counter vector (red_buf, nv words) into red_buf, all on the device */
+static int p2p_allreduce(abm_handle* h, int nv) {
+  const uint32_t seq = ++h->p2p_seq[P2P_CH_STATS];
+  const int parity = (int)(seq & 1u), P = h->n_ranks;
+  P2PStatsSendBody sb;
+  sb.local = (const unsigned long long*)h->red_buf.p; sb.n_peers = P; sb.nv = nv;
+  for (int r = 0; r < P; ++r) sb.dst[r] = (unsigned long long*)(h->p2p_peer[r] + h->p2p_lay.stats_off(h->my_rank, parity));
+  launch_foreach(h->stream, sb, (uint64_t)P * nv);
+  int targets[P2P_MAXP], tslot[P2P_MAXP], sources[P2P_MAXP];
+  for (int r = 0; r < P; ++r) { targets[r] = r; tslot[r] = h->my_rank; sources[r] = r; }
+  int rc = p2p_publish_wait(h, P2P_CH_STATS, seq, targets, tslot, P, sources, P);
+  if (rc) return rc;
+  P2PStatsSumBody sm;
+  sm.n_src = P; sm.nv = nv; sm.out = (unsigned long long*)h->red_buf.p;
+  for (int r = 0; r < P; ++r) sm.src[r] = (const unsigned long long*)(h->p2p_mine + h->p2p_lay.stats_off(r, parity));
+  launch_foreach(h->stream, sm, (uint64_t)nv);
+  return check_launch(h, "peer all-reduce");
+}
+
+/* every rank's offspring message (words u32 at msg) into all[rank * words ...] */
+static int p2p_allgather_births(abm_handle* h, const uint32_t* msg, uint32_t* all, uint64_t words) {
+  if (words * 4 > h->p2p_lay.births_bytes) ABM_FAIL(h, ABM_E_CAPACITY, "offspring message (%llu ids) exceeds the mailbox allocated at abm_p2p_export", (unsigned long long)words);
+  const uint32_t seq = ++h->p2p_seq[P2P_CH_BIRTHS];
+  const int parity = (int)(seq & 1u), P = h->n_ranks;
+  P2PBirthSendBody sb;
+  sb.local = msg; sb.n_peers = P; sb.words = (uint32_t)words;
+  for (int r = 0; r < P; ++r) sb.dst[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.births_off(h->my_rank, parity));
+  launch_foreach(h->stream, sb, (uint64_t)P * words);
+  int targets[P2P_MAXP], tslot[P2P_MAXP], sources[P2P_MAXP];
+  for (int r = 0; r < P; ++r) { targets[r] = r; tslot[r] = h->my_rank; sources[r] = r; }
+  int rc = p2p_publish_wait(h, P2P_CH_BIRTHS, seq, targets, tslot, P, sources, P);
+  if (rc) return rc;
+  P2PBirthGatherBody gb;
+  gb.n_ranks = P; gb.words = (uint32_t)words; gb.all = all;
+  for (int r = 0; r < P; ++r) gb.src[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.births_off(r, parity));
+  launch_foreach(h->stream, gb, (uint64_t)P * words);
+  return check_launch(h, "peer all-gather");
+}
+#endif
+
 /* capacity of a boundary message, agreed by all ranks from the same all-reduced figures */
 static uint64_t strip_cap_for(uint64_t max_row) { return 2 * max_row + 4096; }
 
@@ -929,14 +1026,19 @@ static int strip_exchange_agents(abm_handle* h) {
   launch_cta(h->stream, pk, 2, TILE_THREADS, StripPackCta::smem_bytes());
   for (int d = 0; d < 2; ++d) ABM_CK(h, dev_memset(h->rx_buf[d].p, 0, hdr, h->stream)); /* a missing neighbour sends nothing */
   if ((rc = check_launch(h, "strip pack"))) return rc;
+  const uint8_t* rx_msg[2] = {(const uint8_t*)h->rx_buf[0].p, (const uint8_t*)h->rx_buf[1].p};
   { ProfScope ps(h->prof, h->stream, "halo_exchange", 2 * cap);
+#ifndef ABM_EMU
+    if (h->p2p_on) { if ((rc = p2p_exchange(h, P2P_CH_AGENTS, h->sx_buf[0].p, bytes, h->sx_buf[1].p, bytes, &rx_msg[0], &rx_msg[1]))) return rc; }
+    else
+#endif
     if ((rc = comm_sendrecv(h, h->sx_buf[0].p, bytes, h->sx_buf[1].p, bytes, h->rx_buf[0].p, bytes, h->rx_buf[1].p, bytes))) return rc; }
   StripUnpackCta up;
   up.row[0] = h->g.own_lo / SUB - 1; up.row[1] = h->g.own_hi / SUB; up.nsx = nsx;
   up.tile_row_base[0] = ((uint32_t)(h->g.own_lo / CORE - 1) * (uint32_t)h->g.tiles_x) << 10;
   up.tile_row_base[1] = ((uint32_t)(h->g.own_hi / CORE) * (uint32_t)h->g.tiles_x) << 10;
   up.base[0] = (uint32_t)h->n; up.base[1] = (uint32_t)(h->n + cap); up.cap = (uint32_t)cap;
-  for (int d = 0; d < 2; ++d) { up.msg[d] = (const uint8_t*)h->rx_buf[d].p; up.pre[d] = (uint32_t*)h->rx_pre[d].p; }
+  for (int d = 0; d < 2; ++d) { up.msg[d] = rx_msg[d]; up.pre[d] = (uint32_t*)h->rx_pre[d].p; }
   up.hdr = hdr;
   up.sub_off = (uint32_t*)h->sub_off[cur].p; up.sub_cnt = (uint32_t*)h->sub_cnt[cur].p;
   up.cell = (uint32_t*)h->cell[cur].p; up.id = (uint32_t*)h->id[cur].p; up.energy = (double*)h->energy[cur].p; up.state = (uint8_t*)h->state.p;
@@ -956,11 +1058,18 @@ static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce 
   pk.state = (const uint8_t*)h->state.p;
   for (int d = 0; d < 2; ++d) { pk.pre[d] = (const uint32_t*)h->sx_pre[d].p; pk.out[d] = (uint8_t*)h->sx_st[d].p; }
   launch_foreach(h->stream, pk, 2 * (uint64_t)nsx);
+  const uint8_t* rx_st[2] = {(const uint8_t*)h->rx_st[0].p, (const uint8_t*)h->rx_st[1].p};
   { ProfScope ps(h->prof, h->stream, "decision_exchange", 2 * cap);
+#ifndef ABM_EMU
+    if (h->p2p_on) {
+      if (d_allreduce && (rc = p2p_allreduce(h, n_allreduce))) return rc;
+      if ((rc = p2p_exchange(h, P2P_CH_STATE, h->sx_st[0].p, cap, h->sx_st[1].p, cap, &rx_st[0], &rx_st[1]))) return rc;
+    } else
+#endif
     if ((rc = comm_sendrecv(h, h->sx_st[0].p, cap, h->sx_st[1].p, cap, h->rx_st[0].p, cap, h->rx_st[1].p, cap, d_allreduce, n_allreduce))) return rc; }
   MergeStatesBody mg;
   for (int d = 0; d < 2; ++d) {
-    mg.incoming[d] = (const uint8_t*)h->rx_st[d].p; mg.base[d] = (uint32_t)(h->n + (uint64_t)d * cap);
+    mg.incoming[d] = rx_st[d]; mg.base[d] = (uint32_t)(h->n + (uint64_t)d * cap);
     mg.total[d] = (const uint32_t*)h->rx_pre[d].p + nsx;
   }
   mg.present[0] = h->has_prev ? 1 : 0; mg.present[1] = h->has_next ? 1 : 0;
@@ -971,7 +1080,12 @@ static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce 
 
 /* the figures of StripStatsBody from every rank: one all-reduce on device data, one read-back */
 /* true when the all-reduce of the counters can stay on the device (NCCL, or a ring of one) */
-static bool strip_stats_on_device(abm_handle* h) { return h->nccl_comm != nullptr || h->n_ranks == 1; }
+static bool strip_stats_on_device(abm_handle* h) {
+#ifndef ABM_EMU
+  if (h->p2p_on) return true;
+#endif
+  return h->nccl_comm != nullptr || h->n_ranks == 1;
+}
 
 static void strip_stats_kernel(abm_handle* h, const uint32_t* d_pending) {
   uint32_t* ctr = (uint32_t*)h->counters.p;
@@ -989,6 +1103,10 @@ static int strip_stats_enqueue(abm_handle* h, const uint32_t* d_pending, bool wi
   unsigned long long* d = (unsigned long long*)h->red_buf.p;
   strip_stats_kernel(h, d_pending);
 #ifndef ABM_EMU
+  if (h->p2p_on) {
+    if (with_state_exchange) return strip_exchange_states(h, d, nv);
+    return p2p_allreduce(h, nv);
+  }
   if (h->nccl_comm) {
     if (with_state_exchange) return strip_exchange_states(h, d, nv);
     ABM_NCCL(h, g_nccl.AllReduce(d, d, (size_t)nv, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
@@ -1007,6 +1125,12 @@ static int strip_stats(abm_handle* h, const uint32_t* d_pending, std::vector<uin
   strip_stats_kernel(h, d_pending);
   out.assign((size_t)nv, 0);
 #ifndef ABM_EMU
+  if (h->p2p_on) {
+    if (with_state_exchange) { if ((rc = strip_exchange_states(h, d, nv))) return rc; }
+    else if ((rc = p2p_allreduce(h, nv))) return rc;
+    ABM_CK(h, copy_d2h(out.data(), d, (size_t)nv * 8, h->stream));
+    return 0;
+  }
   if (h->nccl_comm) {
     if (with_state_exchange) { if ((rc = strip_exchange_states(h, d, nv))) return rc; } /* same NCCL group as the decision bytes */
     else ABM_NCCL(h, g_nccl.AllReduce(d, d, (size_t)nv, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
@@ -1038,7 +1162,10 @@ static int strip_birth_ids(abm_handle* h, uint64_t bbcap, int nxt, uint32_t* d_t
   } else {
     bool done = false;
 #ifndef ABM_EMU
-    if (h->nccl_comm) {
+    if (h->p2p_on) {
+      if ((rc = p2p_allgather_births(h, msg, all, words))) return rc;
+      done = true;
+    } else if (h->nccl_comm) {
       ABM_NCCL(h, g_nccl.AllGather(msg, all, (size_t)words, ncclUint32, (ncclComm_t)h->nccl_comm, h->stream));
       done = true;
     }
@@ -1120,7 +1247,7 @@ static int tick_tile(abm_handle* h) {
   };
   bool overlapped = false;
 #ifndef ABM_EMU
-  if (h->strip && h->nccl_comm && h->stream2 && needs_resolve && core_rows >= 3 && n > 0) {
+  if (h->strip && (h->nccl_comm || h->p2p_on) && h->stream2 && h->overlap_halo && needs_resolve && core_rows >= 3 && n > 0) {
     /* the halo exchange travels on a second stream while the core rows that cannot see a ghost row are resolved */
     ABM_CK(h, cudaEventRecord(h->ev_proposed, h->stream));
     ABM_CK(h, cudaStreamWaitEvent(h->stream2, h->ev_proposed, 0));
@@ -1381,6 +1508,8 @@ void ABM_API(destroy)(abm_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); }
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+  for (int r = 0; r < P2P_MAXP; ++r) if (h->p2p_peer[r] && h->p2p_peer[r] != h->p2p_mine) cudaIpcCloseMemHandle(h->p2p_peer[r]);
+  if (h->p2p_mine) cudaFree(h->p2p_mine);
   if (h->ev_proposed) cudaEventDestroy(h->ev_proposed);
   if (h->ev_halo) cudaEventDestroy(h->ev_halo);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
@@ -1460,6 +1589,7 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
                              cfg->nx >= 2 * CORE && cfg->ny >= 2 * CORE);
   h->nsx = g.nx / SUB; h->nsy = g.ny / SUB;
   if (const char* mg = getenv("ABM_MIGRANTS")) h->use_migrants = atoi(mg) != 0;
+  if (const char* ov = getenv("ABM_OVERLAP")) h->overlap_halo = atoi(ov) != 0;
   if (const char* op = getenv("ABM_OPTIMISTIC")) h->optimistic = atoi(op) != 0;
   if (const char* ar = getenv("ABM_AGENT_ROUNDS")) { const int q = atoi(ar); if (q >= 0 && q <= 16) h->fixed_agent_rounds = q; }
   if (const char* tm = getenv("ABM_TILE_MARGIN")) { const int q = atoi(tm); if (q >= 2 && q <= HALO) h->tile_margin = q; }
@@ -1960,6 +2090,60 @@ int ABM_API(comm_init_nccl)(abm_handle* h, const void* unique_id128) {
   return ABM_OK;
 #else
   ABM_FAIL(h, ABM_E_STATE, "NCCL is not part of the emulation build");
+#endif
+}
+
+int ABM_API(p2p_export)(abm_handle* h, void* handle64) {
+  if (!h || !handle64) return ABM_E_BADARG;
+#ifndef ABM_EMU
+  if (!h->strip || h->n_ranks < 2 || h->n_ranks > P2P_MAXP) ABM_FAIL(h, ABM_E_STATE, "abm_p2p_export needs a strip handle with 2..%d ranks", (int)P2P_MAXP);
+  if (!h->agents_set) ABM_FAIL(h, ABM_E_STATE, "abm_set_agents must precede abm_p2p_export (the mailbox is sized from the population)");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (!h->p2p_mine) {
+    h->p2p_capmax = std::max<uint64_t>(1u << 16, h->n / 4 + 4096);   /* agents per boundary row the mailbox can carry */
+    h->p2p_birthmax = std::max<uint64_t>(1u << 16, h->n / 8 + 4096);
+    h->p2p_lay.agents_bytes = (strip_msg_bytes(h->nsx, h->p2p_capmax) + 255) & ~(uint64_t)255;
+    h->p2p_lay.state_bytes = (h->p2p_capmax + 255) & ~(uint64_t)255;
+    h->p2p_lay.births_bytes = ((1 + h->p2p_birthmax) * 4 + 255) & ~(uint64_t)255;
+    ABM_CK(h, cudaMalloc((void**)&h->p2p_mine, h->p2p_lay.total_bytes()));
+    ABM_CK(h, cudaMemset(h->p2p_mine, 0, h->p2p_lay.total_bytes()));
+    ABM_CK(h, cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t mh;
+  ABM_CK(h, cudaIpcGetMemHandle(&mh, h->p2p_mine));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &mh, 64);
+  return ABM_OK;
+#else
+  ABM_FAIL(h, ABM_E_STATE, "peer-memory transport is not part of the emulation build");
+#endif
+}
+
+int ABM_API(p2p_connect)(abm_handle* h, const void* handles, int32_t n) {
+  if (!h || !handles) return ABM_E_BADARG;
+#ifndef ABM_EMU
+  if (!h->p2p_mine || n != h->n_ranks) ABM_FAIL(h, ABM_E_STATE, "abm_p2p_connect needs abm_p2p_export first and one handle per rank");
+  int rc = set_device(h);
+  if (rc) return rc;
+  for (int r = 0; r < n; ++r) {
+    if (r == h->my_rank) { h->p2p_peer[r] = h->p2p_mine; continue; }
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, (const uint8_t*)handles + 64 * r, 64);
+    void* p = nullptr;
+    ABM_CK(h, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->p2p_peer[r] = (uint8_t*)p;
+  }
+  if (!h->stream2) {
+    ABM_CK(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    ABM_CK(h, cudaEventCreateWithFlags(&h->ev_proposed, cudaEventDisableTiming));
+    ABM_CK(h, cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+  }
+  h->p2p_on = true;
+  return ABM_OK;
+#else
+  (void)n;
+  ABM_FAIL(h, ABM_E_STATE, "peer-memory transport is not part of the emulation build");
 #endif
 }
 

@@ -145,7 +145,7 @@ struct View {
   uint32_t* remote_dest;     /* per agent: final tcell */
 };
 
-enum { ERR_NOWALKABLE = 1, ERR_INTERNAL = 2, ERR_STRIP_CAP = 4 };
+enum { ERR_NOWALKABLE = 1, ERR_INTERNAL = 2, ERR_STRIP_CAP = 4, ERR_P2P_TIMEOUT = 8 };
 
 ABM_HD bool walkable(const View& v, uint32_t c) { return (v.walkbits[c >> 5] >> (c & 31)) & 1u; }
 ABM_HD bool present(uint8_t s) { return !(s & ST_DEAD) || (s & ST_BIRTH); }

@@ -1,0 +1,102 @@
+/*
+ * abm_p2p.h — ring exchange and tiny collectives of the row strips as plain kernels over NVLink peer memory.
+ *
+ * No reference counterpart (the reference is one process).  Each rank owns a "mailbox" in device memory that the
+ * other ranks of the node map through CUDA IPC.  A sender's kernel stores its message straight into the receiver's
+ * mailbox and then publishes a sequence number there; the receiver's next kernel spins on that number (with a
+ * time-out) and reads the data locally.  Every channel is used symmetrically once per round (both sides send, then
+ * wait), so two buffers per channel, alternating with the sequence number, are enough: a sender can only reach
+ * round s + 2 after it has seen the receiver's round s + 1, which the receiver issued behind its reads of round s.
+ * Compared with NCCL send/recv + all-reduce this removes the host-side cost of ~5 NCCL groups per tick.
+ */
+#ifndef ABM_P2P_H_
+#define ABM_P2P_H_
+#ifndef ABM_EMU
+
+#include "abm_kernels.h"
+
+namespace abm {
+
+enum { P2P_MAXP = 8, P2P_STATS_WORDS = 32, P2P_FLAG_STRIDE = 32 /* u32: one 128-byte line per flag */ };
+enum { P2P_CH_AGENTS = 0, P2P_CH_STATE = 1, P2P_CH_STATS = 2, P2P_CH_BIRTHS = 3 };
+
+struct P2PLayout {
+  uint64_t agents_bytes, state_bytes, births_bytes; /* capacity of one buffer of each kind */
+  uint64_t flag_off(int ch, int slot, int parity) const { return (uint64_t)(((ch * P2P_MAXP + slot) * 2 + parity) * P2P_FLAG_STRIDE) * 4; }
+  uint64_t flags_bytes() const { return (uint64_t)(4 * P2P_MAXP * 2 * P2P_FLAG_STRIDE) * 4; }
+  uint64_t agents_off(int dir, int parity) const { return flags_bytes() + (uint64_t)(dir * 2 + parity) * agents_bytes; }
+  uint64_t state_off(int dir, int parity) const { return agents_off(2, 0) + (uint64_t)(dir * 2 + parity) * state_bytes; }
+  uint64_t stats_off(int src, int parity) const { return state_off(2, 0) + (uint64_t)(src * 2 + parity) * P2P_STATS_WORDS * 8; }
+  uint64_t births_off(int src, int parity) const { return stats_off(P2P_MAXP, 0) + (uint64_t)(src * 2 + parity) * births_bytes; }
+  uint64_t total_bytes() const { return births_off(P2P_MAXP, 0); }
+};
+
+ABM_D uint32_t ld_flag(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+
+/* up to two messages in one launch: 16-byte words straight into the neighbours' mailboxes */
+struct P2PCopyBody {
+  const uint4* src[2]; uint4* dst[2]; uint64_t words[2];
+  ABM_HD void operator()(uint64_t i) const {
+    if (i < words[0]) dst[0][i] = src[0][i];
+    else { const uint64_t k = i - words[0]; if (k < words[1]) dst[1][k] = src[1][k]; }
+  }
+};
+/* after the copy kernel (stream order): make the data visible, then publish the sequence number in every target */
+struct P2PPublishBody {
+  uint32_t* flag[P2P_MAXP]; int32_t n; uint32_t seq;
+  ABM_HD void operator()(uint64_t i) const {
+    if ((int)i >= n) return;
+    __threadfence_system();
+    *(volatile uint32_t*)flag[i] = seq;
+  }
+};
+/* one thread per awaited flag */
+struct P2PWaitBody {
+  const uint32_t* flag[P2P_MAXP]; int32_t n; uint32_t seq; uint32_t* err; long long limit;
+  ABM_HD void operator()(uint64_t i) const {
+    if ((int)i >= n) return;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_flag(flag[i]) - seq) < 0) {
+      if (clock64() - t0 > limit) { atomic_or(err, ERR_P2P_TIMEOUT); break; }
+      __nanosleep(64);
+    }
+    __threadfence_system();
+  }
+};
+/* all-to-all of the small counter vector: thread (p, w) stores word w into peer p's slot for this rank */
+struct P2PStatsSendBody {
+  const unsigned long long* local; unsigned long long* dst[P2P_MAXP]; int32_t n_peers, nv;
+  ABM_HD void operator()(uint64_t i) const {
+    const int p = (int)(i / (uint64_t)nv), w = (int)(i % (uint64_t)nv);
+    if (p < n_peers) dst[p][w] = local[w];
+  }
+};
+/* after the wait: out[w] = sum over every rank's vector (this rank's own included) */
+struct P2PStatsSumBody {
+  const unsigned long long* src[P2P_MAXP]; int32_t n_src, nv; unsigned long long* out;
+  ABM_HD void operator()(uint64_t w) const {
+    if ((int)w >= nv) return;
+    unsigned long long s = 0;
+    for (int q = 0; q < n_src; ++q) s += src[q][w];
+    out[w] = s;
+  }
+};
+/* all-gather of the offspring messages: thread (p, w) stores word w of this rank's message into peer p's slot */
+struct P2PBirthSendBody {
+  const uint32_t* local; uint32_t* dst[P2P_MAXP]; int32_t n_peers; uint32_t words;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t p = (uint32_t)(i / words), w = (uint32_t)(i % words);
+    if ((int)p < n_peers) dst[p][w] = local[w];
+  }
+};
+struct P2PBirthGatherBody { /* mailbox slots -> the contiguous n_ranks x words array the rank kernel reads */
+  const uint32_t* src[P2P_MAXP]; int32_t n_ranks; uint32_t words; uint32_t* all;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t r = (uint32_t)(i / words), w = (uint32_t)(i % words);
+    if ((int)r < n_ranks) all[i] = src[r][w];
+  }
+};
+
+}  // namespace abm
+#endif /* ABM_EMU */
+#endif /* ABM_P2P_H_ */

@@ -152,3 +152,17 @@ def init_nccl(engine, device=None):
     t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
     dist.broadcast(t, 0)
     engine.comm_init_nccl(bytes(t.cpu().numpy().tobytes()))
+
+
+def init_p2p(engine):
+    """Peer-memory transport (NVLink): every rank exports the CUDA IPC handle of its mailbox, the handles are
+    all-gathered through the default torch.distributed group, every rank maps its peers' mailboxes."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    mine = torch.frombuffer(bytearray(engine.p2p_export()), dtype=torch.uint8)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    parts = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(parts, mine.to(dev))
+    engine.p2p_connect(b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts), world)
+    dist.barrier()

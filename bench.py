@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS) + ["C4"])
+    ap.add_argument("--transport", default=os.environ.get("ABM_TRANSPORT", "nccl"), choices=["nccl", "p2p"], help="multi-GPU halo transport")
     ap.add_argument("--replans", type=int, default=1 << 14)
     ap.add_argument("--ref-replans", type=int, default=64)
     ap.add_argument("--max-dist", type=int, default=0)
@@ -257,7 +258,7 @@ def main():
         eng.ny = size + 2 * strips.GHOST
         eng.set_grid(pad(w["fully_grown"]), pad(w["countdown"]))
         eng.set_agents(w["ids"] + rank * agents, w["x"], w["y"] + size * rank, w["energy"], agents * world + 1)
-        strips.init_nccl(eng)
+        (strips.init_p2p if args.transport == "p2p" else strips.init_nccl)(eng)
     else:
         eng = load(lib, cfg, w, device=local)
     eng.set_profiling(True)
@@ -380,7 +381,7 @@ def main():
             "dtype": "int32 cells / f64 energy", "data": "synthetic",
             "config": {"workload": wl["desc"].format(n=size, a=agents), "grid": [size, size], "agents": agents, "ticks": args.steps,
                        "l2": "flushed between ticks (256 MiB device write)" if flush is not None else "not flushed",
-                       "parallelism": "single GPU" if world == 1 else f"{world} row strips of a {size}x{size * world} grid, one per GPU, NCCL halo exchange inside abm_step",
+                       "parallelism": "single GPU" if world == 1 else f"{world} row strips of a {size}x{size * world} grid, one per GPU, halo exchange inside abm_step over " + ("NVLink peer memory (kernel stores into the neighbours' mailboxes)" if args.transport == "p2p" else "NCCL"),
                        "cells_per_s": G * world * args.steps / (ms_max * 1e-3), "resolution_rounds_per_tick": rounds / args.steps},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "agent-updates/s", "h2d_bytes_per_step": h2d // args.e2e_steps, "d2h_bytes_per_step": d2h // args.e2e_steps,

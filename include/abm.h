@@ -200,6 +200,14 @@ int abm_set_transport(abm_handle* h, const abm_transport* t);
 int abm_nccl_unique_id(void* out128);
 int abm_comm_init_nccl(abm_handle* h, const void* unique_id128);
 
+/* Peer-memory transport for the GPUs of one node (NVLink / NVSwitch): kernels store the boundary rows, decision bytes and
+ * the small per-round counters straight into the neighbours' "mailboxes" and publish sequence numbers there — no NCCL
+ * call, no host staging.  After abm_set_agents every rank calls abm_p2p_export (a 64-byte CUDA IPC handle of its
+ * mailbox), the host all-gathers the handles (n_ranks x 64 bytes, rank order) and every rank calls abm_p2p_connect.
+ * A neighbour that does not deliver within a few seconds makes abm_step fail with ABM_E_CUDA instead of hanging. */
+int abm_p2p_export(abm_handle* h, void* handle64);
+int abm_p2p_connect(abm_handle* h, const void* handles, int32_t n_ranks);
+
 /* message for the last failing call on h (or on creation when h == NULL); valid until the next call */
 const char* abm_last_error(abm_handle* h);
 

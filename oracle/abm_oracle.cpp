@@ -688,6 +688,8 @@ int oracle_get_timing(oracle_handle* h, double* out, int32_t n) {
 int oracle_set_transport(oracle_handle*, const abm_transport*) { return ABM_E_STATE; } /* the oracle is one process, like the reference */
 int oracle_nccl_unique_id(void*) { return ABM_E_STATE; }
 int oracle_comm_init_nccl(oracle_handle*, const void*) { return ABM_E_STATE; }
+int oracle_p2p_export(oracle_handle*, void*) { return ABM_E_STATE; }
+int oracle_p2p_connect(oracle_handle*, const void*, int32_t) { return ABM_E_STATE; }
 int oracle_set_profiling(oracle_handle*, int32_t) { return 0; }
 int oracle_get_kernel_stat(oracle_handle*, int32_t, char*, int32_t, double*, int64_t*, int64_t*) { return ABM_E_SMALL; }
 const char* oracle_last_error(oracle_handle*) { return ""; }

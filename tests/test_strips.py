@@ -39,7 +39,7 @@ def test_single_strip_ring_of_one(emu, oracle, name):
         assert_same_state(strips.merge_snapshots([strips.strip_snapshot(b)]), a.snapshot(), f"{name} tick {t}")
 
 
-def _ring_worker(rank, world, name, ticks, port, out_dir, use_gpu):
+def _ring_worker(rank, world, name, ticks, port, out_dir, use_gpu, transport="nccl"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -57,7 +57,9 @@ def _ring_worker(rank, world, name, ticks, port, out_dir, use_gpu):
     if use_gpu:
         cfgkw = dict(cfgkw, device=rank)
     e = strips.load_strip(lib, cfgkw, w, world, rank)
-    if use_gpu:
+    if use_gpu and transport == "p2p":
+        strips.init_p2p(e)
+    elif use_gpu:
         strips.init_nccl(e)
     else:
         tr = strips.DistTransport()
@@ -71,10 +73,10 @@ def _ring_worker(rank, world, name, ticks, port, out_dir, use_gpu):
     dist.destroy_process_group()
 
 
-def _run_ring(world, name, ticks, tmp_path, use_gpu=False):
+def _run_ring(world, name, ticks, tmp_path, use_gpu=False, transport="nccl"):
     import torch.multiprocessing as mp
     port = 29500 + (os.getpid() + world * 7 + len(name)) % 400
-    mp.spawn(_ring_worker, args=(world, name, ticks, port, str(tmp_path), use_gpu), nprocs=world, join=True)
+    mp.spawn(_ring_worker, args=(world, name, ticks, port, str(tmp_path), use_gpu, transport), nprocs=world, join=True)
     return [np.load(os.path.join(str(tmp_path), f"snap_{r}.npy"), allow_pickle=True) for r in range(world)]
 
 
@@ -110,6 +112,22 @@ def test_two_strips_over_nccl(libabm, oracle, tmp_path, name):
         pytest.skip("needs 2 GPUs")
     ticks = 8
     per_rank = _run_ring(2, name, ticks, tmp_path, use_gpu=True)
+    cfgkw, w = _case(name)
+    a = load_case(oracle, cfgkw, w)
+    for t in range(ticks):
+        a.step(1)
+        assert_same_state(strips.merge_snapshots([per_rank[r][t] for r in range(2)]), a.snapshot(), f"{name} tick {t}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["rw", "gregarious", "walkmap", "rw_clamped"])
+def test_two_strips_over_peer_memory(libabm, oracle, tmp_path, name):
+    """The NVLink mailbox transport (abm_p2p_export / abm_p2p_connect): kernels store into the neighbour's memory."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ticks = 8
+    per_rank = _run_ring(2, name, ticks, tmp_path, use_gpu=True, transport="p2p")
     cfgkw, w = _case(name)
     a = load_case(oracle, cfgkw, w)
     for t in range(ticks):
