@@ -957,23 +957,50 @@ static int p2p_allreduce(abm_handle* h, int nv) {
   return check_launch(h, "peer all-reduce");
 }
 
-/* every rank's offspring message (words u32 at msg) into all[rank * words ...] */
-static int p2p_allgather_births(abm_handle* h, const uint32_t* msg, uint32_t* all, uint64_t words) {
-  if (words * 4 > h->p2p_lay.births_bytes) ABM_FAIL(h, ABM_E_CAPACITY, "offspring message (%llu ids) exceeds the mailbox allocated at abm_p2p_export", (unsigned long long)words);
+/* the counters of this round from every rank, summed into red_buf: two launches (send + publish, wait + sum [+ guard]) */
+static int p2p_stats(abm_handle* h, const uint32_t* d_pending, uint32_t* go, uint32_t birth_cap) {
+  const uint32_t seq = ++h->p2p_seq[P2P_CH_STATS];
+  const int parity = (int)(seq & 1u), P = h->n_ranks;
+  uint32_t* ctr = (uint32_t*)h->counters.p;
+  P2PStatsSendCta sc;
+  sc.pending = d_pending; sc.birth_flags = ctr + CTR_BIRTH_FLAGS;
+  sc.tot_up = (const uint32_t*)h->sx_pre[0].p + h->nsx; sc.tot_down = (const uint32_t*)h->sx_pre[1].p + h->nsx;
+  sc.n_ranks = P; sc.rank = h->my_rank; sc.seq = seq;
+  for (int r = 0; r < P; ++r) {
+    sc.dst[r] = (unsigned long long*)(h->p2p_peer[r] + h->p2p_lay.stats_off(h->my_rank, parity));
+    sc.flag[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.flag_off(P2P_CH_STATS, h->my_rank, parity));
+  }
+  launch_cta(h->stream, sc, 1, 64, P2P_STATS_WORDS * 8);
+  P2PStatsRecvCta rc_;
+  rc_.n_ranks = P; rc_.seq = seq; rc_.out = (unsigned long long*)h->red_buf.p; rc_.err = ctr + CTR_ERR; rc_.go = go; rc_.birth_cap = birth_cap;
+  for (int r = 0; r < P; ++r) {
+    rc_.src[r] = (const unsigned long long*)(h->p2p_mine + h->p2p_lay.stats_off(r, parity));
+    rc_.flag[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.flag_off(P2P_CH_STATS, r, parity));
+  }
+  launch_cta(h->stream, rc_, 1, 64, 16);
+  return check_launch(h, "peer counters");
+}
+
+/* every rank's offspring message [count, parent ids ...] (at most cap ids) into all[rank * (1 + cap) ...] */
+static int p2p_allgather_births(abm_handle* h, uint32_t* all, uint64_t cap) {
+  if ((1 + cap) * 4 > h->p2p_lay.births_bytes) ABM_FAIL(h, ABM_E_CAPACITY, "offspring message (%llu ids) exceeds the mailbox allocated at abm_p2p_export", (unsigned long long)cap);
   const uint32_t seq = ++h->p2p_seq[P2P_CH_BIRTHS];
   const int parity = (int)(seq & 1u), P = h->n_ranks;
-  P2PBirthSendBody sb;
-  sb.local = msg; sb.n_peers = P; sb.words = (uint32_t)words;
-  for (int r = 0; r < P; ++r) sb.dst[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.births_off(h->my_rank, parity));
-  launch_foreach(h->stream, sb, (uint64_t)P * words);
-  int targets[P2P_MAXP], tslot[P2P_MAXP], sources[P2P_MAXP];
-  for (int r = 0; r < P; ++r) { targets[r] = r; tslot[r] = h->my_rank; sources[r] = r; }
-  int rc = p2p_publish_wait(h, P2P_CH_BIRTHS, seq, targets, tslot, P, sources, P);
-  if (rc) return rc;
-  P2PBirthGatherBody gb;
-  gb.n_ranks = P; gb.words = (uint32_t)words; gb.all = all;
-  for (int r = 0; r < P; ++r) gb.src[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.births_off(r, parity));
-  launch_foreach(h->stream, gb, (uint64_t)P * words);
+  uint32_t* ctr = (uint32_t*)h->counters.p;
+  P2PBirthSendCta sc;
+  sc.birth_parent = (const uint32_t*)h->birth_parent.p; sc.birth_count = ctr + CTR_BIRTHS; sc.cap = (uint32_t)cap; sc.n_ranks = P; sc.seq = seq;
+  for (int r = 0; r < P; ++r) {
+    sc.dst[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.births_off(h->my_rank, parity));
+    sc.flag[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.flag_off(P2P_CH_BIRTHS, h->my_rank, parity));
+  }
+  launch_cta(h->stream, sc, 1, 256, 16);
+  P2PBirthRecvCta rv;
+  rv.n_ranks = P; rv.seq = seq; rv.cap = (uint32_t)cap; rv.all = all; rv.err = ctr + CTR_ERR;
+  for (int r = 0; r < P; ++r) {
+    rv.src[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.births_off(r, parity));
+    rv.flag[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.flag_off(P2P_CH_BIRTHS, r, parity));
+  }
+  launch_cta(h->stream, rv, 1, 256, 16);
   return check_launch(h, "peer all-gather");
 }
 #endif
@@ -1021,31 +1048,46 @@ static int strip_exchange_agents(abm_handle* h) {
   StripPackCta pk;
   pk.si = sub_index(h, cur); pk.row[0] = h->g.own_lo / SUB; pk.row[1] = h->g.own_hi / SUB - 1; pk.tiles_x = h->g.tiles_x; pk.cap = (uint32_t)cap;
   pk.cell = (const uint32_t*)h->cell[cur].p; pk.id = (const uint32_t*)h->id[cur].p; pk.energy = (const double*)h->energy[cur].p; pk.state = (const uint8_t*)h->state.p;
-  for (int d = 0; d < 2; ++d) { pk.msg[d] = (uint8_t*)h->sx_buf[d].p; pk.pre[d] = (uint32_t*)h->sx_pre[d].p; }
-  pk.hdr = hdr; pk.err = err;
-  launch_cta(h->stream, pk, 2, TILE_THREADS, StripPackCta::smem_bytes());
-  for (int d = 0; d < 2; ++d) ABM_CK(h, dev_memset(h->rx_buf[d].p, 0, hdr, h->stream)); /* a missing neighbour sends nothing */
-  if ((rc = check_launch(h, "strip pack"))) return rc;
-  const uint8_t* rx_msg[2] = {(const uint8_t*)h->rx_buf[0].p, (const uint8_t*)h->rx_buf[1].p};
-  { ProfScope ps(h->prof, h->stream, "halo_exchange", 2 * cap);
-#ifndef ABM_EMU
-    if (h->p2p_on) { if ((rc = p2p_exchange(h, P2P_CH_AGENTS, h->sx_buf[0].p, bytes, h->sx_buf[1].p, bytes, &rx_msg[0], &rx_msg[1]))) return rc; }
-    else
-#endif
-    if ((rc = comm_sendrecv(h, h->sx_buf[0].p, bytes, h->sx_buf[1].p, bytes, h->rx_buf[0].p, bytes, h->rx_buf[1].p, bytes))) return rc; }
+  for (int d = 0; d < 2; ++d) { pk.msg[d] = (uint8_t*)h->sx_buf[d].p; pk.pre[d] = (uint32_t*)h->sx_pre[d].p; pk.publish[d] = nullptr; }
+  pk.hdr = hdr; pk.err = err; pk.seq = 0;
   StripUnpackCta up;
   up.row[0] = h->g.own_lo / SUB - 1; up.row[1] = h->g.own_hi / SUB; up.nsx = nsx;
   up.tile_row_base[0] = ((uint32_t)(h->g.own_lo / CORE - 1) * (uint32_t)h->g.tiles_x) << 10;
   up.tile_row_base[1] = ((uint32_t)(h->g.own_hi / CORE) * (uint32_t)h->g.tiles_x) << 10;
   up.base[0] = (uint32_t)h->n; up.base[1] = (uint32_t)(h->n + cap); up.cap = (uint32_t)cap;
-  for (int d = 0; d < 2; ++d) { up.msg[d] = rx_msg[d]; up.pre[d] = (uint32_t*)h->rx_pre[d].p; }
-  up.hdr = hdr;
+  for (int d = 0; d < 2; ++d) { up.msg[d] = (const uint8_t*)h->rx_buf[d].p; up.pre[d] = (uint32_t*)h->rx_pre[d].p; up.wait[d] = nullptr; }
+  up.hdr = hdr; up.seq = 0;
   up.sub_off = (uint32_t*)h->sub_off[cur].p; up.sub_cnt = (uint32_t*)h->sub_cnt[cur].p;
   up.cell = (uint32_t*)h->cell[cur].p; up.id = (uint32_t*)h->id[cur].p; up.energy = (double*)h->energy[cur].p; up.state = (uint8_t*)h->state.p;
   up.err = err;
-  launch_cta(h->stream, up, 2, TILE_THREADS, StripUnpackCta::smem_bytes());
+  bool direct = false;
+#ifndef ABM_EMU
+  if (h->p2p_on) { /* the pack CTAs write straight into the neighbours' mailboxes and publish; the unpack CTAs wait for theirs */
+    if (bytes > h->p2p_lay.agents_bytes) ABM_FAIL(h, ABM_E_CAPACITY, "halo message (%llu bytes) exceeds the mailbox allocated at abm_p2p_export", (unsigned long long)bytes);
+    const uint32_t seq = ++h->p2p_seq[P2P_CH_AGENTS];
+    const int parity = (int)(seq & 1u);
+    const int prev = (h->my_rank + h->n_ranks - 1) % h->n_ranks, next = (h->my_rank + 1) % h->n_ranks;
+    const P2PLayout& L = h->p2p_lay;
+    pk.seq = up.seq = seq;
+    if (h->has_prev) { pk.msg[0] = h->p2p_peer[prev] + L.agents_off(1, parity); pk.publish[0] = (uint32_t*)(h->p2p_peer[prev] + L.flag_off(P2P_CH_AGENTS, 1, parity)); }
+    if (h->has_next) { pk.msg[1] = h->p2p_peer[next] + L.agents_off(0, parity); pk.publish[1] = (uint32_t*)(h->p2p_peer[next] + L.flag_off(P2P_CH_AGENTS, 0, parity)); }
+    for (int d = 0; d < 2; ++d) {
+      up.msg[d] = h->p2p_mine + L.agents_off(d, parity); /* a side without a neighbour keeps its zeroed header: an empty ghost row */
+      const bool has = d == 0 ? h->has_prev : h->has_next;
+      up.wait[d] = has ? (const uint32_t*)(h->p2p_mine + L.flag_off(P2P_CH_AGENTS, d, parity)) : nullptr;
+    }
+    direct = true;
+  }
+#endif
+  { ProfScope ps(h->prof, h->stream, "halo_exchange", 2 * cap);
+    launch_cta(h->stream, pk, 2, TILE_THREADS, StripPackCta::smem_bytes());
+    if (!direct) {
+      for (int d = 0; d < 2; ++d) ABM_CK(h, dev_memset(h->rx_buf[d].p, 0, hdr, h->stream)); /* a missing neighbour sends nothing */
+      if ((rc = comm_sendrecv(h, h->sx_buf[0].p, bytes, h->sx_buf[1].p, bytes, h->rx_buf[0].p, bytes, h->rx_buf[1].p, bytes))) return rc;
+    }
+    launch_cta(h->stream, up, 2, TILE_THREADS, StripUnpackCta::smem_bytes()); }
   h->n_ghost = 2 * cap; /* upper bound; the sub-tile index knows the real counts */
-  return check_launch(h, "strip unpack");
+  return check_launch(h, "strip halo exchange");
 }
 
 /* E2: the decision bytes of the same boundary rows (same order), merged into the ghost copies */
@@ -1053,32 +1095,47 @@ static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce 
   int rc;
   const int cur = h->cur, nsx = h->nsx;
   const uint64_t cap = h->bcap;
-  PackStatesBody pk;
+  uint32_t* err = (uint32_t*)h->counters.p + CTR_ERR;
+  PackStatesCta pk;
   pk.si = sub_index(h, cur); pk.row[0] = h->g.own_lo / SUB; pk.row[1] = h->g.own_hi / SUB - 1; pk.cap = (uint32_t)cap;
-  pk.state = (const uint8_t*)h->state.p;
-  for (int d = 0; d < 2; ++d) { pk.pre[d] = (const uint32_t*)h->sx_pre[d].p; pk.out[d] = (uint8_t*)h->sx_st[d].p; }
-  launch_foreach(h->stream, pk, 2 * (uint64_t)nsx);
-  const uint8_t* rx_st[2] = {(const uint8_t*)h->rx_st[0].p, (const uint8_t*)h->rx_st[1].p};
-  { ProfScope ps(h->prof, h->stream, "decision_exchange", 2 * cap);
-#ifndef ABM_EMU
-    if (h->p2p_on) {
-      if (d_allreduce && (rc = p2p_allreduce(h, n_allreduce))) return rc;
-      if ((rc = p2p_exchange(h, P2P_CH_STATE, h->sx_st[0].p, cap, h->sx_st[1].p, cap, &rx_st[0], &rx_st[1]))) return rc;
-    } else
-#endif
-    if ((rc = comm_sendrecv(h, h->sx_st[0].p, cap, h->sx_st[1].p, cap, h->rx_st[0].p, cap, h->rx_st[1].p, cap, d_allreduce, n_allreduce))) return rc; }
-  MergeStatesBody mg;
+  pk.state = (const uint8_t*)h->state.p; pk.seq = 0;
+  for (int d = 0; d < 2; ++d) { pk.pre[d] = (const uint32_t*)h->sx_pre[d].p; pk.out[d] = (uint8_t*)h->sx_st[d].p; pk.publish[d] = nullptr; }
+  MergeStatesCta mg;
+  mg.state = (uint8_t*)h->state.p; mg.err = err; mg.seq = 0;
   for (int d = 0; d < 2; ++d) {
-    mg.incoming[d] = rx_st[d]; mg.base[d] = (uint32_t)(h->n + (uint64_t)d * cap);
-    mg.total[d] = (const uint32_t*)h->rx_pre[d].p + nsx;
+    const bool has = d == 0 ? h->has_prev : h->has_next;
+    mg.incoming[d] = has ? (const uint8_t*)h->rx_st[d].p : nullptr; mg.base[d] = (uint32_t)(h->n + (uint64_t)d * cap);
+    mg.total[d] = (const uint32_t*)h->rx_pre[d].p + nsx; mg.wait[d] = nullptr;
   }
-  mg.present[0] = h->has_prev ? 1 : 0; mg.present[1] = h->has_next ? 1 : 0;
-  mg.state = (uint8_t*)h->state.p; mg.cap = (uint32_t)cap;
-  launch_foreach(h->stream, mg, 2 * cap);
-  return check_launch(h, "strip state merge");
+  bool direct = false;
+#ifndef ABM_EMU
+  if (h->p2p_on) {
+    if (cap > h->p2p_lay.state_bytes) ABM_FAIL(h, ABM_E_CAPACITY, "decision message exceeds the mailbox allocated at abm_p2p_export");
+    if (d_allreduce && (rc = p2p_allreduce(h, n_allreduce))) return rc;
+    const uint32_t seq = ++h->p2p_seq[P2P_CH_STATE];
+    const int parity = (int)(seq & 1u);
+    const int prev = (h->my_rank + h->n_ranks - 1) % h->n_ranks, next = (h->my_rank + 1) % h->n_ranks;
+    const P2PLayout& L = h->p2p_lay;
+    pk.seq = mg.seq = seq;
+    pk.out[0] = h->has_prev ? h->p2p_peer[prev] + L.state_off(1, parity) : nullptr;
+    pk.out[1] = h->has_next ? h->p2p_peer[next] + L.state_off(0, parity) : nullptr;
+    pk.publish[0] = h->has_prev ? (uint32_t*)(h->p2p_peer[prev] + L.flag_off(P2P_CH_STATE, 1, parity)) : nullptr;
+    pk.publish[1] = h->has_next ? (uint32_t*)(h->p2p_peer[next] + L.flag_off(P2P_CH_STATE, 0, parity)) : nullptr;
+    for (int d = 0; d < 2; ++d) {
+      const bool has = d == 0 ? h->has_prev : h->has_next;
+      mg.incoming[d] = has ? h->p2p_mine + L.state_off(d, parity) : nullptr;
+      mg.wait[d] = has ? (const uint32_t*)(h->p2p_mine + L.flag_off(P2P_CH_STATE, d, parity)) : nullptr;
+    }
+    direct = true;
+  }
+#endif
+  { ProfScope ps(h->prof, h->stream, "decision_exchange", 2 * cap);
+    launch_cta(h->stream, pk, 2, TILE_THREADS, 16);
+    if (!direct && (rc = comm_sendrecv(h, h->sx_st[0].p, cap, h->sx_st[1].p, cap, h->rx_st[0].p, cap, h->rx_st[1].p, cap, d_allreduce, n_allreduce))) return rc;
+    launch_cta(h->stream, mg, 2, TILE_THREADS, 16); }
+  return check_launch(h, "strip decision exchange");
 }
 
-/* the figures of StripStatsBody from every rank: one all-reduce on device data, one read-back */
 /* true when the all-reduce of the counters can stay on the device (NCCL, or a ring of one) */
 static bool strip_stats_on_device(abm_handle* h) {
 #ifndef ABM_EMU
@@ -1097,16 +1154,18 @@ static void strip_stats_kernel(abm_handle* h, const uint32_t* d_pending) {
 }
 
 /* counters all-reduced into red_buf and (optionally) the decision exchange, without any read-back */
-static int strip_stats_enqueue(abm_handle* h, const uint32_t* d_pending, bool with_state_exchange) {
+static int strip_stats_enqueue(abm_handle* h, const uint32_t* d_pending, bool with_state_exchange, uint32_t* go = nullptr, uint32_t guard_cap = 0) {
   int rc;
   const int nv = 1 + 3 * h->n_ranks;
   unsigned long long* d = (unsigned long long*)h->red_buf.p;
+#ifndef ABM_EMU
+  if (h->p2p_on) { /* counters (with the commit guard folded into the receiving kernel), then the decision bytes */
+    if ((rc = p2p_stats(h, d_pending, go, guard_cap))) return rc;
+    return with_state_exchange ? strip_exchange_states(h) : 0;
+  }
+#endif
   strip_stats_kernel(h, d_pending);
 #ifndef ABM_EMU
-  if (h->p2p_on) {
-    if (with_state_exchange) return strip_exchange_states(h, d, nv);
-    return p2p_allreduce(h, nv);
-  }
   if (h->nccl_comm) {
     if (with_state_exchange) return strip_exchange_states(h, d, nv);
     ABM_NCCL(h, g_nccl.AllReduce(d, d, (size_t)nv, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
@@ -1122,15 +1181,17 @@ static int strip_stats(abm_handle* h, const uint32_t* d_pending, std::vector<uin
   int rc;
   const int P = h->n_ranks, nv = 1 + 3 * P;
   unsigned long long* d = (unsigned long long*)h->red_buf.p;
-  strip_stats_kernel(h, d_pending);
   out.assign((size_t)nv, 0);
 #ifndef ABM_EMU
   if (h->p2p_on) {
-    if (with_state_exchange) { if ((rc = strip_exchange_states(h, d, nv))) return rc; }
-    else if ((rc = p2p_allreduce(h, nv))) return rc;
+    if ((rc = p2p_stats(h, d_pending, nullptr, 0))) return rc;
+    if (with_state_exchange && (rc = strip_exchange_states(h))) return rc;
     ABM_CK(h, copy_d2h(out.data(), d, (size_t)nv * 8, h->stream));
     return 0;
   }
+#endif
+  strip_stats_kernel(h, d_pending);
+#ifndef ABM_EMU
   if (h->nccl_comm) {
     if (with_state_exchange) { if ((rc = strip_exchange_states(h, d, nv))) return rc; } /* same NCCL group as the decision bytes */
     else ABM_NCCL(h, g_nccl.AllReduce(d, d, (size_t)nv, ncclUint64, ncclSum, (ncclComm_t)h->nccl_comm, h->stream));
@@ -1154,18 +1215,25 @@ static int strip_birth_ids(abm_handle* h, uint64_t bbcap, int nxt, uint32_t* d_t
   uint32_t* msg = (uint32_t*)h->birth_ids.p;
   uint32_t* all = msg + words;
   uint32_t* ctr = (uint32_t*)h->counters.p;
-  BirthPackBody bp;
-  bp.birth_parent = (const uint32_t*)h->birth_parent.p; bp.birth_count = ctr + CTR_BIRTHS; bp.cap = (uint32_t)bbcap; bp.msg = msg;
-  launch_foreach(h->stream, bp, bbcap ? bbcap : 1);
-  if (P == 1) {
+  bool packed_remotely = false;
+#ifndef ABM_EMU
+  if (h->p2p_on && P > 1) {
+    if ((rc = p2p_allgather_births(h, all, bbcap))) return rc;
+    packed_remotely = true;
+  }
+#endif
+  if (!packed_remotely) {
+    BirthPackBody bp;
+    bp.birth_parent = (const uint32_t*)h->birth_parent.p; bp.birth_count = ctr + CTR_BIRTHS; bp.cap = (uint32_t)bbcap; bp.msg = msg;
+    launch_foreach(h->stream, bp, bbcap ? bbcap : 1);
+  }
+  if (packed_remotely) {
+  } else if (P == 1) {
     ABM_CK(h, copy_d2d(all, msg, words * 4, h->stream));
   } else {
     bool done = false;
 #ifndef ABM_EMU
-    if (h->p2p_on) {
-      if ((rc = p2p_allgather_births(h, msg, all, words))) return rc;
-      done = true;
-    } else if (h->nccl_comm) {
+    if (h->nccl_comm) {
       ABM_NCCL(h, g_nccl.AllGather(msg, all, (size_t)words, ncclUint32, (ncclComm_t)h->nccl_comm, h->stream));
       done = true;
     }
@@ -1369,10 +1437,17 @@ static int tick_tile(abm_handle* h) {
     const uint64_t bcapn = h->bf_est;
     uint32_t* d_pend = ctr + (in ? CTR_PEND_B : CTR_PEND_A);
     if (h->strip) {
-      if ((rc = strip_stats_enqueue(h, d_pend, needs_resolve))) return rc;
-      StripGuardBody sg;
-      sg.stats = (const unsigned long long*)h->red_buf.p; sg.n_ranks = P; sg.birth_cap = (uint32_t)std::min<uint64_t>(bcapn, 0xFFFFFFFFull); sg.go = ctr + CTR_GO;
-      launch_foreach(h->stream, sg, 1);
+      const uint32_t gcap = (uint32_t)std::min<uint64_t>(bcapn, 0xFFFFFFFFull);
+      bool guarded = false;
+#ifndef ABM_EMU
+      guarded = h->p2p_on;
+#endif
+      if ((rc = strip_stats_enqueue(h, d_pend, needs_resolve, ctr + CTR_GO, gcap))) return rc;
+      if (!guarded) {
+        StripGuardBody sg;
+        sg.stats = (const unsigned long long*)h->red_buf.p; sg.n_ranks = P; sg.birth_cap = gcap; sg.go = ctr + CTR_GO;
+        launch_foreach(h->stream, sg, 1);
+      }
     } else {
       TickGuardBody tg;
       tg.pending = d_pend; tg.birth_flags = ctr + CTR_BIRTH_FLAGS; tg.birth_cap = (uint32_t)std::min<uint64_t>(bcapn, 0xFFFFFFFFull); tg.go = ctr + CTR_GO;

@@ -97,6 +97,88 @@ struct P2PBirthGatherBody { /* mailbox slots -> the contiguous n_ranks x words a
   }
 };
 
+/* The per-round counters (StripStatsBody's vector) as an all-to-all in two launches.  Send: one CTA computes this rank's
+ * vector, stores it into every rank's mailbox (its own included) and publishes.  Receive: one CTA waits for every rank's
+ * vector, sums them into `out`, and (optionally) evaluates the commit guard from the sums. */
+struct P2PStatsSendCta {
+  const uint32_t* pending; const uint32_t* birth_flags; const uint32_t* tot_up; const uint32_t* tot_down;
+  int32_t n_ranks, rank;
+  unsigned long long* dst[P2P_MAXP]; uint32_t* flag[P2P_MAXP]; uint32_t seq;
+  ABM_HD void operator()(uint32_t, uint32_t* smem) const {
+    const int P = n_ranks, nv = 1 + 3 * P;
+    unsigned long long* vec = (unsigned long long*)smem;
+    ABM_CTA_FOR(t, 64) {
+      if (t < nv) vec[t] = 0;
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, 64) {
+      if (t == 0) {
+        vec[0] = *pending; vec[1 + rank] = *pending; vec[1 + P + rank] = *birth_flags;
+        const uint32_t a = *tot_up, b = *tot_down;
+        vec[1 + 2 * P + rank] = a > b ? a : b;
+      }
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, 64) {
+      for (int i = t; i < P * nv; i += 64) dst[i / nv][i % nv] = vec[i % nv];
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, 64) { if (t < P) flag_publish(flag[t], seq); }
+  }
+};
+struct P2PStatsRecvCta {
+  const unsigned long long* src[P2P_MAXP]; const uint32_t* flag[P2P_MAXP]; uint32_t seq;
+  int32_t n_ranks; unsigned long long* out; uint32_t* err;
+  uint32_t* go; uint32_t birth_cap; /* optional guard (StripGuardBody) */
+  ABM_HD void operator()(uint32_t, uint32_t*) const {
+    const int P = n_ranks, nv = 1 + 3 * P;
+    ABM_CTA_FOR(t, 64) { if (t < P) flag_wait(flag[t], seq, err, ERR_P2P_TIMEOUT); }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, 64) {
+      if (t < nv) { unsigned long long s = 0; for (int q = 0; q < P; ++q) s += src[q][t]; out[t] = s; }
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, 64) {
+      if (t == 0 && go) {
+        bool ok = out[0] == 0;
+        for (int r = 0; r < P; ++r) ok = ok && out[1 + P + r] <= birth_cap;
+        *go = ok ? 1u : 0u;
+      }
+    }
+  }
+};
+
+/* offspring all-gather in two launches: [count, parent ids ...] of this rank into every rank's mailbox + publish; then wait
+ * for everybody and lay the messages out contiguously for the rank kernel */
+struct P2PBirthSendCta {
+  const uint32_t* birth_parent; const uint32_t* birth_count; uint32_t cap;
+  uint32_t* dst[P2P_MAXP]; uint32_t* flag[P2P_MAXP]; int32_t n_ranks; uint32_t seq;
+  ABM_HD void operator()(uint32_t, uint32_t*) const {
+    const uint32_t n = *birth_count < cap ? *birth_count : cap;
+    ABM_CTA_FOR(t, 256) {
+      for (uint32_t i = (uint32_t)t; i < (uint32_t)n_ranks * (1 + n); i += 256) {
+        const uint32_t r = i / (1 + n), w = i % (1 + n);
+        dst[r][w] = w == 0 ? *birth_count : birth_parent[w - 1];
+      }
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, 256) { if (t < n_ranks) flag_publish(flag[t], seq); }
+  }
+};
+struct P2PBirthRecvCta {
+  const uint32_t* src[P2P_MAXP]; const uint32_t* flag[P2P_MAXP]; int32_t n_ranks; uint32_t seq, cap; uint32_t* all; uint32_t* err;
+  ABM_HD void operator()(uint32_t, uint32_t*) const {
+    ABM_CTA_FOR(t, 256) { if (t < n_ranks) flag_wait(flag[t], seq, err, ERR_P2P_TIMEOUT); }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, 256) {
+      for (int r = 0; r < n_ranks; ++r) {
+        const uint32_t n = src[r][0] < cap ? src[r][0] : cap;
+        for (uint32_t w = (uint32_t)t; w < 1 + n; w += 256) all[(size_t)r * (1 + cap) + w] = src[r][w];
+      }
+    }
+  }
+};
+
 }  // namespace abm
 #endif /* ABM_EMU */
 #endif /* ABM_P2P_H_ */

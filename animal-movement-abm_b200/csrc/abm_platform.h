@@ -74,6 +74,10 @@ static inline uint32_t smem_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = 
  * caller (lanes run one after another here, so that is the running value) */
 static inline uint32_t warp_min_into(uint32_t* dst, uint32_t v, int /*lane*/) { if (v < *dst) *dst = v; return *dst; }
 
+/* peer-memory flags (abm_p2p.h) do not exist in the emulation: transports there go through the host */
+static inline void flag_publish(uint32_t*, uint32_t) {}
+static inline void flag_wait(const uint32_t*, uint32_t, uint32_t*, uint32_t) {}
+
 template <class F>
 static inline void launch_cta(abm_stream_t, const F& f, uint64_t n_ctas, int /*threads*/, size_t smem_bytes) {
   ++g_emu_launches;
@@ -148,6 +152,23 @@ ABM_D uint32_t warp_min_into(uint32_t* dst, uint32_t v, int lane) {
   const uint32_t m = __reduce_min_sync(0xffffffffu, v);
   if (lane == 0 && m < *dst) *dst = m;
   return m; /* the same value in every lane */
+}
+
+/* publish a sequence number in (peer) memory after everything this thread's CTA wrote before the preceding barrier */
+ABM_D void flag_publish(uint32_t* flag, uint32_t seq) {
+  if (!flag) return;
+  __threadfence_system();
+  *(volatile uint32_t*)flag = seq;
+}
+/* spin until the flag reaches seq; a lost neighbour becomes an error bit after ~4 s, not a hang */
+ABM_D void flag_wait(const uint32_t* flag, uint32_t seq, uint32_t* err, uint32_t err_bit) {
+  if (!flag) return;
+  const long long t0 = clock64();
+  while ((int32_t)(*(const volatile uint32_t*)flag - seq) < 0) {
+    if (clock64() - t0 > 8000000000ll) { atomicOr(err, err_bit); break; }
+    __nanosleep(32);
+  }
+  __threadfence_system();
 }
 
 template <class F>

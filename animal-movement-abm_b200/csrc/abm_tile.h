@@ -825,8 +825,10 @@ struct StripPackCta {
   uint8_t* msg[2]; uint32_t* pre[2]; /* nsx + 1 entries, the last = total */
   uint64_t hdr;
   uint32_t* err;
+  uint32_t* publish[2]; uint32_t seq; /* peer-memory transport: msg[d] is the neighbour's mailbox; its flag gets seq at the end */
   static size_t smem_bytes() { return (size_t)(TILE_THREADS + 32 + 4) * 4; }
   ABM_HD void operator()(uint32_t d, uint32_t* smem) const {
+    if (!msg[d]) return; /* no neighbour on this side */
     const int NT = TILE_THREADS, nsx = si.nsx, per = (nsx + NT - 1) / NT;
     uint32_t* part = smem; uint32_t* part2 = smem + NT;
     uint32_t* hdr_counts = (uint32_t*)msg[d];
@@ -857,6 +859,8 @@ struct StripPackCta {
       }
       if (t == NT - 1) pre[d][nsx] = o; /* total: the last chunk ends the row */
     }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) { if (t == 0) flag_publish(publish[d], seq); }
   }
 };
 
@@ -867,9 +871,12 @@ struct StripUnpackCta {
   uint32_t* sub_off; uint32_t* sub_cnt;
   uint32_t* cell; uint32_t* id; double* energy; uint8_t* state;
   uint32_t* err;
+  const uint32_t* wait[2]; uint32_t seq; /* peer-memory transport: the neighbour's message is complete when this flag reaches seq */
   static size_t smem_bytes() { return (size_t)(TILE_THREADS + 32 + 4) * 4; }
   ABM_HD void operator()(uint32_t d, uint32_t* smem) const {
     const int NT = TILE_THREADS, per = (nsx + NT - 1) / NT;
+    ABM_CTA_FOR(t, NT) { if (t == 0) flag_wait(wait[d], seq, err, ERR_P2P_TIMEOUT); }
+    ABM_CTA_SYNC();
     uint32_t* part = smem; uint32_t* part2 = smem + NT;
     const uint32_t* counts = (const uint32_t*)msg[d];
     const double* p_energy = (const double*)(msg[d] + hdr);
@@ -901,28 +908,44 @@ struct StripUnpackCta {
   }
 };
 
-/* E2: the decision bytes of both boundary rows, in the order of E1 (one thread per sub-tile, 2 nsx threads) */
-struct PackStatesBody {
+/* E2, sender side, CTA d = direction: the decision bytes of one boundary row in the order of E1 (straight into the
+ * neighbour's mailbox and published there when the peer-memory transport is on) */
+struct PackStatesCta {
   SubIndex si; int32_t row[2]; uint32_t cap;
   const uint8_t* state; const uint32_t* pre[2]; uint8_t* out[2];
-  ABM_HD void operator()(uint64_t w) const {
-    const int d = w >= (uint64_t)si.nsx ? 1 : 0;
-    const uint32_t i = (uint32_t)(w - (uint64_t)d * si.nsx);
-    const uint32_t sub = (uint32_t)row[d] * (uint32_t)si.nsx + i, off = si.off[sub], cnt = si.cnt[sub];
-    uint32_t o = pre[d][i];
-    if (o + cnt > cap) return; /* flagged by the agent exchange */
-    for (uint32_t k = 0; k < cnt; ++k, ++o) out[d][o] = state[off + k];
+  uint32_t* publish[2]; uint32_t seq;
+  ABM_HD void operator()(uint32_t d, uint32_t*) const {
+    if (!out[d]) return;
+    const int NT = TILE_THREADS;
+    ABM_CTA_FOR(t, NT) {
+      for (int i = t; i < si.nsx; i += NT) {
+        const uint32_t sub = (uint32_t)row[d] * (uint32_t)si.nsx + (uint32_t)i, off = si.off[sub], cnt = si.cnt[sub];
+        uint32_t o = pre[d][i];
+        if (o + cnt > cap) continue; /* flagged by the agent exchange */
+        for (uint32_t k = 0; k < cnt; ++k, ++o) out[d][o] = state[off + k];
+      }
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) { if (t == 0) flag_publish(publish[d], seq); }
   }
 };
-/* decisions are unique and final: a ghost copy keeps what it already settled locally, the owner's decision wins otherwise */
-struct MergeStatesBody {
-  const uint8_t* incoming[2]; uint8_t* state; uint32_t base[2], cap; const uint32_t* total[2]; int32_t present[2];
-  ABM_HD void operator()(uint64_t w) const {
-    const int d = w >= cap ? 1 : 0;
-    const uint32_t i = (uint32_t)(w - (uint64_t)d * cap);
-    if (!present[d] || i >= *total[d]) return;
-    const uint8_t in = incoming[d][i];
-    if ((in & ST_DECIDED) || !(state[base[d] + i] & ST_DECIDED)) state[base[d] + i] = in;
+/* E2, receiver side, CTA d: decisions are unique and final — a ghost copy keeps what it already settled locally, the
+ * owner's decision wins otherwise */
+struct MergeStatesCta {
+  const uint8_t* incoming[2]; uint8_t* state; uint32_t base[2]; const uint32_t* total[2];
+  const uint32_t* wait[2]; uint32_t seq; uint32_t* err;
+  ABM_HD void operator()(uint32_t d, uint32_t*) const {
+    if (!incoming[d]) return;
+    const int NT = TILE_THREADS;
+    ABM_CTA_FOR(t, NT) { if (t == 0) flag_wait(wait[d], seq, err, ERR_P2P_TIMEOUT); }
+    ABM_CTA_SYNC();
+    const uint32_t n = *total[d];
+    ABM_CTA_FOR(t, NT) {
+      for (uint32_t i = (uint32_t)t; i < n; i += (uint32_t)NT) {
+        const uint8_t in = incoming[d][i];
+        if ((in & ST_DECIDED) || !(state[base[d] + i] & ST_DECIDED)) state[base[d] + i] = in;
+      }
+    }
   }
 };
 
