@@ -235,7 +235,7 @@ struct ProfScope {
 };
 
 enum { CTR_BIRTH_TOTAL = 12, CTR_PEND_A = 0, CTR_PEND_B = 1, CTR_BIRTHS = 2, CTR_ERR = 3, CTR_RED_LO = 4, CTR_RED_HI = 5, CTR_PLANS = 6, CTR_ROUTE_SLOTS = 7,
-       CTR_EXP_LO = 8, CTR_EXP_HI = 9, CTR_CURSOR = 10, CTR_BIRTH_FLAGS = 11, CTR_PEND_FIRST = 13, CTR_GO = 14, CTR_WORDS = 16 };
+       CTR_EXP_LO = 8, CTR_EXP_HI = 9, CTR_CURSOR = 10, CTR_BIRTH_FLAGS = 11, CTR_PEND_FIRST = 13, CTR_GO = 14, CTR_PACK_DONE = 16, CTR_WORDS = 20 };
 
 }  // namespace
 
@@ -1044,48 +1044,63 @@ static int strip_exchange_agents(abm_handle* h) {
   int rc;
   const int nsx = h->nsx, cur = h->cur;
   const uint64_t cap = h->bcap, hdr = strip_hdr_bytes(nsx), bytes = strip_msg_bytes(nsx, cap);
-  uint32_t* err = (uint32_t*)h->counters.p + CTR_ERR;
-  StripPackCta pk;
-  pk.si = sub_index(h, cur); pk.row[0] = h->g.own_lo / SUB; pk.row[1] = h->g.own_hi / SUB - 1; pk.tiles_x = h->g.tiles_x; pk.cap = (uint32_t)cap;
-  pk.cell = (const uint32_t*)h->cell[cur].p; pk.id = (const uint32_t*)h->id[cur].p; pk.energy = (const double*)h->energy[cur].p; pk.state = (const uint8_t*)h->state.p;
-  for (int d = 0; d < 2; ++d) { pk.msg[d] = (uint8_t*)h->sx_buf[d].p; pk.pre[d] = (uint32_t*)h->sx_pre[d].p; pk.publish[d] = nullptr; }
-  pk.hdr = hdr; pk.err = err; pk.seq = 0;
-  StripUnpackCta up;
-  up.row[0] = h->g.own_lo / SUB - 1; up.row[1] = h->g.own_hi / SUB; up.nsx = nsx;
-  up.tile_row_base[0] = ((uint32_t)(h->g.own_lo / CORE - 1) * (uint32_t)h->g.tiles_x) << 10;
-  up.tile_row_base[1] = ((uint32_t)(h->g.own_hi / CORE) * (uint32_t)h->g.tiles_x) << 10;
-  up.base[0] = (uint32_t)h->n; up.base[1] = (uint32_t)(h->n + cap); up.cap = (uint32_t)cap;
-  for (int d = 0; d < 2; ++d) { up.msg[d] = (const uint8_t*)h->rx_buf[d].p; up.pre[d] = (uint32_t*)h->rx_pre[d].p; up.wait[d] = nullptr; }
-  up.hdr = hdr; up.seq = 0;
-  up.sub_off = (uint32_t*)h->sub_off[cur].p; up.sub_cnt = (uint32_t*)h->sub_cnt[cur].p;
-  up.cell = (uint32_t*)h->cell[cur].p; up.id = (uint32_t*)h->id[cur].p; up.energy = (double*)h->energy[cur].p; up.state = (uint8_t*)h->state.p;
-  up.err = err;
+  const int chunks = (nsx + TILE_THREADS / 32 - 1) / (TILE_THREADS / 32);
+  uint32_t* ctr = (uint32_t*)h->counters.p;
+  uint32_t* err = ctr + CTR_ERR;
+  uint8_t* tx_msg[2] = {(uint8_t*)h->sx_buf[0].p, (uint8_t*)h->sx_buf[1].p};
+  const uint8_t* rx_msg[2] = {(const uint8_t*)h->rx_buf[0].p, (const uint8_t*)h->rx_buf[1].p};
+  uint32_t* publish[2] = {nullptr, nullptr};
+  const uint32_t* wait[2] = {nullptr, nullptr};
+  uint32_t seq = 0;
   bool direct = false;
 #ifndef ABM_EMU
-  if (h->p2p_on) { /* the pack CTAs write straight into the neighbours' mailboxes and publish; the unpack CTAs wait for theirs */
+  if (h->p2p_on) { /* the pack CTAs write straight into the neighbours' mailboxes and publish; the receiving CTAs wait for theirs */
     if (bytes > h->p2p_lay.agents_bytes) ABM_FAIL(h, ABM_E_CAPACITY, "halo message (%llu bytes) exceeds the mailbox allocated at abm_p2p_export", (unsigned long long)bytes);
-    const uint32_t seq = ++h->p2p_seq[P2P_CH_AGENTS];
+    seq = ++h->p2p_seq[P2P_CH_AGENTS];
     const int parity = (int)(seq & 1u);
     const int prev = (h->my_rank + h->n_ranks - 1) % h->n_ranks, next = (h->my_rank + 1) % h->n_ranks;
     const P2PLayout& L = h->p2p_lay;
-    pk.seq = up.seq = seq;
-    if (h->has_prev) { pk.msg[0] = h->p2p_peer[prev] + L.agents_off(1, parity); pk.publish[0] = (uint32_t*)(h->p2p_peer[prev] + L.flag_off(P2P_CH_AGENTS, 1, parity)); }
-    if (h->has_next) { pk.msg[1] = h->p2p_peer[next] + L.agents_off(0, parity); pk.publish[1] = (uint32_t*)(h->p2p_peer[next] + L.flag_off(P2P_CH_AGENTS, 0, parity)); }
+    if (h->has_prev) { tx_msg[0] = h->p2p_peer[prev] + L.agents_off(1, parity); publish[0] = (uint32_t*)(h->p2p_peer[prev] + L.flag_off(P2P_CH_AGENTS, 1, parity)); }
+    if (h->has_next) { tx_msg[1] = h->p2p_peer[next] + L.agents_off(0, parity); publish[1] = (uint32_t*)(h->p2p_peer[next] + L.flag_off(P2P_CH_AGENTS, 0, parity)); }
     for (int d = 0; d < 2; ++d) {
-      up.msg[d] = h->p2p_mine + L.agents_off(d, parity); /* a side without a neighbour keeps its zeroed header: an empty ghost row */
+      rx_msg[d] = h->p2p_mine + L.agents_off(d, parity); /* a side without a neighbour keeps its zeroed header: an empty ghost row */
       const bool has = d == 0 ? h->has_prev : h->has_next;
-      up.wait[d] = has ? (const uint32_t*)(h->p2p_mine + L.flag_off(P2P_CH_AGENTS, d, parity)) : nullptr;
+      wait[d] = has ? (const uint32_t*)(h->p2p_mine + L.flag_off(P2P_CH_AGENTS, d, parity)) : nullptr;
     }
     direct = true;
   }
 #endif
+  StripHeaderCta hd;
+  hd.si = sub_index(h, cur); hd.row[0] = h->g.own_lo / SUB; hd.row[1] = h->g.own_hi / SUB - 1;
+  StripPackCta pk;
+  pk.si = hd.si; pk.row[0] = hd.row[0]; pk.row[1] = hd.row[1]; pk.tiles_x = h->g.tiles_x; pk.chunks = chunks; pk.cap = (uint32_t)cap;
+  pk.cell = (const uint32_t*)h->cell[cur].p; pk.id = (const uint32_t*)h->id[cur].p; pk.energy = (const double*)h->energy[cur].p; pk.state = (const uint8_t*)h->state.p;
+  pk.hdr = hdr; pk.err = err; pk.seq = seq;
+  StripRxHeaderCta rh;
+  rh.row[0] = h->g.own_lo / SUB - 1; rh.row[1] = h->g.own_hi / SUB; rh.nsx = nsx;
+  rh.base[0] = (uint32_t)h->n; rh.base[1] = (uint32_t)(h->n + cap); rh.cap = (uint32_t)cap;
+  rh.sub_off = (uint32_t*)h->sub_off[cur].p; rh.sub_cnt = (uint32_t*)h->sub_cnt[cur].p; rh.err = err; rh.seq = seq;
+  StripUnpackCta up;
+  up.nsx = nsx; up.chunks = chunks; up.cap = (uint32_t)cap; up.hdr = hdr;
+  up.tile_row_base[0] = ((uint32_t)(h->g.own_lo / CORE - 1) * (uint32_t)h->g.tiles_x) << 10;
+  up.tile_row_base[1] = ((uint32_t)(h->g.own_hi / CORE) * (uint32_t)h->g.tiles_x) << 10;
+  up.base[0] = rh.base[0]; up.base[1] = rh.base[1];
+  up.cell = (uint32_t*)h->cell[cur].p; up.id = (uint32_t*)h->id[cur].p; up.energy = (double*)h->energy[cur].p; up.state = (uint8_t*)h->state.p;
+  for (int d = 0; d < 2; ++d) {
+    hd.msg[d] = tx_msg[d]; hd.pre[d] = (uint32_t*)h->sx_pre[d].p; hd.done[d] = ctr + CTR_PACK_DONE + d;
+    pk.msg[d] = tx_msg[d]; pk.pre[d] = hd.pre[d]; pk.done[d] = hd.done[d]; pk.publish[d] = publish[d];
+    rh.msg[d] = rx_msg[d]; rh.pre[d] = (uint32_t*)h->rx_pre[d].p; rh.wait[d] = wait[d];
+    up.msg[d] = rx_msg[d]; up.pre[d] = rh.pre[d];
+  }
   { ProfScope ps(h->prof, h->stream, "halo_exchange", 2 * cap);
-    launch_cta(h->stream, pk, 2, TILE_THREADS, StripPackCta::smem_bytes());
+    launch_cta(h->stream, hd, 2, TILE_THREADS, StripHeaderCta::smem_bytes());
+    launch_cta(h->stream, pk, 2 * (uint64_t)chunks, TILE_THREADS, 16);
     if (!direct) {
       for (int d = 0; d < 2; ++d) ABM_CK(h, dev_memset(h->rx_buf[d].p, 0, hdr, h->stream)); /* a missing neighbour sends nothing */
       if ((rc = comm_sendrecv(h, h->sx_buf[0].p, bytes, h->sx_buf[1].p, bytes, h->rx_buf[0].p, bytes, h->rx_buf[1].p, bytes))) return rc;
     }
-    launch_cta(h->stream, up, 2, TILE_THREADS, StripUnpackCta::smem_bytes()); }
+    launch_cta(h->stream, rh, 2, TILE_THREADS, StripRxHeaderCta::smem_bytes());
+    launch_cta(h->stream, up, 2 * (uint64_t)chunks, TILE_THREADS, 16); }
   h->n_ghost = 2 * cap; /* upper bound; the sub-tile index knows the real counts */
   return check_launch(h, "strip halo exchange");
 }

@@ -76,6 +76,7 @@ static inline uint32_t warp_min_into(uint32_t* dst, uint32_t v, int /*lane*/) { 
 
 /* peer-memory flags (abm_p2p.h) do not exist in the emulation: transports there go through the host */
 static inline void flag_publish(uint32_t*, uint32_t) {}
+static inline void flag_fence() {}
 static inline void flag_wait(const uint32_t*, uint32_t, uint32_t*, uint32_t) {}
 
 template <class F>
@@ -160,6 +161,7 @@ ABM_D void flag_publish(uint32_t* flag, uint32_t seq) {
   __threadfence_system();
   *(volatile uint32_t*)flag = seq;
 }
+ABM_D void flag_fence() { __threadfence_system(); }
 /* spin until the flag reaches seq; a lost neighbour becomes an error bit after ~4 s, not a hang */
 ABM_D void flag_wait(const uint32_t* flag, uint32_t seq, uint32_t* err, uint32_t err_bit) {
   if (!flag) return;

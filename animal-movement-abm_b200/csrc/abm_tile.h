@@ -816,73 +816,84 @@ ABM_HD uint32_t chunk_prefix(const uint32_t* part, const uint32_t* part2, int t)
   return p;
 }
 
-/* E1, sender side, CTA d = direction (0: my first own sub-tile row, to the previous strip; 1: my last, to the next):
- * header counts, their prefix (kept in pre[d] for the decision exchanges of this tick) and the agents, packed in order.
- * Cells are normalised to tile row 0 (the receiver adds its ghost tile row). */
-struct StripPackCta {
-  SubIndex si; int32_t row[2]; int32_t tiles_x; uint32_t cap;
-  const uint32_t* cell; const uint32_t* id; const double* energy; const uint8_t* state;
+/* E1 in four launches.  (1) StripHeaderCta, CTA d = direction (0: my first own sub-tile row, to the previous strip;
+ * 1: my last, to the next): header counts into the message and their prefix (kept in pre[d] for this tick's decision
+ * exchanges).  (2) StripPackCta, one warp per sub-tile: the agents, packed in order, cells normalised to tile row 0
+ * (the receiver adds its ghost tile row); the CTA that finishes last publishes the message.  (3) StripRxHeaderCta, CTA
+ * d: waits for the neighbour's message, prefix of its header, ghost sub-tile runs.  (4) StripUnpackCta: the agents behind
+ * the own ones.  With the peer-memory transport msg[] of (1), (2) is the neighbour's mailbox and nothing else moves. */
+struct StripHeaderCta {
+  SubIndex si; int32_t row[2];
   uint8_t* msg[2]; uint32_t* pre[2]; /* nsx + 1 entries, the last = total */
-  uint64_t hdr;
-  uint32_t* err;
-  uint32_t* publish[2]; uint32_t seq; /* peer-memory transport: msg[d] is the neighbour's mailbox; its flag gets seq at the end */
+  uint32_t* done[2];                 /* pack CTAs finished (reset here) */
   static size_t smem_bytes() { return (size_t)(TILE_THREADS + 32 + 4) * 4; }
   ABM_HD void operator()(uint32_t d, uint32_t* smem) const {
-    if (!msg[d]) return; /* no neighbour on this side */
     const int NT = TILE_THREADS, nsx = si.nsx, per = (nsx + NT - 1) / NT;
     uint32_t* part = smem; uint32_t* part2 = smem + NT;
     uint32_t* hdr_counts = (uint32_t*)msg[d];
-    double* p_energy = (double*)(msg[d] + hdr);
-    uint32_t* p_cell = (uint32_t*)(msg[d] + hdr + (uint64_t)cap * 8);
-    uint32_t* p_id = (uint32_t*)(msg[d] + hdr + (uint64_t)cap * 12);
-    uint8_t* p_state = msg[d] + hdr + (uint64_t)cap * 16;
     ABM_CTA_FOR(t, NT) {
       uint32_t sum = 0;
       for (int i = t * per; i < (t + 1) * per && i < nsx; ++i) { const uint32_t c = si.cnt[(uint32_t)row[d] * (uint32_t)nsx + (uint32_t)i]; hdr_counts[i] = c; sum += c; }
       part[t] = sum;
-      if (t == 0) hdr_counts[nsx] = 0;
+      if (t == 0) { hdr_counts[nsx] = 0; *done[d] = 0; }
     }
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, NT) { if (t < NT / 32) { uint32_t q = 0; for (int k = 0; k < 32; ++k) q += part[32 * t + k]; part2[t] = q; } }
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, NT) {
       uint32_t o = chunk_prefix(part, part2, t);
-      for (int i = t * per; i < (t + 1) * per && i < nsx; ++i) {
-        const uint32_t sub = (uint32_t)row[d] * (uint32_t)nsx + (uint32_t)i, off = si.off[sub], cnt = si.cnt[sub];
-        pre[d][i] = o;
-        if (o + cnt > cap) { atomic_or(err, ERR_STRIP_CAP); o += cnt; continue; }
-        for (uint32_t k = 0; k < cnt; ++k, ++o) {
-          const uint32_t c = cell[off + k];
-          const uint32_t tx = (c >> 10) % (uint32_t)tiles_x;
-          p_cell[o] = (tx << 10) | (c & 1023u); p_id[o] = id[off + k]; p_energy[o] = energy[off + k]; p_state[o] = state[off + k];
-        }
-      }
+      for (int i = t * per; i < (t + 1) * per && i < nsx; ++i) { pre[d][i] = o; o += si.cnt[(uint32_t)row[d] * (uint32_t)nsx + (uint32_t)i]; }
       if (t == NT - 1) pre[d][nsx] = o; /* total: the last chunk ends the row */
     }
-    ABM_CTA_SYNC();
-    ABM_CTA_FOR(t, NT) { if (t == 0) flag_publish(publish[d], seq); }
   }
 };
-
-/* E1, receiver side, CTA d (0: from the previous strip -> ghost row above, 1: from the next -> ghost row below) */
-struct StripUnpackCta {
-  int32_t row[2], nsx; uint32_t tile_row_base[2]; uint32_t base[2], cap;
-  const uint8_t* msg[2]; uint32_t* pre[2]; uint64_t hdr;
+struct StripPackCta { /* grid = 2 * chunks, chunk = 8 sub-tiles (one per warp) */
+  SubIndex si; int32_t row[2], tiles_x, chunks; uint32_t cap;
+  const uint32_t* cell; const uint32_t* id; const double* energy; const uint8_t* state;
+  uint8_t* msg[2]; const uint32_t* pre[2]; uint64_t hdr;
+  uint32_t* err; uint32_t* done[2];
+  uint32_t* publish[2]; uint32_t seq;
+  ABM_HD void operator()(uint32_t cta, uint32_t*) const {
+    const int NT = TILE_THREADS;
+    const int d = (int)(cta / (uint32_t)chunks), chunk = (int)(cta % (uint32_t)chunks);
+    double* p_energy = (double*)(msg[d] + hdr);
+    uint32_t* p_cell = (uint32_t*)(msg[d] + hdr + (uint64_t)cap * 8);
+    uint32_t* p_id = (uint32_t*)(msg[d] + hdr + (uint64_t)cap * 12);
+    uint8_t* p_state = msg[d] + hdr + (uint64_t)cap * 16;
+    ABM_CTA_FOR(t, NT) {
+      const int i = chunk * (NT / 32) + (t >> 5);
+      if (i < si.nsx) {
+        const uint32_t sub = (uint32_t)row[d] * (uint32_t)si.nsx + (uint32_t)i, off = si.off[sub], cnt = si.cnt[sub], o = pre[d][i];
+        if (o + cnt > cap) { if ((t & 31) == 0) atomic_or(err, ERR_STRIP_CAP); }
+        else for (uint32_t k = (uint32_t)(t & 31); k < cnt; k += 32) {
+          const uint32_t c = cell[off + k];
+          const uint32_t tx = (c >> 10) % (uint32_t)tiles_x;
+          p_cell[o + k] = (tx << 10) | (c & 1023u); p_id[o + k] = id[off + k]; p_energy[o + k] = energy[off + k]; p_state[o + k] = state[off + k];
+        }
+      }
+    }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, NT) {
+      if (t == 0 && publish[d]) { /* the CTA that finishes last publishes the whole message */
+        flag_fence();
+        if (atomic_add(done[d], 1u) == (uint32_t)chunks - 1) flag_publish(publish[d], seq);
+      }
+    }
+  }
+};
+struct StripRxHeaderCta {
+  int32_t row[2], nsx; uint32_t base[2], cap;
+  const uint8_t* msg[2]; uint32_t* pre[2];
   uint32_t* sub_off; uint32_t* sub_cnt;
-  uint32_t* cell; uint32_t* id; double* energy; uint8_t* state;
   uint32_t* err;
-  const uint32_t* wait[2]; uint32_t seq; /* peer-memory transport: the neighbour's message is complete when this flag reaches seq */
+  const uint32_t* wait[2]; uint32_t seq;
   static size_t smem_bytes() { return (size_t)(TILE_THREADS + 32 + 4) * 4; }
   ABM_HD void operator()(uint32_t d, uint32_t* smem) const {
     const int NT = TILE_THREADS, per = (nsx + NT - 1) / NT;
-    ABM_CTA_FOR(t, NT) { if (t == 0) flag_wait(wait[d], seq, err, ERR_P2P_TIMEOUT); }
-    ABM_CTA_SYNC();
     uint32_t* part = smem; uint32_t* part2 = smem + NT;
     const uint32_t* counts = (const uint32_t*)msg[d];
-    const double* p_energy = (const double*)(msg[d] + hdr);
-    const uint32_t* p_cell = (const uint32_t*)(msg[d] + hdr + (uint64_t)cap * 8);
-    const uint32_t* p_id = (const uint32_t*)(msg[d] + hdr + (uint64_t)cap * 12);
-    const uint8_t* p_state = msg[d] + hdr + (uint64_t)cap * 16;
+    ABM_CTA_FOR(t, NT) { if (t == 0) flag_wait(wait[d], seq, err, ERR_P2P_TIMEOUT); }
+    ABM_CTA_SYNC();
     ABM_CTA_FOR(t, NT) {
       uint32_t sum = 0;
       for (int i = t * per; i < (t + 1) * per && i < nsx; ++i) sum += counts[i];
@@ -896,14 +907,36 @@ struct StripUnpackCta {
       for (int i = t * per; i < (t + 1) * per && i < nsx; ++i) {
         const uint32_t sub = (uint32_t)row[d] * (uint32_t)nsx + (uint32_t)i, cnt = counts[i];
         pre[d][i] = o;
-        if (o + cnt > cap) { atomic_or(err, ERR_STRIP_CAP); sub_off[sub] = base[d]; sub_cnt[sub] = 0; o += cnt; continue; }
-        sub_off[sub] = base[d] + o; sub_cnt[sub] = cnt;
-        for (uint32_t k = 0; k < cnt; ++k, ++o) {
-          cell[base[d] + o] = p_cell[o] + tile_row_base[d]; id[base[d] + o] = p_id[o];
-          energy[base[d] + o] = p_energy[o]; state[base[d] + o] = p_state[o];
-        }
+        if (o + cnt > cap) { atomic_or(err, ERR_STRIP_CAP); sub_off[sub] = base[d]; sub_cnt[sub] = 0; }
+        else { sub_off[sub] = base[d] + o; sub_cnt[sub] = cnt; }
+        o += cnt;
       }
       if (t == NT - 1) pre[d][nsx] = o;
+    }
+  }
+};
+struct StripUnpackCta { /* grid = 2 * chunks, one warp per ghost sub-tile */
+  int32_t nsx, chunks; uint32_t tile_row_base[2]; /* (ghost tile row * tiles_x) << 10 */
+  uint32_t base[2], cap;
+  const uint8_t* msg[2]; const uint32_t* pre[2]; uint64_t hdr;
+  uint32_t* cell; uint32_t* id; double* energy; uint8_t* state;
+  ABM_HD void operator()(uint32_t cta, uint32_t*) const {
+    const int NT = TILE_THREADS;
+    const int d = (int)(cta / (uint32_t)chunks), chunk = (int)(cta % (uint32_t)chunks);
+    const uint32_t* counts = (const uint32_t*)msg[d];
+    const double* p_energy = (const double*)(msg[d] + hdr);
+    const uint32_t* p_cell = (const uint32_t*)(msg[d] + hdr + (uint64_t)cap * 8);
+    const uint32_t* p_id = (const uint32_t*)(msg[d] + hdr + (uint64_t)cap * 12);
+    const uint8_t* p_state = msg[d] + hdr + (uint64_t)cap * 16;
+    ABM_CTA_FOR(t, NT) {
+      const int i = chunk * (NT / 32) + (t >> 5);
+      if (i < nsx) {
+        const uint32_t cnt = counts[i], o = pre[d][i];
+        if (o + cnt <= cap) for (uint32_t k = (uint32_t)(t & 31); k < cnt; k += 32) {
+          cell[base[d] + o + k] = p_cell[o + k] + tile_row_base[d]; id[base[d] + o + k] = p_id[o + k];
+          energy[base[d] + o + k] = p_energy[o + k]; state[base[d] + o + k] = p_state[o + k];
+        }
+      }
     }
   }
 };

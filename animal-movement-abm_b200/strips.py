@@ -164,5 +164,11 @@ def init_p2p(engine):
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
     parts = [torch.empty(64, dtype=torch.uint8, device=dev) for _ in range(world)]
     dist.all_gather(parts, mine.to(dev))
-    engine.p2p_connect(b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts), world)
+    failure = None
+    try:
+        engine.p2p_connect(b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts), world)
+    except Exception as exc:  # noqa: BLE001 -- keep the collective sequence identical on every rank, then report
+        failure = exc
     dist.barrier()
+    if failure is not None:
+        raise failure

@@ -209,7 +209,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS) + ["C4"])
-    ap.add_argument("--transport", default=os.environ.get("ABM_TRANSPORT", "nccl"), choices=["nccl", "p2p"], help="multi-GPU halo transport")
+    ap.add_argument("--transport", default=os.environ.get("ABM_TRANSPORT", "auto"), choices=["auto", "nccl", "p2p"],
+                    help="multi-GPU halo transport: NVLink peer-memory mailboxes, NCCL, or auto (p2p if every rank can map its peers, else NCCL)")
     ap.add_argument("--replans", type=int, default=1 << 14)
     ap.add_argument("--ref-replans", type=int, default=64)
     ap.add_argument("--max-dist", type=int, default=0)
@@ -258,7 +259,21 @@ def main():
         eng.ny = size + 2 * strips.GHOST
         eng.set_grid(pad(w["fully_grown"]), pad(w["countdown"]))
         eng.set_agents(w["ids"] + rank * agents, w["x"], w["y"] + size * rank, w["energy"], agents * world + 1)
-        (strips.init_p2p if args.transport == "p2p" else strips.init_nccl)(eng)
+        if args.transport == "auto":
+            # peer-memory mailboxes need CUDA IPC + peer access between all ranks of the node; every rank must agree on the choice
+            try:
+                strips.init_p2p(eng)
+                ok = 1
+            except Exception as exc:  # noqa: BLE001 -- any failure to map a peer means NCCL for everybody
+                print(f"[bench rank {rank}] peer-memory transport unavailable ({exc}); trying NCCL", file=sys.stderr)
+                ok = 0
+            flag = torch.tensor([ok], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            args.transport = "p2p" if int(flag.item()) else "nccl"
+            if args.transport == "nccl":
+                strips.init_nccl(eng)
+        else:
+            (strips.init_p2p if args.transport == "p2p" else strips.init_nccl)(eng)
     else:
         eng = load(lib, cfg, w, device=local)
     eng.set_profiling(True)
