@@ -271,6 +271,7 @@ struct abm_handle {
   uint32_t as_gen = 0;
   /* tile path (abm_tile.h): sub-tile runs of the SoA (ping-pong with the SoA), offspring fix-up lists */
   bool tile_mode = false;
+  bool split_waits = false;       /* ABM_SPLIT_WAITS=1: counters and decision bytes as send, send, wait, wait (measured: 2 % slower than one after the other) */
   bool overlap_halo = false;      /* ABM_OVERLAP=1: halo exchange on a second stream behind the interior rows (measured: no gain) */
   bool optimistic = true;         /* enqueue the commit behind a device-side guard instead of reading counters first (ABM_OPTIMISTIC=0 disables) */
   uint64_t bf_est = 0;            /* expected upper bound of reproducing agents, learnt from the previous tick */
@@ -894,71 +895,10 @@ static int comm_allgather_u32(abm_handle* h, const uint32_t* send, uint32_t* rec
 
 #ifndef ABM_EMU
 /* ------------------------------------------------------------------------------- peer-memory transport */
-static const long long P2P_TIMEOUT_CYCLES = 8000000000ll; /* ~4 s at 2 GHz: a lost neighbour becomes an error, not a hang */
 
-static int p2p_publish_wait(abm_handle* h, int ch, uint32_t seq, const int* targets, const int* target_slot, int nt, const int* sources, int ns) {
-  const int parity = (int)(seq & 1u);
-  uint32_t* err = (uint32_t*)h->counters.p + CTR_ERR;
-  if (nt > 0) {
-    P2PPublishBody pb;
-    pb.n = nt; pb.seq = seq;
-    for (int i = 0; i < nt; ++i) pb.flag[i] = (uint32_t*)(h->p2p_peer[targets[i]] + h->p2p_lay.flag_off(ch, target_slot[i], parity));
-    launch_foreach(h->stream, pb, (uint64_t)nt);
-  }
-  if (ns > 0) {
-    P2PWaitBody wb;
-    wb.n = ns; wb.seq = seq; wb.err = err; wb.limit = P2P_TIMEOUT_CYCLES;
-    for (int i = 0; i < ns; ++i) wb.flag[i] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.flag_off(ch, sources[i], parity));
-    launch_foreach(h->stream, wb, (uint64_t)ns);
-  }
-  return check_launch(h, "peer publish / wait");
-}
-
-/* ring exchange of one channel (agents or decision bytes): my `to_prev` lands in the previous strip's "from next" slot and
- * vice versa; returns where the neighbours' messages land in my mailbox */
-static int p2p_exchange(abm_handle* h, int ch, const void* to_prev, uint64_t b_tp, const void* to_next, uint64_t b_tn, const uint8_t** from_prev, const uint8_t** from_next) {
-  const uint32_t seq = ++h->p2p_seq[ch];
-  const int parity = (int)(seq & 1u);
-  const int prev = (h->my_rank + h->n_ranks - 1) % h->n_ranks, next = (h->my_rank + 1) % h->n_ranks;
-  const P2PLayout& L = h->p2p_lay;
-  const uint64_t cap = ch == P2P_CH_AGENTS ? L.agents_bytes : L.state_bytes;
-  if (b_tp > cap || b_tn > cap) ABM_FAIL(h, ABM_E_CAPACITY, "halo message (%llu bytes) exceeds the mailbox allocated at abm_p2p_export", (unsigned long long)std::max(b_tp, b_tn));
-  auto off = [&](int dir) { return ch == P2P_CH_AGENTS ? L.agents_off(dir, parity) : L.state_off(dir, parity); };
-  P2PCopyBody cp;
-  cp.src[0] = (const uint4*)to_prev; cp.dst[0] = (uint4*)(h->p2p_peer[prev] + off(1)); cp.words[0] = h->has_prev ? (b_tp + 15) / 16 : 0;
-  cp.src[1] = (const uint4*)to_next; cp.dst[1] = (uint4*)(h->p2p_peer[next] + off(0)); cp.words[1] = h->has_next ? (b_tn + 15) / 16 : 0;
-  if (cp.words[0] + cp.words[1] > 0) launch_foreach(h->stream, cp, cp.words[0] + cp.words[1]);
-  int targets[2], tslot[2], sources[2], nt = 0, ns = 0;
-  if (h->has_prev) { targets[nt] = prev; tslot[nt] = 1; ++nt; sources[ns++] = 0; }
-  if (h->has_next) { targets[nt] = next; tslot[nt] = 0; ++nt; sources[ns++] = 1; }
-  int rc = p2p_publish_wait(h, ch, seq, targets, tslot, nt, sources, ns);
-  if (rc) return rc;
-  *from_prev = h->p2p_mine + off(0);
-  *from_next = h->p2p_mine + off(1);
-  return 0;
-}
-
-/* sum of every rank's counter vector (red_buf, nv words) into red_buf, all on the device */
-static int p2p_allreduce(abm_handle* h, int nv) {
-  const uint32_t seq = ++h->p2p_seq[P2P_CH_STATS];
-  const int parity = (int)(seq & 1u), P = h->n_ranks;
-  P2PStatsSendBody sb;
-  sb.local = (const unsigned long long*)h->red_buf.p; sb.n_peers = P; sb.nv = nv;
-  for (int r = 0; r < P; ++r) sb.dst[r] = (unsigned long long*)(h->p2p_peer[r] + h->p2p_lay.stats_off(h->my_rank, parity));
-  launch_foreach(h->stream, sb, (uint64_t)P * nv);
-  int targets[P2P_MAXP], tslot[P2P_MAXP], sources[P2P_MAXP];
-  for (int r = 0; r < P; ++r) { targets[r] = r; tslot[r] = h->my_rank; sources[r] = r; }
-  int rc = p2p_publish_wait(h, P2P_CH_STATS, seq, targets, tslot, P, sources, P);
-  if (rc) return rc;
-  P2PStatsSumBody sm;
-  sm.n_src = P; sm.nv = nv; sm.out = (unsigned long long*)h->red_buf.p;
-  for (int r = 0; r < P; ++r) sm.src[r] = (const unsigned long long*)(h->p2p_mine + h->p2p_lay.stats_off(r, parity));
-  launch_foreach(h->stream, sm, (uint64_t)nv);
-  return check_launch(h, "peer all-reduce");
-}
-
-/* the counters of this round from every rank, summed into red_buf: two launches (send + publish, wait + sum [+ guard]) */
-static int p2p_stats(abm_handle* h, const uint32_t* d_pending, uint32_t* go, uint32_t birth_cap) {
+/* the counters of this round from every rank, summed into red_buf: two launches (send + publish, wait + sum [+ guard]).
+ * The halves are separate calls so that the decision bytes can be sent between them: both waits then overlap. */
+static void p2p_stats_send(abm_handle* h, const uint32_t* d_pending) {
   const uint32_t seq = ++h->p2p_seq[P2P_CH_STATS];
   const int parity = (int)(seq & 1u), P = h->n_ranks;
   uint32_t* ctr = (uint32_t*)h->counters.p;
@@ -971,6 +911,11 @@ static int p2p_stats(abm_handle* h, const uint32_t* d_pending, uint32_t* go, uin
     sc.flag[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.flag_off(P2P_CH_STATS, h->my_rank, parity));
   }
   launch_cta(h->stream, sc, 1, 64, P2P_STATS_WORDS * 8);
+}
+static int p2p_stats_recv(abm_handle* h, uint32_t* go, uint32_t birth_cap) {
+  const uint32_t seq = h->p2p_seq[P2P_CH_STATS];
+  const int parity = (int)(seq & 1u), P = h->n_ranks;
+  uint32_t* ctr = (uint32_t*)h->counters.p;
   P2PStatsRecvCta rc_;
   rc_.n_ranks = P; rc_.seq = seq; rc_.out = (unsigned long long*)h->red_buf.p; rc_.err = ctr + CTR_ERR; rc_.go = go; rc_.birth_cap = birth_cap;
   for (int r = 0; r < P; ++r) {
@@ -988,19 +933,19 @@ static int p2p_allgather_births(abm_handle* h, uint32_t* all, uint64_t cap) {
   const int parity = (int)(seq & 1u), P = h->n_ranks;
   uint32_t* ctr = (uint32_t*)h->counters.p;
   P2PBirthSendCta sc;
-  sc.birth_parent = (const uint32_t*)h->birth_parent.p; sc.birth_count = ctr + CTR_BIRTHS; sc.cap = (uint32_t)cap; sc.n_ranks = P; sc.seq = seq;
+  sc.birth_parent = (const uint32_t*)h->birth_parent.p; sc.birth_count = ctr + CTR_BIRTHS; sc.cap = (uint32_t)cap; sc.seq = seq;
   for (int r = 0; r < P; ++r) {
     sc.dst[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.births_off(h->my_rank, parity));
     sc.flag[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.flag_off(P2P_CH_BIRTHS, h->my_rank, parity));
   }
-  launch_cta(h->stream, sc, 1, 256, 16);
+  launch_cta(h->stream, sc, (uint64_t)P, 256, 16);
   P2PBirthRecvCta rv;
-  rv.n_ranks = P; rv.seq = seq; rv.cap = (uint32_t)cap; rv.all = all; rv.err = ctr + CTR_ERR;
+  rv.seq = seq; rv.cap = (uint32_t)cap; rv.all = all; rv.err = ctr + CTR_ERR;
   for (int r = 0; r < P; ++r) {
     rv.src[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.births_off(r, parity));
     rv.flag[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.flag_off(P2P_CH_BIRTHS, r, parity));
   }
-  launch_cta(h->stream, rv, 1, 256, 16);
+  launch_cta(h->stream, rv, (uint64_t)P, 256, 16);
   return check_launch(h, "peer all-gather");
 }
 #endif
@@ -1106,7 +1051,8 @@ static int strip_exchange_agents(abm_handle* h) {
 }
 
 /* E2: the decision bytes of the same boundary rows (same order), merged into the ghost copies */
-static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce = nullptr, int n_allreduce = 0) {
+enum { E2_SEND = 1, E2_RECV = 2, E2_BOTH = 3 };
+static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce = nullptr, int n_allreduce = 0, int phase = E2_BOTH) {
   int rc;
   const int cur = h->cur, nsx = h->nsx;
   const uint64_t cap = h->bcap;
@@ -1126,8 +1072,7 @@ static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce 
 #ifndef ABM_EMU
   if (h->p2p_on) {
     if (cap > h->p2p_lay.state_bytes) ABM_FAIL(h, ABM_E_CAPACITY, "decision message exceeds the mailbox allocated at abm_p2p_export");
-    if (d_allreduce && (rc = p2p_allreduce(h, n_allreduce))) return rc;
-    const uint32_t seq = ++h->p2p_seq[P2P_CH_STATE];
+    const uint32_t seq = (phase & E2_SEND) ? ++h->p2p_seq[P2P_CH_STATE] : h->p2p_seq[P2P_CH_STATE];
     const int parity = (int)(seq & 1u);
     const int prev = (h->my_rank + h->n_ranks - 1) % h->n_ranks, next = (h->my_rank + 1) % h->n_ranks;
     const P2PLayout& L = h->p2p_lay;
@@ -1145,9 +1090,9 @@ static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce 
   }
 #endif
   { ProfScope ps(h->prof, h->stream, "decision_exchange", 2 * cap);
-    launch_cta(h->stream, pk, 2, TILE_THREADS, 16);
+    if (phase & E2_SEND) launch_cta(h->stream, pk, 2, TILE_THREADS, 16);
     if (!direct && (rc = comm_sendrecv(h, h->sx_st[0].p, cap, h->sx_st[1].p, cap, h->rx_st[0].p, cap, h->rx_st[1].p, cap, d_allreduce, n_allreduce))) return rc;
-    launch_cta(h->stream, mg, 2, TILE_THREADS, 16); }
+    if (phase & E2_RECV) launch_cta(h->stream, mg, 2, TILE_THREADS, 16); }
   return check_launch(h, "strip decision exchange");
 }
 
@@ -1174,9 +1119,13 @@ static int strip_stats_enqueue(abm_handle* h, const uint32_t* d_pending, bool wi
   const int nv = 1 + 3 * h->n_ranks;
   unsigned long long* d = (unsigned long long*)h->red_buf.p;
 #ifndef ABM_EMU
-  if (h->p2p_on) { /* counters (with the commit guard folded into the receiving kernel), then the decision bytes */
-    if ((rc = p2p_stats(h, d_pending, go, guard_cap))) return rc;
-    return with_state_exchange ? strip_exchange_states(h) : 0;
+  if (h->p2p_on) { /* counters and decision bytes go out first, then both are awaited (the commit guard is folded into the
+                    * kernel that sums the counters) */
+    p2p_stats_send(h, d_pending);
+    if (!h->split_waits) { if ((rc = p2p_stats_recv(h, go, guard_cap))) return rc; return with_state_exchange ? strip_exchange_states(h) : 0; }
+    if (with_state_exchange && (rc = strip_exchange_states(h, nullptr, 0, E2_SEND))) return rc;
+    if ((rc = p2p_stats_recv(h, go, guard_cap))) return rc;
+    return with_state_exchange ? strip_exchange_states(h, nullptr, 0, E2_RECV) : 0;
   }
 #endif
   strip_stats_kernel(h, d_pending);
@@ -1199,8 +1148,10 @@ static int strip_stats(abm_handle* h, const uint32_t* d_pending, std::vector<uin
   out.assign((size_t)nv, 0);
 #ifndef ABM_EMU
   if (h->p2p_on) {
-    if ((rc = p2p_stats(h, d_pending, nullptr, 0))) return rc;
-    if (with_state_exchange && (rc = strip_exchange_states(h))) return rc;
+    p2p_stats_send(h, d_pending);
+    if (with_state_exchange && (rc = strip_exchange_states(h, nullptr, 0, E2_SEND))) return rc;
+    if ((rc = p2p_stats_recv(h, nullptr, 0))) return rc;
+    if (with_state_exchange && (rc = strip_exchange_states(h, nullptr, 0, E2_RECV))) return rc;
     ABM_CK(h, copy_d2h(out.data(), d, (size_t)nv * 8, h->stream));
     return 0;
   }
@@ -1391,7 +1342,9 @@ static int tick_tile(abm_handle* h) {
      * upper bound learnt from the previous tick (grid-stride inside), and the host reads everything back once */
     ABM_CK(h, copy_d2d(ctr + CTR_PEND_FIRST, ctr + CTR_PEND_A, sizeof(uint32_t), h->stream));
     for (int r = 0; r < h->fixed_agent_rounds; ++r) {
-      if (h->strip && (rc = strip_exchange_states(h))) return rc;
+      /* strips: the owners' decisions reach the ghost copies before the first blind round and once more with the counters
+       * below; an agent that waits for a ghost across the later blind rounds simply stays open and the guard sees it */
+      if (h->strip && r == 0 && (rc = strip_exchange_states(h))) return rc;
       if ((rc = launch_agents(std::max<uint64_t>(h->kf_grid, 1), ctr + (in ? CTR_PEND_A : CTR_PEND_B)))) return rc;
       in ^= 1;
       h->rounds += 1;
@@ -1680,6 +1633,7 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
   h->nsx = g.nx / SUB; h->nsy = g.ny / SUB;
   if (const char* mg = getenv("ABM_MIGRANTS")) h->use_migrants = atoi(mg) != 0;
   if (const char* ov = getenv("ABM_OVERLAP")) h->overlap_halo = atoi(ov) != 0;
+  if (const char* sw = getenv("ABM_SPLIT_WAITS")) h->split_waits = atoi(sw) != 0;
   if (const char* op = getenv("ABM_OPTIMISTIC")) h->optimistic = atoi(op) != 0;
   if (const char* ar = getenv("ABM_AGENT_ROUNDS")) { const int q = atoi(ar); if (q >= 0 && q <= 16) h->fixed_agent_rounds = q; }
   if (const char* tm = getenv("ABM_TILE_MARGIN")) { const int q = atoi(tm); if (q >= 2 && q <= HALO) h->tile_margin = q; }

@@ -7,7 +7,9 @@
  * time-out) and reads the data locally.  Every channel is used symmetrically once per round (both sides send, then
  * wait), so two buffers per channel, alternating with the sequence number, are enough: a sender can only reach
  * round s + 2 after it has seen the receiver's round s + 1, which the receiver issued behind its reads of round s.
- * Compared with NCCL send/recv + all-reduce this removes the host-side cost of ~5 NCCL groups per tick.
+ * Compared with NCCL send/recv + all-reduce this removes the host-side cost of ~5 NCCL groups per tick.  The pack and
+ * merge CTAs of abm_tile.h store into / wait on the mailboxes themselves; this file holds the layout and the two
+ * all-to-all collectives (counters, offspring).
  */
 #ifndef ABM_P2P_H_
 #define ABM_P2P_H_
@@ -32,70 +34,6 @@ struct P2PLayout {
 };
 
 ABM_D uint32_t ld_flag(const uint32_t* p) { return *(const volatile uint32_t*)p; }
-
-/* up to two messages in one launch: 16-byte words straight into the neighbours' mailboxes */
-struct P2PCopyBody {
-  const uint4* src[2]; uint4* dst[2]; uint64_t words[2];
-  ABM_HD void operator()(uint64_t i) const {
-    if (i < words[0]) dst[0][i] = src[0][i];
-    else { const uint64_t k = i - words[0]; if (k < words[1]) dst[1][k] = src[1][k]; }
-  }
-};
-/* after the copy kernel (stream order): make the data visible, then publish the sequence number in every target */
-struct P2PPublishBody {
-  uint32_t* flag[P2P_MAXP]; int32_t n; uint32_t seq;
-  ABM_HD void operator()(uint64_t i) const {
-    if ((int)i >= n) return;
-    __threadfence_system();
-    *(volatile uint32_t*)flag[i] = seq;
-  }
-};
-/* one thread per awaited flag */
-struct P2PWaitBody {
-  const uint32_t* flag[P2P_MAXP]; int32_t n; uint32_t seq; uint32_t* err; long long limit;
-  ABM_HD void operator()(uint64_t i) const {
-    if ((int)i >= n) return;
-    const long long t0 = clock64();
-    while ((int32_t)(ld_flag(flag[i]) - seq) < 0) {
-      if (clock64() - t0 > limit) { atomic_or(err, ERR_P2P_TIMEOUT); break; }
-      __nanosleep(64);
-    }
-    __threadfence_system();
-  }
-};
-/* all-to-all of the small counter vector: thread (p, w) stores word w into peer p's slot for this rank */
-struct P2PStatsSendBody {
-  const unsigned long long* local; unsigned long long* dst[P2P_MAXP]; int32_t n_peers, nv;
-  ABM_HD void operator()(uint64_t i) const {
-    const int p = (int)(i / (uint64_t)nv), w = (int)(i % (uint64_t)nv);
-    if (p < n_peers) dst[p][w] = local[w];
-  }
-};
-/* after the wait: out[w] = sum over every rank's vector (this rank's own included) */
-struct P2PStatsSumBody {
-  const unsigned long long* src[P2P_MAXP]; int32_t n_src, nv; unsigned long long* out;
-  ABM_HD void operator()(uint64_t w) const {
-    if ((int)w >= nv) return;
-    unsigned long long s = 0;
-    for (int q = 0; q < n_src; ++q) s += src[q][w];
-    out[w] = s;
-  }
-};
-/* all-gather of the offspring messages: thread (p, w) stores word w of this rank's message into peer p's slot */
-struct P2PBirthSendBody {
-  const uint32_t* local; uint32_t* dst[P2P_MAXP]; int32_t n_peers; uint32_t words;
-  ABM_HD void operator()(uint64_t i) const {
-    const uint32_t p = (uint32_t)(i / words), w = (uint32_t)(i % words);
-    if ((int)p < n_peers) dst[p][w] = local[w];
-  }
-};
-struct P2PBirthGatherBody { /* mailbox slots -> the contiguous n_ranks x words array the rank kernel reads */
-  const uint32_t* src[P2P_MAXP]; int32_t n_ranks; uint32_t words; uint32_t* all;
-  ABM_HD void operator()(uint64_t i) const {
-    const uint32_t r = (uint32_t)(i / words), w = (uint32_t)(i % words);
-    if ((int)r < n_ranks) all[i] = src[r][w];
-  }
-};
 
 /* The per-round counters (StripStatsBody's vector) as an all-to-all in two launches.  Send: one CTA computes this rank's
  * vector, stores it into every rank's mailbox (its own included) and publishes.  Receive: one CTA waits for every rank's
@@ -148,33 +86,28 @@ struct P2PStatsRecvCta {
   }
 };
 
-/* offspring all-gather in two launches: [count, parent ids ...] of this rank into every rank's mailbox + publish; then wait
- * for everybody and lay the messages out contiguously for the rank kernel */
+/* offspring all-gather in two launches of n_ranks CTAs: CTA r stores [count, parent ids ...] of this rank into rank r's
+ * mailbox and publishes; then CTA r waits for rank r's message and lays it out contiguously for the rank kernel */
 struct P2PBirthSendCta {
   const uint32_t* birth_parent; const uint32_t* birth_count; uint32_t cap;
-  uint32_t* dst[P2P_MAXP]; uint32_t* flag[P2P_MAXP]; int32_t n_ranks; uint32_t seq;
-  ABM_HD void operator()(uint32_t, uint32_t*) const {
+  uint32_t* dst[P2P_MAXP]; uint32_t* flag[P2P_MAXP]; uint32_t seq;
+  ABM_HD void operator()(uint32_t r, uint32_t*) const {
     const uint32_t n = *birth_count < cap ? *birth_count : cap;
     ABM_CTA_FOR(t, 256) {
-      for (uint32_t i = (uint32_t)t; i < (uint32_t)n_ranks * (1 + n); i += 256) {
-        const uint32_t r = i / (1 + n), w = i % (1 + n);
-        dst[r][w] = w == 0 ? *birth_count : birth_parent[w - 1];
-      }
+      for (uint32_t w = (uint32_t)t; w < 1 + n; w += 256) dst[r][w] = w == 0 ? *birth_count : birth_parent[w - 1];
     }
     ABM_CTA_SYNC();
-    ABM_CTA_FOR(t, 256) { if (t < n_ranks) flag_publish(flag[t], seq); }
+    ABM_CTA_FOR(t, 256) { if (t == 0) flag_publish(flag[r], seq); }
   }
 };
 struct P2PBirthRecvCta {
-  const uint32_t* src[P2P_MAXP]; const uint32_t* flag[P2P_MAXP]; int32_t n_ranks; uint32_t seq, cap; uint32_t* all; uint32_t* err;
-  ABM_HD void operator()(uint32_t, uint32_t*) const {
-    ABM_CTA_FOR(t, 256) { if (t < n_ranks) flag_wait(flag[t], seq, err, ERR_P2P_TIMEOUT); }
+  const uint32_t* src[P2P_MAXP]; const uint32_t* flag[P2P_MAXP]; uint32_t seq, cap; uint32_t* all; uint32_t* err;
+  ABM_HD void operator()(uint32_t r, uint32_t*) const {
+    ABM_CTA_FOR(t, 256) { if (t == 0) flag_wait(flag[r], seq, err, ERR_P2P_TIMEOUT); }
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, 256) {
-      for (int r = 0; r < n_ranks; ++r) {
-        const uint32_t n = src[r][0] < cap ? src[r][0] : cap;
-        for (uint32_t w = (uint32_t)t; w < 1 + n; w += 256) all[(size_t)r * (1 + cap) + w] = src[r][w];
-      }
+      const uint32_t n = src[r][0] < cap ? src[r][0] : cap;
+      for (uint32_t w = (uint32_t)t; w < 1 + n; w += 256) all[(size_t)r * (1 + cap) + w] = src[r][w];
     }
   }
 };
