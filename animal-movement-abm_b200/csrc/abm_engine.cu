@@ -1060,7 +1060,12 @@ static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce 
   PackStatesCta pk;
   pk.si = sub_index(h, cur); pk.row[0] = h->g.own_lo / SUB; pk.row[1] = h->g.own_hi / SUB - 1; pk.cap = (uint32_t)cap;
   pk.state = (const uint8_t*)h->state.p; pk.seq = 0;
-  for (int d = 0; d < 2; ++d) { pk.pre[d] = (const uint32_t*)h->sx_pre[d].p; pk.out[d] = (uint8_t*)h->sx_st[d].p; pk.publish[d] = nullptr; }
+  const int chunks = (nsx + TILE_THREADS / 32 - 1) / (TILE_THREADS / 32);
+  pk.chunks = chunks;
+  for (int d = 0; d < 2; ++d) {
+    pk.pre[d] = (const uint32_t*)h->sx_pre[d].p; pk.out[d] = (uint8_t*)h->sx_st[d].p; pk.publish[d] = nullptr;
+    pk.done[d] = (uint32_t*)h->counters.p + CTR_PACK_DONE + 2 + d;
+  }
   MergeStatesCta mg;
   mg.state = (uint8_t*)h->state.p; mg.err = err; mg.seq = 0;
   for (int d = 0; d < 2; ++d) {
@@ -1090,9 +1095,9 @@ static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce 
   }
 #endif
   { ProfScope ps(h->prof, h->stream, "decision_exchange", 2 * cap);
-    if (phase & E2_SEND) launch_cta(h->stream, pk, 2, TILE_THREADS, 16);
+    if (phase & E2_SEND) launch_cta(h->stream, pk, 2 * (uint64_t)chunks, TILE_THREADS, 16);
     if (!direct && (rc = comm_sendrecv(h, h->sx_st[0].p, cap, h->sx_st[1].p, cap, h->rx_st[0].p, cap, h->rx_st[1].p, cap, d_allreduce, n_allreduce))) return rc;
-    if (phase & E2_RECV) launch_cta(h->stream, mg, 2, TILE_THREADS, 16); }
+    if (phase & E2_RECV) launch_cta(h->stream, mg, 2 * MERGE_CTAS, TILE_THREADS, 16); }
   return check_launch(h, "strip decision exchange");
 }
 
@@ -1121,8 +1126,12 @@ static int strip_stats_enqueue(abm_handle* h, const uint32_t* d_pending, bool wi
 #ifndef ABM_EMU
   if (h->p2p_on) { /* counters and decision bytes go out first, then both are awaited (the commit guard is folded into the
                     * kernel that sums the counters) */
+    if (!h->split_waits) {
+      { ProfScope ps(h->prof, h->stream, "counters_exchange", (uint64_t)nv); p2p_stats_send(h, d_pending); rc = p2p_stats_recv(h, go, guard_cap); }
+      if (rc) return rc;
+      return with_state_exchange ? strip_exchange_states(h) : 0;
+    }
     p2p_stats_send(h, d_pending);
-    if (!h->split_waits) { if ((rc = p2p_stats_recv(h, go, guard_cap))) return rc; return with_state_exchange ? strip_exchange_states(h) : 0; }
     if (with_state_exchange && (rc = strip_exchange_states(h, nullptr, 0, E2_SEND))) return rc;
     if ((rc = p2p_stats_recv(h, go, guard_cap))) return rc;
     return with_state_exchange ? strip_exchange_states(h, nullptr, 0, E2_RECV) : 0;

@@ -876,7 +876,7 @@ struct StripPackCta { /* grid = 2 * chunks, chunk = 8 sub-tiles (one per warp) *
     ABM_CTA_FOR(t, NT) {
       if (t == 0 && publish[d]) { /* the CTA that finishes last publishes the whole message */
         flag_fence();
-        if (atomic_add(done[d], 1u) == (uint32_t)chunks - 1) flag_publish(publish[d], seq);
+        if (atomic_add(done[d], 1u) == (uint32_t)chunks - 1) { *done[d] = 0; flag_publish(publish[d], seq); }
       }
     }
   }
@@ -943,38 +943,46 @@ struct StripUnpackCta { /* grid = 2 * chunks, one warp per ghost sub-tile */
 
 /* E2, sender side, CTA d = direction: the decision bytes of one boundary row in the order of E1 (straight into the
  * neighbour's mailbox and published there when the peer-memory transport is on) */
-struct PackStatesCta {
-  SubIndex si; int32_t row[2]; uint32_t cap;
+struct PackStatesCta { /* grid = 2 * chunks, one warp per sub-tile; the CTA that finishes last publishes */
+  SubIndex si; int32_t row[2], chunks; uint32_t cap;
   const uint8_t* state; const uint32_t* pre[2]; uint8_t* out[2];
-  uint32_t* publish[2]; uint32_t seq;
-  ABM_HD void operator()(uint32_t d, uint32_t*) const {
-    if (!out[d]) return;
+  uint32_t* done[2]; uint32_t* publish[2]; uint32_t seq;
+  ABM_HD void operator()(uint32_t cta, uint32_t*) const {
     const int NT = TILE_THREADS;
+    const int d = (int)(cta / (uint32_t)chunks), chunk = (int)(cta % (uint32_t)chunks);
+    if (!out[d]) return;
     ABM_CTA_FOR(t, NT) {
-      for (int i = t; i < si.nsx; i += NT) {
-        const uint32_t sub = (uint32_t)row[d] * (uint32_t)si.nsx + (uint32_t)i, off = si.off[sub], cnt = si.cnt[sub];
-        uint32_t o = pre[d][i];
-        if (o + cnt > cap) continue; /* flagged by the agent exchange */
-        for (uint32_t k = 0; k < cnt; ++k, ++o) out[d][o] = state[off + k];
+      const int i = chunk * (NT / 32) + (t >> 5);
+      if (i < si.nsx) {
+        const uint32_t sub = (uint32_t)row[d] * (uint32_t)si.nsx + (uint32_t)i, off = si.off[sub], cnt = si.cnt[sub], o = pre[d][i];
+        if (o + cnt <= cap) /* else: flagged by the agent exchange */
+          for (uint32_t k = (uint32_t)(t & 31); k < cnt; k += 32) out[d][o + k] = state[off + k];
       }
     }
     ABM_CTA_SYNC();
-    ABM_CTA_FOR(t, NT) { if (t == 0) flag_publish(publish[d], seq); }
+    ABM_CTA_FOR(t, NT) {
+      if (t == 0 && publish[d]) {
+        flag_fence();
+        if (atomic_add(done[d], 1u) == (uint32_t)chunks - 1) { *done[d] = 0; flag_publish(publish[d], seq); }
+      }
+    }
   }
 };
-/* E2, receiver side, CTA d: decisions are unique and final — a ghost copy keeps what it already settled locally, the
- * owner's decision wins otherwise */
+/* E2, receiver side, grid = 2 * MERGE_CTAS: decisions are unique and final — a ghost copy keeps what it already settled
+ * locally, the owner's decision wins otherwise */
+enum { MERGE_CTAS = 8 };
 struct MergeStatesCta {
   const uint8_t* incoming[2]; uint8_t* state; uint32_t base[2]; const uint32_t* total[2];
   const uint32_t* wait[2]; uint32_t seq; uint32_t* err;
-  ABM_HD void operator()(uint32_t d, uint32_t*) const {
-    if (!incoming[d]) return;
+  ABM_HD void operator()(uint32_t cta, uint32_t*) const {
     const int NT = TILE_THREADS;
+    const int d = (int)(cta / MERGE_CTAS), part = (int)(cta % MERGE_CTAS);
+    if (!incoming[d]) return;
     ABM_CTA_FOR(t, NT) { if (t == 0) flag_wait(wait[d], seq, err, ERR_P2P_TIMEOUT); }
     ABM_CTA_SYNC();
     const uint32_t n = *total[d];
     ABM_CTA_FOR(t, NT) {
-      for (uint32_t i = (uint32_t)t; i < n; i += (uint32_t)NT) {
+      for (uint32_t i = (uint32_t)(part * NT + t); i < n; i += (uint32_t)(NT * MERGE_CTAS)) {
         const uint8_t in = incoming[d][i];
         if ((in & ST_DECIDED) || !(state[base[d] + i] & ST_DECIDED)) state[base[d] + i] = in;
       }

@@ -214,12 +214,14 @@ def main():
     ap.add_argument("--replans", type=int, default=1 << 14)
     ap.add_argument("--ref-replans", type=int, default=64)
     ap.add_argument("--max-dist", type=int, default=0)
-    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--size", type=int, default=0, help="grid side; default = the BASELINE.json size of the workload (C2 4096, C3 8192, C4 2048)")
     ap.add_argument("--ref-size", type=int, default=1024)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed ticks")
     args = ap.parse_args()
+    if args.size <= 0:
+        args.size = {"C3": 8192, "C4": 2048}.get(args.workload, 4096)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
