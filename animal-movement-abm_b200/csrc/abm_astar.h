@@ -8,11 +8,15 @@
  * the edge cost and the heuristic), f = g + h, open list ordered by the tuple (f, x, y), parent replaced on strict
  * g improvement, path excludes the start cell.
  *
- * One search per thread.  The open list is a binary min-heap of u64 keys f<<32 | x<<16 | y (1-based x, y), whose
- * integer order IS the reference's tuple order, so the sequence of distinct expansions — and with it every parent
- * pointer — equals the reference's whatever the heap's internal layout.  Per-search state lives in a slot of
- * dense per-cell arrays in HBM (g: u32, meta: u16 = generation<<8 | closed<<4 | parent direction); the generation
- * stamp makes a slot reusable without clearing it.
+ * One search per WARP (a 32-thread CTA), searches taken from a device-side queue.  The open list is a 32-ary min-heap of
+ * u64 keys f<<32 | x<<16 | y (1-based x, y), whose integer order IS the reference's tuple order — and the keys are
+ * unique (a cell is pushed again only with a strictly smaller g, hence f) — so the sequence of distinct expansions,
+ * and with it every parent pointer, equals the reference's whatever the heap's internal layout.  A node's 32 children
+ * are one coalesced 256-byte load, the minimum is found with one shared-memory atomic per lane: a pop is ~log32(n)
+ * dependent memory round trips instead of ~2 log2(n); the 8 neighbours are relaxed by 8 lanes at once.  Per-search
+ * state lives in a slot of dense per-cell arrays in HBM (g: u32, meta: u16 = generation<<8 | closed<<4 | parent
+ * direction); the per-slot generation stamp makes a slot reusable without clearing it.  The finished search walks its
+ * parents and writes the path straight into the route pool (space claimed with one 64-bit atomicAdd).
  */
 #ifndef ABM_ASTAR_H_
 #define ABM_ASTAR_H_
@@ -22,7 +26,7 @@
 namespace abm {
 
 enum { AS_CLOSED = 0x10, AS_NOPARENT = 0x0F };
-enum { AS_FOUND = 1, AS_UNREACHABLE = 2, AS_HEAP_FULL = 3 };
+enum { AS_FOUND = 1, AS_UNREACHABLE = 2, AS_HEAP_FULL = 3, AS_POOL_FULL = 4 };
 
 struct AStarGrid {
   Geo g;
@@ -46,146 +50,284 @@ ABM_HD int64_t astar_cost(const AStarGrid& a, int ax, int ay, uint32_t ca, int b
   return c;
 }
 
+/* the same cost with the two elevations already loaded (the search kernel issues its loads up front) */
+ABM_HD int64_t astar_cost_e(const AStarGrid& a, int ax, int ay, int ea, int bx, int by, int eb) {
+  int64_t dx = ax > bx ? ax - bx : bx - ax, dy = ay > by ? ay - by : by - ay;
+  if (a.g.periodic) {
+    if (a.g.nx - dx < dx) dx = a.g.nx - dx;
+    if (a.g.ny - dy < dy) dy = a.g.ny - dy;
+  }
+  const int64_t mx = dx > dy ? dx : dy, mn = dx > dy ? dy : dx;
+  int64_t c = a.metric == ABM_ASTAR_MAX ? mx : 10 * (mx - mn) + 14 * mn;
+  if (a.penalty) c += ea > eb ? ea - eb : eb - ea;
+  return c;
+}
+
 ABM_HD uint64_t astar_key(int64_t f, int x, int y) { return ((uint64_t)f << 32) | ((uint64_t)(x + 1) << 16) | (uint64_t)(y + 1); }
 
-ABM_HD bool heap_push(uint64_t* h, uint32_t& n, uint32_t cap, uint64_t key) {
+/* Connected components of the walkmap (Moore neighbourhood, the space's wrap): union-find with CAS hooking, then full
+ * compression.  A goal in another component than the start — or not walkable at all — can never be popped, so the
+ * search is known to end as "no path" without running it (the reference explores the whole component first and returns
+ * nothing: same result). */
+static const uint32_t AS_NOCOMP = 0xFFFFFFFFu; /* label of a cell that is not walkable */
+ABM_HD uint32_t comp_find(const uint32_t* comp, uint32_t x) {
+  uint32_t p;
+  while ((p = comp[x]) != x) x = p;
+  return x;
+}
+struct CompInitBody {
+  const uint32_t* walkbits; uint32_t* comp;
+  ABM_HD void operator()(uint64_t c) const { comp[c] = ((walkbits[c >> 5] >> (c & 31)) & 1u) ? (uint32_t)c : AS_NOCOMP; }
+};
+struct CompHookBody {
+  Geo g; const uint32_t* walkbits; uint32_t* comp; uint32_t* changed;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t c = (uint32_t)i;
+    if (!((walkbits[c >> 5] >> (c & 31)) & 1u)) return;
+    int x, y;
+    dec(g, c, x, y);
+    for (int d = 0; d < 8; ++d) {
+      int ddx, ddy, ox, oy;
+      off8(d, ddx, ddy);
+      if (!shift(g, x, y, ddx, ddy, ox, oy)) continue;
+      const uint32_t nc = enc(g, ox, oy);
+      if (!((walkbits[nc >> 5] >> (nc & 31)) & 1u)) continue;
+      uint32_t a = comp_find(comp, c), b = comp_find(comp, nc);
+      while (a != b) { /* hook the larger root under the smaller one; a root that was hooked meanwhile hands us its parent */
+        if (a < b) { const uint32_t q = a; a = b; b = q; }
+        const uint32_t old = atomic_cas(&comp[a], a, b);
+        if (old == a) { *changed = 1u; break; }
+        a = comp_find(comp, old);
+        b = comp_find(comp, b);
+      }
+    }
+  }
+};
+struct CompCompressBody {
+  uint32_t* comp;
+  ABM_HD void operator()(uint64_t c) const { if (comp[c] != AS_NOCOMP) comp[c] = comp_find(comp, (uint32_t)c); }
+};
+
+enum { AS_ARITY_LOG2 = 5, AS_ARITY = 32 };
+static const unsigned long long AS_NOKEY = ~0ull;
+
+enum { AS_TOP = 1 + AS_ARITY }; /* the root and its children live in shared memory for the length of a search */
+
+/* sift-up of a 32-ary heap: one lane, ~1 parent visited in the common case (a new f is rarely below its parent's) */
+ABM_HD bool heap_push(uint64_t* h, unsigned long long* top, uint32_t& n, uint32_t cap, uint64_t key) {
   if (n >= cap) return false;
   uint32_t i = n++;
   while (i > 0) {
-    const uint32_t p = (i - 1) >> 1;
-    const uint64_t pk = h[p];
+    const uint32_t p = (i - 1) >> AS_ARITY_LOG2;
+    const uint64_t pk = p < AS_TOP ? top[p] : h[p];
     if (pk <= key) break;
-    h[i] = pk;
+    if (i < AS_TOP) top[i] = pk; else h[i] = pk;
     i = p;
   }
-  h[i] = key;
+  if (i < AS_TOP) top[i] = key; else h[i] = key;
   return true;
 }
-ABM_HD uint64_t heap_pop(uint64_t* h, uint32_t& n) {
-  const uint64_t top = h[0];
-  const uint64_t last = h[--n];
-  uint32_t i = 0;
-  while (true) {
-    uint32_t c = 2 * i + 1;
-    if (c >= n) break;
-    uint64_t ck = h[c];
-    if (c + 1 < n) { const uint64_t rk = h[c + 1]; if (rk < ck) { ck = rk; ++c; } }
-    if (last <= ck) break;
-    h[i] = ck;
-    i = c;
-  }
-  if (n > 0) h[i] = last;
-  return top;
-}
 
-/* one wave of searches: search i uses slot i */
-struct AStarSearchBody {
+struct AStarShared {
+  unsigned long long top[AS_TOP];  /* heap entries 0..32 */
+  unsigned long long ck[AS_ARITY]; /* the children just loaded */
+  unsigned long long best[2];      /* their minimum, alternating per level */
+  unsigned long long nk[8];        /* keys the 8 neighbour lanes want pushed (0 = none) */
+  unsigned long long last, nexp;
+  uint32_t hn, cur, lvl, sift, fin, skip, status, req, wipe, gen;
+  uint32_t s, t; int32_t tx, ty, x, y, ec, et; uint32_t c, gc;
+};
+
+/* K8: grid = number of search slots; CTA `slot` keeps taking requests until the queue is empty */
+struct AStarWarpCta {
   AStarGrid a;
-  const uint32_t* src; /* tcell */
+  const uint32_t* src; /* tcell per request */
   const uint32_t* dst;
+  const uint32_t* comp; /* nullable: component label per cell (AS_NOCOMP = not walkable) */
+  const uint32_t* todo; /* nullable: the requests to run (indices into src/dst/out_*) */
+  uint32_t n_todo;
+  uint32_t* next_todo;  /* queue head */
   uint32_t* gbuf;      /* slots x gt */
   uint16_t* meta;      /* slots x gt */
   uint64_t* heap;      /* slots x heap_cap */
   uint32_t heap_cap;
-  uint32_t gen;        /* 1..255 */
-  uint32_t* out_status;
-  uint32_t* out_len;
-  int64_t* out_cost;
+  uint32_t* slot_gen;  /* per slot: last generation used (1..255) */
+  uint32_t* out_status; uint32_t* out_len; int64_t* out_cost; uint64_t* out_off;
+  uint32_t* pool; unsigned long long* pool_cursor; uint64_t pool_cap;
   unsigned long long* expansions;
+  static size_t smem_bytes() { return sizeof(AStarShared); }
 
-  ABM_HD void operator()(uint64_t i) const {
+  ABM_HD void operator()(uint32_t slot, uint32_t* smem) const {
+    const int NT = AS_ARITY;
+    AStarShared& sh = *(AStarShared*)smem;
     const uint64_t gt = a.g.gt;
-    uint32_t* g = gbuf + i * gt;
-    uint16_t* m = meta + i * gt;
-    uint64_t* h = heap + i * (uint64_t)heap_cap;
-    const uint32_t s = src[i], t = dst[i];
-    int sx, sy, tx, ty;
-    dec(a.g, s, sx, sy);
-    dec(a.g, t, tx, ty);
-    uint32_t hn = 0;
-    g[s] = 0;
-    m[s] = (uint16_t)(gen << 8 | AS_NOPARENT);
-    heap_push(h, hn, heap_cap, astar_key(astar_cost(a, sx, sy, s, tx, ty, t), sx, sy));
-    uint32_t status = AS_UNREACHABLE;
-    unsigned long long nexp = 0;
-    while (hn > 0) {
-      const uint64_t top = heap_pop(h, hn);
-      const int x = (int)((top >> 16) & 0xFFFF) - 1, y = (int)(top & 0xFFFF) - 1;
-      const uint32_t c = enc(a.g, x, y);
-      if (c == t) { status = AS_FOUND; break; }
-      const uint16_t mc = m[c];
-      if (mc & AS_CLOSED) continue; /* stale duplicate of an expanded node: re-expansion could not improve anything */
-      m[c] = (uint16_t)(mc | AS_CLOSED);
-      ++nexp;
-      const uint32_t gc = g[c];
-      for (int d = 0; d < 8; ++d) {
-        int ddx, ddy, ox, oy;
-        off8(d, ddx, ddy);
-        if (!shift(a.g, x, y, ddx, ddy, ox, oy)) continue;
-        const uint32_t nc = enc(a.g, ox, oy);
-        if (!((a.walkbits[nc >> 5] >> (nc & 31)) & 1u)) continue;
-        const uint16_t mn = m[nc];
-        const bool seen = (uint32_t)(mn >> 8) == gen;
-        if (seen && (mn & AS_CLOSED)) continue;
-        const int64_t ng = (int64_t)gc + astar_cost(a, x, y, c, ox, oy, nc);
-        if (!seen || ng < (int64_t)g[nc]) {
-          g[nc] = (uint32_t)ng;
-          m[nc] = (uint16_t)(gen << 8 | d);
-          if (!heap_push(h, hn, heap_cap, astar_key(ng + astar_cost(a, ox, oy, nc, tx, ty, t), ox, oy))) { status = AS_HEAP_FULL; hn = 0; break; }
+    uint32_t* g = gbuf + (uint64_t)slot * gt;
+    uint16_t* m = meta + (uint64_t)slot * gt;
+    uint64_t* h = heap + (uint64_t)slot * (uint64_t)heap_cap;
+    while (true) {
+      ABM_CTA_FOR(t, NT) {
+        if (t == 0) {
+          const uint32_t q = atomic_add(next_todo, 1u);
+          sh.req = q < n_todo ? (todo ? todo[q] : q) : 0xFFFFFFFFu;
+          sh.wipe = 0;
+          if (q < n_todo) {
+            uint32_t gen = slot_gen[slot] + 1;
+            if (gen > 255) { gen = 1; sh.wipe = 1; }
+            slot_gen[slot] = gen; sh.gen = gen;
+          }
         }
       }
-    }
-    uint32_t len = 0;
-    if (status == AS_FOUND) { /* walk the parents back to the start (the start cell is not part of the path) */
-      uint32_t c = t;
-      int x = tx, y = ty;
-      while (c != s) {
-        const int d = m[c] & 0x0F;
-        int ddx, ddy;
-        off8(d, ddx, ddy);
-        x = g_wrap(x - ddx, a.g.nx, a.g.periodic);
-        y = g_wrap(y - ddy, a.g.ny, a.g.periodic);
-        c = enc(a.g, x, y);
-        ++len;
+      ABM_CTA_SYNC();
+      if (sh.req == 0xFFFFFFFFu) break;
+      if (sh.wipe) { /* the 8-bit stamp wrapped: forget this slot's cells */
+        ABM_CTA_FOR(t, NT) { for (uint64_t k = (uint64_t)t; k < gt; k += NT) m[k] = 0; }
+        ABM_CTA_SYNC();
       }
-      out_cost[i] = (int64_t)g[t];
-    } else {
-      out_cost[i] = -1;
-    }
-    out_status[i] = status;
-    out_len[i] = len;
-    if (nexp) atomic_add64(expansions, nexp);
-  }
-};
-
-/* second pass of a wave: paths into the pool (first element = next cell to move to) */
-struct AStarWriteBody {
-  AStarGrid a;
-  const uint32_t* src;
-  const uint32_t* dst;
-  const uint16_t* meta;
-  const uint32_t* status;
-  const uint32_t* len;
-  const uint64_t* pool_off; /* per search */
-  uint32_t* pool;
-
-  ABM_HD void operator()(uint64_t i) const {
-    if (status[i] != AS_FOUND) return;
-    const uint16_t* m = meta + i * (uint64_t)a.g.gt;
-    uint32_t* out = pool + pool_off[i];
-    uint32_t k = len[i];
-    uint32_t c = dst[i];
-    const uint32_t s = src[i];
-    int x, y;
-    dec(a.g, c, x, y);
-    while (c != s) {
-      out[--k] = c;
-      const int d = m[c] & 0x0F;
-      int ddx, ddy;
-      off8(d, ddx, ddy);
-      x = g_wrap(x - ddx, a.g.nx, a.g.periodic);
-      y = g_wrap(y - ddy, a.g.ny, a.g.periodic);
-      c = enc(a.g, x, y);
+      ABM_CTA_FOR(t, NT) {
+        if (t == 0) {
+          const uint32_t s = src[sh.req], tc = dst[sh.req];
+          int sx, sy, tx, ty;
+          dec(a.g, s, sx, sy);
+          dec(a.g, tc, tx, ty);
+          sh.s = s; sh.t = tc; sh.tx = tx; sh.ty = ty; sh.et = a.penalty ? (int32_t)a.elev[tc] : 0;
+          g[s] = 0;
+          m[s] = (uint16_t)(sh.gen << 8 | AS_NOPARENT);
+          sh.top[0] = astar_key(astar_cost(a, sx, sy, s, tx, ty, tc), sx, sy);
+          sh.hn = 1; sh.status = AS_UNREACHABLE; sh.nexp = 0; sh.fin = 0;
+          if (comp && s != tc) { /* a goal the search could never pop: leave with an empty open list */
+            const uint32_t ls = comp[s], lt = comp[tc];
+            if (lt == AS_NOCOMP || (ls != AS_NOCOMP && ls != lt)) sh.hn = 0;
+          }
+        }
+      }
+      ABM_CTA_SYNC();
+      while (true) {
+        /* pop: the root leaves, the last key waits to be placed; the popped cell is closed (or recognised as stale) */
+        ABM_CTA_FOR(t, NT) {
+          if (t == 0) {
+            if (sh.hn == 0) sh.fin = 1;
+            else {
+              const uint64_t top = sh.top[0];
+              const uint32_t hn = sh.hn - 1;
+              sh.last = hn < AS_TOP ? sh.top[hn] : h[hn]; sh.hn = hn;
+              sh.cur = 0; sh.lvl = 0; sh.sift = hn > 0 ? 1u : 0u; sh.skip = 0;
+              sh.best[0] = AS_NOKEY; sh.best[1] = AS_NOKEY;
+              const int x = (int)((top >> 16) & 0xFFFF) - 1, y = (int)(top & 0xFFFF) - 1;
+              const uint32_t c = enc(a.g, x, y);
+              const uint16_t mc = m[c]; /* the three loads go out together */
+              const uint32_t gc = g[c];
+              const int32_t ec = a.penalty ? (int32_t)a.elev[c] : 0;
+              if (c == sh.t) { sh.status = AS_FOUND; sh.fin = 1; }
+              else if (mc & AS_CLOSED) sh.skip = 1; /* stale duplicate of an expanded node: re-expansion could not improve anything */
+              else { m[c] = (uint16_t)(mc | AS_CLOSED); sh.nexp += 1; sh.gc = gc; sh.ec = ec; sh.x = x; sh.y = y; sh.c = c; }
+            }
+          }
+        }
+        ABM_CTA_SYNC();
+        if (sh.fin) break;
+        /* the 8 neighbours, one lane each (they are 8 different cells) */
+        ABM_CTA_FOR(t, NT) {
+          if (t < 8) {
+            unsigned long long key = 0;
+            if (!sh.skip) {
+              int ddx, ddy, ox, oy;
+              off8(t, ddx, ddy);
+              const bool inside = shift(a.g, sh.x, sh.y, ddx, ddy, ox, oy);
+              const uint32_t nc = inside ? enc(a.g, ox, oy) : sh.c;
+              const uint32_t wb = a.walkbits[nc >> 5]; /* every load of this neighbour up front: one round trip */
+              const uint16_t mn = m[nc];
+              const uint32_t gn = g[nc];
+              const int32_t en = a.penalty ? (int32_t)a.elev[nc] : 0;
+              const bool seen = (uint32_t)(mn >> 8) == sh.gen;
+              if (inside && ((wb >> (nc & 31)) & 1u) && !(seen && (mn & AS_CLOSED))) {
+                const int64_t ng = (int64_t)sh.gc + astar_cost_e(a, sh.x, sh.y, sh.ec, ox, oy, en);
+                if (!seen || ng < (int64_t)gn) {
+                  g[nc] = (uint32_t)ng;
+                  m[nc] = (uint16_t)(sh.gen << 8 | (uint32_t)t);
+                  key = astar_key(ng + astar_cost_e(a, ox, oy, en, sh.tx, sh.ty, sh.et), ox, oy);
+                }
+              }
+            }
+            sh.nk[t] = key;
+          }
+        }
+        /* sift-down of the waiting key: per level one coalesced load of the 32 children and one atomic min per lane */
+        while (sh.sift) {
+          const uint32_t lv = sh.lvl & 1u;
+          ABM_CTA_FOR(t, NT) {
+            const uint64_t ci = (uint64_t)sh.cur * AS_ARITY + 1 + (uint64_t)t;
+            const unsigned long long key = ci < sh.hn ? (ci < AS_TOP ? sh.top[ci] : h[ci]) : AS_NOKEY;
+            sh.ck[t] = key;
+            if (key != AS_NOKEY) smem_min64(&sh.best[lv], key);
+          }
+          ABM_CTA_SYNC();
+          ABM_CTA_FOR(t, NT) {
+            const unsigned long long b = sh.best[lv];
+            const uint32_t cur = sh.cur;
+            if (b == AS_NOKEY) { if (t == 0) { if (cur < AS_TOP) sh.top[cur] = sh.last; else h[cur] = sh.last; sh.sift = 0; } } /* a leaf */
+            else if (sh.ck[t] == b) {                                               /* keys are unique: exactly one lane */
+              const unsigned long long put = sh.last <= b ? sh.last : b;
+              if (cur < AS_TOP) sh.top[cur] = put; else h[cur] = put;
+              if (sh.last <= b) sh.sift = 0;
+              else { sh.cur = cur * AS_ARITY + 1 + (uint32_t)t; sh.lvl += 1; sh.best[lv ^ 1u] = AS_NOKEY; }
+            }
+          }
+          ABM_CTA_SYNC();
+        }
+        ABM_CTA_SYNC();
+        ABM_CTA_FOR(t, NT) {
+          if (t == 0 && !sh.skip) {
+            uint32_t hn = sh.hn;
+            for (int d = 0; d < 8; ++d) {
+              const unsigned long long key = sh.nk[d];
+              if (key && !heap_push(h, sh.top, hn, heap_cap, key)) { sh.status = AS_HEAP_FULL; sh.fin = 1; break; }
+            }
+            sh.hn = hn;
+          }
+        }
+        ABM_CTA_SYNC();
+        if (sh.fin) break;
+      }
+      /* walk the parents back to the start (the start cell is not part of the path), claim pool space, write the path
+       * (first element = next cell to move to) */
+      ABM_CTA_FOR(t, NT) {
+        if (t == 0) {
+          const uint32_t r = sh.req;
+          uint32_t len = 0, status = sh.status;
+          int64_t cost = -1;
+          unsigned long long off = 0;
+          if (status == AS_FOUND) {
+            uint32_t c = sh.t;
+            int x = sh.tx, y = sh.ty;
+            while (c != sh.s) {
+              int ddx, ddy;
+              off8(m[c] & 0x0F, ddx, ddy);
+              x = g_wrap(x - ddx, a.g.nx, a.g.periodic);
+              y = g_wrap(y - ddy, a.g.ny, a.g.periodic);
+              c = enc(a.g, x, y);
+              ++len;
+            }
+            cost = (int64_t)g[sh.t];
+            off = atomic_add64(pool_cursor, (unsigned long long)len);
+            if (off + len > pool_cap) status = AS_POOL_FULL;
+            else {
+              uint32_t k = len;
+              c = sh.t; x = sh.tx; y = sh.ty;
+              while (c != sh.s) {
+                pool[off + --k] = c;
+                int ddx, ddy;
+                off8(m[c] & 0x0F, ddx, ddy);
+                x = g_wrap(x - ddx, a.g.nx, a.g.periodic);
+                y = g_wrap(y - ddy, a.g.ny, a.g.periodic);
+                c = enc(a.g, x, y);
+              }
+            }
+          }
+          out_status[r] = status; out_len[r] = len; out_cost[r] = cost; out_off[r] = off;
+          if (sh.nexp) atomic_add64(expansions, sh.nexp);
+        }
+      }
+      ABM_CTA_SYNC();
     }
   }
 };
@@ -199,7 +341,19 @@ struct RouteStore {
   uint32_t* pool;
 };
 
-/* plan_route!: (re)binds the routes of a finished wave.  A new slot is taken only when the agent had none. */
+/* scheduling hint: the heuristic distance of a request (long searches are started first, see plan_batch) */
+struct AStarHintBody {
+  AStarGrid a; const uint32_t* src; const uint32_t* dst; uint32_t* hint;
+  ABM_HD void operator()(uint64_t i) const {
+    int sx, sy, tx, ty;
+    dec(a.g, src[i], sx, sy);
+    dec(a.g, dst[i], tx, ty);
+    const int64_t c = astar_cost_e(a, sx, sy, 0, tx, ty, 0);
+    hint[i] = c > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)c;
+  }
+};
+
+/* plan_route!: (re)binds the routes of a finished batch.  A new slot is taken only when the agent had none. */
 struct RouteBindBody {
   RouteStore rs;
   int64_t* r_cost;          /* per slot: g(goal) at planning time (bookkeeping for abm_get_paths) */

@@ -235,7 +235,7 @@ struct ProfScope {
 };
 
 enum { CTR_BIRTH_TOTAL = 12, CTR_PEND_A = 0, CTR_PEND_B = 1, CTR_BIRTHS = 2, CTR_ERR = 3, CTR_RED_LO = 4, CTR_RED_HI = 5, CTR_PLANS = 6, CTR_ROUTE_SLOTS = 7,
-       CTR_EXP_LO = 8, CTR_EXP_HI = 9, CTR_CURSOR = 10, CTR_BIRTH_FLAGS = 11, CTR_PEND_FIRST = 13, CTR_GO = 14, CTR_PACK_DONE = 16, CTR_WORDS = 20 };
+       CTR_EXP_LO = 8, CTR_EXP_HI = 9, CTR_CURSOR = 10, CTR_BIRTH_FLAGS = 11, CTR_PEND_FIRST = 13, CTR_GO = 14, CTR_PACK_DONE = 16, CTR_POOL_LO = 20, CTR_POOL_HI = 21, CTR_NEXT_REQ = 22, CTR_WORDS = 24 };
 
 }  // namespace
 
@@ -265,10 +265,11 @@ struct abm_handle {
   DevBuf bits, bits_prefix, scan_tmp, stage, lut, greg_order, greg_dxy, greg_table, counters, partials;
   /* ALTERNATED_WALK / A*: id-order ranks, behaviour segments, plan requests, route followers, the route store */
   DevBuf rank, by_rank, seg_behav, plan_agent, plan_goal, remote_head, remote_next, remote_dest, idx_of_id;
-  DevBuf as_g, as_meta, as_heap, as_src, as_dst, as_id, as_status, as_len, as_cost, as_off;
+  DevBuf as_g, as_meta, as_heap, as_src, as_dst, as_id, as_status, as_len, as_cost, as_off, as_slot_gen, as_todo, as_comp;
+  bool comp_valid = false;        /* as_comp holds the walkmap's component labels */
+  uint64_t astar_budget = 64ull << 30; /* ABM_ASTAR_GB: device bytes the search slots may take (and at most half of what is free) */
   DevBuf rt_slot_of_id, rt_off, rt_len, rt_pos, rt_cost, rt_pool;
   uint64_t as_slots = 0, as_heap_cap = 0, rt_slots_cap = 0, rt_pool_used = 0, rt_ids_cap = 0;
-  uint32_t as_gen = 0;
   /* tile path (abm_tile.h): sub-tile runs of the SoA (ping-pong with the SoA), offspring fix-up lists */
   bool tile_mode = false;
   bool split_waits = false;       /* ABM_SPLIT_WAITS=1: counters and decision bytes as send, send, wait, wait (measured: 2 % slower than one after the other) */
@@ -492,79 +493,140 @@ static size_t device_free_bytes() {
 #endif
 }
 
-/* plan_route! for B requests held in device arrays (agent id, start tcell, goal tcell), in waves of `slots`
- * concurrent searches.  host_cost (nullable) receives g(goal) or -1. */
+/* component labels of the walkmap, computed once per abm_set_grid, on the first plan */
+static int ensure_components(abm_handle* h) {
+  int rc;
+  if (h->comp_valid) return 0;
+  const uint64_t gt = h->g.gt;
+  if ((rc = ensure(h, h->as_comp, gt * 4))) return rc;
+  uint32_t* ctr = (uint32_t*)h->counters.p;
+  ProfScope ps(h->prof, h->stream, "walkmap_components", gt);
+  CompInitBody ci;
+  ci.walkbits = (const uint32_t*)h->walkbits.p; ci.comp = (uint32_t*)h->as_comp.p;
+  launch_foreach(h->stream, ci, gt);
+  for (int it = 0; it < 64; ++it) {
+    ABM_CK(h, dev_memset(ctr + CTR_NEXT_REQ, 0, 4, h->stream));
+    CompHookBody hk;
+    hk.g = h->g; hk.walkbits = ci.walkbits; hk.comp = ci.comp; hk.changed = ctr + CTR_NEXT_REQ;
+    launch_foreach(h->stream, hk, gt);
+    CompCompressBody cc;
+    cc.comp = ci.comp;
+    launch_foreach(h->stream, cc, gt);
+    if ((rc = check_launch(h, "walkmap components"))) return rc;
+    if ((rc = read_counters(h))) return rc;
+    if (!h->h_counters[CTR_NEXT_REQ]) { h->comp_valid = true; return 0; }
+  }
+  ABM_FAIL(h, ABM_E_INTERNAL, "component labelling did not converge");
+}
+
+/* plan_route! for B requests held in device arrays (agent id, start tcell, goal tcell): ONE launch of `slots` warps that
+ * take requests from a device-side queue, search, and write their paths into the route pool themselves.  The host only
+ * reads the status words back; requests that found the pool full are re-run after growing it. */
 static int plan_batch(abm_handle* h, uint64_t B, const uint32_t* d_id, const uint32_t* d_src, const uint32_t* d_dst) {
   int rc;
   if (B == 0) return 0;
   if (h->g.nx > 65534 || h->g.ny > 65534) ABM_FAIL(h, ABM_E_BADARG, "A* needs grid dims below 65535");
+  if (B > 0xFFFFFFF0ull) ABM_FAIL(h, ABM_E_BADARG, "too many route requests in one batch");
   const uint64_t gt = h->g.gt;
   const uint64_t heap_cap = std::min<uint64_t>(8ull * (uint64_t)h->g.nx * h->g.ny + 16, 1ull << 20);
   const uint64_t per_slot = gt * 6 + heap_cap * 8;
-  if (h->as_slots == 0 || h->as_heap_cap != heap_cap || h->as_slots < std::min<uint64_t>(B, 4096)) {
-    const uint64_t budget = std::min<uint64_t>(device_free_bytes() / 2, 48ull << 30);
-    uint64_t slots = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(B, 1u << 16), budget / per_slot));
+  uint64_t max_resident = 148ull * 32; /* one warp-sized CTA per slot, at most 32 CTAs per SM */
+  if (const char* ms = getenv("ABM_ASTAR_SLOTS")) max_resident = (uint64_t)std::max(atoll(ms), 1ll);
+  if (h->as_slots == 0 || h->as_heap_cap != heap_cap || h->as_slots < std::min<uint64_t>(B, max_resident)) {
+    const uint64_t budget = std::min<uint64_t>(device_free_bytes() / 2, h->astar_budget);
+    uint64_t slots = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(B, max_resident), budget / per_slot));
     if (slots > h->as_slots || h->as_heap_cap != heap_cap) {
       if ((rc = ensure(h, h->as_g, slots * gt * 4))) return rc;
       if ((rc = ensure(h, h->as_meta, slots * gt * 2))) return rc;
       if ((rc = ensure(h, h->as_heap, slots * heap_cap * 8))) return rc;
+      if ((rc = ensure(h, h->as_slot_gen, slots * 4))) return rc;
       ABM_CK(h, dev_memset(h->as_meta.p, 0, slots * gt * 2, h->stream));
-      h->as_slots = slots; h->as_heap_cap = heap_cap; h->as_gen = 0;
+      ABM_CK(h, dev_memset(h->as_slot_gen.p, 0, slots * 4, h->stream));
+      h->as_slots = slots; h->as_heap_cap = heap_cap;
     }
   }
-  const uint64_t S = h->as_slots;
-  if ((rc = ensure(h, h->as_status, S * 4))) return rc;
-  if ((rc = ensure(h, h->as_len, S * 4))) return rc;
-  if ((rc = ensure(h, h->as_cost, S * 8))) return rc;
-  if ((rc = ensure(h, h->as_off, S * 8))) return rc;
-  std::vector<uint32_t> st(S), ln(S);
-  std::vector<uint64_t> off(S);
-  unsigned long long* d_exp = (unsigned long long*)((uint32_t*)h->counters.p + CTR_EXP_LO);
-  for (uint64_t base = 0; base < B; base += S) {
-    const uint64_t nb = std::min<uint64_t>(S, B - base);
-    if (++h->as_gen > 255) { ABM_CK(h, dev_memset(h->as_meta.p, 0, S * gt * 2, h->stream)); h->as_gen = 1; }
-    AStarSearchBody sb;
-    sb.a = astar_grid(h); sb.src = d_src + base; sb.dst = d_dst + base;
+  const uint64_t S = std::min<uint64_t>(std::min<uint64_t>(h->as_slots, B), max_resident);
+  if ((rc = ensure_components(h))) return rc;
+  if ((rc = ensure(h, h->as_status, B * 4))) return rc;
+  if ((rc = ensure(h, h->as_len, B * 4))) return rc;
+  if ((rc = ensure(h, h->as_cost, B * 8))) return rc;
+  if ((rc = ensure(h, h->as_off, B * 8))) return rc;
+  uint32_t* ctr = (uint32_t*)h->counters.p;
+  unsigned long long* d_exp = (unsigned long long*)(ctr + CTR_EXP_LO);
+  unsigned long long* d_cursor = (unsigned long long*)(ctr + CTR_POOL_LO);
+  std::vector<uint32_t> st(B), todo;
+  /* room for the new paths: a guess from the grid size; a request that does not fit reports AS_POOL_FULL and runs again */
+  uint64_t pool_cap = std::max<uint64_t>(h->rt_pool.bytes / 4, 1);
+  {
+    uint64_t room = std::min<uint64_t>(B * (uint64_t)std::max(h->g.nx, h->g.ny), 1ull << 28);
+    if (const char* pg = getenv("ABM_ROUTE_POOL_GUESS")) room = (uint64_t)std::max(atoll(pg), 0ll); /* tests: force the overflow path */
+    const uint64_t guess = h->rt_pool_used + room + 1;
+    if (guess > pool_cap) { if ((rc = grow_keep(h, h->rt_pool, guess * 4))) return rc; pool_cap = h->rt_pool.bytes / 4; }
+  }
+  uint64_t n_todo = B;
+  if (B > S) { /* more requests than slots: far goals first, so that the longest searches do not start last */
+    AStarHintBody hb;
+    hb.a = astar_grid(h); hb.src = d_src; hb.dst = d_dst; hb.hint = (uint32_t*)h->as_status.p;
+    launch_foreach(h->stream, hb, B);
+    if ((rc = check_launch(h, "astar hints"))) return rc;
+    ABM_CK(h, copy_d2h(st.data(), h->as_status.p, B * 4, h->stream));
+    ABM_CK(h, stream_sync(h->stream));
+    todo.resize(B);
+    for (uint64_t i = 0; i < B; ++i) todo[i] = (uint32_t)i;
+    std::stable_sort(todo.begin(), todo.end(), [&](uint32_t x, uint32_t y) { return st[x] > st[y]; });
+  }
+  for (int attempt = 0; n_todo > 0; ++attempt) {
+    if (attempt > 40) ABM_FAIL(h, ABM_E_INTERNAL, "route pool kept overflowing");
+    unsigned long long cursor = h->rt_pool_used;
+    ABM_CK(h, copy_h2d(d_cursor, &cursor, 8, h->stream));
+    ABM_CK(h, dev_memset(ctr + CTR_NEXT_REQ, 0, 4, h->stream));
+    if (!todo.empty()) {
+      if ((rc = ensure(h, h->as_todo, todo.size() * 4))) return rc;
+      ABM_CK(h, copy_h2d(h->as_todo.p, todo.data(), todo.size() * 4, h->stream));
+    }
+    AStarWarpCta sb;
+    sb.a = astar_grid(h); sb.src = d_src; sb.dst = d_dst; sb.comp = (const uint32_t*)h->as_comp.p;
+    sb.todo = todo.empty() ? nullptr : (const uint32_t*)h->as_todo.p; sb.n_todo = (uint32_t)n_todo; sb.next_todo = ctr + CTR_NEXT_REQ;
     sb.gbuf = (uint32_t*)h->as_g.p; sb.meta = (uint16_t*)h->as_meta.p; sb.heap = (uint64_t*)h->as_heap.p;
-    sb.heap_cap = (uint32_t)heap_cap; sb.gen = h->as_gen;
+    sb.heap_cap = (uint32_t)heap_cap; sb.slot_gen = (uint32_t*)h->as_slot_gen.p;
     sb.out_status = (uint32_t*)h->as_status.p; sb.out_len = (uint32_t*)h->as_len.p; sb.out_cost = (int64_t*)h->as_cost.p;
+    sb.out_off = (uint64_t*)h->as_off.p;
+    sb.pool = (uint32_t*)h->rt_pool.p; sb.pool_cursor = d_cursor; sb.pool_cap = pool_cap;
     sb.expansions = d_exp;
-    { ProfScope ps(h->prof, h->stream, "astar_search", nb); launch_foreach(h->stream, sb, nb); }
+    const uint64_t grid = std::min<uint64_t>(S, n_todo);
+    { ProfScope ps(h->prof, h->stream, "astar_search", n_todo); launch_cta(h->stream, sb, grid, AS_ARITY, AStarWarpCta::smem_bytes()); }
     if ((rc = check_launch(h, "astar search"))) return rc;
-    ABM_CK(h, copy_d2h(st.data(), h->as_status.p, nb * 4, h->stream));
-    ABM_CK(h, copy_d2h(ln.data(), h->as_len.p, nb * 4, h->stream));
-    uint64_t need = h->rt_pool_used;
-    for (uint64_t i = 0; i < nb; ++i) {
+    ABM_CK(h, copy_d2h(st.data(), h->as_status.p, B * 4, h->stream));
+    ABM_CK(h, copy_d2h(&cursor, d_cursor, 8, h->stream));
+    if ((rc = read_counters(h))) return rc; /* synchronises the stream */
+    std::vector<uint32_t> again;
+    if (todo.empty()) { for (uint64_t i = 0; i < B; ++i) if (st[i] == AS_POOL_FULL) again.push_back((uint32_t)i); }
+    else for (uint32_t i : todo) if (st[i] == AS_POOL_FULL) again.push_back(i);
+    for (uint64_t i = 0; i < B; ++i)
       if (st[i] == AS_HEAP_FULL) ABM_FAIL(h, ABM_E_CAPACITY, "A* open list exceeded %llu entries", (unsigned long long)heap_cap);
-      off[i] = need;
-      if (st[i] == AS_FOUND) need += ln[i];
-    }
-    if ((rc = grow_keep(h, h->rt_pool, (need + 1) * 4))) return rc;
-    /* slots: at most one new slot per request */
-    const uint64_t slots_needed = h->rt_slots_cap ? 0 : 0;
-    (void)slots_needed;
-    if ((rc = read_counters(h))) return rc;
-    const uint64_t used = h->h_counters[CTR_ROUTE_SLOTS];
-    if (used + nb > h->rt_slots_cap) {
-      const uint64_t cap = (used + nb) * 2 + 64;
-      if ((rc = grow_keep(h, h->rt_off, cap * 8))) return rc;
-      if ((rc = grow_keep(h, h->rt_len, cap * 4))) return rc;
-      if ((rc = grow_keep(h, h->rt_pos, cap * 4))) return rc;
-      if ((rc = grow_keep(h, h->rt_cost, cap * 8))) return rc;
-      h->rt_slots_cap = cap;
-    }
-    ABM_CK(h, copy_h2d(h->as_off.p, off.data(), nb * 8, h->stream));
-    AStarWriteBody wb;
-    wb.a = sb.a; wb.src = sb.src; wb.dst = sb.dst; wb.meta = sb.meta; wb.status = sb.out_status; wb.len = sb.out_len;
-    wb.pool_off = (const uint64_t*)h->as_off.p; wb.pool = (uint32_t*)h->rt_pool.p;
-    { ProfScope ps(h->prof, h->stream, "astar_write", nb); launch_foreach(h->stream, wb, nb); }
-    RouteBindBody bb;
-    bb.rs = route_store(h); bb.r_cost = (int64_t*)h->rt_cost.p; bb.agent_id = d_id + base; bb.status = sb.out_status; bb.len = sb.out_len;
-    bb.cost = sb.out_cost; bb.pool_off = wb.pool_off; bb.slot_counter = (uint32_t*)h->counters.p + CTR_ROUTE_SLOTS;
-    { ProfScope ps(h->prof, h->stream, "route_bind", nb); launch_foreach(h->stream, bb, nb); }
-    if ((rc = check_launch(h, "route bind"))) return rc;
-    h->rt_pool_used = need;
+    if (again.empty()) { h->rt_pool_used = cursor; break; }
+    /* the cursor ran past the end: everything that fitted stays (and stays counted), the rest runs again in a larger pool */
+    h->rt_pool_used = std::min<uint64_t>(cursor, pool_cap);
+    if ((rc = grow_keep(h, h->rt_pool, (2 * pool_cap + (cursor - std::min<uint64_t>(cursor, pool_cap)) + 1) * 4))) return rc;
+    pool_cap = h->rt_pool.bytes / 4;
+    todo.swap(again);
+    n_todo = todo.size();
   }
+  const uint64_t used = h->h_counters[CTR_ROUTE_SLOTS];
+  if (used + B > h->rt_slots_cap) { /* at most one new slot per request */
+    const uint64_t cap = (used + B) * 2 + 64;
+    if ((rc = grow_keep(h, h->rt_off, cap * 8))) return rc;
+    if ((rc = grow_keep(h, h->rt_len, cap * 4))) return rc;
+    if ((rc = grow_keep(h, h->rt_pos, cap * 4))) return rc;
+    if ((rc = grow_keep(h, h->rt_cost, cap * 8))) return rc;
+    h->rt_slots_cap = cap;
+  }
+  RouteBindBody bb;
+  bb.rs = route_store(h); bb.r_cost = (int64_t*)h->rt_cost.p; bb.agent_id = d_id; bb.status = (const uint32_t*)h->as_status.p;
+  bb.len = (const uint32_t*)h->as_len.p; bb.cost = (const int64_t*)h->as_cost.p; bb.pool_off = (const uint64_t*)h->as_off.p;
+  bb.slot_counter = ctr + CTR_ROUTE_SLOTS;
+  { ProfScope ps(h->prof, h->stream, "route_bind", B); launch_foreach(h->stream, bb, B); }
+  if ((rc = check_launch(h, "route bind"))) return rc;
   unsigned long long e = 0;
   ABM_CK(h, copy_d2h(&e, d_exp, 8, h->stream));
   h->expansions = (double)e;
@@ -1642,6 +1704,7 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
   h->nsx = g.nx / SUB; h->nsy = g.ny / SUB;
   if (const char* mg = getenv("ABM_MIGRANTS")) h->use_migrants = atoi(mg) != 0;
   if (const char* ov = getenv("ABM_OVERLAP")) h->overlap_halo = atoi(ov) != 0;
+  if (const char* ag = getenv("ABM_ASTAR_GB")) { const int q = atoi(ag); if (q >= 1 && q <= 160) h->astar_budget = (uint64_t)q << 30; }
   if (const char* sw = getenv("ABM_SPLIT_WAITS")) h->split_waits = atoi(sw) != 0;
   if (const char* op = getenv("ABM_OPTIMISTIC")) h->optimistic = atoi(op) != 0;
   if (const char* ar = getenv("ABM_AGENT_ROUNDS")) { const int q = atoi(ar); if (q >= 0 && q <= 16) h->fixed_agent_rounds = q; }
@@ -1716,6 +1779,7 @@ int ABM_API(set_grid)(abm_handle* h, const uint8_t* fg, const int64_t* cd, const
   const Geo& g = h->g;
   ABM_CK(h, dev_memset(h->grass.p, GRASS_PAD, g.gt, h->stream));
   ABM_CK(h, dev_memset(h->walkbits.p, 0, (size_t)g.gt / 8, h->stream));
+  h->comp_valid = false;
   if ((rc = ensure(h, h->elev, (size_t)g.gt * 2))) return rc;
   ABM_CK(h, dev_memset(h->elev.p, 0, (size_t)g.gt * 2, h->stream));
   ABM_CK(h, dev_memset((uint32_t*)h->counters.p + CTR_ERR, 0, 4, h->stream));

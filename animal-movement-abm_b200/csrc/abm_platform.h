@@ -29,6 +29,7 @@ namespace abm {
 
 static inline uint32_t atomic_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 static inline uint32_t atomic_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+static inline uint32_t atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) { uint32_t o = *p; if (o == cmp) *p = v; return o; }
 static inline uint32_t atomic_max(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
 static inline uint32_t atomic_exch(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = v; return o; }
 static inline unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
@@ -69,6 +70,7 @@ static inline void launch_foreach(abm_stream_t, const F& f, uint64_t n, const ch
 static inline uint32_t smem_min(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 static inline uint32_t smem_max(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
 static inline uint32_t smem_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
+static inline void smem_min64(unsigned long long* p, unsigned long long v) { if (v < *p) *p = v; }
 static inline uint32_t smem_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 /* minimum over the 32 lanes of a warp that all execute this call, folded into *dst; returns the minimum known to the
  * caller (lanes run one after another here, so that is the running value) */
@@ -118,6 +120,7 @@ namespace abm {
 
 ABM_D uint32_t atomic_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
 ABM_D uint32_t atomic_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
+ABM_D uint32_t atomic_cas(uint32_t* p, uint32_t cmp, uint32_t v) { return atomicCAS(p, cmp, v); }
 ABM_D uint32_t atomic_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
 ABM_D uint32_t atomic_exch(uint32_t* p, uint32_t v) { return atomicExch(p, v); }
 ABM_D unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
@@ -147,6 +150,7 @@ static inline void launch_foreach(abm_stream_t s, const F& f, uint64_t n, const 
 ABM_D uint32_t smem_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 ABM_D uint32_t smem_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
 ABM_D uint32_t smem_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+ABM_D void smem_min64(unsigned long long* p, unsigned long long v) { atomicMin(p, v); }
 ABM_D uint32_t smem_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
 /* minimum over the 32 lanes of a warp that all execute this call (converged), folded into *dst by lane 0 */
 ABM_D uint32_t warp_min_into(uint32_t* dst, uint32_t v, int lane) {

@@ -167,6 +167,76 @@ def test_emulated_astar_paths_match_oracle(emu, oracle, metric, penalty, periodi
         _same_paths(a, b, ids)
 
 
+def test_emulated_astar_slot_reuse_and_pool_overflow(emu, oracle, monkeypatch):
+    """More than 255 searches through one slot (the emulated launcher lets the first CTA drain the queue: the 8-bit
+    generation stamp wraps and the slot is wiped) and a route pool that starts far too small (requests re-run)."""
+    monkeypatch.setenv("ABM_ROUTE_POOL_GUESS", "40")
+    monkeypatch.setenv("ABM_ASTAR_SLOTS", "3")  # fewer slots than requests: the far-goals-first ordering runs too
+    a, w = _plan_case(oracle, 1, 1, 1, nx=48, ny=40, n=300, seed=5)
+    b, _ = _plan_case(emu, 1, 1, 1, nx=48, ny=40, n=300, seed=5)
+    off = _same_paths(a, b, w["ids"])
+    assert off[-1] > 2000
+    # a second batch over the same agents rebinds every route
+    rng = np.random.default_rng(9)
+    ok = np.argwhere(w["walkmap"] == 1)
+    goals = ok[rng.integers(0, len(ok), 300)]
+    for e in (a, b):
+        e.plan_routes(w["ids"], goals[:, 1] + 1, goals[:, 0] + 1)
+    _same_paths(a, b, w["ids"])
+
+
+def _island_case(lib, periodic):
+    """A wall of water splits the map; agents on both sides, on the wall (not walkable) and goals everywhere."""
+    nx, ny = 40, 32
+    wm = np.ones((ny, nx), np.uint8)
+    wm[:, 18:21] = 0       # the wall
+    wm[10, 18:21] = 1 if periodic else 0  # periodic case: a bridge through the wall
+    wm[:, 0] = 0           # second wall on the seam: without the bridge the halves are disconnected even when periodic
+    wm[20:24, 30:34] = 0
+    wm[21:23, 31:33] = 1   # a lake with an island in it (diagonal moves cannot cross a 1-cell ring either)
+    el = (np.arange(nx)[None, :] * 3 + np.arange(ny)[:, None] * 5) % 17 + 1
+    fg = np.ones((ny, nx), np.uint8)
+    cd = np.full((ny, nx), 30, np.int64)
+    starts = [(3, 3), (25, 5), (19, 4), (32, 22), (5, 28), (38, 30), (2, 16), (22, 11)]   # (x, y) 1-based; (19,4) stands on the wall
+    goals = [(15, 20), (4, 25), (6, 6), (8, 8), (32, 22), (33, 23), (19, 20), (35, 11)]     # (19,20) is water; (32,22)/(33,23) the island
+    n = len(starts)
+    e = lib.create(lib.default_config(nx=nx, ny=ny, periodic=periodic, walk_type=3, astar_metric=1, astar_penalty=1, counter=9))
+    e.set_grid(fg, cd, wm, el.astype(np.int64))
+    ids = np.arange(1, n + 1)
+    e.set_agents(ids, np.array([s[0] for s in starts]), np.array([s[1] for s in starts]), np.full(n, 5.0))
+    e.plan_routes(ids, np.array([g[0] for g in goals]), np.array([g[1] for g in goals]))
+    return e, ids
+
+
+@pytest.mark.parametrize("periodic", [0, 1])
+def test_emulated_astar_unreachable_goals(emu, oracle, periodic):
+    """Goals in another component of the walkmap, on water, and a start that stands on water: the engine answers the
+    first two from its component labels without searching; results must equal the oracle's exhaustive search."""
+    a, ids = _island_case(oracle, periodic)
+    b, _ = _island_case(emu, periodic)
+    off = _same_paths(a, b, ids)
+    _, _, _, cost = b.get_paths(ids)
+    assert (cost < 0).sum() >= 3 and (cost >= 0).sum() >= 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("periodic", [0, 1])
+def test_gpu_astar_unreachable_goals(libabm, oracle, periodic):
+    a, ids = _island_case(oracle, periodic)
+    b, _ = _island_case(libabm, periodic)
+    _same_paths(a, b, ids)
+
+
+@pytest.mark.gpu
+def test_gpu_astar_pool_overflow_and_many_requests(libabm, oracle, monkeypatch):
+    """The device-side request queue with more requests than search slots, and the pool-overflow retry, on the GPU."""
+    monkeypatch.setenv("ABM_ROUTE_POOL_GUESS", "1000")
+    monkeypatch.setenv("ABM_ASTAR_GB", "1")
+    a, w = _plan_case(oracle, 1, 1, 1, nx=256, ny=192, n=6000, seed=8)
+    b, _ = _plan_case(libabm, 1, 1, 1, nx=256, ny=192, n=6000, seed=8)
+    _same_paths(a, b, w["ids"])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("metric,penalty,periodic", [(1, 1, 1), (0, 0, 1), (1, 1, 0)])
 def test_gpu_astar_paths_match_oracle(libabm, oracle, metric, penalty, periodic):
