@@ -12,8 +12,8 @@
  * u64 keys f<<32 | x<<16 | y (1-based x, y), whose integer order IS the reference's tuple order — and the keys are
  * unique (a cell is pushed again only with a strictly smaller g, hence f) — so the sequence of distinct expansions,
  * and with it every parent pointer, equals the reference's whatever the heap's internal layout.  A node's 32 children
- * are one coalesced 256-byte load, the minimum is found with one shared-memory atomic per lane: a pop is ~log32(n)
- * dependent memory round trips instead of ~2 log2(n); the 8 neighbours are relaxed by 8 lanes at once.  Per-search
+ * are one coalesced 256-byte load and their minimum two warp reductions: a pop is ~log32(n) dependent memory round
+ * trips instead of ~2 log2(n); the 8 neighbours are loaded by 8 lanes while lane 0 loads the popped cell.  Per-search
  * state lives in a slot of dense per-cell arrays in HBM (g: u32, meta: u16 = generation<<8 | closed<<4 | parent
  * direction); the per-slot generation stamp makes a slot reusable without clearing it.  The finished search walks its
  * parents and writes the path straight into the route pool (space claimed with one 64-bit atomicAdd).
@@ -133,8 +133,9 @@ struct AStarShared {
   unsigned long long ck[AS_ARITY]; /* the children just loaded */
   unsigned long long best[2];      /* their minimum, alternating per level */
   unsigned long long nk[8];        /* keys the 8 neighbour lanes want pushed (0 = none) */
+  uint32_t n_g[8]; int32_t n_e[8]; uint16_t n_m[8]; uint8_t n_ok[8]; /* what the neighbour lanes loaded */
   unsigned long long last, nexp;
-  uint32_t hn, cur, lvl, sift, fin, skip, status, req, wipe, gen;
+  uint32_t hn, hn2, cur, lvl, sift, fin, skip, status, req, wipe, gen; /* hn: open-list size before the pop, hn2: after */
   uint32_t s, t; int32_t tx, ty, x, y, ec, et; uint32_t c, gc;
 };
 
@@ -202,21 +203,35 @@ struct AStarWarpCta {
       }
       ABM_CTA_SYNC();
       while (true) {
-        /* pop: the root leaves, the last key waits to be placed; the popped cell is closed (or recognised as stale) */
+        /* pop: the root leaves, the last key waits to be placed; the popped cell is closed (or recognised as stale) by
+         * lane 0 while lanes 8..15 load everything about its 8 neighbours — one memory round trip for both */
         ABM_CTA_FOR(t, NT) {
-          if (t == 0) {
-            if (sh.hn == 0) sh.fin = 1;
-            else {
-              const uint64_t top = sh.top[0];
-              const uint32_t hn = sh.hn - 1;
-              sh.last = hn < AS_TOP ? sh.top[hn] : h[hn]; sh.hn = hn;
-              sh.cur = 0; sh.lvl = 0; sh.sift = hn > 0 ? 1u : 0u; sh.skip = 0;
-              sh.best[0] = AS_NOKEY; sh.best[1] = AS_NOKEY;
-              const int x = (int)((top >> 16) & 0xFFFF) - 1, y = (int)(top & 0xFFFF) - 1;
-              const uint32_t c = enc(a.g, x, y);
+          if (sh.hn == 0) { if (t == 0) sh.fin = 1; }
+          else {
+            const uint64_t top = sh.top[0];
+            const int x = (int)((top >> 16) & 0xFFFF) - 1, y = (int)(top & 0xFFFF) - 1;
+            const uint32_t c = enc(a.g, x, y);
+            if (t >= 8 && t < 16) {
+              const int d = t - 8;
+              int ddx, ddy, ox, oy;
+              off8(d, ddx, ddy);
+              const bool inside = shift(a.g, x, y, ddx, ddy, ox, oy);
+              const uint32_t nc = inside ? enc(a.g, ox, oy) : c;
+              const uint32_t wb = a.walkbits[nc >> 5];
+              const uint16_t mn = m[nc];
+              const uint32_t gn = g[nc];
+              const int32_t en = a.penalty ? (int32_t)a.elev[nc] : 0;
+              sh.n_ok[d] = (uint8_t)(inside && ((wb >> (nc & 31)) & 1u));
+              sh.n_m[d] = mn; sh.n_g[d] = gn; sh.n_e[d] = en;
+            }
+            if (t == 0) {
               const uint16_t mc = m[c]; /* the three loads go out together */
               const uint32_t gc = g[c];
               const int32_t ec = a.penalty ? (int32_t)a.elev[c] : 0;
+              const uint32_t hn = sh.hn - 1;
+              sh.last = hn < AS_TOP ? sh.top[hn] : h[hn]; sh.hn2 = hn;
+              sh.cur = 0; sh.lvl = 0; sh.sift = hn > 0 ? 1u : 0u; sh.skip = 0;
+              sh.best[0] = AS_NOKEY; sh.best[1] = AS_NOKEY;
               if (c == sh.t) { sh.status = AS_FOUND; sh.fin = 1; }
               else if (mc & AS_CLOSED) sh.skip = 1; /* stale duplicate of an expanded node: re-expansion could not improve anything */
               else { m[c] = (uint16_t)(mc | AS_CLOSED); sh.nexp += 1; sh.gc = gc; sh.ec = ec; sh.x = x; sh.y = y; sh.c = c; }
@@ -229,19 +244,17 @@ struct AStarWarpCta {
         ABM_CTA_FOR(t, NT) {
           if (t < 8) {
             unsigned long long key = 0;
-            if (!sh.skip) {
-              int ddx, ddy, ox, oy;
-              off8(t, ddx, ddy);
-              const bool inside = shift(a.g, sh.x, sh.y, ddx, ddy, ox, oy);
-              const uint32_t nc = inside ? enc(a.g, ox, oy) : sh.c;
-              const uint32_t wb = a.walkbits[nc >> 5]; /* every load of this neighbour up front: one round trip */
-              const uint16_t mn = m[nc];
-              const uint32_t gn = g[nc];
-              const int32_t en = a.penalty ? (int32_t)a.elev[nc] : 0;
+            if (!sh.skip && sh.n_ok[t]) {
+              const uint16_t mn = sh.n_m[t];
               const bool seen = (uint32_t)(mn >> 8) == sh.gen;
-              if (inside && ((wb >> (nc & 31)) & 1u) && !(seen && (mn & AS_CLOSED))) {
+              if (!(seen && (mn & AS_CLOSED))) {
+                int ddx, ddy, ox, oy;
+                off8(t, ddx, ddy);
+                shift(a.g, sh.x, sh.y, ddx, ddy, ox, oy);
+                const uint32_t nc = enc(a.g, ox, oy);
+                const int32_t en = sh.n_e[t];
                 const int64_t ng = (int64_t)sh.gc + astar_cost_e(a, sh.x, sh.y, sh.ec, ox, oy, en);
-                if (!seen || ng < (int64_t)gn) {
+                if (!seen || ng < (int64_t)sh.n_g[t]) {
                   g[nc] = (uint32_t)ng;
                   m[nc] = (uint16_t)(sh.gen << 8 | (uint32_t)t);
                   key = astar_key(ng + astar_cost_e(a, ox, oy, en, sh.tx, sh.ty, sh.et), ox, oy);
@@ -251,14 +264,14 @@ struct AStarWarpCta {
             sh.nk[t] = key;
           }
         }
-        /* sift-down of the waiting key: per level one coalesced load of the 32 children and one atomic min per lane */
+        /* sift-down of the waiting key: per level one coalesced load of the 32 children and a warp-reduced minimum */
         while (sh.sift) {
           const uint32_t lv = sh.lvl & 1u;
           ABM_CTA_FOR(t, NT) {
             const uint64_t ci = (uint64_t)sh.cur * AS_ARITY + 1 + (uint64_t)t;
-            const unsigned long long key = ci < sh.hn ? (ci < AS_TOP ? sh.top[ci] : h[ci]) : AS_NOKEY;
+            const unsigned long long key = ci < sh.hn2 ? (ci < AS_TOP ? sh.top[ci] : h[ci]) : AS_NOKEY;
             sh.ck[t] = key;
-            if (key != AS_NOKEY) smem_min64(&sh.best[lv], key);
+            warp_min64_into(&sh.best[lv], key, t);
           }
           ABM_CTA_SYNC();
           ABM_CTA_FOR(t, NT) {
@@ -276,8 +289,8 @@ struct AStarWarpCta {
         }
         ABM_CTA_SYNC();
         ABM_CTA_FOR(t, NT) {
-          if (t == 0 && !sh.skip) {
-            uint32_t hn = sh.hn;
+          if (t == 0) {
+            uint32_t hn = sh.hn2;
             for (int d = 0; d < 8; ++d) {
               const unsigned long long key = sh.nk[d];
               if (key && !heap_push(h, sh.top, hn, heap_cap, key)) { sh.status = AS_HEAP_FULL; sh.fin = 1; break; }

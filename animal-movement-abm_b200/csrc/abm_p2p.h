@@ -57,11 +57,12 @@ struct P2PStatsSendCta {
       }
     }
     ABM_CTA_SYNC();
-    ABM_CTA_FOR(t, 64) {
-      for (int i = t; i < P * nv; i += 64) dst[i / nv][i % nv] = vec[i % nv];
+    ABM_CTA_FOR(t, 64) { /* thread r serves rank r: its own stores, its own fence, its own flag */
+      if (t < P) {
+        for (int w = 0; w < nv; ++w) dst[t][w] = vec[w];
+        flag_publish(flag[t], seq);
+      }
     }
-    ABM_CTA_SYNC();
-    ABM_CTA_FOR(t, 64) { if (t < P) flag_publish(flag[t], seq); }
   }
 };
 struct P2PStatsRecvCta {

@@ -70,7 +70,7 @@ static inline void launch_foreach(abm_stream_t, const F& f, uint64_t n, const ch
 static inline uint32_t smem_min(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 static inline uint32_t smem_max(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
 static inline uint32_t smem_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
-static inline void smem_min64(unsigned long long* p, unsigned long long v) { if (v < *p) *p = v; }
+static inline void warp_min64_into(unsigned long long* dst, unsigned long long v, int /*lane*/) { if (v < *dst) *dst = v; }
 static inline uint32_t smem_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 /* minimum over the 32 lanes of a warp that all execute this call, folded into *dst; returns the minimum known to the
  * caller (lanes run one after another here, so that is the running value) */
@@ -150,7 +150,14 @@ static inline void launch_foreach(abm_stream_t s, const F& f, uint64_t n, const 
 ABM_D uint32_t smem_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 ABM_D uint32_t smem_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
 ABM_D uint32_t smem_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
-ABM_D void smem_min64(unsigned long long* p, unsigned long long v) { atomicMin(p, v); }
+/* 64-bit minimum over the 32 converged lanes of a warp (two 32-bit reductions), folded into *dst by lane 0 */
+ABM_D void warp_min64_into(unsigned long long* dst, unsigned long long v, int lane) {
+  const uint32_t hi = (uint32_t)(v >> 32);
+  const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+  const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? (uint32_t)v : 0xFFFFFFFFu);
+  const unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
+  if (lane == 0 && m < *dst) *dst = m;
+}
 ABM_D uint32_t smem_or(uint32_t* p, uint32_t v) { return atomicOr(p, v); }
 /* minimum over the 32 lanes of a warp that all execute this call (converged), folded into *dst by lane 0 */
 ABM_D uint32_t warp_min_into(uint32_t* dst, uint32_t v, int lane) {
