@@ -169,7 +169,8 @@ int abm_get_paths(abm_handle* h, int64_t b, const int64_t* agent_id, int64_t* of
                   int64_t* px, int64_t* py, int64_t* cost);
 
 /* device timing of the last abm_step in milliseconds: out[0] total, out[1] agent phase, out[2] grass phase,
- * out[3] resolution rounds (count), out[4] kernels launched, out[5] A* expansions of the last plan call,
+ * out[3] resolution rounds (count), out[4] kernels launched, out[5] A* expansions performed by the last plan call
+ * (a goal outside the start's walkmap component is answered without searching and costs none),
  * out[6] agent-updates performed (sum over ticks of the population at tick start) */
 int abm_get_timing(abm_handle* h, double* out, int32_t n);
 
