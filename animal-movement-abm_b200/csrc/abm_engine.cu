@@ -272,6 +272,7 @@ struct abm_handle {
   uint64_t as_slots = 0, as_heap_cap = 0, rt_slots_cap = 0, rt_pool_used = 0, rt_ids_cap = 0;
   /* tile path (abm_tile.h): sub-tile runs of the SoA (ping-pong with the SoA), offspring fix-up lists */
   bool tile_mode = false;
+  uint64_t birth_bitmap_from = 32768; /* ABM_BIRTH_BITMAP: gathered offspring capacity above which ids are ranked through a bitmap */
   bool split_waits = false;       /* ABM_SPLIT_WAITS=1: counters and decision bytes as send, send, wait, wait (measured: 2 % slower than one after the other) */
   bool overlap_halo = false;      /* ABM_OVERLAP=1: halo exchange on a second stream behind the interior rows (measured: no gain) */
   bool optimistic = true;         /* enqueue the commit behind a device-side guard instead of reading counters first (ABM_OPTIMISTIC=0 disables) */
@@ -1283,17 +1284,31 @@ static int strip_birth_ids(abm_handle* h, uint64_t bbcap, int nxt, uint32_t* d_t
     }
   }
   uint32_t* ranks = all + words * (size_t)P; /* zeroed scratch, one counter per local birth */
-  ABM_CK(h, dev_memset(ranks, 0, (bbcap + 1) * 4, h->stream));
-  BirthRankBody br;
-  br.all = all; br.n_ranks = P; br.cap = (uint32_t)bbcap;
-  br.birth_parent = (const uint32_t*)h->birth_parent.p; br.birth_count = ctr + CTR_BIRTHS; br.rank_out = ranks;
   BirthAssignBody ba;
   ba.all = all; ba.n_ranks = P; ba.cap = (uint32_t)bbcap; ba.next_id = (uint32_t)h->next_id;
-  ba.birth_pos = (const uint32_t*)h->birth_pos.p; ba.birth_count = ctr + CTR_BIRTHS; ba.rank_in = ranks;
+  ba.birth_pos = (const uint32_t*)h->birth_pos.p; ba.birth_parent = (const uint32_t*)h->birth_parent.p; ba.birth_count = ctr + CTR_BIRTHS;
+  ba.rank_in = ranks; ba.birth_bits = nullptr; ba.birth_prefix = nullptr;
   ba.out_id = (uint32_t*)h->id[nxt].p; ba.total_out = d_total;
-  { ProfScope ps(h->prof, h->stream, "birth_ids", bbcap, 2);
+  if ((uint64_t)P * bbcap > h->birth_bitmap_from) { /* many offspring: bitmap over the id space + popcount prefix */
+    const uint64_t idw = bitmap_words(h->next_id);
+    if ((rc = ensure(h, h->bits, (idw + 4) * 4))) return rc;
+    ProfScope ps(h->prof, h->stream, "birth_ids", bbcap, 2);
+    ABM_CK(h, dev_memset(h->bits.p, 0, idw * 4, h->stream));
+    BirthMarkBody bm;
+    bm.all = all; bm.n_ranks = P; bm.cap = (uint32_t)bbcap; bm.bits = (uint32_t*)h->bits.p;
+    launch_foreach(h->stream, bm, (uint64_t)P * bbcap);
+    if ((rc = rank_prefix(h, idw))) return rc;
+    ba.birth_bits = (const uint32_t*)h->bits.p; ba.birth_prefix = (const uint32_t*)h->bits_prefix.p;
+    launch_foreach(h->stream, ba, bbcap ? bbcap : 1);
+  } else {
+    ABM_CK(h, dev_memset(ranks, 0, (bbcap + 1) * 4, h->stream));
+    BirthRankBody br;
+    br.all = all; br.n_ranks = P; br.cap = (uint32_t)bbcap;
+    br.birth_parent = (const uint32_t*)h->birth_parent.p; br.birth_count = ctr + CTR_BIRTHS; br.rank_out = ranks;
+    ProfScope ps(h->prof, h->stream, "birth_ids", bbcap, 2);
     launch_foreach(h->stream, br, (bbcap ? bbcap : 1) * 32);
-    launch_foreach(h->stream, ba, bbcap ? bbcap : 1); }
+    launch_foreach(h->stream, ba, bbcap ? bbcap : 1);
+  }
   return check_launch(h, "birth ids");
 }
 
@@ -1706,6 +1721,7 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
   if (const char* ov = getenv("ABM_OVERLAP")) h->overlap_halo = atoi(ov) != 0;
   if (const char* ag = getenv("ABM_ASTAR_GB")) { const int q = atoi(ag); if (q >= 1 && q <= 160) h->astar_budget = (uint64_t)q << 30; }
   if (const char* sw = getenv("ABM_SPLIT_WAITS")) h->split_waits = atoi(sw) != 0;
+  if (const char* bb = getenv("ABM_BIRTH_BITMAP")) h->birth_bitmap_from = (uint64_t)std::max(atoll(bb), 0ll);
   if (const char* op = getenv("ABM_OPTIMISTIC")) h->optimistic = atoi(op) != 0;
   if (const char* ar = getenv("ABM_AGENT_ROUNDS")) { const int q = atoi(ar); if (q >= 0 && q <= 16) h->fixed_agent_rounds = q; }
   if (const char* tm = getenv("ABM_TILE_MARGIN")) { const int q = atoi(tm); if (q >= 2 && q <= HALO) h->tile_margin = q; }

@@ -1034,12 +1034,33 @@ struct BirthRankBody {
 };
 struct BirthAssignBody {
   const uint32_t* all; int32_t n_ranks; uint32_t cap; uint32_t next_id;
-  const uint32_t* birth_pos; const uint32_t* birth_count; const uint32_t* rank_in;
+  const uint32_t* birth_pos; const uint32_t* birth_parent; const uint32_t* birth_count;
+  const uint32_t* rank_in;                                  /* from BirthRankBody, or */
+  const uint32_t* birth_bits; const uint32_t* birth_prefix; /* the bitmap of all gathered parents + its popcount prefix */
   uint32_t* out_id; uint32_t* total_out;
   ABM_HD void operator()(uint64_t i) const {
     if (i == 0) { uint32_t t = 0; for (int r = 0; r < n_ranks; ++r) t += all[(size_t)r * (1 + cap)]; *total_out = t; }
     if (i >= *birth_count) return;
-    out_id[birth_pos[i]] = next_id + rank_in[i];
+    uint32_t rank;
+    if (birth_bits) {
+      const uint32_t pid = birth_parent[i], wd = pid >> 5;
+      rank = birth_prefix[wd] + (uint32_t)popc(birth_bits[wd] & ((1u << (pid & 31)) - 1u));
+    } else rank = rank_in[i];
+    out_id[birth_pos[i]] = next_id + rank;
+  }
+};
+/* many offspring (C5: ~10^6 per tick): instead of comparing every parent with every other, mark all gathered parents in
+ * a bitmap over the id space; a parent's rank is the popcount below its bit (the single-GPU way, BirthIdBody) */
+struct BirthMarkBody {
+  const uint32_t* all; int32_t n_ranks; uint32_t cap; uint32_t* bits;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint32_t r = (uint32_t)(i / cap), k = (uint32_t)(i % cap);
+    if ((int)r >= n_ranks) return;
+    const uint32_t* p = all + (size_t)r * (1 + cap);
+    const uint32_t n = p[0] < cap ? p[0] : cap;
+    if (k >= n) return;
+    const uint32_t pid = p[1 + k];
+    atomic_or(&bits[pid >> 5], 1u << (pid & 31));
   }
 };
 

@@ -45,6 +45,52 @@ def make_terrain(nx: int, ny: int, seed: int = 7, octaves: int = 4, base: int = 
     return (np.floor(h * 39 * 0.62) + 1).astype(np.int64)
 
 
+def _noise_rows(nx: int, ny: int, lattices, rows, cols):
+    """Normalised value noise (same construction as make_terrain) at the given global row / column indices."""
+    h = np.zeros((len(rows), len(cols)), np.float64)
+    amp, total = 1.0, 0.0
+    for cell, lat in lattices:
+        gy, gx = lat.shape
+        ys = (np.asarray(rows) / cell) % gy
+        xs = (np.asarray(cols) / cell) % gx
+        y0 = np.floor(ys).astype(np.int64); x0 = np.floor(xs).astype(np.int64)
+        fy = ys - y0; fx = xs - x0
+        fy = fy * fy * (3 - 2 * fy); fx = fx * fx * (3 - 2 * fx)
+        y1 = (y0 + 1) % gy; x1 = (x0 + 1) % gx
+        top = lat[np.ix_(y0, x0)]
+        top += (lat[np.ix_(y0, x1)] - top) * fx[None, :]
+        bot = lat[np.ix_(y1, x0)]
+        bot += (lat[np.ix_(y1, x1)] - bot) * fx[None, :]
+        top += (bot - top) * fy[:, None]
+        h += amp * top
+        total += amp
+        amp *= 0.5
+    return h / total
+
+
+def make_terrain_rows(nx: int, ny: int, y0: int, rows: int, seed: int = 7, octaves: int = 4, base: int = 64, chunk: int = 256):
+    """Rows y0 .. y0+rows-1 (wrapped) of a periodic nx x ny elevation map, without building the whole map: what one
+    strip of a multi-GPU world needs (its own rows plus ghost rows).  Same value noise as make_terrain; the stretch to
+    1..40 uses quantiles of a coarse global sample, so every rank derives the same map from the seed alone."""
+    rng = _rng(seed)
+    lattices = []
+    for o in range(octaves):
+        cell = max(2, base >> o)
+        gx, gy = max(1, -(-nx // cell)), max(1, -(-ny // cell))
+        lattices.append((cell, rng.random((gy, gx))))
+    sy, sx = max(1, ny // 1024), max(1, nx // 1024)
+    coarse = _noise_rows(nx, ny, lattices, np.arange(0, ny, sy), np.arange(0, nx, sx))
+    lo, hi = np.quantile(coarse, 0.02), np.quantile(coarse, 0.98)
+    out = np.empty((rows, nx), np.int64)
+    cols = np.arange(nx)
+    for r0 in range(0, rows, chunk):
+        r1 = min(rows, r0 + chunk)
+        h = _noise_rows(nx, ny, lattices, (y0 + np.arange(r0, r1)) % ny, cols)
+        h = np.clip((h - lo) / max(hi - lo, 1e-12), 0.0, 1.0)
+        out[r0:r1] = np.floor(h * 39 * 0.62) + 1
+    return out
+
+
 def walkmap_from_elevation(elevation, water_level: int = 1, mountain_level: int = 18):
     """land_walkmap[i, j] = water_level < elevation[i, j] < mountain_level (scripts/v0.5.jl:64-68)."""
     return ((elevation > water_level) & (elevation < mountain_level)).astype(np.uint8)
@@ -67,8 +113,9 @@ def has_walkable_neighbour(walkmap, periodic: bool = True):
 
 
 def make_world(nx: int, ny: int, n_sheep: int, seed: int = 321, regrowth_time: int = 30, delta_energy: int = 4,
-               walkmap=None, distinct_cells: bool = False, periodic: bool = True):
-    """Agents (ids 1..n, 1-based positions, energies 0..5Δ-1) and grass arrays."""
+               walkmap=None, distinct_cells: bool = False, periodic: bool = True, placeable=None):
+    """Agents (ids 1..n, 1-based positions, energies 0..5Δ-1) and grass arrays.  `placeable` (optional mask) replaces
+    the walkable-with-a-walkable-neighbour rule, e.g. when the neighbours live in another strip's rows."""
     rng = _rng(seed)
     energy = rng.integers(0, delta_energy * 5, n_sheep).astype(np.float64)
     if walkmap is None:
@@ -79,7 +126,8 @@ def make_world(nx: int, ny: int, n_sheep: int, seed: int = 321, regrowth_time: i
     else:
         # random_walkable: uniform over walkable cells; cells whose 8 neighbours are all blocked are left out
         # because the reference's random_walkmap throws there
-        ok = np.flatnonzero((np.asarray(walkmap).astype(bool) & has_walkable_neighbour(walkmap, periodic)).reshape(-1))
+        mask = placeable if placeable is not None else (np.asarray(walkmap).astype(bool) & has_walkable_neighbour(walkmap, periodic))
+        ok = np.flatnonzero(np.asarray(mask).reshape(-1))
         lin = ok[rng.integers(0, ok.size, n_sheep)]  # random_walkable: uniform over walkable cells
     x = (lin % nx).astype(np.int64) + 1
     y = (lin // nx).astype(np.int64) + 1

@@ -36,15 +36,34 @@ WORKLOADS = {
                desc="v0.3 RANDOM_WALK_GREGARIOUS r=3, periodic {n}x{n} grid, {a} sheep (BASELINE.json configs[1])"),
     "C3": dict(walk_type=4, terrain=True, cfg=dict(walkmap_regrowth=1, reproduction_prob=0.004),
                desc="v0.5 RANDOM_WALKMAP + walkmap regrowth, periodic {n}x{n} terrain, {a} sheep (BASELINE.json configs[2])"),
+    "C5": dict(walk_type=4, terrain=True, cfg=dict(walkmap_regrowth=1, reproduction_prob=0.004),
+               desc="v0.5 RANDOM_WALKMAP + walkmap regrowth, periodic {n}x{m} terrain, {a} sheep (BASELINE.json configs[4] per-GPU share: 32768x4096 rows of 32768x(4096 N))"),
     "C1": dict(walk_type=0, terrain=False, cfg=dict(reproduction_prob=0.001),
                desc="v0.1 RANDOM_WALK, {n}x{n} grid, {a} sheep"),
 }
 
 
-def make_world(workload, size, agents, seed=321):
+def make_world(workload, size, agents, seed=321, nx=None, rank=0, world=1):
+    """One rank's share: `size` rows of an nx-wide world of size * world rows (nx = size, world = 1: the square
+    single-GPU worlds).  With world > 1 the terrain arrays carry the 32 ghost rows above and below (true neighbours'
+    terrain, the y wrap included); grass and agents cover the own rows only."""
     from abm_b200 import worlds
     wl = WORKLOADS[workload]
-    wm = el = None
+    nx = nx or size
+    wm = el = place = None
+    if wl["terrain"] and (world > 1 or nx != size):
+        from abm_b200 import strips
+        gh = strips.GHOST if world > 1 else 1
+        el = worlds.make_terrain_rows(nx, size * world, size * rank - gh, size + 2 * gh, seed=322)
+        wm = worlds.walkmap_from_elevation(el)
+        place = (wm.astype(bool) & worlds.has_walkable_neighbour(wm, True))[gh:-gh]
+        if world == 1:
+            el, wm = el[gh:-gh], wm[gh:-gh]
+        w = worlds.make_world(nx, size, agents, seed=seed, walkmap=wm[gh:-gh] if world > 1 else wm, periodic=True, placeable=place)
+        w["walkmap"], w["elevation"] = wm, el
+        cfg = dict(nx=nx, ny=size, periodic=1, walk_type=wl["walk_type"], seed=seed)
+        cfg.update(wl["cfg"])
+        return cfg, w
     if wl["terrain"]:
         el = worlds.make_terrain(size, size, seed=seed + 1)
         wm = worlds.walkmap_from_elevation(el)
@@ -198,7 +217,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "agent_updates_per_s", "value": v, "unit": "agent-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32 cells / f64 energy", "data": "synthetic",
-        "config": {"workload": wl["desc"].format(n=args.size, a=args.size * args.size // 4), "sample": sample},
+        "config": {"workload": wl["desc"].format(n=args.size_x or args.size, m=args.size, a=(args.size_x or args.size) * args.size // 4), "sample": sample},
         "cpu_baseline": {"value": v, "unit": "agent-updates/s", "cores": 1, "kind": "port", "sample": sample,
                          "note": "C++ restatement of the reference rules + Agents.jl semantics (oracle/); Julia is not installed; Agents.jl step! is serial, hence 1 thread"},
         "e2e": {"value": v, "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -217,7 +236,8 @@ def main():
     ap.add_argument("--replans", type=int, default=1 << 14)
     ap.add_argument("--ref-replans", type=int, default=64)
     ap.add_argument("--max-dist", type=int, default=0)
-    ap.add_argument("--size", type=int, default=0, help="grid side; default = the BASELINE.json size of the workload (C2 4096, C3 8192, C4 2048)")
+    ap.add_argument("--size", type=int, default=0, help="grid side (rows per GPU); default = the BASELINE.json size of the workload (C2 4096, C3 8192, C4 2048, C5 4096 rows)")
+    ap.add_argument("--size-x", type=int, default=0, help="grid width when it differs from --size (C5: 32768)")
     ap.add_argument("--ref-size", type=int, default=1024)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -225,6 +245,8 @@ def main():
     args = ap.parse_args()
     if args.size <= 0:
         args.size = {"C3": 8192, "C4": 2048}.get(args.workload, 4096)
+    if args.size_x <= 0 and args.workload == "C5":
+        args.size_x = 32768
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -250,19 +272,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     lib = capi.CLib(build.LIBABM if os.path.exists(build.LIBABM) else build.build_libabm(), "abm_")
-    size, agents = args.size, args.size * args.size // 4
+    size = args.size                      # rows per GPU
+    nx = args.size_x or size              # width of the world
+    agents = nx * size // 4
     wl = WORKLOADS[args.workload]
-    cfg, w = make_world(args.workload, size, agents, seed=321 + rank)
+    cfg, w = make_world(args.workload, size, agents, seed=321 + rank, nx=nx, rank=rank, world=world)
     if world > 1:
-        # strip `rank` of a size x (size * world) GridSpace: this rank's rows and sheep (global ids and y), ghost rows for the grids
+        # strip `rank` of an nx x (size * world) GridSpace: this rank's rows and sheep (global ids and y), ghost rows for the grids
         from abm_b200 import strips
-        if wl["terrain"]:
-            raise SystemExit("the multi-GPU bench runs the C2 workload (terrain would have to be generated globally)")
         cfg.update(ny=size * world, strip_y0=size * rank, strip_ny=size, n_ranks=world, rank=rank, seed=321, device=local)
         eng = lib.create(lib.default_config(**cfg))
-        pad = lambda a: np.concatenate([np.zeros((strips.GHOST, size), a.dtype), a, np.zeros((strips.GHOST, size), a.dtype)], 0)
+        pad = lambda a: np.concatenate([np.zeros((strips.GHOST, nx), a.dtype), a, np.zeros((strips.GHOST, nx), a.dtype)], 0)
         eng.ny = size + 2 * strips.GHOST
-        eng.set_grid(pad(w["fully_grown"]), pad(w["countdown"]))
+        eng.set_grid(pad(w["fully_grown"]), pad(w["countdown"]), w["walkmap"], w["elevation"])  # terrain comes with its ghost rows
         eng.set_agents(w["ids"] + rank * agents, w["x"], w["y"] + size * rank, w["energy"], agents * world + 1)
         if args.transport == "auto":
             # peer-memory mailboxes need CUDA IPC + peer access between all ranks of the node; every rank must agree on the choice
@@ -282,7 +304,7 @@ def main():
     else:
         eng = load(lib, cfg, w, device=local)
     eng.set_profiling(True)
-    G = size * size
+    G = nx * size
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -330,7 +352,7 @@ def main():
         t = torch.empty(int(n), dtype=dtype).pin_memory()
         return t.numpy(), t
     keep = []
-    Gl = G if world == 1 else eng.ny * size  # grid arrays of a strip carry 2 x 32 ghost rows
+    Gl = G if world == 1 else eng.ny * nx  # grid arrays of a strip carry 2 x 32 ghost rows
     n_now = eng.count_agents()
     cap = int(n_now * 1.25) + 4096  # room for the offspring of the timed ticks
     host = {}
@@ -338,7 +360,7 @@ def main():
         host[k], t = pinned_empty(cap, dt); keep.append(t)
     host["fg"], t = pinned_empty(Gl, torch.uint8); keep.append(t)
     host["cd"], t = pinned_empty(Gl, torch.int64); keep.append(t)
-    host["fg"] = host["fg"].reshape(-1, size); host["cd"] = host["cd"].reshape(-1, size)
+    host["fg"] = host["fg"].reshape(-1, nx); host["cd"] = host["cd"].reshape(-1, nx)
     wm = el = None
     if w.get("walkmap") is not None:
         wm, t = pinned_empty(Gl, torch.uint8); keep.append(t)
@@ -399,9 +421,9 @@ def main():
             "metric": "agent_updates_per_s", "value": value, "unit": "agent-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32 cells / f64 energy", "data": "synthetic",
-            "config": {"workload": wl["desc"].format(n=size, a=agents), "grid": [size, size], "agents": agents, "ticks": args.steps,
+            "config": {"workload": wl["desc"].format(n=nx, m=size, a=agents), "grid": [nx, size], "agents": agents, "ticks": args.steps,
                        "l2": "flushed between ticks (256 MiB device write)" if flush is not None else "not flushed",
-                       "parallelism": "single GPU" if world == 1 else f"{world} row strips of a {size}x{size * world} grid, one per GPU, halo exchange inside abm_step over " + ("NVLink peer memory (kernel stores into the neighbours' mailboxes)" if args.transport == "p2p" else "NCCL"),
+                       "parallelism": "single GPU" if world == 1 else f"{world} row strips of a {nx}x{size * world} grid, one per GPU, halo exchange inside abm_step over " + ("NVLink peer memory (kernel stores into the neighbours' mailboxes)" if args.transport == "p2p" else "NCCL"),
                        "cells_per_s": G * world * args.steps / (ms_max * 1e-3), "resolution_rounds_per_tick": rounds / args.steps},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "agent-updates/s", "h2d_bytes_per_step": h2d // args.e2e_steps, "d2h_bytes_per_step": d2h // args.e2e_steps,

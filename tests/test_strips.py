@@ -92,6 +92,27 @@ def test_ring_of_processes_over_gloo(oracle, tmp_path, world, name):
         assert_same_state(strips.merge_snapshots([per_rank[r][t] for r in range(world)]), a.snapshot(), f"{name} world {world} tick {t}")
 
 
+@pytest.mark.parametrize("world,name", [(1, "walkmap"), (3, "attractor")])
+def test_offspring_ids_through_the_bitmap(emu, oracle, tmp_path, monkeypatch, world, name):
+    """ABM_BIRTH_BITMAP=0: offspring ids of the strips are ranked through the id-space bitmap (the path taken when a tick
+    has ~10^5 births or more) instead of the all-pairs rank kernel; spawned workers inherit the variable."""
+    monkeypatch.setenv("ABM_BIRTH_BITMAP", "0")
+    cfgkw, w = _case(name)
+    a = load_case(oracle, cfgkw, w)
+    ticks = 8
+    if world == 1:
+        b = strips.load_strip(emu, cfgkw, w, 1, 0)
+        for t in range(ticks):
+            a.step(1)
+            b.step(1)
+            assert_same_state(strips.merge_snapshots([strips.strip_snapshot(b)]), a.snapshot(), f"{name} tick {t}")
+        return
+    per_rank = _run_ring(world, name, ticks, tmp_path)
+    for t in range(ticks):
+        a.step(1)
+        assert_same_state(strips.merge_snapshots([per_rank[r][t] for r in range(world)]), a.snapshot(), f"{name} world {world} tick {t}")
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["rw", "gregarious"])
 def test_single_strip_on_the_gpu(libabm, oracle, name):
@@ -133,3 +154,19 @@ def test_two_strips_over_peer_memory(libabm, oracle, tmp_path, name):
     for t in range(ticks):
         a.step(1)
         assert_same_state(strips.merge_snapshots([per_rank[r][t] for r in range(2)]), a.snapshot(), f"{name} tick {t}")
+
+
+@pytest.mark.gpu
+def test_two_strips_offspring_bitmap_on_the_gpu(libabm, oracle, tmp_path, monkeypatch):
+    """The bitmap ranking of offspring ids (ABM_BIRTH_BITMAP=0 forces it) over the peer-memory transport."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("ABM_BIRTH_BITMAP", "0")
+    ticks = 8
+    per_rank = _run_ring(2, "walkmap", ticks, tmp_path, use_gpu=True, transport="p2p")
+    cfgkw, w = _case("walkmap")
+    a = load_case(oracle, cfgkw, w)
+    for t in range(ticks):
+        a.step(1)
+        assert_same_state(strips.merge_snapshots([per_rank[r][t] for r in range(2)]), a.snapshot(), f"walkmap tick {t}")

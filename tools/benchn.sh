@@ -1,6 +1,6 @@
 # usage: benchn.sh TAG N TRANSPORT [extra]
 TAG=$1; N=$2; T=$3; shift 3
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --transport $T "$@" > gpurun_out/${TAG}.json 2> gpurun_out/${TAG}.err
+timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --transport $T "$@" > gpurun_out/${TAG}.json 2> gpurun_out/${TAG}.err
 python - <<EOF
 import json
 d=json.loads(open("gpurun_out/${TAG}.json").read().strip().splitlines()[-1])
