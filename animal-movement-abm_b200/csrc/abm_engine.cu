@@ -235,7 +235,7 @@ struct ProfScope {
 };
 
 enum { CTR_BIRTH_TOTAL = 12, CTR_PEND_A = 0, CTR_PEND_B = 1, CTR_BIRTHS = 2, CTR_ERR = 3, CTR_RED_LO = 4, CTR_RED_HI = 5, CTR_PLANS = 6, CTR_ROUTE_SLOTS = 7,
-       CTR_EXP_LO = 8, CTR_EXP_HI = 9, CTR_CURSOR = 10, CTR_BIRTH_FLAGS = 11, CTR_PEND_FIRST = 13, CTR_GO = 14, CTR_PACK_DONE = 16, CTR_POOL_LO = 20, CTR_POOL_HI = 21, CTR_NEXT_REQ = 22, CTR_WORDS = 24 };
+       CTR_EXP_LO = 8, CTR_EXP_HI = 9, CTR_CURSOR = 10, CTR_BIRTH_FLAGS = 11, CTR_PEND_FIRST = 13, CTR_GO = 14, CTR_PACK_DONE = 16, CTR_POOL_LO = 20, CTR_POOL_HI = 21, CTR_NEXT_REQ = 22, CTR_BIRTH_DONE = 24 /* 8 words */, CTR_WORDS = 32 };
 
 }  // namespace
 
@@ -245,8 +245,6 @@ struct abm_handle {
   Params params;
   abm_stream_t stream = 0;
 #ifndef ABM_EMU
-  cudaStream_t stream2 = nullptr; /* strips: the halo exchange runs here while the interior cores resolve on `stream` */
-  cudaEvent_t ev_proposed = nullptr, ev_halo = nullptr;
   /* peer-memory transport (abm_p2p.h): this rank's mailbox, the peers' mailboxes mapped through CUDA IPC */
   uint8_t* p2p_mine = nullptr;
   uint8_t* p2p_peer[P2P_MAXP] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -273,11 +271,12 @@ struct abm_handle {
   /* tile path (abm_tile.h): sub-tile runs of the SoA (ping-pong with the SoA), offspring fix-up lists */
   bool tile_mode = false;
   uint64_t birth_bitmap_from = 32768; /* ABM_BIRTH_BITMAP: gathered offspring capacity above which ids are ranked through a bitmap */
-  bool split_waits = false;       /* ABM_SPLIT_WAITS=1: counters and decision bytes as send, send, wait, wait (measured: 2 % slower than one after the other) */
-  bool overlap_halo = false;      /* ABM_OVERLAP=1: halo exchange on a second stream behind the interior rows (measured: no gain) */
   bool optimistic = true;         /* enqueue the commit behind a device-side guard instead of reading counters first (ABM_OPTIMISTIC=0 disables) */
   uint64_t bf_est = 0;            /* expected upper bound of reproducing agents, learnt from the previous tick */
-  int32_t fixed_agent_rounds = 2; /* per-agent rounds enqueued without asking the host (ABM_AGENT_ROUNDS overrides) */
+  int32_t fixed_agent_rounds = 2; /* per-agent rounds enqueued without asking the host (ABM_AGENT_ROUNDS sets the floor) */
+  int32_t min_agent_rounds = 2;   /* the guard failing (somebody still open) adds a round; 256 clean ticks in a row take one off.
+                                   * Every rank sees the same guard, so strips stay in step. */
+  int32_t clean_ticks = 0;
   uint64_t kf_grid = 1024;        /* CTAs of those launches: an upper bound learnt from the previous tick */
   int32_t tile_rounds = 8;
   int32_t tile_margin = HALO;     /* halo cells actually taken into a core's window (ABM_TILE_MARGIN overrides) */ /* in-window rounds of the tile resolve kernel (ABM_TILE_ROUNDS overrides; tests use 1) */
@@ -959,8 +958,7 @@ static int comm_allgather_u32(abm_handle* h, const uint32_t* send, uint32_t* rec
 #ifndef ABM_EMU
 /* ------------------------------------------------------------------------------- peer-memory transport */
 
-/* the counters of this round from every rank, summed into red_buf: two launches (send + publish, wait + sum [+ guard]).
- * The halves are separate calls so that the decision bytes can be sent between them: both waits then overlap. */
+/* the counters of this round from every rank, summed into red_buf: two launches (send + publish, wait + sum [+ guard]) */
 static void p2p_stats_send(abm_handle* h, const uint32_t* d_pending) {
   const uint32_t seq = ++h->p2p_seq[P2P_CH_STATS];
   const int parity = (int)(seq & 1u), P = h->n_ranks;
@@ -996,19 +994,20 @@ static int p2p_allgather_births(abm_handle* h, uint32_t* all, uint64_t cap) {
   const int parity = (int)(seq & 1u), P = h->n_ranks;
   uint32_t* ctr = (uint32_t*)h->counters.p;
   P2PBirthSendCta sc;
-  sc.birth_parent = (const uint32_t*)h->birth_parent.p; sc.birth_count = ctr + CTR_BIRTHS; sc.cap = (uint32_t)cap; sc.seq = seq;
+  sc.birth_parent = (const uint32_t*)h->birth_parent.p; sc.birth_count = ctr + CTR_BIRTHS; sc.cap = (uint32_t)cap; sc.seq = seq; sc.done = ctr + CTR_BIRTH_DONE;
   for (int r = 0; r < P; ++r) {
     sc.dst[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.births_off(h->my_rank, parity));
     sc.flag[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.flag_off(P2P_CH_BIRTHS, h->my_rank, parity));
   }
-  launch_cta(h->stream, sc, (uint64_t)P, 256, 16);
+  ProfScope ps(h->prof, h->stream, "offspring_exchange", cap);
+  launch_cta(h->stream, sc, (uint64_t)P * BIRTH_CTAS, 256, 16);
   P2PBirthRecvCta rv;
   rv.seq = seq; rv.cap = (uint32_t)cap; rv.all = all; rv.err = ctr + CTR_ERR;
   for (int r = 0; r < P; ++r) {
     rv.src[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.births_off(r, parity));
     rv.flag[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.flag_off(P2P_CH_BIRTHS, r, parity));
   }
-  launch_cta(h->stream, rv, (uint64_t)P, 256, 16);
+  launch_cta(h->stream, rv, (uint64_t)P * BIRTH_CTAS, 256, 16);
   return check_launch(h, "peer all-gather");
 }
 #endif
@@ -1114,8 +1113,7 @@ static int strip_exchange_agents(abm_handle* h) {
 }
 
 /* E2: the decision bytes of the same boundary rows (same order), merged into the ghost copies */
-enum { E2_SEND = 1, E2_RECV = 2, E2_BOTH = 3 };
-static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce = nullptr, int n_allreduce = 0, int phase = E2_BOTH) {
+static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce = nullptr, int n_allreduce = 0) {
   int rc;
   const int cur = h->cur, nsx = h->nsx;
   const uint64_t cap = h->bcap;
@@ -1140,7 +1138,7 @@ static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce 
 #ifndef ABM_EMU
   if (h->p2p_on) {
     if (cap > h->p2p_lay.state_bytes) ABM_FAIL(h, ABM_E_CAPACITY, "decision message exceeds the mailbox allocated at abm_p2p_export");
-    const uint32_t seq = (phase & E2_SEND) ? ++h->p2p_seq[P2P_CH_STATE] : h->p2p_seq[P2P_CH_STATE];
+    const uint32_t seq = ++h->p2p_seq[P2P_CH_STATE];
     const int parity = (int)(seq & 1u);
     const int prev = (h->my_rank + h->n_ranks - 1) % h->n_ranks, next = (h->my_rank + 1) % h->n_ranks;
     const P2PLayout& L = h->p2p_lay;
@@ -1158,9 +1156,9 @@ static int strip_exchange_states(abm_handle* h, unsigned long long* d_allreduce 
   }
 #endif
   { ProfScope ps(h->prof, h->stream, "decision_exchange", 2 * cap);
-    if (phase & E2_SEND) launch_cta(h->stream, pk, 2 * (uint64_t)chunks, TILE_THREADS, 16);
+    launch_cta(h->stream, pk, 2 * (uint64_t)chunks, TILE_THREADS, 16);
     if (!direct && (rc = comm_sendrecv(h, h->sx_st[0].p, cap, h->sx_st[1].p, cap, h->rx_st[0].p, cap, h->rx_st[1].p, cap, d_allreduce, n_allreduce))) return rc;
-    if (phase & E2_RECV) launch_cta(h->stream, mg, 2 * MERGE_CTAS, TILE_THREADS, 16); }
+    launch_cta(h->stream, mg, 2 * MERGE_CTAS, TILE_THREADS, 16); }
   return check_launch(h, "strip decision exchange");
 }
 
@@ -1187,17 +1185,10 @@ static int strip_stats_enqueue(abm_handle* h, const uint32_t* d_pending, bool wi
   const int nv = 1 + 3 * h->n_ranks;
   unsigned long long* d = (unsigned long long*)h->red_buf.p;
 #ifndef ABM_EMU
-  if (h->p2p_on) { /* counters and decision bytes go out first, then both are awaited (the commit guard is folded into the
-                    * kernel that sums the counters) */
-    if (!h->split_waits) {
-      { ProfScope ps(h->prof, h->stream, "counters_exchange", (uint64_t)nv); p2p_stats_send(h, d_pending); rc = p2p_stats_recv(h, go, guard_cap); }
-      if (rc) return rc;
-      return with_state_exchange ? strip_exchange_states(h) : 0;
-    }
-    p2p_stats_send(h, d_pending);
-    if (with_state_exchange && (rc = strip_exchange_states(h, nullptr, 0, E2_SEND))) return rc;
-    if ((rc = p2p_stats_recv(h, go, guard_cap))) return rc;
-    return with_state_exchange ? strip_exchange_states(h, nullptr, 0, E2_RECV) : 0;
+  if (h->p2p_on) { /* the commit guard is folded into the kernel that sums the counters */
+    { ProfScope ps(h->prof, h->stream, "counters_exchange", (uint64_t)nv); p2p_stats_send(h, d_pending); rc = p2p_stats_recv(h, go, guard_cap); }
+    if (rc) return rc;
+    return with_state_exchange ? strip_exchange_states(h) : 0;
   }
 #endif
   strip_stats_kernel(h, d_pending);
@@ -1221,9 +1212,8 @@ static int strip_stats(abm_handle* h, const uint32_t* d_pending, std::vector<uin
 #ifndef ABM_EMU
   if (h->p2p_on) {
     p2p_stats_send(h, d_pending);
-    if (with_state_exchange && (rc = strip_exchange_states(h, nullptr, 0, E2_SEND))) return rc;
     if ((rc = p2p_stats_recv(h, nullptr, 0))) return rc;
-    if (with_state_exchange && (rc = strip_exchange_states(h, nullptr, 0, E2_RECV))) return rc;
+    if (with_state_exchange && (rc = strip_exchange_states(h))) return rc;
     ABM_CK(h, copy_d2h(out.data(), d, (size_t)nv * 8, h->stream));
     return 0;
   }
@@ -1365,28 +1355,8 @@ static int tick_tile(abm_handle* h) {
     { ProfScope ps(h->prof, h->stream, "resolve_tiles", grid * 256, 1); launch_cta(h->stream, rw, grid, TILE_THREADS, ResolveWindow::smem_bytes_core()); }
     return check_launch(h, "tile resolve");
   };
-  bool overlapped = false;
-#ifndef ABM_EMU
-  if (h->strip && (h->nccl_comm || h->p2p_on) && h->stream2 && h->overlap_halo && needs_resolve && core_rows >= 3 && n > 0) {
-    /* the halo exchange travels on a second stream while the core rows that cannot see a ghost row are resolved */
-    ABM_CK(h, cudaEventRecord(h->ev_proposed, h->stream));
-    ABM_CK(h, cudaStreamWaitEvent(h->stream2, h->ev_proposed, 0));
-    cudaStream_t main_stream = h->stream;
-    h->stream = h->stream2;
-    rc = strip_exchange_agents(h);
-    if (!rc) rc = launch_tiles(0, 2, core_rows - 1); /* the first and the last core row, behind the exchange on its stream */
-    h->stream = main_stream;
-    if (rc) return rc;
-    ABM_CK(h, cudaEventRecord(h->ev_halo, h->stream2));
-    if ((rc = launch_tiles(1, core_rows - 2))) return rc; /* meanwhile: the rows that cannot see a ghost row */
-    ABM_CK(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
-    overlapped = true;
-  }
-#endif
-  if (!overlapped) {
-    if (h->strip && (rc = strip_exchange_agents(h))) return rc; /* neighbours' boundary rows become ghost rows behind the own agents */
-    if (n + h->n_ghost > 0 && needs_resolve && (rc = launch_tiles(0, core_rows))) return rc;
-  }
+  if (h->strip && (rc = strip_exchange_agents(h))) return rc; /* neighbours' boundary rows become ghost rows behind the own agents */
+  if (n + h->n_ghost > 0 && needs_resolve && (rc = launch_tiles(0, core_rows))) return rc;
   /* figures the host needs before it can go on: open agents, reproducing agents (sizes of the output SoA); in strip
    * mode from every rank, through one all-reduce of device-resident counters */
   uint64_t birth_flags = 0, birth_cap = 0, global_cnt = 0, strip_fmax = 0;
@@ -1429,8 +1399,9 @@ static int tick_tile(abm_handle* h) {
     ABM_CK(h, copy_d2d(ctr + CTR_PEND_FIRST, ctr + CTR_PEND_A, sizeof(uint32_t), h->stream));
     for (int r = 0; r < h->fixed_agent_rounds; ++r) {
       /* strips: the owners' decisions reach the ghost copies before the first blind round and once more with the counters
-       * below; an agent that waits for a ghost across the later blind rounds simply stays open and the guard sees it */
-      if (h->strip && r == 0 && (rc = strip_exchange_states(h))) return rc;
+       * below (and before the last of three or more rounds); an agent that waits for a ghost in between simply stays
+       * open and the guard sees it */
+      if (h->strip && (r == 0 || (r >= 2 && r == h->fixed_agent_rounds - 1)) && (rc = strip_exchange_states(h))) return rc;
       if ((rc = launch_agents(std::max<uint64_t>(h->kf_grid, 1), ctr + (in ? CTR_PEND_A : CTR_PEND_B)))) return rc;
       in ^= 1;
       h->rounds += 1;
@@ -1525,6 +1496,7 @@ static int tick_tile(abm_handle* h) {
     if ((rc = read_counters(h))) return rc;
     if ((rc = device_error_to_code(h))) return rc;
     if (h->h_counters[CTR_GO]) {
+      if (needs_resolve && ++h->clean_ticks >= 256) { h->clean_ticks = 0; if (h->fixed_agent_rounds > h->min_agent_rounds) --h->fixed_agent_rounds; }
       if (!h->strip) return finish_tick(h->h_counters[CTR_CURSOR], h->h_counters[CTR_BIRTHS]);
       uint64_t fmax = 0, rmax = 0;
       for (int r = 0; r < P; ++r) { fmax = std::max(fmax, stats[1 + P + r]); rmax = std::max(rmax, stats[1 + 2 * P + r]); }
@@ -1535,6 +1507,7 @@ static int tick_tile(abm_handle* h) {
       return 0;
     }
     /* not ready (agents still open, or more births than expected): nothing was touched; go on carefully */
+    if (needs_resolve) { h->clean_ticks = 0; if (h->fixed_agent_rounds < 6 && h->fixed_agent_rounds >= 1) ++h->fixed_agent_rounds; }
   }
   if ((rc = take_stats(ctr + (in ? CTR_PEND_B : CTR_PEND_A)))) return rc;
   if (h->strip && (rc = read_counters(h))) return rc;
@@ -1636,11 +1609,8 @@ void ABM_API(destroy)(abm_handle* h) {
 #ifndef ABM_EMU
   cudaSetDevice(h->device);
   if (h->stream) { cudaStreamSynchronize(h->stream); }
-  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   for (int r = 0; r < P2P_MAXP; ++r) if (h->p2p_peer[r] && h->p2p_peer[r] != h->p2p_mine) cudaIpcCloseMemHandle(h->p2p_peer[r]);
   if (h->p2p_mine) cudaFree(h->p2p_mine);
-  if (h->ev_proposed) cudaEventDestroy(h->ev_proposed);
-  if (h->ev_halo) cudaEventDestroy(h->ev_halo);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
   if (h->stream) { cudaStreamDestroy(h->stream); }
   if (h->h_counters) cudaFreeHost(h->h_counters);
@@ -1718,12 +1688,10 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
                              cfg->nx >= 2 * CORE && cfg->ny >= 2 * CORE);
   h->nsx = g.nx / SUB; h->nsy = g.ny / SUB;
   if (const char* mg = getenv("ABM_MIGRANTS")) h->use_migrants = atoi(mg) != 0;
-  if (const char* ov = getenv("ABM_OVERLAP")) h->overlap_halo = atoi(ov) != 0;
   if (const char* ag = getenv("ABM_ASTAR_GB")) { const int q = atoi(ag); if (q >= 1 && q <= 160) h->astar_budget = (uint64_t)q << 30; }
-  if (const char* sw = getenv("ABM_SPLIT_WAITS")) h->split_waits = atoi(sw) != 0;
   if (const char* bb = getenv("ABM_BIRTH_BITMAP")) h->birth_bitmap_from = (uint64_t)std::max(atoll(bb), 0ll);
   if (const char* op = getenv("ABM_OPTIMISTIC")) h->optimistic = atoi(op) != 0;
-  if (const char* ar = getenv("ABM_AGENT_ROUNDS")) { const int q = atoi(ar); if (q >= 0 && q <= 16) h->fixed_agent_rounds = q; }
+  if (const char* ar = getenv("ABM_AGENT_ROUNDS")) { const int q = atoi(ar); if (q >= 0 && q <= 16) h->fixed_agent_rounds = h->min_agent_rounds = q; }
   if (const char* tm = getenv("ABM_TILE_MARGIN")) { const int q = atoi(tm); if (q >= 2 && q <= HALO) h->tile_margin = q; }
   if (const char* tr = getenv("ABM_TILE_ROUNDS")) { const int q = atoi(tr); if (q >= 0 && q <= 64) h->tile_rounds = q; }
   rc = 0;
@@ -2215,11 +2183,6 @@ int ABM_API(comm_init_nccl)(abm_handle* h, const void* unique_id128) {
   ncclComm_t c;
   ABM_NCCL(h, g_nccl.CommInitRank(&c, h->n_ranks, id, h->my_rank));
   h->nccl_comm = (void*)c;
-  if (!h->stream2) {
-    ABM_CK(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-    ABM_CK(h, cudaEventCreateWithFlags(&h->ev_proposed, cudaEventDisableTiming));
-    ABM_CK(h, cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
-  }
   return ABM_OK;
 #else
   ABM_FAIL(h, ABM_E_STATE, "NCCL is not part of the emulation build");
@@ -2266,11 +2229,6 @@ int ABM_API(p2p_connect)(abm_handle* h, const void* handles, int32_t n) {
     void* p = nullptr;
     ABM_CK(h, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
     h->p2p_peer[r] = (uint8_t*)p;
-  }
-  if (!h->stream2) {
-    ABM_CK(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-    ABM_CK(h, cudaEventCreateWithFlags(&h->ev_proposed, cudaEventDisableTiming));
-    ABM_CK(h, cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
   }
   h->p2p_on = true;
   return ABM_OK;

@@ -87,28 +87,38 @@ struct P2PStatsRecvCta {
   }
 };
 
-/* offspring all-gather in two launches of n_ranks CTAs: CTA r stores [count, parent ids ...] of this rank into rank r's
- * mailbox and publishes; then CTA r waits for rank r's message and lays it out contiguously for the rank kernel */
+/* offspring all-gather in two launches of n_ranks x BIRTH_CTAS CTAs: the CTAs (r, *) store [count, parent ids ...] of
+ * this rank into rank r's mailbox (coalesced 128-byte rows over NVLink) and the one that finishes last publishes; then
+ * the CTAs (r, *) wait for rank r's message and lay it out contiguously for the rank kernel */
+enum { BIRTH_CTAS = 32 };
 struct P2PBirthSendCta {
   const uint32_t* birth_parent; const uint32_t* birth_count; uint32_t cap;
   uint32_t* dst[P2P_MAXP]; uint32_t* flag[P2P_MAXP]; uint32_t seq;
-  ABM_HD void operator()(uint32_t r, uint32_t*) const {
+  uint32_t* done; /* one counter per destination, left at zero */
+  ABM_HD void operator()(uint32_t cta, uint32_t*) const {
+    const uint32_t r = cta / BIRTH_CTAS, part = cta % BIRTH_CTAS;
     const uint32_t n = *birth_count < cap ? *birth_count : cap;
     ABM_CTA_FOR(t, 256) {
-      for (uint32_t w = (uint32_t)t; w < 1 + n; w += 256) dst[r][w] = w == 0 ? *birth_count : birth_parent[w - 1];
+      for (uint32_t w = part * 256u + (uint32_t)t; w < 1 + n; w += 256u * BIRTH_CTAS) dst[r][w] = w == 0 ? *birth_count : birth_parent[w - 1];
     }
     ABM_CTA_SYNC();
-    ABM_CTA_FOR(t, 256) { if (t == 0) flag_publish(flag[r], seq); }
+    ABM_CTA_FOR(t, 256) {
+      if (t == 0) {
+        flag_fence();
+        if (atomic_add(&done[r], 1u) == BIRTH_CTAS - 1) { done[r] = 0; flag_publish(flag[r], seq); }
+      }
+    }
   }
 };
 struct P2PBirthRecvCta {
   const uint32_t* src[P2P_MAXP]; const uint32_t* flag[P2P_MAXP]; uint32_t seq, cap; uint32_t* all; uint32_t* err;
-  ABM_HD void operator()(uint32_t r, uint32_t*) const {
+  ABM_HD void operator()(uint32_t cta, uint32_t*) const {
+    const uint32_t r = cta / BIRTH_CTAS, part = cta % BIRTH_CTAS;
     ABM_CTA_FOR(t, 256) { if (t == 0) flag_wait(flag[r], seq, err, ERR_P2P_TIMEOUT); }
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, 256) {
       const uint32_t n = src[r][0] < cap ? src[r][0] : cap;
-      for (uint32_t w = (uint32_t)t; w < 1 + n; w += 256) all[(size_t)r * (1 + cap) + w] = src[r][w];
+      for (uint32_t w = part * 256u + (uint32_t)t; w < 1 + n; w += 256u * BIRTH_CTAS) all[(size_t)r * (1 + cap) + w] = src[r][w];
     }
   }
 };

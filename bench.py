@@ -242,6 +242,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed ticks")
+    ap.add_argument("--no-kernel-events", action="store_true", help="do not bracket every kernel with CUDA events (no per-kernel table, no roofline): shows what the events cost")
     args = ap.parse_args()
     if args.size <= 0:
         args.size = {"C3": 8192, "C4": 2048}.get(args.workload, 4096)
@@ -303,7 +304,7 @@ def main():
             (strips.init_p2p if args.transport == "p2p" else strips.init_nccl)(eng)
     else:
         eng = load(lib, cfg, w, device=local)
-    eng.set_profiling(True)
+    eng.set_profiling(not args.no_kernel_events)
     G = nx * size
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
