@@ -178,8 +178,10 @@ struct Prof {
   bool on = false;
   std::vector<KStat> stats;
 #ifndef ABM_EMU
-  struct Rec { int idx; cudaEvent_t a, b; };
+  struct Rec { int idx; cudaEvent_t a, b; bool own_a; };
   std::vector<Rec> recs;
+  unsigned long long launches_at_end = 0; /* a scope that starts with no launch since the previous one ended shares its event */
+  bool last_ended = false;
   std::vector<cudaEvent_t> pool;
   cudaEvent_t get() { if (pool.empty()) { cudaEvent_t e; cudaEventCreate(&e); return e; } cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
 #endif
@@ -194,8 +196,10 @@ struct Prof {
 #ifndef ABM_EMU
     if (!on) return;
     if (recs.size() >= 8192) collect();
-    Rec r; r.idx = i; r.a = get(); r.b = get();
-    cudaEventRecord(r.a, s);
+    Rec r; r.idx = i; r.b = get();
+    if (!recs.empty() && last_ended && launches_at_end == g_launches) { r.a = recs.back().b; r.own_a = false; }
+    else { r.a = get(); r.own_a = true; cudaEventRecord(r.a, s); }
+    last_ended = false;
     recs.push_back(r);
 #else
     (void)s;
@@ -203,7 +207,7 @@ struct Prof {
   }
   void end(abm_stream_t s) {
 #ifndef ABM_EMU
-    if (on && !recs.empty()) cudaEventRecord(recs.back().b, s);
+    if (on && !recs.empty()) { cudaEventRecord(recs.back().b, s); launches_at_end = g_launches; last_ended = true; }
 #else
     (void)s;
 #endif
@@ -215,9 +219,11 @@ struct Prof {
       cudaEventSynchronize(recs[i].b);
       cudaEventElapsedTime(&f, recs[i].a, recs[i].b);
       stats[recs[i].idx].ms += f;
-      pool.push_back(recs[i].a); pool.push_back(recs[i].b);
+      if (recs[i].own_a) pool.push_back(recs[i].a);
+      pool.push_back(recs[i].b);
     }
     recs.clear();
+    last_ended = false;
 #endif
   }
   void destroy() {
