@@ -365,3 +365,42 @@ def test_emulated_tile_path_with_migrant_lists(emu, oracle, name, monkeypatch):
         b.step(1)
         assert "migrant_scan" in {k for k, v in b.kernel_stats().items() if v["launches"]}
         assert_same_state(b.snapshot(), a.snapshot(), f"{name} tick {t}")
+
+
+def _edge_world(nx, ny, n, energy):
+    rng = np.random.default_rng(3)
+    fg = rng.integers(0, 2, (ny, nx)).astype(np.uint8)
+    cd = np.where(fg == 1, 5, rng.integers(0, 5, (ny, nx))).astype(np.int64)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    return dict(fully_grown=fg, countdown=cd, ids=ids, x=rng.integers(1, nx + 1, n).astype(np.int64),
+                y=rng.integers(1, ny + 1, n).astype(np.int64), energy=np.full(n, energy, np.float64))
+
+
+def _edge_run(lib_a, lib_b, nx, ny, n, energy, wt, ticks=6, **kw):
+    cfgkw = dict(nx=nx, ny=ny, periodic=1, walk_type=wt, eat=0, reproduce=1, regrowth_time=5, reproduction_prob=0.3, seed=77, **kw)
+    w = _edge_world(nx, ny, n, energy)
+    a, b = load_case(lib_a, cfgkw, w), load_case(lib_b, cfgkw, w)
+    for t in range(ticks):
+        a.step(1)
+        b.step(1)
+        assert_same_state(b.snapshot(), a.snapshot(), f"{nx}x{ny} n={n} tick {t}")
+    return b
+
+
+@pytest.mark.parametrize("nx,ny,wt", [(64, 64, 0), (64, 96, 2), (40, 30, 0), (1, 1, 0), (64, 64, 4)])
+def test_emulated_empty_world_and_extinction(emu, oracle, nx, ny, wt):
+    """No sheep at all (the grass still regrows), and a herd that starves on its first step (energy 0, no eating:
+    reduce_energy! kills at energy < 0 after the move, reference src/agent_actions.jl:85-92) and leaves an empty world."""
+    b = _edge_run(oracle, emu, nx, ny, 0, 0.0, wt)
+    assert b.count_agents() == 0
+    b = _edge_run(oracle, emu, nx, ny, min(50, 3 * nx * ny), 0.5, wt)
+    assert b.count_agents() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nx,ny,wt", [(64, 64, 0), (64, 96, 2), (40, 30, 0), (1, 1, 0)])
+def test_gpu_empty_world_and_extinction(libabm, oracle, nx, ny, wt):
+    b = _edge_run(oracle, libabm, nx, ny, 0, 0.0, wt)
+    assert b.count_agents() == 0
+    b = _edge_run(oracle, libabm, nx, ny, min(50, 3 * nx * ny), 0.5, wt)
+    assert b.count_agents() == 0
