@@ -284,8 +284,8 @@ struct abm_handle {
                                    * Every rank sees the same guard, so strips stay in step. */
   int32_t clean_ticks = 0;
   uint64_t kf_grid = 1024;        /* CTAs of those launches: an upper bound learnt from the previous tick */
-  int32_t tile_rounds = 8;
-  int32_t tile_margin = HALO;     /* halo cells actually taken into a core's window (ABM_TILE_MARGIN overrides) */ /* in-window rounds of the tile resolve kernel (ABM_TILE_ROUNDS overrides; tests use 1) */
+  int32_t tile_rounds = 8;        /* in-window rounds of the tile resolve kernel (ABM_TILE_ROUNDS overrides; tests use 1) */
+  int32_t tile_margin = HALO;     /* halo cells actually taken into a core's window (ABM_TILE_MARGIN overrides) */
   int32_t nsx = 0, nsy = 0;
   DevBuf sub_off[2], sub_cnt[2], birth_pos, birth_parent, ingest_sub, mig_cnt, mig_a, mig_lc;
   bool use_migrants = false; /* ABM_MIGRANTS=1: border crossers are listed per destination core and the commit reads only its
