@@ -64,7 +64,7 @@ def mod1(a, n):
 class Model:
     def __init__(self, nx, ny, periodic, walk_type, seed=321, eat=True, reproduce=True, walkmap_regrowth=False,
                  regrowth_time=30, visual_distance=5, counter=50, prob_random_walk=0.9, delta_energy=4.0,
-                 movement_cost=1.0, reproduction_prob=0.001, attractor=None, ifempty=True):
+                 movement_cost=1.0, reproduction_prob=0.001, attractor=None, ifempty=True, astar_metric=0, astar_penalty=0):
         self.nx, self.ny, self.periodic, self.walk_type = nx, ny, bool(periodic), walk_type
         self.eat, self.reproduce, self.walkmap_regrowth = eat, reproduce, walkmap_regrowth
         self.regrowth_time, self.r, self.counter = regrowth_time, visual_distance, counter
@@ -78,14 +78,18 @@ class Model:
         self.countdown = {}
         self.walk = {}
         self.behav, self.behav_counter, self.maxid, self.tick = 0, 0, 0, 0
+        self.metric, self.penalty = astar_metric, bool(astar_penalty)
+        self.elev = {}
+        self.paths = {}    # pathfinder.agent_paths :: Dict{Int, Path}
 
     # ---- set-up
-    def set_grid(self, fg, cd, wm=None):
+    def set_grid(self, fg, cd, wm=None, el=None):
         for y in range(1, self.ny + 1):
             for x in range(1, self.nx + 1):
                 self.grown[(x, y)] = bool(fg[y - 1][x - 1])
                 self.countdown[(x, y)] = int(cd[y - 1][x - 1])
                 self.walk[(x, y)] = True if wm is None else bool(wm[y - 1][x - 1])
+                self.elev[(x, y)] = 0 if el is None else int(el[y - 1][x - 1])
                 self.cells[(x, y)] = []
 
     def set_agents(self, ids, xs, ys, es):
@@ -185,14 +189,87 @@ class Model:
         ok = [p for p in self.nearby_positions((a[0], a[1])) if self.walk[p]]
         self.move(aid, ok[self.rng.range1(len(ok)) - 1])
 
+    # ---- Agents.Pathfinding 5.14 (astar.jl / metrics.jl / pathfinding_utils.jl), written from the Julia semantics:
+    # a heap of (f, pos) TUPLES, lazy insertion, strict improvement, stale entries re-expanded exactly as upstream does
+    def delta_cost(self, a, b):
+        dx, dy = abs(a[0] - b[0]), abs(a[1] - b[1])
+        if self.periodic:
+            dx, dy = min(dx, self.nx - dx), min(dy, self.ny - dy)
+        if self.metric == 1:                       # MaxDistance
+            c = max(dx, dy)
+        else:                                      # DirectDistance, direction_costs = [10, 14]
+            lo, hi = sorted((dx, dy))
+            c = 14 * lo + 10 * (hi - lo)
+        if self.penalty:                           # PenaltyMap(pmap, base): base + |pmap[from] - pmap[to]|
+            c += abs(self.elev[a] - self.elev[b])
+        return c
+
+    def find_path(self, src, dst):
+        import heapq
+        INF = 2 ** 62
+        g = {src: 0}
+        parent = {}
+        closed = set()
+        heap = [(self.delta_cost(src, dst), src)]  # f = round(Int, g + (1 + admissibility) * h), admissibility = 0
+        self.expansions = 0
+        while heap:
+            _, cur = heapq.heappop(heap)
+            if cur == dst:
+                break
+            closed.add(cur)
+            self.expansions += 1
+            for d in OFF8:                         # Moore offsets in product order, x fastest
+                x, y = cur[0] + d[0], cur[1] + d[1]
+                if self.periodic:
+                    nb = (mod1(x, self.nx), mod1(y, self.ny))
+                elif 1 <= x <= self.nx and 1 <= y <= self.ny:
+                    nb = (x, y)
+                else:
+                    continue
+                if not self.walk[nb] or nb in closed:
+                    continue
+                ng = g[cur] + self.delta_cost(cur, nb)
+                if ng < g.get(nb, INF):
+                    parent[nb] = cur
+                    g[nb] = ng
+                    heapq.heappush(heap, (ng + self.delta_cost(nb, dst), nb))
+        path, cur = [], dst
+        while cur in parent:
+            path.insert(0, cur)
+            cur = parent[cur]
+        if cur != src:
+            return None, -1
+        return path, g[dst]
+
+    def plan_route(self, aid, dest):
+        a = self.agents[aid]
+        path, _ = self.find_path((a[0], a[1]), dest)
+        if path is None:                           # isnothing(path) && return: an older route stays
+            return
+        self.paths[aid] = path
+
+    def move_along_route(self, aid):
+        path = self.paths.get(aid)
+        if not path:
+            return
+        self.move(aid, path.pop(0))                # unconditional move_agent!, no ifempty
+
+    def random_walkable(self):
+        while True:                                # random_position(model) until the walkmap accepts it
+            pos = (self.rng.range1(self.nx), self.rng.range1(self.ny))
+            if self.walk[pos]:
+                return pos
+
     def alternated(self, aid):
         if self.behav_counter == self.counter:
             self.behav = self.rng.range1(3)
             if self.behav == 2:
-                raise NotImplementedError("route planning is outside pyref")
+                self.plan_route(aid, self.random_walkable())
         if 0 < self.behav_counter <= self.counter:
             if self.behav == 1:
                 self.randomwalk(aid)
+            elif self.behav == 2:
+                self.move_along_route(aid)
             elif self.behav == 3:
                 a = self.agents[aid]
                 self.move(aid, (a[0], a[1]))

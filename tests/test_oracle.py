@@ -289,6 +289,57 @@ def test_oracle_equals_pyref(oracle, wt, per, terr):
     assert e.count_agents() > 0
 
 
+@pytest.mark.parametrize("per,metric,penalty,counter", [(1, 0, 0, 7), (1, 1, 1, 5), (0, 1, 1, 4), (0, 0, 1, 3)])
+def test_oracle_equals_pyref_alternated_walk(oracle, per, metric, penalty, counter):
+    """ALTERNATED_WALK with route planning (v0.4 / v0.6): the model-global behaviour counter, sample(1:3), the
+    random_walkable rejection loop, plan_route! (A*) and move_along_route! — the second restatement (tests/pyref.py,
+    Python heapq over (f, (x, y)) tuples, dict-based cost map, stale heap entries re-expanded as upstream does) must
+    give the oracle's trajectory."""
+    kw = dict(reproduction_prob=0.03, regrowth_time=4, delta_energy=3.0, counter=counter, astar_metric=metric, astar_penalty=penalty)
+    cfgkw, w = make_case(17, 13, 40, 3, per, terrain=True, seed=9, **kw)
+    e = load_case(oracle, cfgkw, w)
+    e.set_global_state(0, 0, counter)  # scripts/v0.4.jl:97
+    m = pyref.Model(17, 13, per, 3, seed=9, reproduction_prob=0.03, regrowth_time=4, delta_energy=3.0, counter=counter,
+                    astar_metric=metric, astar_penalty=penalty)
+    m.set_grid(w["fully_grown"], w["countdown"], w["walkmap"], w["elevation"])
+    m.set_agents(w["ids"], w["x"], w["y"], w["energy"])
+    m.behav, m.behav_counter = 0, counter
+    planned = 0
+    for t in range(30):
+        e.step(1)
+        m.step(1)
+        assert_same_state(e.snapshot(), m.snapshot(), f"alternated periodic {per} metric {metric} penalty {penalty} tick {t}")
+        planned = max(planned, len(m.paths))
+    assert e.count_agents() > 0 and planned > 0
+
+
+@pytest.mark.parametrize("per,metric,penalty", [(1, 1, 1), (1, 0, 0), (0, 1, 1), (0, 0, 1), (0, 1, 0)])
+def test_oracle_paths_equal_pyref_paths(oracle, per, metric, penalty):
+    """abm_plan_routes against pyref.find_path: every cell of every path (tie-breaking included) and the cost."""
+    nx, ny, n = 31, 23, 60
+    cfgkw, w = make_case(nx, ny, n, 3, per, terrain=True, seed=21, astar_metric=metric, astar_penalty=penalty, counter=9)
+    e = load_case(oracle, cfgkw, w)
+    m = pyref.Model(nx, ny, per, 3, seed=21, astar_metric=metric, astar_penalty=penalty)
+    m.set_grid(w["fully_grown"], w["countdown"], w["walkmap"], w["elevation"])
+    rng = np.random.default_rng(4)
+    ok = np.argwhere(w["walkmap"] == 1)
+    goals = ok[rng.integers(0, len(ok), n)]
+    gx, gy = goals[:, 1] + 1, goals[:, 0] + 1
+    e.plan_routes(w["ids"], gx, gy)
+    off, px, py, cost = e.get_paths(w["ids"])
+    found = 0
+    for i in range(n):
+        path, c = m.find_path((int(w["x"][i]), int(w["y"][i])), (int(gx[i]), int(gy[i])))
+        got = list(zip(px[off[i]:off[i + 1]].tolist(), py[off[i]:off[i + 1]].tolist()))
+        if path is None:
+            assert got == [] and cost[i] == -1
+            continue
+        found += 1
+        assert got == path, f"agent {i}: path differs"
+        assert cost[i] == c
+    assert found > 10
+
+
 # ------------------------------------------------------------------ A*
 
 
