@@ -80,7 +80,7 @@ def _run_ring(world, name, ticks, tmp_path, use_gpu=False, transport="nccl"):
     return [np.load(os.path.join(str(tmp_path), f"snap_{r}.npy"), allow_pickle=True) for r in range(world)]
 
 
-@pytest.mark.parametrize("world,name", [(2, "rw"), (2, "gregarious"), (2, "rw_clamped"), (3, "attractor"), (2, "walkmap"), (3, "gregarious_r7")])
+@pytest.mark.parametrize("world,name", [(2, "rw"), (2, "gregarious"), (2, "rw_clamped"), (3, "attractor"), (2, "walkmap"), (3, "gregarious_r7"), (4, "walkmap")])
 def test_ring_of_processes_over_gloo(oracle, tmp_path, world, name):
     build.build_emu()
     ticks = 8
@@ -170,3 +170,20 @@ def test_two_strips_offspring_bitmap_on_the_gpu(libabm, oracle, tmp_path, monkey
     for t in range(ticks):
         a.step(1)
         assert_same_state(strips.merge_snapshots([per_rank[r][t] for r in range(2)]), a.snapshot(), f"walkmap tick {t}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,name,transport", [(4, "walkmap", "p2p"), (3, "gregarious_r7", "p2p"), (3, "attractor", "nccl")])
+def test_rings_of_three_and_four_gpus(libabm, oracle, tmp_path, world, name, transport):
+    """With three or more strips the two neighbours of a rank are different processes (at two they are the same one):
+    the mailbox slots, the all-to-all counters and the offspring all-gather with more than one peer, against the oracle."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ticks = 6
+    per_rank = _run_ring(world, name, ticks, tmp_path, use_gpu=True, transport=transport)
+    cfgkw, w = _case(name)
+    a = load_case(oracle, cfgkw, w)
+    for t in range(ticks):
+        a.step(1)
+        assert_same_state(strips.merge_snapshots([per_rank[r][t] for r in range(world)]), a.snapshot(), f"{name} world {world} tick {t}")
