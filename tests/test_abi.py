@@ -67,3 +67,35 @@ def test_package_never_loads_test_libraries():
             for token in ("LIBORACLE", "LIBEMU", "build_oracle", "build_emu", "oracle_", "emu_"):
                 code = "\n".join(l for l in s.split("\n") if "``" not in l)  # docstring bullet lines name the prefixes
                 assert token not in code, (fn, token)
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "c_host")
+    libdir = os.path.dirname(build.build_libabm())
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_host.c"), "-L" + libdir, "-labm", "-Wl,-rpath," + libdir, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_the_c_example_links(tmp_path):
+    """include/abm.h compiles as strict C99 and examples/c_host.c links against libabm.so; without a GPU the program
+    stops at abm_create with ABM_E_CUDA (no CPU path)."""
+    import subprocess
+    import torch
+    exe = _build_c_example(tmp_path)
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 1 and "-> -2" in r.stderr and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_example_runs_on_the_gpu(tmp_path):
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert len(lines) == 11 and lines[0].split()[:4] == ["tick", "0", "sheep", "100"] and lines[-1].startswith("tick 100")
