@@ -115,7 +115,13 @@ typedef struct abm_handle abm_handle;
 void abm_config_default(abm_config* cfg);
 
 /* replaces: AgentBasedModel(Sheep, GridSpace(dims; periodic, metric=:chebyshev); properties, rng, scheduler)
- * scripts/v0.1.jl:49-64 */
+ * scripts/v0.1.jl:49-64.
+ * ABM_E_BADARG (text through abm_last_error(NULL)) for what the engine does not take: regrowth_time outside 0..126 (the
+ * packed grass byte); RANDOM_WALK_GREGARIOUS on a non-periodic space (the reference itself throws there,
+ * src/agent_actions.jl:334), with visual_distance outside 1..7, or on a grid narrower than 2*visual_distance + 3 (the
+ * neighbour box would wrap onto itself); attractor coordinates that are not multiples of 1/2; counter < 1; a grid whose
+ * 32x32-tiled cell count does not fit 32 bits; strip mode with rows or nx that are not multiples of 32, with nx < 64, or
+ * with ALTERNATED_WALK. */
 int abm_create(const abm_config* cfg, abm_handle** out);
 void abm_destroy(abm_handle* h);
 
