@@ -23,8 +23,22 @@ CASES = {
 }
 
 
+def _fuzz_case(seed):
+    """A random strip-able configuration, reproducible from the seed (the spawned workers rebuild it from the name)."""
+    rng = np.random.default_rng(seed)
+    nx, ny = [(64, 96), (96, 96), (64, 192), (128, 96)][rng.integers(4)]
+    wt = int(rng.choice([0, 1, 2, 4]))
+    per = 1 if wt == 2 else int(rng.integers(0, 2))
+    n = max(1, int(nx * ny * [0.05, 0.3, 0.8, 1.5][rng.integers(4)]))
+    kw = dict(reproduction_prob=float(rng.choice([0.0, 0.05, 0.3])), regrowth_time=int(rng.integers(1, 6)), delta_energy=float(rng.integers(1, 5)),
+              prob_random_walk=float(rng.choice([0.0, 0.3, 0.9])), visual_distance=int(rng.integers(1, 8)))
+    if wt == 4:
+        kw["walkmap_regrowth"] = int(rng.integers(0, 2))
+    return dict(nx=nx, ny=ny, n=n, wt=wt, per=per, terrain=wt == 4, kw=kw)
+
+
 def _case(name):
-    c = CASES[name]
+    c = _fuzz_case(int(name[4:])) if name.startswith("fuzz") else CASES[name]
     return make_case(c["nx"], c["ny"], c["n"], c["wt"], c["per"], terrain=c.get("terrain", False), seed=31, **c["kw"])
 
 
@@ -80,7 +94,7 @@ def _run_ring(world, name, ticks, tmp_path, use_gpu=False, transport="nccl"):
     return [np.load(os.path.join(str(tmp_path), f"snap_{r}.npy"), allow_pickle=True) for r in range(world)]
 
 
-@pytest.mark.parametrize("world,name", [(2, "rw"), (2, "gregarious"), (2, "rw_clamped"), (3, "attractor"), (2, "walkmap"), (3, "gregarious_r7"), (4, "walkmap")])
+@pytest.mark.parametrize("world,name", [(2, "rw"), (2, "gregarious"), (2, "rw_clamped"), (3, "attractor"), (2, "walkmap"), (3, "gregarious_r7"), (4, "walkmap"), (3, "fuzz11"), (2, "fuzz12")])
 def test_ring_of_processes_over_gloo(oracle, tmp_path, world, name):
     build.build_emu()
     ticks = 8
