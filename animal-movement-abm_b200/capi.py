@@ -84,6 +84,7 @@ SIGNATURES = {
     "destroy": (None, [_P]),
     "set_grid": (C.c_int, [_P, _U8P, _I64P, _U8P, _I64P]),
     "set_agents": (C.c_int, [_P, C.c_int64, _I64P, _I64P, _I64P, _F64P, C.c_int64]),
+    "init_random": (C.c_int, [_P, C.c_int64, C.c_uint64]),
     "set_global_state": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64]),
     "get_global_state": (C.c_int, [_P, _I64P, _I64P, _I64P, _I64P]),
     "set_weight_lut": (C.c_int, [_P, _F64P, C.c_int32]),
@@ -188,6 +189,10 @@ class Engine:
         if next_id is None:
             next_id = int(ids.max()) + 1 if n else 1
         self._ck(self.lib.fn["set_agents"](self.h, n, _ptr(ids, _I64P), _ptr(x, _I64P), _ptr(y, _I64P), _ptr(e, _F64P), int(next_id)))
+
+    def init_random(self, n_sheep, init_seed):
+        """The random part of `initialize_model`, built by the engine itself (abm_init_random)."""
+        self._ck(self.lib.fn["init_random"](self.h, int(n_sheep), int(init_seed)))
 
     def set_global_state(self, tick=0, behav=0, behav_counter=0):
         self._ck(self.lib.fn["set_global_state"](self.h, int(tick), int(behav), int(behav_counter)))

@@ -1830,14 +1830,19 @@ int ABM_API(get_grid)(abm_handle* h, uint8_t* fg, int64_t* cd) {
   return ABM_OK;
 }
 
-int ABM_API(set_agents)(abm_handle* h, int64_t n, const int64_t* id, const int64_t* x, const int64_t* y,
-                        const double* energy, int64_t next_id) {
-  if (!h) return ABM_E_BADARG;
-  if (n < 0 || (n > 0 && (!id || !x || !y || !energy))) ABM_FAIL(h, ABM_E_BADARG, "null agent arrays");
-  if (next_id < 1 || next_id > 0xFFFFFFFFll || n >= 0xFFFFFFF0ll) ABM_FAIL(h, ABM_E_CAPACITY, "next_id must be in 1..2^32-1");
-  int rc = set_device(h);
-  if (rc) return rc;
+/* room for n host-layout agent records (id, x, y: i64; energy: f64) in the staging buffer */
+static int stage_agents(abm_handle* h, int64_t n) { return ensure(h, h->stage, (size_t)std::max<int64_t>(n, 1) * 32 + 64); }
+
+/* the agent records waiting in the staging buffer become the population: validated, converted to the SoA and grouped by
+ * cell (general path) or by 8x8 sub-tile (tile path).  Shared by abm_set_agents (records copied from the host) and
+ * abm_init_random (records generated on the device). */
+static int ingest_staged(abm_handle* h, int64_t n, int64_t next_id) {
+  int rc;
   const Geo& g = h->g;
+  int64_t* s_id = (int64_t*)h->stage.p;
+  int64_t* s_x = s_id + n;
+  int64_t* s_y = s_x + n;
+  double* s_e = (double*)(s_y + n);
   const int tmp = h->cur ^ 1, dst = h->cur;
   if ((rc = ensure_soa(h, tmp, n))) return rc;
   if ((rc = ensure_soa(h, dst, n))) return rc;
@@ -1852,16 +1857,7 @@ int ABM_API(set_agents)(abm_handle* h, int64_t n, const int64_t* id, const int64
     uint32_t* soff = (uint32_t*)h->sub_off[dst].p;
     ABM_CK(h, dev_memset(scnt, 0, nsub * 4, h->stream));
     if (n > 0) {
-      if ((rc = ensure(h, h->stage, (size_t)n * 32 + 64))) return rc;
       if ((rc = ensure(h, h->ingest_sub, (size_t)n * 4))) return rc;
-      int64_t* s_id = (int64_t*)h->stage.p;
-      int64_t* s_x = s_id + n;
-      int64_t* s_y = s_x + n;
-      double* s_e = (double*)(s_y + n);
-      ABM_CK(h, copy_h2d(s_id, id, (size_t)n * 8, h->stream));
-      ABM_CK(h, copy_h2d(s_x, x, (size_t)n * 8, h->stream));
-      ABM_CK(h, copy_h2d(s_y, y, (size_t)n * 8, h->stream));
-      ABM_CK(h, copy_h2d(s_e, energy, (size_t)n * 8, h->stream));
       IngestTileBody ib;
       ib.g = g; ib.nsx = h->nsx; ib.hid = s_id; ib.hx = s_x; ib.hy = s_y; ib.he = s_e; ib.next_id = next_id;
       ib.cell = (uint32_t*)h->cell[tmp].p; ib.id = (uint32_t*)h->id[tmp].p; ib.energy = (double*)h->energy[tmp].p;
@@ -1884,15 +1880,6 @@ int ABM_API(set_agents)(abm_handle* h, int64_t n, const int64_t* id, const int64
   uint32_t* start = h->tile_mode ? nullptr : (uint32_t*)h->cell_start[dst].p;
   if (!h->tile_mode) ABM_CK(h, dev_memset(start, 0, ((size_t)g.gt + 1) * 4, h->stream));
   if (n > 0 && !h->tile_mode) {
-    if ((rc = ensure(h, h->stage, (size_t)n * 32 + 64))) return rc;
-    int64_t* s_id = (int64_t*)h->stage.p;
-    int64_t* s_x = s_id + n;
-    int64_t* s_y = s_x + n;
-    double* s_e = (double*)(s_y + n);
-    ABM_CK(h, copy_h2d(s_id, id, (size_t)n * 8, h->stream));
-    ABM_CK(h, copy_h2d(s_x, x, (size_t)n * 8, h->stream));
-    ABM_CK(h, copy_h2d(s_y, y, (size_t)n * 8, h->stream));
-    ABM_CK(h, copy_h2d(s_e, energy, (size_t)n * 8, h->stream));
     IngestBody ib;
     ib.g = g; ib.hid = s_id; ib.hx = s_x; ib.hy = s_y; ib.he = s_e; ib.next_id = next_id;
     ib.cell = (uint32_t*)h->cell[tmp].p; ib.id = (uint32_t*)h->id[tmp].p; ib.energy = (double*)h->energy[tmp].p;
@@ -1928,6 +1915,66 @@ int ABM_API(set_agents)(abm_handle* h, int64_t n, const int64_t* id, const int64
   ABM_CK(h, dev_memset((uint32_t*)h->counters.p + CTR_ROUTE_SLOTS, 0, 4, h->stream));
   h->rt_pool_used = 0;
   return ABM_OK;
+}
+
+int ABM_API(set_agents)(abm_handle* h, int64_t n, const int64_t* id, const int64_t* x, const int64_t* y,
+                        const double* energy, int64_t next_id) {
+  if (!h) return ABM_E_BADARG;
+  if (n < 0 || (n > 0 && (!id || !x || !y || !energy))) ABM_FAIL(h, ABM_E_BADARG, "null agent arrays");
+  if (next_id < 1 || next_id > 0xFFFFFFFFll || n >= 0xFFFFFFF0ll) ABM_FAIL(h, ABM_E_CAPACITY, "next_id must be in 1..2^32-1");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = stage_agents(h, n))) return rc;
+  if (n > 0) {
+    int64_t* s_id = (int64_t*)h->stage.p;
+    ABM_CK(h, copy_h2d(s_id, id, (size_t)n * 8, h->stream));
+    ABM_CK(h, copy_h2d(s_id + n, x, (size_t)n * 8, h->stream));
+    ABM_CK(h, copy_h2d(s_id + 2 * n, y, (size_t)n * 8, h->stream));
+    ABM_CK(h, copy_h2d(s_id + 3 * n, energy, (size_t)n * 8, h->stream));
+  }
+  return ingest_staged(h, n, next_id);
+}
+
+/* the random part of initialize_model, built on the device (include/abm.h) */
+int ABM_API(init_random)(abm_handle* h, int64_t n_sheep, uint64_t init_seed) {
+  if (!h) return ABM_E_BADARG;
+  if (h->strip) ABM_FAIL(h, ABM_E_BADARG, "abm_init_random is not available on a strip handle (placement needs the whole walkmap)");
+  const int64_t span = (int64_t)(h->cfg.delta_energy * 5);
+  if (n_sheep < 0 || n_sheep >= 0xFFFFFFF0ll) ABM_FAIL(h, ABM_E_CAPACITY, "n_sheep must be below 2^32-16");
+  if (span < 1) ABM_FAIL(h, ABM_E_BADARG, "delta_energy * 5 must be at least 1 (energy = rand(1:delta_energy*5) - 1)");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const Geo& g = h->g;
+  uint32_t* err = (uint32_t*)h->counters.p + CTR_ERR;
+  ABM_CK(h, dev_memset(err, 0, 4, h->stream));
+  if (!h->grid_set) { /* no terrain was given: every cell of the space is walkable, elevation 0 */
+    ABM_CK(h, dev_memset(h->grass.p, GRASS_PAD, g.gt, h->stream));
+    ABM_CK(h, dev_memset(h->walkbits.p, 0, (size_t)g.gt / 8, h->stream));
+    if ((rc = ensure(h, h->elev, (size_t)g.gt * 2))) return rc;
+    ABM_CK(h, dev_memset(h->elev.p, 0, (size_t)g.gt * 2, h->stream));
+    h->comp_valid = false;
+  }
+  InitGrassBody gb;
+  gb.g = g; gb.seed = init_seed; gb.regrowth_time = h->cfg.regrowth_time; gb.open_terrain = h->grid_set ? 0 : 1;
+  gb.grass = (uint8_t*)h->grass.p; gb.walkbits = (uint32_t*)h->walkbits.p;
+  launch_foreach(h->stream, gb, (uint64_t)g.nx * (uint64_t)g.ny);
+  if ((rc = check_launch(h, "grass initialisation"))) return rc;
+  h->grid_set = true;
+  if ((rc = stage_agents(h, n_sheep))) return rc;
+  if (n_sheep > 0) {
+    InitSheepBody sb;
+    sb.g = g; sb.seed = init_seed; sb.span = (uint64_t)span; sb.walkbits = (const uint32_t*)h->walkbits.p;
+    sb.s_id = (int64_t*)h->stage.p; sb.s_x = sb.s_id + n_sheep; sb.s_y = sb.s_x + n_sheep; sb.s_e = (double*)(sb.s_y + n_sheep);
+    sb.err = err;
+    launch_foreach(h->stream, sb, (uint64_t)n_sheep);
+    if ((rc = check_launch(h, "sheep initialisation"))) return rc;
+    if ((rc = read_counters(h))) return rc;
+    if (h->h_counters[CTR_ERR] & ERR_NOWALKABLE) {
+      ABM_CK(h, dev_memset(err, 0, 4, h->stream));
+      ABM_FAIL(h, ABM_E_NOWALKABLE, "random_walkable found no walkable cell in 4096 draws");
+    }
+  }
+  return ingest_staged(h, n_sheep, n_sheep + 1);
 }
 
 int ABM_API(count_agents)(abm_handle* h, int64_t* n) {

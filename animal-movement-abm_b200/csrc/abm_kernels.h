@@ -821,6 +821,45 @@ struct GridImportBody {
   }
 };
 
+/* abm_init_random: the grass of initialize_model (scripts/v0.1.jl:73-78; walkable cells only, scripts/v0.5.jl:115-122),
+ * one Philox stream per cell keyed by its linear index (x fastest) */
+struct InitGrassBody {
+  Geo g; uint64_t seed; int32_t regrowth_time, open_terrain;
+  uint8_t* grass; uint32_t* walkbits;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint64_t y = i / (uint64_t)g.nx, x = i - y * (uint64_t)g.nx;
+    const uint32_t c = enc(g, (int)x, (int)y);
+    if (open_terrain) atomic_or(&walkbits[c >> 5], 1u << (c & 31));
+    else if (!((walkbits[c >> 5] >> (c & 31)) & 1u)) { grass[c] = 0; return; }
+    AgentStream r;
+    r.init(seed, 0xFFFFFFFEull, i);
+    const bool grown = (r.next_u64() & 1ull) != 0;
+    const uint32_t k = grown ? (uint32_t)regrowth_time : (regrowth_time > 0 ? r.next_below((uint64_t)regrowth_time) : 0u);
+    grass[c] = (uint8_t)((grown ? GRASS_GROWN : 0) | (k & 0x7F));
+  }
+};
+/* abm_init_random: sheep i + 1 — energy = rand(1:span) - 1, then random_position until the cell is walkable
+ * (scripts/v0.1.jl:66-71, random_walkable in scripts/v0.5.jl:103) — written as host-layout records for the ingest */
+struct InitSheepBody {
+  Geo g; uint64_t seed, span; const uint32_t* walkbits;
+  int64_t* s_id; int64_t* s_x; int64_t* s_y; double* s_e; uint32_t* err;
+  ABM_HD void operator()(uint64_t i) const {
+    AgentStream r;
+    r.init(seed, 0xFFFFFFFFull, i + 1);
+    const uint32_t e = r.next_below(span);
+    uint32_t x = 0, y = 0;
+    int tries = 0;
+    while (true) {
+      x = r.next_below((uint64_t)g.nx);
+      y = r.next_below((uint64_t)g.ny);
+      const uint32_t c = enc(g, (int)x, (int)y);
+      if ((walkbits[c >> 5] >> (c & 31)) & 1u) break;
+      if (++tries >= 4096) { atomic_or(err, ERR_NOWALKABLE); break; }
+    }
+    s_id[i] = (int64_t)(i + 1); s_x[i] = (int64_t)x + 1; s_y[i] = (int64_t)y + 1; s_e[i] = (double)e;
+  }
+};
+
 struct GridExportBody {
   Geo g;
   const uint8_t* grass;

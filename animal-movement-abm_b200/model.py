@@ -101,6 +101,7 @@ class SheepModel:
         self._next_id = 1
         self._state = dict(tick=0, behav=0, behav_counter=0)
         self._host_fresh = True
+        self._device_init = None  # (n_sheep, init_seed): the engine builds grass and sheep itself (abm_init_random)
 
     # ---- construction helpers (the host keeps `initialize_model`)
     def set_grass(self, fully_grown, countdown):
@@ -119,6 +120,15 @@ class SheepModel:
         self._agents = dict(ids=np.concatenate([a["ids"], np.asarray(ids, np.int64)]), x=np.concatenate([a["x"], x]),
                             y=np.concatenate([a["y"], y]), energy=np.concatenate([a["energy"], e]))
         self._next_id = max(self._next_id, int(np.max(ids)) + 1) if x.size else self._next_id
+        self._drop_engine()
+
+    def init_on_device(self, n_sheep, init_seed=None):
+        """The random part of `initialize_model` built by the engine itself (`abm_init_random`): nothing is generated or
+        uploaded by the host except the terrain.  Takes effect when the first `step`/`run` creates the engine; the host
+        views (`agents()`, `fully_grown`, ...) are then fetched lazily like after any step."""
+        self._device_init = (int(n_sheep), int(self.seed if init_seed is None else init_seed))
+        self._agents = dict(ids=np.zeros(0, np.int64), x=np.zeros(0, np.int64), y=np.zeros(0, np.int64), energy=np.zeros(0, np.float64))
+        self._next_id = int(n_sheep) + 1
         self._drop_engine()
 
     def set_behaviour(self, behav=0, behav_counter=None):
@@ -161,9 +171,15 @@ class SheepModel:
             movement_cost=self.movement_cost, reproduction_prob=self.reproduction_prob, attractor_x=self.attractor[0],
             attractor_y=self.attractor[1], seed=self.seed)
         e = lib.create(cfg)
-        e.set_grid(self._fg, self._cd, self.land_walkmap, self.elevation)
-        a = self._agents
-        e.set_agents(a["ids"], a["x"], a["y"], a["energy"], self._next_id)
+        if self._device_init is None or self.land_walkmap is not None or self.elevation is not None:
+            e.set_grid(self._fg, self._cd, self.land_walkmap, self.elevation)  # with a device init only the terrain matters
+        if self._device_init is not None:
+            e.init_random(*self._device_init)
+            self._device_init = None
+            self._host_fresh = False
+        else:
+            a = self._agents
+            e.set_agents(a["ids"], a["x"], a["y"], a["energy"], self._next_id)
         e.set_global_state(self._state["tick"], self._state["behav"], self._state["behav_counter"])
         if agent_step.walk_type == WalkType.RANDOM_WALK_GREGARIOUS:
             e.set_weight_lut(worlds.weight_lut(self.visual_distance))  # the host's exp (parity note in include/abm.h)
@@ -188,6 +204,8 @@ class SheepModel:
         return a["ids"], a["x"], a["y"], a["energy"]
 
     def nagents(self) -> int:
+        if self._engine is None and self._device_init is not None:
+            return self._device_init[0]
         return self._engine.count_agents() if self._engine is not None else int(self._agents["ids"].size)
 
     @property
@@ -286,7 +304,7 @@ def run(model: SheepModel, agent_step: EngineAgentStep, model_step: EngineModelS
 
 def initialize_model(*, n_sheep=40, griddims=(80, 80), regrowth_time=30, delta_energy_sheep=4, sheep_reproduce=0.001, movement_cost=1,
                      visual_distance=5, seed=321, periodic=False, counter=50, water_level=1, mountain_level=18, elevation=None,
-                     use_walkmap=False, synthetic_terrain_seed=7, astar_metric=capi.ASTAR_DIRECT, astar_penalty=False, lib=None, device=0) -> SheepModel:
+                     use_walkmap=False, synthetic_terrain_seed=7, astar_metric=capi.ASTAR_DIRECT, astar_penalty=False, lib=None, device=0, on_device=False) -> SheepModel:
     """The scripts' `initialize_model(; kwargs)` (scripts/v0.1.jl:36-81 ... scripts/v0.6.jl:36-135), same keywords
     (Δenergy_sheep spelled delta_energy_sheep).  v0.1/v0.2 are non-periodic, v0.3-v0.6 periodic; v0.5/v0.6 build
     `land_walkmap = water_level .< elevation .< mountain_level` from a heightmap — the scripts download theirs, here
@@ -298,11 +316,14 @@ def initialize_model(*, n_sheep=40, griddims=(80, 80), regrowth_time=30, delta_e
         if elevation is None:
             elevation = worlds.make_terrain(nx, ny, seed=synthetic_terrain_seed)
         wm = worlds.walkmap_from_elevation(np.asarray(elevation), water_level, mountain_level)
-    w = worlds.make_world(nx, ny, n_sheep, seed=seed, regrowth_time=regrowth_time, delta_energy=int(delta_energy_sheep), walkmap=wm, periodic=bool(periodic))
+    w = None if on_device else worlds.make_world(nx, ny, n_sheep, seed=seed, regrowth_time=regrowth_time, delta_energy=int(delta_energy_sheep), walkmap=wm, periodic=bool(periodic))
     m = SheepModel((nx, ny), periodic=periodic, seed=seed, regrowth_time=regrowth_time, delta_energy=delta_energy_sheep, movement_cost=movement_cost,
                    reproduction_prob=sheep_reproduce, visual_distance=visual_distance, counter=counter, land_walkmap=wm, elevation=elevation,
                    astar_metric=astar_metric, astar_penalty=astar_penalty, lib=lib, device=device)
-    m.set_grass(w["fully_grown"], w["countdown"])
-    m.add_agents(w["x"], w["y"], w["energy"], w["ids"])
+    if on_device:  # grass and sheep are drawn by the engine (abm_init_random): a 2^28-sheep world needs no host arrays
+        m.init_on_device(n_sheep, seed)
+    else:
+        m.set_grass(w["fully_grown"], w["countdown"])
+        m.add_agents(w["x"], w["y"], w["energy"], w["ids"])
     m.set_behaviour(0, counter)  # model.behav_counter[1] = counter, scripts/v0.4.jl:97
     return m

@@ -136,6 +136,19 @@ int abm_set_grid(abm_handle* h, const uint8_t* fully_grown, const int64_t* count
 int abm_set_agents(abm_handle* h, int64_t n, const int64_t* id, const int64_t* x, const int64_t* y,
                    const double* energy, int64_t next_id);
 
+/* replaces: the random part of `initialize_model` (scripts/v0.1.jl:66-79: `n_sheep` sheep, each with
+ * `energy = rand(1:Δenergy*5) - 1` at a random position; every cell `fully_grown = rand(Bool)`,
+ * `countdown = fully_grown ? regrowth_time : rand(1:regrowth_time) - 1`; scripts/v0.5.jl:100-122: sheep at
+ * `random_walkable` positions, grass only on walkable cells) — built on the device, so a 2^28-sheep world needs no host
+ * arrays.  Terrain, if any, must have been given before through abm_set_grid (its grass arguments are overwritten
+ * here); without a previous abm_set_grid every cell is walkable.  Sheep get ids 1..n_sheep, next_id = n_sheep + 1.
+ * The reference draws all of this from one sequential MersenneTwister stream; here every sheep and every cell has its
+ * own stream of the contract above — sheep i: draw(init_seed, tick = 2^32-1, id = i, n) with n = 0 the energy, then
+ * (x, y) pairs until the cell is walkable; cell (x, y): draw(init_seed, tick = 2^32-2, id = (y-1)*nx + (x-1), n) with
+ * n = 0 the grown bit (lowest bit of the word), n = 1.. the countdown — so the world does not depend on who builds it.
+ * Not available on a strip handle (placement needs the whole walkmap). */
+int abm_init_random(abm_handle* h, int64_t n_sheep, uint64_t init_seed);
+
 /* replaces: model.behav[1], model.behav_counter[1] (scripts/v0.4.jl:69-71,97) and the tick the RNG is keyed by */
 int abm_set_global_state(abm_handle* h, int64_t tick, int64_t behav, int64_t behav_counter);
 int abm_get_global_state(abm_handle* h, int64_t* tick, int64_t* behav, int64_t* behav_counter, int64_t* next_id);

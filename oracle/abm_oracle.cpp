@@ -585,6 +585,52 @@ int oracle_set_agents(oracle_handle* h, int64_t n, const int64_t* id, const int6
   return 0;
 }
 
+/* the random part of initialize_model (scripts/v0.1.jl:66-79, scripts/v0.5.jl:100-122) under the per-sheep / per-cell
+ * streams that include/abm.h states for abm_init_random */
+int oracle_init_random(oracle_handle* h, int64_t n_sheep, uint64_t init_seed) {
+  Model& m = h->m;
+  const i64 span = (i64)(m.cfg.delta_energy * 5);
+  if (n_sheep < 0 || n_sheep >= 0xFFFFFFF0ll || span < 1 || m.cfg.n_ranks > 1 || m.cfg.strip_ny > 0) return ABM_E_BADARG;
+  AgentRng r;
+  r.seed = init_seed;
+  bool any = false;
+  for (int y = 1; y <= m.ny; ++y)
+    for (int x = 1; x <= m.nx; ++x) { /* for p in positions(model): grass on walkable cells only */
+      const size_t c = m.lin(x, y);
+      m.fully_grown[c] = 0;
+      m.countdown[c] = 0;
+      if (!m.walkmap[c]) continue;
+      any = true;
+      r.reset(0xFFFFFFFEull, (u64)c);
+      const bool grown = (r.next_u64() & 1ull) != 0;
+      m.fully_grown[c] = grown ? 1 : 0;
+      m.countdown[c] = grown ? m.cfg.regrowth_time : (m.cfg.regrowth_time > 0 ? r.rand_1_to((u64)m.cfg.regrowth_time) - 1 : 0);
+    }
+  m.grid_set = true;
+  if (n_sheep > 0 && !any) return ABM_E_NOWALKABLE;
+  m.agents.clear();
+  m.paths.clear();
+  m.path_cost.clear();
+  for (size_t i = 0; i < m.stored.size(); ++i) m.stored[i].clear();
+  for (i64 i = 1; i <= n_sheep; ++i) {
+    r.reset(0xFFFFFFFFull, (u64)i);
+    Sheep s;
+    s.id = i;
+    s.energy = (double)(r.rand_1_to((u64)span) - 1);
+    int tries = 0;
+    while (true) { /* random_position / random_walkable */
+      s.x = (int)r.rand_1_to((u64)m.nx);
+      s.y = (int)r.rand_1_to((u64)m.ny);
+      if (m.walkmap[m.lin(s.x, s.y)]) break;
+      if (++tries >= 4096) return ABM_E_NOWALKABLE;
+    }
+    m.agents[i] = s;
+    m.stored[m.lin(s.x, s.y)].push_back(i);
+  }
+  m.maxid = n_sheep;
+  return 0;
+}
+
 int oracle_set_global_state(oracle_handle* h, int64_t tick, int64_t behav, int64_t bc) {
   h->m.tick = (u64)tick; h->m.behav = behav; h->m.behav_counter = bc;
   return 0;

@@ -81,3 +81,22 @@ def test_product_library_is_the_default_and_has_no_cpu_path():
     with pytest.raises(A.AbmError) as ei:
         A.step(m, A.herbivore_dynamics(), A.grass_growth_dynamics(), 1)
     assert ei.value.code == A.capi.ABM_E_CUDA
+
+
+def test_initialize_model_on_the_device(emu, oracle):
+    """`initialize_model(...; on_device=True)`: the engine draws grass and sheep itself (abm_init_random); the emulated
+    engine and the oracle, driven through the same mirror, build and step the same world; changing the rules afterwards
+    keeps it."""
+    models = [A.initialize_model(n_sheep=120, griddims=(64, 64), periodic=True, use_walkmap=True, seed=5, on_device=True, lib=lib) for lib in (emu, oracle)]
+    astep, mstep = A.herbivore_dynamics(walk_type=A.WalkType.RANDOM_WALKMAP), A.grass_growth_dynamics(walkmap=True)
+    assert all(m.nagents() == 120 for m in models)
+    for m in models:
+        A.step(m, astep, mstep, 4)
+    (ia, xa, ya, ea), (ib, xb, yb, eb) = models[0].agents(), models[1].agents()
+    assert np.array_equal(ia, ib) and np.array_equal(xa, xb) and np.array_equal(ya, yb) and np.array_equal(ea, eb) and ia.size > 0
+    assert np.array_equal(models[0].fully_grown, models[1].fully_grown) and models[0].tick == 4
+    m = models[0]
+    wm = m.land_walkmap.astype(bool)
+    assert wm[ya - 1, xa - 1].all()
+    A.step(m, A.herbivore_dynamics(walk_type=A.WalkType.RANDOM_WALK), A.grass_growth_dynamics(), 1)  # new engine, same world
+    assert m.tick == 5 and m.nagents() > 0

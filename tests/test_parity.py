@@ -404,3 +404,59 @@ def test_gpu_empty_world_and_extinction(libabm, oracle, nx, ny, wt):
     assert b.count_agents() == 0
     b = _edge_run(oracle, libabm, nx, ny, min(50, 3 * nx * ny), 0.5, wt)
     assert b.count_agents() == 0
+
+
+def _init_pair(lib_a, lib_b, nx, ny, n, wt, terrain, seed=11, **kw):
+    from conftest import make_case
+    cfgkw, w = make_case(nx, ny, 1, wt, 1, terrain=terrain, seed=seed, regrowth_time=6, delta_energy=3.0, reproduction_prob=0.05, **kw)
+    out = []
+    for lib in (lib_a, lib_b):
+        e = lib.create(lib.default_config(**cfgkw))
+        if terrain:  # only the terrain of this call survives abm_init_random
+            e.set_grid(np.zeros((ny, nx), np.uint8), np.zeros((ny, nx), np.int64), w["walkmap"], w["elevation"])
+        e.init_random(n, 4242)
+        out.append(e)
+    return out[0], out[1], w
+
+
+@pytest.mark.parametrize("nx,ny,n,wt,terrain", [(40, 30, 300, 0, False), (64, 64, 1500, 2, False), (96, 64, 2000, 4, True), (33, 7, 0, 0, False), (64, 96, 900, 3, True)])
+def test_emulated_device_side_initialisation(emu, oracle, nx, ny, n, wt, terrain):
+    """abm_init_random (the random part of initialize_model): engine and oracle build the same world from
+    the per-sheep / per-cell streams, the world has the reference's shape, and stepping it stays bit-exact."""
+    a, b, w = _init_pair(oracle, emu, nx, ny, n, wt, terrain, counter=5, astar_metric=1, astar_penalty=1)
+    sa = a.snapshot()
+    assert_same_state(b.snapshot(), sa, "after init")
+    assert sa["ids"].tolist() == list(range(1, n + 1)) and sa["next_id"] == n + 1
+    assert ((sa["energy"] >= 0) & (sa["energy"] <= 14) & (sa["energy"] == np.floor(sa["energy"]))).all()  # rand(1:3*5) - 1
+    walk = np.ones((ny, nx), bool) if not terrain else w["walkmap"].astype(bool)
+    assert walk[sa["y"] - 1, sa["x"] - 1].all()
+    fg, cd = sa["fully_grown"].astype(bool), sa["countdown"]
+    assert not fg[~walk].any() and (cd[~walk] == 0).all()          # scripts/v0.5.jl:115-122
+    assert (cd[fg] == 6).all() and ((cd[walk & ~fg] >= 0) & (cd[walk & ~fg] <= 5)).all()
+    if walk.sum() > 500:
+        assert 0.4 < fg[walk].mean() < 0.6
+    for e in (a, b):
+        if wt == 3:
+            e.set_global_state(0, 0, 5)
+    for t in range(5):
+        a.step(1)
+        b.step(1)
+        assert_same_state(b.snapshot(), a.snapshot(), f"tick {t} after init")
+
+
+def test_device_side_initialisation_is_refused_on_strips(emu):
+    from abm_b200 import capi as _capi
+    e = emu.create(emu.default_config(nx=64, ny=64, periodic=1, walk_type=0, strip_y0=0, strip_ny=64, n_ranks=1, rank=0))
+    with pytest.raises(_capi.AbmError):
+        e.init_random(10, 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nx,ny,n,wt,terrain", [(100, 70, 2000, 0, False), (128, 96, 6000, 4, True)])
+def test_gpu_device_side_initialisation(libabm, oracle, nx, ny, n, wt, terrain):
+    a, b, _ = _init_pair(oracle, libabm, nx, ny, n, wt, terrain)
+    assert_same_state(b.snapshot(), a.snapshot(), "after init")
+    for t in range(5):
+        a.step(1)
+        b.step(1)
+        assert_same_state(b.snapshot(), a.snapshot(), f"tick {t} after init")
