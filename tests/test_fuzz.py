@@ -32,3 +32,11 @@ def test_oracle_matches_second_restatement_on_random_configurations():
     bad = {s: r for s, r in results.items() if r.split()[0] in ("DIFF", "ERROR")}
     assert not bad, bad
     assert sum(r == "ok" for r in results.values()) >= 250
+
+
+def test_astar_api_matches_oracle_on_random_terrain(monkeypatch):
+    monkeypatch.setenv("ABM_ASTAR_SLOTS", "1")       # the fuzzer overwrites both per seed; monkeypatch restores them
+    monkeypatch.setenv("ABM_ROUTE_POOL_GUESS", "5")
+    results = {s: fuzz.astar_vs_oracle(s) for s in range(400000, 400150)}
+    bad = {s: r for s, r in results.items() if r.split()[0] == "DIFF"}
+    assert not bad, bad

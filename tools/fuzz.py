@@ -2,12 +2,14 @@
 
     python tools/fuzz.py engine START COUNT   # the engine's kernels (emulated launcher) against the CPU oracle
     python tools/fuzz.py oracle START COUNT   # the CPU oracle against the independent Python restatement (tests/pyref.py)
+    python tools/fuzz.py astar START COUNT    # abm_plan_routes / abm_get_paths (random terrain, goals anywhere, replans,
+                                              # 1-64 search slots, route pools that overflow): engine vs oracle
 
 `FORCE_GENERAL=1` sends a third of the tile-sized engine cases down the general path; `ABM_TILE_ROUNDS=1` leaves most
 conflicts to the per-agent windows.  Every seed is reproducible: `engine_vs_oracle(seed)` / `oracle_vs_pyref(seed)` return
 "ok", "skip ...", "refused ..." (abm_create turned the configuration down), "both raised", or a line starting with DIFF /
-ERROR.  tests/test_fuzz.py runs a bounded number of seeds; 2,300 engine and 4,400 oracle seeds were clean when this was
-written.
+ERROR.  tests/test_fuzz.py runs a bounded number of seeds; 2,300 engine, 4,400 oracle and 5,600 A* seeds were clean when this
+was written.
 """
 import os
 import sys
@@ -122,8 +124,37 @@ def oracle_vs_pyref(seed):
     return "ok"
 
 
+def astar_vs_oracle(seed):
+    rng = np.random.default_rng(seed)
+    nx, ny = int(rng.integers(3, 70)), int(rng.integers(3, 70))
+    per = int(rng.integers(0, 2)); metric = int(rng.integers(0, 2)); pen = int(rng.integers(0, 2))
+    n = int(rng.integers(1, 80))
+    os.environ["ABM_ASTAR_SLOTS"] = str(int(rng.choice([1, 3, 64])))
+    os.environ["ABM_ROUTE_POOL_GUESS"] = str(int(rng.choice([5, 200, 100000])))
+    try:
+        cfgkw, w = make_case(nx, ny, n, 3, per, terrain=True, seed=int(seed % 99991), astar_metric=metric, astar_penalty=pen, counter=9)
+    except Exception as exc:
+        return "skip"
+    ok = np.argwhere(np.ones_like(w["walkmap"]) == 1)   # goals anywhere, walkable or not
+    goals = ok[rng.integers(0, len(ok), n)]
+    res = []
+    for lib in (_lib("oracle"), _lib("emu")):
+        e = load_case(lib, cfgkw, w)
+        e.plan_routes(w["ids"], goals[:, 1] + 1, goals[:, 0] + 1)
+        res.append(e.get_paths(w["ids"]))
+        # replan half of them to new goals: routes are overwritten / kept when unreachable
+        g2 = ok[np.random.default_rng(seed + 1).integers(0, len(ok), n)]
+        half = w["ids"][: max(1, n // 2)]
+        e.plan_routes(half, g2[: half.size, 1] + 1, g2[: half.size, 0] + 1)
+        res.append(e.get_paths(w["ids"]))
+    for k in range(2):
+        for u, v in zip(res[k], res[k + 2]):
+            if not np.array_equal(u, v): return f"DIFF seed {seed} stage {k} cfg={cfgkw} n={n}"
+    return "ok"
+
+
 if __name__ == "__main__":
-    fn = engine_vs_oracle if sys.argv[1] == "engine" else oracle_vs_pyref
+    fn = {"engine": engine_vs_oracle, "oracle": oracle_vs_pyref, "astar": astar_vs_oracle}[sys.argv[1]]
     t0, stats = time.time(), {}
     start, count = int(sys.argv[2]), int(sys.argv[3])
     for s in range(start, start + count):
