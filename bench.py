@@ -5,7 +5,10 @@ Workload (BASELINE.json configs[1], "C2"): v0.3 rules — RANDOM_WALK_GREGARIOUS
 prob_random_walk = 0.9, eat + reproduce + grass regrowth — on a periodic 4096 x 4096 GridSpace with 2^22 sheep,
 synthetic seeded world (abm_b200.worlds).  A "step" is one tick: every agent's agent_step! in id order, then
 model_step!.  At N > 1 the GridSpace is 4096 x (4096 N) with 2^22 N sheep, cut into N row strips (one per GPU, weak
-scaling); abm_step exchanges the boundary sub-tile rows with the ring neighbours over NCCL every tick.
+scaling); abm_step exchanges the boundary sub-tile rows with the ring neighbours every tick — over NVLink peer memory
+(kernels store into the neighbours' mailboxes; `--transport auto`, the default, falls back to NCCL when a rank cannot map
+its peers).  Other workloads: `--workload C3` (v0.5 walkmap rules, 8192^2), `C5` (the same rules on 32768 x 4096 rows per
+GPU: 32768^2 and 2^28 sheep at 8 GPUs), `C1`, and `C4` (batched A* replans; prints its own line).
 
   value      agent-updates/s with the world resident in HBM; per-tick CUDA-event time on the library's stream,
              L2 flushed (256 MiB write) between ticks, max over ranks.
