@@ -252,7 +252,14 @@ struct ResolveWindow {
   uint32_t* out_count;
 
   static size_t smem_bytes(int wx, int wy) { return (size_t)(3 * wx * wy + RUNTABLE_WORDS + 8) * 4; }
-  static size_t smem_bytes_core() { return (size_t)(4 * WIN * WIN + 3 * ULIST_CAP + RUNTABLE_WORDS + 16) * 4; }
+  /* -DABM_ONE_MAYBE (experiment, off by default): one min_maybe buffer instead of the double buffer — 9 KB less shared
+   * memory per CTA (5 CTAs/SM instead of 4) for a third barrier and a rebuild pass per round */
+#ifdef ABM_ONE_MAYBE
+  enum { MAYBE_BUFS = 1 };
+#else
+  enum { MAYBE_BUFS = 2 };
+#endif
+  static size_t smem_bytes_core() { return (size_t)((2 + MAYBE_BUFS) * WIN * WIN + 3 * ULIST_CAP + RUNTABLE_WORDS + 16) * 4; }
 
   /* Core window with the undecided agents held in a shared-memory work list: each round touches only what is still
    * open.  min_new only ever gains entries (decisions are final), min_maybe is rebuilt per round from the list (double
@@ -266,12 +273,12 @@ struct ResolveWindow {
     const int cells = WIN * WIN, nruns = w.runs(), NT = TILE_THREADS;
     uint32_t* max_old = smem;
     uint32_t* min_new = smem + cells;
-    uint32_t* maybe[2] = {smem + 2 * cells, smem + 3 * cells};
+    uint32_t* maybe[2] = {smem + 2 * cells, smem + (1 + MAYBE_BUFS) * cells};
     /* one work list, never compacted: `ifempty` walkers from the front, gregarious agents from the back (each kind is
      * then evaluated by full warps; their code paths differ by an order of magnitude in length).  Entry = agent index,
      * id, and a word  best:9 | done:1 | state:8 | y:6 | x:6  — `best` is the running minimum of the gregarious search
      * (visiting rank << 1 | only-maybe), in the top bits so that atomicMin on the word orders by it. */
-    uint32_t* l_a = smem + 4 * cells;
+    uint32_t* l_a = smem + (2 + MAYBE_BUFS) * cells;
     uint32_t* l_id = l_a + ULIST_CAP;
     uint32_t* l_xs = l_id + ULIST_CAP;
     RunTable rt;
@@ -282,7 +289,7 @@ struct ResolveWindow {
 
     ABM_CTA_FOR(t, NT) {
       rt.load(t, NT, nruns, w, v.g, si);
-      for (int c = t; c < cells; c += NT) { max_old[c] = 0u; min_new[c] = NONE32; maybe[0][c] = NONE32; maybe[1][c] = NONE32; }
+      for (int c = t; c < cells; c += NT) { max_old[c] = 0u; min_new[c] = NONE32; maybe[0][c] = NONE32; if (MAYBE_BUFS == 2) maybe[1][c] = NONE32; }
       if (t < 16) cnt[t] = 0;
     }
     ABM_CTA_SYNC();
@@ -353,7 +360,7 @@ struct ResolveWindow {
             l_xs[u] = xs | XS_DONE;
             flag[0] = 1;
           } else {
-            contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
+            if (MAYBE_BUFS == 2) contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
             if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&flag[1], 1u);
           }
         }
@@ -403,7 +410,7 @@ struct ResolveWindow {
             flag[0] = 1;
           } else {
             l_xs[e] = (xs & XS_LOW) | XS_BEST_NONE; /* search again next round */
-            contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
+            if (MAYBE_BUFS == 2) contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
             if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&flag[1], 1u);
           }
         }
@@ -414,6 +421,17 @@ struct ResolveWindow {
       ABM_CTA_SYNC();
       cur ^= 1;
       if (flag[1] == 0 || flag[0] == 0) break;
+      if (MAYBE_BUFS == 1) { /* the single buffer was cleared above: rebuild it from the entries still open */
+        ABM_CTA_FOR(t, NT) {
+          for (uint32_t u = (uint32_t)t; u < nc + ng; u += (uint32_t)NT) {
+            const uint32_t e = u >= nc ? ULIST_CAP - 1 - (u - nc) : u;
+            const uint32_t xs = l_xs[e];
+            if (xs & XS_DONE) continue;
+            contribute_maybe(maybe[0], w, l_id[e], (int)(xs & 63), (int)((xs >> 6) & 63), (uint8_t)(xs >> 12));
+          }
+        }
+        ABM_CTA_SYNC();
+      }
     }
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, NT) { /* the core's agents that stay open go to the per-agent windows */
