@@ -252,18 +252,18 @@ struct ResolveWindow {
   uint32_t* out_count;
 
   static size_t smem_bytes(int wx, int wy) { return (size_t)(3 * wx * wy + RUNTABLE_WORDS + 8) * 4; }
-  /* -DABM_ONE_MAYBE (experiment, off by default): one min_maybe buffer instead of the double buffer — 9 KB less shared
-   * memory per CTA (5 CTAs/SM instead of 4) for a third barrier and a rebuild pass per round */
-#ifdef ABM_ONE_MAYBE
-  enum { MAYBE_BUFS = 1 };
-#else
+  /* One min_maybe buffer, cleared and rebuilt from the open entries every round: 9 KB less shared memory per CTA than
+   * the double buffer (5 CTAs/SM instead of 4) for a third barrier and a rebuild pass per round — measured 19 % faster
+   * (resolve_tiles 0.396 vs 0.489 ms, C2, same box).  -DABM_TWO_MAYBE brings the double buffer back. */
+#ifdef ABM_TWO_MAYBE
   enum { MAYBE_BUFS = 2 };
+#else
+  enum { MAYBE_BUFS = 1 };
 #endif
   static size_t smem_bytes_core() { return (size_t)((2 + MAYBE_BUFS) * WIN * WIN + 3 * ULIST_CAP + RUNTABLE_WORDS + 16) * 4; }
 
   /* Core window with the undecided agents held in a shared-memory work list: each round touches only what is still
-   * open.  min_new only ever gains entries (decisions are final), min_maybe is rebuilt per round from the list (double
-   * buffered).  Agents are read from global memory exactly once.  Returns false (uniformly) when the list overflows. */
+   * open.  min_new only ever gains entries (decisions are final), min_maybe is rebuilt per round from the list.  Agents are read from global memory exactly once.  Returns false (uniformly) when the list overflows. */
   ABM_HD bool core_fast(uint32_t cta, uint32_t* smem) const {
     Window w;
     const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) * row_step + core_y0;
@@ -336,9 +336,10 @@ struct ResolveWindow {
       }
     }
     ABM_CTA_SYNC();
-    /* Rounds, two barriers each.  P1: open walkers are evaluated, open gregarious agents searched.  P2: gregarious agents
-     * draw and publish; the buffer this round read is cleared for the round after next.  min_new only gains entries
-     * (decisions are final); min_maybe is rebuilt every round from the entries still open (double buffered). */
+    /* Rounds, three barriers each.  P1: open walkers are evaluated, open gregarious agents searched.  P2: gregarious agents
+     * draw and publish; min_maybe, which nobody reads in this phase, is cleared.  P3: the entries still open put their
+     * candidate cells back into min_maybe.  min_new only gains entries (decisions are final).  (With -DABM_TWO_MAYBE the
+     * open entries write into a second buffer during P1/P2 instead and P3 disappears.) */
     const int side = 2 * v.p.r + 1, box = side * side;
     int cur = 0;
     for (int round = 0; round < max_rounds; ++round) {
