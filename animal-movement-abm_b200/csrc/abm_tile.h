@@ -31,7 +31,16 @@ namespace abm {
 
 enum { SUB = 8, CORE = 32, HALO = 8, WIN = CORE + 2 * HALO, MAX_RUNS = 36, TILE_THREADS = 256, COMMIT_THREADS = 128, AGENT_THREADS = 32 };
 enum { NONE32 = 0xFFFFFFFFu };
-enum { ULIST_CAP = 1024, ARRIVE_CAP = 768, RUNOF_CAP = 2048, RUNTABLE_WORDS = 4 * MAX_RUNS + 1 + RUNOF_CAP / 4 }; /* shared-memory work lists of a core; larger populations take the streaming code */
+/* shared-memory work lists of a core; larger populations take the streaming code.  The two capacities trade shared memory
+ * (CTAs per SM) against how crowded a core may be before the slower code runs: overridable for tuning runs
+ * (-DABM_ULIST_CAP=..., -DABM_ARRIVE_CAP=..., compared with tools/variant_probe.py). */
+#ifndef ABM_ULIST_CAP
+#define ABM_ULIST_CAP 1024
+#endif
+#ifndef ABM_ARRIVE_CAP
+#define ABM_ARRIVE_CAP 768
+#endif
+enum { ULIST_CAP = ABM_ULIST_CAP, ARRIVE_CAP = ABM_ARRIVE_CAP, RUNOF_CAP = 2048, RUNTABLE_WORDS = 4 * MAX_RUNS + 1 + RUNOF_CAP / 4 };
 
 struct SubIndex {
   const uint32_t* off; /* first agent of the sub-tile's run */
