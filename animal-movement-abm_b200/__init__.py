@@ -9,4 +9,4 @@ from . import capi, model, strips, worlds  # noqa: F401
 from .capi import (ALTERNATED_WALK, RANDOM_WALK, RANDOM_WALK_ATTRACTOR, RANDOM_WALK_GREGARIOUS,  # noqa: F401
                    RANDOM_WALKMAP, AbmConfig, AbmError, CLib, Engine)
 from .model import (EngineAgentStep, EngineModelStep, SheepModel, WalkType, count, count_grass,  # noqa: F401
-                    grass_growth_dynamics, herbivore_dynamics, initialize_model, run, sheep, step)
+                    grass_growth_dynamics, grasscolor, herbivore_dynamics, initialize_model, plot_data, run, sheep, step)

@@ -300,6 +300,21 @@ def run(model: SheepModel, agent_step: EngineAgentStep, model_step: EngineModelS
     return pd.DataFrame(arows), pd.DataFrame(mrows)
 
 
+# ---- what plot_abm_model reads ------------------------------------------------------------------------------------
+
+def grasscolor(model: SheepModel):
+    """`grasscolor(model) = model.countdown ./ model.regrowth_time` — the `heatarray` of `plot_abm_model`
+    (src/plotting.jl:33, :27-57), shape (ny, nx), 1.0 = just eaten / fully grown, towards 0 = about to regrow."""
+    return model.countdown.astype(np.float64) / float(model.regrowth_time)
+
+
+def plot_data(model: SheepModel):
+    """Everything `plot_abm_model` draws, fetched from the device in one go: sheep positions (x, y; 1-based, for the
+    scatter) and the grass heat array.  The GUI itself (Makie) stays on the host side and out of scope."""
+    _, x, y, _ = model.agents()
+    return dict(x=x, y=y, heatarray=grasscolor(model), colorrange=(0.0, 1.0))
+
+
 # ---- initialize_model --------------------------------------------------------------------------------------------
 
 def initialize_model(*, n_sheep=40, griddims=(80, 80), regrowth_time=30, delta_energy_sheep=4, sheep_reproduce=0.001, movement_cost=1,

@@ -100,3 +100,13 @@ def test_initialize_model_on_the_device(emu, oracle):
     assert wm[ya - 1, xa - 1].all()
     A.step(m, A.herbivore_dynamics(walk_type=A.WalkType.RANDOM_WALK), A.grass_growth_dynamics(), 1)  # new engine, same world
     assert m.tick == 5 and m.nagents() > 0
+
+
+def test_plot_data_matches_the_reference_heat_array(emu):
+    """`plot_abm_model` draws `countdown ./ regrowth_time` and the sheep positions (src/plotting.jl:27-57)."""
+    m, astep, mstep = _script_model(emu, "v0.1")
+    A.step(m, astep, mstep, 3)
+    d = A.plot_data(m)
+    assert d["heatarray"].shape == (m.ny, m.nx) and d["heatarray"].min() >= 0 and d["heatarray"].max() <= 1
+    assert np.array_equal(d["heatarray"], m.countdown / m.regrowth_time)
+    assert d["x"].size == m.nagents() and d["x"].min() >= 1 and d["y"].max() <= m.ny
