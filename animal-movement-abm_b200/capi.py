@@ -76,6 +76,7 @@ _P = C.c_void_p
 _I64P = C.POINTER(C.c_int64)
 _U8P = C.POINTER(C.c_uint8)
 _F64P = C.POINTER(C.c_double)
+_U32P = C.POINTER(C.c_uint32)
 
 # name -> (restype, argtypes); mirrors include/abm.h one to one
 SIGNATURES = {
@@ -92,6 +93,10 @@ SIGNATURES = {
     "count_agents": (C.c_int, [_P, _I64P]),
     "get_agents": (C.c_int, [_P, _I64P, _I64P, _I64P, _I64P, _F64P]),
     "get_grid": (C.c_int, [_P, _U8P, _I64P]),
+    "set_grass_packed": (C.c_int, [_P, _U8P]),
+    "get_grass_packed": (C.c_int, [_P, _U8P]),
+    "set_agents_packed": (C.c_int, [_P, C.c_int64, _U32P, _U32P, _F64P, C.c_int64]),
+    "get_agents_packed": (C.c_int, [_P, _I64P, _U32P, _U32P, _F64P]),
     "reduce": (C.c_int, [_P, C.c_int32, _F64P]),
     "plan_routes": (C.c_int, [_P, C.c_int64, _I64P, _I64P, _I64P]),
     "get_paths": (C.c_int, [_P, C.c_int64, _I64P, _I64P, _I64P, _I64P, _I64P, _I64P]),
@@ -235,6 +240,42 @@ class Engine:
             fg, cd = out
         self._ck(self.lib.fn["get_grid"](self.h, _ptr(fg, _U8P), _ptr(cd, _I64P)))
         return fg, cd
+
+    # narrow transfer forms: one grass byte per cell (fully_grown << 7 | countdown), agents as (id u32, x | y << 16, energy)
+    def set_grass_packed(self, state):
+        st = np.ascontiguousarray(state, dtype=np.uint8).reshape(-1)
+        if st.size != self.nx * self.ny:
+            raise ValueError("grid array has the wrong size")
+        self._ck(self.lib.fn["set_grass_packed"](self.h, _ptr(st, _U8P)))
+
+    def get_grass_packed(self, out=None):
+        st = np.empty((self.ny, self.nx), np.uint8) if out is None else out
+        self._ck(self.lib.fn["get_grass_packed"](self.h, _ptr(st, _U8P)))
+        return st
+
+    def set_agents_packed(self, ids, xy, energy, next_id=None):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        xy = np.ascontiguousarray(xy, dtype=np.uint32)
+        e = np.ascontiguousarray(energy, dtype=np.float64)
+        n = ids.size
+        if not (xy.size == e.size == n):
+            raise ValueError("agent arrays differ in length")
+        if next_id is None:
+            next_id = int(ids.max()) + 1 if n else 1
+        self._ck(self.lib.fn["set_agents_packed"](self.h, n, _ptr(ids, _U32P), _ptr(xy, _U32P), _ptr(e, _F64P), int(next_id)))
+
+    def get_agents_packed(self, out=None):
+        """ids (u32), x | y << 16 (u32), energy in id order; `out`: optional (ids, xy, energy) buffers."""
+        n = self.count_agents()
+        if out is None:
+            ids = np.empty(n, np.uint32); xy = np.empty(n, np.uint32); e = np.empty(n, np.float64)
+        else:
+            ids, xy, e = out
+            if min(ids.size, xy.size, e.size) < n:
+                raise AbmError(ABM_E_SMALL, f"agent buffers hold fewer than {n} entries")
+        cap = C.c_int64(ids.size)
+        self._ck(self.lib.fn["get_agents_packed"](self.h, C.byref(cap), _ptr(ids, _U32P), _ptr(xy, _U32P), _ptr(e, _F64P)))
+        return ids[:n], xy[:n], e[:n]
 
     def reduce(self, what: int) -> float:
         out = C.c_double()

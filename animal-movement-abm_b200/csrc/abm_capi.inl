@@ -243,13 +243,19 @@ static int stage_agents(abm_handle* h, int64_t n) { return ensure(h, h->stage, (
 /* the agent records waiting in the staging buffer become the population: validated, converted to the SoA and grouped by
  * cell (general path) or by 8x8 sub-tile (tile path).  Shared by abm_set_agents (records copied from the host) and
  * abm_init_random (records generated on the device). */
-static int ingest_staged(abm_handle* h, int64_t n, int64_t next_id) {
+static int ingest_staged(abm_handle* h, int64_t n, int64_t next_id, bool packed = false) {
   int rc;
   const Geo& g = h->g;
   int64_t* s_id = (int64_t*)h->stage.p;
   int64_t* s_x = s_id + n;
   int64_t* s_y = s_x + n;
   double* s_e = (double*)(s_y + n);
+  const uint32_t* p_id = nullptr; const uint32_t* p_xy = nullptr;
+  if (packed) { /* abm_set_agents_packed staged [energy f64 x n][id u32 x n][x | y << 16 u32 x n] */
+    s_e = (double*)h->stage.p;
+    p_id = (const uint32_t*)(s_e + n); p_xy = p_id + n;
+    s_id = s_x = s_y = nullptr;
+  }
   const int tmp = h->cur ^ 1, dst = h->cur;
   if ((rc = ensure_soa(h, tmp, n))) return rc;
   if ((rc = ensure_soa(h, dst, n))) return rc;
@@ -266,7 +272,7 @@ static int ingest_staged(abm_handle* h, int64_t n, int64_t next_id) {
     if (n > 0) {
       if ((rc = ensure(h, h->ingest_sub, (size_t)n * 4))) return rc;
       IngestTileBody ib;
-      ib.g = g; ib.nsx = h->nsx; ib.hid = s_id; ib.hx = s_x; ib.hy = s_y; ib.he = s_e; ib.next_id = next_id;
+      ib.g = g; ib.nsx = h->nsx; ib.hid = s_id; ib.hx = s_x; ib.hy = s_y; ib.he = s_e; ib.pid = p_id; ib.pxy = p_xy; ib.next_id = next_id;
       ib.cell = (uint32_t*)h->cell[tmp].p; ib.id = (uint32_t*)h->id[tmp].p; ib.energy = (double*)h->energy[tmp].p;
       ib.slot = (uint32_t*)h->slot.p; ib.sub = (uint32_t*)h->ingest_sub.p; ib.sub_cnt = scnt;
       ib.alive_bits = (uint32_t*)h->bits.p; ib.err = (uint32_t*)h->counters.p + CTR_ERR;
@@ -288,7 +294,7 @@ static int ingest_staged(abm_handle* h, int64_t n, int64_t next_id) {
   if (!h->tile_mode) ABM_CK(h, dev_memset(start, 0, ((size_t)g.gt + 1) * 4, h->stream));
   if (n > 0 && !h->tile_mode) {
     IngestBody ib;
-    ib.g = g; ib.hid = s_id; ib.hx = s_x; ib.hy = s_y; ib.he = s_e; ib.next_id = next_id;
+    ib.g = g; ib.hid = s_id; ib.hx = s_x; ib.hy = s_y; ib.he = s_e; ib.pid = p_id; ib.pxy = p_xy; ib.next_id = next_id;
     ib.cell = (uint32_t*)h->cell[tmp].p; ib.id = (uint32_t*)h->id[tmp].p; ib.energy = (double*)h->energy[tmp].p;
     ib.state = (uint8_t*)h->state.p; ib.slot = (uint32_t*)h->slot.p;
     ib.new_count = start; ib.alive_bits = (uint32_t*)h->bits.p; ib.err = (uint32_t*)h->counters.p + CTR_ERR;
@@ -334,12 +340,80 @@ int ABM_API(set_agents)(abm_handle* h, int64_t n, const int64_t* id, const int64
   if ((rc = stage_agents(h, n))) return rc;
   if (n > 0) {
     int64_t* s_id = (int64_t*)h->stage.p;
-    ABM_CK(h, copy_h2d(s_id, id, (size_t)n * 8, h->stream));
-    ABM_CK(h, copy_h2d(s_id + n, x, (size_t)n * 8, h->stream));
-    ABM_CK(h, copy_h2d(s_id + 2 * n, y, (size_t)n * 8, h->stream));
-    ABM_CK(h, copy_h2d(s_id + 3 * n, energy, (size_t)n * 8, h->stream));
+    ABM_CK(h, copy_h2d_async(s_id, id, (size_t)n * 8, h->stream)); /* ingest_staged ends with a synchronising read-back */
+    ABM_CK(h, copy_h2d_async(s_id + n, x, (size_t)n * 8, h->stream));
+    ABM_CK(h, copy_h2d_async(s_id + 2 * n, y, (size_t)n * 8, h->stream));
+    ABM_CK(h, copy_h2d_async(s_id + 3 * n, energy, (size_t)n * 8, h->stream));
   }
-  return ingest_staged(h, n, next_id);
+  rc = ingest_staged(h, n, next_id);
+  if (rc) stream_sync(h->stream);
+  return rc;
+}
+
+int ABM_API(set_agents_packed)(abm_handle* h, int64_t n, const uint32_t* id, const uint32_t* xy, const double* energy, int64_t next_id) {
+  if (!h) return ABM_E_BADARG;
+  if (n < 0 || (n > 0 && (!id || !xy || !energy))) ABM_FAIL(h, ABM_E_BADARG, "null agent arrays");
+  if (next_id < 1 || next_id > 0xFFFFFFFFll || n >= 0xFFFFFFF0ll) ABM_FAIL(h, ABM_E_CAPACITY, "next_id must be in 1..2^32-1");
+  if (h->cfg.nx > 65535 || h->cfg.ny > 65535) ABM_FAIL(h, ABM_E_BADARG, "packed agent records hold 16-bit coordinates: grid dims must be <= 65535");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if ((rc = stage_agents(h, n))) return rc;
+  if (n > 0) { /* three copies enqueued back to back, one synchronisation */
+    double* s_e = (double*)h->stage.p;
+    uint32_t* s_id = (uint32_t*)(s_e + n);
+    ABM_CK(h, copy_h2d_async(s_e, energy, (size_t)n * 8, h->stream));
+    ABM_CK(h, copy_h2d_async(s_id, id, (size_t)n * 4, h->stream));
+    ABM_CK(h, copy_h2d_async(s_id + n, xy, (size_t)n * 4, h->stream));
+  }
+  rc = ingest_staged(h, n, next_id, true);
+  if (rc) stream_sync(h->stream); /* the host buffers must not be in flight when the caller gets them back */
+  return rc;
+}
+
+/* the grass bytes alone: the terrain (walkmap, elevation) given to abm_set_grid stays */
+int ABM_API(set_grass_packed)(abm_handle* h, const uint8_t* state) {
+  if (!h || !state) return ABM_E_BADARG;
+  int rc = set_device(h);
+  if (rc) return rc;
+  const Geo& g = h->g;
+  const uint64_t cells = (uint64_t)g.nx * (uint64_t)g.ny;
+  if (!h->grid_set) { /* no terrain was given: every cell walkable, elevation 0 (as abm_set_grid with NULL walkmap) */
+    ABM_CK(h, dev_memset(h->grass.p, GRASS_PAD, g.gt, h->stream));
+    ABM_CK(h, dev_memset(h->walkbits.p, 0, (size_t)g.gt / 8, h->stream));
+    h->comp_valid = false;
+  }
+  const bool open_terrain = !h->grid_set;
+  if ((rc = ensure(h, h->stage, cells + 64))) return rc;
+  uint32_t* err = (uint32_t*)h->counters.p + CTR_ERR;
+  ABM_CK(h, dev_memset(err, 0, 4, h->stream));
+  ABM_CK(h, copy_h2d_async(h->stage.p, state, cells, h->stream));
+  GrassPackedBody gb;
+  gb.g = g; gb.grass = (uint8_t*)h->grass.p; gb.host = (uint8_t*)h->stage.p; gb.to_device = 1; gb.err = err; gb.open_walkbits = open_terrain ? (uint32_t*)h->walkbits.p : nullptr;
+  launch_foreach(h->stream, gb, (uint64_t)((g.nx + 3) / 4) * (uint64_t)g.ny);
+  if ((rc = check_launch(h, "grass import"))) return rc;
+  if ((rc = read_counters(h))) return rc;
+  if (h->h_counters[CTR_ERR]) {
+    ABM_CK(h, dev_memset(err, 0, 4, h->stream));
+    ABM_FAIL(h, ABM_E_BADARG, "countdown must be in 0..126");
+  }
+  h->grid_set = true;
+  return ABM_OK;
+}
+
+int ABM_API(get_grass_packed)(abm_handle* h, uint8_t* state) {
+  if (!h || !state) return ABM_E_BADARG;
+  if (!h->grid_set) ABM_FAIL(h, ABM_E_STATE, "abm_set_grid has not been called");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const Geo& g = h->g;
+  const uint64_t cells = (uint64_t)g.nx * (uint64_t)g.ny;
+  if ((rc = ensure(h, h->stage, cells + 64))) return rc;
+  GrassPackedBody gb;
+  gb.g = g; gb.grass = (uint8_t*)h->grass.p; gb.host = (uint8_t*)h->stage.p; gb.to_device = 0; gb.err = nullptr; gb.open_walkbits = nullptr;
+  launch_foreach(h->stream, gb, (uint64_t)((g.nx + 3) / 4) * (uint64_t)g.ny);
+  if ((rc = check_launch(h, "grass export"))) return rc;
+  ABM_CK(h, copy_d2h(state, h->stage.p, cells, h->stream));
+  return ABM_OK;
 }
 
 /* the random part of initialize_model, built on the device (include/abm.h) */
@@ -390,7 +464,7 @@ int ABM_API(count_agents)(abm_handle* h, int64_t* n) {
   return ABM_OK;
 }
 
-int ABM_API(get_agents)(abm_handle* h, int64_t* n_inout, int64_t* id, int64_t* x, int64_t* y, double* energy) {
+static int export_agents(abm_handle* h, int64_t* n_inout, int64_t* id, int64_t* x, int64_t* y, double* energy, uint32_t* pid, uint32_t* pxy, bool packed) {
   if (!h || !n_inout) return ABM_E_BADARG;
   const int64_t n = (int64_t)h->n;
   if (*n_inout < n) { *n_inout = n; ABM_FAIL(h, ABM_E_SMALL, "agent buffers hold %lld entries, %lld needed", (long long)*n_inout, (long long)n); }
@@ -410,18 +484,36 @@ int ABM_API(get_agents)(abm_handle* h, int64_t* n_inout, int64_t* id, int64_t* x
   int64_t* s_x = s_id + n;
   int64_t* s_y = s_x + n;
   double* s_e = (double*)(s_y + n);
+  uint32_t* sp_id = nullptr;
+  if (packed) { s_e = (double*)h->stage.p; sp_id = (uint32_t*)(s_e + n); s_id = s_x = s_y = nullptr; }
   ExportBody eb;
   eb.g = h->g;
   eb.cell = (const uint32_t*)h->cell[h->cur].p; eb.id = (const uint32_t*)h->id[h->cur].p; eb.energy = (const double*)h->energy[h->cur].p;
   eb.alive_bits = (const uint32_t*)h->bits.p; eb.prefix = (const uint32_t*)h->bits_prefix.p;
-  eb.oid = s_id; eb.ox = s_x; eb.oy = s_y; eb.oe = s_e;
+  eb.oid = s_id; eb.ox = s_x; eb.oy = s_y; eb.oe = s_e; eb.pid = sp_id; eb.pxy = sp_id ? sp_id + n : nullptr;
   launch_foreach(h->stream, eb, (uint64_t)n);
   if ((rc = check_launch(h, "export"))) return rc;
-  if (id) ABM_CK(h, copy_d2h(id, s_id, (size_t)n * 8, h->stream));
-  if (x) ABM_CK(h, copy_d2h(x, s_x, (size_t)n * 8, h->stream));
-  if (y) ABM_CK(h, copy_d2h(y, s_y, (size_t)n * 8, h->stream));
-  if (energy) ABM_CK(h, copy_d2h(energy, s_e, (size_t)n * 8, h->stream));
+  /* the copies are enqueued back to back and waited for once */
+  if (packed) {
+    if (pid) ABM_CK(h, copy_d2h_async(pid, sp_id, (size_t)n * 4, h->stream));
+    if (pxy) ABM_CK(h, copy_d2h_async(pxy, sp_id + n, (size_t)n * 4, h->stream));
+  } else {
+    if (id) ABM_CK(h, copy_d2h_async(id, s_id, (size_t)n * 8, h->stream));
+    if (x) ABM_CK(h, copy_d2h_async(x, s_x, (size_t)n * 8, h->stream));
+    if (y) ABM_CK(h, copy_d2h_async(y, s_y, (size_t)n * 8, h->stream));
+  }
+  if (energy) ABM_CK(h, copy_d2h_async(energy, s_e, (size_t)n * 8, h->stream));
+  ABM_CK(h, stream_sync(h->stream));
   return ABM_OK;
+}
+
+int ABM_API(get_agents)(abm_handle* h, int64_t* n_inout, int64_t* id, int64_t* x, int64_t* y, double* energy) {
+  return export_agents(h, n_inout, id, x, y, energy, nullptr, nullptr, false);
+}
+
+int ABM_API(get_agents_packed)(abm_handle* h, int64_t* n_inout, uint32_t* id, uint32_t* xy, double* energy) {
+  if (h && (h->cfg.nx > 65535 || h->cfg.ny > 65535)) ABM_FAIL(h, ABM_E_BADARG, "packed agent records hold 16-bit coordinates: grid dims must be <= 65535");
+  return export_agents(h, n_inout, nullptr, nullptr, nullptr, energy, id, xy, true);
 }
 
 int ABM_API(set_global_state)(abm_handle* h, int64_t tick, int64_t behav, int64_t behav_counter) {

@@ -753,10 +753,19 @@ struct IdIndexBody { /* id -> position in the cell-sorted arrays */
 
 /* ---------------------------------------------------------------------------------------- boundary helpers */
 
+/* one agent record of the host: wide (abm_set_agents: id, x, y as int64) or packed (abm_set_agents_packed: id u32,
+ * x | y << 16); y becomes the stored row (global y minus the strip offset) */
+ABM_HD void host_record(const int64_t* hid, const int64_t* hx, const int64_t* hy, const uint32_t* pid, const uint32_t* pxy,
+                        const Geo& g, uint64_t i, int64_t& a, int64_t& x, int64_t& y) {
+  if (pid) { const uint32_t q = pxy[i]; a = (int64_t)pid[i]; x = (int64_t)(q & 0xFFFFu); y = (int64_t)(q >> 16) - g.y_off; }
+  else { a = hid[i]; x = hx[i]; y = hy[i] - g.y_off; }
+}
+
 /* abm_set_agents: host records -> unsorted SoA + counting-sort bookkeeping */
 struct IngestBody {
   Geo g;
   const int64_t* hid; const int64_t* hx; const int64_t* hy; const double* he;
+  const uint32_t* pid; const uint32_t* pxy; /* abm_set_agents_packed: id, x | y << 16 (else null) */
   int64_t next_id;
   uint32_t* cell; uint32_t* id; double* energy; uint8_t* state; uint32_t* slot;
   uint32_t* new_count;
@@ -764,7 +773,8 @@ struct IngestBody {
   uint32_t* err;
 
   ABM_HD void operator()(uint64_t i) const {
-    const int64_t x = hx[i], y = hy[i] - g.y_off, a = hid[i];
+    int64_t x, y, a;
+    host_record(hid, hx, hy, pid, pxy, g, i, a, x, y);
     if (x < 1 || x > g.nx || y < 1 + g.own_lo || y > g.own_hi || a < 1 || a >= next_id) { atomic_or(err, ERR_INTERNAL); cell[i] = 0; id[i] = 0; energy[i] = 0; state[i] = ST_DEAD; return; }
     const uint32_t c = enc(g, (int)(x - 1), (int)(y - 1));
     const uint32_t bit = 1u << ((uint32_t)a & 31);
@@ -786,6 +796,7 @@ struct ExportBody {
   const uint32_t* cell; const uint32_t* id; const double* energy;
   const uint32_t* alive_bits; const uint32_t* prefix;
   int64_t* oid; int64_t* ox; int64_t* oy; double* oe;
+  uint32_t* pid; uint32_t* pxy; /* abm_get_agents_packed: id, x | y << 16 instead of oid/ox/oy (else null) */
 
   ABM_HD void operator()(uint64_t i) const {
     const uint32_t a = id[i];
@@ -793,7 +804,9 @@ struct ExportBody {
     const uint32_t rank = prefix[w] + (uint32_t)popc(alive_bits[w] & ((1u << (a & 31)) - 1u));
     int x, y;
     dec(g, cell[i], x, y);
-    oid[rank] = a; ox[rank] = x + 1; oy[rank] = y + g.y_off + 1; oe[rank] = energy[i];
+    if (pid) { pid[rank] = a; pxy[rank] = (uint32_t)(x + 1) | ((uint32_t)(y + g.y_off + 1) << 16); }
+    else { oid[rank] = a; ox[rank] = x + 1; oy[rank] = y + g.y_off + 1; }
+    oe[rank] = energy[i];
   }
 };
 
@@ -870,6 +883,32 @@ struct GridExportBody {
     const uint8_t s = grass[enc(g, (int)x, (int)(row0 + yy))];
     if (fg) fg[i] = (s & GRASS_GROWN) ? 1 : 0;
     if (cd) cd[i] = s & 0x7F;
+  }
+};
+
+/* abm_set_grass_packed / abm_get_grass_packed: the grass bytes (bit 7 = fully_grown, bits 0..6 = countdown) between the
+ * host's column-major array (x fastest) and the tile-major array; four cells of one row per thread */
+struct GrassPackedBody {
+  Geo g;
+  uint8_t* grass;        /* tile-major */
+  uint8_t* host;         /* nx * ny, x fastest (staged on the device) */
+  int32_t to_device;
+  uint32_t* err;
+  uint32_t* open_walkbits; /* import without terrain: every cell of the grid becomes walkable (else null) */
+  ABM_HD void operator()(uint64_t i) const {
+    const uint64_t per_row = (uint64_t)(g.nx + 3) >> 2;
+    const uint64_t y = i / per_row, x0 = (i - y * per_row) << 2;
+    for (int k = 0; k < 4 && x0 + k < (uint64_t)g.nx; ++k) {
+      const uint32_t c = enc(g, (int)(x0 + k), (int)y);
+      const uint64_t l = y * (uint64_t)g.nx + x0 + k;
+      if (to_device) {
+        const uint8_t b = host[l];
+        if ((b & 0x7F) == GRASS_PAD) atomic_or(err, ERR_INTERNAL);
+        grass[c] = b;
+        if (open_walkbits) atomic_or(&open_walkbits[c >> 5], 1u << (c & 31));
+      }
+      else host[l] = grass[c];
+    }
   }
 };
 

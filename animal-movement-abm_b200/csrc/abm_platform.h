@@ -102,6 +102,8 @@ static inline abm_err_t dev_memset(void* p, int v, size_t bytes, abm_stream_t) {
 static inline abm_err_t copy_h2d(void* d, const void* h, size_t bytes, abm_stream_t) { memcpy(d, h, bytes); return 0; }
 static inline abm_err_t copy_d2h(void* h, const void* d, size_t bytes, abm_stream_t) { memcpy(h, d, bytes); return 0; }
 static inline abm_err_t copy_d2d(void* d, const void* s, size_t bytes, abm_stream_t) { memmove(d, s, bytes); return 0; }
+static inline abm_err_t copy_h2d_async(void* d, const void* h, size_t bytes, abm_stream_t) { memcpy(d, h, bytes); return 0; }
+static inline abm_err_t copy_d2h_async(void* h, const void* d, size_t bytes, abm_stream_t) { memcpy(h, d, bytes); return 0; }
 static inline abm_err_t stream_sync(abm_stream_t) { return 0; }
 static inline const char* err_string(abm_err_t e) { return e ? "emulated allocation failure" : "ok"; }
 
@@ -220,6 +222,9 @@ static inline abm_err_t copy_d2h(void* h, const void* d, size_t bytes, abm_strea
   abm_err_t e = cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s);
   return e != cudaSuccess ? e : cudaStreamSynchronize(s);
 }
+/* enqueue only: the caller synchronises the stream before it returns to the host program (host buffers are never retained) */
+static inline abm_err_t copy_h2d_async(void* d, const void* h, size_t bytes, abm_stream_t s) { return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s); }
+static inline abm_err_t copy_d2h_async(void* h, const void* d, size_t bytes, abm_stream_t s) { return cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s); }
 static inline abm_err_t copy_d2d(void* d, const void* src, size_t bytes, abm_stream_t s) {
   return cudaMemcpyAsync(d, src, bytes, cudaMemcpyDeviceToDevice, s);
 }

@@ -798,11 +798,13 @@ struct BirthIdBody {
 struct IngestTileBody {
   Geo g; int32_t nsx;
   const int64_t* hid; const int64_t* hx; const int64_t* hy; const double* he;
+  const uint32_t* pid; const uint32_t* pxy; /* abm_set_agents_packed (else null) */
   int64_t next_id;
   uint32_t* cell; uint32_t* id; double* energy; uint32_t* slot; uint32_t* sub;
   uint32_t* sub_cnt; uint32_t* alive_bits; uint32_t* err;
   ABM_HD void operator()(uint64_t i) const {
-    const int64_t x = hx[i], y = hy[i] - g.y_off, a = hid[i];
+    int64_t x, y, a;
+    host_record(hid, hx, hy, pid, pxy, g, i, a, x, y);
     if (x < 1 || x > g.nx || y < 1 + g.own_lo || y > g.own_hi || a < 1 || a >= next_id) { atomic_or(err, ERR_INTERNAL); cell[i] = 0; id[i] = 0; energy[i] = 0; sub[i] = NONE32; return; }
     const uint32_t bit = 1u << ((uint32_t)a & 31);
     if (atomic_or(&alive_bits[(uint32_t)a >> 5], bit) & bit) atomic_or(err, ERR_INTERNAL);

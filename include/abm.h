@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ABM_ABI_VERSION 2
+#define ABM_ABI_VERSION 3
 
 /* error codes */
 enum {
@@ -170,6 +170,19 @@ int abm_get_agents(abm_handle* h, int64_t* n_inout, int64_t* id, int64_t* x, int
 
 /* replaces: reading model.fully_grown / model.countdown (e.g. src/plotting.jl:27-57).  Either may be NULL. */
 int abm_get_grid(abm_handle* h, uint8_t* fully_grown, int64_t* countdown);
+
+/* Narrow forms of the four state transfers above, for hosts that round-trip the model every tick (abmplot/abmvideo step
+ * one tick per frame, scripts/v0.3.jl:124): 1 byte per cell and 16 bytes per agent instead of 9 and 32.
+ *   grass byte  = fully_grown << 7 | countdown (0..126)  — model.fully_grown[x,y] and model.countdown[x,y] in one byte;
+ *                 the terrain (walkmap, elevation) given to abm_set_grid is kept; without a previous abm_set_grid every
+ *                 cell is walkable and flat;
+ *   agent       = id (uint32), xy = x | y << 16 (1-based agent.pos; grid dims <= 65535), energy (double).
+ * Same layouts (x fastest; strip handles: strip_ny + 64 rows, global y), same validation, same id order on the way out. */
+int abm_set_grass_packed(abm_handle* h, const uint8_t* state);
+int abm_get_grass_packed(abm_handle* h, uint8_t* state);
+int abm_set_agents_packed(abm_handle* h, int64_t n, const uint32_t* id, const uint32_t* xy, const double* energy,
+                          int64_t next_id);
+int abm_get_agents_packed(abm_handle* h, int64_t* n_inout, uint32_t* id, uint32_t* xy, double* energy);
 
 /* replaces: adata/mdata aggregation inside Agents.run! (scripts/v0.6.jl:204-210) */
 int abm_reduce(abm_handle* h, int32_t what, double* out);

@@ -672,6 +672,42 @@ int oracle_get_grid(oracle_handle* h, uint8_t* fg, int64_t* cd) {
   }
   return 0;
 }
+/* the narrow transfer forms of include/abm.h, as conversions around the wide ones */
+int oracle_set_grass_packed(oracle_handle* h, const uint8_t* state) {
+  Model& m = h->m;
+  if (!state) return ABM_E_BADARG;
+  const size_t G = (size_t)m.nx * m.ny;
+  for (size_t i = 0; i < G; ++i) if ((state[i] & 0x7F) == 0x7F) return ABM_E_BADARG;
+  for (size_t i = 0; i < G; ++i) { m.fully_grown[i] = state[i] >> 7; m.countdown[i] = state[i] & 0x7F; }
+  m.grid_set = true;
+  return 0;
+}
+int oracle_get_grass_packed(oracle_handle* h, uint8_t* state) {
+  Model& m = h->m;
+  const size_t G = (size_t)m.nx * m.ny;
+  for (size_t i = 0; i < G; ++i) state[i] = (uint8_t)((m.fully_grown[i] ? 0x80 : 0) | (m.countdown[i] & 0x7F));
+  return 0;
+}
+int oracle_set_agents_packed(oracle_handle* h, int64_t n, const uint32_t* id, const uint32_t* xy, const double* e, int64_t next_id) {
+  if (h->m.nx > 65535 || h->m.ny > 65535) return ABM_E_BADARG;
+  std::vector<int64_t> a((size_t)n), x((size_t)n), y((size_t)n);
+  for (i64 i = 0; i < n; ++i) { a[i] = id[i]; x[i] = xy[i] & 0xFFFFu; y[i] = xy[i] >> 16; }
+  return oracle_set_agents(h, n, a.data(), x.data(), y.data(), e, next_id);
+}
+int oracle_get_agents_packed(oracle_handle* h, int64_t* n_inout, uint32_t* id, uint32_t* xy, double* e) {
+  Model& m = h->m;
+  if (m.nx > 65535 || m.ny > 65535) return ABM_E_BADARG;
+  const i64 n = (i64)m.agents.size();
+  if (*n_inout < n) { *n_inout = n; return ABM_E_SMALL; }
+  i64 i = 0;
+  for (std::map<i64, Sheep>::iterator it = m.agents.begin(); it != m.agents.end(); ++it, ++i) {
+    if (id) id[i] = (uint32_t)it->first;
+    if (xy) xy[i] = (uint32_t)it->second.x | ((uint32_t)it->second.y << 16);
+    if (e) e[i] = it->second.energy;
+  }
+  *n_inout = n;
+  return 0;
+}
 int oracle_reduce(oracle_handle* h, int32_t what, double* out) {
   Model& m = h->m;
   double v = 0;

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from cases import CASES, build_case
-from conftest import ROOT, assert_same_state, load_case
+from conftest import ROOT, assert_same_state, capi, load_case, make_case
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -460,3 +460,47 @@ def test_gpu_device_side_initialisation(libabm, oracle, nx, ny, n, wt, terrain):
         a.step(1)
         b.step(1)
         assert_same_state(b.snapshot(), a.snapshot(), f"tick {t} after init")
+
+
+# ------------------------------------------------------------------ narrow transfer forms (abm_*_packed)
+
+def _check_packed_round_trip(lib, oracle):
+    """abm_set_grass_packed / abm_set_agents_packed feed the same world as the wide forms, the *_packed getters return the
+    same state, and a host that round-trips the model through them every tick stays on the oracle's trajectory."""
+    for walk_type, terrain, nx, ny in ((2, False, 96, 64), (4, True, 64, 96), (0, False, 33, 20)):
+        cfgkw, w = make_case(nx, ny, nx * ny // 4, walk_type, 1 if walk_type else 0, seed=77, terrain=terrain, visual_distance=3, reproduction_prob=0.02,
+                             walkmap_regrowth=1 if terrain else 0)
+        ref = load_case(oracle, cfgkw, w)
+        e = load_case(lib, cfgkw, w)  # terrain through the wide abm_set_grid
+        st = (w["fully_grown"].astype(np.uint8) << 7) | w["countdown"].astype(np.uint8)
+        for tick in range(4):
+            e.set_grass_packed(st)
+            if tick == 0:
+                e.set_agents_packed(w["ids"], w["x"].astype(np.uint32) | (w["y"].astype(np.uint32) << 16), w["energy"])
+            else:
+                e.set_agents_packed(ids, xy, en, nid)
+            e.set_global_state(tick)
+            e.step(1)
+            ref.step(1)
+            ids, xy, en = e.get_agents_packed()
+            st = e.get_grass_packed()
+            nid = e.get_global_state()["next_id"]
+            o = ref.snapshot()
+            assert np.array_equal(ids, o["ids"]) and np.array_equal(xy & 0xFFFF, o["x"]) and np.array_equal(xy >> 16, o["y"]), (walk_type, tick)
+            assert np.array_equal(en, o["energy"]) and nid == o["next_id"]
+            assert np.array_equal(st >> 7, o["fully_grown"]) and np.array_equal(st & 0x7F, o["countdown"])
+        # the oracle's own packed forms agree with its wide ones
+        oi, oxy, oe = ref.get_agents_packed()
+        assert np.array_equal(oi, ids) and np.array_equal(oxy, xy) and np.array_equal(ref.get_grass_packed(), st)
+        with pytest.raises(capi.AbmError):
+            e.set_grass_packed(np.full((ny, nx), 0x7F, np.uint8))  # countdown 127 is the padding value
+        e.close(); ref.close()
+
+
+def test_packed_transfer_forms_emulated(emu, oracle):
+    _check_packed_round_trip(emu, oracle)
+
+
+@pytest.mark.gpu
+def test_gpu_packed_transfer_forms(libabm, oracle):
+    _check_packed_round_trip(libabm, oracle)
