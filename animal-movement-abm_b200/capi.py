@@ -86,6 +86,7 @@ SIGNATURES = {
     "set_grid": (C.c_int, [_P, _U8P, _I64P, _U8P, _I64P]),
     "set_agents": (C.c_int, [_P, C.c_int64, _I64P, _I64P, _I64P, _F64P, C.c_int64]),
     "init_random": (C.c_int, [_P, C.c_int64, C.c_uint64]),
+    "set_global_walkmap_bits": (C.c_int, [_P, _U32P]),
     "set_global_state": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64]),
     "get_global_state": (C.c_int, [_P, _I64P, _I64P, _I64P, _I64P]),
     "set_weight_lut": (C.c_int, [_P, _F64P, C.c_int32]),
@@ -174,8 +175,8 @@ class Engine:
     # grids are (ny, nx) C-ordered numpy arrays == Julia (nx, ny) column-major: a[y, x]
     def set_grid(self, fully_grown, countdown, walkmap=None, elevation=None):
         G = self.nx * self.ny
-        fg = np.ascontiguousarray(fully_grown, dtype=np.uint8).reshape(-1)
-        cd = np.ascontiguousarray(countdown, dtype=np.int64).reshape(-1)
+        fg = None if fully_grown is None else np.ascontiguousarray(fully_grown, dtype=np.uint8).reshape(-1)
+        cd = None if countdown is None else np.ascontiguousarray(countdown, dtype=np.int64).reshape(-1)
         wm = None if walkmap is None else np.ascontiguousarray(walkmap, dtype=np.uint8).reshape(-1)
         el = None if elevation is None else np.ascontiguousarray(elevation, dtype=np.int64).reshape(-1)
         for a in (fg, cd, wm, el):
@@ -198,6 +199,22 @@ class Engine:
     def init_random(self, n_sheep, init_seed):
         """The random part of `initialize_model`, built by the engine itself (abm_init_random)."""
         self._ck(self.lib.fn["init_random"](self.h, int(n_sheep), int(init_seed)))
+
+    def set_global_walkmap(self, walkmap):
+        """Strip handles: the walkmap of the whole GridSpace ((ny, nx) array of 0/1), packed to one bit per cell."""
+        if walkmap is None:
+            self._ck(self.lib.fn["set_global_walkmap_bits"](self.h, None))
+            return
+        bits = np.packbits(np.ascontiguousarray(walkmap, dtype=np.uint8).reshape(-1) != 0, bitorder="little")
+        bits = np.concatenate([bits, np.zeros((-bits.size) % 4, np.uint8)]).view(np.uint32)
+        self._ck(self.lib.fn["set_global_walkmap_bits"](self.h, _ptr(bits, _U32P)))
+
+    def set_global_walkmap_bits(self, bits):
+        """The same from bits the caller packed already (uint32 words, bit l & 31 of word l >> 5, l = (y-1)*nx + (x-1))."""
+        bits = np.ascontiguousarray(bits, dtype=np.uint32).reshape(-1)
+        if bits.size * 32 < self.cfg.nx * self.cfg.ny:
+            raise ValueError("global walkmap bits are too short")
+        self._ck(self.lib.fn["set_global_walkmap_bits"](self.h, _ptr(bits, _U32P)))
 
     def set_global_state(self, tick=0, behav=0, behav_counter=0):
         self._ck(self.lib.fn["set_global_state"](self.h, int(tick), int(behav), int(behav_counter)))

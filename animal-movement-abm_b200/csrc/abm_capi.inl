@@ -60,13 +60,13 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
       delete h; return ABM_E_CUDA;
     }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost((void**)&h->h_counters, CTR_WORDS * sizeof(uint32_t)) != cudaSuccess) {
+        cudaMallocHost((void**)&h->h_counters, 2 * CTR_WORDS * sizeof(uint32_t)) != cudaSuccess) {
       g_create_error = "stream / pinned memory creation failed";
       delete h; return ABM_E_CUDA;
     }
   }
 #else
-  h->h_counters = (uint32_t*)calloc(CTR_WORDS, sizeof(uint32_t));
+  h->h_counters = (uint32_t*)calloc(2 * CTR_WORDS, sizeof(uint32_t));
 #endif
   h->tm_total.init();
   h->strip = cfg->n_ranks > 1 || cfg->strip_ny > 0;
@@ -100,6 +100,9 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
   h->tile_mode = h->strip || (cfg->reserved0 != 1 && cfg->walk_type != ABM_ALTERNATED_WALK && cfg->nx % CORE == 0 && cfg->ny % CORE == 0 &&
                              cfg->nx >= 2 * CORE && cfg->ny >= 2 * CORE);
   h->nsx = g.nx / SUB; h->nsy = g.ny / SUB;
+  h->stream_mode = h->tile_mode && stream_rule(*cfg) && h->n_ranks <= STREAM_MAX_RANKS;
+  if (const char* sm = getenv("ABM_STREAM")) { if (atoi(sm) == 0) h->stream_mode = false; }
+  if (const char* sq = getenv("ABM_STREAM_CAP")) { const int q = atoi(sq); if (q >= 1 && q <= (1 << 20)) h->s_cap_forced = (uint32_t)q; }
   if (const char* mg = getenv("ABM_MIGRANTS")) h->use_migrants = atoi(mg) != 0;
   if (const char* ag = getenv("ABM_ASTAR_GB")) { const int q = atoi(ag); if (q >= 1 && q <= 160) h->astar_budget = (uint64_t)q << 30; }
   if (const char* bb = getenv("ABM_BIRTH_BITMAP")) h->birth_bitmap_from = (uint64_t)std::max(atoll(bb), 0ll);
@@ -170,10 +173,11 @@ int ABM_API(set_weight_lut)(abm_handle* h, const double* w, int32_t n) {
 
 int ABM_API(set_grid)(abm_handle* h, const uint8_t* fg, const int64_t* cd, const uint8_t* wm, const int64_t* el) {
   if (!h) return ABM_E_BADARG;
-  if (!fg || !cd) ABM_FAIL(h, ABM_E_BADARG, "fully_grown and countdown are required");
+  if ((fg == nullptr) != (cd == nullptr)) ABM_FAIL(h, ABM_E_BADARG, "fully_grown and countdown come together (both NULL: terrain only, the grass starts bare with countdown 0)");
   int rc = set_device(h);
   if (rc) return rc;
   const Geo& g = h->g;
+  if ((rc = stream_invalidate(h))) return rc; /* the filed steps were drawn on the old walkmap */
   ABM_CK(h, dev_memset(h->grass.p, GRASS_PAD, g.gt, h->stream));
   ABM_CK(h, dev_memset(h->walkbits.p, 0, (size_t)g.gt / 8, h->stream));
   h->comp_valid = false;
@@ -191,12 +195,12 @@ int ABM_API(set_grid)(abm_handle* h, const uint8_t* fg, const int64_t* cd, const
     int64_t* s_el = (int64_t*)(s + cells * 8);
     uint8_t* s_fg = s + cells * 16;
     uint8_t* s_wm = s + cells * 17;
-    ABM_CK(h, copy_h2d(s_cd, cd + off, cells * 8, h->stream));
-    ABM_CK(h, copy_h2d(s_fg, fg + off, cells, h->stream));
+    if (cd) ABM_CK(h, copy_h2d(s_cd, cd + off, cells * 8, h->stream));
+    if (fg) ABM_CK(h, copy_h2d(s_fg, fg + off, cells, h->stream));
     if (wm) ABM_CK(h, copy_h2d(s_wm, wm + off, cells, h->stream));
     if (el) ABM_CK(h, copy_h2d(s_el, el + off, cells * 8, h->stream));
     GridImportBody ib;
-    ib.g = g; ib.fg = s_fg; ib.cd = s_cd; ib.wm = wm ? s_wm : nullptr; ib.el = el ? s_el : nullptr;
+    ib.g = g; ib.fg = fg ? s_fg : nullptr; ib.cd = cd ? s_cd : nullptr; ib.wm = wm ? s_wm : nullptr; ib.el = el ? s_el : nullptr;
     ib.row0 = row0; ib.rows = rows;
     ib.grass = (uint8_t*)h->grass.p; ib.walkbits = (uint32_t*)h->walkbits.p; ib.elev = (int16_t*)h->elev.p;
     ib.err = (uint32_t*)h->counters.p + CTR_ERR;
@@ -210,6 +214,7 @@ int ABM_API(set_grid)(abm_handle* h, const uint8_t* fg, const int64_t* cd, const
     ABM_FAIL(h, ABM_E_BADARG, "countdown must be in 0..126 and elevation in -32768..32767");
   }
   h->grid_set = true;
+  h->has_walkmap = wm != nullptr;
   return ABM_OK;
 }
 
@@ -323,6 +328,7 @@ static int ingest_staged(abm_handle* h, int64_t n, int64_t next_id, bool packed 
   h->next_id = (uint64_t)next_id;
   h->agents_set = true;
   h->bcap_agreed = false;
+  h->s_lists = false; h->s_canon = true; h->s_parent_used = 0; /* stream path: the canonical SoA is the population now */
   /* a fresh population has no routes (pathfinder.agent_paths is empty) */
   if (h->rt_slot_of_id.p) ABM_CK(h, dev_memset(h->rt_slot_of_id.p, 0, h->rt_slot_of_id.bytes, h->stream));
   ABM_CK(h, dev_memset((uint32_t*)h->counters.p + CTR_ROUTE_SLOTS, 0, 4, h->stream));
@@ -417,14 +423,30 @@ int ABM_API(get_grass_packed)(abm_handle* h, uint8_t* state) {
 }
 
 /* the random part of initialize_model, built on the device (include/abm.h) */
+int ABM_API(set_global_walkmap_bits)(abm_handle* h, const uint32_t* bits) {
+  if (!h) return ABM_E_BADARG;
+  if (!h->strip) ABM_FAIL(h, ABM_E_STATE, "abm_set_global_walkmap_bits is for strip handles (a single handle already holds the whole walkmap)");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (!bits) { h->global_bits_set = false; return ABM_OK; }
+  const uint64_t words = ((uint64_t)h->cfg.nx * (uint64_t)h->cfg.ny + 31) / 32;
+  if ((rc = ensure(h, h->global_bits, words * 4))) return rc;
+  ABM_CK(h, copy_h2d(h->global_bits.p, bits, words * 4, h->stream));
+  h->global_bits_set = true;
+  return ABM_OK;
+}
+
 int ABM_API(init_random)(abm_handle* h, int64_t n_sheep, uint64_t init_seed) {
   if (!h) return ABM_E_BADARG;
-  if (h->strip) ABM_FAIL(h, ABM_E_BADARG, "abm_init_random is not available on a strip handle (placement needs the whole walkmap)");
   const int64_t span = (int64_t)(h->cfg.delta_energy * 5);
   if (n_sheep < 0 || n_sheep >= 0xFFFFFFF0ll) ABM_FAIL(h, ABM_E_CAPACITY, "n_sheep must be below 2^32-16");
   if (span < 1) ABM_FAIL(h, ABM_E_BADARG, "delta_energy * 5 must be at least 1 (energy = rand(1:delta_energy*5) - 1)");
+  if (h->strip && h->grid_set && h->has_walkmap && !h->global_bits_set)
+    ABM_FAIL(h, ABM_E_STATE, "abm_init_random on a strip handle with terrain needs the walkmap of the whole GridSpace first (abm_set_global_walkmap_bits): random_walkable draws positions over all strips");
+  if (h->strip && (h->cfg.nx > 65535 || h->cfg.ny > 65535)) ABM_FAIL(h, ABM_E_BADARG, "strip initialisation files 16-bit coordinates: grid dims must be <= 65535");
   int rc = set_device(h);
   if (rc) return rc;
+  if ((rc = stream_invalidate(h))) return rc;
   const Geo& g = h->g;
   uint32_t* err = (uint32_t*)h->counters.p + CTR_ERR;
   ABM_CK(h, dev_memset(err, 0, 4, h->stream));
@@ -434,19 +456,42 @@ int ABM_API(init_random)(abm_handle* h, int64_t n_sheep, uint64_t init_seed) {
     if ((rc = ensure(h, h->elev, (size_t)g.gt * 2))) return rc;
     ABM_CK(h, dev_memset(h->elev.p, 0, (size_t)g.gt * 2, h->stream));
     h->comp_valid = false;
+    if (h->strip) { /* the ghost rows of an open terrain are walkable too */
+      GhostWalkableBody gw;
+      gw.g = g; gw.walkbits = (uint32_t*)h->walkbits.p;
+      launch_foreach(h->stream, gw, (uint64_t)g.nx * (uint64_t)g.ny);
+    }
   }
   InitGrassBody gb;
   gb.g = g; gb.seed = init_seed; gb.regrowth_time = h->cfg.regrowth_time; gb.open_terrain = h->grid_set ? 0 : 1;
   gb.grass = (uint8_t*)h->grass.p; gb.walkbits = (uint32_t*)h->walkbits.p;
-  launch_foreach(h->stream, gb, (uint64_t)g.nx * (uint64_t)g.ny);
+  launch_foreach(h->stream, gb, (uint64_t)g.nx * (uint64_t)(g.own_hi - g.own_lo));
   if ((rc = check_launch(h, "grass initialisation"))) return rc;
+  const bool open_terrain = !h->grid_set;
   h->grid_set = true;
+  InitSheepBody sb;
+  memset(&sb, 0, sizeof sb);
+  sb.g = g; sb.seed = init_seed; sb.span = (uint64_t)span; sb.walkbits = (const uint32_t*)h->walkbits.p; sb.err = err;
+  if (h->strip) { /* every rank walks through all the sheep's draws and keeps the ones that land on its rows */
+    uint32_t* cursor = (uint32_t*)h->counters.p + CTR_CURSOR;
+    sb.strip = 1; sb.ny_global = h->cfg.ny; sb.global_bits = (!open_terrain && h->has_walkmap) ? (const uint32_t*)h->global_bits.p : nullptr;
+    sb.cursor = cursor;
+    ABM_CK(h, dev_memset(cursor, 0, 4, h->stream));
+    if (n_sheep > 0) launch_foreach(h->stream, sb, (uint64_t)n_sheep); /* pass 1: how many are mine */
+    if ((rc = check_launch(h, "sheep initialisation"))) return rc;
+    if ((rc = read_counters(h))) return rc;
+    if (h->h_counters[CTR_ERR] & ERR_NOWALKABLE) { ABM_CK(h, dev_memset(err, 0, 4, h->stream)); ABM_FAIL(h, ABM_E_NOWALKABLE, "random_walkable found no walkable cell in 4096 draws"); }
+    const int64_t mine = (int64_t)h->h_counters[CTR_CURSOR];
+    if ((rc = stage_agents(h, mine))) return rc;
+    sb.p_e = (double*)h->stage.p; sb.p_id = (uint32_t*)(sb.p_e + mine); sb.p_xy = sb.p_id + mine;
+    ABM_CK(h, dev_memset(cursor, 0, 4, h->stream));
+    if (n_sheep > 0) launch_foreach(h->stream, sb, (uint64_t)n_sheep); /* pass 2: file them */
+    if ((rc = check_launch(h, "sheep initialisation"))) return rc;
+    return ingest_staged(h, mine, n_sheep + 1, true);
+  }
   if ((rc = stage_agents(h, n_sheep))) return rc;
   if (n_sheep > 0) {
-    InitSheepBody sb;
-    sb.g = g; sb.seed = init_seed; sb.span = (uint64_t)span; sb.walkbits = (const uint32_t*)h->walkbits.p;
     sb.s_id = (int64_t*)h->stage.p; sb.s_x = sb.s_id + n_sheep; sb.s_y = sb.s_x + n_sheep; sb.s_e = (double*)(sb.s_y + n_sheep);
-    sb.err = err;
     launch_foreach(h->stream, sb, (uint64_t)n_sheep);
     if ((rc = check_launch(h, "sheep initialisation"))) return rc;
     if ((rc = read_counters(h))) return rc;
@@ -472,6 +517,7 @@ static int export_agents(abm_handle* h, int64_t* n_inout, int64_t* id, int64_t* 
   if (n == 0) return ABM_OK;
   int rc = set_device(h);
   if (rc) return rc;
+  if ((rc = stream_canonical(h))) return rc;
   const uint64_t words = bitmap_words(h->next_id);
   if ((rc = ensure(h, h->bits, (words + 4) * 4))) return rc;
   ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, h->stream));
@@ -519,6 +565,7 @@ int ABM_API(get_agents_packed)(abm_handle* h, int64_t* n_inout, uint32_t* id, ui
 int ABM_API(set_global_state)(abm_handle* h, int64_t tick, int64_t behav, int64_t behav_counter) {
   if (!h) return ABM_E_BADARG;
   if (tick < 0 || tick > 0xFFFFFFFFll) ABM_FAIL(h, ABM_E_BADARG, "tick must fit 32 bits");
+  if ((uint64_t)tick != h->tick) { int rc = stream_invalidate(h); if (rc) return rc; } /* the filed steps were drawn for another tick */
   if (h->cfg.walk_type == ABM_ALTERNATED_WALK && (behav < 0 || behav > 3 || behav_counter < 0 || behav_counter > h->cfg.counter))
     ABM_FAIL(h, ABM_E_BADARG, "behav must be in 0..3 and behav_counter in 0..counter");
   h->tick = (uint64_t)tick; h->behav = behav; h->behav_counter = behav_counter;
@@ -547,7 +594,7 @@ int ABM_API(step)(abm_handle* h, int64_t n_ticks) {
   h->tm_total.start(h->stream);
   for (int64_t t = 0; t < n_ticks; ++t) {
     if (h->tick >= 0xFFFFFFFFull) ABM_FAIL(h, ABM_E_CAPACITY, "tick counter exhausted");
-    if ((rc = h->tile_mode ? tick_tile(h) : tick_once(h))) return rc;
+    if ((rc = h->stream_mode ? tick_stream(h) : (h->tile_mode ? tick_tile(h) : tick_once(h)))) return rc;
   }
   h->tm_total.stop(h->stream);
   ABM_CK(h, stream_sync(h->stream));
@@ -557,18 +604,21 @@ int ABM_API(step)(abm_handle* h, int64_t n_ticks) {
   return ABM_OK;
 }
 
-int ABM_API(reduce)(abm_handle* h, int32_t what, double* out) {
-  if (!h || !out) return ABM_E_BADARG;
-  int rc = set_device(h);
-  if (rc) return rc;
+/* this handle's share of a reduction; `any` = it holds at least one agent (min / max of nothing is undefined) */
+static int reduce_local(abm_handle* h, int32_t what, double* out, bool* any) {
+  int rc;
+  *any = h->n > 0;
   if (what == ABM_REDUCE_COUNT_AGENTS) { *out = (double)h->n; return ABM_OK; }
   if (what == ABM_REDUCE_COUNT_GROWN) {
     if (!h->grid_set) ABM_FAIL(h, ABM_E_STATE, "abm_set_grid has not been called");
     unsigned long long* acc = (unsigned long long*)((uint32_t*)h->counters.p + CTR_RED_LO);
     ABM_CK(h, dev_memset(acc, 0, 8, h->stream));
     CountGrownBody cb;
-    cb.grass4 = (const uint32_t*)h->grass.p; cb.out = acc;
-    launch_foreach(h->stream, cb, (uint64_t)h->g.gt / 4);
+    /* a strip counts its own rows only (whole tile rows: a contiguous range of the tile-major array) */
+    const uint64_t first = (uint64_t)(h->g.own_lo / CORE) * (uint64_t)h->g.tiles_x * TILE_CELLS;
+    const uint64_t cells = (uint64_t)((h->g.own_hi - h->g.own_lo + CORE - 1) / CORE) * (uint64_t)h->g.tiles_x * TILE_CELLS;
+    cb.grass4 = (const uint32_t*)((const uint8_t*)h->grass.p + first); cb.out = acc;
+    launch_foreach(h->stream, cb, cells / 4);
     if ((rc = check_launch(h, "count grown"))) return rc;
     unsigned long long v = 0;
     ABM_CK(h, copy_d2h(&v, acc, 8, h->stream));
@@ -578,6 +628,7 @@ int ABM_API(reduce)(abm_handle* h, int32_t what, double* out) {
   if (what == ABM_REDUCE_SUM_ENERGY || what == ABM_REDUCE_MAX_ENERGY || what == ABM_REDUCE_MIN_ENERGY) {
     const uint64_t n = h->n;
     if (n == 0) { *out = 0; return ABM_OK; }
+    if ((rc = stream_canonical(h))) return rc;
     const uint64_t chunks = (n + ENERGY_CHUNK - 1) / ENERGY_CHUNK;
     if ((rc = ensure(h, h->partials, chunks * 8))) return rc;
     EnergyPartialBody eb;
@@ -598,6 +649,36 @@ int ABM_API(reduce)(abm_handle* h, int32_t what, double* out) {
   ABM_FAIL(h, ABM_E_BADARG, "unknown reduction %d", what);
 }
 
+int ABM_API(reduce)(abm_handle* h, int32_t what, double* out) {
+  if (!h || !out) return ABM_E_BADARG;
+  int rc = set_device(h);
+  if (rc) return rc;
+  double mine = 0;
+  bool any = false;
+  if ((rc = reduce_local(h, what, &mine, &any))) return rc;
+  if (!h->strip || h->n_ranks <= 1) { *out = mine; return ABM_OK; }
+  /* strips: the value over the whole GridSpace, combined in rank order from every rank's share (collective call) */
+  const int P = h->n_ranks;
+  uint64_t snd[2];
+  memcpy(&snd[0], &mine, 8);
+  snd[1] = any ? 1 : 0;
+  std::vector<uint64_t> all((size_t)2 * P);
+  if ((rc = comm_allgather_small(h, snd, 2, all.data()))) return rc;
+  double v = 0;
+  bool first = true;
+  for (int r = 0; r < P; ++r) {
+    double x;
+    memcpy(&x, &all[2 * r], 8);
+    if (what == ABM_REDUCE_MAX_ENERGY || what == ABM_REDUCE_MIN_ENERGY) {
+      if (!all[2 * r + 1]) continue;
+      if (first || (what == ABM_REDUCE_MAX_ENERGY ? x > v : x < v)) v = x;
+      first = false;
+    } else v += x;
+  }
+  *out = v;
+  return ABM_OK;
+}
+
 int ABM_API(plan_routes)(abm_handle* h, int64_t b, const int64_t* agent_id, const int64_t* goal_x, const int64_t* goal_y) {
   if (!h) return ABM_E_BADARG;
   if (b < 0 || (b > 0 && (!agent_id || !goal_x || !goal_y))) ABM_FAIL(h, ABM_E_BADARG, "null request arrays");
@@ -614,6 +695,7 @@ int ABM_API(plan_routes)(abm_handle* h, int64_t b, const int64_t* agent_id, cons
     for (int64_t i = 1; i < b; ++i) if (srt[i] == srt[i - 1]) ABM_FAIL(h, ABM_E_BADARG, "agent id %lld appears twice in one abm_plan_routes batch", (long long)srt[i]);
   }
   const uint64_t n = h->n;
+  if ((rc = stream_canonical(h))) return rc;
   if ((rc = ensure(h, h->idx_of_id, (h->next_id + 1) * 4))) return rc;
   if ((rc = ensure_route_ids(h, h->next_id))) return rc;
   ABM_CK(h, dev_memset(h->idx_of_id.p, 0xFF, (h->next_id + 1) * 4, h->stream));
@@ -749,8 +831,11 @@ int ABM_API(p2p_export)(abm_handle* h, void* handle64) {
   int rc = set_device(h);
   if (rc) return rc;
   if (!h->p2p_mine) {
-    h->p2p_capmax = std::max<uint64_t>(1u << 16, h->n / 4 + 4096);   /* agents per boundary row the mailbox can carry */
-    h->p2p_birthmax = std::max<uint64_t>(1u << 16, h->n / 8 + 4096);
+    /* Every rank addresses its neighbours' mailboxes with its OWN layout, so the layout must be the same on all ranks: it is
+     * derived from the grid alone (never from this rank's population).  A boundary sub-tile row may hold 16 agents per
+     * cell on average; offspring per tick and rank: 1/32 of a rank's share of the cells. */
+    h->p2p_capmax = std::max<uint64_t>(1u << 16, (uint64_t)h->cfg.nx * SUB * 16);
+    h->p2p_birthmax = std::max<uint64_t>(1u << 16, (uint64_t)h->cfg.nx * (uint64_t)h->cfg.ny / (uint64_t)h->n_ranks / 32);
     h->p2p_lay.agents_bytes = (strip_msg_bytes(h->nsx, h->p2p_capmax) + 255) & ~(uint64_t)255;
     h->p2p_lay.state_bytes = (h->p2p_capmax + 255) & ~(uint64_t)255;
     h->p2p_lay.births_bytes = ((1 + h->p2p_birthmax) * 4 + 255) & ~(uint64_t)255;

@@ -19,6 +19,7 @@
 #include "abm_kernels.h"
 #include "abm_astar.h"
 #include "abm_tile.h"
+#include "abm_stream.h"
 #include "abm_p2p.h"
 
 #ifdef ABM_EMU
@@ -265,7 +266,8 @@ struct abm_handle {
   DevBuf cell_start[2];             /* gt + 1 (+ padding) */
   int cur = 0;
   DevBuf state, slot, new_cell, pend[2], births;
-  DevBuf grass, walkbits, elev;
+  DevBuf grass, walkbits, elev, global_bits; /* global_bits: strips, the whole GridSpace's walkmap (abm_set_global_walkmap_bits) */
+  bool global_bits_set = false, has_walkmap = false;
   DevBuf bits, bits_prefix, scan_tmp, stage, lut, greg_order, greg_dxy, greg_table, counters, partials;
   /* ALTERNATED_WALK / A*: id-order ranks, behaviour segments, plan requests, route followers, the route store */
   DevBuf rank, by_rank, seg_behav, plan_agent, plan_goal, remote_head, remote_next, remote_dest, idx_of_id;
@@ -300,6 +302,15 @@ struct abm_handle {
   DevBuf sx_pre[2], rx_pre[2], sx_buf[2], rx_buf[2], sx_st[2], rx_st[2], red_buf, birth_ids;
   uint64_t n_ghost = 0, bcap = 4096, next_bcap = 4096;
   bool bcap_agreed = false; /* capacity (agents) of a boundary message, the same on every rank */
+  /* stream path (abm_stream.h): arrival lists of the current and the next tick, parents bitmaps, counters */
+  bool stream_mode = false;      /* walk rule without conflicts on a tile-path grid (ABM_STREAM=0 disables) */
+  bool s_lists = false;          /* the lists of tick `tick` are filed */
+  bool s_canon = true;           /* cell/id/energy[cur] hold the population (the getters' view) */
+  bool s_relayout = false;       /* file again with more slots per core */
+  int s_cur = 0;
+  uint32_t s_cap = 0, s_cap_forced = 0; /* record slots per core (ABM_STREAM_CAP forces a value: tests) */
+  uint64_t s_ovf_cap = 0, s_n_ovf = 0, s_n_layout = 0, s_words[2] = {0, 0}, s_parent_cap = 0, s_parent_used = 0, s_msg_cap = 0;
+  DevBuf s_rec[2], s_cnt[2], s_ovf_rec[2], s_ovf_tile[2], s_bits[2], s_ctr, s_parents, s_gather, s_tx[2], s_rx[2];
   std::vector<uint8_t> hstage[4];
   uint32_t* h_counters = nullptr; /* host mirror (pinned on CUDA) */
 
@@ -638,6 +649,8 @@ static SubIndex sub_index(abm_handle* h, int which) {
 }
 
 #include "abm_host_strips.inl"
+
+#include "abm_host_stream.inl"
 
 /* one tick on the tile path (abm_tile.h): propose -> window resolve -> per-agent windows for the rest -> commit */
 static int tick_tile(abm_handle* h) {

@@ -170,6 +170,44 @@ static int p2p_allgather_births(abm_handle* h, uint32_t* all, uint64_t cap) {
 }
 #endif
 
+/* every rank's n (<= 4) values, rank-major, on the host: the collective behind abm_reduce on strips */
+static int comm_allgather_small(abm_handle* h, const uint64_t* mine, int n, uint64_t* all) {
+  const int P = h->n_ranks;
+  if (P == 1) { memcpy(all, mine, (size_t)n * 8); return 0; }
+#ifndef ABM_EMU
+  if (h->p2p_on) {
+    int rc = ensure(h, h->red_buf, 4096);
+    if (rc) return rc;
+    unsigned long long* d_src = (unsigned long long*)h->red_buf.p;
+    unsigned long long* d_out = d_src + 8;
+    ABM_CK(h, copy_h2d(d_src, mine, (size_t)n * 8, h->stream));
+    const uint32_t seq = ++h->p2p_seq[P2P_CH_STATS];
+    const int parity = (int)(seq & 1u);
+    P2PSmallSendCta sd;
+    sd.src = d_src; sd.n = n; sd.n_ranks = P; sd.seq = seq;
+    P2PSmallRecvCta rv;
+    rv.n = n; rv.n_ranks = P; rv.seq = seq; rv.out = d_out; rv.err = (uint32_t*)h->counters.p + CTR_ERR;
+    for (int r = 0; r < P; ++r) {
+      sd.dst[r] = (unsigned long long*)(h->p2p_peer[r] + h->p2p_lay.stats_off(h->my_rank, parity));
+      sd.flag[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.flag_off(P2P_CH_STATS, h->my_rank, parity));
+      rv.src[r] = (const unsigned long long*)(h->p2p_mine + h->p2p_lay.stats_off(r, parity));
+      rv.flag[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.flag_off(P2P_CH_STATS, r, parity));
+    }
+    launch_cta(h->stream, sd, 1, 64, 16);
+    launch_cta(h->stream, rv, 1, 64, 16);
+    if ((rc = check_launch(h, "peer all-gather"))) return rc;
+    ABM_CK(h, copy_d2h(all, d_out, (size_t)n * 8 * (size_t)P, h->stream));
+    return 0;
+  }
+#endif
+  std::vector<uint32_t> snd((size_t)2 * n), rcv((size_t)2 * n * P);
+  memcpy(snd.data(), mine, (size_t)n * 8);
+  int rc = comm_allgather_u32(h, snd.data(), rcv.data(), (uint32_t)(2 * n));
+  if (rc) return rc;
+  memcpy(all, rcv.data(), (size_t)n * 8 * (size_t)P);
+  return 0;
+}
+
 /* capacity of a boundary message, agreed by all ranks from the same all-reduced figures */
 static uint64_t strip_cap_for(uint64_t max_row) { return 2 * max_row + 4096; }
 

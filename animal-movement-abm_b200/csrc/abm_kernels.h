@@ -145,7 +145,7 @@ struct View {
   uint32_t* remote_dest;     /* per agent: final tcell */
 };
 
-enum { ERR_NOWALKABLE = 1, ERR_INTERNAL = 2, ERR_STRIP_CAP = 4, ERR_P2P_TIMEOUT = 8 };
+enum { ERR_NOWALKABLE = 1, ERR_INTERNAL = 2, ERR_STRIP_CAP = 4, ERR_P2P_TIMEOUT = 8, ERR_LIST_CAP = 16 };
 
 ABM_HD bool walkable(const View& v, uint32_t c) { return (v.walkbits[c >> 5] >> (c & 31)) & 1u; }
 ABM_HD bool present(uint8_t s) { return !(s & ST_DEAD) || (s & ST_BIRTH); }
@@ -184,6 +184,82 @@ ABM_HD void attractor_dir(const Params& p, const Geo& g, int x, int y, int& dx, 
   if (3 * ey * ey > ex * ex) dy = ey > 0 ? 1 : -1;
 }
 
+/* custom_agent_step! up to the point where other agents matter (src/agent_actions.jl:36-67): the draws of agent `id` at
+ * (x, y) for tick v.p.tick, the walk rule, the death and birth flags -> decision byte.  `nowalk`: random_walkmap found no
+ * walkable neighbour (the reference throws on rand(1:0)). */
+ABM_HD uint8_t propose_state(const View& v, int x, int y, uint32_t id, double energy, bool& nowalk) {
+  const Params& p = v.p;
+  AgentStream rs;
+  rs.init(p.seed, p.tick, id);
+  uint8_t st = 0;
+  bool cond = false; /* move gated by isempty(target) */
+  int dx = 0, dy = 0;
+  bool randomwalk = false;
+  nowalk = false;
+
+  switch (p.walk_type) {
+    case ABM_RANDOM_WALK: randomwalk = true; break; /* :37-39 */
+    case ABM_RANDOM_WALK_ATTRACTOR:                 /* :40-42, execute_walk! :109-117 */
+      if (rs.next_f64() < p.prob_random_walk) randomwalk = true;
+      else { attractor_dir(p, v.g, x, y, dx, dy); cond = true; /* walk!(...; ifempty=true), :266 */ }
+      break;
+    case ABM_RANDOM_WALK_GREGARIOUS:                /* :43-45 */
+      if (rs.next_f64() < p.prob_random_walk) randomwalk = true;
+      else { st = DIR_GREG; rs.n += 1; /* draw 1 is consumed in resolve (wsample or rand(1:8)) */ }
+      break;
+    case ABM_RANDOM_WALKMAP: {                      /* :49-51 with prob 0, random_walkmap :182-186 */
+      rs.n += 1; /* rand(model.rng, Uniform(0,1)) < 0 is never true but is drawn */
+      /* nearby_walkable(pos, model, pathfinder, 1): bit d of `ok` = neighbour d (offsets_at_radius order) is walkable */
+      uint32_t ok = 0;
+      int xs[3] = {x - 1, x, x + 1};
+      if (v.g.periodic) { xs[0] = wrap(xs[0], v.g.nx); xs[2] = wrap(xs[2], v.g.nx); }
+      else { if (xs[0] < 0) xs[0] = -1; if (xs[2] >= v.g.nx) xs[2] = -1; } /* nearby_positions drops out-of-bounds */
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        int yy = y + r - 1;
+        if (v.g.py) yy = wrap(yy, v.g.ny); else if (yy < v.g.y_lo || yy >= v.g.y_hi) continue;
+        const uint32_t* row = v.walkbits + ((size_t)(yy >> 5) * v.g.tiles_x) * 32 + (yy & 31); /* word of tile column 0 */
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          if (r == 1 && q == 1) continue;
+          const int xx = xs[q];
+          if (xx < 0) continue;
+          const uint32_t bit = (row[(size_t)(xx >> 5) * 32] >> (xx & 31)) & 1u;
+          const int idx = r * 3 + q;
+          ok |= bit << (idx < 4 ? idx : idx - 1);
+        }
+      }
+      const int nc = popc(ok);
+      if (nc == 0) { nowalk = true; st = DIR_STAY | ST_DECIDED; break; }
+      int pick = (int)rs.next_below((uint64_t)nc); /* rand(model.rng, 1:length(nearby_pos)) */
+      int d = 0;
+      for (uint32_t m = ok; ; m >>= 1, ++d) { if (m & 1u) { if (pick == 0) break; --pick; } }
+      off8(d, dx, dy);
+      const int e = effective_dir(v.g, x, y, dx, dy);
+      st = (uint8_t)(e | ST_DECIDED | (e != DIR_STAY ? ST_MOVED : 0)); /* move_agent!, unconditional */
+      break;
+    }
+    default: break; /* ABM_ALTERNATED_WALK is proposed by AlternatedProposeBody */
+  }
+  if (randomwalk) { /* randomwalk!: rand(rng, offsets_at_radius(model, 1)) then walk!(...; ifempty) */
+    off8((int)rs.next_below(8), dx, dy);
+    cond = true;
+    if (!p.ifempty) {
+      const int e = effective_dir(v.g, x, y, dx, dy);
+      st = (uint8_t)(e | ST_DECIDED | (e != DIR_STAY ? ST_MOVED : 0));
+      cond = false;
+    }
+  }
+  if (cond) {
+    const int e = effective_dir(v.g, x, y, dx, dy);
+    /* a target equal to the own cell is never empty (the agent stands on it): decided, no move */
+    st = (uint8_t)(e == DIR_STAY ? (DIR_STAY | ST_DECIDED) : e);
+  }
+  if (energy - p.movement_cost < 0) st |= ST_DEAD;
+  if (p.reproduce && rs.next_f64() <= p.reproduction_prob) st |= ST_BIRTH;
+  return st;
+}
+
 struct ProposeBody {
   View v;
   uint32_t* pending;       /* worklist of undecided agents (general path; null on the tile path) */
@@ -192,78 +268,11 @@ struct ProposeBody {
 
   ABM_HD void operator()(uint64_t i) const {
     const uint32_t k = (uint32_t)i;
-    const Params& p = v.p;
-    const uint32_t c = v.cell[k];
-    const uint32_t id = v.id[k];
     int x, y;
-    dec(v.g, c, x, y);
-    AgentStream rs;
-    rs.init(p.seed, p.tick, id);
-    uint8_t st = 0;
-    bool cond = false; /* move gated by isempty(target) */
-    int dx = 0, dy = 0;
-    bool randomwalk = false;
-
-    switch (p.walk_type) {
-      case ABM_RANDOM_WALK: randomwalk = true; break; /* :37-39 */
-      case ABM_RANDOM_WALK_ATTRACTOR:                 /* :40-42, execute_walk! :109-117 */
-        if (rs.next_f64() < p.prob_random_walk) randomwalk = true;
-        else { attractor_dir(p, v.g, x, y, dx, dy); cond = true; /* walk!(...; ifempty=true), :266 */ }
-        break;
-      case ABM_RANDOM_WALK_GREGARIOUS:                /* :43-45 */
-        if (rs.next_f64() < p.prob_random_walk) randomwalk = true;
-        else { st = DIR_GREG; rs.n += 1; /* draw 1 is consumed in resolve (wsample or rand(1:8)) */ }
-        break;
-      case ABM_RANDOM_WALKMAP: {                      /* :49-51 with prob 0, random_walkmap :182-186 */
-        (void)rs.next_f64(); /* rand(model.rng, Uniform(0,1)) < 0 is never true but is drawn */
-        /* nearby_walkable(pos, model, pathfinder, 1): bit d of `ok` = neighbour d (offsets_at_radius order) is walkable */
-        uint32_t ok = 0;
-        int xs[3] = {x - 1, x, x + 1};
-        if (v.g.periodic) { xs[0] = wrap(xs[0], v.g.nx); xs[2] = wrap(xs[2], v.g.nx); }
-        else { if (xs[0] < 0) xs[0] = -1; if (xs[2] >= v.g.nx) xs[2] = -1; } /* nearby_positions drops out-of-bounds */
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          int yy = y + r - 1;
-          if (v.g.py) yy = wrap(yy, v.g.ny); else if (yy < v.g.y_lo || yy >= v.g.y_hi) continue;
-          const uint32_t* row = v.walkbits + ((size_t)(yy >> 5) * v.g.tiles_x) * 32 + (yy & 31); /* word of tile column 0 */
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            if (r == 1 && q == 1) continue;
-            const int xx = xs[q];
-            if (xx < 0) continue;
-            const uint32_t bit = (row[(size_t)(xx >> 5) * 32] >> (xx & 31)) & 1u;
-            const int idx = r * 3 + q;
-            ok |= bit << (idx < 4 ? idx : idx - 1);
-          }
-        }
-        const int nc = popc(ok);
-        if (nc == 0) { atomic_or(v.err, ERR_NOWALKABLE); st = DIR_STAY | ST_DECIDED; break; }
-        int pick = (int)rs.next_below((uint64_t)nc); /* rand(model.rng, 1:length(nearby_pos)) */
-        int d = 0;
-        for (uint32_t m = ok; ; m >>= 1, ++d) { if (m & 1u) { if (pick == 0) break; --pick; } }
-        off8(d, dx, dy);
-        const int e = effective_dir(v.g, x, y, dx, dy);
-        st = (uint8_t)(e | ST_DECIDED | (e != DIR_STAY ? ST_MOVED : 0)); /* move_agent!, unconditional */
-        break;
-      }
-      default: break; /* ABM_ALTERNATED_WALK is proposed by AlternatedProposeBody */
-    }
-    if (randomwalk) { /* randomwalk!: rand(rng, offsets_at_radius(model, 1)) then walk!(...; ifempty) */
-      off8((int)rs.next_below(8), dx, dy);
-      cond = true;
-      if (!p.ifempty) {
-        const int e = effective_dir(v.g, x, y, dx, dy);
-        st = (uint8_t)(e | ST_DECIDED | (e != DIR_STAY ? ST_MOVED : 0));
-        cond = false;
-      }
-    }
-    if (cond) {
-      const int e = effective_dir(v.g, x, y, dx, dy);
-      /* a target equal to the own cell is never empty (the agent stands on it): decided, no move */
-      st = (uint8_t)(e == DIR_STAY ? (DIR_STAY | ST_DECIDED) : e);
-    }
-    if (v.energy[k] - p.movement_cost < 0) st |= ST_DEAD;
-    if (p.reproduce && rs.next_f64() <= p.reproduction_prob) st |= ST_BIRTH;
+    dec(v.g, v.cell[k], x, y);
+    bool nowalk;
+    const uint8_t st = propose_state(v, x, y, v.id[k], v.energy[k], nowalk);
+    if (nowalk) atomic_or(v.err, ERR_NOWALKABLE);
     v.state[k] = st;
     if (pending && !(st & ST_DECIDED)) pending[atomic_add(pending_count, 1u)] = k;
     if (birth_flags && (st & ST_BIRTH)) atomic_add(birth_flags, 1u);
@@ -822,9 +831,9 @@ struct GridImportBody {
     const uint64_t yy = i / (uint64_t)g.nx, x = i - yy * (uint64_t)g.nx;
     const uint64_t y = row0 + yy;
     const uint32_t c = enc(g, (int)x, (int)y);
-    const int64_t k = cd[i];
+    const int64_t k = cd ? cd[i] : 0;
     if (k < 0 || k > 126) atomic_or(err, ERR_INTERNAL);
-    grass[c] = (uint8_t)((fg[i] ? GRASS_GROWN : 0) | (uint8_t)(k & 0x7F));
+    grass[c] = (uint8_t)(((fg && fg[i]) ? GRASS_GROWN : 0) | (uint8_t)(k & 0x7F));
     if (!wm || wm[i]) atomic_or(&walkbits[c >> 5], 1u << (c & 31));
     if (el) {
       const int64_t e = el[i];
@@ -839,13 +848,15 @@ struct GridImportBody {
 struct InitGrassBody {
   Geo g; uint64_t seed; int32_t regrowth_time, open_terrain;
   uint8_t* grass; uint32_t* walkbits;
-  ABM_HD void operator()(uint64_t i) const {
-    const uint64_t y = i / (uint64_t)g.nx, x = i - y * (uint64_t)g.nx;
+  ABM_HD void operator()(uint64_t i) const { /* i = cell of the rows this handle owns, x fastest */
+    const uint64_t yy = i / (uint64_t)g.nx, x = i - yy * (uint64_t)g.nx;
+    const uint64_t y = yy + (uint64_t)g.own_lo;           /* stored row */
+    const uint64_t key = (uint64_t)((int64_t)y + g.y_off) * (uint64_t)g.nx + x; /* the cell's index in the whole GridSpace */
     const uint32_t c = enc(g, (int)x, (int)y);
     if (open_terrain) atomic_or(&walkbits[c >> 5], 1u << (c & 31));
     else if (!((walkbits[c >> 5] >> (c & 31)) & 1u)) { grass[c] = 0; return; }
     AgentStream r;
-    r.init(seed, 0xFFFFFFFEull, i);
+    r.init(seed, 0xFFFFFFFEull, key);
     const bool grown = (r.next_u64() & 1ull) != 0;
     const uint32_t k = grown ? (uint32_t)regrowth_time : (regrowth_time > 0 ? r.next_below((uint64_t)regrowth_time) : 0u);
     grass[c] = (uint8_t)((grown ? GRASS_GROWN : 0) | (k & 0x7F));
@@ -855,7 +866,12 @@ struct InitGrassBody {
  * (scripts/v0.1.jl:66-71, random_walkable in scripts/v0.5.jl:103) — written as host-layout records for the ingest */
 struct InitSheepBody {
   Geo g; uint64_t seed, span; const uint32_t* walkbits;
+  int32_t ny_global;               /* strips: random_position draws over the whole GridSpace ... */
+  const uint32_t* global_bits;     /* ... whose walkmap is this (1 bit per cell, x fastest; null = every cell walkable) */
   int64_t* s_id; int64_t* s_x; int64_t* s_y; double* s_e; uint32_t* err;
+  /* strips: only the sheep that land on the own rows are kept, as packed records behind a cursor (a first pass with
+   * p_e == null counts them) */
+  int32_t strip; uint32_t* cursor; double* p_e; uint32_t* p_id; uint32_t* p_xy;
   ABM_HD void operator()(uint64_t i) const {
     AgentStream r;
     r.init(seed, 0xFFFFFFFFull, i + 1);
@@ -864,12 +880,28 @@ struct InitSheepBody {
     int tries = 0;
     while (true) {
       x = r.next_below((uint64_t)g.nx);
-      y = r.next_below((uint64_t)g.ny);
-      const uint32_t c = enc(g, (int)x, (int)y);
-      if ((walkbits[c >> 5] >> (c & 31)) & 1u) break;
+      y = r.next_below((uint64_t)(strip ? ny_global : g.ny));
+      bool ok;
+      if (strip) { const uint64_t l = (uint64_t)y * (uint64_t)g.nx + x; ok = !global_bits || ((global_bits[l >> 5] >> (l & 31)) & 1u); }
+      else { const uint32_t c = enc(g, (int)x, (int)y); ok = (walkbits[c >> 5] >> (c & 31)) & 1u; }
+      if (ok) break;
       if (++tries >= 4096) { atomic_or(err, ERR_NOWALKABLE); break; }
     }
-    s_id[i] = (int64_t)(i + 1); s_x[i] = (int64_t)x + 1; s_y[i] = (int64_t)y + 1; s_e[i] = (double)e;
+    if (!strip) { s_id[i] = (int64_t)(i + 1); s_x[i] = (int64_t)x + 1; s_y[i] = (int64_t)y + 1; s_e[i] = (double)e; return; }
+    const int64_t ys = (int64_t)y - g.y_off; /* stored row */
+    if (ys < g.own_lo || ys >= g.own_hi) return; /* another strip's sheep */
+    const uint32_t k = atomic_add(cursor, 1u);
+    if (p_e) { p_e[k] = (double)e; p_id[k] = (uint32_t)(i + 1); p_xy[k] = (x + 1) | ((y + 1) << 16); }
+  }
+};
+
+struct GhostWalkableBody { /* abm_init_random on a strip without terrain: the ghost rows are open land as well */
+  Geo g; uint32_t* walkbits;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint64_t y = i / (uint64_t)g.nx, x = i - y * (uint64_t)g.nx;
+    if ((int64_t)y >= g.own_lo && (int64_t)y < g.own_hi) return;
+    const uint32_t c = enc(g, (int)x, (int)y);
+    atomic_or(&walkbits[c >> 5], 1u << (c & 31));
   }
 };
 

@@ -87,6 +87,26 @@ struct P2PStatsRecvCta {
   }
 };
 
+/* a few u64 per rank, all-to-all over the counters channel (abm_reduce on strips): thread r serves rank r */
+struct P2PSmallSendCta {
+  const unsigned long long* src; int32_t n, n_ranks;
+  unsigned long long* dst[P2P_MAXP]; uint32_t* flag[P2P_MAXP]; uint32_t seq;
+  ABM_HD void operator()(uint32_t, uint32_t*) const {
+    ABM_CTA_FOR(t, 64) {
+      if (t < n_ranks) { for (int w = 0; w < n; ++w) dst[t][w] = src[w]; flag_publish(flag[t], seq); }
+    }
+  }
+};
+struct P2PSmallRecvCta {
+  const unsigned long long* src[P2P_MAXP]; const uint32_t* flag[P2P_MAXP]; uint32_t seq;
+  int32_t n, n_ranks; unsigned long long* out; uint32_t* err;
+  ABM_HD void operator()(uint32_t, uint32_t*) const {
+    ABM_CTA_FOR(t, 64) { if (t < n_ranks) flag_wait(flag[t], seq, err, ERR_P2P_TIMEOUT); }
+    ABM_CTA_SYNC();
+    ABM_CTA_FOR(t, 64) { if (t < n_ranks) for (int w = 0; w < n; ++w) out[t * n + w] = src[t][w]; }
+  }
+};
+
 /* offspring all-gather in two launches of n_ranks x BIRTH_CTAS CTAs: the CTAs (r, *) store [count, parent ids ...] of
  * this rank into rank r's mailbox (coalesced 128-byte rows over NVLink) and the one that finishes last publishes; then
  * the CTAs (r, *) wait for rank r's message and lay it out contiguously for the rank kernel */

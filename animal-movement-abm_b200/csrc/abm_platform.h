@@ -19,6 +19,7 @@
 /* ------------------------------------------------------------------ emulation (tests only) --------------- */
 #define ABM_HD inline
 #define ABM_D inline
+#define ABM_HOSTDEV inline
 #include <algorithm>
 #include <vector>
 
@@ -75,6 +76,8 @@ static inline uint32_t smem_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = 
 /* minimum over the 32 lanes of a warp that all execute this call, folded into *dst; returns the minimum known to the
  * caller (lanes run one after another here, so that is the running value) */
 static inline uint32_t warp_min_into(uint32_t* dst, uint32_t v, int /*lane*/) { if (v < *dst) *dst = v; return *dst; }
+/* base[key] += 1 for every calling lane with valid set; returns the lane's own slot (see the CUDA version) */
+static inline uint32_t agg_add(uint32_t* base, uint32_t key, bool valid) { return valid ? atomic_add(&base[key], 1u) : 0u; }
 
 /* peer-memory flags (abm_p2p.h) do not exist in the emulation: transports there go through the host */
 static inline void flag_publish(uint32_t*, uint32_t) {}
@@ -96,6 +99,9 @@ static inline void launch_cta(abm_stream_t, const F& f, uint64_t n_ctas, int /*t
   }
 }
 
+template <int THREADS, int MINB, class F>
+static inline void launch_cta_lb(abm_stream_t s, const F& f, uint64_t n_ctas, size_t smem_bytes) { launch_cta(s, f, n_ctas, THREADS, smem_bytes); }
+
 static inline abm_err_t dev_malloc(void** p, size_t bytes) { *p = calloc(bytes ? bytes : 1, 1); return *p ? 0 : 2; }
 static inline void dev_free(void* p) { free(p); }
 static inline abm_err_t dev_memset(void* p, int v, size_t bytes, abm_stream_t) { memset(p, v, bytes); return 0; }
@@ -114,6 +120,7 @@ static inline const char* err_string(abm_err_t e) { return e ? "emulated allocat
 #include <cuda_runtime.h>
 #define ABM_HD __device__ __forceinline__
 #define ABM_D __device__ __forceinline__
+#define ABM_HOSTDEV __host__ __device__ __forceinline__
 
 typedef cudaStream_t abm_stream_t;
 typedef cudaError_t abm_err_t;
@@ -168,6 +175,18 @@ ABM_D uint32_t warp_min_into(uint32_t* dst, uint32_t v, int lane) {
   return m; /* the same value in every lane */
 }
 
+/* base[key] += 1 for every lane with `valid`, one atomic per distinct key in the warp; returns the lane's own slot.
+ * Every lane of the warp must call it (the *_sync intrinsics wait for all 32). */
+ABM_D uint32_t agg_add(uint32_t* base, uint32_t key, bool valid) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t peers = __match_any_sync(0xffffffffu, valid ? key : 0xFFFFFFFFu);
+  const int leader = __ffs((int)peers) - 1;
+  uint32_t b = 0;
+  if (valid && (int)lane == leader) b = atomicAdd(&base[key], (uint32_t)__popc(peers));
+  b = __shfl_sync(peers, b, leader);
+  return b + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+}
+
 /* publish a sequence number in (peer) memory after everything this thread's CTA wrote before the preceding barrier */
 ABM_D void flag_publish(uint32_t* flag, uint32_t seq) {
   if (!flag) return;
@@ -203,6 +222,20 @@ static inline void launch_cta(abm_stream_t s, const F& f, uint64_t n_ctas, int t
     configured = true;
   }
   k_cta<F><<<(unsigned)n_ctas, threads, smem_bytes, s>>>(f);
+}
+
+/* the same with the register budget of THREADS x MINB resident threads per SM (occupancy of latency-bound kernels) */
+template <class F, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_cta_lb(const F f) {
+  extern __shared__ __align__(16) uint32_t abm_smem[];
+  f(blockIdx.x, abm_smem);
+}
+template <int THREADS, int MINB, class F>
+static inline void launch_cta_lb(abm_stream_t s, const F& f, uint64_t n_ctas, size_t smem_bytes) {
+  if (n_ctas == 0) return;
+  ++g_launches;
+  cudaFuncSetAttribute(k_cta_lb<F, THREADS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  k_cta_lb<F, THREADS, MINB><<<(unsigned)n_ctas, THREADS, smem_bytes, s>>>(f);
 }
 
 static inline abm_err_t dev_malloc(void** p, size_t bytes) {

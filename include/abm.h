@@ -127,7 +127,8 @@ void abm_destroy(abm_handle* h);
 
 /* replaces: model.fully_grown / model.countdown / model.land_walkmap / model.elevation property arrays
  * (scripts/v0.6.jl:78-94).  fully_grown, walkmap: one byte per cell (0/1); walkmap and elevation may be NULL
- * (all walkable / flat).  countdown must be in 0..126, elevation in -32768..32767. */
+ * (all walkable / flat); fully_grown and countdown may both be NULL (terrain only: bare grass, countdown 0 — e.g. before
+ * abm_init_random).  countdown must be in 0..126, elevation in -32768..32767. */
 int abm_set_grid(abm_handle* h, const uint8_t* fully_grown, const int64_t* countdown, const uint8_t* walkmap,
                  const int64_t* elevation);
 
@@ -146,8 +147,15 @@ int abm_set_agents(abm_handle* h, int64_t n, const int64_t* id, const int64_t* x
  * own stream of the contract above — sheep i: draw(init_seed, tick = 2^32-1, id = i, n) with n = 0 the energy, then
  * (x, y) pairs until the cell is walkable; cell (x, y): draw(init_seed, tick = 2^32-2, id = (y-1)*nx + (x-1), n) with
  * n = 0 the grown bit (lowest bit of the word), n = 1.. the countdown — so the world does not depend on who builds it.
- * Not available on a strip handle (placement needs the whole walkmap). */
+ * Strip handles: every rank calls it with the same arguments (n_sheep = the population of the WHOLE GridSpace); each rank
+ * goes through every sheep's draws and keeps those that land on its rows, so the strips together hold exactly the world a
+ * single handle would build.  random_walkable rejects positions anywhere in the space, so a strip with terrain must have
+ * been given the whole walkmap before (abm_set_global_walkmap_bits); without terrain nothing else is needed. */
 int abm_init_random(abm_handle* h, int64_t n_sheep, uint64_t init_seed);
+
+/* Strip handles only: the walkmap of the whole GridSpace, one bit per cell — bit (l & 31) of word (l >> 5),
+ * l = (y-1)*nx + (x-1) — for abm_init_random (32768^2 cells are 128 MiB).  NULL forgets it. */
+int abm_set_global_walkmap_bits(abm_handle* h, const uint32_t* bits);
 
 /* replaces: model.behav[1], model.behav_counter[1] (scripts/v0.4.jl:69-71,97) and the tick the RNG is keyed by */
 int abm_set_global_state(abm_handle* h, int64_t tick, int64_t behav, int64_t behav_counter);
@@ -184,7 +192,8 @@ int abm_set_agents_packed(abm_handle* h, int64_t n, const uint32_t* id, const ui
                           int64_t next_id);
 int abm_get_agents_packed(abm_handle* h, int64_t* n_inout, uint32_t* id, uint32_t* xy, double* energy);
 
-/* replaces: adata/mdata aggregation inside Agents.run! (scripts/v0.6.jl:204-210) */
+/* replaces: adata/mdata aggregation inside Agents.run! (scripts/v0.6.jl:204-210).  On a strip handle the call is
+ * collective (every rank makes it) and returns the value over the WHOLE GridSpace, combined in rank order. */
 int abm_reduce(abm_handle* h, int32_t what, double* out);
 
 /* replaces: plan_route!(agent, dest, model.pathfinder) for a batch of agents (src/agent_actions.jl:217-221;

@@ -554,10 +554,10 @@ void oracle_destroy(oracle_handle* h) { delete h; }
 int oracle_set_grid(oracle_handle* h, const uint8_t* fg, const int64_t* cd, const uint8_t* wm, const int64_t* el) {
   Model& m = h->m;
   const size_t G = (size_t)m.nx * m.ny;
-  if (!fg || !cd) return ABM_E_BADARG;
+  if ((fg == nullptr) != (cd == nullptr)) return ABM_E_BADARG;
   for (size_t i = 0; i < G; ++i) {
-    m.fully_grown[i] = fg[i] ? 1 : 0;
-    m.countdown[i] = cd[i];
+    m.fully_grown[i] = (fg && fg[i]) ? 1 : 0;
+    m.countdown[i] = cd ? cd[i] : 0;
     m.walkmap[i] = wm ? (wm[i] ? 1 : 0) : 1;
     m.elevation[i] = el ? el[i] : 0;
   }
@@ -767,6 +767,7 @@ int oracle_get_timing(oracle_handle* h, double* out, int32_t n) {
   if (n > 5) out[5] = (double)h->m.astar_expansions;
   return 0;
 }
+int oracle_set_global_walkmap_bits(oracle_handle*, const uint32_t*) { return ABM_E_STATE; } /* strips only */
 int oracle_set_transport(oracle_handle*, const abm_transport*) { return ABM_E_STATE; } /* the oracle is one process, like the reference */
 int oracle_nccl_unique_id(void*) { return ABM_E_STATE; }
 int oracle_comm_init_nccl(oracle_handle*, const void*) { return ABM_E_STATE; }

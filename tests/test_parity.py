@@ -297,7 +297,7 @@ def test_gpu_tile_path_matches_oracle(libabm, oracle, wt, per, terr, n, nx, ny, 
     for t in range(12):
         a.step(1)
         b.step(1)
-        assert "commit_tiles" in {k for k, v in b.kernel_stats().items() if v["launches"]}
+        assert ("stream_tick" if wt == 4 else "commit_tiles") in {k for k, v in b.kernel_stats().items() if v["launches"]}
         assert_same_state(b.snapshot(), a.snapshot(), f"wt {wt} tick {t}")
     a.step(20)
     b.step(20)
@@ -334,8 +334,8 @@ def test_gpu_full_size_two_engine_paths_and_invariants(libabm, wt, size, extra):
     for t in range(3):
         a.step(1)
         b.step(1)
-        assert "commit_tiles" in {k for k, v in a.kernel_stats().items() if v["launches"]}
-        assert "commit_tiles" not in {k for k, v in b.kernel_stats().items() if v["launches"]}
+        assert ("stream_tick" if wt == 4 else "commit_tiles") in {k for k, v in a.kernel_stats().items() if v["launches"]}
+        assert not {"commit_tiles", "stream_tick"} & {k for k, v in b.kernel_stats().items() if v["launches"]}
         sa, sb = a.snapshot(), b.snapshot()
         assert_same_state(sa, sb, f"tile vs general path, walk type {wt}, tick {t}")
         ids, pid = sa["ids"], prev["ids"]
@@ -354,10 +354,35 @@ def test_gpu_full_size_two_engine_paths_and_invariants(libabm, wt, size, extra):
         prev = sa
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("label,wt,nx,ny,ticks,extra", [
+    ("C2 full size", 2, 4096, 4096, 2, dict(visual_distance=3, prob_random_walk=0.9, reproduction_prob=0.001)),  # BASELINE.json configs[1]
+    ("C3 slab", 4, 8192, 1024, 2, dict(walkmap_regrowth=1, reproduction_prob=0.004)),                              # configs[2] rules, an 8192 x 1024 slab
+])
+def test_gpu_baseline_configs_match_the_oracle(libabm, oracle, label, wt, nx, ny, ticks, extra):
+    """The BASELINE.json configurations against the ORACLE (not against a second GPU path): the oracle runs ~1.4e6
+    agent-updates/s, so two ticks of the full C2 world (2^22 sheep) are affordable."""
+    from abm_b200 import worlds
+    wm = el = None
+    if wt == 4:
+        el = worlds.make_terrain(nx, ny, seed=6)
+        wm = worlds.walkmap_from_elevation(el)
+    w = worlds.make_world(nx, ny, nx * ny // 4, seed=5, walkmap=wm, periodic=True)
+    w["walkmap"], w["elevation"] = wm, el
+    cfg = dict(nx=nx, ny=ny, periodic=1, walk_type=wt, seed=77, **extra)
+    a, b = load_case(oracle, cfg, w), load_case(libabm, cfg, w)
+    for t in range(ticks):
+        a.step(1)
+        b.step(1)
+        assert_same_state(b.snapshot(), a.snapshot(), f"{label} tick {t}")
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("name", ["tile_rw_96x64", "tile_gregarious_r3_96x96", "tile_walkmap_128x96", "tile_crowded_64x64"])
 def test_emulated_tile_path_with_migrant_lists(emu, oracle, name, monkeypatch):
     """ABM_MIGRANTS=1: the commit reads its own core plus the per-core list of border crossers (off by default)."""
     monkeypatch.setenv("ABM_MIGRANTS", "1")
+    monkeypatch.setenv("ABM_STREAM", "0")  # the walkmap case would otherwise take the stream path (no commit kernel)
     cfgkw, w, state, ticks = build_case(name)
     a, b = load_case(oracle, cfgkw, w), load_case(emu, cfgkw, w)
     for t in range(6):
@@ -504,3 +529,63 @@ def test_packed_transfer_forms_emulated(emu, oracle):
 @pytest.mark.gpu
 def test_gpu_packed_transfer_forms(libabm, oracle):
     _check_packed_round_trip(libabm, oracle)
+
+
+# ------------------------------------------------------------------ stream path (abm_stream.h): rules without conflicts
+
+def _check_stream_path(lib, oracle, monkeypatch, cap):
+    """RANDOM_WALKMAP and RANDOM_WALK without `ifempty` on tile grids take the one-kernel-per-tick stream path: arrival lists
+    per core, the next step drawn in the same kernel.  Checked against the oracle tick by tick, with the getters and
+    setters of the ABI called between the ticks (they convert between the lists and the canonical arrays), with few list
+    slots per core (overflow list, re-filing) and across several ticks per abm_step."""
+    if cap:
+        monkeypatch.setenv("ABM_STREAM_CAP", str(cap))
+    cases = [
+        dict(nx=128, ny=96, n=9000, wt=4, per=1, terrain=True, kw=dict(walkmap_regrowth=1, reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0)),
+        dict(nx=64, ny=96, n=7000, wt=0, per=0, terrain=False, kw=dict(randomwalk_ifempty=0, reproduction_prob=0.1, regrowth_time=2, delta_energy=2.0)),
+        dict(nx=96, ny=64, n=300, wt=0, per=1, terrain=False, kw=dict(randomwalk_ifempty=0, reproduction_prob=0.3, regrowth_time=1, delta_energy=5.0)),
+        dict(nx=64, ny=64, n=20000, wt=4, per=1, terrain=True, kw=dict(walkmap_regrowth=0, reproduction_prob=0.02, regrowth_time=4, eat=0)),
+        # everybody starts on one core of sixteen: the lists are filed again with more slots per core
+        dict(nx=128, ny=128, n=12000, wt=0, per=1, terrain=False, crowd=True, kw=dict(randomwalk_ifempty=0, reproduction_prob=0.05, regrowth_time=2, delta_energy=3.0)),
+    ]
+    for ci, c in enumerate(cases):
+        cfgkw, w = make_case(c["nx"], c["ny"], c["n"], c["wt"], c["per"], terrain=c["terrain"], seed=41 + ci, **c["kw"])
+        if c.get("crowd"):
+            w["x"], w["y"] = 33 + (w["x"] - 1) % 32, 65 + (w["y"] - 1) % 32
+        a, b = load_case(oracle, cfgkw, w), load_case(lib, cfgkw, w)
+        assert "stream_tick" not in b.kernel_stats()
+        for t in range(5):
+            a.step(1); b.step(1)
+            assert_same_state(b.snapshot(), a.snapshot(), f"stream case {ci} tick {t}")
+        assert b.kernel_stats()["stream_tick"]["launches"] == 1
+        a.step(4); b.step(4)  # several ticks per call: no getter in between
+        assert_same_state(b.snapshot(), a.snapshot(), f"stream case {ci} after step(4)")
+        assert b.reduce(capi.REDUCE_SUM_ENERGY) == a.reduce(capi.REDUCE_SUM_ENERGY) and b.count_agents() == a.count_agents()
+        # the host rewinds the clock: the filed steps were drawn for another tick and must be drawn again
+        a.set_global_state(2); b.set_global_state(2)
+        a.step(2); b.step(2)
+        assert_same_state(b.snapshot(), a.snapshot(), f"stream case {ci} after a tick change")
+        # new grass through the narrow form keeps the filed steps; a new population replaces them
+        st = b.get_grass_packed()
+        st[::2, ::3] = 0x80 | 3
+        a.set_grass_packed(st); b.set_grass_packed(st)
+        a.step(1); b.step(1)
+        assert_same_state(b.snapshot(), a.snapshot(), f"stream case {ci} after new grass")
+        s = a.snapshot()
+        keep = s["ids"] % 3 != 0
+        for e in (a, b):
+            e.set_agents(s["ids"][keep], s["x"][keep], s["y"][keep], s["energy"][keep] + 1.0, s["next_id"])
+            e.step(3)
+        assert_same_state(b.snapshot(), a.snapshot(), f"stream case {ci} after a new population")
+        a.close(); b.close()
+
+
+@pytest.mark.parametrize("cap", [0, 8])
+def test_stream_path_emulated(emu, oracle, monkeypatch, cap):
+    _check_stream_path(emu, oracle, monkeypatch, cap)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cap", [0, 8])
+def test_gpu_stream_path(libabm, oracle, monkeypatch, cap):
+    _check_stream_path(libabm, oracle, monkeypatch, cap)

@@ -75,10 +75,14 @@ def _ring_worker(rank, world, name, ticks, port, out_dir, use_gpu, transport="nc
     else:
         dist.init_process_group("gloo", rank=rank, world_size=world)
         lib = c2.CLib(b2.LIBEMU, "emu_")
-    cfgkw, w = _case(name)
+    cfgkw, w = _case(name[5:] if name.startswith("init_") else name)
     if use_gpu:
         cfgkw = dict(cfgkw, device=rank)
     e = strips.load_strip(lib, cfgkw, w, world, rank)
+    if name.startswith("init_"):  # the engine draws grass and sheep itself (abm_init_random on strips)
+        if w.get("walkmap") is not None:
+            e.set_global_walkmap(w["walkmap"])
+        e.init_random(w["ids"].size, 99)
     if use_gpu and transport == "p2p":
         strips.init_p2p(e)
     elif use_gpu:
@@ -90,6 +94,7 @@ def _ring_worker(rank, world, name, ticks, port, out_dir, use_gpu, transport="nc
     for t in range(ticks):
         e.step(1)
         snaps.append(strips.strip_snapshot(e))
+        snaps[-1]["reduced"] = [e.reduce(k) for k in range(5)]  # collective: the values over the whole GridSpace
     np.save(os.path.join(out_dir, f"snap_{rank}.npy"), np.array(snaps, dtype=object), allow_pickle=True)
     dist.barrier()
     dist.destroy_process_group()
@@ -112,6 +117,39 @@ def test_ring_of_processes_over_gloo(oracle, tmp_path, world, name):
     for t in range(ticks):
         a.step(1)
         assert_same_state(strips.merge_snapshots([per_rank[r][t] for r in range(world)]), a.snapshot(), f"{name} world {world} tick {t}")
+
+
+def _check_init_and_reduce(oracle, per_rank, world, name, ticks):
+    cfgkw, w = _case(name)
+    a = load_case(oracle, cfgkw, w)
+    a.init_random(w["ids"].size, 99)
+    for t in range(ticks):
+        a.step(1)
+        assert_same_state(strips.merge_snapshots([per_rank[r][t] for r in range(world)]), a.snapshot(), f"init {name} world {world} tick {t}")
+        want = [a.reduce(k) for k in range(5)]
+        for r in range(world):
+            assert per_rank[r][t]["reduced"] == want, (name, world, t, r)
+
+
+@pytest.mark.parametrize("world,name", [(2, "rw"), (3, "walkmap"), (2, "gregarious")])
+def test_init_random_and_reduce_on_strips(oracle, tmp_path, world, name):
+    """abm_init_random on strip handles builds the world a single handle would build (every rank keeps the sheep that
+    land on its rows), and abm_reduce returns the value over the whole GridSpace on every rank."""
+    build.build_emu()
+    ticks = 5
+    per_rank = _run_ring(world, "init_" + name, ticks, tmp_path)
+    _check_init_and_reduce(oracle, per_rank, world, name, ticks)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,name,transport", [(2, "walkmap", "p2p"), (2, "gregarious", "nccl")])
+def test_init_random_and_reduce_on_gpu_strips(libabm, oracle, tmp_path, world, name, transport):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ticks = 5
+    per_rank = _run_ring(world, "init_" + name, ticks, tmp_path, use_gpu=True, transport=transport)
+    _check_init_and_reduce(oracle, per_rank, world, name, ticks)
 
 
 @pytest.mark.parametrize("world,name", [(1, "walkmap"), (3, "attractor")])
