@@ -81,6 +81,7 @@ _U32P = C.POINTER(C.c_uint32)
 # name -> (restype, argtypes); mirrors include/abm.h one to one
 SIGNATURES = {
     "config_default": (None, [C.POINTER(AbmConfig)]),
+    "config_size": (C.c_int, []),
     "create": (C.c_int, [C.POINTER(AbmConfig), C.POINTER(_P)]),
     "destroy": (None, [_P]),
     "set_grid": (C.c_int, [_P, _U8P, _I64P, _U8P, _I64P]),
@@ -110,7 +111,23 @@ SIGNATURES = {
     "p2p_export": (C.c_int, [_P, C.c_void_p]),
     "p2p_connect": (C.c_int, [_P, C.c_void_p, C.c_int32]),
     "last_error": (C.c_char_p, [_P]),
+    "group_create": (C.c_int, [C.POINTER(AbmConfig), C.c_int32, C.POINTER(C.c_int32), C.POINTER(_P)]),
+    "group_destroy": (None, [_P]),
+    "group_set_grid": (C.c_int, [_P, _U8P, _I64P, _U8P, _I64P]),
+    "group_set_agents": (C.c_int, [_P, C.c_int64, _I64P, _I64P, _I64P, _F64P, C.c_int64]),
+    "group_init_random": (C.c_int, [_P, C.c_int64, C.c_uint64]),
+    "group_set_global_state": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64]),
+    "group_get_global_state": (C.c_int, [_P, _I64P, _I64P, _I64P, _I64P]),
+    "group_step": (C.c_int, [_P, C.c_int64]),
+    "group_count_agents": (C.c_int, [_P, _I64P]),
+    "group_get_agents": (C.c_int, [_P, _I64P, _I64P, _I64P, _I64P, _F64P]),
+    "group_get_grid": (C.c_int, [_P, _U8P, _I64P]),
+    "group_reduce": (C.c_int, [_P, C.c_int32, _F64P]),
+    "group_member": (_P, [_P, C.c_int32]),
+    "group_last_error": (C.c_char_p, [_P]),
 }
+# entry points the CPU oracle does not have (it is one process on one device, like the reference)
+ENGINE_ONLY = {n for n in SIGNATURES if n.startswith("group_")}
 
 
 def _ptr(a, ty):
@@ -127,9 +144,13 @@ class CLib:
         self.dll = C.CDLL(path)
         self.fn = {}
         for name, (res, args) in SIGNATURES.items():
+            if name in ENGINE_ONLY and not hasattr(self.dll, prefix + name):
+                continue
             f = getattr(self.dll, prefix + name)
             f.restype, f.argtypes = res, args
             self.fn[name] = f
+        if self.fn["config_size"]() != C.sizeof(AbmConfig):
+            raise RuntimeError(f"{path}: abm_config is {self.fn['config_size']()} bytes, the ctypes mirror {C.sizeof(AbmConfig)}")
 
     def default_config(self, **kw) -> AbmConfig:
         cfg = AbmConfig()
@@ -142,6 +163,92 @@ class CLib:
 
     def create(self, cfg: AbmConfig) -> "Engine":
         return Engine(self, cfg)
+
+    def create_group(self, cfg: AbmConfig, device_ids) -> "Group":
+        return Group(self, cfg, device_ids)
+
+
+class Group:
+    """One abm_group: n strip handles on n devices of one process, whole-GridSpace arrays in and out (include/abm.h)."""
+
+    def __init__(self, lib: "CLib", cfg: AbmConfig, device_ids):
+        self.lib, self.cfg = lib, cfg
+        ids = (C.c_int32 * len(device_ids))(*device_ids)
+        self.g = _P()
+        rc = lib.fn["group_create"](C.byref(cfg), len(device_ids), ids, C.byref(self.g))
+        if rc != ABM_OK:
+            msg = lib.fn["group_last_error"](None)
+            self.g = None
+            raise AbmError(rc, (msg or b"").decode())
+        self.nx, self.ny, self.n_devices = cfg.nx, cfg.ny, len(device_ids)
+
+    def _ck(self, rc):
+        if rc != ABM_OK:
+            raise AbmError(rc, (self.lib.fn["group_last_error"](self.g) or b"").decode())
+
+    def close(self):
+        if self.g is not None and self.g.value is not None:
+            self.lib.fn["group_destroy"](self.g)
+        self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_grid(self, fully_grown, countdown, walkmap=None, elevation=None):
+        c = lambda a, dt: None if a is None else np.ascontiguousarray(a, dtype=dt).reshape(-1)
+        fg, cd, wm, el = c(fully_grown, np.uint8), c(countdown, np.int64), c(walkmap, np.uint8), c(elevation, np.int64)
+        self._ck(self.lib.fn["group_set_grid"](self.g, _ptr(fg, _U8P), _ptr(cd, _I64P), _ptr(wm, _U8P), _ptr(el, _I64P)))
+
+    def set_agents(self, ids, x, y, energy, next_id=None):
+        ids = np.ascontiguousarray(ids, dtype=np.int64); x = np.ascontiguousarray(x, dtype=np.int64)
+        y = np.ascontiguousarray(y, dtype=np.int64); e = np.ascontiguousarray(energy, dtype=np.float64)
+        if next_id is None:
+            next_id = int(ids.max()) + 1 if ids.size else 1
+        self._ck(self.lib.fn["group_set_agents"](self.g, ids.size, _ptr(ids, _I64P), _ptr(x, _I64P), _ptr(y, _I64P), _ptr(e, _F64P), int(next_id)))
+
+    def init_random(self, n_sheep, init_seed):
+        self._ck(self.lib.fn["group_init_random"](self.g, int(n_sheep), int(init_seed)))
+
+    def set_global_state(self, tick=0, behav=0, behav_counter=0):
+        self._ck(self.lib.fn["group_set_global_state"](self.g, int(tick), int(behav), int(behav_counter)))
+
+    def get_global_state(self):
+        v = [C.c_int64() for _ in range(4)]
+        self._ck(self.lib.fn["group_get_global_state"](self.g, *[C.byref(a) for a in v]))
+        return dict(tick=v[0].value, behav=v[1].value, behav_counter=v[2].value, next_id=v[3].value)
+
+    def step(self, n=1):
+        self._ck(self.lib.fn["group_step"](self.g, int(n)))
+
+    def count_agents(self):
+        n = C.c_int64()
+        self._ck(self.lib.fn["group_count_agents"](self.g, C.byref(n)))
+        return n.value
+
+    def get_agents(self):
+        n = self.count_agents()
+        ids = np.empty(n, np.int64); x = np.empty(n, np.int64); y = np.empty(n, np.int64); e = np.empty(n, np.float64)
+        cap = C.c_int64(n)
+        self._ck(self.lib.fn["group_get_agents"](self.g, C.byref(cap), _ptr(ids, _I64P), _ptr(x, _I64P), _ptr(y, _I64P), _ptr(e, _F64P)))
+        return ids, x, y, e
+
+    def get_grid(self):
+        fg = np.empty((self.ny, self.nx), np.uint8); cd = np.empty((self.ny, self.nx), np.int64)
+        self._ck(self.lib.fn["group_get_grid"](self.g, _ptr(fg, _U8P), _ptr(cd, _I64P)))
+        return fg, cd
+
+    def reduce(self, what):
+        out = C.c_double()
+        self._ck(self.lib.fn["group_reduce"](self.g, int(what), C.byref(out)))
+        return out.value
+
+    def snapshot(self):
+        ids, x, y, e = self.get_agents()
+        fg, cd = self.get_grid()
+        return dict(ids=ids, x=x, y=y, energy=e, fully_grown=fg, countdown=cd, **self.get_global_state())
 
 
 class Engine:

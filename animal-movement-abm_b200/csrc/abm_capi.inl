@@ -15,6 +15,8 @@ void ABM_API(config_default)(abm_config* c) {
   c->attractor_x = 40; c->attractor_y = 40; c->seed = 321;
 }
 
+int ABM_API(config_size)(void) { return (int)sizeof(abm_config); }
+
 const char* ABM_API(last_error)(abm_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 void ABM_API(destroy)(abm_handle* h) {

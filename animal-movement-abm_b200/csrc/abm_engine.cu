@@ -941,3 +941,4 @@ static int validate_config(const abm_config* c, std::string& why) {
 
 /* ================================================================================================ C ABI */
 #include "abm_capi.inl"
+#include "abm_group.inl"

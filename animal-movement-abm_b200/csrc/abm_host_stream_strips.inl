@@ -123,10 +123,11 @@ static int stream_agree_parent_cap(abm_handle* h, bool first) {
   if (!h->strip || P <= 1 || !h->cfg.reproduce) return 0;
   int rc;
   uint64_t bound = 0;
-  if (first) { /* after filing: all-reduce of the local counts (a sum bounds every rank's count) */
-    uint64_t v = h->h_counters[SC_PARENTS];
-    if ((rc = comm_allreduce_u64(h, &v, 1))) return rc;
-    bound = v;
+  if (first) { /* after filing: every rank's local count */
+    const uint64_t v = h->h_counters[SC_PARENTS];
+    std::vector<uint64_t> all((size_t)P);
+    if ((rc = comm_allgather_small(h, &v, 1, all.data()))) return rc;
+    for (int r = 0; r < P; ++r) bound = std::max(bound, all[r]);
   } else { /* the counts every rank gathered this tick (StreamMarkParentsBody left them beside the tick's counters) */
     for (int r = 0; r < P; ++r) bound = std::max<uint64_t>(bound, h->h_counters[SC_GCOUNT + r]);
   }

@@ -63,11 +63,9 @@ struct Geo {
 
 /* offsets_at_radius(model, 1) order (x fastest), SURVEY.md A-5 */
 ABM_HD void off8(int d, int& dx, int& dy) {
-  /* d: 0..7 -> (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1) */
-  const int q = d + (d >= 4); /* skip the centre of the 3x3 */
-  const int row = (q >= 3) + (q >= 6);
-  dx = q - 3 * row - 1;
-  dy = row - 1;
+  /* d: 0..7 -> (-1,-1),(0,-1),(1,-1),(-1,0),(1,0),(-1,1),(0,1),(1,1): two bits per entry, dx + 1 and dy + 1 */
+  dx = (int)((0x9224u >> (2 * d)) & 3u) - 1;
+  dy = (int)((0xA940u >> (2 * d)) & 3u) - 1;
 }
 ABM_HD int dir_code(int ex, int ey) {
   const int q = (ey + 1) * 3 + (ex + 1);
@@ -211,31 +209,46 @@ ABM_HD uint8_t propose_state(const View& v, int x, int y, uint32_t id, double en
       rs.n += 1; /* rand(model.rng, Uniform(0,1)) < 0 is never true but is drawn */
       /* nearby_walkable(pos, model, pathfinder, 1): bit d of `ok` = neighbour d (offsets_at_radius order) is walkable */
       uint32_t ok = 0;
-      int xs[3] = {x - 1, x, x + 1};
-      if (v.g.periodic) { xs[0] = wrap(xs[0], v.g.nx); xs[2] = wrap(xs[2], v.g.nx); }
-      else { if (xs[0] < 0) xs[0] = -1; if (xs[2] >= v.g.nx) xs[2] = -1; } /* nearby_positions drops out-of-bounds */
+      const int lx = x & 31;
+      const bool inner = x >= 1 && x + 1 < v.g.nx && y >= 1 && y + 1 < v.g.ny && (v.g.py || (y - 1 >= v.g.y_lo && y + 1 < v.g.y_hi));
+      if (inner) { /* away from the rim nothing wraps: per row one word of the tile-major bitmap, and the neighbouring tile's
+                    * word for the one cell that may lie across a tile border (predicated loads, no divergent path) */
+        const uint32_t tx = (uint32_t)(x >> 5);
+        uint32_t b3[3];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        int yy = y + r - 1;
-        if (v.g.py) yy = wrap(yy, v.g.ny); else if (yy < v.g.y_lo || yy >= v.g.y_hi) continue;
-        const uint32_t* row = v.walkbits + ((size_t)(yy >> 5) * v.g.tiles_x) * 32 + (yy & 31); /* word of tile column 0 */
+        for (int r = 0; r < 3; ++r) {
+          const int yy = y + r - 1;
+          const uint32_t* wp = v.walkbits + ((size_t)(yy >> 5) * v.g.tiles_x + tx) * 32 + (yy & 31);
+          const uint32_t wc = wp[0];
+          const uint32_t wl = lx == 0 ? wp[-32] : wc, wr = lx == 31 ? wp[32] : wc;
+          b3[r] = ((wl >> ((lx - 1) & 31)) & 1u) | (((wc >> lx) & 1u) << 1) | (((wr >> ((lx + 1) & 31)) & 1u) << 2);
+        }
+        ok = b3[0] | ((b3[1] & 1u) << 3) | ((b3[1] & 4u) << 2) | (b3[2] << 5);
+      } else {
+        int xs[3] = {x - 1, x, x + 1};
+        if (v.g.periodic) { xs[0] = wrap(xs[0], v.g.nx); xs[2] = wrap(xs[2], v.g.nx); }
+        else { if (xs[0] < 0) xs[0] = -1; if (xs[2] >= v.g.nx) xs[2] = -1; } /* nearby_positions drops out-of-bounds */
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          if (r == 1 && q == 1) continue;
-          const int xx = xs[q];
-          if (xx < 0) continue;
-          const uint32_t bit = (row[(size_t)(xx >> 5) * 32] >> (xx & 31)) & 1u;
-          const int idx = r * 3 + q;
-          ok |= bit << (idx < 4 ? idx : idx - 1);
+        for (int r = 0; r < 3; ++r) {
+          int yy = y + r - 1;
+          if (v.g.py) yy = wrap(yy, v.g.ny); else if (yy < v.g.y_lo || yy >= v.g.y_hi) continue;
+          const uint32_t* row = v.walkbits + ((size_t)(yy >> 5) * v.g.tiles_x) * 32 + (yy & 31); /* word of tile column 0 */
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            if (r == 1 && q == 1) continue;
+            const int xx = xs[q];
+            if (xx < 0) continue;
+            const uint32_t bit = (row[(size_t)(xx >> 5) * 32] >> (xx & 31)) & 1u;
+            const int idx = r * 3 + q;
+            ok |= bit << (idx < 4 ? idx : idx - 1);
+          }
         }
       }
       const int nc = popc(ok);
       if (nc == 0) { nowalk = true; st = DIR_STAY | ST_DECIDED; break; }
-      int pick = (int)rs.next_below((uint64_t)nc); /* rand(model.rng, 1:length(nearby_pos)) */
-      int d = 0;
-      for (uint32_t m = ok; ; m >>= 1, ++d) { if (m & 1u) { if (pick == 0) break; --pick; } }
-      off8(d, dx, dy);
-      const int e = effective_dir(v.g, x, y, dx, dy);
+      const int d = nth_set_bit(ok, (int)rs.next_below((uint64_t)nc)); /* rand(model.rng, 1:length(nearby_pos)) */
+      int e = d; /* away from the rim the step neither wraps nor clamps: the direction is the draw */
+      if (!inner) { off8(d, dx, dy); e = effective_dir(v.g, x, y, dx, dy); }
       st = (uint8_t)(e | ST_DECIDED | (e != DIR_STAY ? ST_MOVED : 0)); /* move_agent!, unconditional */
       break;
     }
@@ -593,19 +606,18 @@ struct PopcountBody { /* per-word popcounts as the input of the rank scan */
 
 /* ------------------------------------------------------------------------------------------------- regrow */
 
+/* custom_model_step! on four cells at once (one grass byte each: bit 7 = fully_grown, bits 0..6 = countdown, 0x7F =
+ * padding).  Per byte: if allowed (walkmap bit, when used), not padding and not grown: countdown == 0 -> grown with
+ * countdown = regrowth_time, else countdown -= 1.  SWAR: every step below works on the four bytes independently. */
 ABM_HD uint32_t regrow4(uint32_t w, uint32_t rt, uint32_t walk4, bool use_walk) {
-  uint32_t out = 0;
-#pragma unroll
-  for (int b = 0; b < 4; ++b) {
-    uint32_t s = (w >> (8 * b)) & 0xFFu;
-    const bool ok = !use_walk || ((walk4 >> b) & 1u);
-    if (ok && s != GRASS_PAD && !(s & GRASS_GROWN)) {
-      if (s == 0) s = GRASS_GROWN | rt; /* countdown <= 0: fully_grown = true, countdown = regrowth_time */
-      else s -= 1;
-    }
-    out |= s << (8 * b);
-  }
-  return out;
+  const uint32_t H = 0x80808080u;
+  const uint32_t low = w & 0x7F7F7F7Fu;
+  const uint32_t zero = ((low + 0x7F7F7F7Fu) & H) ^ H;      /* 0x80 where countdown == 0 */
+  const uint32_t pad = (low + 0x01010101u) & H;              /* 0x80 where the byte is 0x7F (or 0xFF) */
+  uint32_t act = ~w & H & ~pad;                              /* not grown, not padding */
+  if (use_walk) act &= (((walk4 & 0xFu) * 0x00204081u) & 0x01010101u) << 7; /* bit b of walk4 -> byte b */
+  const uint32_t grow = act & zero, dec = act & ~zero;
+  return (w - (dec >> 7)) | grow | ((grow >> 7) * rt);
 }
 
 /* custom_model_step! (src/model_actions.jl:18-30): 16 cells per thread */

@@ -36,6 +36,8 @@ static inline uint32_t atomic_exch(uint32_t* p, uint32_t v) { uint32_t o = *p; *
 static inline unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 static inline uint8_t load_state(const uint8_t* p) { return *(const volatile uint8_t*)p; }
 static inline int popc(uint32_t v) { return __builtin_popcount(v); }
+/* position of the (k + 1)-th set bit of m (k < popc(m)) */
+static inline int nth_set_bit(uint32_t m, int k) { int d = 0; for (;; m >>= 1, ++d) { if (m & 1u) { if (k == 0) return d; --k; } } }
 
 struct EmuRand {
   uint64_t s;
@@ -76,6 +78,11 @@ static inline uint32_t smem_or(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = 
 /* minimum over the 32 lanes of a warp that all execute this call, folded into *dst; returns the minimum known to the
  * caller (lanes run one after another here, so that is the running value) */
 static inline uint32_t warp_min_into(uint32_t* dst, uint32_t v, int /*lane*/) { if (v < *dst) *dst = v; return *dst; }
+/* true when the predicate holds on every lane of the warp (lanes run one after another here: the lane's own answer) */
+static inline bool warp_all(bool pred) { return pred; }
+/* lanes that share one gregarious search (abm_tile.h): one here, so group_min is the identity */
+enum { GREG_LANES = 1 };
+static inline uint32_t group_min(uint32_t v) { return v; }
 /* base[key] += 1 for every calling lane with valid set; returns the lane's own slot (see the CUDA version) */
 static inline uint32_t agg_add(uint32_t* base, uint32_t key, bool valid) { return valid ? atomic_add(&base[key], 1u) : 0u; }
 
@@ -137,6 +144,8 @@ ABM_D unsigned long long atomic_add64(unsigned long long* p, unsigned long long 
  * bypass L1 so that a decision published by another SM becomes visible (ld.global.cg = cache at L2 only) */
 ABM_D uint8_t load_state(const uint8_t* p) { return __ldcg(p); }
 ABM_D int popc(uint32_t v) { return __popc(v); }
+/* position of the (k + 1)-th set bit of m (k < popc(m)) */
+ABM_D int nth_set_bit(uint32_t m, int k) { return (int)__fns(m, 0u, k + 1); }
 
 extern unsigned long long g_launches;
 
@@ -175,6 +184,15 @@ ABM_D uint32_t warp_min_into(uint32_t* dst, uint32_t v, int lane) {
   return m; /* the same value in every lane */
 }
 
+/* GREG_LANES consecutive lanes share one gregarious search (abm_tile.h); their minimum, in every lane of the group */
+enum { GREG_LANES = 4 };
+ABM_D uint32_t group_min(uint32_t v) {
+  v = min(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = min(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+/* true when the predicate holds on every lane of the warp; every lane must call it (it also reconverges the warp) */
+ABM_D bool warp_all(bool pred) { return __all_sync(0xffffffffu, pred) != 0; }
 /* base[key] += 1 for every lane with `valid`, one atomic per distinct key in the warp; returns the lane's own slot.
  * Every lane of the warp must call it (the *_sync intrinsics wait for all 32). */
 ABM_D uint32_t agg_add(uint32_t* base, uint32_t key, bool valid) {

@@ -102,7 +102,12 @@ ABM_HD void stream_emit(const View& v, const StreamLists& out, const ParentSink&
     bool nowalk;
     const uint8_t st = propose_state(v, x, y, id, e, nowalk);
     int fx = x, fy = y;
-    if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); shift(v.g, x, y, dx, dy, fx, fy); }
+    if (st & ST_MOVED) {
+      int dx, dy;
+      off8(st & ST_DIRMASK, dx, dy);
+      if (x >= 1 && x + 1 < v.g.nx && y >= 1 && y + 1 < v.g.ny) { fx = x + dx; fy = y + dy; } /* away from the rim: no wrap */
+      else shift(v.g, x, y, dx, dy, fx, fy);
+    }
     tile = (uint32_t)((fy >> TILE_SHIFT) * v.g.tiles_x + (fx >> TILE_SHIFT));
     r.w0 = (uint32_t)(((fy & 31) << 5) | (fx & 31)) | ((uint32_t)((st & ST_MOVED) ? (st & ST_DIRMASK) : (int)DIR_STAY) << SR_DIR_SHIFT) |
            ((st & ST_DEAD) ? (uint32_t)SR_DEAD : 0u) | ((st & ST_BIRTH) ? (uint32_t)SR_BIRTH : 0u) | (nowalk ? (uint32_t)SR_NOWALK : 0u);
@@ -179,7 +184,7 @@ struct StreamTickCta {
     vn.p.tick = v.p.tick + 1;
 
     ABM_CTA_FOR(t, NT) {
-      for (int c = t; c < CORE * CORE; c += NT) min_all[c] = NONE32;
+      fill_words(min_all, NONE32, CORE * CORE, t, NT);
       for (int c = t; c < CORE * CORE / 4; c += NT) ((uint32_t*)grass)[c] = gtile[c];
       if (t < 8) misc[t] = 0;
     }

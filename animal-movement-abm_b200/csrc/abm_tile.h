@@ -123,6 +123,17 @@ struct RunTable {
   }
 };
 
+/* n words (a multiple of 4, 16-byte aligned) set to `val` by the NT threads of a CTA, four words per store */
+ABM_HD void fill_words(uint32_t* p, uint32_t val, int n, int t, int NT) {
+#if defined(__CUDA_ARCH__)
+  uint4* q = reinterpret_cast<uint4*>(p);
+  const uint4 v4 = make_uint4(val, val, val, val);
+  for (int c = t; c < (n >> 2); c += NT) q[c] = v4;
+#else
+  for (int c = t; c < n; c += NT) p[c] = val;
+#endif
+}
+
 struct Summaries {
   uint32_t* max_old;
   uint32_t* min_new;
@@ -269,7 +280,8 @@ struct ResolveWindow {
 #else
   enum { MAYBE_BUFS = 1 };
 #endif
-  static size_t smem_bytes_core() { return (size_t)((2 + MAYBE_BUFS) * WIN * WIN + 3 * ULIST_CAP + RUNTABLE_WORDS + 16) * 4; }
+  enum { GREG_REL_WORDS = 120 }; /* (2 * GREG_MAX_R + 1)^2 = 225 window offsets of the box cells in visiting order, int16 */
+  static size_t smem_bytes_core() { return (size_t)((2 + MAYBE_BUFS) * WIN * WIN + 3 * ULIST_CAP + RUNTABLE_WORDS + 16 + GREG_REL_WORDS) * 4; }
 
   /* Core window with the undecided agents held in a shared-memory work list: each round touches only what is still
    * open.  min_new only ever gains entries (decisions are final), min_maybe is rebuilt per round from the list.  Agents are read from global memory exactly once.  Returns false (uniformly) when the list overflows. */
@@ -294,12 +306,17 @@ struct ResolveWindow {
     rt.bind(l_xs + ULIST_CAP);
     uint32_t* cnt = l_xs + ULIST_CAP + RUNTABLE_WORDS; /* [0] walkers, [5] gregarious,
                                                         * [8 + 2p], [9 + 2p] progress / open agents of the core, round parity p */
+    int16_t* grel = (int16_t*)(cnt + 16);              /* the box cells in visiting order, as offsets inside the window */
     const uint32_t XS_DONE = 1u << 20, XS_BEST_NONE = 0x1FFu << 21, XS_LOW = (1u << 21) - 1;
 
+    const int side = 2 * v.p.r + 1, box = side * side;
     ABM_CTA_FOR(t, NT) {
       rt.load(t, NT, nruns, w, v.g, si);
-      for (int c = t; c < cells; c += NT) { max_old[c] = 0u; min_new[c] = NONE32; maybe[0][c] = NONE32; if (MAYBE_BUFS == 2) maybe[1][c] = NONE32; }
+      fill_words(max_old, 0u, cells, t, NT);
+      fill_words(min_new, NONE32, (1 + MAYBE_BUFS) * cells, t, NT); /* min_new and the maybe buffer(s) are contiguous */
       if (t < 16) cnt[t] = 0;
+      if (v.p.walk_type == ABM_RANDOM_WALK_GREGARIOUS)
+        for (int q = t; q < box; q += NT) grel[q] = (int16_t)((int)v.greg_dxy[2 * q + 1] * WIN + (int)v.greg_dxy[2 * q]);
     }
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, NT) { rt.scan(t, NT, nruns); }
@@ -345,11 +362,12 @@ struct ResolveWindow {
       }
     }
     ABM_CTA_SYNC();
-    /* Rounds, three barriers each.  P1: open walkers are evaluated, open gregarious agents searched.  P2: gregarious agents
-     * draw and publish; min_maybe, which nobody reads in this phase, is cleared.  P3: the entries still open put their
-     * candidate cells back into min_maybe.  min_new only gains entries (decisions are final).  (With -DABM_TWO_MAYBE the
-     * open entries write into a second buffer during P1/P2 instead and P3 disappears.) */
-    const int side = 2 * v.p.r + 1, box = side * side;
+    /* Rounds, three barriers each.  P1: every open agent is evaluated by its own thread (walkers from the front of the
+     * thread range, gregarious agents from the back, so that each kind fills whole warps: their code paths differ by an
+     * order of magnitude in length) and publishes its decision at once.  P2: min_maybe, which nobody reads in this phase,
+     * is cleared.  P3: the entries still open put their candidate cells back into min_maybe.  min_new only gains entries
+     * (decisions are final); a reader that misses a fresh entry still finds the same id in min_maybe and waits a round.
+     * (With -DABM_TWO_MAYBE the open entries write into a second buffer during P1 instead and P3 disappears.) */
     int cur = 0;
     for (int round = 0; round < max_rounds; ++round) {
       uint32_t* flag = cnt + 8 + 2 * (round & 1);
@@ -371,65 +389,55 @@ struct ResolveWindow {
             flag[0] = 1;
           } else {
             if (MAYBE_BUFS == 2) contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
-            if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&flag[1], 1u);
+            if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) flag[1] = 1;
           }
         }
-        /* gregarious closest-neighbour search: one warp per agent, one lane per box cell; the first cell in visiting
-         * order that is occupied or unknown wins through a shared-memory min on the entry's top bits */
-        int rel[8]; /* this lane's box cells (visiting ranks lane, lane + 32, ...) as offsets inside the window */
-        if (ng > 0) {
-          for (int j = 0; j < 8 && (t & 31) + 32 * j < box; ++j) {
-            const int q = (t & 31) + 32 * j;
-            rel[j] = (int)v.greg_dxy[2 * q + 1] * WIN + (int)v.greg_dxy[2 * q];
-          }
-        }
-        for (uint32_t task = (uint32_t)t >> 5; task < ng; task += (uint32_t)NT >> 5) {
-          const uint32_t e = ULIST_CAP - 1 - task, xs = l_xs[e];
-          if (xs & XS_DONE) continue;
-          const uint32_t id = l_id[e], low = xs & XS_LOW;
-          const int x = (int)(xs & 63), y = (int)((xs >> 6) & 63);
-          if (x - v.p.r < w.tlo || x + v.p.r > w.thi || y - v.p.r < w.tlo || y + v.p.r > w.thi) continue; /* box not fully trusted */
-          const int base = y * WIN + x;
-          uint32_t mine = NONE32; /* this lane's best candidate word; the box is visited 32 cells at a time, nearest first */
-          for (int j = 0; j < 8 && 32 * j < box; ++j) {
-            const uint32_t q = (uint32_t)((t & 31) + 32 * j);
-            if ((int)q < box && mine == NONE32) {
-              const int c = base + rel[j];
-              if (s.occupied(c, id)) mine = ((q << 1) << 21) | low;
-              else if (s.unknown(c, id)) mine = (((q << 1) | 1u) << 21) | low;
-            }
-            const uint32_t m = warp_min_into(&l_xs[e], mine, t & 31);
-            if ((m >> 22) < 32u * (uint32_t)(j + 1)) break; /* nearer than every cell still to visit: done (warp-uniform) */
-          }
-        }
-      }
-      ABM_CTA_SYNC();
-      ABM_CTA_FOR(t, NT) { /* one thread per open gregarious agent: draw and publish, or stay open */
-        for (uint32_t u = (uint32_t)t; u < ng; u += (uint32_t)NT) {
-          const uint32_t e = ULIST_CAP - 1 - u, xs = l_xs[e];
-          if (xs & XS_DONE) continue;
-          const uint32_t id = l_id[e], b = xs >> 21;
+        /* gregarious closest-neighbour search (src/agent_actions.jl:297-336): GREG_LANES lanes per agent walk the box cells
+         * nearest first, GREG_LANES at a time; the first chunk with an occupied cell (the closest neighbour: draw and move) or
+         * a still unknown one (wait) ends the search.  The lanes of a warp leave the loop together, so that the tail (the
+         * draw, one lane per agent) runs converged. */
+        for (uint32_t ubase = 0; ubase < ng; ubase += (uint32_t)(NT / GREG_LANES)) {
+          const uint32_t u = ubase + (uint32_t)(t / GREG_LANES);
+          const int lane_in = t % GREG_LANES;
+          const uint32_t e = ULIST_CAP - 1 - (u < ng ? u : 0u), xs = l_xs[e];
+          const bool open = u < ng && !(xs & XS_DONE);
+          const uint32_t id = l_id[e];
           const int x = (int)(xs & 63), y = (int)((xs >> 6) & 63);
           const uint8_t st = (uint8_t)(xs >> 12);
-          const bool inside = !(x - v.p.r < w.tlo || x + v.p.r > w.thi || y - v.p.r < w.tlo || y + v.p.r > w.thi);
-          if (inside && (b == 0x1FFu || !(b & 1u))) {
-            const uint8_t nst = greg_finish(v, id, st, b == 0x1FFu ? (int)GREG_NOBODY : (int)v.greg_order[b >> 1]);
+          const bool trusted = !(x - v.p.r < w.tlo || x + v.p.r > w.thi || y - v.p.r < w.tlo || y + v.p.r > w.thi);
+          const bool search = open && trusted; /* an untrusted box: the agent stays open */
+          const int base = y * WIN + x;
+          uint32_t found = NONE32; /* visiting rank << 1 | only-maybe of the group's first hit */
+          for (int q0 = 0; q0 < box; q0 += GREG_LANES) {
+            const int q = q0 + lane_in;
+            uint32_t mine = NONE32;
+            if (search && q < box) {
+              const int c = base + (int)grel[q];
+              if (s.occupied(c, id)) mine = (uint32_t)q << 1;
+              else if (s.unknown(c, id)) mine = ((uint32_t)q << 1) | 1u;
+            }
+            found = group_min(mine);
+            if (warp_all(!search || found != NONE32)) break;
+          }
+          if (search && lane_in == 0 && !(found != NONE32 && (found & 1u))) {
+            const uint8_t nst = greg_finish(v, id, st, found == NONE32 ? (int)GREG_NOBODY : (int)v.greg_order[found >> 1]);
             v.state[l_a[e]] = nst;
             contribute_final(min_new, w, id, x, y, nst);
             l_xs[e] = xs | XS_DONE;
             flag[0] = 1;
-          } else {
-            l_xs[e] = (xs & XS_LOW) | XS_BEST_NONE; /* search again next round */
+          } else if (open && lane_in == 0) {
             if (MAYBE_BUFS == 2) contribute_maybe(maybe[cur ^ 1], w, id, x, y, st);
-            if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) smem_add(&flag[1], 1u);
+            if (x >= HALO && x < HALO + CORE && y >= HALO && y < HALO + CORE) flag[1] = 1;
           }
         }
-        /* what this round read is dead now: make it the clean target of the next round */
-        for (int c = t; c < cells; c += NT) maybe[cur][c] = NONE32;
+      }
+      ABM_CTA_SYNC();
+      ABM_CTA_FOR(t, NT) { /* what this round read is dead now: make it the clean target of the next round */
+        fill_words(maybe[cur], NONE32, cells, t, NT);
         if (t == 0) { flag_next[0] = 0; flag_next[1] = 0; }
       }
       ABM_CTA_SYNC();
-      cur ^= 1;
+      cur ^= (MAYBE_BUFS == 2);
       if (flag[1] == 0 || flag[0] == 0) break;
       if (MAYBE_BUFS == 1) { /* the single buffer was cleared above: rebuild it from the entries still open */
         ABM_CTA_FOR(t, NT) {

@@ -113,6 +113,9 @@ typedef struct abm_handle abm_handle;
 
 /* fills cfg with the defaults of scripts/v0.1.jl:36-46 (80x80, regrowth 30, Δenergy 4, repro 0.001, cost 1) */
 void abm_config_default(abm_config* cfg);
+/* sizeof(abm_config) of this library: a binding that mirrors the struct by hand (julia/AbmEngine.jl, ctypes) checks its
+ * own layout against it before the first abm_create */
+int abm_config_size(void);
 
 /* replaces: AgentBasedModel(Sheep, GridSpace(dims; periodic, metric=:chebyshev); properties, rng, scheduler)
  * scripts/v0.1.jl:49-64.
@@ -249,6 +252,31 @@ int abm_comm_init_nccl(abm_handle* h, const void* unique_id128);
  * A neighbour that does not deliver within a few seconds makes abm_step fail with ABM_E_CUDA instead of hanging. */
 int abm_p2p_export(abm_handle* h, void* handle64);
 int abm_p2p_connect(abm_handle* h, const void* handles, int32_t n_ranks);
+
+/* ---- multi-GPU from ONE process: the reference's caller is a single Julia process (scripts/v0.3.jl:124, abmvideo ->
+ * step!(model, agent_step!, model_step!, n)) and cannot start a process per GPU.  An abm_group owns n_devices strip handles
+ * (whole 32-row core rows, as even as possible) of the GridSpace described by cfg (strip fields ignored) and drives them
+ * from the calling thread: each call below fans out to one worker thread per device and returns when all are done.  The
+ * strips exchange their boundaries over NVLink peer memory mapped inside the process (cudaDeviceEnablePeerAccess), or
+ * through an in-process host mailbox when the devices cannot reach each other.  All arrays are those of the WHOLE
+ * GridSpace, exactly as for a single handle; device_ids == NULL means devices 0 .. n_devices-1. ---- */
+typedef struct abm_group abm_group;
+int abm_group_create(const abm_config* cfg, int32_t n_devices, const int32_t* device_ids, abm_group** out);
+void abm_group_destroy(abm_group* g);
+int abm_group_set_grid(abm_group* g, const uint8_t* fully_grown, const int64_t* countdown, const uint8_t* walkmap,
+                       const int64_t* elevation);
+int abm_group_set_agents(abm_group* g, int64_t n, const int64_t* id, const int64_t* x, const int64_t* y,
+                         const double* energy, int64_t next_id);
+int abm_group_init_random(abm_group* g, int64_t n_sheep, uint64_t init_seed);
+int abm_group_set_global_state(abm_group* g, int64_t tick, int64_t behav, int64_t behav_counter);
+int abm_group_get_global_state(abm_group* g, int64_t* tick, int64_t* behav, int64_t* behav_counter, int64_t* next_id);
+int abm_group_step(abm_group* g, int64_t n_ticks);            /* replaces: Agents.step!(model, agent_step!, model_step!, n) */
+int abm_group_count_agents(abm_group* g, int64_t* n);
+int abm_group_get_agents(abm_group* g, int64_t* n_inout, int64_t* id, int64_t* x, int64_t* y, double* energy); /* id order */
+int abm_group_get_grid(abm_group* g, uint8_t* fully_grown, int64_t* countdown);
+int abm_group_reduce(abm_group* g, int32_t what, double* out);
+abm_handle* abm_group_member(abm_group* g, int32_t i);        /* strip i's handle (profiling, timing); owned by the group */
+const char* abm_group_last_error(abm_group* g);
 
 /* message for the last failing call on h (or on creation when h == NULL); valid until the next call */
 const char* abm_last_error(abm_handle* h);

@@ -533,6 +533,8 @@ void oracle_config_default(abm_config* c) {
   c->attractor_x = 40; c->attractor_y = 40; c->seed = 321;
 }
 
+int oracle_config_size(void) { return (int)sizeof(abm_config); }
+
 int oracle_create(const abm_config* cfg, oracle_handle** out) {
   if (!cfg || !out || cfg->struct_size != (int32_t)sizeof(abm_config) || cfg->nx < 1 || cfg->ny < 1) return ABM_E_BADARG;
   oracle_handle* h = new oracle_handle();

@@ -469,11 +469,22 @@ def test_emulated_device_side_initialisation(emu, oracle, nx, ny, n, wt, terrain
         assert_same_state(b.snapshot(), a.snapshot(), f"tick {t} after init")
 
 
-def test_device_side_initialisation_is_refused_on_strips(emu):
-    from abm_b200 import capi as _capi
-    e = emu.create(emu.default_config(nx=64, ny=64, periodic=1, walk_type=0, strip_y0=0, strip_ny=64, n_ranks=1, rank=0))
-    with pytest.raises(_capi.AbmError):
-        e.init_random(10, 1)
+def test_device_side_initialisation_on_a_strip_needs_the_whole_walkmap(emu, oracle):
+    """abm_init_random on a strip handle: random_walkable draws positions over the whole GridSpace, so a strip with terrain
+    refuses until the global walkmap was given; then (a ring of one here) it builds the single handle's world."""
+    from abm_b200 import capi as _capi, strips
+    cfgkw, w = make_case(64, 96, 500, 4, 1, terrain=True, seed=9, walkmap_regrowth=1)
+    e = strips.load_strip(emu, cfgkw, w, 1, 0)
+    with pytest.raises(_capi.AbmError) as ei:
+        e.init_random(500, 3)
+    assert ei.value.code == _capi.ABM_E_STATE
+    e.set_global_walkmap(w["walkmap"])
+    e.init_random(500, 3)
+    a = load_case(oracle, cfgkw, w)
+    a.init_random(500, 3)
+    for t in range(4):
+        a.step(1); e.step(1)
+        assert_same_state(strips.merge_snapshots([strips.strip_snapshot(e)]), a.snapshot(), f"strip init tick {t}")
 
 
 @pytest.mark.gpu

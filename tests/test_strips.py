@@ -247,3 +247,38 @@ def test_rings_of_three_and_four_gpus(libabm, oracle, tmp_path, world, name, tra
     for t in range(ticks):
         a.step(1)
         assert_same_state(strips.merge_snapshots([per_rank[r][t] for r in range(world)]), a.snapshot(), f"{name} world {world} tick {t}")
+
+
+# ------------------------------------------------------------------ single-process multi-device (abm_group)
+
+def _check_group(lib, oracle, devices, names):
+    """abm_group: one call fans out to one worker thread per strip; whole-GridSpace arrays in and out.  Against the oracle,
+    tick by tick, including a world built by the engine itself and the reductions of run!."""
+    for name in names:
+        cfgkw, w = _case(name)
+        a = load_case(oracle, cfgkw, w)
+        g = lib.create_group(lib.default_config(**cfgkw), devices)
+        g.set_grid(w["fully_grown"], w["countdown"], w.get("walkmap"), w.get("elevation"))
+        g.set_agents(w["ids"], w["x"], w["y"], w["energy"])
+        for t in range(6):
+            a.step(1); g.step(1)
+            assert_same_state(g.snapshot(), a.snapshot(), f"group {name} x{len(devices)} tick {t}")
+        assert [g.reduce(k) for k in range(5)] == [a.reduce(k) for k in range(5)]
+        g.init_random(w["ids"].size, 17); a.init_random(w["ids"].size, 17)
+        a.step(3); g.step(3)  # several ticks per call
+        assert_same_state(g.snapshot(), a.snapshot(), f"group {name} after init_random")
+        g.close(); a.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_group_of_strips_in_one_process_emulated(emu, oracle, n):
+    _check_group(emu, oracle, [0] * n, ["walkmap", "gregarious", "rw_clamped"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [2, 3])
+def test_group_of_strips_in_one_process_on_the_gpu(libabm, oracle, n):
+    """All the devices the box has (a 1-GPU box puts every strip on device 0: same code, same peer-memory mailboxes)."""
+    import torch
+    nd = torch.cuda.device_count()
+    _check_group(libabm, oracle, [i % nd for i in range(n)], ["walkmap", "gregarious", "attractor"])
