@@ -8,5 +8,5 @@ operator interface (``herbivore_dynamics`` / ``grass_growth_dynamics`` / ``step`
 from . import capi, model, strips, worlds  # noqa: F401
 from .capi import (ALTERNATED_WALK, RANDOM_WALK, RANDOM_WALK_ATTRACTOR, RANDOM_WALK_GREGARIOUS,  # noqa: F401
                    RANDOM_WALKMAP, AbmConfig, AbmError, CLib, Engine)
-from .model import (EngineAgentStep, EngineModelStep, SheepModel, WalkType, count, count_grass,  # noqa: F401
-                    grass_growth_dynamics, grasscolor, herbivore_dynamics, initialize_model, plot_data, run, sheep, step)
+from .model import (EngineAgentStep, EngineModelStep, SheepModel, WalkType, Where, count, count_grass,  # noqa: F401
+                    grass_growth_dynamics, grasscolor, herbivore_dynamics, initialize_model, penaltymap_heat, plot_data, run, sheep, step)

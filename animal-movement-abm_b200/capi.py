@@ -66,6 +66,12 @@ class AbmTransport(C.Structure):
     _fields_ = [("user", C.c_void_p), ("sendrecv", SENDRECV_FN), ("allreduce_sum_u64", ALLREDUCE_FN), ("allgather_u32", ALLGATHER_FN)]
 
 
+class AbmFilter(C.Structure):
+    """struct abm_filter (include/abm.h): a box of (energy, x, y), inclusive, 1-based."""
+
+    _fields_ = [("energy_lo", C.c_double), ("energy_hi", C.c_double), ("x_lo", C.c_int32), ("x_hi", C.c_int32), ("y_lo", C.c_int32), ("y_hi", C.c_int32)]
+
+
 class AbmError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"abm error {code}: {msg}")
@@ -100,6 +106,8 @@ SIGNATURES = {
     "set_agents_packed": (C.c_int, [_P, C.c_int64, _U32P, _U32P, _F64P, C.c_int64]),
     "get_agents_packed": (C.c_int, [_P, _I64P, _U32P, _U32P, _F64P]),
     "reduce": (C.c_int, [_P, C.c_int32, _F64P]),
+    "reduce_where": (C.c_int, [_P, C.c_int32, C.POINTER(AbmFilter), _F64P]),
+    "get_heat": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_float)]),
     "plan_routes": (C.c_int, [_P, C.c_int64, _I64P, _I64P, _I64P]),
     "get_paths": (C.c_int, [_P, C.c_int64, _I64P, _I64P, _I64P, _I64P, _I64P, _I64P]),
     "get_timing": (C.c_int, [_P, _F64P, C.c_int32]),
@@ -405,6 +413,21 @@ class Engine:
         out = C.c_double()
         self._ck(self.lib.fn["reduce"](self.h, int(what), C.byref(out)))
         return out.value
+
+    def reduce_where(self, what: int, energy=(-np.inf, np.inf), x=None, y=None) -> float:
+        """abm_reduce_where: `what` over the agents with energy, x, y inside the given inclusive ranges."""
+        x = x or (1, self.cfg.nx)
+        y = y or (1, self.cfg.ny)
+        f = AbmFilter(float(energy[0]), float(energy[1]), int(x[0]), int(x[1]), int(y[0]), int(y[1]))
+        out = C.c_double()
+        self._ck(self.lib.fn["reduce_where"](self.h, int(what), C.byref(f), C.byref(out)))
+        return out.value
+
+    def get_heat(self, which=0):
+        """0: countdown ./ regrowth_time (grasscolor); 1: the penaltymap (elevation) — float32 (ny, nx), computed on the device."""
+        out = np.empty((self.ny, self.nx), np.float32)
+        self._ck(self.lib.fn["get_heat"](self.h, int(which), out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
 
     def plan_routes(self, agent_ids, goal_x, goal_y):
         a = np.ascontiguousarray(agent_ids, dtype=np.int64)

@@ -681,6 +681,76 @@ int ABM_API(reduce)(abm_handle* h, int32_t what, double* out) {
   return ABM_OK;
 }
 
+int ABM_API(reduce_where)(abm_handle* h, int32_t what, const abm_filter* f, double* out) {
+  if (!h || !out || !f) return ABM_E_BADARG;
+  if (what != ABM_REDUCE_COUNT_AGENTS && what != ABM_REDUCE_SUM_ENERGY && what != ABM_REDUCE_MAX_ENERGY && what != ABM_REDUCE_MIN_ENERGY)
+    ABM_FAIL(h, ABM_E_BADARG, "abm_reduce_where takes the agent reductions (count, sum, max, min)");
+  int rc = set_device(h);
+  if (rc) return rc;
+  double mine = 0;
+  bool any = false;
+  const uint64_t n = h->n;
+  if (n > 0) {
+    if ((rc = stream_canonical(h))) return rc;
+    const uint64_t chunks = (n + ENERGY_CHUNK - 1) / ENERGY_CHUNK;
+    if ((rc = ensure(h, h->partials, chunks * 12 + 64))) return rc;
+    WherePartialBody wb;
+    wb.g = h->g; wb.cell = (const uint32_t*)h->cell[h->cur].p; wb.energy = (const double*)h->energy[h->cur].p; wb.n = n; wb.what = what;
+    wb.e_lo = f->energy_lo; wb.e_hi = f->energy_hi; wb.x_lo = f->x_lo - 1; wb.x_hi = f->x_hi - 1;
+    wb.y_lo = f->y_lo - 1 - h->g.y_off; wb.y_hi = f->y_hi - 1 - h->g.y_off; /* stored rows (a strip keeps its rows at an offset) */
+    wb.out = (double*)h->partials.p; wb.any = (uint32_t*)((double*)h->partials.p + chunks);
+    launch_foreach(h->stream, wb, chunks);
+    if ((rc = check_launch(h, "filtered reduce"))) return rc;
+    std::vector<double> part(chunks);
+    std::vector<uint32_t> cnt(chunks);
+    ABM_CK(h, copy_d2h(part.data(), wb.out, chunks * 8, h->stream));
+    ABM_CK(h, copy_d2h(cnt.data(), wb.any, chunks * 4, h->stream));
+    for (uint64_t i = 0; i < chunks; ++i) {
+      if (!cnt[i]) continue;
+      if (what == ABM_REDUCE_COUNT_AGENTS || what == ABM_REDUCE_SUM_ENERGY) mine += part[i];
+      else if (!any || (what == ABM_REDUCE_MAX_ENERGY ? part[i] > mine : part[i] < mine)) mine = part[i];
+      any = true;
+    }
+  }
+  if (!h->strip || h->n_ranks <= 1) { *out = mine; return ABM_OK; }
+  const int P = h->n_ranks;
+  uint64_t snd[2];
+  memcpy(&snd[0], &mine, 8);
+  snd[1] = any ? 1 : 0;
+  std::vector<uint64_t> all((size_t)2 * P);
+  if ((rc = comm_allgather_small(h, snd, 2, all.data()))) return rc;
+  double v = 0;
+  bool first = true;
+  for (int r = 0; r < P; ++r) {
+    double x;
+    memcpy(&x, &all[2 * r], 8);
+    if (what == ABM_REDUCE_MAX_ENERGY || what == ABM_REDUCE_MIN_ENERGY) {
+      if (!all[2 * r + 1]) continue;
+      if (first || (what == ABM_REDUCE_MAX_ENERGY ? x > v : x < v)) v = x;
+      first = false;
+    } else v += x;
+  }
+  *out = v;
+  return ABM_OK;
+}
+
+int ABM_API(get_heat)(abm_handle* h, int32_t which, float* out) {
+  if (!h || !out || which < 0 || which > 1) return ABM_E_BADARG;
+  if (!h->grid_set) ABM_FAIL(h, ABM_E_STATE, "abm_set_grid has not been called");
+  int rc = set_device(h);
+  if (rc) return rc;
+  const Geo& g = h->g;
+  const uint64_t cells = (uint64_t)g.nx * (uint64_t)g.ny;
+  if ((rc = ensure(h, h->stage, cells * 4 + 64))) return rc;
+  HeatExportBody hb;
+  hb.g = g; hb.grass = (const uint8_t*)h->grass.p; hb.elev = (const int16_t*)h->elev.p; hb.which = which;
+  hb.inv_rt = h->cfg.regrowth_time > 0 ? 1.0f / (float)h->cfg.regrowth_time : 0.0f; hb.out = (float*)h->stage.p;
+  launch_foreach(h->stream, hb, cells);
+  if ((rc = check_launch(h, "heat export"))) return rc;
+  ABM_CK(h, copy_d2h(out, h->stage.p, cells * 4, h->stream));
+  return ABM_OK;
+}
+
 int ABM_API(plan_routes)(abm_handle* h, int64_t b, const int64_t* agent_id, const int64_t* goal_x, const int64_t* goal_y) {
   if (!h) return ABM_E_BADARG;
   if (b < 0 || (b > 0 && (!agent_id || !goal_x || !goal_y))) ABM_FAIL(h, ABM_E_BADARG, "null request arrays");
@@ -843,7 +913,7 @@ int ABM_API(p2p_export)(abm_handle* h, void* handle64) {
     h->p2p_lay.births_bytes = ((1 + h->p2p_birthmax) * 4 + 255) & ~(uint64_t)255;
     ABM_CK(h, cudaMalloc((void**)&h->p2p_mine, h->p2p_lay.total_bytes()));
     ABM_CK(h, cudaMemset(h->p2p_mine, 0, h->p2p_lay.total_bytes()));
-    ABM_CK(h, cudaDeviceSynchronize());
+    ABM_CK(h, cudaStreamSynchronize(cudaStreamLegacy));
   }
   cudaIpcMemHandle_t mh;
   ABM_CK(h, cudaIpcGetMemHandle(&mh, h->p2p_mine));

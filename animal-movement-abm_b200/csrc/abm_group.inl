@@ -130,6 +130,12 @@ int ABM_API(group_create)(const abm_config* cfg, int32_t n_devices, const int32_
   if (!cfg || !out || n_devices < 1 || n_devices > 8) { g_create_error = "abm_group_create: 1..8 devices"; return ABM_E_BADARG; }
   *out = nullptr;
   if (cfg->nx % CORE || cfg->ny % CORE || cfg->ny / CORE < n_devices) { g_create_error = "abm_group_create: grid dims must be multiples of 32 with at least one 32-row core row per device"; return ABM_E_BADARG; }
+#ifndef ABM_EMU
+  /* one strip per device: while a strip's kernel waits for its neighbour's message, an allocation by the neighbour's thread
+   * would synchronise the whole device (cudaMalloc / cudaFree do) and never return */
+  for (int i = 0; i < n_devices; ++i) for (int j = 0; j < i; ++j)
+    if ((device_ids ? device_ids[i] : i) == (device_ids ? device_ids[j] : j)) { g_create_error = "abm_group_create: every strip needs its own device"; return ABM_E_BADARG; }
+#endif
   abm_group* g = new (std::nothrow) abm_group();
   if (!g) return ABM_E_NOMEM;
   g->cfg = *cfg; g->n = n_devices;

@@ -991,5 +991,39 @@ struct EnergyPartialBody {
   }
 };
 
+/* abm_reduce_where: count / sum / min / max of energy over the agents inside a box of (energy, x, y); one partial per chunk,
+ * combined in order by the host */
+struct WherePartialBody {
+  Geo g; const uint32_t* cell; const double* energy; uint64_t n; int32_t what;
+  double e_lo, e_hi; int32_t x_lo, x_hi, y_lo, y_hi; /* 0-based stored coordinates, inclusive */
+  double* out; uint32_t* any;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint64_t lo = i * ENERGY_CHUNK, hi = lo + ENERGY_CHUNK < n ? lo + ENERGY_CHUNK : n;
+    double v = 0; uint32_t cnt = 0;
+    for (uint64_t k = lo; k < hi; ++k) {
+      const double e = energy[k];
+      int x, y;
+      dec(g, cell[k], x, y);
+      if (!(e >= e_lo && e <= e_hi && x >= x_lo && x <= x_hi && y >= y_lo && y <= y_hi)) continue;
+      if (what == ABM_REDUCE_COUNT_AGENTS) v += 1;
+      else if (what == ABM_REDUCE_SUM_ENERGY) v += e;
+      else if (what == ABM_REDUCE_MAX_ENERGY) v = (cnt == 0 || e > v) ? e : v;
+      else v = (cnt == 0 || e < v) ? e : v;
+      ++cnt;
+    }
+    out[i] = v; any[i] = cnt;
+  }
+};
+
+/* abm_get_heat: countdown / regrowth_time, or the elevation, as floats in the host's layout (x fastest) */
+struct HeatExportBody {
+  Geo g; const uint8_t* grass; const int16_t* elev; int32_t which; float inv_rt; float* out;
+  ABM_HD void operator()(uint64_t i) const {
+    const uint64_t y = i / (uint64_t)g.nx, x = i - y * (uint64_t)g.nx;
+    const uint32_t c = enc(g, (int)x, (int)y);
+    out[i] = which == 0 ? (float)(grass[c] == GRASS_PAD ? 0 : (grass[c] & 0x7F)) * inv_rt : (float)elev[c];
+  }
+};
+
 }  // namespace abm
 #endif /* ABM_KERNELS_H_ */

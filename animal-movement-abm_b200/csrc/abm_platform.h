@@ -145,7 +145,13 @@ ABM_D unsigned long long atomic_add64(unsigned long long* p, unsigned long long 
 ABM_D uint8_t load_state(const uint8_t* p) { return __ldcg(p); }
 ABM_D int popc(uint32_t v) { return __popc(v); }
 /* position of the (k + 1)-th set bit of m (k < popc(m)) */
-ABM_D int nth_set_bit(uint32_t m, int k) { return (int)__fns(m, 0u, k + 1); }
+ABM_D int nth_set_bit(uint32_t m, int k) { /* m has at most 8 bits (a Moore neighbourhood): three popcount steps, a third of __fns */
+  int d = 0;
+  int c = __popc(m & 0xFu); if (k >= c) { k -= c; d = 4; m >>= 4; }
+  c = __popc(m & 0x3u); if (k >= c) { k -= c; d += 2; m >>= 2; }
+  c = (int)(m & 1u); if (k >= c) d += 1;
+  return d;
+}
 
 extern unsigned long long g_launches;
 
@@ -259,8 +265,9 @@ static inline void launch_cta_lb(abm_stream_t s, const F& f, uint64_t n_ctas, si
 static inline abm_err_t dev_malloc(void** p, size_t bytes) {
   abm_err_t e = cudaMalloc(p, bytes ? bytes : 1);
   if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes ? bytes : 1);
-  /* the handle's stream is non-blocking: make the legacy-stream memset land before anyone writes the buffer */
-  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  /* the handle's stream is non-blocking: make the legacy-stream memset land before anyone writes the buffer.  Only the
+   * legacy stream is waited for, not the whole device (other handles' kernels may be running). */
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
   return e;
 }
 static inline void dev_free(void* p) { if (p) cudaFree(p); }

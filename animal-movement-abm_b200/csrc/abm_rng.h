@@ -34,10 +34,8 @@ ABM_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
                           uint32_t out[4]) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    /* one widening multiply per product (IMAD.WIDE) instead of a high and a low one */
-    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
-    const uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0;
-    const uint32_t h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+    const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
     c0 = h1 ^ c1 ^ k0;
     c1 = l1;
     c2 = h0 ^ c3 ^ k1;

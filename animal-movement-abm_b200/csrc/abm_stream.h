@@ -35,10 +35,10 @@
 namespace abm {
 
 #ifndef ABM_S_THREADS
-#define ABM_S_THREADS 128
+#define ABM_S_THREADS 96
 #endif
 #ifndef ABM_S_MIN_CTAS
-#define ABM_S_MIN_CTAS 10
+#define ABM_S_MIN_CTAS 21
 #endif
 enum { S_THREADS = ABM_S_THREADS, S_MIN_CTAS = ABM_S_MIN_CTAS }; /* CTA size of the tick kernel, CTAs per SM its registers must allow */
 /* record word 0: destination cell inside its core (ly << 5 | lx) | direction << 10 (0..7 moved, DIR_STAY) | flags */

@@ -38,7 +38,7 @@ enum { NONE32 = 0xFFFFFFFFu };
 #define ABM_ULIST_CAP 1024
 #endif
 #ifndef ABM_ARRIVE_CAP
-#define ABM_ARRIVE_CAP 768
+#define ABM_ARRIVE_CAP 384
 #endif
 enum { ULIST_CAP = ABM_ULIST_CAP, ARRIVE_CAP = ABM_ARRIVE_CAP, RUNOF_CAP = 2048, RUNTABLE_WORDS = 4 * MAX_RUNS + 1 + RUNOF_CAP / 4 };
 
@@ -416,7 +416,8 @@ struct ResolveWindow {
               if (s.occupied(c, id)) mine = (uint32_t)q << 1;
               else if (s.unknown(c, id)) mine = ((uint32_t)q << 1) | 1u;
             }
-            found = group_min(mine);
+            const uint32_t gm = group_min(mine); /* every lane of the warp takes part in the shuffles of every chunk ... */
+            if (found == NONE32) found = gm;     /* ... but a group keeps its first hit while the others go on */
             if (warp_all(!search || found != NONE32)) break;
           }
           if (search && lane_in == 0 && !(found != NONE32 && (found & 1u))) {

@@ -240,6 +240,20 @@ def count_grass(model: SheepModel) -> int:
     return int(np.count_nonzero(model._fg))
 
 
+class Where:
+    """A filter of an adata tuple `(property, aggregator, filter)` that the engine evaluates on the device
+    (abm_reduce_where): agents with energy, x, y inside the given inclusive ranges.  Also callable on a host-side agent
+    record, so it works wherever a plain predicate does."""
+
+    def __init__(self, energy=(-np.inf, np.inf), x=None, y=None):
+        self.energy, self.x, self.y = energy, x, y
+
+    def __call__(self, a):
+        ex, (px, py) = a["energy"], a["pos"]
+        return (self.energy[0] <= ex <= self.energy[1] and (self.x is None or self.x[0] <= px <= self.x[1])
+                and (self.y is None or self.y[0] <= py <= self.y[1]))
+
+
 _FAST_AGENT = {("energy", "sum"): capi.REDUCE_SUM_ENERGY, ("energy", "maximum"): capi.REDUCE_MAX_ENERGY, ("energy", "max"): capi.REDUCE_MAX_ENERGY,
                ("energy", "minimum"): capi.REDUCE_MIN_ENERGY, ("energy", "min"): capi.REDUCE_MIN_ENERGY}
 
@@ -265,6 +279,16 @@ def _collect_agents(model: SheepModel, adata):
         elif flt is None and e is not None and pname == "energy" and _agg_name(agg) == "mean":
             n = e.reduce(capi.REDUCE_COUNT_AGENTS)
             row[col] = e.reduce(capi.REDUCE_SUM_ENERGY) / n if n else float("nan")
+        elif isinstance(flt, Where) and e is not None and ((prop is sheep and agg is count) or (pname, _agg_name(agg)) in _FAST_AGENT or (pname, _agg_name(agg)) == ("energy", "mean")):
+            # filtered tuple on the device: no agent leaves the GPU
+            kw = dict(energy=flt.energy, x=flt.x, y=flt.y)
+            if prop is sheep:
+                row[col] = int(e.reduce_where(capi.REDUCE_COUNT_AGENTS, **kw))
+            elif _agg_name(agg) == "mean":
+                n = e.reduce_where(capi.REDUCE_COUNT_AGENTS, **kw)
+                row[col] = e.reduce_where(capi.REDUCE_SUM_ENERGY, **kw) / n if n else float("nan")
+            else:
+                row[col] = e.reduce_where(_FAST_AGENT[(pname, _agg_name(agg))], **kw)
         else:  # general case: materialise the agents on the host
             ids, x, y, en = model.agents()
             fields = dict(id=ids, energy=en, x=x, y=y)
@@ -305,7 +329,16 @@ def run(model: SheepModel, agent_step: EngineAgentStep, model_step: EngineModelS
 def grasscolor(model: SheepModel):
     """`grasscolor(model) = model.countdown ./ model.regrowth_time` — the `heatarray` of `plot_abm_model`
     (src/plotting.jl:33, :27-57), shape (ny, nx), 1.0 = just eaten / fully grown, towards 0 = about to regrow."""
+    if model._engine is not None:  # computed on the device (abm_get_heat): 4 bytes per cell come back instead of 9
+        return model._engine.get_heat(0)
     return model.countdown.astype(np.float64) / float(model.regrowth_time)
+
+
+def penaltymap_heat(model: SheepModel):
+    """`heatarray = model -> penaltymap(model.pathfinder)` (scripts/v0.6.jl:179): the elevation the PenaltyMap was built from."""
+    if model._engine is not None:
+        return model._engine.get_heat(1)
+    return np.zeros((model.ny, model.nx), np.float32) if model.elevation is None else np.asarray(model.elevation, np.float32)
 
 
 def plot_data(model: SheepModel):

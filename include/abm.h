@@ -199,6 +199,19 @@ int abm_get_agents_packed(abm_handle* h, int64_t* n_inout, uint32_t* id, uint32_
  * collective (every rank makes it) and returns the value over the WHOLE GridSpace, combined in rank order. */
 int abm_reduce(abm_handle* h, int32_t what, double* out);
 
+/* replaces: filtered adata tuples of run!, `(property, aggregator, filter)` (Agents.jl; naming at src/agent_actions.jl:964),
+ * for filters that are boxes: agents with energy in [energy_lo, energy_hi] standing on x in [x_lo, x_hi], y in [y_lo, y_hi]
+ * (1-based, inclusive; use -inf / +inf and 1 / nx, ny for "any").  `what` as for abm_reduce (COUNT_GROWN is not an agent
+ * reduction: ABM_E_BADARG); min / max of an empty selection give 0.  Collective on strip handles, like abm_reduce. */
+typedef struct abm_filter { double energy_lo, energy_hi; int32_t x_lo, x_hi, y_lo, y_hi; } abm_filter;
+int abm_reduce_where(abm_handle* h, int32_t what, const abm_filter* f, double* out);
+
+/* replaces: the heat arrays the reference's plots draw, computed on the device and returned as nx*ny floats (x fastest):
+ *   which = 0: `model.countdown ./ model.regrowth_time` (grasscolor / heatarray of plot_abm_model, src/plotting.jl:27-57)
+ *   which = 1: `penaltymap(model.pathfinder)` = the elevation the PenaltyMap was built from (scripts/v0.6.jl:179)
+ * Strip handles: strip_ny + 64 rows, like abm_get_grid. */
+int abm_get_heat(abm_handle* h, int32_t which, float* out);
+
 /* replaces: plan_route!(agent, dest, model.pathfinder) for a batch of agents (src/agent_actions.jl:217-221;
  * Agents.Pathfinding.find_path).  goal coordinates 1-based.  Existing routes of these agents are overwritten;
  * an unreachable goal leaves the agent without a route. */
@@ -259,7 +272,7 @@ int abm_p2p_connect(abm_handle* h, const void* handles, int32_t n_ranks);
  * from the calling thread: each call below fans out to one worker thread per device and returns when all are done.  The
  * strips exchange their boundaries over NVLink peer memory mapped inside the process (cudaDeviceEnablePeerAccess), or
  * through an in-process host mailbox when the devices cannot reach each other.  All arrays are those of the WHOLE
- * GridSpace, exactly as for a single handle; device_ids == NULL means devices 0 .. n_devices-1. ---- */
+ * GridSpace, exactly as for a single handle; device_ids == NULL means devices 0 .. n_devices-1 (all distinct). ---- */
 typedef struct abm_group abm_group;
 int abm_group_create(const abm_config* cfg, int32_t n_devices, const int32_t* device_ids, abm_group** out);
 void abm_group_destroy(abm_group* g);

@@ -731,6 +731,30 @@ int oracle_reduce(oracle_handle* h, int32_t what, double* out) {
   *out = v;
   return 0;
 }
+int oracle_reduce_where(oracle_handle* h, int32_t what, const abm_filter* f, double* out) {
+  Model& m = h->m;
+  if (!f || !out || what == ABM_REDUCE_COUNT_GROWN || what < 0 || what > ABM_REDUCE_MIN_ENERGY) return ABM_E_BADARG;
+  double v = 0;
+  bool first = true;
+  for (std::map<i64, Sheep>::iterator it = m.agents.begin(); it != m.agents.end(); ++it) {
+    const Sheep& s = it->second;
+    if (!(s.energy >= f->energy_lo && s.energy <= f->energy_hi && s.x >= f->x_lo && s.x <= f->x_hi && s.y >= f->y_lo && s.y <= f->y_hi)) continue;
+    if (what == ABM_REDUCE_COUNT_AGENTS) v += 1;
+    else if (what == ABM_REDUCE_SUM_ENERGY) v += s.energy;
+    else if (first || (what == ABM_REDUCE_MAX_ENERGY ? s.energy > v : s.energy < v)) v = s.energy;
+    first = false;
+  }
+  *out = v;
+  return 0;
+}
+int oracle_get_heat(oracle_handle* h, int32_t which, float* out) {
+  Model& m = h->m;
+  if (!out || which < 0 || which > 1) return ABM_E_BADARG;
+  const size_t G = (size_t)m.nx * m.ny;
+  const float inv = m.cfg.regrowth_time > 0 ? 1.0f / (float)m.cfg.regrowth_time : 0.0f;
+  for (size_t i = 0; i < G; ++i) out[i] = which == 0 ? (float)m.countdown[i] * inv : (float)m.elevation[i];
+  return 0;
+}
 int oracle_plan_routes(oracle_handle* h, int64_t b, const int64_t* aid, const int64_t* gx, const int64_t* gy) {
   Model& m = h->m;
   m.astar_expansions = 0;

@@ -102,11 +102,42 @@ def test_initialize_model_on_the_device(emu, oracle):
     assert m.tick == 5 and m.nagents() > 0
 
 
+def _check_filtered_adata_and_heat(lib, oracle):
+    """Filtered adata tuples `(property, aggregator, filter)` whose filter is a box are reduced on the device
+    (abm_reduce_where) and equal the host-side evaluation of the same predicate; the heat arrays of the plots come from the
+    device (abm_get_heat) and equal `countdown ./ regrowth_time` / the elevation."""
+    m, astep, mstep = _script_model(lib, "v0.6")
+    A.step(m, astep, mstep, 4)
+    w = A.Where(energy=(2.0, 9.0), x=(10, 60), y=(5, 70))
+    adf, _ = A.run(m, astep, mstep, 3, adata=[(A.sheep, A.count, w), ("energy", sum, w), ("energy", max, w), ("energy", min, w)])
+    ids, x, y, e = m.agents()
+    keep = (e >= 2.0) & (e <= 9.0) & (x >= 10) & (x <= 60) & (y >= 5) & (y <= 70)
+    assert keep.any() and not keep.all()
+    last = adf.iloc[-1]
+    assert last["count_sheep"] == keep.sum() and last["sum_energy"] == e[keep].sum() and last["max_energy"] == e[keep].max() and last["min_energy"] == e[keep].min()
+    # the same numbers from the oracle's restatement of the entry point
+    ref, _, _ = _script_model(oracle, "v0.6")
+    A.step(ref, astep, mstep, 7)
+    assert ref._engine.reduce_where(A.capi.REDUCE_SUM_ENERGY, energy=(2.0, 9.0), x=(10, 60), y=(5, 70)) == last["sum_energy"]
+    heat = A.grasscolor(m)
+    assert heat.dtype == np.float32 and np.allclose(heat, m.countdown / m.regrowth_time, rtol=1e-6)
+    assert np.array_equal(A.penaltymap_heat(m), np.asarray(m.elevation, np.float32))
+
+
+def test_filtered_adata_and_heat_arrays_emulated(emu, oracle):
+    _check_filtered_adata_and_heat(emu, oracle)
+
+
+@pytest.mark.gpu
+def test_filtered_adata_and_heat_arrays_on_the_gpu(libabm, oracle):
+    _check_filtered_adata_and_heat(libabm, oracle)
+
+
 def test_plot_data_matches_the_reference_heat_array(emu):
     """`plot_abm_model` draws `countdown ./ regrowth_time` and the sheep positions (src/plotting.jl:27-57)."""
     m, astep, mstep = _script_model(emu, "v0.1")
     A.step(m, astep, mstep, 3)
     d = A.plot_data(m)
     assert d["heatarray"].shape == (m.ny, m.nx) and d["heatarray"].min() >= 0 and d["heatarray"].max() <= 1
-    assert np.array_equal(d["heatarray"], m.countdown / m.regrowth_time)
+    assert np.allclose(d["heatarray"], m.countdown / m.regrowth_time, rtol=1e-6)
     assert d["x"].size == m.nagents() and d["x"].min() >= 1 and d["y"].max() <= m.ny
