@@ -972,3 +972,13 @@ int ABM_API(get_timing)(abm_handle* h, double* out, int32_t n) {
 }
 
 }  // extern "C"
+
+#if defined(ABM_PHASE_CLOCKS) && !defined(ABM_EMU)
+/* tuning builds only: the summed phase clocks of the instrumented kernels (32 counters), reset after the read */
+extern "C" int abm_debug_phase_clocks(unsigned long long* out) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, abm::abm_phase_clk, sizeof(unsigned long long) * 32) != cudaSuccess) return ABM_E_CUDA;
+  unsigned long long zero[32] = {0};
+  return cudaMemcpyToSymbol(abm::abm_phase_clk, zero, sizeof zero) == cudaSuccess ? 0 : ABM_E_CUDA;
+}
+#endif

@@ -70,6 +70,12 @@ static inline void launch_foreach(abm_stream_t, const F& f, uint64_t n, const ch
  * shuffled order.  Code outside the phases must be uniform across the CTA. */
 #define ABM_CTA_FOR(t, NT) for (int t = 0; t < (int)(NT); ++t)
 #define ABM_CTA_SYNC() ((void)0)
+/* a stretch of phases run by the first warp alone: `if (ABM_IN_WARP0) { ABM_WARP0_FOR(t) { ... } ABM_WARP_SYNC(); ... }` */
+#define ABM_IN_WARP0 true
+#define ABM_WARP0_FOR(t) for (int t = 0; t < 32; ++t)
+#define ABM_WARP_SYNC() ((void)0)
+#define ABM_PHASE_BEGIN() ((void)0)
+#define ABM_PHASE(k) ((void)0)
 static inline uint32_t smem_min(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v < o) *p = v; return o; }
 static inline uint32_t smem_max(uint32_t* p, uint32_t v) { uint32_t o = *p; if (v > o) *p = v; return o; }
 static inline uint32_t smem_add(uint32_t* p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
@@ -125,6 +131,7 @@ static inline const char* err_string(abm_err_t e) { return e ? "emulated allocat
 #else
 /* ------------------------------------------------------------------ CUDA, sm_100a (the product) ---------- */
 #include <cuda_runtime.h>
+#include <atomic>
 #define ABM_HD __device__ __forceinline__
 #define ABM_D __device__ __forceinline__
 #define ABM_HOSTDEV __host__ __device__ __forceinline__
@@ -155,6 +162,17 @@ ABM_D int nth_set_bit(uint32_t m, int k) { /* m has at most 8 bits (a Moore neig
 
 extern unsigned long long g_launches;
 
+/* -DABM_PHASE_CLOCKS (tuning builds only, tools/phase_probe.py): SM cycles between the marks of a CTA-structured kernel,
+ * taken by thread 0 and summed over all CTAs into abm_phase_clk[] (read and reset through abm_debug_phase_clocks) */
+#ifdef ABM_PHASE_CLOCKS
+__device__ unsigned long long abm_phase_clk[32];
+#define ABM_PHASE_BEGIN() long long abm_phase_t0_ = clock64()
+#define ABM_PHASE(k) do { if (threadIdx.x == 0) { const long long c_ = clock64(); atomicAdd(&abm_phase_clk[k], (unsigned long long)(c_ - abm_phase_t0_)); abm_phase_t0_ = c_; } } while (0)
+#else
+#define ABM_PHASE_BEGIN() ((void)0)
+#define ABM_PHASE(k) ((void)0)
+#endif
+
 template <class F>
 __global__ void __launch_bounds__(256) k_foreach(const F f, uint64_t n) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -171,6 +189,9 @@ static inline void launch_foreach(abm_stream_t s, const F& f, uint64_t n, const 
 
 #define ABM_CTA_FOR(t, NT) for (int t = (int)threadIdx.x, abm_once_ = 1; abm_once_ && t < (int)(NT); abm_once_ = 0)
 #define ABM_CTA_SYNC() __syncthreads()
+#define ABM_IN_WARP0 (threadIdx.x < 32)
+#define ABM_WARP0_FOR(t) for (int t = (int)threadIdx.x, abm_once_ = 1; abm_once_; abm_once_ = 0)
+#define ABM_WARP_SYNC() __syncwarp()
 ABM_D uint32_t smem_min(uint32_t* p, uint32_t v) { return atomicMin(p, v); }
 ABM_D uint32_t smem_max(uint32_t* p, uint32_t v) { return atomicMax(p, v); }
 ABM_D uint32_t smem_add(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
@@ -239,11 +260,14 @@ template <class F>
 static inline void launch_cta(abm_stream_t s, const F& f, uint64_t n_ctas, int threads, size_t smem_bytes) {
   if (n_ctas == 0) return;
   ++g_launches;
-  static bool configured = false; /* per kernel instantiation */
-  if (!configured) {
+  static std::atomic<unsigned long long> configured{0}; /* per kernel instantiation: one bit per device (the attributes are per device) */
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(configured.load(std::memory_order_relaxed) & bit)) {
     cudaFuncSetAttribute(k_cta<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(k_cta<F>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
+    configured.fetch_or(bit, std::memory_order_relaxed);
   }
   k_cta<F><<<(unsigned)n_ctas, threads, smem_bytes, s>>>(f);
 }

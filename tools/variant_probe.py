@@ -32,13 +32,16 @@ def main():
         e = b.load(capi.CLib(path, "abm_"), cfg, w, device=0)
         e.set_profiling(True)
         e.step(3)
-        tot, ms = {}, 0.0
+        tot, ms, rounds, launches = {}, 0.0, 0.0, 0.0
         for _ in range(args.ticks):
             e.step(1)
-            ms += e.timing()["ms_total"] / args.ticks
+            tm = e.timing()
+            ms += tm["ms_total"] / args.ticks
+            rounds += tm["rounds"] / args.ticks
+            launches += tm["launches"] / args.ticks
             for k, v in e.kernel_stats().items():
                 tot[k] = tot.get(k, 0) + v["ms"] / args.ticks
-        print(os.path.basename(path), f"tick {ms:.4f} ms", {k: round(v, 4) for k, v in tot.items()}, flush=True)
+        print(os.path.basename(path), f"tick {ms:.4f} ms", {k: round(v, 4) for k, v in tot.items()}, f"per-agent rounds {rounds:.1f} launches {launches:.1f}", flush=True)
         e.close()
 
 
