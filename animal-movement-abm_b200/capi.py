@@ -52,6 +52,8 @@ class AbmConfig(C.Structure):
         ("strip_ny", C.c_int32),
         ("n_ranks", C.c_int32),
         ("rank", C.c_int32),
+        ("scheduler", C.c_int32),
+        ("reserved1", C.c_int32),
     ]
 
 

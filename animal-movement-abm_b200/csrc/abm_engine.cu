@@ -288,6 +288,7 @@ struct abm_handle {
   uint64_t kf_grid = 1024;        /* CTAs of those launches: an upper bound learnt from the previous tick */
   int32_t tile_rounds = 8;        /* in-window rounds of the tile resolve kernel (ABM_TILE_ROUNDS overrides; tests use 1) */
   int32_t tile_margin = HALO;     /* halo cells actually taken into a core's window (ABM_TILE_MARGIN overrides) */
+  DevBuf okey;                    /* Schedulers.randomly: order key per agent (own + ghost), recomputed every tick */
   int32_t nsx = 0, nsy = 0;
   DevBuf sub_off[2], sub_cnt[2], birth_pos, birth_parent, ingest_sub, mig_cnt, mig_a, mig_lc;
   bool use_migrants = false; /* ABM_MIGRANTS=1: border crossers are listed per destination core and the commit reads only its
@@ -382,15 +383,40 @@ static int build_greg_table(abm_handle* h) {
   return 0;
 }
 
+/* the scheduler's order keys (abm_rng.h) of tick `tick`, when nextid(model) is `next_id` at its start */
+static SchedKey sched_key(const abm_handle* h, uint64_t tick, uint64_t next_id) {
+  SchedKey sk;
+  memset(&sk, 0, sizeof sk);
+  if (h->cfg.scheduler == ABM_SCHED_RANDOMLY) { sk.on = 1; sk.hb = sched_half_bits(next_id); sched_round_keys(h->cfg.seed, tick, sk.k); }
+  return sk;
+}
+/* ids are below id_bound: what their order keys are below (bitmaps and ranks over the schedule are indexed by key) */
+static uint64_t key_space(const abm_handle* h, uint64_t id_bound) {
+  return h->cfg.scheduler == ABM_SCHED_RANDOMLY ? std::max<uint64_t>(id_bound, 1ull << (2 * sched_half_bits(id_bound))) : id_bound;
+}
+/* Schedulers.randomly: room for the order keys of `capacity` agents (call before make_view binds v.okey) ... */
+static int order_keys_room(abm_handle* h, uint64_t capacity) {
+  return h->cfg.scheduler == ABM_SCHED_RANDOMLY ? ensure(h, h->okey, (capacity + 1) * 4) : 0;
+}
+/* ... and the keys of agents [first, first + count) of the current SoA for the tick that is about to run */
+static void order_keys(abm_handle* h, uint64_t first, uint64_t count) {
+  if (h->cfg.scheduler != ABM_SCHED_RANDOMLY || count == 0) return;
+  OrderKeyBody ok;
+  ok.sk = sched_key(h, h->tick, h->next_id); ok.id = (const uint32_t*)h->id[h->cur].p + first; ok.okey = (uint32_t*)h->okey.p + first;
+  launch_foreach(h->stream, ok, count);
+}
+
 static View make_view(abm_handle* h) {
   View v;
   memset(&v, 0, sizeof v);
   v.g = h->g;
   v.p = h->params;
   v.p.tick = h->tick;
+  v.p.sk = sched_key(h, h->tick, h->next_id);
   v.n = (uint32_t)h->n;
   v.cell = (uint32_t*)h->cell[h->cur].p;
   v.id = (uint32_t*)h->id[h->cur].p;
+  v.okey = v.p.sk.on ? (const uint32_t*)h->okey.p : v.id;
   v.energy = (double*)h->energy[h->cur].p;
   v.state = (uint8_t*)h->state.p;
   v.slot = (uint32_t*)h->slot.p;
@@ -520,6 +546,8 @@ static int tick_once(abm_handle* h) {
   if ((rc = ensure_agent_scratch(h, n))) return rc;
   uint32_t* ctr = (uint32_t*)h->counters.p;
   ABM_CK(h, dev_memset(ctr, 0, 3 * sizeof(uint32_t), h->stream)); /* keeps the sticky error word */
+  if ((rc = order_keys_room(h, n))) return rc;
+  order_keys(h, 0, n);
   View v = make_view(h);
 
   if (n > 0 && h->cfg.walk_type == ABM_ALTERNATED_WALK) {
@@ -565,7 +593,7 @@ static int tick_once(abm_handle* h) {
   const int nxt = h->cur ^ 1;
   uint32_t* new_start = (uint32_t*)h->cell_start[nxt].p;
   { ProfScope ps(h->prof, h->stream, "memset_cell_counts", gt + 1); ABM_CK(h, dev_memset(new_start, 0, (gt + 1) * 4, h->stream)); }
-  const uint64_t words = bitmap_words(h->next_id);
+  const uint64_t words = bitmap_words(key_space(h, h->next_id));
   const bool repro = h->cfg.reproduce != 0;
   if (repro) {
     if ((rc = ensure(h, h->bits, (words + 4) * 4))) return rc;
@@ -683,6 +711,8 @@ static int tick_tile(abm_handle* h) {
     }
     if ((rc = strip_prepare(h))) return rc; /* before anybody takes pointers */
   }
+  if ((rc = order_keys_room(h, n + (h->strip ? 2 * h->bcap : 0)))) return rc;
+  order_keys(h, 0, n);
   View v = make_view(h);
   const SubIndex si = sub_index(h, h->cur);
   const int wt = h->cfg.walk_type;
@@ -706,6 +736,7 @@ static int tick_tile(abm_handle* h) {
     return check_launch(h, "tile resolve");
   };
   if (h->strip && (rc = strip_exchange_agents(h))) return rc; /* neighbours' boundary rows become ghost rows behind the own agents */
+  if (h->strip) order_keys(h, n, 2 * h->bcap); /* the ghosts' order keys (slots beyond the real counts are never read) */
   if (n + h->n_ghost > 0 && needs_resolve && (rc = launch_tiles(0, core_rows))) return rc;
   /* figures the host needs before it can go on: open agents, reproducing agents (sizes of the output SoA); in strip
    * mode from every rank, through one all-reduce of device-resident counters */
@@ -758,7 +789,7 @@ static int tick_tile(abm_handle* h) {
     }
   }
   const int nxt = h->cur ^ 1;
-  const uint64_t words = bitmap_words(h->next_id);
+  const uint64_t words = bitmap_words(key_space(h, h->next_id));
   /* commit + grass + re-grouping (+ offspring ids on one GPU); `go` = device flag checked by the kernels, or null */
   auto commit_phase = [&](uint64_t bflags, const uint32_t* go) -> int {
     const uint64_t arrivals_cap = h->strip ? 2 * h->bcap : 0; /* ghost agents (and their offspring) may land here */
@@ -925,6 +956,7 @@ static int validate_config(const abm_config* c, std::string& why) {
   if (c->walk_type == ABM_ALTERNATED_WALK && c->counter < 1) BAD("counter must be >= 1");
   if (!(c->prob_random_walk >= 0 && c->prob_random_walk <= 1)) BAD("prob_random_walk must be in [0,1]");
   if (c->astar_metric != ABM_ASTAR_DIRECT && c->astar_metric != ABM_ASTAR_MAX) BAD("astar_metric out of range");
+  if (c->scheduler != ABM_SCHED_BY_ID && c->scheduler != ABM_SCHED_RANDOMLY) BAD("scheduler out of range");
   if (c->n_ranks > 1 || c->strip_ny > 0) { /* row strip */
     const int P = c->n_ranks > 1 ? c->n_ranks : 1;
     if (c->rank < 0 || c->rank >= P) BAD("rank out of range");

@@ -148,7 +148,7 @@ static int alternated_propose(abm_handle* h, View& v, uint32_t* ctr) {
   int rc;
   const uint64_t n = h->n;
   const uint32_t C = (uint32_t)h->cfg.counter;
-  const uint64_t words = bitmap_words(h->next_id);
+  const uint64_t words = bitmap_words(key_space(h, h->next_id)); /* ranks in schedule order: a bitmap over the order keys */
   if ((rc = ensure(h, h->bits, (words + 4) * 4))) return rc;
   if ((rc = ensure(h, h->rank, n * 4))) return rc;
   if ((rc = ensure(h, h->by_rank, n * 4))) return rc;
@@ -158,11 +158,11 @@ static int alternated_propose(abm_handle* h, View& v, uint32_t* ctr) {
   v = make_view(h);
   ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, h->stream));
   SetBitsBody sbb;
-  sbb.id = v.id; sbb.bits = (uint32_t*)h->bits.p;
+  sbb.id = v.okey; sbb.bits = (uint32_t*)h->bits.p;
   { ProfScope ps(h->prof, h->stream, "rank_by_id", n, 4); launch_foreach(h->stream, sbb, n);
     if ((rc = rank_prefix(h, words))) return rc;
     RankBody rb;
-    rb.id = v.id; rb.alive_bits = (const uint32_t*)h->bits.p; rb.prefix = (const uint32_t*)h->bits_prefix.p;
+    rb.id = v.okey; rb.alive_bits = (const uint32_t*)h->bits.p; rb.prefix = (const uint32_t*)h->bits_prefix.p;
     rb.rank = (uint32_t*)h->rank.p; rb.by_rank = (uint32_t*)h->by_rank.p;
     launch_foreach(h->stream, rb, n); }
   /* counter value seen by rank r: ((c - 1 - r) mod C) + 1 for c in 1..C; a switch happens where it equals C */

@@ -3,7 +3,7 @@
  * the one-kernel tick, and (row strips) the shipment of the ghost-row lists and of the parents' ids.
  * Part of abm_engine.cu (one translation unit: included there, inside its anonymous namespace); not a stand-alone header.
  */
-enum { SC_EMITTED = 0, SC_OVF0 = 1, SC_OVF1 = 2, SC_PARENTS = 3, SC_CURSOR = 4, SC_ERR = 8, SC_GCOUNT = 16 /* parents per rank, 16 ranks */, SC_WORDS = 32, SC_HOST_BIRTHS = 40 };
+enum { SC_EMITTED = 0, SC_OVF0 = 1, SC_OVF1 = 2, SC_PARENTS = 3, SC_CURSOR = 4, SC_ERR = 8, SC_ZERO = 12 /* never written */, SC_GCOUNT = 16 /* parents per rank, 16 ranks */, SC_WORDS = 32, SC_HOST_BIRTHS = 40 };
 enum { STREAM_MAX_RANKS = 16 };
 
 /* walk rules whose move never waits for another agent */
@@ -25,6 +25,9 @@ static ParentSink stream_sink(abm_handle* h, int which) {
   if (h->strip && h->n_ranks > 1) { /* strips rank the parents of all ranks: a list to all-gather */
     ps.list = (uint32_t*)h->s_parents.p + 1; ps.list_count = (uint32_t*)h->s_ctr.p + SC_PARENTS; ps.list_cap = (uint32_t)h->s_parent_cap;
   }
+  /* the parents are recorded under the order keys of the tick whose steps are being filed: h->tick for the lists of the
+   * current tick (ingest), h->tick + 1 for those the tick kernel files (it derives that tick's key width itself) */
+  ps.sk = sched_key(h, which == h->s_cur ? h->tick : h->tick + 1, h->next_id);
   return ps;
 }
 
@@ -88,7 +91,7 @@ static int stream_ingest(abm_handle* h) {
     h->s_ovf_cap = std::min<uint64_t>(h->s_ovf_rec[0].bytes / sizeof(SRec), h->s_ovf_tile[0].bytes / 4); /* the head room of ensure() counts */
     h->s_ovf_cap = std::min<uint64_t>(h->s_ovf_cap, std::min<uint64_t>(h->s_ovf_rec[1].bytes / sizeof(SRec), h->s_ovf_tile[1].bytes / 4));
     const int cur = h->s_cur;
-    h->s_words[cur] = stream_bitmap_words(h->next_id + 1);
+    h->s_words[cur] = stream_bitmap_words(key_space(h, h->next_id + 1));
     if ((rc = ensure(h, h->s_bits[cur], h->s_words[cur] * 4))) return rc;
     if (h->strip && h->n_ranks > 1) {
       /* the same on every rank (it bounds the all-gathered message): from the grid alone */
@@ -164,21 +167,25 @@ static int tick_stream(abm_handle* h) {
   if (h->cfg.reproduce && (rc = stream_prefix(h, (const uint32_t*)h->s_bits[cur].p, h->s_words[cur]))) return rc;
   /* the lists and the parents bitmap of the next tick start empty */
   /* parents of tick + 1 have ids below next_id + births(tick), and births <= agents alive (all strips': < next_id) */
-  h->s_words[nxt] = stream_bitmap_words(h->next_id + ((h->strip && h->n_ranks > 1) ? h->next_id : n) + 1);
+  h->s_words[nxt] = stream_bitmap_words(key_space(h, h->next_id + ((h->strip && h->n_ranks > 1) ? h->next_id : n) + 1));
   if ((rc = ensure(h, h->s_bits[nxt], h->s_words[nxt] * 4))) return rc;
   if (h->cfg.reproduce) ABM_CK(h, dev_memset(h->s_bits[nxt].p, 0, h->s_words[nxt] * 4, h->stream));
   ABM_CK(h, dev_memset(h->s_cnt[nxt].p, 0, tiles * 4, h->stream));
   ABM_CK(h, dev_memset(sc + SC_EMITTED, 0, 4, h->stream));
   ABM_CK(h, dev_memset(sc + (nxt ? SC_OVF1 : SC_OVF0), 0, 4, h->stream));
   ABM_CK(h, dev_memset(sc + SC_PARENTS, 0, 4, h->stream));
-  StreamTickCta tk;
-  tk.v = make_view(h); tk.v.err = sc + SC_ERR;
-  tk.in = stream_lists(h, cur); tk.out = stream_lists(h, nxt); tk.ps = stream_sink(h, nxt);
-  tk.cores_x = cores_x; tk.core_y0 = h->g.own_lo / CORE;
-  tk.next_id = (uint32_t)h->next_id;
-  tk.birth_bits = (const uint32_t*)h->s_bits[cur].p; tk.birth_prefix = (const uint32_t*)h->bits_prefix.p;
-  tk.emitted = sc + SC_EMITTED;
-  { ProfScope ps(h->prof, h->stream, "stream_tick", n); launch_cta_lb<S_THREADS, S_MIN_CTAS>(h->stream, tk, (uint64_t)cores_x * (uint64_t)core_rows, StreamTickCta::smem_bytes()); }
+  auto launch_tick = [&](auto tk) { /* one instantiation per scheduler: by_id carries no key arithmetic */
+    tk.v = make_view(h); tk.v.err = sc + SC_ERR;
+    tk.in = stream_lists(h, cur); tk.out = stream_lists(h, nxt); tk.ps = stream_sink(h, nxt);
+    tk.cores_x = cores_x; tk.core_y0 = h->g.own_lo / CORE;
+    tk.next_id = (uint32_t)h->next_id;
+    tk.birth_bits = (const uint32_t*)h->s_bits[cur].p; tk.birth_prefix = (const uint32_t*)h->bits_prefix.p;
+    tk.emitted = sc + SC_EMITTED;
+    tk.births_total = h->cfg.reproduce ? (const uint32_t*)h->bits_prefix.p + (h->s_words[cur] - 1) : sc + SC_ZERO;
+    ProfScope ps(h->prof, h->stream, "stream_tick", n);
+    launch_cta_lb<S_THREADS, S_MIN_CTAS>(h->stream, tk, (uint64_t)cores_x * (uint64_t)core_rows, tk.smem_bytes());
+  };
+  if (h->cfg.scheduler == ABM_SCHED_RANDOMLY) launch_tick(StreamTickCta<true>()); else launch_tick(StreamTickCta<false>());
   if ((rc = check_launch(h, "stream tick"))) return rc;
   /* the tick's figures: records filed, overflow, births (= total of the parents bitmap) */
   ABM_CK(h, copy_d2h_async(h->h_counters, sc, SC_WORDS * sizeof(uint32_t), h->stream));

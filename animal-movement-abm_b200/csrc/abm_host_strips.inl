@@ -476,7 +476,7 @@ static int strip_birth_ids(abm_handle* h, uint64_t bbcap, int nxt, uint32_t* d_t
   ba.rank_in = ranks; ba.birth_bits = nullptr; ba.birth_prefix = nullptr;
   ba.out_id = (uint32_t*)h->id[nxt].p; ba.total_out = d_total;
   if ((uint64_t)P * bbcap > h->birth_bitmap_from) { /* many offspring: bitmap over the id space + popcount prefix */
-    const uint64_t idw = bitmap_words(h->next_id);
+    const uint64_t idw = bitmap_words(key_space(h, h->next_id)); /* birth_parent holds order keys */
     if ((rc = ensure(h, h->bits, (idw + 4) * 4))) return rc;
     ProfScope ps(h->prof, h->stream, "birth_ids", bbcap, 2);
     ABM_CK(h, dev_memset(h->bits.p, 0, idw * 4, h->stream));

@@ -116,6 +116,7 @@ struct Params {
   double prob_random_walk, delta_energy, movement_cost, reproduction_prob;
   int64_t ax2, ay2; /* 2 * attractor, in 1-based coordinates */
   uint64_t seed, tick;
+  SchedKey sk;      /* the scheduler's order keys of this tick (abm_rng.h) */
 };
 
 /* everything a body needs; plain pointers, passed by value */
@@ -125,6 +126,7 @@ struct View {
   uint32_t n;                /* agents at tick start */
   uint32_t* cell;            /* tcell of each agent, ascending */
   uint32_t* id;
+  const uint32_t* okey;      /* order key of each agent: what decides who acts first (== id under Schedulers.by_id) */
   double* energy;
   uint8_t* state;
   uint32_t* slot;            /* position inside the new cell run */
@@ -292,13 +294,19 @@ struct ProposeBody {
   }
 };
 
+/* Schedulers.randomly: the order keys of this tick, one thread per agent (own and ghost) */
+struct OrderKeyBody {
+  SchedKey sk; const uint32_t* id; uint32_t* okey;
+  ABM_HD void operator()(uint64_t i) const { okey[i] = order_key(sk, id[i]); }
+};
+
 /* ------------------------------------------------------------------------------------------------ resolve */
 
 enum { RES_PENDING = 0, RES_DONE = 1 };
 
 /* `ifempty` walk of agent k towards T = old + dir.  SURVEY.md Appendix C D1. */
 ABM_HD int resolve_cond(const View& v, uint32_t k, uint8_t st) {
-  const uint32_t myid = v.id[k];
+  const uint32_t myid = v.okey[k]; /* order key: the ids below are only compared */
   int x, y, dx, dy, tx, ty;
   dec(v.g, v.cell[k], x, y);
   off8(st & ST_DIRMASK, dx, dy);
@@ -311,7 +319,7 @@ ABM_HD int resolve_cond(const View& v, uint32_t k, uint8_t st) {
     const uint32_t beg = v.cell_start[cb], end = v.cell_start[cb + 1];
     for (uint32_t j = beg; j < end; ++j) {
       if (j == k) continue;
-      const uint32_t idj = v.id[j];
+      const uint32_t idj = v.okey[j];
       if (b == 0) { /* agents that start the tick on T */
         if (idj > myid) { blocked = true; break; } /* still there at k's turn */
         const uint8_t sj = load_state(&v.state[j]);
@@ -337,7 +345,7 @@ ABM_HD int resolve_cond(const View& v, uint32_t k, uint8_t st) {
   }
   if (!blocked && v.remote_head) { /* lower-id route followers that already arrived on T (decided at propose) */
     for (uint32_t j = v.remote_head[enc(v.g, tx, ty)]; j != REMOTE_NONE; j = v.remote_next[j]) {
-      if (j != k && v.id[j] < myid && present(v.state[j])) { blocked = true; break; }
+      if (j != k && v.okey[j] < myid && present(v.state[j])) { blocked = true; break; }
     }
   }
   if (blocked) { v.state[k] = (uint8_t)(st | ST_DECIDED); return RES_DONE; }
@@ -355,7 +363,7 @@ struct BoxMask {
 
 /* random_walk_gregarious (src/agent_actions.jl:297-336) for agent k.  SURVEY.md Appendix C D3, A-5, A-7. */
 ABM_HD int resolve_greg(const View& v, uint32_t k, uint8_t st) {
-  const uint32_t myid = v.id[k];
+  const uint32_t myid = v.okey[k]; /* order key */
   const int r = v.p.r, side = 2 * r + 1;
   int x, y;
   dec(v.g, v.cell[k], x, y);
@@ -371,7 +379,7 @@ ABM_HD int resolve_greg(const View& v, uint32_t k, uint8_t st) {
       const uint32_t beg = v.cell_start[cb], end = v.cell_start[cb + 1];
       for (uint32_t j = beg; j < end; ++j) {
         if (j == k) continue;
-        if (v.id[j] > myid) { ABM_MARK(def, sx, sy); continue; } /* still on its old cell */
+        if (v.okey[j] > myid) { ABM_MARK(def, sx, sy); continue; } /* still on its old cell */
         const uint8_t sj = load_state(&v.state[j]);
         const int dj = sj & ST_DIRMASK;
         int jx = 0, jy = 0;
@@ -398,7 +406,7 @@ ABM_HD int resolve_greg(const View& v, uint32_t k, uint8_t st) {
     if (unk.get(bit)) return RES_PENDING;
   }
   AgentStream rs;
-  rs.init(v.p.seed, v.p.tick, myid);
+  rs.init(v.p.seed, v.p.tick, v.id[k]);
   rs.n = 1; /* draw 0 was the execute_walk! uniform */
   int dir;
   if (closest < 0) {
@@ -495,7 +503,7 @@ struct CommitBody {
   ABM_HD void operator()(uint64_t i) const {
     const uint32_t k = (uint32_t)i;
     const uint8_t st = v.state[k];
-    const uint32_t myid = v.id[k];
+    const uint32_t myid = v.okey[k]; /* order key: first come, first served */
     int x, y, fx, fy;
     dec(v.g, v.cell[k], x, y);
     if ((st & ST_DIRMASK) == DIR_REMOTE) dec(v.g, v.remote_dest[k], fx, fy);
@@ -519,7 +527,7 @@ struct CommitBody {
         }
         const bool alive = !(sj & ST_DEAD), birth = (sj & ST_BIRTH) != 0;
         alive_tot += alive; birth_tot += birth;
-        if (j != k && v.id[j] < myid) { lower = true; slot_alive += alive; slot_birth += birth; }
+        if (j != k && v.okey[j] < myid) { lower = true; slot_alive += alive; slot_birth += birth; }
       }
     }
     if (v.remote_head) { /* route followers landing on fc */
@@ -527,7 +535,7 @@ struct CommitBody {
         const uint8_t sj = v.state[j];
         const bool alive = !(sj & ST_DEAD), birth = (sj & ST_BIRTH) != 0;
         alive_tot += alive; birth_tot += birth;
-        if (j != k && v.id[j] < myid) { lower = true; slot_alive += alive; slot_birth += birth; }
+        if (j != k && v.okey[j] < myid) { lower = true; slot_alive += alive; slot_birth += birth; }
       }
     }
     /* eat!: the first agent (lowest id) to stand on a grown cell eats it; killed agents still eat */
@@ -587,7 +595,7 @@ struct BirthScatterBody {
   ABM_HD void operator()(uint64_t i) const {
     const BirthRec rec = births[i];
     const uint32_t k = rec.parent;
-    const uint32_t pid = v.id[k];
+    const uint32_t pid = v.okey[k]; /* nextid in the order the parents were stepped */
     const uint32_t w = pid >> 5;
     const uint32_t rank = birth_prefix[w] + (uint32_t)popc(birth_bits[w] & ((1u << (pid & 31)) - 1u));
     const uint32_t fc = new_cell[k];

@@ -13,7 +13,7 @@
 
 namespace abm {
 
-ABM_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+ABM_HOSTDEV uint32_t mulhi32(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
   return __umulhi(a, b);
 #else
@@ -30,7 +30,7 @@ ABM_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
 }
 
 /* Philox4x32-10 (multipliers/Weyl constants as in curand_philox4x32_x.h:88-91) */
-ABM_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+ABM_HOSTDEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                           uint32_t out[4]) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -85,6 +85,39 @@ struct AgentStream {
     return (uint32_t)mulhi64(x, s);
   }
 };
+
+/*
+ * Schedulers.randomly (the scheduler every reference script selects, scripts/v0.1.jl:63) under the counter-based
+ * contract of include/abm.h: in tick t the agents are stepped in ascending ORDER KEY, where key = P_t(id) and P_t is a
+ * keyed permutation of [0, 2^b) — a 4-round balanced Feistel network over b = 2 hb bits, b the smallest even number
+ * >= 2 with 2^b >= nextid(model) at the start of the tick (every id is below it), round keys = the four words of the
+ * Philox block (seed; counter 0, tick, reserved agent id 2^64 - 1).  Schedulers.by_id: key = id.  Keys are unique and
+ * below 2^b, so everything the engine indexes by id for ORDER (bitmaps, ranks, the min/max summaries) works on keys.
+ */
+struct SchedKey {
+  int32_t on, hb;   /* on = 0: by_id */
+  uint32_t k[4];
+};
+ABM_HOSTDEV int sched_half_bits(uint64_t next_id) { /* hb: 2^(2 hb) >= next_id */
+  int hb = 1;
+  while (hb < 16 && (1ull << (2 * hb)) < next_id) ++hb;
+  return hb;
+}
+ABM_HOSTDEV void sched_round_keys(uint64_t seed, uint64_t tick, uint32_t k[4]) {
+  philox4x32_10(0u, (uint32_t)tick, 0xFFFFFFFFu, 0xFFFFFFFFu, (uint32_t)seed, (uint32_t)(seed >> 32), k);
+}
+ABM_HOSTDEV uint32_t sched_mix(uint32_t z) {
+  z *= 0x9E3779B1u; z ^= z >> 15; z *= 0x85EBCA77u; z ^= z >> 13;
+  return z;
+}
+ABM_HOSTDEV uint32_t order_key(const SchedKey& sk, uint32_t id) {
+  if (!sk.on) return id;
+  const uint32_t m = (1u << sk.hb) - 1u;
+  uint32_t L = id >> sk.hb, R = id & m;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const uint32_t t = L ^ (sched_mix(R ^ sk.k[i]) & m); L = R; R = t; }
+  return (L << sk.hb) | R;
+}
 
 }  // namespace abm
 #endif /* ABM_RNG_H_ */

@@ -89,11 +89,12 @@ struct StreamLists {
 
 /* where the parents of the next tick are recorded: a bitmap over the id space (one GPU) or a list that the strips
  * all-gather (then every rank marks the bitmap from the gathered list) */
-struct ParentSink { uint32_t* bits; uint32_t* list; uint32_t* list_count; uint32_t list_cap; };
+struct ParentSink { uint32_t* bits; uint32_t* list; uint32_t* list_count; uint32_t list_cap; SchedKey sk; /* order keys of that tick */ };
 
 /* Agent (id, energy e) stands on (x, y) of the stored grid when tick v.p.tick begins: draw its step and file the record at
  * the core it ends on.  Every lane of the warp calls this (valid = this lane has an agent): the slots of one core are
  * taken with one atomic per warp. */
+template <bool SCHED>
 ABM_HD void stream_emit(const View& v, const StreamLists& out, const ParentSink& ps, int x, int y, uint32_t id, double e, bool valid) {
   SRec r;
   r.w0 = 0; r.id = id; r.e_lo = 0; r.e_hi = 0;
@@ -112,9 +113,10 @@ ABM_HD void stream_emit(const View& v, const StreamLists& out, const ParentSink&
     r.w0 = (uint32_t)(((fy & 31) << 5) | (fx & 31)) | ((uint32_t)((st & ST_MOVED) ? (st & ST_DIRMASK) : (int)DIR_STAY) << SR_DIR_SHIFT) |
            ((st & ST_DEAD) ? (uint32_t)SR_DEAD : 0u) | ((st & ST_BIRTH) ? (uint32_t)SR_BIRTH : 0u) | (nowalk ? (uint32_t)SR_NOWALK : 0u);
     set_rec_energy(r, e);
-    if (st & ST_BIRTH) {
-      if (ps.list) { const uint32_t k = atomic_add(ps.list_count, 1u); if (k < ps.list_cap) ps.list[k] = id; }
-      else atomic_or(&ps.bits[id >> 5], 1u << (id & 31));
+    if (st & ST_BIRTH) { /* parents are recorded by order key: nextid goes to the offspring in the order the parents are stepped */
+      const uint32_t pk = SCHED ? order_key(ps.sk, id) : id;
+      if (ps.list) { const uint32_t k = atomic_add(ps.list_count, 1u); if (k < ps.list_cap) ps.list[k] = pk; }
+      else atomic_or(&ps.bits[pk >> 5], 1u << (pk & 31));
     }
   }
   const uint32_t slot = agg_add(out.cnt, tile, valid);
@@ -134,13 +136,15 @@ struct StreamIngestBody {
     int x = 0, y = 0;
     uint32_t id = 0; double e = 0;
     if (valid) { dec(v.g, v.cell[i], x, y); id = v.id[i]; e = v.energy[i]; }
-    stream_emit(v, out, ps, x, y, id, e, valid);
+    stream_emit<true>(v, out, ps, x, y, id, e, valid); /* not a hot path: the scheduler is looked up at run time */
   }
 };
 
 /* One tick: CTA b = core b of the own rows.  custom_agent_step! after the walk (reduce_energy!, eat!, reproduce!,
  * src/agent_actions.jl:54-67) for every agent that ends tick v.p.tick on this core, the walk of tick + 1 for what remains,
  * custom_model_step! (src/model_actions.jl:18-30) on the core's grass tile. */
+/* SCHED = false: Schedulers.by_id, order key = id (the instantiation the benchmarks run: no key arithmetic at all) */
+template <bool SCHED>
 struct StreamTickCta {
   View v;                /* v.p.tick = the tick being completed */
   StreamLists in, out;
@@ -149,20 +153,22 @@ struct StreamTickCta {
   uint32_t next_id;      /* nextid(model) when the tick began */
   const uint32_t* birth_bits; const uint32_t* birth_prefix; /* parents of this tick, every strip's, + popcount prefix */
   uint32_t* emitted;     /* records filed for tick + 1 */
+  const uint32_t* births_total; /* Schedulers.randomly: offspring of this tick (device side), for the key width of tick + 1 */
 
   enum { BIRTH_LIST = 128 }; /* parents listed per core and tick; a core with more re-scans its records for them */
   static size_t smem_bytes() { return (size_t)(CORE * CORE + CORE * CORE / 4 + 8 + BIRTH_LIST) * 4; }
 
   /* the offspring of record r (whose energy field already holds the halved energy): on the parent's cell, id = nextid in
    * the order of the parents' ids (:172-178, Appendix C D6); its first step is drawn like everybody's */
-  ABM_HD uint32_t newborn(const View& vn, const SRec& r, bool valid, int x0, int y0) const {
+  ABM_HD uint32_t key_of(uint32_t id) const { return SCHED ? order_key(v.p.sk, id) : id; }
+  ABM_HD uint32_t newborn(const View& vn, const ParentSink& psn, const SRec& r, bool valid, int x0, int y0) const {
     const uint32_t lc = r.w0 & SR_LC;
     uint32_t child = 0;
     if (valid) {
-      const uint32_t wd = r.id >> 5;
-      child = next_id + birth_prefix[wd] + (uint32_t)popc(birth_bits[wd] & ((1u << (r.id & 31)) - 1u));
+      const uint32_t pk = key_of(r.id), wd = pk >> 5;
+      child = next_id + birth_prefix[wd] + (uint32_t)popc(birth_bits[wd] & ((1u << (pk & 31)) - 1u));
     }
-    stream_emit(vn, out, ps, x0 + (int)(lc & 31), y0 + (int)(lc >> 5), child, rec_energy(r), valid);
+    stream_emit<SCHED>(vn, out, psn, x0 + (int)(lc & 31), y0 + (int)(lc >> 5), child, rec_energy(r), valid);
     return valid ? 1u : 0u;
   }
 
@@ -182,6 +188,8 @@ struct StreamTickCta {
     const int x0 = cx * CORE, y0 = cy * CORE;
     View vn = v;
     vn.p.tick = v.p.tick + 1;
+    ParentSink psn = ps; /* the parents of tick + 1 under that tick's order keys: its key width follows from nextid after this tick */
+    if (SCHED) psn.sk.hb = sched_half_bits((uint64_t)next_id + (uint64_t)*births_total);
 
     ABM_CTA_FOR(t, NT) {
       fill_words(min_all, NONE32, CORE * CORE, t, NT);
@@ -192,10 +200,10 @@ struct StreamTickCta {
     ABM_CTA_FOR(t, NT) { /* pass 1: who eats where */
       for (uint32_t i = (uint32_t)t; i < n; i += (uint32_t)NT) {
         const SRec r = load_rec(&mine[i]);
-        smem_min(&min_all[r.w0 & SR_LC], r.id);
+        smem_min(&min_all[r.w0 & SR_LC], key_of(r.id)); /* first come (lowest order key), first served */
       }
       for (uint32_t o = (uint32_t)t; o < n_ovf; o += (uint32_t)NT)
-        if (in.ovf_tile[o] == tile) { const SRec r = load_rec(&in.ovf_rec[o]); smem_min(&min_all[r.w0 & SR_LC], r.id); }
+        if (in.ovf_tile[o] == tile) { const SRec r = load_rec(&in.ovf_rec[o]); smem_min(&min_all[r.w0 & SR_LC], key_of(r.id)); }
     }
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, NT) { /* pass 2: the rest of the step, and the next one (whole warps: stream_emit aggregates) */
@@ -210,7 +218,7 @@ struct StreamTickCta {
         const uint32_t lc = r.w0 & SR_LC;
         double e = rec_energy(r) - v.p.movement_cost; /* walk_ocurred is always true */
         if (valid) {
-          if (v.p.eat && min_all[lc] == r.id && (grass[lc] & GRASS_GROWN)) { /* killed agents still eat (Appendix D-1) */
+          if (v.p.eat && min_all[lc] == key_of(r.id) && (grass[lc] & GRASS_GROWN)) { /* killed agents still eat (Appendix D-1) */
             e += v.p.delta_energy;
             grass[lc] = (uint8_t)(grass[lc] & ~GRASS_GROWN);
           }
@@ -224,7 +232,7 @@ struct StreamTickCta {
           }
         }
         const bool alive = valid && !(r.w0 & SR_DEAD);
-        stream_emit(vn, out, ps, x0 + (int)(lc & 31), y0 + (int)(lc >> 5), r.id, e, alive);
+        stream_emit<SCHED>(vn, out, psn, x0 + (int)(lc & 31), y0 + (int)(lc >> 5), r.id, e, alive);
         made += alive ? 1u : 0u;
       }
       if (made) smem_add(&misc[0], made);
@@ -241,7 +249,7 @@ struct StreamTickCta {
           SRec r;
           r.w0 = 0; r.id = 0; r.e_lo = 0; r.e_hi = 0;
           if (valid) r = load_rec(&mine[blist[k]]);
-          made += newborn(vn, r, valid, x0, y0);
+          made += newborn(vn, psn, r, valid, x0, y0);
         }
       } else {
         for (uint32_t base = 0; base < n + n_ovf; base += (uint32_t)NT) {
@@ -250,7 +258,7 @@ struct StreamTickCta {
           SRec r;
           r.w0 = 0; r.id = 0; r.e_lo = 0; r.e_hi = 0;
           if (mine_too) r = load_rec(i < n ? &mine[i] : &in.ovf_rec[i - n]);
-          made += newborn(vn, r, mine_too && (r.w0 & SR_BIRTH), x0, y0);
+          made += newborn(vn, psn, r, mine_too && (r.w0 & SR_BIRTH), x0, y0);
         }
       }
       if (made) smem_add(&misc[0], made);

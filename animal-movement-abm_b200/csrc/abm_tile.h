@@ -232,8 +232,8 @@ ABM_HD uint8_t greg_finish(const View& v, uint32_t id, uint8_t st, int code) {
   return (uint8_t)((st & (ST_DEAD | ST_BIRTH)) | d | ST_DECIDED | ST_MOVED);
 }
 
-/* one attempt to decide agent (id, st) at window cell (x, y); summaries are complete on [1, w-2]^2 */
-ABM_HD int evaluate(const View& v, const Summaries& s, const Window& w, uint32_t id, int x, int y, uint8_t st, uint8_t& out) {
+/* one attempt to decide agent (order key id, RNG stream rng_id, st) at window cell (x, y); summaries are complete on [1, w-2]^2 */
+ABM_HD int evaluate(const View& v, const Summaries& s, const Window& w, uint32_t id, uint32_t rng_id, int x, int y, uint8_t st, uint8_t& out) {
   const int dir = st & ST_DIRMASK;
   if (dir != DIR_GREG) { /* walk!(...; ifempty = true) towards old + dir */
     int dx, dy;
@@ -250,7 +250,7 @@ ABM_HD int evaluate(const View& v, const Summaries& s, const Window& w, uint32_t
   const int code = greg_scan(v, s, w, id, x, y);
   if (code == GREG_OUTSIDE) return EV_OUTSIDE;
   if (code == GREG_PENDING) return EV_PENDING;
-  out = greg_finish(v, id, st, code);
+  out = greg_finish(v, rng_id, st, code); /* the draw comes from the agent's own stream, whatever its place in the schedule */
   return EV_DECIDED;
 }
 
@@ -286,6 +286,7 @@ struct ResolveWindow {
   /* Core window with the undecided agents held in a shared-memory work list: each round touches only what is still
    * open.  min_new only ever gains entries (decisions are final), min_maybe is rebuilt per round from the list.  Agents are read from global memory exactly once.  Returns false (uniformly) when the list overflows. */
   ABM_HD bool core_fast(uint32_t cta, uint32_t* smem) const {
+    ABM_PHASE_BEGIN(); /* -DABM_PHASE_CLOCKS builds only (tools/phase_probe.py) */
     Window w;
     const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) * row_step + core_y0;
     w.set(cx * CORE - HALO, cy * CORE - HALO, WIN, WIN);
@@ -323,6 +324,7 @@ struct ResolveWindow {
     ABM_CTA_SYNC();
     ABM_CTA_FOR(t, NT) { rt.expand(t, NT, nruns); }
     ABM_CTA_SYNC();
+    ABM_PHASE(0); /* setup: fills, run table */
     const uint32_t M = rt.prefix[nruns];
     ABM_CTA_FOR(t, NT) {
       for (uint32_t m0 = (uint32_t)t; m0 < M; m0 += 3u * (uint32_t)NT) {
@@ -332,7 +334,7 @@ struct ResolveWindow {
         if (m >= M) { rr[j] = -1; continue; }
         rr[j] = rt.find(m, nruns);
         aa[j] = rt.off[rr[j]] + (m - rt.prefix[rr[j]]);
-        cc[j] = v.cell[aa[j]]; ii[j] = v.id[aa[j]]; ss[j] = load_state(&v.state[aa[j]]);
+        cc[j] = v.cell[aa[j]]; ii[j] = v.okey[aa[j]]; ss[j] = load_state(&v.state[aa[j]]); /* the list and the summaries hold order keys */
        }
        for (int j = 0; j < 3; ++j) {
         if (rr[j] < 0) continue;
@@ -353,6 +355,7 @@ struct ResolveWindow {
       }
     }
     ABM_CTA_SYNC();
+    ABM_PHASE(1); /* agents loaded and listed */
     if (cnt[0] + cnt[5] > ULIST_CAP) return false; /* the two ends of the list met: take the streaming code */
     const uint32_t nc = cnt[0], ng = cnt[5];
     ABM_CTA_FOR(t, NT) { /* the gregarious agents' eight candidate cells, by full warps */
@@ -368,6 +371,7 @@ struct ResolveWindow {
      * is cleared.  P3: the entries still open put their candidate cells back into min_maybe.  min_new only gains entries
      * (decisions are final); a reader that misses a fresh entry still finds the same id in min_maybe and waits a round.
      * (With -DABM_TWO_MAYBE the open entries write into a second buffer during P1 instead and P3 disappears.) */
+    ABM_PHASE(2); /* candidate cells of the gregarious agents */
     int cur = 0;
     for (int round = 0; round < max_rounds; ++round) {
       uint32_t* flag = cnt + 8 + 2 * (round & 1);
@@ -382,7 +386,7 @@ struct ResolveWindow {
           const int x = (int)(xs & 63), y = (int)((xs >> 6) & 63);
           const uint8_t st = (uint8_t)(xs >> 12);
           uint8_t nst = st;
-          if (evaluate(v, s, w, id, x, y, st, nst) == EV_DECIDED) {
+          if (evaluate(v, s, w, id, id, x, y, st, nst) == EV_DECIDED) { /* a walker draws nothing here */
             v.state[l_a[u]] = nst;
             contribute_final(min_new, w, id, x, y, nst);
             l_xs[u] = xs | XS_DONE;
@@ -421,7 +425,8 @@ struct ResolveWindow {
             if (warp_all(!search || found != NONE32)) break;
           }
           if (search && lane_in == 0 && !(found != NONE32 && (found & 1u))) {
-            const uint8_t nst = greg_finish(v, id, st, found == NONE32 ? (int)GREG_NOBODY : (int)v.greg_order[found >> 1]);
+            const uint32_t rng_id = v.okey == v.id ? id : v.id[l_a[e]];
+            const uint8_t nst = greg_finish(v, rng_id, st, found == NONE32 ? (int)GREG_NOBODY : (int)v.greg_order[found >> 1]);
             v.state[l_a[e]] = nst;
             contribute_final(min_new, w, id, x, y, nst);
             l_xs[e] = xs | XS_DONE;
@@ -453,6 +458,7 @@ struct ResolveWindow {
       }
     }
     ABM_CTA_SYNC();
+    ABM_PHASE(3); /* rounds */
     ABM_CTA_FOR(t, NT) { /* the core's agents that stay open go to the per-agent windows */
       for (uint32_t u = (uint32_t)t; u < nc + ng; u += (uint32_t)NT) {
         const uint32_t e = u >= nc ? ULIST_CAP - 1 - (u - nc) : u;
@@ -515,7 +521,7 @@ struct ResolveWindow {
         const int r = rt.find(m, nruns);
         const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
         int x, y;
-        if (rt.locate(w, r, v.cell[a], x, y)) smem_max(&s.max_old[y * w.wx + x], v.id[a]);
+        if (rt.locate(w, r, v.cell[a], x, y)) smem_max(&s.max_old[y * w.wx + x], v.okey[a]);
       }
     }
     ABM_CTA_SYNC();
@@ -531,7 +537,7 @@ struct ResolveWindow {
           const int r = rt.find(m, nruns);
           const uint32_t a = rt.off[r] + (m - rt.prefix[r]);
           int x, y;
-          if (rt.locate(w, r, v.cell[a], x, y)) contribute(s, w, v.id[a], x, y, load_state(&v.state[a]));
+          if (rt.locate(w, r, v.cell[a], x, y)) contribute(s, w, v.okey[a], x, y, load_state(&v.state[a]));
         }
       }
       ABM_CTA_SYNC();
@@ -545,7 +551,7 @@ struct ResolveWindow {
           int x, y;
           if (!rt.locate(w, r, v.cell[a], x, y)) continue;
           uint8_t nst = st;
-          const int res = evaluate(v, s, w, v.id[a], x, y, st, nst);
+          const int res = evaluate(v, s, w, v.okey[a], v.id[a], x, y, st, nst);
           if (res == EV_DECIDED) { v.state[a] = nst; flags[0] = 1; }
           else if (mode == 1 || (x >= own_lo && x < own_hi && y >= own_lo && y < own_hi)) smem_add(&flags[1], 1u);
         }
@@ -685,7 +691,7 @@ struct CommitTile {
           x = (int)(lc & 31); y = (int)(lc >> 5);
           st = v.state[a];
         }
-        const uint32_t id = v.id[a];
+        const uint32_t id = v.okey[a]; /* order key: the first to arrive eats */
         smem_min(&min_all[y * CORE + x], id);
         const uint32_t add = ((st & ST_DEAD) ? 0u : 1u) + ((st & ST_BIRTH) ? 1u : 0u);
         if (add) smem_add(&wcounts[(t >> 5) * 16 + (y >> 3) * 4 + (x >> 3)], add);
@@ -718,7 +724,7 @@ struct CommitTile {
     const uint32_t n_pass2 = listed ? misc[1] : M + (use_mig ? n_mig : 0u);
     ABM_CTA_FOR(t, NT) { /* pass 2: energy, eating, births, output (over the arrival list when it fits) */
       for (uint32_t m = (uint32_t)t; m < n_pass2; m += (uint32_t)NT) {
-        uint32_t a, id;
+        uint32_t a, id; /* id: the order key here as well */
         int x, y;
         uint8_t st;
         if (listed) {
@@ -733,12 +739,12 @@ struct CommitTile {
           if (st & ST_MOVED) { int dx, dy; off8(st & ST_DIRMASK, dx, dy); x += dx; y += dy; }
           x -= halo; y -= halo;
           if (x < 0 || x >= CORE || y < 0 || y >= CORE) continue;
-          id = v.id[a];
+          id = v.okey[a];
         } else {
           a = my_mig_a[m - M];
           const uint32_t lc = my_mig_lc[m - M];
           x = (int)(lc & 31); y = (int)(lc >> 5);
-          st = v.state[a]; id = v.id[a];
+          st = v.state[a]; id = v.okey[a];
         }
         const int lc = y * CORE + x;
         double e = v.energy[a] - v.p.movement_cost; /* walk_ocurred is always true */
@@ -751,7 +757,7 @@ struct CommitTile {
         const int q = (y >> 3) * 4 + (x >> 3);
         if (!(st & ST_DEAD)) {
           const uint32_t pos = smem_add(&cur[q], 1u);
-          out_cell[pos] = fc; out_id[pos] = id; out_energy[pos] = e;
+          out_cell[pos] = fc; out_id[pos] = v.okey == v.id ? id : v.id[a]; out_energy[pos] = e;
         }
         if (st & ST_BIRTH) { /* offspring on the parent's cell with the halved energy; its id is patched in afterwards */
           const uint32_t pos = smem_add(&cur[q], 1u);

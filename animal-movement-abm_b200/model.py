@@ -73,17 +73,21 @@ def product_library() -> capi.CLib:
     return _PRODUCT_LIB
 
 
+SCHEDULERS = {"by_id": 0, "randomly": 1}  # Agents.Schedulers.by_id / Schedulers.randomly -> abm_config.scheduler
+
+
 class SheepModel:
     """The `ABM(Sheep, GridSpace(griddims; periodic, metric = :chebyshev); properties, rng, scheduler)` of
     scripts/v0.1.jl:49-64 ... scripts/v0.6.jl:74-101, with the state kept on the device between calls.
 
     Host views (`fully_grown`, `countdown`, `agents()`) are fetched lazily, as the Julia shim does when a plot or
-    `adata` touches them.  Scheduler: by id; randomness: Philox keyed by (seed, tick, id, draw) — include/abm.h.
+    `adata` touches them.  Scheduler: `scheduler="by_id"` (default) or `"randomly"` (what every reference script selects,
+    scripts/v0.1.jl:63: a fresh Philox-keyed order every tick); randomness: Philox keyed by (seed, tick, id, draw) — include/abm.h.
     """
 
     def __init__(self, griddims, *, periodic=True, seed=321, regrowth_time=30, delta_energy=4.0, movement_cost=1.0,
                  reproduction_prob=0.001, visual_distance=5, counter=50, attractor=None, land_walkmap=None, elevation=None,
-                 astar_metric=capi.ASTAR_DIRECT, astar_penalty=False, lib: capi.CLib | None = None, device=0):
+                 astar_metric=capi.ASTAR_DIRECT, astar_penalty=False, lib: capi.CLib | None = None, device=0, scheduler="by_id"):
         self.nx, self.ny = int(griddims[0]), int(griddims[1])
         self.periodic, self.seed = bool(periodic), int(seed)
         self.regrowth_time, self.delta_energy, self.movement_cost = int(regrowth_time), float(delta_energy), float(movement_cost)
@@ -92,6 +96,9 @@ class SheepModel:
         self.land_walkmap = None if land_walkmap is None else np.ascontiguousarray(land_walkmap, np.uint8)
         self.elevation = None if elevation is None else np.ascontiguousarray(elevation, np.int64)
         self.astar_metric, self.astar_penalty = int(astar_metric), bool(astar_penalty)
+        if scheduler not in SCHEDULERS:
+            raise ValueError(f"scheduler must be one of {sorted(SCHEDULERS)} (Agents.Schedulers.by_id / Schedulers.randomly)")
+        self.scheduler = scheduler
         self._lib, self._device = lib, int(device)
         self._engine, self._engine_key = None, None
         # host-side initial state (uploaded when the engine is created)
@@ -169,7 +176,7 @@ class SheepModel:
             visual_distance=self.visual_distance, counter=self.counter, astar_metric=self.astar_metric, astar_penalty=int(self.astar_penalty),
             device=self._device, prob_random_walk=agent_step.prob_random_walk, delta_energy=self.delta_energy,
             movement_cost=self.movement_cost, reproduction_prob=self.reproduction_prob, attractor_x=self.attractor[0],
-            attractor_y=self.attractor[1], seed=self.seed)
+            attractor_y=self.attractor[1], seed=self.seed, scheduler=SCHEDULERS[self.scheduler])
         e = lib.create(cfg)
         if self._device_init is None or self.land_walkmap is not None or self.elevation is not None:
             e.set_grid(self._fg, self._cd, self.land_walkmap, self.elevation)  # with a device init only the terrain matters
@@ -352,12 +359,13 @@ def plot_data(model: SheepModel):
 
 def initialize_model(*, n_sheep=40, griddims=(80, 80), regrowth_time=30, delta_energy_sheep=4, sheep_reproduce=0.001, movement_cost=1,
                      visual_distance=5, seed=321, periodic=False, counter=50, water_level=1, mountain_level=18, elevation=None,
-                     use_walkmap=False, synthetic_terrain_seed=7, astar_metric=capi.ASTAR_DIRECT, astar_penalty=False, lib=None, device=0, on_device=False) -> SheepModel:
+                     use_walkmap=False, synthetic_terrain_seed=7, astar_metric=capi.ASTAR_DIRECT, astar_penalty=False, lib=None, device=0, on_device=False, scheduler="by_id") -> SheepModel:
     """The scripts' `initialize_model(; kwargs)` (scripts/v0.1.jl:36-81 ... scripts/v0.6.jl:36-135), same keywords
     (Δenergy_sheep spelled delta_energy_sheep).  v0.1/v0.2 are non-periodic, v0.3-v0.6 periodic; v0.5/v0.6 build
     `land_walkmap = water_level .< elevation .< mountain_level` from a heightmap — the scripts download theirs, here
     a seeded synthetic one stands in unless `elevation` is given.  Initial draws come from numpy's Philox stream (the
-    scripts use MersenneTwister(seed); initialisation is host-side and not part of the parity contract)."""
+    scripts use MersenneTwister(seed); initialisation is host-side and not part of the parity contract).
+    `scheduler="randomly"` is the scripts' `scheduler = Schedulers.randomly` (scripts/v0.1.jl:63); the default steps by id."""
     nx, ny = int(griddims[0]), int(griddims[1])
     wm = None
     if use_walkmap or elevation is not None:
@@ -367,7 +375,7 @@ def initialize_model(*, n_sheep=40, griddims=(80, 80), regrowth_time=30, delta_e
     w = None if on_device else worlds.make_world(nx, ny, n_sheep, seed=seed, regrowth_time=regrowth_time, delta_energy=int(delta_energy_sheep), walkmap=wm, periodic=bool(periodic))
     m = SheepModel((nx, ny), periodic=periodic, seed=seed, regrowth_time=regrowth_time, delta_energy=delta_energy_sheep, movement_cost=movement_cost,
                    reproduction_prob=sheep_reproduce, visual_distance=visual_distance, counter=counter, land_walkmap=wm, elevation=elevation,
-                   astar_metric=astar_metric, astar_penalty=astar_penalty, lib=lib, device=device)
+                   astar_metric=astar_metric, astar_penalty=astar_penalty, lib=lib, device=device, scheduler=scheduler)
     if on_device:  # grass and sheep are drawn by the engine (abm_init_random): a 2^28-sheep world needs no host arrays
         m.init_on_device(n_sheep, seed)
     else:

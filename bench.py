@@ -639,6 +639,7 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=120.0, help="--impl reference: stop timing ticks after this many seconds (at least two ticks are timed)")
     ap.add_argument("--cpu-ticks", type=int, default=2, help="timed ticks of the cpu_baseline leg of the b200 arm (same configuration, after 1 warm-up tick)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--scheduler", default="by_id", choices=["by_id", "randomly"], help="Agents.Schedulers.by_id (the north star's fixed order; default) or Schedulers.randomly (what the reference scripts select: a Philox-keyed order per tick, include/abm.h)")
     ap.add_argument("--stationary", action="store_true", help="reproduce=false and movement_cost=0: nobody is born, nobody dies — the population of tick 0 stays (BASELINE.md §3)")
     ap.add_argument("--device-world", action="store_true", help="build the world on the device (abm_init_random) instead of numpy (always for C5 and for the sub-records)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -657,6 +658,10 @@ def main():
     elif args.ref_nx <= 0:
         args.ref_nx = args.ref_size
 
+    if args.scheduler == "randomly":
+        for wl in WORKLOADS.values():
+            wl["cfg"]["scheduler"] = 1
+            wl["desc"] += " [scheduler = Schedulers.randomly]"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

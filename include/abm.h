@@ -24,7 +24,8 @@
  *   (tick, agent), with the two global-RNG call sites (src/agent_actions.jl:213 `sample(1:3)`, :328
  *   `wsample`) routed through the injected RNG.  Float64 = low 52 bits as [1,2) mantissa minus 1
  *   (Julia Random, generic AbstractRNG); `rand(1:k)` = Lemire nearly-division-less (Julia
- *   SamplerRangeNDL), redraws advance n.  Scheduler order is by agent id (Schedulers.by_id).
+ *   SamplerRangeNDL), redraws advance n.  Scheduler order: abm_config.scheduler (ABM_SCHED_* below) — by agent id, or
+ *   Schedulers.randomly as a Philox-keyed permutation of the ids, fresh every tick.
  */
 #ifndef ABM_H_
 #define ABM_H_
@@ -58,6 +59,17 @@ enum {
   ABM_ALTERNATED_WALK = 3,
   ABM_RANDOM_WALKMAP = 4
 };
+
+/* Agents.Schedulers: the order in which the agents of a tick are stepped.  Every reference script selects
+ * Schedulers.randomly (scripts/v0.1.jl:63 ... scripts/v0.6.jl:100).  BY_ID is ascending id.  RANDOMLY is a fresh
+ * pseudo-random order every tick: ascending ORDER KEY, key = P_t(id), where P_t is a keyed permutation of [0, 2^b): a
+ * 4-round balanced Feistel network over b = 2 hb bits, b the smallest even number >= 2 with 2^b >= nextid(model) at the
+ * start of the tick; round i maps (L, R) -> (R, L xor (mix(R xor k_i) mod 2^hb)) with mix(z) = z * 0x9E3779B1, z ^= z >> 15,
+ * z *= 0x85EBCA77, z ^= z >> 13 (32-bit), and (k_0..k_3) = Philox4x32-10(counter (0, tick, 2^32-1, 2^32-1); key = seed), the
+ * stream of the reserved agent id 2^64-1.  (The reference shuffles with its MersenneTwister; the north star replaces that
+ * RNG, so the permutation is part of the Philox contract above.)  Offspring receive nextid(model) in the order their
+ * parents are stepped; the first agent stepped onto a grown cell eats it. */
+enum { ABM_SCHED_BY_ID = 0, ABM_SCHED_RANDOMLY = 1 };
 
 /* Agents.Pathfinding cost metrics used by the scripts (v0.4/v0.5: DirectDistance default,
  * v0.6: PenaltyMap(elevation, MaxDistance{2}()), scripts/v0.6.jl:87-93) */
@@ -107,6 +119,8 @@ typedef struct abm_config {
    * ghost rows of the neighbouring strips above and below (wrapped when periodic; only walkmap and elevation are read
    * there), and agents are exchanged with global 1-based y. */
   int32_t strip_y0, strip_ny, n_ranks, rank;
+  int32_t scheduler;        /* ABM_SCHED_BY_ID (default) / ABM_SCHED_RANDOMLY: AgentBasedModel(...; scheduler), scripts/v0.1.jl:63 */
+  int32_t reserved1;
 } abm_config;
 
 typedef struct abm_handle abm_handle;

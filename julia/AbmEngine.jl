@@ -31,6 +31,7 @@ Base.@kwdef mutable struct AbmConfig
     reproduction_prob::Float64 = 0.001;  attractor_x::Float64 = 40;  attractor_y::Float64 = 40
     seed::UInt64 = 321
     strip_y0::Int32 = 0;  strip_ny::Int32 = 0;  n_ranks::Int32 = 0;  rank::Int32 = 0
+    scheduler::Int32 = 0;  reserved1::Int32 = 0   # 0 = Schedulers.by_id, 1 = Schedulers.randomly (Philox-keyed permutation per tick)
 end
 
 function __init__()
@@ -83,6 +84,7 @@ function create_handle(model, a::EngineAgentStep, m::EngineModelStep)
                     counter = prop(model, :counter, 50), prob_random_walk = a.prob_random_walk,
                     delta_energy = s.Δenergy, movement_cost = s.movement_cost, reproduction_prob = s.reproduction_prob,
                     attractor_x = att[1], attractor_y = att[2], seed = prop(model, :seed, 321),
+                    scheduler = model.scheduler === Schedulers.randomly ? 1 : 0,   # scripts/v0.1.jl:63; anything else is stepped by id
                     astar_metric = prop(model, :astar_max_distance, false) ? 1 : 0, astar_penalty = hasproperty(model, :elevation) ? 1 : 0)
     cfg.struct_size = sizeof(AbmConfig)
     h = Ref{Ptr{Cvoid}}(C_NULL)

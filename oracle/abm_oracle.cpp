@@ -495,12 +495,38 @@ static void model_step(Model& m) {
   }
 }
 
-/* Agents.step!(model, agent_step!, model_step!, n) with Schedulers.by_id, agents_first = true */
+/* Schedulers.randomly under the Philox contract (include/abm.h, ABM_SCHED_RANDOMLY): the order key of `id` in tick `tick`
+ * — a 4-round balanced Feistel permutation of [0, 2^(2 hb)), 2^(2 hb) >= nextid, round keys from the Philox block of the
+ * reserved agent id 2^64-1 */
+static u32 sched_mix(u32 z) { z *= 0x9E3779B1u; z ^= z >> 15; z *= 0x85EBCA77u; z ^= z >> 13; return z; }
+static std::vector<i64> schedule(const Model& m) {
+  std::vector<i64> ids;
+  ids.reserve(m.agents.size());
+  for (std::map<i64, Sheep>::const_iterator it = m.agents.begin(); it != m.agents.end(); ++it) ids.push_back(it->first);
+  if (m.cfg.scheduler != ABM_SCHED_RANDOMLY) return ids; /* Schedulers.by_id = sorted keys of model.agents */
+  int hb = 1;
+  while (hb < 16 && (1ull << (2 * hb)) < (u64)(m.maxid + 1)) ++hb;
+  const u32 ctr[4] = {0u, (u32)m.tick, 0xFFFFFFFFu, 0xFFFFFFFFu}, key[2] = {(u32)m.cfg.seed, (u32)(m.cfg.seed >> 32)};
+  u32 k[4];
+  philox4x32_10(ctr, key, k);
+  const u32 mask = (1u << hb) - 1u;
+  std::vector<std::pair<u32, i64>> keyed;
+  keyed.reserve(ids.size());
+  for (size_t i = 0; i < ids.size(); ++i) {
+    u32 L = (u32)ids[i] >> hb, R = (u32)ids[i] & mask;
+    for (int r = 0; r < 4; ++r) { const u32 t = L ^ (sched_mix(R ^ k[r]) & mask); L = R; R = t; }
+    keyed.push_back(std::make_pair((L << hb) | R, ids[i]));
+  }
+  std::sort(keyed.begin(), keyed.end());
+  for (size_t i = 0; i < ids.size(); ++i) ids[i] = keyed[i].second;
+  return ids;
+}
+
+/* Agents.step!(model, agent_step!, model_step!, n), agents_first = true: the scheduler's ids are collected before the first
+ * agent steps (newborns are not scheduled until the next tick), dead agents are skipped */
 static int step(Model& m, i64 n) {
   for (i64 t = 0; t < n; ++t) {
-    std::vector<i64> ids;
-    ids.reserve(m.agents.size());
-    for (std::map<i64, Sheep>::iterator it = m.agents.begin(); it != m.agents.end(); ++it) ids.push_back(it->first);
+    const std::vector<i64> ids = schedule(m);
     for (size_t i = 0; i < ids.size(); ++i) {
       if (!m.agents.count(ids[i])) continue;
       m.rng.reset(m.tick, (u64)ids[i]);

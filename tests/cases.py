@@ -36,6 +36,13 @@ CASES = {
     "tile_gregarious_r1_dense_64x64": (64, 64, 3500, GREG, 1, False, dict(visual_distance=1, prob_random_walk=0.3, reproduction_prob=0.08, regrowth_time=2, delta_energy=3.0), (1, 5, 30)),
     "tile_walkmap_128x96": (128, 96, 3000, WMAP, 1, True, dict(walkmap_regrowth=1, reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0), (1, 5, 30)),
     "tile_crowded_64x64": (64, 64, 12000, RW, 1, False, dict(reproduction_prob=0.1, regrowth_time=1, delta_energy=3.0), (1, 5, 20)),
+    # Schedulers.randomly (the scheduler every reference script selects, scripts/v0.1.jl:63): the Philox-keyed order of include/abm.h
+    "randomly_v0.1_default": (80, 80, 40, RW, 0, False, dict(scheduler=1), (1, 10, 100)),
+    "randomly_dense_rw_clamped": (37, 29, 500, RW, 0, False, dict(scheduler=1, reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0), (1, 5, 40)),
+    "randomly_dense_alternated": (40, 40, 300, ALT, 1, True, dict(scheduler=1, counter=7, reproduction_prob=0.03, regrowth_time=3, delta_energy=3.0, astar_metric=1, astar_penalty=1), (1, 5, 40)),
+    "randomly_tile_gregarious_r3_96x96": (96, 96, 2500, GREG, 1, False, dict(scheduler=1, visual_distance=3, reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0), (1, 5, 30)),
+    "randomly_tile_attractor_128x64": (128, 64, 3000, ATT, 0, False, dict(scheduler=1, reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0, prob_random_walk=0.5), (1, 5, 30)),
+    "randomly_tile_walkmap_128x96": (128, 96, 3000, WMAP, 1, True, dict(scheduler=1, walkmap_regrowth=1, reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0), (1, 5, 30)),
     "tiny_ring_2x2": (2, 2, 3, RW, 1, False, dict(reproduction_prob=0.2, regrowth_time=1), (1, 5, 20)),
     "ragged_33x1": (33, 1, 12, RW, 1, False, dict(reproduction_prob=0.1, regrowth_time=2), (1, 5, 20)),
 }

@@ -3,7 +3,7 @@
 There is no runnable reference in this container (Julia absent; Agents.jl not vendored), and the reference's tests
 hold no vectors, so these are ORACLE-GENERATED regression fixtures, labelled as such: they pin the oracle (and
 through it the engine) against silent change; they are not outputs of the reference.
-Run:  python tests/golden/make_golden.py
+Run:  python tests/golden/make_golden.py [case ...]   (no argument: every case of tests/cases.py)
 """
 import json
 import os
@@ -19,7 +19,7 @@ from cases import CASES, build_case  # noqa: E402
 
 def main():
     lib = capi.CLib(build.build_oracle(), "oracle_")
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):
         cfgkw, w, state, ticks = build_case(name)
         e = load_case(lib, cfgkw, w)
         if state:

@@ -64,13 +64,15 @@ def mod1(a, n):
 class Model:
     def __init__(self, nx, ny, periodic, walk_type, seed=321, eat=True, reproduce=True, walkmap_regrowth=False,
                  regrowth_time=30, visual_distance=5, counter=50, prob_random_walk=0.9, delta_energy=4.0,
-                 movement_cost=1.0, reproduction_prob=0.001, attractor=None, ifempty=True, astar_metric=0, astar_penalty=0):
+                 movement_cost=1.0, reproduction_prob=0.001, attractor=None, ifempty=True, astar_metric=0, astar_penalty=0, scheduler=0):
         self.nx, self.ny, self.periodic, self.walk_type = nx, ny, bool(periodic), walk_type
         self.eat, self.reproduce, self.walkmap_regrowth = eat, reproduce, walkmap_regrowth
         self.regrowth_time, self.r, self.counter = regrowth_time, visual_distance, counter
         self.prob, self.de, self.cost, self.rp = prob_random_walk, delta_energy, movement_cost, reproduction_prob
         self.attractor = attractor if attractor is not None else (nx / 2, ny / 2)
         self.ifempty = ifempty
+        self.scheduler = scheduler  # 0 = Schedulers.by_id, 1 = Schedulers.randomly (include/abm.h, ABM_SCHED_RANDOMLY)
+        self.seed = seed
         self.rng = Rng(seed)
         self.agents = {}   # id -> [x, y, energy]
         self.cells = {}    # (x, y) -> [ids] in insertion order
@@ -310,9 +312,35 @@ class Model:
                 else:
                     self.countdown[p] -= 1
 
+    def schedule(self):
+        """ids in the order the scheduler steps them this tick: sorted (by_id), or by the Feistel order key (randomly)."""
+        ids = sorted(self.agents)
+        if not self.scheduler:
+            return ids
+        hb = 1
+        while hb < 16 and (1 << (2 * hb)) < self.maxid + 1:
+            hb += 1
+        k = philox4x32_10([0, self.tick & MASK, MASK, MASK], [self.seed & MASK, (self.seed >> 32) & MASK])
+        m = (1 << hb) - 1
+
+        def mix(z):
+            z = (z * 0x9E3779B1) & MASK
+            z ^= z >> 15
+            z = (z * 0x85EBCA77) & MASK
+            z ^= z >> 13
+            return z
+
+        def key(i):
+            left, right = i >> hb, i & m
+            for r in range(4):
+                left, right = right, left ^ (mix(right ^ k[r]) & m)
+            return (left << hb) | right
+
+        return sorted(ids, key=key)
+
     def step(self, n=1):
         for _ in range(n):
-            for aid in sorted(self.agents):
+            for aid in self.schedule():
                 if aid in self.agents:
                     self.rng.reset(self.tick, aid)
                     self.agent_step(aid)

@@ -35,13 +35,13 @@ def test_binding_covers_every_declared_symbol():
 def test_config_struct_layout_matches_header():
     lib = capi.CLib(build.build_libabm(), "abm_")
     cfg = lib.default_config()
-    assert cfg.struct_size == C.sizeof(capi.AbmConfig) == 136
+    assert cfg.struct_size == C.sizeof(capi.AbmConfig) == 144
     assert (cfg.nx, cfg.ny, cfg.regrowth_time, cfg.seed) == (80, 80, 30, 321)  # scripts/v0.1.jl:36-46
 
 
 def test_bad_config_is_rejected_without_a_gpu():
     lib = capi.CLib(build.build_libabm(), "abm_")
-    for kw in (dict(nx=0), dict(walk_type=9), dict(regrowth_time=500), dict(walk_type=2, periodic=0)):
+    for kw in (dict(nx=0), dict(walk_type=9), dict(regrowth_time=500), dict(walk_type=2, periodic=0), dict(scheduler=2)):
         with pytest.raises(capi.AbmError) as ei:
             lib.create(lib.default_config(**kw))
         assert ei.value.code == capi.ABM_E_BADARG

@@ -65,6 +65,23 @@ def test_step_and_run_on_the_gpu(libabm, oracle):
     _check_step_and_run(libabm, oracle)
 
 
+def test_scheduler_randomly_through_the_mirror(emu, oracle):
+    """`scheduler = Schedulers.randomly` (scripts/v0.1.jl:63): same trajectory from engine and oracle, and not the by-id one."""
+    runs = {}
+    for sched in ("by_id", "randomly"):
+        m, astep, mstep = _script_model(emu, "v0.3", scheduler=sched, n_sheep=900)
+        ref, _, _ = _script_model(oracle, "v0.3", scheduler=sched, n_sheep=900)
+        A.step(m, astep, mstep, 6)
+        A.step(ref, astep, mstep, 6)
+        for a, b in zip(m.agents(), ref.agents()):
+            assert np.array_equal(a, b)
+        assert np.array_equal(m.fully_grown, ref.fully_grown)
+        runs[sched] = m.agents()
+    assert not (runs["by_id"][1].shape == runs["randomly"][1].shape and np.array_equal(runs["by_id"][1], runs["randomly"][1]))
+    with pytest.raises(ValueError):
+        A.initialize_model(scheduler="fastest", lib=emu)
+
+
 def test_changing_the_rules_keeps_the_state(emu):
     m, astep, mstep = _script_model(emu, "v0.3")
     A.step(m, astep, mstep, 3)

@@ -97,6 +97,11 @@ def test_gpu_matches_golden(libabm, name):
     (2, 1, 0, 9000, 200, 130, dict(visual_distance=5)),
     (4, 1, 1, 20000, 256, 256, dict(walkmap_regrowth=1)),
     (3, 1, 1, 6000, 192, 160, dict(counter=50, astar_metric=1, astar_penalty=1)),
+    # Schedulers.randomly on the general, tile and stream paths
+    (0, 0, 0, 20000, 250, 190, dict(scheduler=1)),
+    (2, 1, 0, 16000, 256, 256, dict(visual_distance=3, scheduler=1)),
+    (4, 1, 1, 20000, 256, 256, dict(walkmap_regrowth=1, scheduler=1)),
+    (3, 1, 1, 6000, 192, 160, dict(counter=50, astar_metric=1, astar_penalty=1, scheduler=1)),
 ])
 def test_gpu_matches_oracle_tick_by_tick(libabm, oracle, wt, per, terr, n, nx, ny, extra):
     """Mid-size seeded worlds (the oracle needs seconds): every tick compared."""

@@ -20,6 +20,10 @@ CASES = {
     "gregarious": dict(nx=64, ny=128, n=2500, wt=2, per=1, kw=dict(visual_distance=3, reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0)),
     "gregarious_r7": dict(nx=64, ny=96, n=900, wt=2, per=1, kw=dict(visual_distance=7, prob_random_walk=0.2, reproduction_prob=0.05, regrowth_time=2, delta_energy=3.0)),
     "walkmap": dict(nx=96, ny=128, n=3000, wt=4, per=1, terrain=True, kw=dict(walkmap_regrowth=1, reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0)),
+    # Schedulers.randomly: order keys instead of ids in everything the strips exchange for ORDER (ghost summaries, parents)
+    "rw_randomly": dict(nx=64, ny=128, n=3000, wt=0, per=1, kw=dict(scheduler=1, reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0)),
+    "gregarious_randomly": dict(nx=64, ny=128, n=2500, wt=2, per=1, kw=dict(scheduler=1, visual_distance=3, reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0)),
+    "walkmap_randomly": dict(nx=96, ny=128, n=3000, wt=4, per=1, terrain=True, kw=dict(scheduler=1, walkmap_regrowth=1, reproduction_prob=0.05, regrowth_time=3, delta_energy=3.0)),
 }
 
 
@@ -50,7 +54,7 @@ def _case(name):
     return make_case(c["nx"], c["ny"], c["n"], c["wt"], c["per"], terrain=c.get("terrain", False), seed=31, **c["kw"])
 
 
-@pytest.mark.parametrize("name", ["rw", "gregarious", "walkmap"])
+@pytest.mark.parametrize("name", ["rw", "gregarious", "walkmap", "gregarious_randomly", "walkmap_randomly"])
 def test_single_strip_ring_of_one(emu, oracle, name):
     cfgkw, w = _case(name)
     a = load_case(oracle, cfgkw, w)
@@ -107,7 +111,8 @@ def _run_ring(world, name, ticks, tmp_path, use_gpu=False, transport="nccl"):
     return [np.load(os.path.join(str(tmp_path), f"snap_{r}.npy"), allow_pickle=True) for r in range(world)]
 
 
-@pytest.mark.parametrize("world,name", [(2, "rw"), (2, "gregarious"), (2, "rw_clamped"), (3, "attractor"), (2, "walkmap"), (3, "gregarious_r7"), (4, "walkmap"), (3, "fuzz11"), (2, "fuzz12"), (3, "crowd3"), (2, "crowd4"), (3, "crowd9")])
+@pytest.mark.parametrize("world,name", [(2, "rw"), (2, "gregarious"), (2, "rw_clamped"), (3, "attractor"), (2, "walkmap"), (3, "gregarious_r7"), (4, "walkmap"), (3, "fuzz11"), (2, "fuzz12"), (3, "crowd3"), (2, "crowd4"), (3, "crowd9"),
+                                        (2, "rw_randomly"), (3, "gregarious_randomly"), (2, "walkmap_randomly")])
 def test_ring_of_processes_over_gloo(oracle, tmp_path, world, name):
     build.build_emu()
     ticks = 8
@@ -201,7 +206,7 @@ def test_two_strips_over_nccl(libabm, oracle, tmp_path, name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["rw", "gregarious", "walkmap", "rw_clamped"])
+@pytest.mark.parametrize("name", ["rw", "gregarious", "walkmap", "rw_clamped", "gregarious_randomly", "walkmap_randomly"])
 def test_two_strips_over_peer_memory(libabm, oracle, tmp_path, name):
     """The NVLink mailbox transport (abm_p2p_export / abm_p2p_connect): kernels store into the neighbour's memory."""
     import torch

@@ -5,7 +5,7 @@
     python tools/fuzz.py astar START COUNT    # abm_plan_routes / abm_get_paths (random terrain, goals anywhere, replans,
                                               # 1-64 search slots, route pools that overflow): engine vs oracle
 
-`FORCE_GENERAL=1` sends a third of the tile-sized engine cases down the general path; `ABM_TILE_ROUNDS=1` leaves most
+`FUZZ_SCHED=1` steps every case under Schedulers.randomly (default: half of them).  `FORCE_GENERAL=1` sends a third of the tile-sized engine cases down the general path; `ABM_TILE_ROUNDS=1` leaves most
 conflicts to the per-agent windows.  Every seed is reproducible: `engine_vs_oracle(seed)` / `oracle_vs_pyref(seed)` return
 "ok", "skip ...", "refused ..." (abm_create turned the configuration down), "both raised", or a line starting with DIFF /
 ERROR.  tests/test_fuzz.py runs a bounded number of seeds; 2,300 engine, 4,400 oracle and 5,600 A* seeds were clean when this
@@ -31,6 +31,12 @@ def _lib(which):
     return _libs[which]
 
 
+def _sched(rng):
+    """Schedulers.by_id or Schedulers.randomly (FUZZ_SCHED=0/1 forces one)"""
+    v = int(rng.integers(0, 2))
+    return int(os.environ["FUZZ_SCHED"]) if "FUZZ_SCHED" in os.environ else v
+
+
 SIZES = [(64, 64), (96, 64), (64, 96), (128, 64), (5, 7), (33, 31), (40, 30), (1, 9), (2, 2), (17, 64), (64, 33)]
 
 
@@ -46,7 +52,7 @@ def engine_vs_oracle(seed):
     terr = wt in (3, 4) or (rng.random() < 0.2 and wt != 2)
     kw = dict(reproduction_prob=float(rng.choice([0.0, 0.01, 0.1, 0.5])), regrowth_time=int(rng.integers(1, 8)), delta_energy=float(rng.integers(1, 5)),
               prob_random_walk=float(rng.choice([0.0, 0.3, 0.9, 1.0])), visual_distance=int(rng.integers(1, 8)), eat=int(rng.random() < 0.8), reproduce=int(rng.random() < 0.8),
-              movement_cost=float(rng.choice([0.5, 1.0, 2.0])))
+              movement_cost=float(rng.choice([0.5, 1.0, 2.0])), scheduler=_sched(rng))
     if wt == 4: kw["walkmap_regrowth"] = int(rng.integers(0, 2))
     if wt == 3:
         kw.update(counter=int(rng.integers(2, 9)), astar_metric=int(rng.integers(0, 2)), astar_penalty=int(rng.integers(0, 2)))
@@ -93,7 +99,7 @@ def oracle_vs_pyref(seed):
     terr = wt in (3, 4) or (rng.random() < 0.2 and wt != 2)
     kw = dict(reproduction_prob=float(rng.choice([0.0, 0.02, 0.2])), regrowth_time=int(rng.integers(1, 8)), delta_energy=float(rng.integers(1, 5)),
               prob_random_walk=float(rng.choice([0.0, 0.3, 0.9, 1.0])), visual_distance=r, eat=int(rng.random() < 0.8), reproduce=int(rng.random() < 0.8),
-              movement_cost=float(rng.choice([0.5, 1.0, 2.0])))
+              movement_cost=float(rng.choice([0.5, 1.0, 2.0])), scheduler=_sched(rng))
     if wt == 4: kw["walkmap_regrowth"] = int(rng.integers(0, 2))
     if wt == 3: kw.update(counter=int(rng.integers(2, 9)), astar_metric=int(rng.integers(0, 2)), astar_penalty=int(rng.integers(0, 2)))
     try:
@@ -103,7 +109,8 @@ def oracle_vs_pyref(seed):
     e = load_case(_lib("oracle"), cfgkw, w)
     m = pyref.Model(nx, ny, per, wt, seed=cfgkw["seed"], eat=bool(kw["eat"]), reproduce=bool(kw["reproduce"]), walkmap_regrowth=bool(kw.get("walkmap_regrowth", 0)),
                     regrowth_time=kw["regrowth_time"], visual_distance=r, counter=kw.get("counter", 50), prob_random_walk=kw["prob_random_walk"], delta_energy=kw["delta_energy"],
-                    movement_cost=kw["movement_cost"], reproduction_prob=kw["reproduction_prob"], astar_metric=kw.get("astar_metric", 0), astar_penalty=kw.get("astar_penalty", 0))
+                    movement_cost=kw["movement_cost"], reproduction_prob=kw["reproduction_prob"], astar_metric=kw.get("astar_metric", 0), astar_penalty=kw.get("astar_penalty", 0),
+                    scheduler=kw["scheduler"])
     m.set_grid(w["fully_grown"], w["countdown"], w["walkmap"], w["elevation"])
     m.set_agents(w["ids"], w["x"], w["y"], w["energy"])
     if wt == 3:
