@@ -289,6 +289,12 @@ struct abm_handle {
   int32_t tile_rounds = 8;        /* in-window rounds of the tile resolve kernel (ABM_TILE_ROUNDS overrides; tests use 1) */
   int32_t tile_margin = HALO;     /* halo cells actually taken into a core's window (ABM_TILE_MARGIN overrides) */
   DevBuf okey;                    /* Schedulers.randomly: order key per agent (own + ghost), recomputed every tick */
+  /* offspring ids off the critical path: the reproducing agents are known after propose, so their order keys are gathered
+   * and ranked on a second stream while the tick resolves and commits (ABM_EARLY_BIRTHS=0: after the commit, as before) */
+  bool early_births = true;
+  abm_stream_t side = 0;
+  abm_event_t ev_proposed = 0, ev_ranked = 0;
+  DevBuf parents;                 /* [count][order keys of this handle's reproducing agents] */
   int32_t nsx = 0, nsy = 0;
   DevBuf sub_off[2], sub_cnt[2], birth_pos, birth_parent, ingest_sub, mig_cnt, mig_a, mig_lc;
   bool use_migrants = false; /* ABM_MIGRANTS=1: border crossers are listed per destination core and the commit reads only its
@@ -557,7 +563,7 @@ static int tick_once(abm_handle* h) {
     pb.v = v;
     pb.pending = (uint32_t*)h->pend[0].p;
     pb.pending_count = ctr + CTR_PEND_A;
-    pb.birth_flags = nullptr;
+    pb.birth_flags = nullptr; pb.parent_list = nullptr; pb.parent_cap = 0;
     { ProfScope ps(h->prof, h->stream, "propose", n); launch_foreach(h->stream, pb, n); }
     if ((rc = check_launch(h, "propose"))) return rc;
   }
@@ -680,6 +686,60 @@ static SubIndex sub_index(abm_handle* h, int which) {
 
 #include "abm_host_stream.inl"
 
+/* The offspring ids' ranks, prepared on the side stream while the tick resolves (tick_tile).  In: [count][order keys] of this
+ * handle's reproducing agents (ProposeBody; count = CTR_BIRTH_FLAGS).  Out: every strip's list side by side in h->birth_ids,
+ * the bitmap of all of them over the key space in h->bits and its popcount prefix in h->bits_prefix; ev_ranked is recorded
+ * behind the last kernel.  Strips exchange the lists through their peer-memory mailboxes (the birth channel). */
+struct ParentCountBody {
+  const uint32_t* count; uint32_t cap; uint32_t* msg;
+  ABM_HD void operator()(uint64_t) const { const uint32_t c = *count; msg[0] = c < cap ? c : cap; }
+};
+static int early_births_enqueue(abm_handle* h, uint64_t cap, uint64_t words) {
+  const int P = h->n_ranks;
+  uint32_t* ctr = (uint32_t*)h->counters.p;
+  uint32_t* msg = (uint32_t*)h->parents.p;
+  uint32_t* all = (uint32_t*)h->birth_ids.p;
+  const abm_stream_t s = h->side;
+  event_record(h->ev_proposed, h->stream);
+  stream_wait_event(s, h->ev_proposed);
+  bool gathered = false;
+#ifndef ABM_EMU
+  if (h->strip && h->p2p_on && P > 1) {
+    const uint32_t seq = ++h->p2p_seq[P2P_CH_BIRTHS];
+    const int parity = (int)(seq & 1u);
+    P2PBirthSendCta sd;
+    sd.birth_parent = msg + 1; sd.birth_count = ctr + CTR_BIRTH_FLAGS; sd.cap = (uint32_t)cap; sd.seq = seq; sd.done = ctr + CTR_BIRTH_DONE;
+    P2PBirthRecvCta rv;
+    rv.seq = seq; rv.cap = (uint32_t)cap; rv.all = all; rv.err = ctr + CTR_ERR;
+    for (int r = 0; r < P; ++r) {
+      sd.dst[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.births_off(h->my_rank, parity));
+      sd.flag[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.flag_off(P2P_CH_BIRTHS, h->my_rank, parity));
+      rv.src[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.births_off(r, parity));
+      rv.flag[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.flag_off(P2P_CH_BIRTHS, r, parity));
+    }
+    launch_cta(s, sd, (uint64_t)P * BIRTH_CTAS, 256, 16);
+    launch_cta(s, rv, (uint64_t)P * BIRTH_CTAS, 256, 16);
+    gathered = true;
+  }
+#endif
+  if (!gathered) { /* a single handle (or a ring of one): its own list is the whole gathering */
+    ParentCountBody pc;
+    pc.count = ctr + CTR_BIRTH_FLAGS; pc.cap = (uint32_t)cap; pc.msg = msg;
+    launch_foreach(s, pc, 1);
+    ABM_CK(h, copy_d2d(all, msg, (1 + cap) * 4, s));
+  }
+  ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, s));
+  BirthMarkBody bm;
+  bm.all = all; bm.n_ranks = P; bm.cap = (uint32_t)cap; bm.bits = (uint32_t*)h->bits.p;
+  launch_foreach(s, bm, (uint64_t)P * std::max<uint64_t>(cap, 1));
+  PopcountBody pb;
+  pb.bits = (const uint32_t*)h->bits.p; pb.out = (uint32_t*)h->bits_prefix.p;
+  launch_foreach(s, pb, words);
+  ABM_CK(h, scan_exclusive_u32(s, (uint32_t*)h->bits_prefix.p, words, (uint32_t*)h->scan_tmp.p));
+  event_record(h->ev_ranked, s);
+  return check_launch(h, "early offspring ranks");
+}
+
 /* one tick on the tile path (abm_tile.h): propose -> window resolve -> per-agent windows for the rest -> commit */
 static int tick_tile(abm_handle* h) {
   int rc;
@@ -718,12 +778,37 @@ static int tick_tile(abm_handle* h) {
   const int wt = h->cfg.walk_type;
   const bool needs_resolve = wt == ABM_RANDOM_WALK_ATTRACTOR || wt == ABM_RANDOM_WALK_GREGARIOUS || (wt == ABM_RANDOM_WALK && h->cfg.randomwalk_ifempty);
   uint64_t cnt = 0;
-  if (n > 0) {
+  /* Will this tick commit behind the device-side guard?  Then the offspring ids can be prepared early: every reproducing
+   * agent is known after propose, so the parents' order keys are gathered from all strips and ranked (bitmap over the key
+   * space + popcount prefix) on the side stream while the tick resolves and commits; what stays behind the commit is one
+   * small kernel.  Peer-memory strips and single handles only (an NCCL collective must not run beside the main stream's). */
+  const bool optimistic = h->optimistic && h->bf_est > 0 && (!h->strip || strip_stats_on_device(h));
+  bool early = optimistic && h->early_births && h->cfg.reproduce && (!h->strip || h->n_ranks == 1);
+#ifndef ABM_EMU
+  if (optimistic && h->early_births && h->cfg.reproduce && h->strip && h->p2p_on) early = true;
+#endif
+  const int P_all = h->n_ranks;
+  const uint64_t ecap = h->bf_est, ewords = bitmap_words(key_space(h, h->next_id));
+  if (early) { /* every buffer the side stream touches exists before anything is enqueued */
+    if ((rc = ensure(h, h->parents, (ecap + 2) * 4))) return rc;
+    if ((rc = ensure(h, h->birth_ids, (1 + ecap) * 4 * (size_t)(P_all + 2) + 64))) return rc;
+    if ((rc = ensure(h, h->bits, (ewords + 4) * 4))) return rc;
+    if ((rc = ensure(h, h->bits_prefix, (ewords + 4) * 4))) return rc;
+    if ((rc = ensure(h, h->scan_tmp, scan_tmp_words(std::max<uint64_t>(ewords, (uint64_t)h->g.gt + 1)) * 4))) return rc;
+#ifndef ABM_EMU
+    if (h->strip && h->p2p_on && (1 + ecap) * 4 > h->p2p_lay.births_bytes) early = false; /* the mailbox is smaller: gather after the commit */
+#endif
+  }
+  {
     ProposeBody pb;
     pb.v = v; pb.pending = nullptr; pb.pending_count = nullptr; pb.birth_flags = ctr + CTR_BIRTH_FLAGS;
-    { ProfScope ps(h->prof, h->stream, "propose", n); launch_foreach(h->stream, pb, n); }
-    if ((rc = check_launch(h, "propose"))) return rc;
+    pb.parent_list = early ? (uint32_t*)h->parents.p + 1 : nullptr; pb.parent_cap = (uint32_t)ecap;
+    if (n > 0) {
+      { ProfScope ps(h->prof, h->stream, "propose", n); launch_foreach(h->stream, pb, n); }
+      if ((rc = check_launch(h, "propose"))) return rc;
+    }
   }
+  if (early && (rc = early_births_enqueue(h, ecap, ewords))) return rc;
   const int cores_x = h->g.nx / CORE, core_rows = (h->g.own_hi - h->g.own_lo) / CORE;
   auto launch_tiles = [&](int row0, int nrows, int row_step = 1) -> int { /* window resolve of the core rows row0, row0 + step, ... */
     if (nrows <= 0) return 0;
@@ -797,7 +882,7 @@ static int tick_tile(abm_handle* h) {
     if ((r = ensure_soa(h, nxt, n + bflags + 2 * arrivals_cap))) return r;
     if ((r = ensure(h, h->birth_pos, (bflags + arrivals_cap + 1) * 4))) return r;
     if ((r = ensure(h, h->birth_parent, (bflags + arrivals_cap + 1) * 4))) return r;
-    if (bflags > 0 || h->strip) {
+    if ((bflags > 0 || h->strip) && !(early && go)) {
       if ((r = ensure(h, h->bits, (words + 4) * 4))) return r;
       if (!h->strip) ABM_CK(h, dev_memset(h->bits.p, 0, words * 4, h->stream));
     }
@@ -823,7 +908,7 @@ static int tick_tile(abm_handle* h) {
     ct.new_off = (uint32_t*)h->sub_off[nxt].p; ct.new_cnt = (uint32_t*)h->sub_cnt[nxt].p;
     ct.cursor = ctr + CTR_CURSOR;
     ct.birth_pos = (uint32_t*)h->birth_pos.p; ct.birth_parent = (uint32_t*)h->birth_parent.p; ct.birth_count = ctr + CTR_BIRTHS;
-    ct.birth_bits = h->strip ? nullptr : (uint32_t*)h->bits.p; /* strips rank the parents globally instead */
+    ct.birth_bits = (h->strip || (early && go)) ? nullptr : (uint32_t*)h->bits.p; /* strips (and the early gather) rank the parents from their lists */
     ct.go = go;
     { ProfScope ps(h->prof, h->stream, "commit_tiles", n); launch_cta(h->stream, ct, cores, COMMIT_THREADS, CommitTile::smem_bytes()); }
     return check_launch(h, "tile commit");
@@ -835,7 +920,7 @@ static int tick_tile(abm_handle* h) {
     h->cur = nxt; h->n = n_new; h->next_id += nb_total; h->n_ghost = 0; h->tick += 1; h->updates += (double)n;
     return 0;
   };
-  if (h->optimistic && h->bf_est > 0 && (!h->strip || strip_stats_on_device(h))) {
+  if (optimistic) {
     /* steady state: no read-back before the commit.  A one-thread guard tells the commit and the offspring kernels
      * whether everybody is decided and the output arrays (sized from last tick's births) are large enough; when not,
      * they do nothing and the careful path below redoes this part with exact figures.  Strips: the guard reads the
@@ -860,7 +945,22 @@ static int tick_tile(abm_handle* h) {
       launch_foreach(h->stream, tg, 1);
     }
     if ((rc = commit_phase(bcapn, ctr + CTR_GO))) return rc;
-    if (h->strip) {
+    if (early) { /* the ranks are ready (or about to be): offspring ids = next_id + rank of the parent's order key */
+      stream_wait_event(h->stream, h->ev_ranked);
+      const uint64_t arrivals_cap = h->strip ? 2 * h->bcap : 0;
+      BirthAssignBody ba;
+      ba.all = (const uint32_t*)h->birth_ids.p; ba.n_ranks = P; ba.cap = (uint32_t)ecap; ba.next_id = (uint32_t)h->next_id;
+      ba.birth_pos = (const uint32_t*)h->birth_pos.p; ba.birth_parent = (const uint32_t*)h->birth_parent.p; ba.birth_count = ctr + CTR_BIRTHS;
+      ba.rank_in = nullptr; ba.birth_bits = (const uint32_t*)h->bits.p; ba.birth_prefix = (const uint32_t*)h->bits_prefix.p;
+      ba.out_id = (uint32_t*)h->id[nxt].p; ba.total_out = ctr + CTR_BIRTH_TOTAL;
+      { ProfScope ps(h->prof, h->stream, "birth_ids", bcapn); launch_foreach(h->stream, ba, bcapn + arrivals_cap + 1); }
+      if ((rc = check_launch(h, "birth ids"))) return rc;
+      if (h->strip) {
+        birth_cap = 3 * bcapn + 64;
+        stats.assign((size_t)(1 + 3 * P), 0);
+        ABM_CK(h, copy_d2h(stats.data(), h->red_buf.p, stats.size() * 8, h->stream));
+      }
+    } else if (h->strip) {
       birth_cap = 3 * bcapn + 64;
       if ((rc = strip_birth_ids(h, birth_cap, nxt, ctr + CTR_BIRTH_TOTAL))) return rc;
       stats.assign((size_t)(1 + 3 * P), 0);
@@ -888,6 +988,7 @@ static int tick_tile(abm_handle* h) {
       return 0;
     }
     /* not ready (agents still open, or more births than expected): nothing was touched; go on carefully */
+    if (early) stream_wait_event(h->stream, h->ev_ranked); /* the side stream's buffers are about to be reused */
     if (needs_resolve) { h->clean_ticks = 0; if (h->fixed_agent_rounds < 6 && h->fixed_agent_rounds >= 1) ++h->fixed_agent_rounds; }
   }
   if ((rc = take_stats(ctr + (in ? CTR_PEND_B : CTR_PEND_A)))) return rc;

@@ -280,6 +280,8 @@ struct ProposeBody {
   uint32_t* pending;       /* worklist of undecided agents (general path; null on the tile path) */
   uint32_t* pending_count;
   uint32_t* birth_flags;   /* tile path: number of agents that will reproduce (sizes the output SoA); else null */
+  uint32_t* parent_list;   /* optional: their order keys, in any order (the offspring ids are ranked while the tick resolves) */
+  uint32_t parent_cap;
 
   ABM_HD void operator()(uint64_t i) const {
     const uint32_t k = (uint32_t)i;
@@ -290,7 +292,10 @@ struct ProposeBody {
     if (nowalk) atomic_or(v.err, ERR_NOWALKABLE);
     v.state[k] = st;
     if (pending && !(st & ST_DECIDED)) pending[atomic_add(pending_count, 1u)] = k;
-    if (birth_flags && (st & ST_BIRTH)) atomic_add(birth_flags, 1u);
+    if (birth_flags && (st & ST_BIRTH)) {
+      const uint32_t q = atomic_add(birth_flags, 1u);
+      if (parent_list && q < parent_cap) parent_list[q] = v.okey[k];
+    }
   }
 };
 

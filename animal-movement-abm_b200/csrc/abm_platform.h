@@ -124,6 +124,14 @@ static inline abm_err_t copy_d2d(void* d, const void* s, size_t bytes, abm_strea
 static inline abm_err_t copy_h2d_async(void* d, const void* h, size_t bytes, abm_stream_t) { memcpy(d, h, bytes); return 0; }
 static inline abm_err_t copy_d2h_async(void* h, const void* d, size_t bytes, abm_stream_t) { memcpy(h, d, bytes); return 0; }
 static inline abm_err_t stream_sync(abm_stream_t) { return 0; }
+/* a second stream and the events that order it against the first: the emulation runs everything in program order */
+typedef int abm_event_t;
+static inline abm_err_t side_stream_create(abm_stream_t* s) { *s = 0; return 0; }
+static inline void side_stream_destroy(abm_stream_t) {}
+static inline abm_err_t event_create(abm_event_t* e) { *e = 0; return 0; }
+static inline void event_destroy(abm_event_t) {}
+static inline void event_record(abm_event_t, abm_stream_t) {}
+static inline void stream_wait_event(abm_stream_t, abm_event_t) {}
 static inline const char* err_string(abm_err_t e) { return e ? "emulated allocation failure" : "ok"; }
 
 }  // namespace abm
@@ -311,6 +319,18 @@ static inline abm_err_t copy_d2d(void* d, const void* src, size_t bytes, abm_str
   return cudaMemcpyAsync(d, src, bytes, cudaMemcpyDeviceToDevice, s);
 }
 static inline abm_err_t stream_sync(abm_stream_t s) { return cudaStreamSynchronize(s); }
+/* a second, higher-priority stream for small work that overlaps the tick's big kernels, and the events that order it */
+typedef cudaEvent_t abm_event_t;
+static inline abm_err_t side_stream_create(abm_stream_t* s) {
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  return cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, hi);
+}
+static inline void side_stream_destroy(abm_stream_t s) { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
+static inline abm_err_t event_create(abm_event_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); }
+static inline void event_destroy(abm_event_t e) { if (e) cudaEventDestroy(e); }
+static inline void event_record(abm_event_t e, abm_stream_t s) { cudaEventRecord(e, s); }
+static inline void stream_wait_event(abm_stream_t s, abm_event_t e) { cudaStreamWaitEvent(s, e, 0); }
 static inline const char* err_string(abm_err_t e) { return cudaGetErrorString(e); }
 
 }  // namespace abm
