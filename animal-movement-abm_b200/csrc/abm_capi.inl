@@ -28,7 +28,7 @@ void ABM_API(destroy)(abm_handle* h) {
   if (h->p2p_mine) cudaFree(h->p2p_mine);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
   side_stream_destroy(h->side);
-  event_destroy(h->ev_proposed); event_destroy(h->ev_ranked);
+  event_destroy(h->ev_proposed); event_destroy(h->ev_ranked); event_destroy(h->ev_rows); event_destroy(h->ev_halo);
   if (h->stream) { cudaStreamDestroy(h->stream); }
   if (h->h_counters) cudaFreeHost(h->h_counters);
 #else
@@ -65,6 +65,7 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
     }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess || side_stream_create(&h->side) != cudaSuccess ||
         event_create(&h->ev_proposed) != cudaSuccess || event_create(&h->ev_ranked) != cudaSuccess ||
+        event_create(&h->ev_rows) != cudaSuccess || event_create(&h->ev_halo) != cudaSuccess ||
         cudaMallocHost((void**)&h->h_counters, 2 * CTR_WORDS * sizeof(uint32_t)) != cudaSuccess) {
       g_create_error = "stream / pinned memory creation failed";
       delete h; return ABM_E_CUDA;
@@ -115,6 +116,8 @@ int ABM_API(create)(const abm_config* cfg, abm_handle** out) {
   if (const char* ar = getenv("ABM_AGENT_ROUNDS")) { const int q = atoi(ar); if (q >= 0 && q <= 16) h->fixed_agent_rounds = h->min_agent_rounds = q; }
   if (const char* tm = getenv("ABM_TILE_MARGIN")) { const int q = atoi(tm); if (q >= 2 && q <= HALO) h->tile_margin = q; }
   if (const char* eb = getenv("ABM_EARLY_BIRTHS")) h->early_births = atoi(eb) != 0;
+  if (const char* oh = getenv("ABM_OVERLAP_HALO")) h->overlap_halo = atoi(oh) != 0;
+  if (const char* ol = getenv("ABM_OVERLAP_LISTS")) h->overlap_lists = atoi(ol) != 0;
   if (const char* tr = getenv("ABM_TILE_ROUNDS")) { const int q = atoi(tr); if (q >= 0 && q <= 64) h->tile_rounds = q; }
   rc = 0;
   do {

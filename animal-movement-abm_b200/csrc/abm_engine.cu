@@ -183,6 +183,7 @@ struct Prof {
   std::vector<Rec> recs;
   unsigned long long launches_at_end = 0; /* a scope that starts with no launch since the previous one ended shares its event */
   bool last_ended = false;
+  cudaStream_t last_stream = nullptr; /* ... and only when both are on the same stream */
   std::vector<cudaEvent_t> pool;
   cudaEvent_t get() { if (pool.empty()) { cudaEvent_t e; cudaEventCreate(&e); return e; } cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
 #endif
@@ -198,7 +199,7 @@ struct Prof {
     if (!on) return;
     if (recs.size() >= 8192) collect();
     Rec r; r.idx = i; r.b = get();
-    if (!recs.empty() && last_ended && launches_at_end == g_launches) { r.a = recs.back().b; r.own_a = false; }
+    if (!recs.empty() && last_ended && launches_at_end == g_launches && last_stream == s) { r.a = recs.back().b; r.own_a = false; }
     else { r.a = get(); r.own_a = true; cudaEventRecord(r.a, s); }
     last_ended = false;
     recs.push_back(r);
@@ -208,7 +209,7 @@ struct Prof {
   }
   void end(abm_stream_t s) {
 #ifndef ABM_EMU
-    if (on && !recs.empty()) { cudaEventRecord(recs.back().b, s); launches_at_end = g_launches; last_ended = true; }
+    if (on && !recs.empty()) { cudaEventRecord(recs.back().b, s); launches_at_end = g_launches; last_ended = true; last_stream = s; }
 #else
     (void)s;
 #endif
@@ -293,7 +294,11 @@ struct abm_handle {
    * and ranked on a second stream while the tick resolves and commits (ABM_EARLY_BIRTHS=0: after the commit, as before) */
   bool early_births = true;
   abm_stream_t side = 0;
-  abm_event_t ev_proposed = 0, ev_ranked = 0;
+  abm_event_t ev_proposed = 0, ev_ranked = 0, ev_rows = 0, ev_halo = 0;
+  /* peer-memory strips: exchanges beside compute on the side stream.  Tile path: the halo exchange beside propose — measured
+   * 0.641 vs 0.664 ms at 2 GPUs but 0.747 vs 0.712 ms at 8, so it is off unless ABM_OVERLAP_HALO=1.  Stream path: the list
+   * exchange beside the interior rows' kernel — 1.019 vs 1.045 ms at 8 GPUs (C5), on unless ABM_OVERLAP_LISTS=0. */
+  bool overlap_halo = false, overlap_lists = true;
   DevBuf parents;                 /* [count][order keys of this handle's reproducing agents] */
   int32_t nsx = 0, nsy = 0;
   DevBuf sub_off[2], sub_cnt[2], birth_pos, birth_parent, ingest_sub, mig_cnt, mig_a, mig_lc;
@@ -799,6 +804,25 @@ static int tick_tile(abm_handle* h) {
     if (h->strip && h->p2p_on && (1 + ecap) * 4 > h->p2p_lay.births_bytes) early = false; /* the mailbox is smaller: gather after the commit */
 #endif
   }
+  /* peer-memory strips: the two boundary rows are proposed first and travel (side stream) while propose does the rest */
+  bool halo_beside = false;
+#ifndef ABM_EMU
+  halo_beside = h->strip && h->p2p_on && h->n_ranks > 1 && h->overlap_halo;
+#endif
+  if (halo_beside) {
+    ProposeRowsCta pr;
+    pr.v = v; pr.si = si; pr.row[0] = h->g.own_lo / SUB; pr.row[1] = h->g.own_hi / SUB - 1;
+    pr.chunks = (h->nsx + TILE_THREADS / 32 - 1) / (TILE_THREADS / 32);
+    launch_cta(h->stream, pr, 2 * (uint64_t)pr.chunks, TILE_THREADS, 16);
+    event_record(h->ev_rows, h->stream);
+    stream_wait_event(h->side, h->ev_rows);
+    std::swap(h->stream, h->side); /* the exchange (and its profiling scope) is enqueued on the side stream */
+    rc = strip_exchange_agents(h);
+    if (!rc) order_keys(h, n, 2 * h->bcap);
+    event_record(h->ev_halo, h->stream);
+    std::swap(h->stream, h->side);
+    if (rc) return rc;
+  }
   {
     ProposeBody pb;
     pb.v = v; pb.pending = nullptr; pb.pending_count = nullptr; pb.birth_flags = ctr + CTR_BIRTH_FLAGS;
@@ -809,6 +833,7 @@ static int tick_tile(abm_handle* h) {
     }
   }
   if (early && (rc = early_births_enqueue(h, ecap, ewords))) return rc;
+  if (halo_beside) stream_wait_event(h->stream, h->ev_halo); /* the ghost rows are in place before anything looks across the border */
   const int cores_x = h->g.nx / CORE, core_rows = (h->g.own_hi - h->g.own_lo) / CORE;
   auto launch_tiles = [&](int row0, int nrows, int row_step = 1) -> int { /* window resolve of the core rows row0, row0 + step, ... */
     if (nrows <= 0) return 0;
@@ -820,9 +845,11 @@ static int tick_tile(abm_handle* h) {
     { ProfScope ps(h->prof, h->stream, "resolve_tiles", grid * 256, 1); launch_cta(h->stream, rw, grid, TILE_THREADS, ResolveWindow::smem_bytes_core()); }
     return check_launch(h, "tile resolve");
   };
-  if (h->strip && (rc = strip_exchange_agents(h))) return rc; /* neighbours' boundary rows become ghost rows behind the own agents */
-  if (h->strip) order_keys(h, n, 2 * h->bcap); /* the ghosts' order keys (slots beyond the real counts are never read) */
+  if (h->strip && !halo_beside && (rc = strip_exchange_agents(h))) return rc; /* neighbours' boundary rows become ghost rows behind the own agents */
+  if (h->strip && !halo_beside) order_keys(h, n, 2 * h->bcap); /* the ghosts' order keys (slots beyond the real counts are never read) */
   if (n + h->n_ghost > 0 && needs_resolve && (rc = launch_tiles(0, core_rows))) return rc;
+  /* (measured and dropped: resolving the two boundary core rows first and shipping their decisions beside the interior
+   * rows' resolve — the two 128-CTA launches cost more than the exchange they hide: 0.706 vs 0.666 ms at 2 GPUs) */
   /* figures the host needs before it can go on: open agents, reproducing agents (sizes of the output SoA); in strip
    * mode from every rank, through one all-reduce of device-resident counters */
   uint64_t birth_flags = 0, birth_cap = 0, global_cnt = 0, strip_fmax = 0;

@@ -163,7 +163,25 @@ static int tick_stream(abm_handle* h) {
   const uint64_t tiles = (uint64_t)h->g.tiles_x * (uint64_t)h->g.tiles_y;
   const int cores_x = h->g.nx / CORE, core_rows = (h->g.own_hi - h->g.own_lo) / CORE;
   uint32_t* sc = (uint32_t*)h->s_ctr.p;
-  if (h->strip && (rc = stream_exchange(h))) return rc; /* arrivals from the neighbouring strips; every strip's parents */
+  /* Strips: arrivals from the neighbours, and every strip's parents.  Over peer memory the list exchange runs on the side
+   * stream and only the two boundary core rows wait for it: the interior rows' kernel hides it.  (Not in a tick whose lists
+   * overflowed: an interior core would then scan the overflow list while the unpack appends to it.) */
+  bool lists_beside = false;
+#ifndef ABM_EMU
+  lists_beside = h->strip && h->p2p_on && h->n_ranks > 1 && h->overlap_lists && core_rows >= 3 && h->s_n_ovf == 0;
+#endif
+  if (h->strip) {
+    if (lists_beside) {
+      event_record(h->ev_rows, h->stream);
+      stream_wait_event(h->side, h->ev_rows);
+      std::swap(h->stream, h->side);
+      rc = stream_exchange_lists(h);
+      event_record(h->ev_halo, h->stream);
+      std::swap(h->stream, h->side);
+      if (rc) return rc;
+    } else if ((rc = stream_exchange_lists(h))) return rc;
+    if ((rc = stream_exchange_parents(h))) return rc;
+  }
   if (h->cfg.reproduce && (rc = stream_prefix(h, (const uint32_t*)h->s_bits[cur].p, h->s_words[cur]))) return rc;
   /* the lists and the parents bitmap of the next tick start empty */
   /* parents of tick + 1 have ids below next_id + births(tick), and births <= agents alive (all strips': < next_id) */
@@ -174,18 +192,25 @@ static int tick_stream(abm_handle* h) {
   ABM_CK(h, dev_memset(sc + SC_EMITTED, 0, 4, h->stream));
   ABM_CK(h, dev_memset(sc + (nxt ? SC_OVF1 : SC_OVF0), 0, 4, h->stream));
   ABM_CK(h, dev_memset(sc + SC_PARENTS, 0, 4, h->stream));
-  auto launch_tick = [&](auto tk) { /* one instantiation per scheduler: by_id carries no key arithmetic */
+  auto launch_tick = [&](auto tk, int row0, int nrows, int row_step) { /* one instantiation per scheduler: by_id carries no key arithmetic */
     tk.v = make_view(h); tk.v.err = sc + SC_ERR;
     tk.in = stream_lists(h, cur); tk.out = stream_lists(h, nxt); tk.ps = stream_sink(h, nxt);
-    tk.cores_x = cores_x; tk.core_y0 = h->g.own_lo / CORE;
+    tk.cores_x = cores_x; tk.core_y0 = h->g.own_lo / CORE + row0; tk.row_step = row_step;
     tk.next_id = (uint32_t)h->next_id;
     tk.birth_bits = (const uint32_t*)h->s_bits[cur].p; tk.birth_prefix = (const uint32_t*)h->bits_prefix.p;
     tk.emitted = sc + SC_EMITTED;
     tk.births_total = h->cfg.reproduce ? (const uint32_t*)h->bits_prefix.p + (h->s_words[cur] - 1) : sc + SC_ZERO;
-    ProfScope ps(h->prof, h->stream, "stream_tick", n);
-    launch_cta_lb<S_THREADS, S_MIN_CTAS>(h->stream, tk, (uint64_t)cores_x * (uint64_t)core_rows, tk.smem_bytes());
+    ProfScope ps(h->prof, h->stream, "stream_tick", row0 == 0 ? n : 0, row0 == 0 ? 1 : 0);
+    launch_cta_lb<S_THREADS, S_MIN_CTAS>(h->stream, tk, (uint64_t)cores_x * (uint64_t)nrows, tk.smem_bytes());
   };
-  if (h->cfg.scheduler == ABM_SCHED_RANDOMLY) launch_tick(StreamTickCta<true>()); else launch_tick(StreamTickCta<false>());
+  auto launch_rows = [&](int row0, int nrows, int row_step) {
+    if (h->cfg.scheduler == ABM_SCHED_RANDOMLY) launch_tick(StreamTickCta<true>(), row0, nrows, row_step); else launch_tick(StreamTickCta<false>(), row0, nrows, row_step);
+  };
+  if (lists_beside) { /* interior rows, then (arrivals in place) the first and the last core row in one launch */
+    launch_rows(1, core_rows - 2, 1);
+    stream_wait_event(h->stream, h->ev_halo);
+    launch_rows(0, 2, core_rows - 1);
+  } else launch_rows(0, core_rows, 1);
   if ((rc = check_launch(h, "stream tick"))) return rc;
   /* the tick's figures: records filed, overflow, births (= total of the parents bitmap) */
   ABM_CK(h, copy_d2h_async(h->h_counters, sc, SC_WORDS * sizeof(uint32_t), h->stream));

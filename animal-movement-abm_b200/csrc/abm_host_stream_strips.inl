@@ -1,6 +1,7 @@
 /*
  * abm_host_stream_strips.inl — row strips on the stream path: at the start of a tick the lists of the two ghost tile rows
- * travel to the neighbouring strips and every strip's parents are all-gathered (the tick's only rendezvous).
+ * travel to the neighbouring strips and every strip's parents are all-gathered.  Over peer memory the two exchanges run
+ * side by side: the lists on the side stream, hidden behind the tick kernel of the interior core rows (tick_stream).
  * Part of abm_engine.cu (included by abm_host_stream.inl); not a stand-alone header.
  */
 
@@ -23,11 +24,11 @@ struct StreamParentCountBody { /* [count][ids ...]: the count in front of the li
   ABM_HD void operator()(uint64_t) const { const uint32_t c = *count; if (c > cap) atomic_or(err, ERR_LIST_CAP); msg[0] = c < cap ? c : cap; }
 };
 
-static int stream_exchange(abm_handle* h) {
+/* the arrivals from the neighbouring strips: my two ghost-row lists travel, theirs join the lists of my boundary core rows */
+static int stream_exchange_lists(abm_handle* h) {
   int rc;
   const int cur = h->s_cur, P = h->n_ranks, tiles_x = h->g.tiles_x;
   uint32_t* sc = (uint32_t*)h->s_ctr.p;
-  uint32_t* ctr = (uint32_t*)h->counters.p;
   h->s_msg_cap = stream_msg_cap(h);
   const uint64_t bytes = stream_msg_bytes(tiles_x, h->s_msg_cap);
   StreamPackCta pk;
@@ -60,55 +61,48 @@ static int stream_exchange(abm_handle* h) {
     if (h->has_prev) { pk.msg[0] = (uint8_t*)h->s_tx[0].p; up.msg[0] = (const uint8_t*)h->s_rx[0].p; }
     if (h->has_next) { pk.msg[1] = (uint8_t*)h->s_tx[1].p; up.msg[1] = (const uint8_t*)h->s_rx[1].p; }
   }
-  /* Both messages are SENT before either is awaited (lists to the two neighbours, parents to everybody): the rank then
-   * waits once, for its slowest peer, instead of once per message. */
-  const bool parents = P > 1 && h->cfg.reproduce;
-  const uint64_t cap = h->s_parent_used, words = 1 + cap;
-  uint32_t* msg = (uint32_t*)h->s_parents.p;
-  uint32_t* all = nullptr;
-  bool gathered = false;
-#ifndef ABM_EMU
-  P2PBirthRecvCta rv;
-#endif
   { ProfScope ps(h->prof, h->stream, "list_exchange", 2 * h->s_msg_cap);
     launch_cta(h->stream, pk, 2, TILE_THREADS, StreamPackCta::smem_bytes());
-    if (parents) { /* every strip's parents of this tick -> bitmap over the id space (the kernels appended the own ones to s_parents) */
-      if ((rc = ensure(h, h->s_gather, words * 4 * (size_t)(P + 1) + 64))) return rc;
-      all = (uint32_t*)h->s_gather.p;
-      StreamParentCountBody pc;
-      pc.count = sc + SC_PARENTS; pc.cap = (uint32_t)cap; pc.msg = msg; pc.err = sc + SC_ERR;
-      launch_foreach(h->stream, pc, 1);
-#ifndef ABM_EMU
-      if (h->p2p_on) {
-        if ((1 + cap) * 4 > h->p2p_lay.births_bytes) ABM_FAIL(h, ABM_E_CAPACITY, "parents message (%llu ids) exceeds the mailbox allocated at abm_p2p_export", (unsigned long long)cap);
-        const uint32_t seq = ++h->p2p_seq[P2P_CH_BIRTHS];
-        const int parity = (int)(seq & 1u);
-        P2PBirthSendCta sd;
-        sd.birth_parent = msg + 1; sd.birth_count = msg; sd.cap = (uint32_t)cap; sd.seq = seq; sd.done = ctr + CTR_BIRTH_DONE;
-        for (int r = 0; r < P; ++r) {
-          sd.dst[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.births_off(h->my_rank, parity));
-          sd.flag[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.flag_off(P2P_CH_BIRTHS, h->my_rank, parity));
-        }
-        launch_cta(h->stream, sd, (uint64_t)P * BIRTH_CTAS, 256, 16);
-        rv.seq = seq; rv.cap = (uint32_t)cap; rv.all = all; rv.err = sc + SC_ERR;
-        for (int r = 0; r < P; ++r) {
-          rv.src[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.births_off(r, parity));
-          rv.flag[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.flag_off(P2P_CH_BIRTHS, r, parity));
-        }
-      }
-#endif
-    }
     if (!direct && (rc = comm_sendrecv(h, h->s_tx[0].p, bytes, h->s_tx[1].p, bytes, h->s_rx[0].p, bytes, h->s_rx[1].p, bytes))) return rc;
     launch_cta(h->stream, up, 2, TILE_THREADS, StreamUnpackCta::smem_bytes());
     StreamClearGhostBody cg;
     cg.cnt = (uint32_t*)h->s_cnt[cur].p; cg.tiles_x = tiles_x; cg.ghost_row[0] = pk.ghost_row[0]; cg.ghost_row[1] = pk.ghost_row[1];
     launch_foreach(h->stream, cg, 2 * (uint64_t)tiles_x); }
-  if ((rc = check_launch(h, "stream list exchange"))) return rc;
-  if (!parents) return 0;
+  return check_launch(h, "stream list exchange");
+}
 
+/* every strip's parents of this tick -> bitmap over the key space (the kernels appended the own ones to s_parents) */
+static int stream_exchange_parents(abm_handle* h) {
+  int rc;
+  const int cur = h->s_cur, P = h->n_ranks;
+  if (P <= 1 || !h->cfg.reproduce) return 0;
+  uint32_t* sc = (uint32_t*)h->s_ctr.p;
+  uint32_t* ctr = (uint32_t*)h->counters.p;
+  const uint64_t cap = h->s_parent_used, words = 1 + cap;
+  if ((rc = ensure(h, h->s_gather, words * 4 * (size_t)(P + 1) + 64))) return rc;
+  uint32_t* msg = (uint32_t*)h->s_parents.p;
+  uint32_t* all = (uint32_t*)h->s_gather.p;
   ProfScope ps(h->prof, h->stream, "parents_exchange", cap);
+  StreamParentCountBody pc;
+  pc.count = sc + SC_PARENTS; pc.cap = (uint32_t)cap; pc.msg = msg; pc.err = sc + SC_ERR;
+  launch_foreach(h->stream, pc, 1);
+  bool gathered = false;
 #ifndef ABM_EMU
   if (h->p2p_on) {
+    if ((1 + cap) * 4 > h->p2p_lay.births_bytes) ABM_FAIL(h, ABM_E_CAPACITY, "parents message (%llu ids) exceeds the mailbox allocated at abm_p2p_export", (unsigned long long)cap);
+    const uint32_t seq = ++h->p2p_seq[P2P_CH_BIRTHS];
+    const int parity = (int)(seq & 1u);
+    P2PBirthSendCta sd;
+    sd.birth_parent = msg + 1; sd.birth_count = msg; sd.cap = (uint32_t)cap; sd.seq = seq; sd.done = ctr + CTR_BIRTH_DONE;
+    P2PBirthRecvCta rv;
+    rv.seq = seq; rv.cap = (uint32_t)cap; rv.all = all; rv.err = sc + SC_ERR;
+    for (int r = 0; r < P; ++r) {
+      sd.dst[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.births_off(h->my_rank, parity));
+      sd.flag[r] = (uint32_t*)(h->p2p_peer[r] + h->p2p_lay.flag_off(P2P_CH_BIRTHS, h->my_rank, parity));
+      rv.src[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.births_off(r, parity));
+      rv.flag[r] = (const uint32_t*)(h->p2p_mine + h->p2p_lay.flag_off(P2P_CH_BIRTHS, r, parity));
+    }
+    launch_cta(h->stream, sd, (uint64_t)P * BIRTH_CTAS, 256, 16);
     launch_cta(h->stream, rv, (uint64_t)P * BIRTH_CTAS, 256, 16);
     gathered = true;
   } else if (h->nccl_comm) {

@@ -149,7 +149,7 @@ struct StreamTickCta {
   View v;                /* v.p.tick = the tick being completed */
   StreamLists in, out;
   ParentSink ps;         /* parents of tick + 1 */
-  int32_t cores_x, core_y0;
+  int32_t cores_x, core_y0, row_step; /* CTA row q works on core row core_y0 + q * row_step */
   uint32_t next_id;      /* nextid(model) when the tick began */
   const uint32_t* birth_bits; const uint32_t* birth_prefix; /* parents of this tick, every strip's, + popcount prefix */
   uint32_t* emitted;     /* records filed for tick + 1 */
@@ -174,7 +174,7 @@ struct StreamTickCta {
 
   ABM_HD void operator()(uint32_t cta, uint32_t* smem) const {
     const int NT = S_THREADS;
-    const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) + core_y0;
+    const int cx = (int)(cta % (uint32_t)cores_x), cy = (int)(cta / (uint32_t)cores_x) * row_step + core_y0;
     const uint32_t tile = (uint32_t)(cy * v.g.tiles_x + cx);
     uint32_t* min_all = smem;                        /* lowest id arriving on each cell: the one that eats */
     uint8_t* grass = (uint8_t*)(smem + CORE * CORE); /* the core's grass tile */

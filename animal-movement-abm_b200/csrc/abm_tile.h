@@ -892,6 +892,31 @@ struct StripHeaderCta {
     }
   }
 };
+/* The proposals of the two boundary sub-tile rows ahead of everybody else's (grid = 2 * chunks, one warp per sub-tile): the
+ * halo message carries them, so the exchange can start while propose works through the rest of the strip.  propose is a
+ * pure function of (tick, id, cell, energy): the full pass writes the same bytes again. */
+struct ProposeRowsCta {
+  View v; SubIndex si; int32_t row[2], chunks;
+  ABM_HD void operator()(uint32_t cta, uint32_t*) const {
+    const int NT = TILE_THREADS;
+    const int d = (int)(cta / (uint32_t)chunks), chunk = (int)(cta % (uint32_t)chunks);
+    ABM_CTA_FOR(t, NT) {
+      const int i = chunk * (NT / 32) + (t >> 5);
+      if (i < si.nsx) {
+        const uint32_t sub = (uint32_t)row[d] * (uint32_t)si.nsx + (uint32_t)i, off = si.off[sub], cnt = si.cnt[sub];
+        for (uint32_t k = (uint32_t)(t & 31); k < cnt; k += 32) {
+          const uint32_t a = off + k;
+          int x, y;
+          dec(v.g, v.cell[a], x, y);
+          bool nowalk;
+          const uint8_t st = propose_state(v, x, y, v.id[a], v.energy[a], nowalk);
+          if (nowalk) atomic_or(v.err, ERR_NOWALKABLE);
+          v.state[a] = st;
+        }
+      }
+    }
+  }
+};
 struct StripPackCta { /* grid = 2 * chunks, chunk = 8 sub-tiles (one per warp) */
   SubIndex si; int32_t row[2], tiles_x, chunks; uint32_t cap;
   const uint32_t* cell; const uint32_t* id; const double* energy; const uint8_t* state;
