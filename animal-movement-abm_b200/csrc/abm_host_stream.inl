@@ -47,20 +47,23 @@ static int stream_error_to_code(abm_handle* h) {
   ABM_FAIL(h, ABM_E_INTERNAL, "device-side error flags 0x%x on the stream path", e);
 }
 
-/* popcount prefix of a parents bitmap over `words` words (the last one is a spare zero word: its prefix is the total) */
+/* popcount prefix of a parents bitmap per block of 8 words; `words` is a multiple of 8 and the last block is a spare of
+ * zeros, so its prefix is the total */
 static int stream_prefix(abm_handle* h, const uint32_t* bits, uint64_t words) {
   int rc;
-  if ((rc = ensure(h, h->bits_prefix, (words + 4) * 4))) return rc;
-  if ((rc = ensure(h, h->scan_tmp, scan_tmp_words(std::max<uint64_t>(words, (uint64_t)h->g.gt + 1)) * 4))) return rc;
+  const uint64_t blocks = words / 8;
+  if ((rc = ensure(h, h->bits_prefix, (blocks + 4) * 4))) return rc;
+  if ((rc = ensure(h, h->scan_tmp, scan_tmp_words(std::max<uint64_t>(blocks, (uint64_t)h->g.gt + 1)) * 4))) return rc;
   ProfScope ps(h->prof, h->stream, "birth_prefix", words, 2);
-  PopcountBody pb;
+  PopcountBlockBody pb;
   pb.bits = bits; pb.out = (uint32_t*)h->bits_prefix.p;
-  launch_foreach(h->stream, pb, words);
-  ABM_CK(h, scan_exclusive_u32(h->stream, (uint32_t*)h->bits_prefix.p, words, (uint32_t*)h->scan_tmp.p));
+  launch_foreach(h->stream, pb, blocks);
+  ABM_CK(h, scan_exclusive_u32(h->stream, (uint32_t*)h->bits_prefix.p, blocks, (uint32_t*)h->scan_tmp.p));
   return 0;
 }
 
-static uint64_t stream_bitmap_words(uint64_t id_bound) { return bitmap_words(id_bound) + 1; }
+/* words of a parents bitmap whose keys are below key_bound: whole 8-word blocks plus the spare block */
+static uint64_t stream_bitmap_words(uint64_t key_bound) { return ((bitmap_words(key_bound) + 7) & ~(uint64_t)7) + 8; }
 static int stream_agree_parent_cap(abm_handle* h, bool first);
 
 /* canonical SoA -> arrival lists of tick h->tick */
@@ -184,8 +187,9 @@ static int tick_stream(abm_handle* h) {
   }
   if (h->cfg.reproduce && (rc = stream_prefix(h, (const uint32_t*)h->s_bits[cur].p, h->s_words[cur]))) return rc;
   /* the lists and the parents bitmap of the next tick start empty */
-  /* parents of tick + 1 have ids below next_id + births(tick), and births <= agents alive (all strips': < next_id) */
-  h->s_words[nxt] = stream_bitmap_words(key_space(h, h->next_id + ((h->strip && h->n_ranks > 1) ? h->next_id : n) + 1));
+  /* parents of tick + 1 have ids below next_id + births(tick); births = this tick's parents: at most the agents alive on a
+   * single handle, at most what the ranks' parents messages can carry on strips (a fuller message is an error) */
+  h->s_words[nxt] = stream_bitmap_words(key_space(h, h->next_id + ((h->strip && h->n_ranks > 1) ? (uint64_t)h->n_ranks * h->s_parent_used : n) + 1));
   if ((rc = ensure(h, h->s_bits[nxt], h->s_words[nxt] * 4))) return rc;
   if (h->cfg.reproduce) ABM_CK(h, dev_memset(h->s_bits[nxt].p, 0, h->s_words[nxt] * 4, h->stream));
   ABM_CK(h, dev_memset(h->s_cnt[nxt].p, 0, tiles * 4, h->stream));
@@ -199,7 +203,7 @@ static int tick_stream(abm_handle* h) {
     tk.next_id = (uint32_t)h->next_id;
     tk.birth_bits = (const uint32_t*)h->s_bits[cur].p; tk.birth_prefix = (const uint32_t*)h->bits_prefix.p;
     tk.emitted = sc + SC_EMITTED;
-    tk.births_total = h->cfg.reproduce ? (const uint32_t*)h->bits_prefix.p + (h->s_words[cur] - 1) : sc + SC_ZERO;
+    tk.births_total = h->cfg.reproduce ? (const uint32_t*)h->bits_prefix.p + (h->s_words[cur] / 8 - 1) : sc + SC_ZERO;
     ProfScope ps(h->prof, h->stream, "stream_tick", row0 == 0 ? n : 0, row0 == 0 ? 1 : 0);
     launch_cta_lb<S_THREADS, S_MIN_CTAS>(h->stream, tk, (uint64_t)cores_x * (uint64_t)nrows, tk.smem_bytes());
   };
@@ -215,7 +219,7 @@ static int tick_stream(abm_handle* h) {
   /* the tick's figures: records filed, overflow, births (= total of the parents bitmap) */
   ABM_CK(h, copy_d2h_async(h->h_counters, sc, SC_WORDS * sizeof(uint32_t), h->stream));
   h->h_counters[SC_HOST_BIRTHS] = 0;
-  if (h->cfg.reproduce) ABM_CK(h, copy_d2h_async(h->h_counters + SC_HOST_BIRTHS, (const uint32_t*)h->bits_prefix.p + (h->s_words[cur] - 1), 4, h->stream));
+  if (h->cfg.reproduce) ABM_CK(h, copy_d2h_async(h->h_counters + SC_HOST_BIRTHS, (const uint32_t*)h->bits_prefix.p + (h->s_words[cur] / 8 - 1), 4, h->stream));
   ABM_CK(h, stream_sync(h->stream));
   if ((rc = stream_error_to_code(h))) return rc;
   const uint64_t births = h->h_counters[SC_HOST_BIRTHS];

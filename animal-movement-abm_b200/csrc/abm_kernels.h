@@ -617,6 +617,30 @@ struct PopcountBody { /* per-word popcounts as the input of the rank scan */
   ABM_HD void operator()(uint64_t i) const { out[i] = (uint32_t)popc(bits[i]); }
 };
 
+/* the same per block of 8 words (two 16-byte loads): the scan that follows is 8 times shorter; a lookup adds the popcounts
+ * of the words before its own inside the block (rank_in_blocks) */
+struct PopcountBlockBody {
+  const uint32_t* bits; /* a multiple of 8 words, 32-byte aligned */
+  uint32_t* out;
+  ABM_HD void operator()(uint64_t b) const {
+    uint32_t c = 0;
+#if defined(__CUDA_ARCH__)
+    const uint4 lo = reinterpret_cast<const uint4*>(bits)[2 * b], hi = reinterpret_cast<const uint4*>(bits)[2 * b + 1];
+    c = (uint32_t)(__popc(lo.x) + __popc(lo.y) + __popc(lo.z) + __popc(lo.w) + __popc(hi.x) + __popc(hi.y) + __popc(hi.z) + __popc(hi.w));
+#else
+    for (int j = 0; j < 8; ++j) c += (uint32_t)popc(bits[8 * b + j]);
+#endif
+    out[b] = c;
+  }
+};
+/* number of set bits below bit `key`, from the exclusive prefix over 8-word blocks */
+ABM_HD uint32_t rank_in_blocks(const uint32_t* bits, const uint32_t* prefix8, uint32_t key) {
+  const uint32_t wd = key >> 5, blk = wd >> 3;
+  uint32_t r = prefix8[blk] + (uint32_t)popc(bits[wd] & ((1u << (key & 31)) - 1u));
+  for (uint32_t w = blk << 3; w < wd; ++w) r += (uint32_t)popc(bits[w]);
+  return r;
+}
+
 /* ------------------------------------------------------------------------------------------------- regrow */
 
 /* custom_model_step! on four cells at once (one grass byte each: bit 7 = fully_grown, bits 0..6 = countdown, 0x7F =

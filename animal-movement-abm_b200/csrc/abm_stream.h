@@ -151,7 +151,7 @@ struct StreamTickCta {
   ParentSink ps;         /* parents of tick + 1 */
   int32_t cores_x, core_y0, row_step; /* CTA row q works on core row core_y0 + q * row_step */
   uint32_t next_id;      /* nextid(model) when the tick began */
-  const uint32_t* birth_bits; const uint32_t* birth_prefix; /* parents of this tick, every strip's, + popcount prefix */
+  const uint32_t* birth_bits; const uint32_t* birth_prefix; /* parents of this tick, every strip's, + popcount prefix per 8-word block */
   uint32_t* emitted;     /* records filed for tick + 1 */
   const uint32_t* births_total; /* Schedulers.randomly: offspring of this tick (device side), for the key width of tick + 1 */
 
@@ -165,8 +165,7 @@ struct StreamTickCta {
     const uint32_t lc = r.w0 & SR_LC;
     uint32_t child = 0;
     if (valid) {
-      const uint32_t pk = key_of(r.id), wd = pk >> 5;
-      child = next_id + birth_prefix[wd] + (uint32_t)popc(birth_bits[wd] & ((1u << (pk & 31)) - 1u));
+      child = next_id + rank_in_blocks(birth_bits, birth_prefix, key_of(r.id));
     }
     stream_emit<SCHED>(vn, out, psn, x0 + (int)(lc & 31), y0 + (int)(lc >> 5), child, rec_energy(r), valid);
     return valid ? 1u : 0u;
