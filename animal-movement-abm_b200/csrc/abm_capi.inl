@@ -594,6 +594,7 @@ int ABM_API(step)(abm_handle* h, int64_t n_ticks) {
   if (!h) return ABM_E_BADARG;
   if (n_ticks < 0) ABM_FAIL(h, ABM_E_BADARG, "n_ticks must be >= 0");
   if (!h->grid_set || !h->agents_set) ABM_FAIL(h, ABM_E_STATE, "abm_set_grid and abm_set_agents must precede abm_step");
+  if (h->poisoned) ABM_FAIL(h, ABM_E_STATE, "this handle lost a peer exchange (time-out) and cannot be stepped any more");
   int rc = set_device(h);
   if (rc) return rc;
   const uint64_t l0 = launches_now();
@@ -932,12 +933,26 @@ int ABM_API(p2p_export)(abm_handle* h, void* handle64) {
 #endif
 }
 
+#ifndef ABM_EMU
+/* ABM_P2P_TIMEOUT_S (1..3600, default 30): how long a kernel waits for a neighbour's flag before it gives up (per device) */
+static int p2p_apply_timeout(abm_handle* h) {
+  long secs = 30;
+  if (const char* e = getenv("ABM_P2P_TIMEOUT_S")) { const long q = atol(e); if (q >= 1 && q <= 3600) secs = q; }
+  int khz = 0;
+  if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device) != cudaSuccess || khz <= 0) khz = 2000000;
+  const long long cycles = (long long)secs * (long long)khz * 1000ll;
+  ABM_CK(h, cudaMemcpyToSymbol(abm::abm_flag_timeout_cycles, &cycles, sizeof cycles));
+  return 0;
+}
+#endif
+
 int ABM_API(p2p_connect)(abm_handle* h, const void* handles, int32_t n) {
   if (!h || !handles) return ABM_E_BADARG;
 #ifndef ABM_EMU
   if (!h->p2p_mine || n != h->n_ranks) ABM_FAIL(h, ABM_E_STATE, "abm_p2p_connect needs abm_p2p_export first and one handle per rank");
   int rc = set_device(h);
   if (rc) return rc;
+  if ((rc = p2p_apply_timeout(h))) return rc;
   for (int r = 0; r < n; ++r) {
     if (r == h->my_rank) { h->p2p_peer[r] = h->p2p_mine; continue; }
     cudaIpcMemHandle_t mh;

@@ -274,7 +274,7 @@ struct abm_handle {
   DevBuf rank, by_rank, seg_behav, plan_agent, plan_goal, remote_head, remote_next, remote_dest, idx_of_id;
   DevBuf as_g, as_meta, as_heap, as_src, as_dst, as_id, as_status, as_len, as_cost, as_off, as_slot_gen, as_todo, as_comp;
   bool comp_valid = false;        /* as_comp holds the walkmap's component labels */
-  uint64_t astar_budget = 64ull << 30; /* ABM_ASTAR_GB: device bytes the search slots may take (and at most half of what is free) */
+  uint64_t astar_budget = 128ull << 30; /* ABM_ASTAR_GB: device bytes the search slots may take (and at most three quarters of what is free) */
   DevBuf rt_slot_of_id, rt_off, rt_len, rt_pos, rt_cost, rt_pool;
   uint64_t as_slots = 0, as_heap_cap = 0, rt_slots_cap = 0, rt_pool_used = 0, rt_ids_cap = 0;
   /* tile path (abm_tile.h): sub-tile runs of the SoA (ping-pong with the SoA), offspring fix-up lists */
@@ -292,6 +292,7 @@ struct abm_handle {
   DevBuf okey;                    /* Schedulers.randomly: order key per agent (own + ghost), recomputed every tick */
   /* offspring ids off the critical path: the reproducing agents are known after propose, so their order keys are gathered
    * and ranked on a second stream while the tick resolves and commits (ABM_EARLY_BIRTHS=0: after the commit, as before) */
+  bool poisoned = false;          /* a peer exchange timed out: the state is garbage, every later call fails */
   bool early_births = true;
   abm_stream_t side = 0;
   abm_event_t ev_proposed = 0, ev_ranked = 0, ev_rows = 0, ev_halo = 0;
@@ -455,7 +456,7 @@ static int read_counters(abm_handle* h) {
 static int device_error_to_code(abm_handle* h) {
   const uint32_t e = h->h_counters[CTR_ERR];
   if (e & ERR_NOWALKABLE) ABM_FAIL(h, ABM_E_NOWALKABLE, "random_walkmap: an agent has no walkable neighbour (the reference throws on rand(1:0))");
-  if (e & ERR_P2P_TIMEOUT) ABM_FAIL(h, ABM_E_CUDA, "peer exchange timed out: a neighbouring strip did not deliver its message");
+  if (e & ERR_P2P_TIMEOUT) { h->poisoned = true; ABM_FAIL(h, ABM_E_CUDA, "peer exchange timed out: a neighbouring strip did not deliver its message (the kernels went on without it: this handle is unusable now)"); }
   if (e & ERR_STRIP_CAP) ABM_FAIL(h, ABM_E_CAPACITY, "a boundary row outgrew the agreed halo message capacity (%llu agents) within one tick", (unsigned long long)h->bcap);
   if (e & ERR_INTERNAL) ABM_FAIL(h, ABM_E_BADARG, "device-side validation failed (out-of-range coordinate, id, countdown or elevation, or duplicate id)");
   return 0;

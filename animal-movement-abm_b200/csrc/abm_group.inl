@@ -178,6 +178,7 @@ static int group_connect(abm_group* g) {
   }
   for (int i = 0; i < g->n; ++i) {
     cudaSetDevice(g->h[i]->device);
+    if (int rc = p2p_apply_timeout(g->h[i])) { g->err = g->h[i]->err; return rc; }
     for (int j = 0; j < g->n; ++j) {
       if (i != j && g->h[i]->device != g->h[j]->device) {
         cudaError_t e = cudaDeviceEnablePeerAccess(g->h[j]->device, 0);

@@ -43,7 +43,7 @@ static int plan_batch(abm_handle* h, uint64_t B, const uint32_t* d_id, const uin
   uint64_t max_resident = 148ull * 32; /* one warp-sized CTA per slot, at most 32 CTAs per SM */
   if (const char* ms = getenv("ABM_ASTAR_SLOTS")) max_resident = (uint64_t)std::max(atoll(ms), 1ll);
   if (h->as_slots == 0 || h->as_heap_cap != heap_cap || h->as_slots < std::min<uint64_t>(B, max_resident)) {
-    const uint64_t budget = std::min<uint64_t>(device_free_bytes() / 2, h->astar_budget);
+    const uint64_t budget = std::min<uint64_t>(device_free_bytes() / 4 * 3, h->astar_budget); /* searches are latency-bound: slots in flight are throughput */
     uint64_t slots = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(B, max_resident), budget / per_slot));
     if (slots > h->as_slots || h->as_heap_cap != heap_cap) {
       if ((rc = ensure(h, h->as_g, slots * gt * 4))) return rc;

@@ -41,7 +41,7 @@ static int stream_error_to_code(abm_handle* h) {
   if (!e) return 0;
   dev_memset((uint32_t*)h->s_ctr.p + SC_ERR, 0, 4, h->stream);
   if (e & ERR_NOWALKABLE) ABM_FAIL(h, ABM_E_NOWALKABLE, "random_walkmap: an agent has no walkable neighbour (the reference throws on rand(1:0))");
-  if (e & ERR_P2P_TIMEOUT) ABM_FAIL(h, ABM_E_CUDA, "peer exchange timed out: a neighbouring strip did not deliver its message");
+  if (e & ERR_P2P_TIMEOUT) { h->poisoned = true; ABM_FAIL(h, ABM_E_CUDA, "peer exchange timed out: a neighbouring strip did not deliver its message (the kernels went on without it: this handle is unusable now)"); }
   if (e & ERR_STRIP_CAP) ABM_FAIL(h, ABM_E_CAPACITY, "a ghost-row list outgrew the agreed message capacity (%llu records) within one tick", (unsigned long long)h->s_msg_cap);
   if (e & ERR_LIST_CAP) ABM_FAIL(h, ABM_E_CAPACITY, "arrival lists and their overflow list are full (%u slots per core, %llu overflow slots)", h->s_cap, (unsigned long long)h->s_ovf_cap);
   ABM_FAIL(h, ABM_E_INTERNAL, "device-side error flags 0x%x on the stream path", e);

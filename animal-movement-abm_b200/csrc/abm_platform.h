@@ -247,12 +247,14 @@ ABM_D void flag_publish(uint32_t* flag, uint32_t seq) {
   *(volatile uint32_t*)flag = seq;
 }
 ABM_D void flag_fence() { __threadfence_system(); }
-/* spin until the flag reaches seq; a lost neighbour becomes an error bit after ~4 s, not a hang */
+/* spin until the flag reaches seq; a lost neighbour becomes an error bit after abm_flag_timeout_cycles (~30 s by default,
+ * ABM_P2P_TIMEOUT_S at abm_p2p_connect / abm_group_create; the handle is then unusable), not a hang */
+__device__ long long abm_flag_timeout_cycles = 60000000000ll;
 ABM_D void flag_wait(const uint32_t* flag, uint32_t seq, uint32_t* err, uint32_t err_bit) {
   if (!flag) return;
-  const long long t0 = clock64();
+  const long long t0 = clock64(), limit = abm_flag_timeout_cycles;
   while ((int32_t)(*(const volatile uint32_t*)flag - seq) < 0) {
-    if (clock64() - t0 > 8000000000ll) { atomicOr(err, err_bit); break; }
+    if (clock64() - t0 > limit) { atomicOr(err, err_bit); break; }
     __nanosleep(32);
   }
   __threadfence_system();
