@@ -122,6 +122,10 @@ struct Model {
   std::vector<double> lut;                /* optional host-supplied exp(-sqrt(k)/3) table */
   AgentRng rng;
   bool grid_set = false;
+  /* alternative readings of the third-party semantics that SURVEY.md Appendix A could not settle without running Julia
+   * (confidence M / L): bit mask set through oracle_set_variants (tests, tools/compare_reference_dump.py --variants); 0 = the
+   * reading the engine implements */
+  uint32_t variants = 0;
   u64 astar_expansions = 0;
   std::string err;
 
@@ -139,6 +143,10 @@ static inline int mod1(int a, int n) { /* Julia mod1 */
 /* offsets_at_radius(model, 1) == offsets_within_radius_no_0(model, 1): Iterators.product(-1:1, -1:1), x fastest,
  * (0,0) removed. */
 static const int OFF8[8][2] = {{-1, -1}, {0, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {0, 1}, {1, 1}};
+/* the other reading of A-5 / A-8 (order marked M): the second coordinate fastest */
+static const int OFF8_YFAST[8][2] = {{-1, -1}, {-1, 0}, {-1, 1}, {0, -1}, {0, 1}, {1, -1}, {1, 0}, {1, 1}};
+enum { VAR_OFFSETS_Y_FASTEST = 1, VAR_RANDOM_POSITION_Y_FIRST = 2, VAR_ASTAR_NEIGHBOURS_Y_FASTEST = 4, VAR_ALL = 7 };
+static const int (*offsets8(const Model& m))[2] { return (m.variants & VAR_OFFSETS_Y_FASTEST) ? OFF8_YFAST : OFF8; }
 
 static void remove_from_cell(Model& m, i64 id, int x, int y) {
   std::vector<i64>& v = m.stored[m.lin(x, y)];
@@ -174,14 +182,14 @@ static void walk(Model& m, Sheep& a, int dx, int dy, bool ifempty) {
 /* randomwalk!(agent, model) = walk!(agent, rand(abmrng(model), offsets_at_radius(model, 1)), model) */
 static void randomwalk(Model& m, Sheep& a) {
   const i64 k = m.rng.rand_1_to(8);
-  walk(m, a, OFF8[k - 1][0], OFF8[k - 1][1], m.cfg.randomwalk_ifempty != 0);
+  walk(m, a, offsets8(m)[k - 1][0], offsets8(m)[k - 1][1], m.cfg.randomwalk_ifempty != 0);
 }
 
 /* nearby_positions(pos, model, 1): wrapped when periodic, bounds-filtered otherwise */
 static std::vector<Pos> nearby_positions(const Model& m, int x, int y) {
   std::vector<Pos> out;
   for (int i = 0; i < 8; ++i) {
-    int px = x + OFF8[i][0], py = y + OFF8[i][1];
+    int px = x + offsets8(m)[i][0], py = y + offsets8(m)[i][1];
     if (m.periodic) {
       out.push_back(Pos(mod1(px, m.nx), mod1(py, m.ny)));
     } else if (px >= 1 && px <= m.nx && py >= 1 && py <= m.ny) {
@@ -242,7 +250,8 @@ static bool find_path(Model& m, Pos from, Pos to, std::deque<Pos>& path, i64* co
     closed.insert(lc);
     ++m.astar_expansions;
     for (int i = 0; i < 8; ++i) { /* moore_neighborhood, product order */
-      int px = cur.first + OFF8[i][0], py = cur.second + OFF8[i][1];
+      const int (*nb8)[2] = (m.variants & VAR_ASTAR_NEIGHBOURS_Y_FASTEST) ? OFF8_YFAST : OFF8;
+      int px = cur.first + nb8[i][0], py = cur.second + nb8[i][1];
       if (m.periodic) {
         px = mod1(px, m.nx);
         py = mod1(py, m.ny);
@@ -292,8 +301,9 @@ static void plan_route(Model& m, const Sheep& a, Pos dest) {
 /* random_walkable(model, pathfinder): rejection-sample random_position(model) = (rand(1:nx), rand(1:ny)) */
 static Pos random_walkable(Model& m) {
   while (true) {
-    const int x = (int)m.rng.rand_1_to((u64)m.nx);
-    const int y = (int)m.rng.rand_1_to((u64)m.ny);
+    int x, y;
+    if (m.variants & VAR_RANDOM_POSITION_Y_FIRST) { y = (int)m.rng.rand_1_to((u64)m.ny); x = (int)m.rng.rand_1_to((u64)m.nx); }
+    else { x = (int)m.rng.rand_1_to((u64)m.nx); y = (int)m.rng.rand_1_to((u64)m.ny); }
     if (m.walkmap[m.lin(x, y)]) return Pos(x, y);
   }
 }
@@ -336,8 +346,11 @@ static int random_walk_gregarious(Model& m, Sheep& a) {
   bool have = false;
   i64 best = 0;
   Pos closest(0, 0);
-  for (int by = -r; by <= r; ++by)
-    for (int bx = -r; bx <= r; ++bx) {
+  const int side = 2 * r + 1;
+  for (int q = 0; q < side * side; ++q) {
+    {
+      /* offsets_within_radius order: first coordinate fastest (or, VAR_OFFSETS_Y_FASTEST, the second) */
+      const int bx = (m.variants & VAR_OFFSETS_Y_FASTEST) ? q / side - r : q % side - r, by = (m.variants & VAR_OFFSETS_Y_FASTEST) ? q % side - r : q / side - r;
       int px = a.x + bx, py = a.y + by;
       if (m.periodic) {
         px = mod1(px, m.nx);
@@ -357,6 +370,7 @@ static int random_walk_gregarious(Model& m, Sheep& a) {
         }
       }
     }
+  }
   if (have) {
     const size_t n = possible.size();
     std::vector<double> w(n), p(n);
@@ -675,6 +689,13 @@ int oracle_set_weight_lut(oracle_handle* h, const double* w, int32_t n) {
   return 0;
 }
 int oracle_step(oracle_handle* h, int64_t n) { return step(h->m, n); }
+
+/* test infrastructure only (no abm_ counterpart): selects alternative readings of Appendix-A items, see Model::variants */
+int oracle_set_variants(oracle_handle* h, uint32_t mask) {
+  if (!h || (mask & ~(uint32_t)VAR_ALL)) return ABM_E_BADARG;
+  h->m.variants = mask;
+  return ABM_OK;
+}
 int oracle_count_agents(oracle_handle* h, int64_t* n) { *n = (i64)h->m.agents.size(); return 0; }
 
 int oracle_get_agents(oracle_handle* h, int64_t* n_inout, int64_t* id, int64_t* x, int64_t* y, double* e) {

@@ -424,3 +424,69 @@ def test_astar_tie_break_prefers_lower_x_then_y(oracle):
     e.plan_routes(np.array([1]), np.array([3]), np.array([1]))
     off, px, py, cost = e.get_paths(np.array([1]))
     assert list(zip(px, py)) == [(2, 1), (3, 1)] and cost[0] == 2
+
+
+# ---- Appendix-A items the survey could not settle without Julia (confidence M / L): each alternative reading is an oracle
+# variant (oracle_set_variants, test infrastructure only), and each changes an observable of a small case.  One run of
+# tools/dump_reference.jl + `tools/compare_reference_dump.py --variants` on a Julia box tells which reading is the reference's.
+VARIANTS = {
+    1: ("offsets_at_radius / offsets_within_radius with the second coordinate fastest (A-5)", "dense_rw"),
+    2: ("random_position draws y before x (A-8)", "dense_alternated"),
+    4: ("A* Moore neighbourhood with the second coordinate fastest (A-8): settled here — it cannot be observed", "routes"),
+}
+
+
+def _set_variants(oracle, engine, mask):
+    import ctypes as C
+    fn = oracle.dll.oracle_set_variants
+    fn.argtypes, fn.restype = [C.c_void_p, C.c_uint32], C.c_int
+    assert fn(engine.h, mask) == 0
+
+
+@pytest.mark.parametrize("mask", sorted(VARIANTS))
+def test_unsettled_appendix_a_readings_are_observable(oracle, mask):
+    """A wrong guess would not hide: under each alternative reading the golden case leaves its trajectory within 40 ticks
+    (positions for the offset orders, the planned routes / goals for the A* items)."""
+    from cases import build_case
+    name = VARIANTS[mask][1]
+    if mask == 4:  # the open list orders by the (f, x, y) tuple and the neighbours of one expansion are different cells, so the
+        # order in which they are visited can change neither an expansion nor a parent: identical routes, cell for cell
+        from conftest import make_case
+        cfgkw, w = make_case(40, 31, 60, 3, 1, terrain=True, seed=12, astar_metric=0, astar_penalty=0, counter=9)
+        ok = np.argwhere(w["walkmap"] == 1)
+        goals = ok[np.random.default_rng(12).integers(0, len(ok), 60)]
+        paths = []
+        for m in (0, mask):
+            e = load_case(oracle, cfgkw, w)
+            _set_variants(oracle, e, m)
+            e.plan_routes(w["ids"], goals[:, 1] + 1, goals[:, 0] + 1)
+            off, px, py, cost = e.get_paths(w["ids"])
+            paths.append((off, px, py, cost))
+            e.close()
+        for a, b in zip(paths[0], paths[1]):
+            assert np.array_equal(a, b), "the neighbour order changed a route"
+        return
+    cfgkw, w, state, _ = build_case(name)
+    snaps = []
+    for m in (0, mask):
+        e = load_case(oracle, cfgkw, w)
+        if state:
+            e.set_global_state(*state)
+        _set_variants(oracle, e, m)
+        e.step(40)
+        snaps.append(e.snapshot())
+        e.close()
+    a, b = snaps
+    same = a["ids"].shape == b["ids"].shape and all(np.array_equal(a[k], b[k]) for k in ("ids", "x", "y", "fully_grown"))
+    assert not same, f"variant {mask} ({VARIANTS[mask][0]}) does not change {name}: the case cannot discriminate it"
+
+
+def test_variants_are_refused_outside_the_known_set(oracle):
+    import ctypes as C
+    from cases import build_case
+    cfgkw, w, _, _ = build_case("v0.1_default")
+    e = load_case(oracle, cfgkw, w)
+    fn = oracle.dll.oracle_set_variants
+    fn.argtypes, fn.restype = [C.c_void_p, C.c_uint32], C.c_int
+    assert fn(e.h, 8) != 0
+    e.close()

@@ -2,6 +2,10 @@
 
     python tools/compare_reference_dump.py CASES_DIR            # after the Julia run
     python tools/compare_reference_dump.py CASES_DIR --selftest # write the dumps FROM the oracle first (checks the file formats only)
+    python tools/compare_reference_dump.py CASES_DIR --variants # try every alternative reading of the Appendix-A items the
+                                                                # survey left at confidence M / L (oracle_set_variants: offset order,
+                                                                # random_position draw order, randomwalk ifempty default) and print
+                                                                # which combination reproduces the Julia dumps
 
 The day this passes on a box with Julia + Agents.jl 5.14, the oracle stops being "parity unpinned".
 """
@@ -24,7 +28,7 @@ def read_config(path):
     return cfg
 
 
-def oracle_engine(d):
+def oracle_engine(d, ifempty=None):
     import abm_b200  # noqa: F401  (registers the package shim)
     from abm_b200 import build, capi
     lib = capi.CLib(build.build_oracle(), "oracle_")
@@ -32,6 +36,8 @@ def oracle_engine(d):
     ints = ("nx", "ny", "periodic", "walk_type", "eat", "reproduce", "walkmap_regrowth", "regrowth_time", "visual_distance", "counter",
             "astar_metric", "astar_penalty", "seed")
     kw = {k: (int(cfg[k]) if k in ints else cfg[k]) for k in cfg if k not in ("behav", "behav_counter", "ticks")}
+    if ifempty is not None:
+        kw["randomwalk_ifempty"] = int(ifempty)
     e = lib.create(lib.default_config(**kw))
     grid = lambda fn: np.loadtxt(os.path.join(d, fn), delimiter=",", dtype=np.int64, ndmin=2) if os.path.exists(os.path.join(d, fn)) else None
     wm = grid("walkmap.csv")
@@ -57,8 +63,13 @@ def write_dump(d, t, snap):
         f.write(f"behav={snap['behav']}\nbehav_counter={snap['behav_counter']}\n")
 
 
-def compare_case(d, selftest=False):
-    e, ticks = oracle_engine(d)
+def compare_case(d, selftest=False, variants=0, ifempty=None):
+    e, ticks = oracle_engine(d, ifempty)
+    if variants:
+        import ctypes as C
+        fn = e.lib.dll.oracle_set_variants
+        fn.argtypes, fn.restype = [C.c_void_p, C.c_uint32], C.c_int
+        assert fn(e.h, variants) == 0
     if selftest:
         w, _ = oracle_engine(d)
         for t in range(1, ticks + 1):
@@ -87,6 +98,20 @@ def compare_case(d, selftest=False):
 if __name__ == "__main__":
     base = sys.argv[1]
     selftest = "--selftest" in sys.argv
+    if "--variants" in sys.argv:
+        names = {1: "offsets second-coordinate-fastest", 2: "random_position y first"}
+        cases = [os.path.join(base, n) for n in sorted(os.listdir(base)) if os.path.exists(os.path.join(base, n, "config.txt"))]
+        winners = []
+        for ifempty in (1, 0):
+            for mask in (0, 1, 2, 3):
+                res = [compare_case(d, False, mask, ifempty) for d in cases]
+                ok = sum(not r.startswith("MISMATCH") for r in res)
+                label = ", ".join([f"ifempty={ifempty}"] + [names[b] for b in (1, 2) if mask & b]) or "the engine's reading"
+                print(f"variants={mask} {label}: {ok}/{len(cases)} cases identical")
+                if ok == len(cases):
+                    winners.append((mask, ifempty))
+        print("readings that reproduce every dump:", winners or "none — something else differs")
+        sys.exit(0 if winners else 1)
     bad = 0
     for name in sorted(os.listdir(base)):
         d = os.path.join(base, name)
