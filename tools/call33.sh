@@ -1,0 +1,2 @@
+D=animal-movement-abm_b200
+python tools/variant_probe.py --workload C2 --size 4096 --ticks 30 $D/libabm.so $D/libabm_fastsetup.so $D/libabm.so $D/libabm_fastsetup.so 2>&1 | tee gpurun_out/r2_probe_fastsetup.log
