@@ -49,8 +49,12 @@ WORKLOADS = {
                desc="v0.5 RANDOM_WALKMAP + walkmap regrowth, periodic {n}x{m} terrain, {a} sheep at tick 0 (BASELINE.json configs[4] per-GPU share: 32768x4096 rows of 32768x(4096 N))"),
     "C1": dict(walk_type=0, terrain=False, cfg=dict(reproduction_prob=0.001),
                desc="v0.1 RANDOM_WALK, {n}x{m} grid, {a} sheep at tick 0"),
+    # the v0.4 / v0.6 rules (src/agent_actions.jl:211-242): model-global behaviour counter, a third of the switches plans an A*
+    # route (PenaltyMap(elevation, MaxDistance), scripts/v0.6.jl:87-93).  General path, one GPU; the batched A* dominates the tick.
+    "V6": dict(walk_type=3, terrain=True, cfg=dict(counter=50, reproduction_prob=0.004, astar_metric=1, astar_penalty=1, walkmap_regrowth=1),
+               desc="v0.6 ALTERNATED_WALK (counter 50) + A* routes on PenaltyMap(elevation, MaxDistance), periodic {n}x{m} terrain, {a} sheep at tick 0"),
 }
-DEFAULT_SIZE = {"C2": (4096, 4096), "C3": (8192, 8192), "C5": (32768, 4096), "C1": (4096, 4096), "C4": (2048, 2048)}  # (nx, rows per GPU)
+DEFAULT_SIZE = {"C2": (4096, 4096), "C3": (8192, 8192), "C5": (32768, 4096), "C1": (4096, 4096), "C4": (2048, 2048), "V6": (1024, 1024)}  # (nx, rows per GPU)
 
 
 def make_world(workload, size, agents, seed=321, nx=None, rank=0, world=1):
@@ -88,6 +92,8 @@ def load(lib, cfg, w, device=0):
     e = lib.create(lib.default_config(device=device, **cfg))
     e.set_grid(w["fully_grown"], w["countdown"], w.get("walkmap"), w.get("elevation"))
     e.set_agents(w["ids"], w["x"], w["y"], w["energy"])
+    if cfg.get("walk_type") == 3:  # model.behav_counter[1] = counter, scripts/v0.4.jl:97
+        e.set_global_state(0, 0, cfg["counter"])
     return e
 
 

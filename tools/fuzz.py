@@ -5,7 +5,7 @@
     python tools/fuzz.py astar START COUNT    # abm_plan_routes / abm_get_paths (random terrain, goals anywhere, replans,
                                               # 1-64 search slots, route pools that overflow): engine vs oracle
 
-`FUZZ_SCHED=1` steps every case under Schedulers.randomly (default: half of them).  `FORCE_GENERAL=1` sends a third of the tile-sized engine cases down the general path; `ABM_TILE_ROUNDS=1` leaves most
+`FUZZ_LIB=abm` (GPU box) fuzzes libabm.so itself instead of the emulated build.  `FUZZ_SCHED=1` steps every case under Schedulers.randomly (default: half of them).  `FORCE_GENERAL=1` sends a third of the tile-sized engine cases down the general path; `ABM_TILE_ROUNDS=1` leaves most
 conflicts to the per-agent windows.  Every seed is reproducible: `engine_vs_oracle(seed)` / `oracle_vs_pyref(seed)` return
 "ok", "skip ...", "refused ..." (abm_create turned the configuration down), "both raised", or a line starting with DIFF /
 ERROR.  tests/test_fuzz.py runs a bounded number of seeds; 2,300 engine, 4,400 oracle and 5,600 A* seeds were clean when this
@@ -27,7 +27,12 @@ _libs = {}
 
 def _lib(which):
     if which not in _libs:
-        _libs[which] = capi.CLib(build.build_oracle(), "oracle_") if which == "oracle" else capi.CLib(build.build_emu(), "emu_")
+        if which == "oracle":
+            _libs[which] = capi.CLib(build.build_oracle(), "oracle_")
+        elif os.environ.get("FUZZ_LIB") == "abm":  # on a GPU box: the product library instead of the emulated build
+            _libs[which] = capi.CLib(build.LIBABM, "abm_")
+        else:
+            _libs[which] = capi.CLib(build.build_emu(), "emu_")
     return _libs[which]
 
 
