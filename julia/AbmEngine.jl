@@ -253,4 +253,90 @@ function heatarray(model)
     return (st .& 0x7f) ./ model.regrowth_time
 end
 
+# ---- several GPUs from this ONE Julia process (abm_group_*, include/abm.h): the GridSpace is cut into row strips, one per
+#      device, and stepped by one ccall; arrays go in and come out whole.  group_step!(model, a, m, n; devices = 0:7) ---------
+mutable struct GroupEngine
+    g::Ptr{Cvoid}
+    rules::Tuple{EngineAgentStep,EngineModelStep}
+    host_stale::Bool
+end
+const GROUPS = IdDict{Any,GroupEngine}()
+gcheck(g, rc) = rc == 0 || error("libabm group error $rc: ", unsafe_string(ccall((:abm_group_last_error, libabm), Cstring, (Ptr{Cvoid},), g)))
+
+function group_engine!(model, a::EngineAgentStep, m::EngineModelStep, devices)
+    ge = get(GROUPS, model, nothing)
+    ge !== nothing && ge.rules == (a, m) && return ge
+    ge === nothing || (group_sync_host!(model); ccall((:abm_group_destroy, libabm), Cvoid, (Ptr{Cvoid},), ge.g))
+    h1 = create_handle(model, a, m)                          # only to fill an AbmConfig the same way; the group owns its handles
+    ccall((:abm_destroy, libabm), Cvoid, (Ptr{Cvoid},), h1)
+    nx, ny = size(model.space);  s = first(allagents(model));  att = prop(model, :attractor, (nx / 2, ny / 2))
+    cfg = AbmConfig(nx = nx, ny = ny, periodic = model.space.periodic ? 1 : 0, walk_type = Int32(a.walk_type), eat = a.eat,
+                    reproduce = a.reproduce, walkmap_regrowth = m.walkmap, regrowth_time = model.regrowth_time,
+                    visual_distance = floor(Int32, s.visual_distance), counter = prop(model, :counter, 50),
+                    prob_random_walk = a.prob_random_walk, delta_energy = s.Δenergy, movement_cost = s.movement_cost,
+                    reproduction_prob = s.reproduction_prob, attractor_x = att[1], attractor_y = att[2], seed = prop(model, :seed, 321),
+                    scheduler = model.scheduler === Schedulers.randomly ? 1 : 0)
+    cfg.struct_size = sizeof(AbmConfig)
+    devs = Int32.(collect(devices));  g = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:abm_group_create, libabm), Cint, (Ref{AbmConfig}, Int32, Ptr{Int32}, Ref{Ptr{Cvoid}}), cfg, length(devs), devs, g)
+    rc == 0 || error("abm_group_create ($rc): ", last_error(C_NULL))
+    if a.walk_type == RANDOM_WALK_GREGARIOUS                 # every member takes the host's exp table
+        lut = Float64[exp(-sqrt(k) / 3) for k in 0:2(cfg.visual_distance + 1)^2]
+        for i in 0:length(devs)-1
+            hm = ccall((:abm_group_member, libabm), Ptr{Cvoid}, (Ptr{Cvoid}, Int32), g[], i)
+            check(hm, ccall((:abm_set_weight_lut, libabm), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32), hm, lut, length(lut)))
+        end
+    end
+    fg = Matrix{UInt8}(model.fully_grown);  cd = Matrix{Int64}(model.countdown)
+    wm = hasproperty(model, :land_walkmap) ? Matrix{UInt8}(model.land_walkmap) : nothing
+    el = hasproperty(model, :elevation) ? Matrix{Int64}(model.elevation) : nothing
+    GC.@preserve fg cd wm el gcheck(g[], ccall((:abm_group_set_grid, libabm), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Int64}, Ptr{UInt8}, Ptr{Int64}),
+        g[], fg, cd, wm === nothing ? C_NULL : pointer(wm), el === nothing ? C_NULL : pointer(el)))
+    ids = sort!(collect(allids(model)))
+    xs = Int64[model[i].pos[1] for i in ids];  ys = Int64[model[i].pos[2] for i in ids];  es = Float64[model[i].energy for i in ids]
+    gcheck(g[], ccall((:abm_group_set_agents, libabm), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64),
+                      g[], length(ids), Int64.(ids), xs, ys, es, nextid(model)))
+    GROUPS[model] = GroupEngine(g[], (a, m), false)
+end
+
+function group_step!(model::ABM, a::EngineAgentStep, m::EngineModelStep, n::Integer = 1; devices = 0:0)
+    ge = group_engine!(model, a, m, devices)
+    gcheck(ge.g, ccall((:abm_group_step, libabm), Cint, (Ptr{Cvoid}, Int64), ge.g, n))
+    ge.host_stale = true
+    return model
+end
+
+"the all-reduced adata / mdata scalars of a group (`what` as in REDUCE)"
+function group_reduce(model, what::Symbol)
+    out = Ref{Float64}(0);  g = GROUPS[model].g
+    gcheck(g, ccall((:abm_group_reduce, libabm), Cint, (Ptr{Cvoid}, Int32, Ref{Float64}), g, REDUCE[what], out))
+    out[]
+end
+
+function group_sync_host!(model)
+    ge = get(GROUPS, model, nothing)
+    (ge === nothing || !ge.host_stale) && return model
+    n = Ref{Int64}(0);  gcheck(ge.g, ccall((:abm_group_count_agents, libabm), Cint, (Ptr{Cvoid}, Ref{Int64}), ge.g, n))
+    ids = Vector{Int64}(undef, n[]); xs = similar(ids); ys = similar(ids); es = Vector{Float64}(undef, n[])
+    gcheck(ge.g, ccall((:abm_group_get_agents, libabm), Cint, (Ptr{Cvoid}, Ref{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}), ge.g, n, ids, xs, ys, es))
+    alive = Set(ids);  proto = first(allagents(model))
+    for id in collect(allids(model)); id in alive || kill_agent!(model[id], model); end
+    for k in eachindex(ids)
+        id, pos = ids[k], (Int(xs[k]), Int(ys[k]))
+        if haskey(model.agents, id)
+            ag = model[id];  ag.pos == pos || move_agent!(ag, pos, model);  ag.energy = es[k]
+        else
+            ag = deepcopy(proto);  ag.id = id;  ag.pos = pos;  ag.energy = es[k];  add_agent_pos!(ag, model)
+        end
+    end
+    next = Ref{Int64}(0)
+    ccall((:abm_group_get_global_state, libabm), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ref{Int64}), ge.g, C_NULL, C_NULL, C_NULL, next)
+    model.maxid[] = next[] - 1
+    fg = Matrix{UInt8}(undef, size(model.space)...);  cd = Matrix{Int64}(undef, size(model.space)...)
+    gcheck(ge.g, ccall((:abm_group_get_grid, libabm), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Int64}), ge.g, fg, cd))
+    model.fully_grown .= fg .== 1;  model.countdown .= cd
+    ge.host_stale = false
+    return model
+end
+
 end # module
