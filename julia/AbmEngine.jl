@@ -267,8 +267,6 @@ function group_engine!(model, a::EngineAgentStep, m::EngineModelStep, devices)
     ge = get(GROUPS, model, nothing)
     ge !== nothing && ge.rules == (a, m) && return ge
     ge === nothing || (group_sync_host!(model); ccall((:abm_group_destroy, libabm), Cvoid, (Ptr{Cvoid},), ge.g))
-    h1 = create_handle(model, a, m)                          # only to fill an AbmConfig the same way; the group owns its handles
-    ccall((:abm_destroy, libabm), Cvoid, (Ptr{Cvoid},), h1)
     nx, ny = size(model.space);  s = first(allagents(model));  att = prop(model, :attractor, (nx / 2, ny / 2))
     cfg = AbmConfig(nx = nx, ny = ny, periodic = model.space.periodic ? 1 : 0, walk_type = Int32(a.walk_type), eat = a.eat,
                     reproduce = a.reproduce, walkmap_regrowth = m.walkmap, regrowth_time = model.regrowth_time,
