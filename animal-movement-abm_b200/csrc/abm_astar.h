@@ -158,7 +158,176 @@ struct AStarWarpCta {
   unsigned long long* expansions;
   static size_t smem_bytes() { return sizeof(AStarShared); }
 
+#ifndef ABM_EMU
+  /* The device form of the search below: warp-synchronous, every lane carries the search's scalars in registers (no staging
+   * through shared memory, no CTA barriers), single-address loads are broadcast loads, lane 0 does the stores.  Only the top
+   * 33 heap entries live in shared memory.  Same pops, same relaxations, same parents, same heap layout as the phase form,
+   * which stays as the emulated build's version (tests/emu) and as the specification; the GPU tests compare this one with the
+   * oracle.  (ncu on the phase form: 1165 warp instructions per expansion, a third in the sift-down, a fifth in lane 0's
+   * serial pushes — profiles/r2_astar_ncu_metrics.csv.) */
+  __device__ __forceinline__ void search_warp(uint32_t slot, uint32_t* smem) const {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = (int)threadIdx.x;
+    unsigned long long* top = ((AStarShared*)smem)->top;
+    const uint64_t gt = a.g.gt;
+    uint32_t* g = gbuf + (uint64_t)slot * gt;
+    uint16_t* m = meta + (uint64_t)slot * gt;
+    uint64_t* h = heap + (uint64_t)slot * (uint64_t)heap_cap;
+    while (true) {
+      uint32_t req = 0xFFFFFFFFu, gen = 0, wipe = 0;
+      if (lane == 0) {
+        const uint32_t q = atomic_add(next_todo, 1u);
+        if (q < n_todo) {
+          req = todo ? todo[q] : q;
+          gen = slot_gen[slot] + 1;
+          if (gen > 255) { gen = 1; wipe = 1; }
+          slot_gen[slot] = gen;
+        }
+      }
+      req = __shfl_sync(FULL, req, 0); gen = __shfl_sync(FULL, gen, 0); wipe = __shfl_sync(FULL, wipe, 0);
+      if (req == 0xFFFFFFFFu) break;
+      if (wipe) { for (uint64_t k = (uint64_t)lane; k < gt; k += 32) m[k] = 0; } /* the 8-bit stamp wrapped: forget this slot's cells */
+      __syncwarp();
+      const uint32_t s = src[req], tc = dst[req];
+      int sx, sy, tx, ty;
+      dec(a.g, s, sx, sy);
+      dec(a.g, tc, tx, ty);
+      const int et = a.penalty ? (int)a.elev[tc] : 0;
+      if (lane == 0) {
+        g[s] = 0;
+        m[s] = (uint16_t)(gen << 8 | AS_NOPARENT);
+        top[0] = astar_key(astar_cost(a, sx, sy, s, tx, ty, tc), sx, sy);
+      }
+      uint32_t hn = 1, status = AS_UNREACHABLE;
+      unsigned long long nexp = 0;
+      if (comp && s != tc) { /* a goal the search could never pop: leave with an empty open list */
+        const uint32_t ls = comp[s], lt = comp[tc];
+        if (lt == AS_NOCOMP || (ls != AS_NOCOMP && ls != lt)) hn = 0;
+      }
+      __syncwarp();
+      while (hn > 0) {
+        /* pop: everything about the popped cell and its 8 neighbours (lanes 0..7) in one memory round trip */
+        const unsigned long long root = top[0];
+        const int x = (int)((root >> 16) & 0xFFFF) - 1, y = (int)(root & 0xFFFF) - 1;
+        const uint32_t c = enc(a.g, x, y);
+        bool inside = false;
+        uint32_t nc = c;
+        int ox = x, oy = y;
+        if (lane < 8) {
+          int ddx, ddy;
+          off8(lane, ddx, ddy);
+          inside = shift(a.g, x, y, ddx, ddy, ox, oy);
+          if (inside) nc = enc(a.g, ox, oy);
+        }
+        uint32_t wb = 0, gn = 0;
+        uint16_t mn = 0;
+        int en = 0;
+        if (lane < 8) { wb = a.walkbits[nc >> 5]; mn = m[nc]; gn = g[nc]; en = a.penalty ? (int)a.elev[nc] : 0; }
+        const uint16_t mc = m[c];
+        const uint32_t gc = g[c];
+        const int ec = a.penalty ? (int)a.elev[c] : 0;
+        const uint32_t hn2 = hn - 1;
+        const unsigned long long last = hn2 < AS_TOP ? top[hn2] : h[hn2];
+        if (c == tc) { status = AS_FOUND; break; }
+        unsigned long long key = 0;
+        if (!(mc & AS_CLOSED)) { /* else: a stale duplicate of an expanded node */
+          if (lane == 0) m[c] = (uint16_t)(mc | AS_CLOSED);
+          nexp += 1;
+          if (lane < 8 && inside && ((wb >> (nc & 31)) & 1u)) {
+            const bool seen = (uint32_t)(mn >> 8) == gen;
+            if (!(seen && (mn & AS_CLOSED))) {
+              const int64_t ng = (int64_t)gc + astar_cost_e(a, x, y, ec, ox, oy, en);
+              if (!seen || ng < (int64_t)gn) {
+                g[nc] = (uint32_t)ng;
+                m[nc] = (uint16_t)(gen << 8 | (uint32_t)lane);
+                key = astar_key(ng + astar_cost_e(a, ox, oy, en, tx, ty, et), ox, oy);
+              }
+            }
+          }
+        }
+        /* sift-down of the waiting key: per level one coalesced load of the 32 children and a warp-reduced minimum */
+        if (hn2 > 0) {
+          uint32_t cur = 0;
+          while (true) {
+            const uint32_t ci = cur * AS_ARITY + 1 + (uint32_t)lane;
+            const unsigned long long ck = ci < hn2 ? (ci < AS_TOP ? top[ci] : h[ci]) : AS_NOKEY;
+            const uint32_t hi = (uint32_t)(ck >> 32);
+            const uint32_t mhi = __reduce_min_sync(FULL, hi);
+            const uint32_t mlo = __reduce_min_sync(FULL, hi == mhi ? (uint32_t)ck : 0xFFFFFFFFu);
+            const unsigned long long b = ((unsigned long long)mhi << 32) | mlo;
+            if (b == AS_NOKEY || last <= b) { /* a leaf, or the key's place */
+              if (lane == 0) { if (cur < AS_TOP) top[cur] = last; else h[cur] = last; }
+              break;
+            }
+            if (lane == 0) { if (cur < AS_TOP) top[cur] = b; else h[cur] = b; }
+            cur = cur * AS_ARITY + 1 + (uint32_t)(__ffs((int)__ballot_sync(FULL, ck == b)) - 1); /* keys are unique: exactly one lane */
+          }
+        }
+        __syncwarp();
+        /* the new keys, in direction order (the order decides nothing but the heap's internal layout, kept equal to the phase form) */
+        hn = hn2;
+        bool full = false;
+        for (int d = 0; d < 8; ++d) {
+          const unsigned long long kd = __shfl_sync(FULL, key, d);
+          if (kd == 0) continue;
+          if (hn >= heap_cap) { full = true; break; }
+          uint32_t i = hn++;
+          while (i > 0) {
+            const uint32_t p = (i - 1) >> AS_ARITY_LOG2;
+            const unsigned long long pk = p < AS_TOP ? top[p] : h[p];
+            if (pk <= kd) break;
+            if (lane == 0) { if (i < AS_TOP) top[i] = pk; else h[i] = pk; }
+            i = p;
+          }
+          if (lane == 0) { if (i < AS_TOP) top[i] = kd; else h[i] = kd; }
+          __syncwarp();
+        }
+        if (full) { status = AS_HEAP_FULL; break; }
+      }
+      if (lane == 0) { /* walk the parents back to the start, claim pool space, write the path (first element = next cell to move to) */
+        uint32_t len = 0;
+        int64_t cost = -1;
+        unsigned long long off = 0;
+        if (status == AS_FOUND) {
+          uint32_t c = tc;
+          int x = tx, y = ty;
+          while (c != s) {
+            int ddx, ddy;
+            off8(m[c] & 0x0F, ddx, ddy);
+            x = g_wrap(x - ddx, a.g.nx, a.g.periodic);
+            y = g_wrap(y - ddy, a.g.ny, a.g.periodic);
+            c = enc(a.g, x, y);
+            ++len;
+          }
+          cost = (int64_t)g[tc];
+          off = atomic_add64(pool_cursor, (unsigned long long)len);
+          if (off + len > pool_cap) status = AS_POOL_FULL;
+          else {
+            uint32_t k = len;
+            c = tc; x = tx; y = ty;
+            while (c != s) {
+              pool[off + --k] = c;
+              int ddx, ddy;
+              off8(m[c] & 0x0F, ddx, ddy);
+              x = g_wrap(x - ddx, a.g.nx, a.g.periodic);
+              y = g_wrap(y - ddy, a.g.ny, a.g.periodic);
+              c = enc(a.g, x, y);
+            }
+          }
+        }
+        out_status[req] = status; out_len[req] = len; out_cost[req] = cost; out_off[req] = off;
+        if (nexp) atomic_add64(expansions, nexp);
+      }
+      __syncwarp();
+    }
+  }
+#endif
+
   ABM_HD void operator()(uint32_t slot, uint32_t* smem) const {
+#ifndef ABM_EMU
+    search_warp(slot, smem);
+    return;
+#endif
     const int NT = AS_ARITY;
     AStarShared& sh = *(AStarShared*)smem;
     const uint64_t gt = a.g.gt;

@@ -274,7 +274,8 @@ struct abm_handle {
   DevBuf rank, by_rank, seg_behav, plan_agent, plan_goal, remote_head, remote_next, remote_dest, idx_of_id;
   DevBuf as_g, as_meta, as_heap, as_src, as_dst, as_id, as_status, as_len, as_cost, as_off, as_slot_gen, as_todo, as_comp;
   bool comp_valid = false;        /* as_comp holds the walkmap's component labels */
-  uint64_t astar_budget = 128ull << 30; /* ABM_ASTAR_GB: device bytes the search slots may take (and at most three quarters of what is free) */
+  uint64_t astar_budget = 128ull << 30; /* ABM_ASTAR_GB: device bytes the search slots may take (and at most three quarters of what is free:
+                                         * 7/8 left too little for the buffers allocated afterwards) */
   DevBuf rt_slot_of_id, rt_off, rt_len, rt_pos, rt_cost, rt_pool;
   uint64_t as_slots = 0, as_heap_cap = 0, rt_slots_cap = 0, rt_pool_used = 0, rt_ids_cap = 0;
   /* tile path (abm_tile.h): sub-tile runs of the SoA (ping-pong with the SoA), offspring fix-up lists */
