@@ -63,6 +63,19 @@ ABM_HD int64_t astar_cost_e(const AStarGrid& a, int ax, int ay, int ea, int bx, 
   return c;
 }
 
+/* the same in 32-bit arithmetic for the search kernel (g is a u32 per cell; one step costs below 2^20 + 2^16) */
+ABM_HD uint32_t astar_cost32(const AStarGrid& a, int ax, int ay, int ea, int bx, int by, int eb) {
+  int dx = ax > bx ? ax - bx : bx - ax, dy = ay > by ? ay - by : by - ay;
+  if (a.g.periodic) {
+    if (a.g.nx - dx < dx) dx = a.g.nx - dx;
+    if (a.g.ny - dy < dy) dy = a.g.ny - dy;
+  }
+  const int mx = dx > dy ? dx : dy, mn = dx > dy ? dy : dx;
+  int c = a.metric == ABM_ASTAR_MAX ? mx : 10 * (mx - mn) + 14 * mn;
+  if (a.penalty) c += ea > eb ? ea - eb : eb - ea;
+  return (uint32_t)c;
+}
+
 ABM_HD uint64_t astar_key(int64_t f, int x, int y) { return ((uint64_t)f << 32) | ((uint64_t)(x + 1) << 16) | (uint64_t)(y + 1); }
 
 /* Connected components of the walkmap (Moore neighbourhood, the space's wrap): union-find with CAS hooking, then full
@@ -112,6 +125,7 @@ enum { AS_ARITY_LOG2 = 5, AS_ARITY = 32 };
 static const unsigned long long AS_NOKEY = ~0ull;
 
 enum { AS_TOP = 1 + AS_ARITY }; /* the root and its children live in shared memory for the length of a search */
+enum { AS_L3 = AS_TOP + AS_ARITY * AS_ARITY }; /* first heap index whose parent lies outside shared memory */
 
 /* sift-up of a 32-ary heap: one lane, ~1 parent visited in the common case (a new f is rarely below its parent's) */
 ABM_HD bool heap_push(uint64_t* h, unsigned long long* top, uint32_t& n, uint32_t cap, uint64_t key) {
@@ -159,12 +173,28 @@ struct AStarWarpCta {
   static size_t smem_bytes() { return sizeof(AStarShared); }
 
 #ifndef ABM_EMU
+  /* minimum of a 64-bit key over the warp, in every lane (two 32-bit reductions) */
+  static __device__ __forceinline__ unsigned long long warp_min64(unsigned long long v) {
+    const uint32_t hi = (uint32_t)(v >> 32);
+    const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+    const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? (uint32_t)v : 0xFFFFFFFFu);
+    return ((unsigned long long)mhi << 32) | mlo;
+  }
+  /* loads ptxas may not sink into the branches that use them (it does with plain ones): a pop issues all of its loads up
+   * front and pays one memory round trip instead of three dependent ones */
+  static __device__ __forceinline__ uint32_t ld_now(const uint32_t* p) { uint32_t v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+  static __device__ __forceinline__ uint32_t ld_now(const uint16_t* p) { uint16_t v; asm volatile("ld.volatile.global.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory"); return v; }
+  static __device__ __forceinline__ int ld_now(const int16_t* p) { int16_t v; asm volatile("ld.volatile.global.s16 %0, [%1];" : "=h"(v) : "l"(p) : "memory"); return (int)v; }
+  static __device__ __forceinline__ unsigned long long ld_now(const uint64_t* p) { unsigned long long v; asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
   /* The device form of the search below: warp-synchronous, every lane carries the search's scalars in registers (no staging
    * through shared memory, no CTA barriers), single-address loads are broadcast loads, lane 0 does the stores.  Only the top
-   * 33 heap entries live in shared memory.  Same pops, same relaxations, same parents, same heap layout as the phase form,
-   * which stays as the emulated build's version (tests/emu) and as the specification; the GPU tests compare this one with the
-   * oracle.  (ncu on the phase form: 1165 warp instructions per expansion, a third in the sift-down, a fifth in lane 0's
-   * serial pushes — profiles/r2_astar_ncu_metrics.csv.) */
+   * 33 heap entries live in shared memory.  Same pops, same relaxations, same parents as the phase form, which stays as the
+   * emulated build's version (tests/emu) and as the specification; the GPU tests compare this one with the oracle.
+   * Per pop (instruction counts from the SASS, `cuobjdump -sass`): ~110 up to the one batch of loads (lanes 0..7 the
+   * neighbours, lanes 8.. the popped cell, plus the heap's last entry), ~85 for the relaxations, a sift-down unrolled by where
+   * the level lives (shared memory / boundary / heap array: 23 / 43 / 51 per level) that starts from the smallest NEW key when
+   * there is one (pop + push in one pass), and a sift-up (~70) only for the second and later new keys, found with a ballot:
+   * ~300 warp instructions per pop against ~700 of round 2's first warp form (1.45x the replans/s; profiles/README.md). */
   __device__ __forceinline__ void search_warp(uint32_t slot, uint32_t* smem) const {
     const unsigned FULL = 0xffffffffu;
     const int lane = (int)threadIdx.x;
@@ -173,6 +203,8 @@ struct AStarWarpCta {
     uint32_t* g = gbuf + (uint64_t)slot * gt;
     uint16_t* m = meta + (uint64_t)slot * gt;
     uint64_t* h = heap + (uint64_t)slot * (uint64_t)heap_cap;
+    int ddx, ddy;
+    off8(lane & 7, ddx, ddy); /* lanes 0..7: the lane's neighbour direction */
     while (true) {
       uint32_t req = 0xFFFFFFFFu, gen = 0, wipe = 0;
       if (lane == 0) {
@@ -206,78 +238,111 @@ struct AStarWarpCta {
       }
       __syncwarp();
       while (hn > 0) {
-        /* pop: everything about the popped cell and its 8 neighbours (lanes 0..7) in one memory round trip */
+        /* pop: lanes 0..7 load everything about the popped cell's 8 neighbours, the other lanes the same four words of the
+         * popped cell itself (one address, one transaction; lane 8 hands them round) — ONE memory round trip, together with
+         * the heap's last entry */
         const unsigned long long root = top[0];
         const int x = (int)((root >> 16) & 0xFFFF) - 1, y = (int)(root & 0xFFFF) - 1;
-        const uint32_t c = enc(a.g, x, y);
-        bool inside = false;
-        uint32_t nc = c;
         int ox = x, oy = y;
+        bool inside = false;
         if (lane < 8) {
-          int ddx, ddy;
-          off8(lane, ddx, ddy);
           inside = shift(a.g, x, y, ddx, ddy, ox, oy);
-          if (inside) nc = enc(a.g, ox, oy);
+          if (!inside) { ox = x; oy = y; }
         }
-        uint32_t wb = 0, gn = 0;
-        uint16_t mn = 0;
-        int en = 0;
-        if (lane < 8) { wb = a.walkbits[nc >> 5]; mn = m[nc]; gn = g[nc]; en = a.penalty ? (int)a.elev[nc] : 0; }
-        const uint16_t mc = m[c];
-        const uint32_t gc = g[c];
-        const int ec = a.penalty ? (int)a.elev[c] : 0;
+        const uint32_t nc = enc(a.g, ox, oy);
+        const uint32_t wb = ld_now(a.walkbits + (nc >> 5));
+        const uint32_t mn = ld_now(m + nc);
+        const uint32_t gn = ld_now(g + nc);
+        const int en = a.penalty ? ld_now(a.elev + nc) : 0;
         const uint32_t hn2 = hn - 1;
-        const unsigned long long last = hn2 < AS_TOP ? top[hn2] : h[hn2];
+        const unsigned long long last = hn2 < AS_TOP ? top[hn2] : ld_now(h + hn2);
+        const uint32_t c = __shfl_sync(FULL, nc, 8);
         if (c == tc) { status = AS_FOUND; break; }
+        const uint32_t mc = __shfl_sync(FULL, mn, 8);
+        const uint32_t gc = __shfl_sync(FULL, gn, 8);
+        const int ec = __shfl_sync(FULL, en, 8);
         unsigned long long key = 0;
         if (!(mc & AS_CLOSED)) { /* else: a stale duplicate of an expanded node */
           if (lane == 0) m[c] = (uint16_t)(mc | AS_CLOSED);
           nexp += 1;
-          if (lane < 8 && inside && ((wb >> (nc & 31)) & 1u)) {
-            const bool seen = (uint32_t)(mn >> 8) == gen;
+          if (inside && ((wb >> (nc & 31)) & 1u)) {
+            const bool seen = (mn >> 8) == gen;
             if (!(seen && (mn & AS_CLOSED))) {
-              const int64_t ng = (int64_t)gc + astar_cost_e(a, x, y, ec, ox, oy, en);
-              if (!seen || ng < (int64_t)gn) {
-                g[nc] = (uint32_t)ng;
+              const uint32_t ng = gc + astar_cost32(a, x, y, ec, ox, oy, en);
+              if (!seen || ng < gn) {
+                g[nc] = ng;
                 m[nc] = (uint16_t)(gen << 8 | (uint32_t)lane);
-                key = astar_key(ng + astar_cost_e(a, ox, oy, en, tx, ty, et), ox, oy);
+                key = ((unsigned long long)(ng + astar_cost32(a, ox, oy, en, tx, ty, et)) << 32) | ((uint32_t)(ox + 1) << 16) | (uint32_t)(oy + 1);
               }
             }
           }
         }
-        /* sift-down of the waiting key: per level one coalesced load of the 32 children and a warp-reduced minimum */
-        if (hn2 > 0) {
-          uint32_t cur = 0;
-          while (true) {
-            const uint32_t ci = cur * AS_ARITY + 1 + (uint32_t)lane;
-            const unsigned long long ck = ci < hn2 ? (ci < AS_TOP ? top[ci] : h[ci]) : AS_NOKEY;
-            const uint32_t hi = (uint32_t)(ck >> 32);
-            const uint32_t mhi = __reduce_min_sync(FULL, hi);
-            const uint32_t mlo = __reduce_min_sync(FULL, hi == mhi ? (uint32_t)ck : 0xFFFFFFFFu);
-            const unsigned long long b = ((unsigned long long)mhi << 32) | mlo;
-            if (b == AS_NOKEY || last <= b) { /* a leaf, or the key's place */
-              if (lane == 0) { if (cur < AS_TOP) top[cur] = last; else h[cur] = last; }
-              break;
+        /* What replaces the popped root: the smallest of the new keys when there is one (pop + push in one sift-down that
+         * often ends near the top, since a new key is rarely far above the minimum — and one sift-up fewer), else the heap's last
+         * entry.  The heap's internal layout differs from the phase form's; the pop sequence cannot (distinct keys). */
+        uint32_t kmask = __ballot_sync(FULL, key != 0);
+        unsigned long long place = last;
+        uint32_t n = hn2;
+        if (kmask) {
+          place = warp_min64(key ? key : AS_NOKEY);
+          kmask &= ~__ballot_sync(FULL, key == place);
+          n = hn;
+        }
+        /* sift-down, one coalesced load of the 32 children and a warp-reduced minimum per level: level 0 reads its children from
+         * shared memory, level 1 writes there, the deeper ones live in the slot's heap array */
+        if (n > 0) {
+          unsigned long long ck = (uint32_t)(1 + lane) < n ? top[1 + lane] : AS_NOKEY;
+          unsigned long long b = warp_min64(ck);
+          if (b == AS_NOKEY || place <= b) { if (lane == 0) top[0] = place; }
+          else {
+            if (lane == 0) top[0] = b;
+            uint32_t cur = (uint32_t)__ffs((int)__ballot_sync(FULL, ck == b)); /* keys are unique: exactly one lane; 1 + its index */
+            uint32_t ci = cur * AS_ARITY + 1 + (uint32_t)lane;
+            ck = ci < n ? h[ci] : AS_NOKEY;
+            b = warp_min64(ck);
+            if (b == AS_NOKEY || place <= b) { if (lane == 0) top[cur] = place; }
+            else {
+              if (lane == 0) top[cur] = b;
+              cur = cur * AS_ARITY + (uint32_t)__ffs((int)__ballot_sync(FULL, ck == b));
+              while (true) {
+                ci = cur * AS_ARITY + 1 + (uint32_t)lane;
+                ck = ci < n ? h[ci] : AS_NOKEY;
+                b = warp_min64(ck);
+                if (b == AS_NOKEY || place <= b) { if (lane == 0) h[cur] = place; break; }
+                if (lane == 0) h[cur] = b;
+                cur = cur * AS_ARITY + (uint32_t)__ffs((int)__ballot_sync(FULL, ck == b));
+              }
             }
-            if (lane == 0) { if (cur < AS_TOP) top[cur] = b; else h[cur] = b; }
-            cur = cur * AS_ARITY + 1 + (uint32_t)(__ffs((int)__ballot_sync(FULL, ck == b)) - 1); /* keys are unique: exactly one lane */
           }
         }
         __syncwarp();
-        /* the new keys, in direction order (the order decides nothing but the heap's internal layout, kept equal to the phase form) */
-        hn = hn2;
+        /* the other new keys, in direction order: sift-up through the heap array (parents at index >= AS_TOP), then the entry
+         * below shared memory, then shared memory */
+        hn = n;
         bool full = false;
-        for (int d = 0; d < 8; ++d) {
+        while (kmask) {
+          const int d = __ffs((int)kmask) - 1;
+          kmask &= kmask - 1;
           const unsigned long long kd = __shfl_sync(FULL, key, d);
-          if (kd == 0) continue;
           if (hn >= heap_cap) { full = true; break; }
           uint32_t i = hn++;
-          while (i > 0) {
+          bool up = true;
+          while (i >= AS_L3) {
             const uint32_t p = (i - 1) >> AS_ARITY_LOG2;
-            const unsigned long long pk = p < AS_TOP ? top[p] : h[p];
-            if (pk <= kd) break;
-            if (lane == 0) { if (i < AS_TOP) top[i] = pk; else h[i] = pk; }
+            const unsigned long long pk = h[p];
+            if (pk <= kd) { up = false; break; }
+            if (lane == 0) h[i] = pk;
             i = p;
+          }
+          if (up && i >= AS_TOP) {
+            const uint32_t p = (i - 1) >> AS_ARITY_LOG2;
+            const unsigned long long pk = top[p];
+            if (pk <= kd) up = false;
+            else { if (lane == 0) h[i] = pk; i = p; }
+          }
+          if (up && i >= 1 && i < AS_TOP) {
+            const unsigned long long pk = top[0];
+            if (pk > kd) { if (lane == 0) top[i] = pk; i = 0; }
           }
           if (lane == 0) { if (i < AS_TOP) top[i] = kd; else h[i] = kd; }
           __syncwarp();
@@ -422,17 +487,33 @@ struct AStarWarpCta {
                 shift(a.g, sh.x, sh.y, ddx, ddy, ox, oy);
                 const uint32_t nc = enc(a.g, ox, oy);
                 const int32_t en = sh.n_e[t];
-                const int64_t ng = (int64_t)sh.gc + astar_cost_e(a, sh.x, sh.y, sh.ec, ox, oy, en);
-                if (!seen || ng < (int64_t)sh.n_g[t]) {
-                  g[nc] = (uint32_t)ng;
+                const uint32_t ng = sh.gc + astar_cost32(a, sh.x, sh.y, sh.ec, ox, oy, en);
+                if (!seen || ng < sh.n_g[t]) {
+                  g[nc] = ng;
                   m[nc] = (uint16_t)(sh.gen << 8 | (uint32_t)t);
-                  key = astar_key(ng + astar_cost_e(a, ox, oy, en, sh.tx, sh.ty, sh.et), ox, oy);
+                  key = ((unsigned long long)(ng + astar_cost32(a, ox, oy, en, sh.tx, sh.ty, sh.et)) << 32) | ((uint32_t)(ox + 1) << 16) | (uint32_t)(oy + 1);
                 }
               }
             }
             sh.nk[t] = key;
           }
         }
+        ABM_CTA_SYNC();
+        /* what replaces the popped root: the smallest new key when there is one (the open list then keeps its size and the
+         * waiting last entry stays where it is), as in the device form */
+        ABM_CTA_FOR(t, NT) {
+          if (t == 0) {
+            int dmin = -1;
+            for (int d = 0; d < 8; ++d)
+              if (sh.nk[d] && (dmin < 0 || sh.nk[d] < sh.nk[dmin])) dmin = d;
+            if (dmin >= 0) {
+              const unsigned long long k0 = sh.nk[dmin];
+              for (int d = 0; d < 8; ++d) if (sh.nk[d] == k0) sh.nk[d] = 0;
+              sh.last = k0; sh.hn2 = sh.hn; sh.sift = 1;
+            }
+          }
+        }
+        ABM_CTA_SYNC();
         /* sift-down of the waiting key: per level one coalesced load of the 32 children and a warp-reduced minimum */
         while (sh.sift) {
           const uint32_t lv = sh.lvl & 1u;
