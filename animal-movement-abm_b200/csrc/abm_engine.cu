@@ -277,7 +277,7 @@ struct abm_handle {
   uint64_t astar_budget = 128ull << 30; /* ABM_ASTAR_GB: device bytes the search slots may take (and at most three quarters of what is free:
                                          * 7/8 left too little for the buffers allocated afterwards) */
   DevBuf rt_slot_of_id, rt_off, rt_len, rt_pos, rt_cost, rt_pool;
-  uint64_t as_slots = 0, as_heap_cap = 0, rt_slots_cap = 0, rt_pool_used = 0, rt_ids_cap = 0;
+  uint64_t as_slots = 0, as_heap_cap = 0, as_heap_want = 0, rt_slots_cap = 0, rt_pool_used = 0, rt_ids_cap = 0;
   /* tile path (abm_tile.h): sub-tile runs of the SoA (ping-pong with the SoA), offspring fix-up lists */
   bool tile_mode = false;
   uint64_t birth_bitmap_from = 32768; /* ABM_BIRTH_BITMAP: gathered offspring capacity above which ids are ranked through a bitmap */

@@ -38,24 +38,50 @@ static int plan_batch(abm_handle* h, uint64_t B, const uint32_t* d_id, const uin
   if (h->g.nx > 65534 || h->g.ny > 65534) ABM_FAIL(h, ABM_E_BADARG, "A* needs grid dims below 65535");
   if (B > 0xFFFFFFF0ull) ABM_FAIL(h, ABM_E_BADARG, "too many route requests in one batch");
   const uint64_t gt = h->g.gt;
-  const uint64_t heap_cap = std::min<uint64_t>(8ull * (uint64_t)h->g.nx * h->g.ny + 16, 1ull << 20);
-  const uint64_t per_slot = gt * 6 + heap_cap * 8;
+  /* Open-list capacity per slot: a search that pushes every neighbour of every cell holds at most 8 * cells entries, and never
+   * more than 2^20 are allowed; searches on real terrain hold a few thousand, so slots start with 2^18 entries (2 MB instead of
+   * 8: at 2048 x 2048 that is 27 instead of 33 MB per slot, a quarter more searches in flight) and the rare search that
+   * overflows is run again after the heaps grew fourfold.  ABM_ASTAR_HEAP0 (tests) sets the first capacity. */
+  const uint64_t heap_max = std::min<uint64_t>(8ull * (uint64_t)h->g.nx * h->g.ny + 16, 1ull << 20);
+  if (h->as_heap_want == 0 || h->as_heap_want > heap_max) {
+    h->as_heap_want = std::min<uint64_t>(heap_max, 1ull << 18);
+    if (const char* hs = getenv("ABM_ASTAR_HEAP0")) h->as_heap_want = std::min<uint64_t>(heap_max, (uint64_t)std::max(atoll(hs), 2ll));
+  }
   uint64_t max_resident = 148ull * 32; /* one warp-sized CTA per slot, at most 32 CTAs per SM */
   if (const char* ms = getenv("ABM_ASTAR_SLOTS")) max_resident = (uint64_t)std::max(atoll(ms), 1ll);
-  if (h->as_slots == 0 || h->as_heap_cap != heap_cap || h->as_slots < std::min<uint64_t>(B, max_resident)) {
-    const uint64_t budget = std::min<uint64_t>(device_free_bytes() / 4 * 3, h->astar_budget); /* searches are latency-bound: slots in flight are throughput */
-    uint64_t slots = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(B, max_resident), budget / per_slot));
+  /* (re)allocates the slots for the wanted heap capacity; a larger heap may mean fewer slots */
+  auto size_slots = [&]() -> int {
+    const uint64_t heap_cap = h->as_heap_want;
+    if (h->as_slots != 0 && h->as_heap_cap == heap_cap && h->as_slots >= std::min<uint64_t>(B, max_resident)) return 0;
+    const uint64_t per_slot = gt * 6 + heap_cap * 8;
+    /* searches are latency-bound: slots in flight are throughput.  The arrays already held count as free. */
+    const uint64_t held = h->as_g.bytes + h->as_meta.bytes + h->as_heap.bytes;
+    const uint64_t budget = std::min<uint64_t>((device_free_bytes() + held) / 4 * 3, h->astar_budget);
+    const uint64_t slots = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(B, max_resident), budget / per_slot));
     if (slots > h->as_slots || h->as_heap_cap != heap_cap) {
-      if ((rc = ensure(h, h->as_g, slots * gt * 4))) return rc;
-      if ((rc = ensure(h, h->as_meta, slots * gt * 2))) return rc;
-      if ((rc = ensure(h, h->as_heap, slots * heap_cap * 8))) return rc;
-      if ((rc = ensure(h, h->as_slot_gen, slots * 4))) return rc;
+      /* exact sizes (ensure() adds a quarter of head room, which is tens of GB here), the old array released first */
+      auto exact = [&](DevBuf& b, uint64_t bytes) -> int {
+        bytes = (bytes + 255) & ~(uint64_t)255;
+        if (b.p && b.bytes >= bytes) return 0;
+        dev_free(b.p);
+        b.p = nullptr; b.bytes = 0;
+        if (dev_malloc(&b.p, bytes) != 0) { b.p = nullptr; ABM_FAIL(h, ABM_E_NOMEM, "device allocation of %llu bytes failed", (unsigned long long)bytes); }
+        b.bytes = bytes;
+        return 0;
+      };
+      int rc2;
+      if ((rc2 = exact(h->as_g, slots * gt * 4))) return rc2;
+      if ((rc2 = exact(h->as_meta, slots * gt * 2))) return rc2;
+      if ((rc2 = exact(h->as_heap, slots * heap_cap * 8))) return rc2;
+      if ((rc2 = ensure(h, h->as_slot_gen, slots * 4))) return rc2;
       ABM_CK(h, dev_memset(h->as_meta.p, 0, slots * gt * 2, h->stream));
       ABM_CK(h, dev_memset(h->as_slot_gen.p, 0, slots * 4, h->stream));
       h->as_slots = slots; h->as_heap_cap = heap_cap;
     }
-  }
-  const uint64_t S = std::min<uint64_t>(std::min<uint64_t>(h->as_slots, B), max_resident);
+    return 0;
+  };
+  if ((rc = size_slots())) return rc;
+  uint64_t S = std::min<uint64_t>(std::min<uint64_t>(h->as_slots, B), max_resident);
   if ((rc = ensure_components(h))) return rc;
   if ((rc = ensure(h, h->as_status, B * 4))) return rc;
   if ((rc = ensure(h, h->as_len, B * 4))) return rc;
@@ -98,7 +124,7 @@ static int plan_batch(abm_handle* h, uint64_t B, const uint32_t* d_id, const uin
     sb.a = astar_grid(h); sb.src = d_src; sb.dst = d_dst; sb.comp = (const uint32_t*)h->as_comp.p;
     sb.todo = todo.empty() ? nullptr : (const uint32_t*)h->as_todo.p; sb.n_todo = (uint32_t)n_todo; sb.next_todo = ctr + CTR_NEXT_REQ;
     sb.gbuf = (uint32_t*)h->as_g.p; sb.meta = (uint16_t*)h->as_meta.p; sb.heap = (uint64_t*)h->as_heap.p;
-    sb.heap_cap = (uint32_t)heap_cap; sb.slot_gen = (uint32_t*)h->as_slot_gen.p;
+    sb.heap_cap = (uint32_t)h->as_heap_cap; sb.slot_gen = (uint32_t*)h->as_slot_gen.p;
     sb.out_status = (uint32_t*)h->as_status.p; sb.out_len = (uint32_t*)h->as_len.p; sb.out_cost = (int64_t*)h->as_cost.p;
     sb.out_off = (uint64_t*)h->as_off.p;
     sb.pool = (uint32_t*)h->rt_pool.p; sb.pool_cursor = d_cursor; sb.pool_cap = pool_cap;
@@ -110,15 +136,26 @@ static int plan_batch(abm_handle* h, uint64_t B, const uint32_t* d_id, const uin
     ABM_CK(h, copy_d2h(&cursor, d_cursor, 8, h->stream));
     if ((rc = read_counters(h))) return rc; /* synchronises the stream */
     std::vector<uint32_t> again;
-    if (todo.empty()) { for (uint64_t i = 0; i < B; ++i) if (st[i] == AS_POOL_FULL) again.push_back((uint32_t)i); }
-    else for (uint32_t i : todo) if (st[i] == AS_POOL_FULL) again.push_back(i);
-    for (uint64_t i = 0; i < B; ++i)
-      if (st[i] == AS_HEAP_FULL) ABM_FAIL(h, ABM_E_CAPACITY, "A* open list exceeded %llu entries", (unsigned long long)heap_cap);
+    bool heap_full = false, pool_full = false;
+    auto look = [&](uint32_t i) {
+      if (st[i] == AS_POOL_FULL) { pool_full = true; again.push_back(i); }
+      else if (st[i] == AS_HEAP_FULL) { heap_full = true; again.push_back(i); }
+    };
+    if (todo.empty()) { for (uint64_t i = 0; i < B; ++i) look((uint32_t)i); }
+    else for (uint32_t i : todo) look(i);
     if (again.empty()) { h->rt_pool_used = cursor; break; }
-    /* the cursor ran past the end: everything that fitted stays (and stays counted), the rest runs again in a larger pool */
+    /* everything that fitted stays (and stays counted); the rest runs again with more room */
     h->rt_pool_used = std::min<uint64_t>(cursor, pool_cap);
-    if ((rc = grow_keep(h, h->rt_pool, (2 * pool_cap + (cursor - std::min<uint64_t>(cursor, pool_cap)) + 1) * 4))) return rc;
-    pool_cap = h->rt_pool.bytes / 4;
+    if (heap_full) {
+      if (h->as_heap_cap >= heap_max) ABM_FAIL(h, ABM_E_CAPACITY, "A* open list exceeded %llu entries", (unsigned long long)heap_max);
+      h->as_heap_want = std::min<uint64_t>(heap_max, h->as_heap_cap * 4);
+      if ((rc = size_slots())) return rc;
+      S = std::min<uint64_t>(std::min<uint64_t>(h->as_slots, B), max_resident);
+    }
+    if (pool_full) {
+      if ((rc = grow_keep(h, h->rt_pool, (2 * pool_cap + (cursor - std::min<uint64_t>(cursor, pool_cap)) + 1) * 4))) return rc;
+      pool_cap = h->rt_pool.bytes / 4;
+    }
     todo.swap(again);
     n_todo = todo.size();
   }

@@ -190,6 +190,32 @@ def test_emulated_astar_slot_reuse_and_pool_overflow(emu, oracle, monkeypatch):
     _same_paths(a, b, w["ids"])
 
 
+def test_emulated_astar_open_list_overflow_is_rerun(emu, oracle, monkeypatch):
+    """Open lists start small (2^18 entries per slot; here 4) and a search that overflows runs again after the heaps grew
+    fourfold (4 -> 16 -> 64 -> ...): same paths and costs as the oracle's unbounded open list."""
+    monkeypatch.setenv("ABM_ASTAR_HEAP0", "4")
+    monkeypatch.setenv("ABM_ASTAR_SLOTS", "5")
+    a, w = _plan_case(oracle, 1, 1, 1, nx=48, ny=40, n=120, seed=6)
+    b, _ = _plan_case(emu, 1, 1, 1, nx=48, ny=40, n=120, seed=6)
+    off = _same_paths(a, b, w["ids"])
+    assert off[-1] > 800
+    monkeypatch.delenv("ABM_ASTAR_HEAP0")  # the grown capacity stays with the handle
+    rng = np.random.default_rng(10)
+    ok = np.argwhere(w["walkmap"] == 1)
+    goals = ok[rng.integers(0, len(ok), 120)]
+    for e in (a, b):
+        e.plan_routes(w["ids"], goals[:, 1] + 1, goals[:, 0] + 1)
+    _same_paths(a, b, w["ids"])
+
+
+@pytest.mark.gpu
+def test_gpu_astar_open_list_overflow_is_rerun(libabm, oracle, monkeypatch):
+    monkeypatch.setenv("ABM_ASTAR_HEAP0", "16")
+    a, w = _plan_case(oracle, 1, 1, 1, nx=160, ny=120, n=500, seed=7)
+    b, _ = _plan_case(libabm, 1, 1, 1, nx=160, ny=120, n=500, seed=7)
+    _same_paths(a, b, w["ids"])
+
+
 def _island_case(lib, periodic):
     """A wall of water splits the map; agents on both sides, on the wall (not walkable) and goals everywhere."""
     nx, ny = 40, 32
