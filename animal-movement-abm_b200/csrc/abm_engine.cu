@@ -1084,6 +1084,9 @@ static int validate_config(const abm_config* c, std::string& why) {
     if (ax != floor(ax) || ay != floor(ay) || fabs(ax) > 1e9 || fabs(ay) > 1e9) BAD("2*attractor must be integral (griddims ./ 2)");
   }
   if (c->walk_type == ABM_ALTERNATED_WALK && c->counter < 1) BAD("counter must be >= 1");
+  /* on a periodic grid with a dimension below 3 two of the 8 neighbour offsets wrap onto the same cell: the batched A* relaxes
+   * the 8 neighbours side by side and does not reproduce the reference's one-after-the-other result there */
+  if (c->walk_type == ABM_ALTERNATED_WALK && c->periodic && (c->nx < 3 || c->ny < 3)) BAD("ALTERNATED_WALK (A* routes) on a periodic grid needs dims >= 3");
   if (!(c->prob_random_walk >= 0 && c->prob_random_walk <= 1)) BAD("prob_random_walk must be in [0,1]");
   if (c->astar_metric != ABM_ASTAR_DIRECT && c->astar_metric != ABM_ASTAR_MAX) BAD("astar_metric out of range");
   if (c->scheduler != ABM_SCHED_BY_ID && c->scheduler != ABM_SCHED_RANDOMLY) BAD("scheduler out of range");

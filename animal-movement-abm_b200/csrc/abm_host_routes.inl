@@ -36,6 +36,7 @@ static int plan_batch(abm_handle* h, uint64_t B, const uint32_t* d_id, const uin
   int rc;
   if (B == 0) return 0;
   if (h->g.nx > 65534 || h->g.ny > 65534) ABM_FAIL(h, ABM_E_BADARG, "A* needs grid dims below 65535");
+  if (h->cfg.periodic && (h->cfg.nx < 3 || h->cfg.ny < 3)) ABM_FAIL(h, ABM_E_BADARG, "A* on a periodic grid needs dims >= 3 (two neighbour offsets wrap onto one cell)");
   if (B > 0xFFFFFFF0ull) ABM_FAIL(h, ABM_E_BADARG, "too many route requests in one batch");
   const uint64_t gt = h->g.gt;
   /* Open-list capacity per slot: a search that pushes every neighbour of every cell holds at most 8 * cells entries, and never

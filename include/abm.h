@@ -229,7 +229,8 @@ int abm_get_heat(abm_handle* h, int32_t which, float* out);
 /* replaces: plan_route!(agent, dest, model.pathfinder) for a batch of agents (src/agent_actions.jl:217-221;
  * Agents.Pathfinding.find_path).  goal coordinates 1-based.  Existing routes of these agents are overwritten;
  * an unreachable goal leaves the agent without a route.  A search whose open list outgrows its slot is run again with a
- * larger one; beyond 2^20 open entries the call fails with ABM_E_CAPACITY. */
+ * larger one; beyond 2^20 open entries the call fails with ABM_E_CAPACITY.  Periodic grids need nx, ny >= 3 for A* (below,
+ * two of the 8 neighbour offsets wrap onto one cell): ABM_E_BADARG here, and from abm_create for ALTERNATED_WALK. */
 int abm_plan_routes(abm_handle* h, int64_t b, const int64_t* agent_id, const int64_t* goal_x,
                     const int64_t* goal_y);
 

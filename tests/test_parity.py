@@ -216,6 +216,25 @@ def test_gpu_astar_open_list_overflow_is_rerun(libabm, oracle, monkeypatch):
     _same_paths(a, b, w["ids"])
 
 
+def test_emulated_astar_refuses_periodic_grids_thinner_than_three(emu):
+    """Two of the 8 neighbour offsets wrap onto the same cell there; the batched search relaxes its 8 neighbours side by side
+    and says so instead of guessing (the refusal is host code, the same in libabm.so)."""
+    with pytest.raises(Exception, match="dims >= 3"):
+        emu.create(emu.default_config(nx=7, ny=2, periodic=1, walk_type=3, counter=9))
+    e = emu.create(emu.default_config(nx=7, ny=2, periodic=1, walk_type=0))
+    e.set_grid(np.ones((2, 7), np.uint8), np.full((2, 7), 30, np.int64), np.ones((2, 7), np.uint8), np.ones((2, 7), np.int64))
+    e.set_agents(np.array([1]), np.array([1]), np.array([1]), np.array([5.0]))
+    with pytest.raises(Exception, match="dims >= 3"):
+        e.plan_routes(np.array([1]), np.array([5]), np.array([2]))
+    # not periodic: nothing wraps, thin grids are fine
+    e = emu.create(emu.default_config(nx=7, ny=2, periodic=0, walk_type=0))
+    e.set_grid(np.ones((2, 7), np.uint8), np.full((2, 7), 30, np.int64), np.ones((2, 7), np.uint8), np.ones((2, 7), np.int64))
+    e.set_agents(np.array([1]), np.array([1]), np.array([1]), np.array([5.0]))
+    e.plan_routes(np.array([1]), np.array([5]), np.array([2]))
+    off, px, py, cost = e.get_paths(np.array([1]))
+    assert off[-1] == 4 and px[-1] == 5 and py[-1] == 2
+
+
 def _island_case(lib, periodic):
     """A wall of water splits the map; agents on both sides, on the wall (not walkable) and goals everywhere."""
     nx, ny = 40, 32
