@@ -68,11 +68,19 @@ static inline void launch_foreach(abm_stream_t, const F& f, uint64_t n, const ch
  * device every thread runs each phase once (t = threadIdx.x) and phases are separated by __syncthreads(); here a
  * phase is a loop over the thread indices (visited forwards or backwards), and CTAs run one after another in a
  * shuffled order.  Code outside the phases must be uniform across the CTA. */
+#ifdef ABM_EMU_REVERSE /* tools/sanitize.sh: the threads of a phase visited backwards — a result that changes is a race on the device */
+#define ABM_CTA_FOR(t, NT) for (int t = (int)(NT) - 1; t >= 0; --t)
+#else
 #define ABM_CTA_FOR(t, NT) for (int t = 0; t < (int)(NT); ++t)
+#endif
 #define ABM_CTA_SYNC() ((void)0)
 /* a stretch of phases run by the first warp alone: `if (ABM_IN_WARP0) { ABM_WARP0_FOR(t) { ... } ABM_WARP_SYNC(); ... }` */
 #define ABM_IN_WARP0 true
+#ifdef ABM_EMU_REVERSE
+#define ABM_WARP0_FOR(t) for (int t = 31; t >= 0; --t)
+#else
 #define ABM_WARP0_FOR(t) for (int t = 0; t < 32; ++t)
+#endif
 #define ABM_WARP_SYNC() ((void)0)
 #define ABM_PHASE_BEGIN() ((void)0)
 #define ABM_PHASE(k) ((void)0)

@@ -19,3 +19,12 @@ python -m pytest tests/test_parity.py tests/test_strips.py tests/test_host_api.p
 python tools/fuzz.py engine 930000 $SEEDS
 python tools/fuzz.py astar 940000 $SEEDS
 FUZZ_SCHED=1 ABM_TILE_ROUNDS=1 FORCE_GENERAL=1 python tools/fuzz.py engine 950000 $SEEDS
+# second pass: the threads of every CTA phase visited backwards (-DABM_EMU_REVERSE): a result that depends on the order in which the
+# threads of a phase run would be a race between barriers on the device
+unset LD_PRELOAD
+g++ -O2 -g -std=c++17 -fPIC -Wno-unknown-pragmas -ffp-contract=off -DABM_EMU -DABM_EMU_REVERSE -x c++ -shared -o $EMU animal-movement-abm_b200/csrc/abm_engine.cu 2>/dev/null
+touch $EMU
+python -m pytest tests/test_parity.py tests/test_strips.py -x -q -m "not gpu" -p no:cacheprovider
+python tools/fuzz.py engine 960000 $SEEDS
+python tools/fuzz.py astar 970000 $SEEDS
+FUZZ_SCHED=1 ABM_TILE_ROUNDS=1 python tools/fuzz.py engine 980000 $SEEDS
