@@ -99,3 +99,27 @@ def test_c_example_runs_on_the_gpu(tmp_path):
     assert r.returncode == 0, r.stderr
     lines = r.stdout.strip().splitlines()
     assert len(lines) == 11 and lines[0].split()[:4] == ["tick", "0", "sheep", "100"] and lines[-1].startswith("tick 100")
+
+
+def test_binding_signatures_match_the_prototypes():
+    """capi.SIGNATURES against the prototypes of include/abm.h: argument count, pointers where the header has pointers, scalar
+    widths and float-ness elsewhere, and the return type (a mismatch here corrupts the stack silently at call time)."""
+    from test_julia_shim import C_SIZES, _c_prototypes
+    protos = _c_prototypes()
+    for name, (res, args) in capi.SIGNATURES.items():
+        cret, cargs = protos["abm_" + name]
+        assert len(args) == len(cargs), f"abm_{name}: binding has {len(args)} arguments, header {len(cargs)}"
+        if cret == "void":
+            assert res is None, name
+        elif "*" in cret:
+            assert res in (C.c_char_p, C.c_void_p), name
+        else:
+            assert C.sizeof(res) == C_SIZES[cret.split()[-1]], name
+        for k, (a, ca) in enumerate(zip(args, cargs)):
+            is_ptr = a in (C.c_void_p, C.c_char_p) or hasattr(a, "contents") or issubclass(a, C._Pointer)
+            if "*" in ca:
+                assert is_ptr, f"abm_{name} argument {k}: {ca}"
+            else:
+                cty = [t for t in ca.replace("const", "").split() if t in C_SIZES][0]
+                assert not is_ptr and C.sizeof(a) == C_SIZES[cty], f"abm_{name} argument {k}: {ca}"
+                assert (cty in ("double", "float")) == (a in (C.c_double, C.c_float)), f"abm_{name} argument {k}"
